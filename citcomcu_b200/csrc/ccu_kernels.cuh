@@ -1,0 +1,443 @@
+// ccu_kernels.cuh -- sm_100a kernels of the Stokes hot path (velocity block).
+// All are HBM-bound stencil / streaming kernels in the reference's mixed precision
+// (fp32 coefficients, fp64 vectors and accumulation); no tensor-core work here.
+#pragma once
+#include "ccu_layout.cuh"
+#include <cuda_runtime.h>
+
+#define CCU_VBX 0x2u
+#define CCU_VBZ 0x4u
+#define CCU_VBY 0x8u
+// device flag byte per storage slot
+#define CCU_F_VBX 1
+#define CCU_F_VBY 2
+#define CCU_F_VBZ 4
+#define CCU_F_VALID 128
+
+struct CcuLevelDev
+{
+    CcuGeom g;
+    const float *K;            // [14*9][NS]
+    const double *BI;          // [3][NS]
+    const unsigned char *flags;// [NS]
+    const float *MASS;         // [nno] natural order
+    const float *TWW;          // [nel*8]
+    const float *eco;          // [nel*3]
+    const float *elt_del;      // [nel*24]
+    const double *BPI;         // [npno]
+};
+
+// ------------------------------------------------------------------------------------------
+// One row-block of K*x for a node of colour C: the 14 blocks the node owns (self + 13 lower
+// neighbours) and the 13 transposed blocks owned by its upper neighbours.  Every load is a unit
+// -stride, fully coalesced 128-byte warp access: colour-blocked layout makes "neighbour of my
+// neighbour thread" = "my neighbour + 1".
+// Replaces the gather+scatter loops of n_assemble_del2_u (Element_calculations.c:592-605) and
+// the gather/scatter of gauss_seidel (General_matrix_functions.c:1241-1255) with a pure gather.
+// ------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void ccu_row_product(const CcuGeom &g, const float *__restrict__ K, const double *x,
+                                                const int cell, double &a0, double &a1, double &a2)
+{
+    constexpr int LO[13][3] = CCU_LO_INIT;
+    constexpr int pi = (C >> 2) & 1, pj = (C >> 1) & 1, pk = C & 1;
+    const size_t NS = (size_t)g.NS;
+    const int s = C * g.NC + cell;
+    double r0, r1, r2;
+    {   // self block
+        const double x0 = x[s], x1 = x[NS + s], x2 = x[2 * NS + s];
+        const float *Kp = K + s;
+        r0 = (double)__ldg(Kp) * x0 + (double)__ldg(Kp + NS) * x1 + (double)__ldg(Kp + 2 * NS) * x2;
+        r1 = (double)__ldg(Kp + 3 * NS) * x0 + (double)__ldg(Kp + 4 * NS) * x1 + (double)__ldg(Kp + 5 * NS) * x2;
+        r2 = (double)__ldg(Kp + 6 * NS) * x0 + (double)__ldg(Kp + 7 * NS) * x1 + (double)__ldg(Kp + 8 * NS) * x2;
+    }
+#pragma unroll
+    for(int b = 0; b < 13; b++)
+    {   // own blocks: lower neighbour m = n + LO[b], block stored at n in slot b+1
+        constexpr int dummy = 0; (void)dummy;
+        const int di = LO[b][0], dj = LO[b][1], dk = LO[b][2];
+        const int cm = C ^ (((di != 0) << 2) | ((dj != 0) << 1) | (dk != 0));
+        const int sm = cm * g.NC + cell + ccu_shift(pi, di) * g.JK + ccu_shift(pj, dj) * g.Kd + ccu_shift(pk, dk);
+        const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
+        const float *Kp = K + (size_t)((b + 1) * 9) * NS + s;
+        r0 += (double)__ldg(Kp) * x0 + (double)__ldg(Kp + NS) * x1 + (double)__ldg(Kp + 2 * NS) * x2;
+        r1 += (double)__ldg(Kp + 3 * NS) * x0 + (double)__ldg(Kp + 4 * NS) * x1 + (double)__ldg(Kp + 5 * NS) * x2;
+        r2 += (double)__ldg(Kp + 6 * NS) * x0 + (double)__ldg(Kp + 7 * NS) * x1 + (double)__ldg(Kp + 8 * NS) * x2;
+    }
+#pragma unroll
+    for(int b = 0; b < 13; b++)
+    {   // transposed blocks: upper neighbour m = n - LO[b] owns K_mn in its slot b+1
+        const int di = -LO[b][0], dj = -LO[b][1], dk = -LO[b][2];
+        const int cm = C ^ (((di != 0) << 2) | ((dj != 0) << 1) | (dk != 0));
+        const int sm = cm * g.NC + cell + ccu_shift(pi, di) * g.JK + ccu_shift(pj, dj) * g.Kd + ccu_shift(pk, dk);
+        const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
+        const float *Kp = K + (size_t)((b + 1) * 9) * NS + sm;
+        r0 += (double)__ldg(Kp) * x0 + (double)__ldg(Kp + 3 * NS) * x1 + (double)__ldg(Kp + 6 * NS) * x2;
+        r1 += (double)__ldg(Kp + NS) * x0 + (double)__ldg(Kp + 4 * NS) * x1 + (double)__ldg(Kp + 7 * NS) * x2;
+        r2 += (double)__ldg(Kp + 2 * NS) * x0 + (double)__ldg(Kp + 5 * NS) * x1 + (double)__ldg(Kp + 8 * NS) * x2;
+    }
+    a0 = r0; a1 = r1; a2 = r2;
+}
+
+// One colour pass of the 8-colour Gauss-Seidel smoother (replaces the lexicographic node loop of
+// gauss_seidel, General_matrix_functions.c:1231-1260).  Same per-node update as the reference:
+// all three equations of a node relaxed together with the scalar inverse diagonal BI and the
+// correction rounded to fp32 (`higher_precision *temp`, :1172,1250-1252).
+template <int C>
+__global__ void __launch_bounds__(128) ccu_k_relax(const CcuGeom g, const float *__restrict__ K,
+                                                    const double *__restrict__ BI, const double *__restrict__ F, double *x)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, C, cell, i, j, k)) return;
+    double a0, a1, a2;
+    ccu_row_product<C>(g, K, x, cell, a0, a1, a2);
+    const size_t NS = (size_t)g.NS;
+    const int s = C * g.NC + cell;
+    const float t0 = (float)((F[s] - a0) * BI[s]);
+    const float t1 = (float)((F[NS + s] - a1) * BI[NS + s]);
+    const float t2 = (float)((F[2 * NS + s] - a2) * BI[2 * NS + s]);
+    x[s] += (double)t0;
+    x[NS + s] += (double)t1;
+    x[2 * NS + s] += (double)t2;
+}
+
+// Au = K*u for all nodes (n_assemble_del2_u, Element_calculations.c:552).  One warp per colour,
+// the eight warps of a block cover the same 32 cells, so the transposed reads of a block hit
+// lines its sibling warps stream in at the same time: each coefficient crosses HBM once.
+// MODE 0: Au = K u (optionally stripped); MODE 1: out = rhs - K u (residual, stripped rows give rhs)
+template <int MODE>
+__global__ void __launch_bounds__(256) ccu_k_matvec(const CcuGeom g, const float *__restrict__ K,
+                                                     const unsigned char *__restrict__ flags, const double *u,
+                                                     const double *rhs, double *out, const int strip)
+{
+    const int c = threadIdx.x >> 5;
+    const int cell = blockIdx.x * 32 + (threadIdx.x & 31);
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    double a0, a1, a2;
+    switch(c)
+    {
+    case 0: ccu_row_product<0>(g, K, u, cell, a0, a1, a2); break;
+    case 1: ccu_row_product<1>(g, K, u, cell, a0, a1, a2); break;
+    case 2: ccu_row_product<2>(g, K, u, cell, a0, a1, a2); break;
+    case 3: ccu_row_product<3>(g, K, u, cell, a0, a1, a2); break;
+    case 4: ccu_row_product<4>(g, K, u, cell, a0, a1, a2); break;
+    case 5: ccu_row_product<5>(g, K, u, cell, a0, a1, a2); break;
+    case 6: ccu_row_product<6>(g, K, u, cell, a0, a1, a2); break;
+    default: ccu_row_product<7>(g, K, u, cell, a0, a1, a2); break;
+    }
+    const size_t NS = (size_t)g.NS;
+    const int s = c * g.NC + cell;
+    if(strip)
+    {
+        const unsigned char f = flags[s];
+        if(f & CCU_F_VBX) a0 = 0.0;
+        if(f & CCU_F_VBY) a1 = 0.0;
+        if(f & CCU_F_VBZ) a2 = 0.0;
+    }
+    if(MODE == 0) { out[s] = a0; out[NS + s] = a1; out[2 * NS + s] = a2; }
+    else { out[s] = rhs[s] - a0; out[NS + s] = rhs[NS + s] - a1; out[2 * NS + s] = rhs[2 * NS + s] - a2; }
+}
+
+// ---------------------------------------------------------------- layout conversion
+// reference vector double[neq] (equation 3n+d) <-> colour-blocked SoA
+__global__ void ccu_k_vec_to_dev(const CcuGeom g, const double *__restrict__ nat, double *dev)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    dev[s] = nat[3 * (size_t)n]; dev[(size_t)g.NS + s] = nat[3 * (size_t)n + 1]; dev[2 * (size_t)g.NS + s] = nat[3 * (size_t)n + 2];
+}
+__global__ void ccu_k_vec_to_nat(const CcuGeom g, const double *__restrict__ dev, double *nat)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    nat[3 * (size_t)n] = dev[s]; nat[3 * (size_t)n + 1] = dev[(size_t)g.NS + s]; nat[3 * (size_t)n + 2] = dev[2 * (size_t)g.NS + s];
+}
+__global__ void ccu_k_flags_to_dev(const CcuGeom g, const unsigned *__restrict__ node, unsigned char *flags)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const unsigned f = node[n];
+    flags[ccu_sidx(g, i, j, k)] = (unsigned char)(CCU_F_VALID | ((f & CCU_VBX) ? CCU_F_VBX : 0) | ((f & CCU_VBY) ? CCU_F_VBY : 0) |
+                                                  ((f & CCU_VBZ) ? CCU_F_VBZ : 0));
+}
+// Eqn_k1/2/3 in the reference's layout (node-major, 42 per node, slots only for in-grid lower
+// neighbours, Construct_arrays.c:320-347) -> fixed 13-neighbour slots, coefficient-major SoA.
+__global__ void ccu_k_stiffness_to_dev(const CcuGeom g, const float *__restrict__ k1, const float *__restrict__ k2,
+                                       const float *__restrict__ k3, float *K)
+{
+    constexpr int LO[13][3] = CCU_LO_INIT;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    const size_t NS = (size_t)g.NS, base = (size_t)n * 42;
+    const float *kk[3] = { k1 + base, k2 + base, k3 + base };
+    for(int a = 0; a < 3; a++)
+        for(int b = 0; b < 3; b++) K[(size_t)(a * 3 + b) * NS + s] = kk[a][b];
+    int rs = 0;
+    for(int q = 0; q < 13; q++)
+    {
+        const int ii = i + LO[q][0], jj = j + LO[q][1], kz = k + LO[q][2];
+        const bool in = ii >= 0 && jj >= 0 && jj < g.nox && kz >= 0 && kz < g.noz;
+        if(in) rs++;
+        for(int a = 0; a < 3; a++)
+            for(int b = 0; b < 3; b++) K[(size_t)((q + 1) * 9 + a * 3 + b) * NS + s] = in ? kk[a][3 * rs + b] : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------- vector algebra on whole padded arrays
+__global__ void ccu_k_strip(const CcuGeom g, const unsigned char *__restrict__ flags, double *v)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= g.NS) return;
+    const unsigned char f = flags[s];
+    if(f & CCU_F_VBX) v[s] = 0.0;
+    if(f & CCU_F_VBY) v[(size_t)g.NS + s] = 0.0;
+    if(f & CCU_F_VBZ) v[2 * (size_t)g.NS + s] = 0.0;
+}
+// y = a*x + b*y with a, b read from device scalars: a = sa*num_a/den_a (den null -> 1)
+struct CcuCoef { const double *num, *den; double scale; };
+__device__ __forceinline__ double ccu_coef(const CcuCoef &c)
+{
+    double v = c.scale;
+    if(c.num) v *= *c.num;
+    if(c.den) v /= *c.den;
+    return v;
+}
+__global__ void ccu_k_axpby(const size_t n, double *y, const double *__restrict__ x, const CcuCoef ca, const CcuCoef cb)
+{
+    const double a = ccu_coef(ca), b = ccu_coef(cb);
+    for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = a * x[i] + b * y[i];
+}
+// z = a*x + b*y
+__global__ void ccu_k_waxpby(const size_t n, double *z, const double *__restrict__ x, const double *__restrict__ y,
+                             const CcuCoef ca, const CcuCoef cb)
+{
+    const double a = ccu_coef(ca), b = ccu_coef(cb);
+    for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        z[i] = a * x[i] + b * y[i];
+}
+__global__ void ccu_k_mul(const size_t n, double *z, const double *__restrict__ x, const double *__restrict__ y)
+{
+    for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        z[i] = x[i] * y[i];
+}
+
+// deterministic dot: fixed grid, fixed per-thread stride order, shuffle tree, then one block folds
+// the partials (global_vdot / global_pdot, Global_operations.c:339-375).  Up to 3 dots per pass so
+// the pairs the callers need together share one read of the vectors.
+#define CCU_DOT_BLOCKS 592
+__global__ void __launch_bounds__(256) ccu_k_dot_partial(const size_t n, const double *__restrict__ a0, const double *__restrict__ b0,
+                                                          const double *__restrict__ a1, const double *__restrict__ b1,
+                                                          const double *__restrict__ a2, const double *__restrict__ b2,
+                                                          double *partial)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        s0 += a0[i] * b0[i];
+        if(a1) s1 += a1[i] * b1[i];
+        if(a2) s2 += a2[i] * b2[i];
+    }
+    __shared__ double sh[3][8];
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        s0 += __shfl_down_sync(0xffffffffu, s0, o);
+        s1 += __shfl_down_sync(0xffffffffu, s1, o);
+        s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s0; sh[1][threadIdx.x >> 5] = s1; sh[2][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if(threadIdx.x < 3)
+    {
+        double t = 0.0;
+        for(int w = 0; w < 8; w++) t += sh[threadIdx.x][w];
+        partial[threadIdx.x * CCU_DOT_BLOCKS + blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) ccu_k_dot_final(const double *__restrict__ partial, const int nblocks, double *out0, double *out1, double *out2)
+{
+    __shared__ double sh[8];
+    double *outs[3] = { out0, out1, out2 };
+    for(int q = 0; q < 3; q++)
+    {
+        if(!outs[q]) continue;
+        double s = 0.0;
+        for(int i = threadIdx.x; i < nblocks; i += blockDim.x) s += partial[q * CCU_DOT_BLOCKS + i];
+        for(int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            double t = 0.0;
+            for(int w = 0; w < 8; w++) t += sh[w];
+            *outs[q] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- multigrid transfers
+// project_vector (Solver_multigrid.c:72-159): one thread per coarse node gathers the eight coarse
+// elements around it in the reference's accumulation order (ascending element number), each
+// contributing TWW * (sum of the 8 nodes of the fine sub-element in that octant); then * MASS.
+__global__ void __launch_bounds__(128) ccu_k_project(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ TWW,
+                                                      const float *__restrict__ MASS, const double *__restrict__ fine, double *coarse)
+{
+    constexpr int OFFS[9][3] = CCU_OFFS_INIT;
+    constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };   // [dz][dx][dy] -> local node
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= 8 * gc.NC) return;
+    const int c = t / gc.NC, cell = t - c * gc.NC;
+    int I, J, Kz;
+    if(!ccu_decode(gc, c, cell, I, J, Kz)) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for(int ey = I - 1; ey <= I; ey++)
+    {
+        if(ey < 0 || ey >= gc.ely) continue;
+        for(int ex = J - 1; ex <= J; ex++)
+        {
+            if(ex < 0 || ex >= gc.elx) continue;
+            for(int ez = Kz - 1; ez <= Kz; ez++)
+            {
+                if(ez < 0 || ez >= gc.elz) continue;
+                const int oy = I - ey, ox = J - ex, oz = Kz - ez;
+                const int a = LUT[oz][ox][oy];
+                const int el = ez + gc.elz * (ex + gc.elx * ey);
+                const int fy = 2 * ey + oy, fx = 2 * ex + ox, fz = 2 * ez + oz;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                for(int q = 1; q <= 8; q++)
+                {
+                    const int sf = ccu_sidx(gf, fy + OFFS[q][2], fx + OFFS[q][1], fz + OFFS[q][0]);
+                    a0 += fine[sf]; a1 += fine[(size_t)gf.NS + sf]; a2 += fine[2 * (size_t)gf.NS + sf];
+                }
+                const double w = (double)TWW[(size_t)el * 8 + a - 1];
+                s0 += w * a0; s1 += w * a1; s2 += w * a2;
+            }
+        }
+    }
+    const double m = (double)MASS[Kz + gc.noz * (J + gc.nox * I)];
+    const int sc = c * gc.NC + cell;
+    coarse[sc] = s0 * m; coarse[(size_t)gc.NS + sc] = s1 * m; coarse[2 * (size_t)gc.NS + sc] = s2 * m;
+}
+
+// interp_vector + un_inject_vector (Solver_multigrid.c:173-298, 581-634): the reference fills x,
+// then z, then y gaps in place; evaluated here per fine node as the same nested two-point
+// interpolations (fp32 weights from the element sizes the reference looks up, Appendix A #8).
+__device__ __forceinline__ int ccu_first_elt(const CcuGeom &g, int i, int j, int k)
+{
+    return (k > 0 ? k - 1 : 0) + g.elz * ((j > 0 ? j - 1 : 0) + g.elx * (i > 0 ? i - 1 : 0));
+}
+__device__ __forceinline__ void ccu_w12(const float *__restrict__ eco, int e1, int e2, int dir, float &w1, float &w2)
+{
+    const float x1 = eco[(size_t)e1 * 3 + dir], x2 = eco[(size_t)e2 * 3 + dir];
+    w1 = x2 / (x1 + x2); w2 = x1 / (x1 + x2);
+}
+__device__ __forceinline__ double ccu_interp_x(const CcuGeom &gf, const CcuGeom &gc, const float *__restrict__ eco,
+                                               const double *__restrict__ cv, int i, int j, int k)   // i, k even
+{
+    if(!(j & 1)) return cv[ccu_sidx(gc, i >> 1, j >> 1, k >> 1)];
+    float w1, w2;
+    ccu_w12(eco, ccu_first_elt(gf, i, j - 1, k), ccu_first_elt(gf, i, j + 1, k), 0, w1, w2);
+    return (double)w1 * cv[ccu_sidx(gc, i >> 1, (j - 1) >> 1, k >> 1)] + (double)w2 * cv[ccu_sidx(gc, i >> 1, (j + 1) >> 1, k >> 1)];
+}
+__device__ __forceinline__ double ccu_interp_z(const CcuGeom &gf, const CcuGeom &gc, const float *__restrict__ eco,
+                                               const double *__restrict__ cv, int i, int j, int k)   // i even
+{
+    if(!(k & 1)) return ccu_interp_x(gf, gc, eco, cv, i, j, k);
+    float w1, w2;
+    ccu_w12(eco, ccu_first_elt(gf, i, j, k - 1), ccu_first_elt(gf, i, j, k + 1), 2, w1, w2);
+    return (double)w1 * ccu_interp_x(gf, gc, eco, cv, i, j, k - 1) + (double)w2 * ccu_interp_x(gf, gc, eco, cv, i, j, k + 1);
+}
+__global__ void __launch_bounds__(128) ccu_k_interp(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ eco_f,
+                                                     const unsigned char *__restrict__ flags_f, const double *__restrict__ coarse,
+                                                     double *fine, const int strip)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= 8 * gf.NC) return;
+    const int c = t / gf.NC, cell = t - c * gf.NC;
+    int i, j, k;
+    if(!ccu_decode(gf, c, cell, i, j, k)) return;
+    const int s = c * gf.NC + cell;
+    const unsigned char f = strip ? flags_f[s] : 0;
+    for(int d = 0; d < 3; d++)
+    {
+        const double *cv = coarse + (size_t)d * gc.NS;
+        double v;
+        if(!(i & 1)) v = ccu_interp_z(gf, gc, eco_f, cv, i, j, k);
+        else
+        {
+            float w1, w2;
+            ccu_w12(eco_f, ccu_first_elt(gf, i - 1, j, k), ccu_first_elt(gf, i + 1, j, k), 1, w1, w2);
+            v = (double)w1 * ccu_interp_z(gf, gc, eco_f, cv, i - 1, j, k) + (double)w2 * ccu_interp_z(gf, gc, eco_f, cv, i + 1, j, k);
+        }
+        if(f & (d == 0 ? CCU_F_VBX : (d == 1 ? CCU_F_VBY : CCU_F_VBZ))) v = 0.0;
+        fine[(size_t)d * gf.NS + s] = v;
+    }
+}
+
+// ---------------------------------------------------------------- pressure coupling
+// assemble_div_u (Element_calculations.c:691-720): one thread per element, local nodes in order.
+__global__ void __launch_bounds__(128) ccu_k_div_u(const CcuGeom g, const float *__restrict__ elt_del, const double *__restrict__ U, double *divU)
+{
+    constexpr int OFFS[9][3] = CCU_OFFS_INIT;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    const float *gg = elt_del + (size_t)e * 24;
+    double s = 0.0;
+#pragma unroll
+    for(int a = 1; a <= 8; a++)
+    {
+        const int sn = ccu_sidx(g, ey + OFFS[a][2], ex + OFFS[a][1], ez + OFFS[a][0]);
+        s += (double)gg[3 * (a - 1)] * U[sn] + (double)gg[3 * (a - 1) + 1] * U[(size_t)g.NS + sn] + (double)gg[3 * (a - 1) + 2] * U[2 * (size_t)g.NS + sn];
+    }
+    divU[e] = s;
+}
+// assemble_grad_p (Element_calculations.c:727-769) as a gather: one thread per node sums its <= 8
+// elements in ascending element order (the order the reference's element loop adds them), then
+// strips the boundary dofs.
+__global__ void __launch_bounds__(128) ccu_k_grad_p(const CcuGeom g, const float *__restrict__ elt_del, const unsigned char *__restrict__ flags,
+                                                     const double *__restrict__ P, double *gradP)
+{
+    constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= 8 * g.NC) return;
+    const int c = t / g.NC, cell = t - c * g.NC;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                const int a = LUT[k - ez][j - ex][i - ey];
+                const double p = P[e];
+                const float *gg = elt_del + (size_t)e * 24 + 3 * (a - 1);
+                s0 += (double)gg[0] * p; s1 += (double)gg[1] * p; s2 += (double)gg[2] * p;
+            }
+        }
+    }
+    const int s = c * g.NC + cell;
+    const unsigned char f = flags[s];
+    gradP[s] = (f & CCU_F_VBX) ? 0.0 : s0;
+    gradP[(size_t)g.NS + s] = (f & CCU_F_VBY) ? 0.0 : s1;
+    gradP[2 * (size_t)g.NS + s] = (f & CCU_F_VBZ) ? 0.0 : s2;
+}

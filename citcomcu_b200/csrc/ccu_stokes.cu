@@ -1,0 +1,653 @@
+// ccu_stokes.cu -- host side of libcitcomcu_b200.so: device context, operator upload, and the
+// solver drivers (gauss_seidel, multi_grid, solve_del2_u, solve_Ahat_p_fhat) re-stated around the
+// kernels of ccu_kernels.cuh.  Scalars of the iteration (dot products, line-search alpha, CG alpha
+// and delta) stay in device memory; the host reads back only the convergence monitors the
+// reference's control flow branches on.
+#include "../../include/citcomcu_b200.h"
+#include "ccu_kernels.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+const char *ccu_last_error(void) { return g_err.c_str(); }
+
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+    g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__); return 1; } } while(0)
+#define FAIL(msg) do { g_err = (msg); return 2; } while(0)
+
+enum { S_DOT0 = 0, S_DOT1, S_DOT2, S_R1Z1, S_R0Z0, S_S2AH, S_VDOTV, S_PDOTP, S_AHAH, S_S2S2, S_U1U1, S_TMP, S_ONE, S_COUNT = 32 };
+
+struct Level
+{
+    CcuGeom g;
+    float *K = nullptr;
+    double *BI = nullptr;
+    unsigned char *flags = nullptr;
+    float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
+    double *BPI = nullptr;
+    double *vec[CCU_VEC_COUNT] = { nullptr };
+    bool have_K = false, have_flags = false, have_tw = false, have_p = false;
+    CcuLevelDev dev() const { return CcuLevelDev{ g, K, BI, flags, MASS, TWW, eco, elt_del, BPI }; }
+    size_t vlen() const { return 3 * (size_t)g.NS; }
+};
+
+struct ccu_ctx
+{
+    ccu_config cfg;
+    cudaStream_t st = 0;
+    Level L[CCU_MAX_LEVELS];
+    double *scal = nullptr;        // device scalars
+    double *partial = nullptr;     // dot partials
+    void *stage = nullptr;         // upload/download staging
+    size_t stage_bytes = 0;
+    // finest-level Uzawa work space (solve_Ahat_p_fhat's statics, Stokes_flow_Incomp.c:325-336)
+    double *uzAh = nullptr, *uzU1 = nullptr;
+    double *P = nullptr, *r0 = nullptr, *r1 = nullptr, *r2 = nullptr, *z0 = nullptr, *z1 = nullptr, *s1 = nullptr, *s2 = nullptr, *pAh = nullptr;
+    long long launches = 0;
+};
+
+#define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->st>>>(__VA_ARGS__); (ctx)->launches++; } while(0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+static int ensure_stage(ccu_ctx *c, size_t bytes)
+{
+    if(bytes <= c->stage_bytes) return 0;
+    if(c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+static int check_lev(ccu_ctx *c, int lev)
+{
+    if(!c) FAIL("null context");
+    if(lev < c->cfg.levmin || lev > c->cfg.levmax) FAIL("level out of range");
+    return 0;
+}
+
+int ccu_create(const ccu_config *cfg, ccu_ctx **out)
+{
+    if(!cfg || !out) FAIL("ccu_create: null argument");
+    if(cfg->levmin < 0 || cfg->levmax >= CCU_MAX_LEVELS || cfg->levmin > cfg->levmax) FAIL("ccu_create: bad level range");
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL("ccu_create: no CUDA device (this library has no CPU fallback)");
+    CK(cudaSetDevice(cfg->device));
+    ccu_ctx *c = new ccu_ctx();
+    c->cfg = *cfg;
+    for(int lev = cfg->levmin; lev <= cfg->levmax; lev++)
+    {
+        Level &L = c->L[lev];
+        L.g = ccu_make_geom(cfg->nox[lev], cfg->noy[lev], cfg->noz[lev]);
+        if(lev > cfg->levmin)
+        {
+            const CcuGeom &gc = c->L[lev - 1].g;
+            if(L.g.elx != 2 * gc.elx || L.g.ely != 2 * gc.ely || L.g.elz != 2 * gc.elz) { delete c; FAIL("ccu_create: levels must double"); }
+        }
+        const size_t NS = (size_t)L.g.NS;
+        CK(cudaMalloc(&L.K, sizeof(float) * 14 * 9 * NS));
+        CK(cudaMemsetAsync(L.K, 0, sizeof(float) * 14 * 9 * NS, c->st));
+        CK(cudaMalloc(&L.BI, sizeof(double) * 3 * NS));
+        CK(cudaMemsetAsync(L.BI, 0, sizeof(double) * 3 * NS, c->st));
+        CK(cudaMalloc(&L.flags, NS));
+        CK(cudaMemsetAsync(L.flags, 0, NS, c->st));
+        CK(cudaMalloc(&L.MASS, sizeof(float) * L.g.nno));
+        CK(cudaMalloc(&L.TWW, sizeof(float) * 8 * (size_t)L.g.nel));
+        CK(cudaMalloc(&L.eco, sizeof(float) * 3 * (size_t)L.g.nel));
+        const int nvec = (lev == cfg->levmax) ? CCU_VEC_COUNT : CCU_VEC_U;   // U, F, T* only at the top level
+        for(int v = 0; v < nvec; v++)
+        {
+            CK(cudaMalloc(&L.vec[v], sizeof(double) * 3 * NS));
+            CK(cudaMemsetAsync(L.vec[v], 0, sizeof(double) * 3 * NS, c->st));
+        }
+    }
+    {
+        Level &L = c->L[cfg->levmax];
+        const size_t NS = (size_t)L.g.NS, np = (size_t)L.g.npno;
+        CK(cudaMalloc(&L.elt_del, sizeof(float) * 24 * np));
+        CK(cudaMalloc(&L.BPI, sizeof(double) * np));
+        CK(cudaMalloc(&c->uzAh, sizeof(double) * 3 * NS)); CK(cudaMemsetAsync(c->uzAh, 0, sizeof(double) * 3 * NS, c->st));
+        CK(cudaMalloc(&c->uzU1, sizeof(double) * 3 * NS)); CK(cudaMemsetAsync(c->uzU1, 0, sizeof(double) * 3 * NS, c->st));
+        double **pv[] = { &c->P, &c->r0, &c->r1, &c->r2, &c->z0, &c->z1, &c->s1, &c->s2, &c->pAh };
+        for(auto p : pv) { CK(cudaMalloc(p, sizeof(double) * np)); CK(cudaMemsetAsync(*p, 0, sizeof(double) * np, c->st)); }
+    }
+    CK(cudaMalloc(&c->scal, sizeof(double) * S_COUNT));
+    CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_COUNT, c->st));
+    { const double one = 1.0; CK(cudaMemcpyAsync(c->scal + S_ONE, &one, sizeof(double), cudaMemcpyHostToDevice, c->st)); }
+    CK(cudaMalloc(&c->partial, sizeof(double) * 3 * CCU_DOT_BLOCKS));
+    CK(cudaStreamSynchronize(c->st));
+    *out = c;
+    return 0;
+}
+
+void ccu_destroy(ccu_ctx *c)
+{
+    if(!c) return;
+    for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
+    {
+        Level &L = c->L[lev];
+        cudaFree(L.K); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.BPI);
+        for(auto v : L.vec) cudaFree(v);
+    }
+    cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
+    cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
+    delete c;
+}
+
+int ccu_set_stream(ccu_ctx *c, void *s) { if(!c) FAIL("null context"); c->st = (cudaStream_t)s; return 0; }
+int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); CK(cudaStreamSynchronize(c->st)); return 0; }
+long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------ uploads
+int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    if(ensure_stage(c, sizeof(unsigned) * L.g.nno)) return 1;
+    CK(cudaMemcpyAsync(c->stage, node, sizeof(unsigned) * L.g.nno, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, ccu_k_flags_to_dev, cdiv(L.g.nno, 256), 256, L.g, (const unsigned *)c->stage, L.flags);
+    CK(cudaStreamSynchronize(c->st));
+    L.have_flags = true;
+    return 0;
+}
+
+static int vec_h2d(ccu_ctx *c, Level &L, const double *host, double *dev)
+{
+    if(ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
+    CK(cudaMemcpyAsync(c->stage, host, sizeof(double) * L.g.neq, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, ccu_k_vec_to_dev, cdiv(L.g.nno, 256), 256, L.g, (const double *)c->stage, dev);
+    return 0;
+}
+static int vec_d2h(ccu_ctx *c, Level &L, const double *dev, double *host)
+{
+    if(ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
+    LAUNCH(c, ccu_k_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, dev, (double *)c->stage);
+    CK(cudaMemcpyAsync(host, c->stage, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int ccu_set_stiffness(ccu_ctx *c, int lev, const float *k1, const float *k2, const float *k3, const double *BI)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    const size_t n42 = (size_t)L.g.nno * 42;
+    if(ensure_stage(c, sizeof(float) * 3 * n42)) return 1;
+    float *s = (float *)c->stage;
+    CK(cudaMemcpyAsync(s, k1, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(s + n42, k2, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(s + 2 * n42, k3, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, ccu_k_stiffness_to_dev, cdiv(L.g.nno, 128), 128, L.g, s, s + n42, s + 2 * n42, L.K);
+    CK(cudaStreamSynchronize(c->st));
+    if(vec_h2d(c, L, BI, L.BI)) return 1;
+    CK(cudaStreamSynchronize(c->st));
+    L.have_K = true;
+    return 0;
+}
+
+int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double *BPI)
+{
+    if(check_lev(c, lev)) return 2;
+    if(lev != c->cfg.levmax) return 0;          // only the finest level's div/grad/BPI are on the hot path
+    Level &L = c->L[lev];
+    CK(cudaMemcpyAsync(L.elt_del, elt_del, sizeof(float) * 24 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.BPI, BPI, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    L.have_p = true;
+    return 0;
+}
+
+int ccu_set_transfer_weights(ccu_ctx *c, int lev, const float *TWW, const float *MASS, const float *eco)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    CK(cudaMemcpyAsync(L.TWW, TWW, sizeof(float) * 8 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.MASS, MASS, sizeof(float) * L.g.nno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.eco, eco, sizeof(float) * 3 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    L.have_tw = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ device-side building blocks
+static const CcuCoef C_ONE = { nullptr, nullptr, 1.0 };
+static const CcuCoef C_ZERO = { nullptr, nullptr, 0.0 };
+static const CcuCoef C_MINUS = { nullptr, nullptr, -1.0 };
+static inline CcuCoef coef(const double *num, const double *den, double scale) { return CcuCoef{ num, den, scale }; }
+
+static void d_copy(ccu_ctx *c, double *dst, const double *src, size_t n)
+{
+    cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->st);
+}
+static void d_zero(ccu_ctx *c, double *dst, size_t n) { cudaMemsetAsync(dst, 0, sizeof(double) * n, c->st); }
+static void d_axpby(ccu_ctx *c, size_t n, double *y, const double *x, CcuCoef a, CcuCoef b)
+{
+    LAUNCH(c, ccu_k_axpby, min(cdiv(n, 256), 148u * 16u), 256, n, y, x, a, b);
+}
+static void d_waxpby(ccu_ctx *c, size_t n, double *z, const double *x, const double *y, CcuCoef a, CcuCoef b)
+{
+    LAUNCH(c, ccu_k_waxpby, min(cdiv(n, 256), 148u * 16u), 256, n, z, x, y, a, b);
+}
+// up to three dots in one pass over the vectors; results land in scal[slot*]
+static void d_dot3(ccu_ctx *c, size_t n, const double *a0, const double *b0, int s0, const double *a1 = nullptr, const double *b1 = nullptr,
+                   int s1 = -1, const double *a2 = nullptr, const double *b2 = nullptr, int s2 = -1)
+{
+    const int nb = (int)min((size_t)CCU_DOT_BLOCKS, (size_t)cdiv(n, 256));
+    LAUNCH(c, ccu_k_dot_partial, nb, 256, n, a0, b0, a1, b1, a2, b2, c->partial);
+    LAUNCH(c, ccu_k_dot_final, 1, 256, c->partial, nb, c->scal + s0, s1 >= 0 ? c->scal + s1 : nullptr, s2 >= 0 ? c->scal + s2 : nullptr);
+}
+static int read_scal(ccu_ctx *c, int first, int count, double *out)
+{
+    CK(cudaMemcpyAsync(out, c->scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cdiv(L.g.NS, 256), 256, L.g, L.flags, v); }
+
+static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int strip)
+{
+    LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+}
+// out = rhs - K u, boundary rows of K u stripped first (the reference's res = rhs - AU with AU stripped)
+static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs, double *out)
+{
+    LAUNCH(c, ccu_k_matvec<1>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, rhs, out, 1);
+}
+
+static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
+{
+    const unsigned grid = cdiv(L.g.NC, 128);
+    for(int s = 0; s < cycles; s++)
+    {   // colours 7..0: odd-odd-odd nodes first, the coarse-grid nodes (colour 0) last
+        LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<4>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<3>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<2>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<1>, grid, 128, L.g, L.K, L.BI, F, x);
+        LAUNCH(c, ccu_k_relax<0>, grid, 128, L.g, L.K, L.BI, F, x);
+    }
+}
+
+// gauss_seidel (General_matrix_functions.c:1160): d0, Ad = K d0
+static void d_gauss_seidel(ccu_ctx *c, Level &L, double *d0, const double *F, double *Ad, int cycles, int guess)
+{
+    if(!guess) d_zero(c, d0, L.vlen());
+    d_relax_sweeps(c, L, d0, F, cycles);
+    d_matvec(c, L, d0, Ad, 1);
+}
+
+static void d_project(ccu_ctx *c, int lev, const double *fine, double *coarse, int strip)
+{
+    Level &Lf = c->L[lev], &Lc = c->L[lev - 1];
+    LAUNCH(c, ccu_k_project, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse);
+    if(strip) d_strip(c, Lc, coarse);
+}
+static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, int strip)
+{
+    Level &Lc = c->L[lev], &Lf = c->L[lev + 1];
+    LAUNCH(c, ccu_k_interp, cdiv(8 * (size_t)Lf.g.NC, 128), 128, Lc.g, Lf.g, Lf.eco, Lf.flags, coarse, fine, strip);
+}
+
+// multi_grid (General_matrix_functions.c:525-653).  F: in rhs, out residual; d1: out correction.
+// Returns through scal[S_DOT0] the squared residual norm (host divides / roots).
+static void d_multi_grid(ccu_ctx *c, double *d1, double *F)
+{
+    const int levmin = c->cfg.levmin, levmax = c->cfg.levmax;
+    Level *L = c->L;
+    d_copy(c, L[levmax].vec[CCU_VEC_FL], F, L[levmax].vlen());
+    for(int lev = levmax; lev > levmin; lev--)
+        d_project(c, lev, L[lev].vec[CCU_VEC_FL], L[lev - 1].vec[CCU_VEC_FL], 1);
+    d_gauss_seidel(c, L[levmin], L[levmin].vec[CCU_VEC_VEL], L[levmin].vec[CCU_VEC_FL], L[levmin].vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+    for(int lev = levmin + 1; lev <= levmax; lev++)
+    {
+        d_interp(c, lev - 1, L[lev - 1].vec[CCU_VEC_VEL], L[lev].vec[CCU_VEC_VEL], 1);
+        d_copy(c, L[lev].vec[CCU_VEC_RHS], L[lev].vec[CCU_VEC_FL], L[lev].vlen());
+        for(int Vn = 1; Vn <= c->cfg.mg_cycle; Vn++)
+        {
+            for(int dlev = lev; dlev >= levmin + 1; dlev--)
+            {
+                const int cycles = (dlev == levmax) ? c->cfg.v_steps_high : c->cfg.down_heavy;
+                Level &D = L[dlev];
+                if(dlev != lev) d_zero(c, D.vec[CCU_VEC_VEL], D.vlen());
+                d_relax_sweeps(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], cycles);
+                d_residual(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], D.vec[CCU_VEC_RES]);   // res = rhs - AU
+                d_project(c, dlev, D.vec[CCU_VEC_RES], L[dlev - 1].vec[CCU_VEC_RHS], 1);
+            }
+            d_gauss_seidel(c, L[levmin], L[levmin].vec[CCU_VEC_VEL], L[levmin].vec[CCU_VEC_RHS], L[levmin].vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+            for(int ulev = levmin + 1; ulev <= lev; ulev++)
+            {
+                const int cycles = (ulev == levmax) ? c->cfg.v_steps_high : c->cfg.up_heavy;
+                Level &U = L[ulev];
+                d_interp(c, ulev - 1, L[ulev - 1].vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], 1);
+                d_gauss_seidel(c, U, U.vec[CCU_VEC_DEL_VEL], U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], cycles, 1);
+                // alpha = <AU,res>/<AU,AU>  (line search, :626-627); both dots share one pass
+                d_dot3(c, U.vlen(), U.vec[CCU_VEC_AU], U.vec[CCU_VEC_AU], S_DOT1, U.vec[CCU_VEC_AU], U.vec[CCU_VEC_RES], S_DOT2);
+                d_axpby(c, U.vlen(), U.vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], coef(c->scal + S_DOT2, c->scal + S_DOT1, 1.0), C_ONE);
+                if(ulev == levmax)
+                    d_axpby(c, U.vlen(), U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], coef(c->scal + S_DOT2, c->scal + S_DOT1, -1.0), C_ONE);
+            }
+        }
+    }
+    d_copy(c, F, L[levmax].vec[CCU_VEC_RES], L[levmax].vlen());
+    d_copy(c, d1, L[levmax].vec[CCU_VEC_VEL], L[levmax].vlen());
+    d_dot3(c, L[levmax].vlen(), F, F, S_DOT0);
+}
+
+// solve_del2_u (General_matrix_functions.c:368-520), multigrid branch.  d0 out, F in (device).
+static int d_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, int *valid, int *cycles_out)
+{
+    Level &L = c->L[c->cfg.levmax];
+    double *r = L.vec[CCU_VEC_T0], *D1 = L.vec[CCU_VEC_T1];
+    const double gneq = (double)L.g.neq;
+    d_copy(c, r, F, L.vlen());
+    d_zero(c, d0, L.vlen());
+    d_dot3(c, L.vlen(), r, r, S_DOT0);
+    double rr;
+    if(read_scal(c, S_DOT0, 1, &rr)) return 1;
+    double residual = sqrt(rr / gneq);
+    const double r0 = residual;
+    acc = fmax(acc, r0 * c->cfg.accuracy);
+    *valid = (residual < acc) ? 0 : 1;
+    int count = 0;
+    while(residual > acc)
+    {
+        d_multi_grid(c, D1, r);
+        d_axpby(c, L.vlen(), d0, D1, C_ONE, C_ONE);
+        if(read_scal(c, S_DOT0, 1, &rr)) return 1;
+        residual = sqrt(rr / gneq);
+        count++;
+        if(!(residual == residual) || count > 500) { g_err = "solve_del2_u: multigrid diverged or stalled"; return 3; }
+    }
+    if(cycles_out) *cycles_out = count;
+    return 0;
+}
+
+static void d_div_u(ccu_ctx *c, Level &L, const double *U, double *divU)
+{
+    LAUNCH(c, ccu_k_div_u, cdiv(L.g.nel, 128), 128, L.g, L.elt_del, U, divU);
+}
+static void d_grad_p(ccu_ctx *c, Level &L, const double *P, double *gradP)
+{
+    LAUNCH(c, ccu_k_grad_p, cdiv(8 * (size_t)L.g.NC, 128), 128, L.g, L.elt_del, L.flags, P, gradP);
+}
+
+// solve_Ahat_p_fhat (Stokes_flow_Incomp.c:295-497) on resident V (= vec U), P, F.
+static int d_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *residual_out, double *hist)
+{
+    Level &L = c->L[c->cfg.levmax];
+    const size_t nv = L.vlen(), np = (size_t)L.g.npno;
+    const double gneq = (double)L.g.neq, gnpno = (double)L.g.npno;
+    double *V = L.vec[CCU_VEC_U], *F = L.vec[CCU_VEC_F], *Ah = c->uzAh, *u1 = c->uzU1;
+    double *r0 = c->r0, *r1 = c->r1, *r2 = c->r2, *z0 = c->z0, *z1 = c->z1, *s1 = c->s1, *s2 = c->s2, *P = c->P, *pAh = c->pAh;
+    double h[8];
+    int valid = 1;
+
+    d_dot3(c, nv, F, F, S_DOT0);
+    if(read_scal(c, S_DOT0, 1, h)) return 1;
+    const double v_res = sqrt(h[0] / gneq);
+
+    d_grad_p(c, L, P, Ah);
+    d_matvec(c, L, V, u1, 1);
+    d_waxpby(c, nv, Ah, F, Ah, C_ONE, C_MINUS);         // Ah = F - gradP
+    d_axpby(c, nv, Ah, u1, C_MINUS, C_ONE);             //    - K V
+    d_strip(c, L, Ah);
+    if(d_solve_del2_u(c, u1, Ah, imp * v_res, &valid, nullptr)) return 1;
+    d_strip(c, L, u1);
+    d_axpby(c, nv, V, u1, C_ONE, C_ONE);
+    d_div_u(c, L, V, r1);
+    d_dot3(c, np, r1, r1, S_DOT0);
+    if(read_scal(c, S_DOT0, 1, h)) return 1;
+    const double residual = sqrt(h[0] / gnpno);
+    if(residual_out) *residual_out = (float)residual;
+
+    int count = 0;
+    float dpressure = 1.0f, dvelocity = 1.0f;
+    while(count < *steps_max && (dpressure >= imp || dvelocity >= imp))
+    {
+        LAUNCH(c, ccu_k_mul, min(cdiv(np, 256), 148u * 16u), 256, np, z1, L.BPI, r1);
+        if(count == 0)
+        {
+            d_dot3(c, np, r1, z1, S_R1Z1);
+            d_copy(c, s2, z1, np);
+        }
+        else
+        {
+            d_dot3(c, np, r1, z1, S_R1Z1, r0, z0, S_R0Z0);
+            d_waxpby(c, np, s2, z1, s1, C_ONE, coef(c->scal + S_R1Z1, c->scal + S_R0Z0, 1.0));   // s2 = z1 + delta*s1
+        }
+        d_grad_p(c, L, s2, Ah);
+        if(d_solve_del2_u(c, u1, Ah, imp * v_res, &valid, nullptr)) return 1;
+        d_strip(c, L, u1);
+        d_div_u(c, L, u1, pAh);
+        d_dot3(c, np, s2, pAh, S_S2AH);
+        // alpha = r1dotz1 / s2dotAhat, or 0 when the velocity solve was a no-op (:422-425)
+        const CcuCoef alpha = valid ? coef(c->scal + S_R1Z1, c->scal + S_S2AH, 1.0) : C_ZERO;
+        const CcuCoef malpha = valid ? coef(c->scal + S_R1Z1, c->scal + S_S2AH, -1.0) : C_ZERO;
+        d_waxpby(c, np, r2, r1, pAh, C_ONE, malpha);
+        d_axpby(c, np, P, s2, alpha, C_ONE);
+        d_axpby(c, nv, V, u1, malpha, C_ONE);
+        d_div_u(c, L, V, pAh);
+        d_dot3(c, nv, V, V, S_VDOTV, u1, u1, S_U1U1);
+        d_dot3(c, np, P, P, S_PDOTP, pAh, pAh, S_AHAH, s2, s2, S_S2S2);
+        if(read_scal(c, S_R1Z1, S_U1U1 - S_R1Z1 + 1, h)) return 1;
+        const double r1z1 = h[0], s2ah = h[S_S2AH - S_R1Z1], vdotv = h[S_VDOTV - S_R1Z1], pdotp = h[S_PDOTP - S_R1Z1];
+        const double ahah = h[S_AHAH - S_R1Z1], s2s2 = h[S_S2S2 - S_R1Z1], u1u1 = h[S_U1U1 - S_R1Z1];
+        const double al = valid ? r1z1 / s2ah : 0.0;
+        const float incomp = (float)sqrt((double)(L.g.neq / L.g.npno) * (1.0e-32 + ahah / (1.0e-32 + (double)(float)vdotv)));
+        dpressure = (float)(al * sqrt(s2s2 / (1.0e-32 + (double)(float)pdotp)));
+        dvelocity = (float)(al * sqrt(u1u1 / (1.0e-32 + (double)(float)vdotv)));
+        if(hist)
+        {
+            hist[5 * count + 0] = sqrt((double)(float)vdotv / gneq); hist[5 * count + 1] = dvelocity; hist[5 * count + 2] = incomp;
+            hist[5 * count + 3] = sqrt((double)(float)pdotp / gnpno); hist[5 * count + 4] = dpressure;
+        }
+        count++;
+        double *sh;
+        sh = s1; s1 = s2; s2 = sh;
+        sh = r0; r0 = r1; r1 = r2; r2 = sh;
+        sh = z0; z0 = z1; z1 = sh;
+    }
+    c->s1 = s1; c->s2 = s2; c->r0 = r0; c->r1 = r1; c->r2 = r2; c->z0 = z0; c->z1 = z1;
+    *steps_max = count;
+    return 0;
+}
+
+// ------------------------------------------------------------------ C ABI: device-resident forms
+static double *vecp(ccu_ctx *c, int lev, int v)
+{
+    if(v < 0 || v >= CCU_VEC_COUNT) return nullptr;
+    return c->L[lev].vec[v];
+}
+#define VEC(ptr, lev, v) double *ptr = vecp(c, lev, v); if(!ptr) FAIL("bad vector id for this level")
+
+int ccu_vec_upload(ccu_ctx *c, int lev, int v, const double *host)
+{
+    if(check_lev(c, lev)) return 2;
+    VEC(p, lev, v);
+    if(vec_h2d(c, c->L[lev], host, p)) return 1;
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_vec_download(ccu_ctx *c, int lev, int v, double *host)
+{
+    if(check_lev(c, lev)) return 2;
+    VEC(p, lev, v);
+    return vec_d2h(c, c->L[lev], p, host);
+}
+int ccu_pvec_upload(ccu_ctx *c, const double *host)
+{
+    if(!c) FAIL("null context");
+    CK(cudaMemcpyAsync(c->P, host, sizeof(double) * c->L[c->cfg.levmax].g.npno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_pvec_download(ccu_ctx *c, double *host)
+{
+    if(!c) FAIL("null context");
+    CK(cudaMemcpyAsync(host, c->P, sizeof(double) * c->L[c->cfg.levmax].g.npno, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_dev_matvec(ccu_ctx *c, int lev, int vu, int vAu, int strip)
+{
+    if(check_lev(c, lev)) return 2;
+    VEC(u, lev, vu); VEC(Au, lev, vAu);
+    d_matvec(c, c->L[lev], u, Au, strip);
+    CK(cudaGetLastError());
+    return 0;
+}
+int ccu_dev_gauss_seidel(ccu_ctx *c, int lev, int vd, int vF, int vAd, int cycles, int guess)
+{
+    if(check_lev(c, lev)) return 2;
+    VEC(d0, lev, vd); VEC(F, lev, vF); VEC(Ad, lev, vAd);
+    d_gauss_seidel(c, c->L[lev], d0, F, Ad, cycles, guess);
+    CK(cudaGetLastError());
+    return 0;
+}
+int ccu_dev_relax_sweeps(ccu_ctx *c, int lev, int vd, int vF, int cycles)
+{
+    if(check_lev(c, lev)) return 2;
+    VEC(d0, lev, vd); VEC(F, lev, vF);
+    d_relax_sweeps(c, c->L[lev], d0, F, cycles);
+    CK(cudaGetLastError());
+    return 0;
+}
+int ccu_dev_multi_grid(ccu_ctx *c, int vd1, int vF, double *residual_out)
+{
+    if(!c) FAIL("null context");
+    const int lev = c->cfg.levmax;
+    VEC(d1, lev, vd1); VEC(F, lev, vF);
+    d_multi_grid(c, d1, F);
+    double rr;
+    if(read_scal(c, S_DOT0, 1, &rr)) return 1;
+    if(residual_out) *residual_out = sqrt(rr / (double)c->L[lev].g.neq);
+    return 0;
+}
+int ccu_dev_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *residual_out, double *hist)
+{
+    if(!c) FAIL("null context");
+    return d_solve_Ahat_p_fhat(c, imp, steps_max, residual_out, hist);
+}
+
+// ------------------------------------------------------------------ C ABI: host-vector forms
+int ccu_n_assemble_del2_u(ccu_ctx *c, int lev, const double *u, double *Au, int strip)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    if(vec_h2d(c, L, u, L.vec[CCU_VEC_VEL])) return 1;
+    d_matvec(c, L, L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_AU], strip);
+    return vec_d2h(c, L, L.vec[CCU_VEC_AU], Au);
+}
+int ccu_gauss_seidel(ccu_ctx *c, int lev, double *d0, const double *F, double *Ad, int cycles, int guess)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    if(guess && vec_h2d(c, L, d0, L.vec[CCU_VEC_VEL])) return 1;
+    if(vec_h2d(c, L, F, L.vec[CCU_VEC_RHS])) return 1;
+    d_gauss_seidel(c, L, L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_RHS], L.vec[CCU_VEC_AU], cycles, guess);
+    if(vec_d2h(c, L, L.vec[CCU_VEC_VEL], d0)) return 1;
+    return vec_d2h(c, L, L.vec[CCU_VEC_AU], Ad);
+}
+int ccu_project_vector(ccu_ctx *c, int lev, const double *AU, double *AD)
+{
+    if(check_lev(c, lev) || check_lev(c, lev - 1)) return 2;
+    if(vec_h2d(c, c->L[lev], AU, c->L[lev].vec[CCU_VEC_RES])) return 1;
+    d_project(c, lev, c->L[lev].vec[CCU_VEC_RES], c->L[lev - 1].vec[CCU_VEC_RHS], 0);
+    return vec_d2h(c, c->L[lev - 1], c->L[lev - 1].vec[CCU_VEC_RHS], AD);
+}
+int ccu_interp_vector(ccu_ctx *c, int lev, const double *AD, double *AU)
+{
+    if(check_lev(c, lev) || check_lev(c, lev + 1)) return 2;
+    if(vec_h2d(c, c->L[lev], AD, c->L[lev].vec[CCU_VEC_VEL])) return 1;
+    d_interp(c, lev, c->L[lev].vec[CCU_VEC_VEL], c->L[lev + 1].vec[CCU_VEC_DEL_VEL], 0);
+    return vec_d2h(c, c->L[lev + 1], c->L[lev + 1].vec[CCU_VEC_DEL_VEL], AU);
+}
+int ccu_strip_bcs_from_residual(ccu_ctx *c, int lev, double *res)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    if(vec_h2d(c, L, res, L.vec[CCU_VEC_RES])) return 1;
+    d_strip(c, L, L.vec[CCU_VEC_RES]);
+    return vec_d2h(c, L, L.vec[CCU_VEC_RES], res);
+}
+int ccu_assemble_div_u(ccu_ctx *c, int lev, const double *U, double *divU)
+{
+    if(check_lev(c, lev)) return 2;
+    if(lev != c->cfg.levmax) FAIL("div_u: only the finest level is resident");
+    Level &L = c->L[lev];
+    if(vec_h2d(c, L, U, L.vec[CCU_VEC_VEL])) return 1;
+    d_div_u(c, L, L.vec[CCU_VEC_VEL], c->pAh);
+    CK(cudaMemcpyAsync(divU, c->pAh, sizeof(double) * L.g.npno, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_assemble_grad_p(ccu_ctx *c, int lev, const double *P, double *gradP)
+{
+    if(check_lev(c, lev)) return 2;
+    if(lev != c->cfg.levmax) FAIL("grad_p: only the finest level is resident");
+    Level &L = c->L[lev];
+    CK(cudaMemcpyAsync(c->pAh, P, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
+    d_grad_p(c, L, c->pAh, L.vec[CCU_VEC_AU]);
+    return vec_d2h(c, L, L.vec[CCU_VEC_AU], gradP);
+}
+int ccu_global_vdot(ccu_ctx *c, int lev, const double *A, const double *B, double *out)
+{
+    if(check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    if(vec_h2d(c, L, A, L.vec[CCU_VEC_VEL])) return 1;
+    CK(cudaStreamSynchronize(c->st));
+    if(vec_h2d(c, L, B, L.vec[CCU_VEC_RES])) return 1;
+    d_dot3(c, L.vlen(), L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_RES], S_TMP);
+    return read_scal(c, S_TMP, 1, out);
+}
+int ccu_global_pdot(ccu_ctx *c, int lev, const double *A, const double *B, double *out)
+{
+    if(check_lev(c, lev)) return 2;
+    if(lev != c->cfg.levmax) FAIL("pdot: only the finest level is resident");
+    const size_t np = (size_t)c->L[lev].g.npno;
+    CK(cudaMemcpyAsync(c->pAh, A, sizeof(double) * np, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->z1, B, sizeof(double) * np, cudaMemcpyHostToDevice, c->st));
+    d_dot3(c, np, c->pAh, c->z1, S_TMP);
+    return read_scal(c, S_TMP, 1, out);
+}
+int ccu_multi_grid(ccu_ctx *c, double *d1, double *F, double *residual_out)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(vec_h2d(c, L, F, L.vec[CCU_VEC_T0])) return 1;
+    if(ccu_dev_multi_grid(c, CCU_VEC_T1, CCU_VEC_T0, residual_out)) return 1;
+    if(vec_d2h(c, L, L.vec[CCU_VEC_T0], F)) return 1;
+    return vec_d2h(c, L, L.vec[CCU_VEC_T1], d1);
+}
+int ccu_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, int *valid_out, int *cycles_out)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(vec_h2d(c, L, F, L.vec[CCU_VEC_T2])) return 1;
+    int valid = 0, cyc = 0;
+    if(d_solve_del2_u(c, c->uzU1, L.vec[CCU_VEC_T2], acc, &valid, &cyc)) return 1;
+    if(valid_out) *valid_out = valid;
+    if(cycles_out) *cycles_out = cyc;
+    return vec_d2h(c, L, c->uzU1, d0);
+}
+int ccu_solve_Ahat_p_fhat(ccu_ctx *c, double *V, double *P, const double *F, double imp, int *steps_max, float *residual_out, double *hist)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(!L.have_K || !L.have_flags || !L.have_p) FAIL("solve_Ahat_p_fhat: operator not uploaded");
+    if(vec_h2d(c, L, V, L.vec[CCU_VEC_U])) return 1;
+    CK(cudaStreamSynchronize(c->st));
+    if(vec_h2d(c, L, F, L.vec[CCU_VEC_F])) return 1;
+    CK(cudaMemcpyAsync(c->P, P, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
+    if(d_solve_Ahat_p_fhat(c, imp, steps_max, residual_out, hist)) return 1;
+    CK(cudaMemcpyAsync(P, c->P, sizeof(double) * L.g.npno, cudaMemcpyDeviceToHost, c->st));
+    return vec_d2h(c, L, L.vec[CCU_VEC_U], V);
+}

@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's Stokes hot-path interface, over the C ABI.
+
+Method names, argument meaning and return conventions follow the reference functions they
+stand in for (src/prototypes.h): `n_assemble_del2_u`, `gauss_seidel`, `project_vector`,
+`interp_vector`, `assemble_div_u`, `assemble_grad_p`, `global_vdot`, `multi_grid`,
+`solve_del2_u`, `solve_Ahat_p_fhat`.  Vectors are numpy float64 arrays in the reference's
+equation numbering; PyTorch is not involved in the data path (ctypes -> libcitcomcu_b200.so).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ccu_config
+
+VEC = dict(VEL=0, RES=1, RHS=2, FL=3, DEL_VEL=4, AU=5, U=6, F=7, T0=8, T1=9, T2=10)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+class StokesContext:
+    """Device context for one subdomain: `struct All_variables` members the hot path reads."""
+
+    def __init__(self, levmin, levmax, nox, noy, noz, *, v_steps_low=20, v_steps_high=3, down_heavy=3,
+                 up_heavy=3, mg_cycle=1, p_iterations=375, accuracy=1e-3, device=0):
+        self.lib = _lib.lib()
+        cfg = ccu_config()
+        cfg.levmin, cfg.levmax = levmin, levmax
+        for lev in range(levmin, levmax + 1):
+            cfg.nox[lev], cfg.noy[lev], cfg.noz[lev] = nox[lev], noy[lev], noz[lev]
+        cfg.v_steps_low, cfg.v_steps_high = v_steps_low, v_steps_high
+        cfg.down_heavy, cfg.up_heavy, cfg.mg_cycle = down_heavy, up_heavy, mg_cycle
+        cfg.p_iterations, cfg.accuracy, cfg.device = p_iterations, accuracy, device
+        self.cfg = cfg
+        self.levmin, self.levmax = levmin, levmax
+        self.dims = {lev: (nox[lev], noy[lev], noz[lev]) for lev in range(levmin, levmax + 1)}
+        self._ctx = C.c_void_p()
+        check(self.lib.ccu_create(C.byref(cfg), C.byref(self._ctx)))
+
+    # -- geometry helpers
+    def nno(self, lev):
+        x, y, z = self.dims[lev]
+        return x * y * z
+
+    def neq(self, lev):
+        return 3 * self.nno(lev)
+
+    def nel(self, lev):
+        x, y, z = self.dims[lev]
+        return (x - 1) * (y - 1) * (z - 1)
+
+    def close(self):
+        if self._ctx:
+            self.lib.ccu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        check(self.lib.ccu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(self.lib.ccu_synchronize(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ccu_launch_count(self._ctx))
+
+    # -- operator upload (what construct_stiffness_B_matrix leaves in E)
+    def set_node_flags(self, lev, node):
+        a = np.ascontiguousarray(node, dtype=np.uint32)
+        assert a.size == self.nno(lev)
+        check(self.lib.ccu_set_node_flags(self._ctx, lev, a.ctypes.data_as(C.c_void_p)))
+
+    def set_stiffness(self, lev, k1, k2, k3, BI):
+        ks = [np.ascontiguousarray(k, dtype=np.float32) for k in (k1, k2, k3)]
+        for k in ks:
+            assert k.size == self.nno(lev) * 42
+        b, bp = _f64(BI)
+        assert b.size >= self.neq(lev)
+        check(self.lib.ccu_set_stiffness(self._ctx, lev, *[k.ctypes.data_as(C.c_void_p) for k in ks], bp))
+
+    def set_pressure_ops(self, lev, elt_del, BPI):
+        g = np.ascontiguousarray(elt_del, dtype=np.float32)
+        assert g.size == self.nel(lev) * 24
+        b, bp = _f64(BPI)
+        check(self.lib.ccu_set_pressure_ops(self._ctx, lev, g.ctypes.data_as(C.c_void_p), bp))
+
+    def set_transfer_weights(self, lev, TWW, MASS, eco_size):
+        t = np.ascontiguousarray(TWW, dtype=np.float32)
+        m = np.ascontiguousarray(MASS, dtype=np.float32)
+        e = np.ascontiguousarray(eco_size, dtype=np.float32)
+        assert t.size == self.nel(lev) * 8 and m.size == self.nno(lev) and e.size == self.nel(lev) * 3
+        check(self.lib.ccu_set_transfer_weights(self._ctx, lev, t.ctypes.data_as(C.c_void_p),
+                                                m.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p)))
+
+    def load_operator_from(self, src):
+        """Upload every level from an object with mapping access to the reference's arrays
+        (`L{lev}_NODE`, `L{lev}_Eqn_k1`, ...), e.g. an oracle dump."""
+        for lev in range(self.levmin, self.levmax + 1):
+            self.set_node_flags(lev, src[f"L{lev}_NODE"])
+            self.set_stiffness(lev, src[f"L{lev}_Eqn_k1"], src[f"L{lev}_Eqn_k2"], src[f"L{lev}_Eqn_k3"], src[f"L{lev}_BI"])
+            self.set_transfer_weights(lev, src[f"L{lev}_TWW"], src[f"L{lev}_MASS"], src[f"L{lev}_eco_size"])
+        lm = self.levmax
+        self.set_pressure_ops(lm, src[f"L{lm}_elt_del"], src[f"L{lm}_BPI"])
+
+    # -- reference-named operators (host vectors in/out)
+    def n_assemble_del2_u(self, u, level, strip_bcs=1):
+        u, up = _f64(u)
+        Au = np.empty(self.neq(level))
+        check(self.lib.ccu_n_assemble_del2_u(self._ctx, level, up, Au.ctypes.data_as(C.c_void_p), int(strip_bcs)))
+        return Au
+
+    assemble_del2_u = n_assemble_del2_u
+
+    def gauss_seidel(self, F, cycles, level, guess, d0=None):
+        n = self.neq(level)
+        d = np.zeros(n) if d0 is None else np.array(d0, dtype=np.float64)
+        F, Fp = _f64(F)
+        Ad = np.empty(n)
+        check(self.lib.ccu_gauss_seidel(self._ctx, level, d.ctypes.data_as(C.c_void_p), Fp,
+                                        Ad.ctypes.data_as(C.c_void_p), int(cycles), int(guess)))
+        return d, Ad
+
+    def project_vector(self, start_lev, AU):
+        AU, p = _f64(AU)
+        AD = np.empty(self.neq(start_lev - 1))
+        check(self.lib.ccu_project_vector(self._ctx, start_lev, p, AD.ctypes.data_as(C.c_void_p)))
+        return AD
+
+    def interp_vector(self, start_lev, AD):
+        AD, p = _f64(AD)
+        AU = np.empty(self.neq(start_lev + 1))
+        check(self.lib.ccu_interp_vector(self._ctx, start_lev, p, AU.ctypes.data_as(C.c_void_p)))
+        return AU
+
+    def strip_bcs_from_residual(self, Res, level):
+        r = np.array(Res, dtype=np.float64)
+        check(self.lib.ccu_strip_bcs_from_residual(self._ctx, level, r.ctypes.data_as(C.c_void_p)))
+        return r
+
+    def assemble_div_u(self, U, level):
+        U, p = _f64(U)
+        out = np.empty(self.nel(level))
+        check(self.lib.ccu_assemble_div_u(self._ctx, level, p, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def assemble_grad_p(self, P, lev):
+        P, p = _f64(P)
+        out = np.empty(self.neq(lev))
+        check(self.lib.ccu_assemble_grad_p(self._ctx, lev, p, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def global_vdot(self, A, B, lev):
+        A, ap = _f64(A)
+        B, bp = _f64(B)
+        out = C.c_double()
+        check(self.lib.ccu_global_vdot(self._ctx, lev, ap, bp, C.byref(out)))
+        return out.value
+
+    def global_pdot(self, A, B, lev):
+        A, ap = _f64(A)
+        B, bp = _f64(B)
+        out = C.c_double()
+        check(self.lib.ccu_global_pdot(self._ctx, lev, ap, bp, C.byref(out)))
+        return out.value
+
+    def multi_grid(self, F):
+        """Returns (d1, residual vector, residual norm) like multi_grid's in/out arguments."""
+        Fw = np.array(F, dtype=np.float64)
+        d1 = np.empty_like(Fw)
+        res = C.c_double()
+        check(self.lib.ccu_multi_grid(self._ctx, d1.ctypes.data_as(C.c_void_p), Fw.ctypes.data_as(C.c_void_p), C.byref(res)))
+        return d1, Fw, res.value
+
+    def solve_del2_u(self, F, acc):
+        F, p = _f64(F)
+        d0 = np.empty_like(F)
+        valid, cyc = C.c_int(), C.c_int()
+        check(self.lib.ccu_solve_del2_u(self._ctx, d0.ctypes.data_as(C.c_void_p), p, C.c_double(acc), C.byref(valid), C.byref(cyc)))
+        return d0, valid.value, cyc.value
+
+    def solve_Ahat_p_fhat(self, V, P, F, imp, steps_max):
+        """Returns (V, P, iterations, residual, hist[iterations,5])."""
+        Vw = np.array(V, dtype=np.float64)
+        Pw = np.array(P, dtype=np.float64)
+        F, fp = _f64(F)
+        steps = C.c_int(steps_max)
+        res = C.c_float()
+        hist = np.zeros((max(steps_max, 1), 5))
+        check(self.lib.ccu_solve_Ahat_p_fhat(self._ctx, Vw.ctypes.data_as(C.c_void_p), Pw.ctypes.data_as(C.c_void_p), fp,
+                                             C.c_double(imp), C.byref(steps), C.byref(res), hist.ctypes.data_as(C.c_void_p)))
+        return Vw, Pw, steps.value, res.value, hist[:steps.value]
+
+    # -- device-resident forms
+    def vec_upload(self, lev, vec, host):
+        h, p = _f64(host)
+        check(self.lib.ccu_vec_upload(self._ctx, lev, VEC[vec], p))
+
+    def vec_download(self, lev, vec):
+        out = np.empty(self.neq(lev))
+        check(self.lib.ccu_vec_download(self._ctx, lev, VEC[vec], out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def pvec_upload(self, host):
+        h, p = _f64(host)
+        check(self.lib.ccu_pvec_upload(self._ctx, p))
+
+    def pvec_download(self):
+        out = np.empty(self.nel(self.levmax))
+        check(self.lib.ccu_pvec_download(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dev_matvec(self, lev, u, Au, strip_bcs=1):
+        check(self.lib.ccu_dev_matvec(self._ctx, lev, VEC[u], VEC[Au], int(strip_bcs)))
+
+    def dev_gauss_seidel(self, lev, d0, F, Ad, cycles, guess):
+        check(self.lib.ccu_dev_gauss_seidel(self._ctx, lev, VEC[d0], VEC[F], VEC[Ad], int(cycles), int(guess)))
+
+    def dev_relax_sweeps(self, lev, d0, F, cycles):
+        check(self.lib.ccu_dev_relax_sweeps(self._ctx, lev, VEC[d0], VEC[F], int(cycles)))
+
+    def dev_multi_grid(self, d1, F):
+        res = C.c_double()
+        check(self.lib.ccu_dev_multi_grid(self._ctx, VEC[d1], VEC[F], C.byref(res)))
+        return res.value
+
+    def dev_solve_Ahat_p_fhat(self, imp, steps_max):
+        steps = C.c_int(steps_max)
+        res = C.c_float()
+        hist = np.zeros((max(steps_max, 1), 5))
+        check(self.lib.ccu_dev_solve_Ahat_p_fhat(self._ctx, C.c_double(imp), C.byref(steps), C.byref(res), hist.ctypes.data_as(C.c_void_p)))
+        return steps.value, res.value, hist[:steps.value]
+
+
+def context_from_dump(dump, **overrides) -> StokesContext:
+    """Build a context from the control block of an oracle dump (tests / smoke only pass the
+    dump object in; this module does not import the oracle)."""
+    ctl = dump.control()
+    nox, noy, noz = {}, {}, {}
+    for lev in range(ctl["levmin"], ctl["levmax"] + 1):
+        d = dump.dims(lev)
+        nox[lev], noy[lev], noz[lev] = d["nox"], d["noy"], d["noz"]
+    kw = dict(v_steps_low=ctl["v_steps_low"], v_steps_high=ctl["v_steps_high"], down_heavy=ctl["down_heavy"],
+              up_heavy=ctl["up_heavy"], mg_cycle=ctl["mg_cycle"], p_iterations=ctl["p_iterations"], accuracy=ctl["accuracy"])
+    kw.update(overrides)
+    ctx = StokesContext(ctl["levmin"], ctl["levmax"], nox, noy, noz, **kw)
+    ctx.load_operator_from(dump)
+    return ctx

@@ -1,0 +1,105 @@
+/* citcomcu_b200.h -- C ABI of libcitcomcu_b200.so: CitcomCU's per-timestep hot path
+ * (Stokes solve; energy step to follow) as hand-written sm_100a CUDA kernels.
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference function it
+ * replaces (paths relative to the reference tree, src/...).  Host arrays use the
+ * REFERENCE's conventions so a caller holding `struct All_variables *E` can pass its
+ * members straight through (see INTEGRATION.md for the exact bindings):
+ *   - nodes      n = k + noz*(j + nox*i), k = z index (fastest), j = x, i = y   (Construct_arrays.c:158-165)
+ *   - equations  3*n + d, vectors are double[neq] (slack slots of the reference are not touched)
+ *   - elements / pressure dofs  e = ez + elz*(ex + elx*ey); arrays passed here are 0-based,
+ *     i.e. the caller passes `E->P + 1`, `E->BPI[lev] + 1`, `E->NODE[lev] + 1`, ...
+ *   - levels are the reference's level numbers (E->mesh.levmin .. levmax)
+ * Inside the library every level lives in HBM in an 8-colour blocked layout.
+ *
+ * All functions return 0 on success, non-zero on failure (ccu_last_error() has the text);
+ * there is no CPU fallback: without a CUDA device ccu_create fails.
+ */
+#ifndef CITCOMCU_B200_H
+#define CITCOMCU_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCU_MAX_LEVELS 12
+
+typedef struct ccu_ctx ccu_ctx;
+
+/* Mesh + solver controls the hot path reads from E (SURVEY.md 8b "State the callee reads") */
+typedef struct {
+    int levmin, levmax;                 /* E->mesh.levmin / levmax */
+    int nox[CCU_MAX_LEVELS];            /* E->lmesh.NOX[lev] (nodes in x), indexed by level */
+    int noy[CCU_MAX_LEVELS];            /* E->lmesh.NOY[lev] */
+    int noz[CCU_MAX_LEVELS];            /* E->lmesh.NOZ[lev] */
+    int v_steps_low, v_steps_high;      /* E->control.v_steps_low / v_steps_high */
+    int down_heavy, up_heavy, mg_cycle; /* E->control.down_heavy / up_heavy / mg_cycle */
+    int p_iterations;                   /* E->control.p_iterations */
+    double accuracy;                    /* E->control.accuracy */
+    int device;                         /* CUDA device ordinal */
+} ccu_config;
+
+const char *ccu_last_error(void);
+int ccu_create(const ccu_config *cfg, ccu_ctx **out);
+void ccu_destroy(ccu_ctx *ctx);
+/* run all kernels on this CUDA stream (cudaStream_t cast to void*); default: legacy stream 0 */
+int ccu_set_stream(ccu_ctx *ctx, void *cuda_stream);
+int ccu_synchronize(ccu_ctx *ctx);
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+long long ccu_launch_count(ccu_ctx *ctx);
+
+/* ---- operator upload (what construct_stiffness_B_matrix, Construct_arrays.c:834, leaves in E) ---- */
+/* E->NODE[lev]+1 : flag bits VBX 0x2, VBZ 0x4, VBY 0x8 (global_defs.h:65-89) */
+int ccu_set_node_flags(ccu_ctx *ctx, int lev, const unsigned *node /*[nno]*/);
+/* E->Eqn_k1/2/3[lev] in the reference's half-matrix layout (Construct_arrays.c:359-535), E->BI[lev] */
+int ccu_set_stiffness(ccu_ctx *ctx, int lev, const float *eqn_k1, const float *eqn_k2, const float *eqn_k3 /*[nno*42]*/,
+                      const double *BI /*[neq]*/);
+/* E->elt_del[lev][1..nel].g (get_elt_g, Element_calculations.c:831) and E->BPI[lev]+1 (build_diagonal_of_Ahat, :654) */
+int ccu_set_pressure_ops(ccu_ctx *ctx, int lev, const float *elt_del /*[nel*24]*/, const double *BPI /*[npno]*/);
+/* E->TWW[lev][1..nel].node[1..8], E->MASS[lev]+1 (Size_does_matter.c:618), E->ECO[lev][1..nel].size[1..3] */
+int ccu_set_transfer_weights(ccu_ctx *ctx, int lev, const float *TWW /*[nel*8]*/, const float *MASS /*[nno]*/,
+                             const float *eco_size /*[nel*3]*/);
+
+/* ---- hot-path operators, host vectors in / out (drop-in granularity of SURVEY.md 8b) ---- */
+/* n_assemble_del2_u / assemble_del2_u (Element_calculations.c:552, :480) */
+int ccu_n_assemble_del2_u(ccu_ctx *ctx, int lev, const double *u, double *Au, int strip_bcs);
+/* gauss_seidel (General_matrix_functions.c:1160): `cycles` 8-colour sweeps; d0 in/out (in only if guess), Ad = K*d0 out */
+int ccu_gauss_seidel(ccu_ctx *ctx, int lev, double *d0, const double *F, double *Ad, int cycles, int guess);
+/* project_vector (Solver_multigrid.c:72): fine level `lev` -> lev-1 */
+int ccu_project_vector(ccu_ctx *ctx, int lev, const double *AU, double *AD);
+/* interp_vector (Solver_multigrid.c:173): coarse level `lev` -> lev+1 */
+int ccu_interp_vector(ccu_ctx *ctx, int lev, const double *AD, double *AU);
+/* strip_bcs_from_residual (Boundary_conditions.c:926) */
+int ccu_strip_bcs_from_residual(ccu_ctx *ctx, int lev, double *res);
+/* assemble_div_u / assemble_grad_p (Element_calculations.c:691, :727), finest level */
+int ccu_assemble_div_u(ccu_ctx *ctx, int lev, const double *U, double *divU /*[npno]*/);
+int ccu_assemble_grad_p(ccu_ctx *ctx, int lev, const double *P /*[npno]*/, double *gradP);
+/* global_vdot / global_pdot (Global_operations.c:339, :359) */
+int ccu_global_vdot(ccu_ctx *ctx, int lev, const double *A, const double *B, double *out);
+int ccu_global_pdot(ccu_ctx *ctx, int lev, const double *A, const double *B, double *out);
+/* multi_grid (General_matrix_functions.c:525): one FMG cycle at levmax; F in = rhs, out = residual; d1 out */
+int ccu_multi_grid(ccu_ctx *ctx, double *d1, double *F, double *residual_out);
+/* solve_del2_u (General_matrix_functions.c:368): returns `valid` through *valid_out, MG cycle count through *cycles_out */
+int ccu_solve_del2_u(ccu_ctx *ctx, double *d0, const double *F, double acc, int *valid_out, int *cycles_out);
+/* solve_Ahat_p_fhat (Stokes_flow_Incomp.c:295): V, P in/out, F in; *steps_max in = p_iterations, out = iterations done.
+ * hist (may be NULL) receives per iteration {v, dv/v, div/v, p, dp/p} as printed by generate_log_message (:501). */
+int ccu_solve_Ahat_p_fhat(ccu_ctx *ctx, double *V, double *P, const double *F, double imp, int *steps_max,
+                          float *residual_out, double *hist /*[steps_max*5]*/);
+
+/* ---- device-resident forms (inputs already in HBM; used by bench.py for `value` and the roofline) ---- */
+enum { CCU_VEC_VEL = 0, CCU_VEC_RES = 1, CCU_VEC_RHS = 2, CCU_VEC_FL = 3, CCU_VEC_DEL_VEL = 4, CCU_VEC_AU = 5,
+       CCU_VEC_U = 6, CCU_VEC_F = 7, CCU_VEC_T0 = 8, CCU_VEC_T1 = 9, CCU_VEC_T2 = 10, CCU_VEC_COUNT = 11 };
+int ccu_vec_upload(ccu_ctx *ctx, int lev, int vec, const double *host /*[neq]*/);
+int ccu_vec_download(ccu_ctx *ctx, int lev, int vec, double *host /*[neq]*/);
+int ccu_pvec_upload(ccu_ctx *ctx, const double *host /*[npno]*/);    /* pressure P at levmax */
+int ccu_pvec_download(ccu_ctx *ctx, double *host /*[npno]*/);
+int ccu_dev_matvec(ccu_ctx *ctx, int lev, int vec_u, int vec_Au, int strip_bcs);
+int ccu_dev_gauss_seidel(ccu_ctx *ctx, int lev, int vec_d0, int vec_F, int vec_Ad, int cycles, int guess);
+int ccu_dev_relax_sweeps(ccu_ctx *ctx, int lev, int vec_d0, int vec_F, int cycles);   /* sweeps only, no Ad */
+int ccu_dev_multi_grid(ccu_ctx *ctx, int vec_d1, int vec_F, double *residual_out);
+/* whole Stokes solve on resident CCU_VEC_U (in/out), CCU_VEC_F (in) and the resident pressure */
+int ccu_dev_solve_Ahat_p_fhat(ccu_ctx *ctx, double imp, int *steps_max, float *residual_out, double *hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

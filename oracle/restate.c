@@ -5,7 +5,7 @@
  *
  * Two families:
  *   ccu_r_*      reference algorithms (file:line cited per function)
- *   ccu_r_mc_*   the 8-colour symmetric Gauss-Seidel the CUDA path implements,
+ *   ccu_r_mc_*   the 8-colour Gauss-Seidel (colours 7..0 each sweep) the CUDA path implements,
  *                stated on the reference's own arrays; it is the exact checker
  *                for the kernels, and is itself checked against the reference at
  *                converged tolerance (colouring changes iterates, not solutions).
@@ -134,12 +134,11 @@ void ccu_r_gauss_seidel(const ccu_r_level *L, double *d0, const double *F, doubl
 }
 
 /* ------------------------------------------------------------------------------------------
- * 8-colour symmetric Gauss-Seidel model (what the CUDA path computes).
- * colour(n) = 4*(i&1) + 2*(j&1) + (k&1); colours are relaxed in order 0..7 on forward
- * sweeps and 7..0 on backward sweeps.  The pair block K_nm is owned by the endpoint with the
- * larger colour, so a forward pass touches only "own" blocks and a backward pass only the
- * transposed blocks owned by later-colour neighbours: every stored coefficient is read once
- * per sweep.  lo = (L x), up = (L^T x) are carried between sweeps (Conrad-Wallach style).
+ * 8-colour Gauss-Seidel model (what the CUDA path computes).
+ * colour(n) = 4*(i&1) + 2*(j&1) + (k&1).  Nodes of one colour share no stencil neighbour, so a
+ * colour pass is order-independent; it is stated here on the reference's half-stored arrays:
+ * row of n = self block + blocks n owns (lower neighbours) + transposed blocks its upper
+ * neighbours own.
  * ------------------------------------------------------------------------------------------ */
 static inline int colour_of(int i, int j, int k) { return ((i & 1) << 2) | ((j & 1) << 1) | (k & 1); }
 
@@ -171,7 +170,7 @@ static void get_block(const ccu_r_level *L, int n, int m, double B[3][3])
     }
 }
 
-/* sum over neighbours with colour < (which<0) or > (which>0) own colour, in offset order o=0..26 */
+/* sum over the lower-numbered (which<0) or higher-numbered (which>0) neighbours of n */
 static void tri_product(const ccu_r_level *L, int n, const double *x, int which, double out[3])
 {
     int i, j, k, o, a;
@@ -186,9 +185,9 @@ static void tri_product(const ccu_r_level *L, int n, const double *x, int which,
         int cm, m;
         if(o == 13) continue;
         if(ii < 0 || ii >= L->noy || jj < 0 || jj >= L->nox || kk < 0 || kk >= L->noz) continue;
-        cm = colour_of(ii, jj, kk);
-        if((which < 0 && cm > c) || (which > 0 && cm < c)) continue;
+        (void)cm; (void)c;
         m = nid(L, ii, jj, kk);
+        if((which < 0 && m > n) || (which > 0 && m < n)) continue;      /* lower / upper neighbours (natural numbering) */
         get_block(L, n, m, B);
         for(a = 0; a < 3; a++)
             out[a] += B[a][0] * x[3 * m] + B[a][1] * x[3 * m + 1] + B[a][2] * x[3 * m + 2];
@@ -213,53 +212,35 @@ void ccu_r_mc_matvec(const ccu_r_level *L, const double *u, double *Au, int stri
         tri_product(L, n, u, -1, lo);
         tri_product(L, n, u, +1, up);
         self_product(L, n, u, s);
-        for(a = 0; a < 3; a++) Au[3 * n + a] = (lo[a] + s[a]) + up[a];
+        for(a = 0; a < 3; a++) Au[3 * n + a] = (s[a] + lo[a]) + up[a];
     }
     if(strip) ccu_r_strip_bcs(L, Au);
 }
 
-static void mc_relax(const ccu_r_level *L, int n, double *x, const double *F, double *lo, double *up)
-{
-    double s[3];
-    int a;
-    self_product(L, n, x, s);
-    for(a = 0; a < 3; a++)
-    {
-        const double r = F[3 * n + a] - ((lo[3 * n + a] + s[a]) + up[3 * n + a]);
-        const float t = (float)(r * L->BI[3 * n + a]);      /* reference keeps the correction in fp32 (General_matrix_functions.c:1172,1250) */
-        x[3 * n + a] += t;
-    }
-}
-
+/* One colour pass = every node of that colour relaxed from the full row with the values its
+ * neighbours hold now (neighbours never share its colour).  Colours go 7,6,...,0 on every sweep:
+ * the design study below (ccu_r_ordered_gs) shows this fixed order matches the lexicographic
+ * smoother's multigrid convergence, while alternating directions does not. */
 void ccu_r_mc_gauss_seidel(const ccu_r_level *L, double *d0, const double *F, double *Ad, int cycles, int guess)
 {
-    int n, c, sweep, i, j, k, a, last_fwd = 1;
-    double *lo = (double *)calloc(L->neq, sizeof(double)), *up = (double *)calloc(L->neq, sizeof(double));
+    int n, c, sweep, i, j, k, a;
     if(!guess) for(n = 0; n < L->neq; n++) d0[n] = 0.0;
-    else for(n = 0; n < L->nno; n++) tri_product(L, n, d0, +1, up + 3 * n);
     for(sweep = 0; sweep < cycles; sweep++)
-    {
-        last_fwd = !(sweep & 1);
-        for(c = last_fwd ? 0 : 7; c >= 0 && c < 8; c += last_fwd ? 1 : -1)
+        for(c = 7; c >= 0; c--)
             for(n = 0; n < L->nno; n++)
             {
+                double lo[3], up[3], s[3];
                 nijk(L, n, &i, &j, &k);
                 if(colour_of(i, j, k) != c) continue;
-                if(last_fwd) tri_product(L, n, d0, -1, lo + 3 * n);
-                else tri_product(L, n, d0, +1, up + 3 * n);
-                mc_relax(L, n, d0, F, lo, up);
+                tri_product(L, n, d0, -1, lo); tri_product(L, n, d0, +1, up); self_product(L, n, d0, s);
+                for(a = 0; a < 3; a++)
+                {
+                    const double r = F[3 * n + a] - ((s[a] + lo[a]) + up[a]);
+                    const float t = (float)(r * L->BI[3 * n + a]);   /* fp32 correction, General_matrix_functions.c:1172,1250 */
+                    d0[3 * n + a] += t;
+                }
             }
-    }
-    for(n = 0; n < L->nno; n++)
-    {
-        double s[3];
-        if(cycles == 0 || last_fwd) tri_product(L, n, d0, +1, up + 3 * n);
-        if(cycles == 0 || !last_fwd) tri_product(L, n, d0, -1, lo + 3 * n);
-        self_product(L, n, d0, s);
-        for(a = 0; a < 3; a++) Ad[3 * n + a] = (lo[3 * n + a] + s[a]) + up[3 * n + a];
-    }
-    ccu_r_strip_bcs(L, Ad);     /* the reference's guess path strips Ad (n_assemble_del2_u(...,1)); BC rows of K are zero anyway */
-    free(lo); free(up);
+    ccu_r_mc_matvec(L, d0, Ad, 1);
 }
 
 /* Solver_multigrid.c:72-159 (project_vector, 3-D) */

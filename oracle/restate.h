@@ -37,7 +37,7 @@ typedef struct {
 typedef struct {
     int levmin, levmax;
     int v_steps_low, v_steps_high, down_heavy, up_heavy, mg_cycle;
-    int smoother;               /* 0 = reference lexicographic GS, 1 = 8-colour symmetric GS model */
+    int smoother;               /* 0 = reference lexicographic GS, 1 = 8-colour GS model (colours 7..0) */
     double accuracy;            /* E->control.accuracy */
     ccu_r_level lev[12];
 } ccu_r_mg;

@@ -1,0 +1,99 @@
+"""CPU tests: the plain-C restatement (oracle/restate.c) against the reference's own outputs.
+
+The reference ships no tests or golden vectors; the pins are known-answer
+vectors produced by the unmodified reference functions on seeded inputs (oracle/ref_harness.c
+`dump_kats`).  Bar: bit-exact for the restated reference algorithms; converged-solution
+tolerance (1e-6 relative L2, north star) for the 8-colour smoother model.
+"""
+import numpy as np
+import pytest
+
+from conftest import get_case, po
+
+
+@pytest.fixture(scope="module")
+def case(oracle_built):
+    return get_case("busse_l3")[0]
+
+
+def test_restated_operators_bit_exact(case):
+    d = case
+    R = po.Restate(d, smoother=0)
+    for lev in range(d.levmin, d.levmax + 1):
+        u, f = d[f"kat_L{lev}_u"], d[f"kat_L{lev}_f"]
+        assert np.array_equal(R.matvec(lev, u), d[f"kat_L{lev}_Au"])
+        dd, Ad = R.gauss_seidel(lev, f, 2, 0)
+        assert np.array_equal(dd, d[f"kat_L{lev}_gs0_d"]) and np.array_equal(Ad, d[f"kat_L{lev}_gs0_Ad"])
+        dd, Ad = R.gauss_seidel(lev, f, 3, 1, d0=u)
+        assert np.array_equal(dd, d[f"kat_L{lev}_gs1_d"]) and np.array_equal(Ad, d[f"kat_L{lev}_gs1_Ad"])
+        if lev > d.levmin:
+            assert np.array_equal(R.project_vector(lev, u), d[f"kat_L{lev}_proj"])
+        if lev < d.levmax:
+            assert np.array_equal(R.interp_vector(lev, u), d[f"kat_L{lev}_interp"])
+        assert R.vdot(lev, u, f) == d[f"kat_L{lev}_vdot"][0]
+    lm = d.levmax
+    assert np.array_equal(R.div_u(lm, d["kat_div_u"]), d["kat_div_out"])
+    assert np.array_equal(R.grad_p(lm, d["kat_grad_p"]), d["kat_grad_out"])
+
+
+def test_restated_multigrid_and_solve_bit_exact(case):
+    d = case
+    R = po.Restate(d, smoother=0)
+    d1, res, r = R.multi_grid(d["kat_solve_f"])
+    assert np.array_equal(d1, d["kat_mg_d1"]) and np.array_equal(res, d["kat_mg_res"]) and r == d["kat_mg_residual"][0]
+    R2 = po.Restate(d, smoother=0, accuracy=1e-11)
+    d0, valid, cyc = R2.solve_del2_u(d["kat_solve_f"])
+    assert np.array_equal(d0, d["kat_solve_d0"]) and valid == int(d["kat_solve_valid"][0])
+
+
+def test_restated_uzawa_bit_exact(case):
+    d = case
+    lm = d.levmax
+    R = po.Restate(d, smoother=0)
+    n, npno = d.dims(lm)["neq"], d.dims(lm)["npno"]
+    V, P, steps, hist = R.solve_Ahat_p_fhat(np.zeros(n), np.zeros(npno), d["s0_F"], d.control()["accuracy"], 375)
+    assert np.array_equal(V, d["s0_U"]) and np.array_equal(P, d["s0_P"])
+
+
+def test_colour_matvec_matches_reference(case):
+    d = case
+    R = po.Restate(d)
+    for lev in range(d.levmin, d.levmax + 1):
+        u = d[f"kat_L{lev}_u"]
+        ref = d[f"kat_L{lev}_Au"]
+        assert np.abs(R.matvec(lev, u, mc=True) - ref).max() <= 1e-14 * np.abs(ref).max()
+
+
+def test_colour_smoother_converges_to_reference_solution(case):
+    """8-colour smoother inside the reference's multigrid: same solution at solver tolerance,
+    comparable cycle count (the north star's comparison level)."""
+    d = case
+    ref = d["kat_solve_d0"]
+    R = po.Restate(d, smoother=1, accuracy=1e-11)
+    d0, valid, cyc = R.solve_del2_u(d["kat_solve_f"])
+    R0 = po.Restate(d, smoother=0, accuracy=1e-11)
+    _, _, cyc_ref = R0.solve_del2_u(d["kat_solve_f"])
+    assert np.linalg.norm(d0 - ref) <= 1e-6 * np.linalg.norm(ref)
+    assert cyc <= cyc_ref + 2
+
+
+def test_colour_smoother_stokes_solution_tight():
+    d = get_case("tdepv_l3_tight")[0]
+    lm = d.levmax
+    n, npno = d.dims(lm)["neq"], d.dims(lm)["npno"]
+    R = po.Restate(d, smoother=1)
+    V, P, steps, hist = R.solve_Ahat_p_fhat(np.zeros(n), np.zeros(npno), d["s0_F"], d.control()["accuracy"], 375)
+    assert np.linalg.norm(V - d["s0_U"]) <= 1e-6 * np.linalg.norm(d["s0_U"])
+    assert np.linalg.norm(P - d["s0_P"]) <= 1e-6 * np.linalg.norm(d["s0_P"])
+
+
+def test_golden_scalars_busse1a_survey_values():
+    """SURVEY.md section 4 probe values for Busse 1a step 0 (first golden values): momentum residue
+    1.93359e-4 over 55539 equations; reproduced by the restated Uzawa on the reference's arrays."""
+    import json
+    from conftest import GOLDEN
+    g = json.loads((GOLDEN / "busse1a_scalars.json").read_text())
+    assert g["neq"] == 55539
+    assert abs(g["v_res"] - 0.000193359) < 5e-10
+    assert g["pressure_loops"] == 9
+    assert abs(g["v"] - 9.073266e-02) < 5e-8 and abs(g["p"] - 1.925851e+00) < 5e-6
