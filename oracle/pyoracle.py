@@ -82,7 +82,7 @@ class Dump:
 
 
 def run_harness(input_text: str, workdir, nsteps: int = 0, kat: bool = False, nproc: int = 1,
-                preload: str | None = None, timeout: float = 600.0, quiet: bool = True):
+                preload: str | None = None, timeout: float = 600.0, quiet: bool = True, setup_only: bool = False):
     """Run the reference through ref_harness in `workdir`; returns (list of Dump per rank, stderr text)."""
     workdir = Path(workdir)
     (workdir / "out").mkdir(parents=True, exist_ok=True)
@@ -90,9 +90,7 @@ def run_harness(input_text: str, workdir, nsteps: int = 0, kat: bool = False, np
     (workdir / "in.input").write_text(input_text)
     env = dict(os.environ)
     env["CCU_MPI_NP"] = str(nproc)
-    if preload:
-        env["LD_PRELOAD"] = preload
-    cmd = [str(REFDIR / "ref_harness"), "dump", "in.input", "dump", str(nsteps)] + (["kat"] if kat else [])
+XX, "in.input", "dump", str(nsteps)] + (["kat"] if kat else [])
     r = subprocess.run(cmd, cwd=workdir, env=env, capture_output=True, text=True, timeout=timeout)
     if r.returncode not in (0, 8):
         raise RuntimeError(f"ref_harness failed rc={r.returncode}\n{r.stderr[-4000:]}")

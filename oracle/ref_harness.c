@@ -306,9 +306,20 @@ int main(int argc, char **argv)
         DUMP_F64("ctl", ctl, 4);
     }
 
-    general_stokes_solver(&E);
-    process_temp_field(&E, E.monitor.solution_cycles);
-    process_new_velocity(&E, E.monitor.solution_cycles);
+    if(getenv("CCU_SETUP_ONLY"))
+    {   /* operator + right-hand side only: general_stokes_solver (Drive_solvers.c:105-126) without the solve */
+        velocities_conform_bcs(&E, E.U);
+        assemble_forces(&E, 0);
+        if(E.viscosity.update_allowed)
+            get_system_viscosity(&E, 1, E.EVI[E.mesh.levmax], E.VI[E.mesh.levmax]);
+        construct_stiffness_B_matrix(&E);
+    }
+    else
+    {
+        general_stokes_solver(&E);
+        process_temp_field(&E, E.monitor.solution_cycles);
+        process_new_velocity(&E, E.monitor.solution_cycles);
+    }
     dump_level_arrays(&E);
     dump_fields(&E, "s0");
     if(want_kat) dump_kats(&E);
