@@ -90,7 +90,11 @@ def run_harness(input_text: str, workdir, nsteps: int = 0, kat: bool = False, np
     (workdir / "in.input").write_text(input_text)
     env = dict(os.environ)
     env["CCU_MPI_NP"] = str(nproc)
-XX, "in.input", "dump", str(nsteps)] + (["kat"] if kat else [])
+    if preload:
+        env["LD_PRELOAD"] = preload
+    if setup_only:
+        env["CCU_SETUP_ONLY"] = "1"
+    cmd = [str(REFDIR / "ref_harness"), "dump", "in.input", "dump", str(nsteps)] + (["kat"] if kat else [])
     r = subprocess.run(cmd, cwd=workdir, env=env, capture_output=True, text=True, timeout=timeout)
     if r.returncode not in (0, 8):
         raise RuntimeError(f"ref_harness failed rc={r.returncode}\n{r.stderr[-4000:]}")
