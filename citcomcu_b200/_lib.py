@@ -23,7 +23,17 @@ def build_library(verbose: bool = False) -> Path:
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [CSRC.parent.parent / "include" / "citcomcu_b200.h"]
     if LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return LIB_PATH
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB_PATH), *srcs]
+    # *_exact.cu reproduce the reference's rounding sequence: no FMA contraction there
+    objs = []
+    for src in srcs:
+        obj = src[:-3] + ".o"
+        extra = ["-fmad=false"] if src.endswith("_exact.cu") else []
+        cmd = ["nvcc", *[f for f in NVCC_FLAGS if f != "--shared"], *extra, "-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    cmd = ["nvcc", "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *objs]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

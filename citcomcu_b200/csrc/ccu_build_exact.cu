@@ -1,0 +1,719 @@
+// ccu_build_exact.cu -- operator construction on the device:
+// element geometry (get_global_shape_fn), mass matrix and transfer weights (mass_matrix), pressure
+// gradient rows (get_elt_g), viscosity from temperature (get_system_viscosity / visc_from_T),
+// viscosity coarsening (project_viscosity), element stiffness + augmented Lagrangian (get_elt_k,
+// get_aug_k), node-stored half matrix and inverse diagonal (construct_node_ks, build_diagonal_of_K),
+// pressure preconditioner (build_diagonal_of_Ahat) and the body-force vector (assemble_forces).
+//
+// This translation unit is compiled with -fmad=false: every expression follows the reference's
+// operand types and evaluation order (float products where both operands are float, double
+// otherwise, float accumulators where the reference accumulates into float arrays), so that the
+// coefficients written to HBM are bit-identical to the ones the reference's host code builds.
+// Scatter loops of the reference are restated as gathers in ascending element order, which is
+// the order the reference's element loops add contributions in.
+#include "ccu_ctx.cuh"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#define CCU_F_VBX 1
+#define CCU_F_VBY 2
+#define CCU_F_VBZ 4
+
+// master-element tables (construct_shape_functions, Shape_functions.c:53; indices GNVINDEX / GNVXINDEX,
+// element_definitions.h:59-63): Nv[8*(n-1)+(v-1)], Nxv[64*d + 8*(n-1) + (v-1)], Np[n-1], Nxp[8*d + (n-1)]
+struct ShapeTables { float Nv[64], Nxv[192], Np[8], Nxp[24]; };
+__constant__ ShapeTables c_sh;
+
+static double h_lpoly(int p, double y) { return p == 1 ? 0.5 * (1 - y) : (p == 2 ? 0.5 * (1 + y) : 0.0); }
+static double h_lpolydash(int p) { return p == 1 ? -0.5 : (p == 2 ? 0.5 : 0.0); }
+
+static void make_shape_tables(ShapeTables &t)
+{
+    const float B = (float)0.57735026918962576451;
+    const float gx[9][3] = { {0,0,0}, {-B,-B,-B}, {B,-B,-B}, {B,B,-B}, {-B,B,-B}, {-B,-B,B}, {B,-B,B}, {B,B,B}, {-B,B,B} };   // g_point
+    const int bb[3][9] = { {0,1,2,2,1,1,2,2,1}, {0,1,1,2,2,1,1,2,2}, {0,1,1,1,1,2,2,2,2} };
+    for(int i = 1; i <= 8; i++)
+    {
+        for(int j = 1; j <= 8; j++)
+        {
+            float n = 1.0f;
+            for(int d = 0; d < 3; d++) n = (float)((double)n * h_lpoly(bb[d][i], (double)gx[j][d]));
+            t.Nv[8 * (i - 1) + (j - 1)] = n;
+            for(int dd = 0; dd < 3; dd++)
+            {
+                float v = (float)h_lpolydash(bb[dd][i]);
+                for(int d = 0; d < 3; d++) if(d != dd) v = (float)((double)v * h_lpoly(bb[d][i], (double)gx[j][d]));
+                t.Nxv[64 * dd + 8 * (i - 1) + (j - 1)] = v;
+            }
+        }
+        {
+            float n = 1.0f;
+            for(int d = 0; d < 3; d++) n = (float)((double)n * h_lpoly(bb[d][i], 0.0));
+            t.Np[i - 1] = n;
+            for(int dd = 0; dd < 3; dd++)
+            {
+                float v = (float)h_lpolydash(bb[dd][i]);
+                for(int d = 0; d < 3; d++) if(d != dd) v = (float)((double)v * h_lpoly(bb[d][i], 0.0));
+                t.Nxp[8 * dd + (i - 1)] = v;
+            }
+        }
+    }
+}
+
+__device__ __constant__ int c_OFFS[9][3] = CCU_OFFS_INIT;      // local node -> (dz, dx, dy)
+
+// natural node id of local node a of element (ey, ex, ez)
+__device__ __forceinline__ int elt_node(const CcuGeom &g, int ey, int ex, int ez, int a)
+{
+    return (ez + c_OFFS[a][0]) + g.noz * ((ex + c_OFFS[a][1]) + g.nox * (ey + c_OFFS[a][2]));
+}
+
+// get_global_shape_fn (Size_does_matter.c:60-179), Cartesian branch, one integration point:
+// NX = master-element derivatives at that point, [d][node]; out: gnx[d][node] (float), return Jacobian (double)
+__device__ __forceinline__ double gp_geom(const float X[3][8], const float *NX, int stride_d, int stride_n, float gnx[3][8])
+{
+    double dxda[3][3];
+    for(int d = 0; d < 3; d++) for(int e = 0; e < 3; e++) dxda[d][e] = 0.0;
+    for(int i = 0; i < 8; i++)
+        for(int d = 0; d < 3; d++)
+            for(int e = 0; e < 3; e++)
+                dxda[d][e] += X[e][i] * NX[d * stride_d + i * stride_n];         // float * float
+    const double (*A)[3] = dxda;
+    const double jac = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    double cof[3][3];
+    for(int d = 0; d < 3; d++)
+        for(int e = 0; e < 3; e++)
+        {
+            const int r0 = (d == 0) ? 1 : 0, r1 = (d == 2) ? 1 : 2, c0 = (e == 0) ? 1 : 0, c1 = (e == 2) ? 1 : 2;
+            const double det2 = A[r0][c0] * A[r1][c1] - A[r0][c1] * A[r1][c0];
+            cof[d][e] = (((d + e) & 1) ? -1 : 1) * det2;
+        }
+    for(int j = 0; j < 8; j++)
+        for(int d = 0; d < 3; d++)
+        {
+            float v = 0.0f;
+            for(int e = 0; e < 3; e++) v = (float)((double)v + NX[e * stride_d + j * stride_n] * cof[e][d]);
+            v = (float)((double)v / jac);
+            gnx[d][j] = v;
+        }
+    return jac;
+}
+
+__device__ __forceinline__ void load_elt_coords(const CcuGeom &g, const float *__restrict__ XX, int ey, int ex, int ez, float X[3][8])
+{
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        for(int e = 0; e < 3; e++) X[e][a - 1] = XX[(size_t)e * g.nno + n];
+    }
+}
+
+// ---------------------------------------------------------------- geometry-derived arrays
+// mass_matrix (Size_does_matter.c:618-757): TWW, ECO.size; get_elt_g (Element_calculations.c:831, CART3D :921-927)
+__global__ void __launch_bounds__(128) bk_elt_geometry(const CcuGeom g, const float *__restrict__ XX, float *TWW, double *TWWd, float *eco, float *elt_del)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8], gnx[3][8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    double temp[8];
+    for(int a = 0; a < 8; a++) temp[a] = 0.0;
+    for(int k = 0; k < 8; k++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gnx);
+        for(int a = 0; a < 8; a++) temp[a] += gda * 1.0f * c_sh.Nv[8 * a + k];          // float*float*float
+    }
+    for(int a = 0; a < 8; a++) { TWW[(size_t)e * 8 + a] = (float)temp[a]; TWWd[(size_t)e * 8 + a] = temp[a]; }
+    {   // element sizes: n[] are 1-based local nodes in the reference expressions (:688-695)
+        const float *x1 = X[0], *x2 = X[1], *x3 = X[2];
+        float d;
+        d = (float)(0.25 * ((double)x1[1] + x1[2] + x1[5] + x1[6] - x1[0] - x1[3] - x1[4] - x1[7]));
+        eco[(size_t)e * 3 + 0] = (float)sqrt((double)(d * d));
+        d = (float)(0.25 * ((double)x2[2] + x2[3] + x2[6] + x2[7] - x2[0] - x2[1] - x2[4] - x2[5]));
+        eco[(size_t)e * 3 + 1] = (float)sqrt((double)(d * d));
+        d = (float)(0.25 * ((double)x3[4] + x3[5] + x3[6] + x3[7] - x3[0] - x3[1] - x3[2] - x3[3]));
+        eco[(size_t)e * 3 + 2] = (float)sqrt((double)(d * d));
+    }
+    {   // pressure point: elt_del[p+d] = -GNX.ppt(d,a) * (p_point weight * GDA.ppt)
+        const float gdap = (float)gp_geom(X, c_sh.Nxp, 8, 1, gnx);
+        const double temp_p = (double)(8.0f * gdap);
+        for(int a = 0; a < 8; a++)
+            for(int d = 0; d < 3; d++) elt_del[(size_t)e * 24 + 3 * a + d] = (float)(-gnx[d][a] * temp_p);
+    }
+}
+
+// MASS[node] = 1 / sum over its elements (ascending) of TWW   (float accumulation, Size_does_matter.c:718,739)
+__global__ void __launch_bounds__(128) bk_mass(const CcuGeom g, const double *__restrict__ TWWd, float *MASS)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    float m = 0.0f;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                m = (float)((double)m + TWWd[(size_t)e * 8 + LUT[k - ez][j - ex][i - ey] - 1]);     // float += double temp[node]
+            }
+        }
+    }
+    MASS[n] = (float)(1.0 / (double)m);
+}
+
+// ---------------------------------------------------------------- viscosity
+// visc_from_T (Viscosity_structures.c:491-) rheol 0/1/3 + visc_from_mat (:477) + min/max clip (:411-425)
+__global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscParams vp, const int *__restrict__ mat,
+                                               const float *__restrict__ T, float *EVI)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    const int l = mat[e] - 1;
+    const float tempa = vp.N0[l];
+    float TT[8];
+    for(int a = 1; a <= 8; a++) TT[a - 1] = T[elt_node(g, ey, ex, ez, a)];
+    for(int jj = 0; jj < 8; jj++)
+    {
+        float v;
+        if(!vp.tdepv) v = tempa;
+        else
+        {
+            float temp = 1.0e-32f;
+            for(int kk = 0; kk < 8; kk++) temp += fmaxf(0.0f, TT[kk]) * c_sh.Nv[8 * kk + jj];
+            if(vp.rheol == 0) v = (float)((double)tempa * exp((double)(vp.E[l] * (1.0f - temp))));
+            else if(vp.rheol == 1) v = (float)((double)tempa * exp((double)(vp.E[l] / (temp + vp.T[l]))));
+            else v = (float)((double)tempa * exp((double)(vp.E[l] * (vp.T[l] - temp))));      // rheol 3
+        }
+        if(vp.vmax && v > vp.max_value) v = vp.max_value;
+        if(vp.vmin && v < vp.min_value) v = vp.min_value;
+        EVI[(size_t)e * 8 + jj] = v;
+    }
+}
+
+// visc_from_gint_to_nodes (Nodal_mesh.c:583-615)
+__global__ void __launch_bounds__(128) bk_gint_to_nodes(const CcuGeom g, const float *__restrict__ EVI, const float *__restrict__ TWW,
+                                                         const float *__restrict__ MASS, float *VN)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    float v = 0.0f;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                double tv = 0.0;
+                for(int q = 0; q < 8; q++) tv += EVI[(size_t)e * 8 + q];
+                tv = tv / 8;
+                v = (float)((double)v + TWW[(size_t)e * 8 + LUT[k - ez][j - ex][i - ey] - 1] * tv);
+            }
+        }
+    }
+    VN[n] = v * MASS[n];
+}
+// project_scalar (Solver_multigrid.c:344-388): fine nodal field -> coarse nodal field
+__global__ void __launch_bounds__(128) bk_project_scalar(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ TWWc,
+                                                          const float *__restrict__ MASSc, const float *__restrict__ AU, float *AD)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= gc.nno) return;
+    const int K = n % gc.noz, J = (n / gc.noz) % gc.nox, I = n / (gc.noz * gc.nox);
+    const double weight = (double)1.0 / 8;
+    float ad = 0.0f;
+    for(int ey = I - 1; ey <= I; ey++)
+    {
+        if(ey < 0 || ey >= gc.ely) continue;
+        for(int ex = J - 1; ex <= J; ex++)
+        {
+            if(ex < 0 || ex >= gc.elx) continue;
+            for(int ez = K - 1; ez <= K; ez++)
+            {
+                if(ez < 0 || ez >= gc.elz) continue;
+                const int oy = I - ey, ox = J - ex, oz = K - ez;
+                const int el = ez + gc.elz * (ex + gc.elx * ey);
+                float average = 0.0f;
+                for(int q = 1; q <= 8; q++) average += AU[elt_node(gf, 2 * ey + oy, 2 * ex + ox, 2 * ez + oz, q)];
+                const float w = (float)(weight * average);
+                ad += w * TWWc[(size_t)el * 8 + LUT[oz][ox][oy] - 1];
+            }
+        }
+    }
+    AD[n] = ad * MASSc[n];
+}
+// visc_from_nodes_to_gint (Nodal_mesh.c:617-640)
+__global__ void __launch_bounds__(128) bk_nodes_to_gint(const CcuGeom g, const float *__restrict__ VN, float *EVI)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float vn[8];
+    for(int a = 1; a <= 8; a++) vn[a - 1] = VN[elt_node(g, ey, ex, ez, a)];
+    for(int i = 0; i < 8; i++)
+    {
+        double tv = 0.0;
+        for(int j = 0; j < 8; j++) tv += c_sh.Nv[8 * j + i] * vn[j];     // float * float
+        EVI[(size_t)e * 8 + i] = (float)tv;
+    }
+}
+
+// ---------------------------------------------------------------- element stiffness
+// get_elt_k (Element_calculations.c:133-293, CART3D :223-248): the 36 node-pair blocks a<=b of one
+// element, bdbmu[i][j], written SoA (pair*9 + 3*i + j) over the chunk's elements.
+__global__ void __launch_bounds__(64) bk_elt_k(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ EVI,
+                                              const int e_begin, const int e_count, double *blocks)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= e_count) return;
+    const int e = e_begin + t;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    float gn[8][3][8];        // [gauss point][d][node]
+    double W[8];
+    for(int k = 0; k < 8; k++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gn[k]);
+        W[k] = (double)(1.0f * gda * EVI[(size_t)e * 8 + k]);             // float*float*float
+    }
+    int pair = 0;
+    for(int a = 0; a < 8; a++)
+        for(int b = a; b < 8; b++, pair++)
+        {
+            double bd[3][3];
+            for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) bd[i][j] = 0.0;
+            for(int k = 0; k < 8; k++)
+                for(int j = 0; j < 3; j++)
+                    for(int i = 0; i < 3; i++)
+                        bd[i][j] += W[k] * gn[k][j][a] * gn[k][i][b];
+            double temp = 0.0;
+            for(int k = 0; k < 8; k++)
+                temp += W[k] * (gn[k][0][a] * gn[k][0][b] + gn[k][1][a] * gn[k][1][b] + gn[k][2][a] * gn[k][2][b]);   // float sum of float products
+            bd[0][0] += temp; bd[1][1] += temp; bd[2][2] += temp;
+            for(int i = 0; i < 3; i++)
+                for(int j = 0; j < 3; j++) blocks[(size_t)(pair * 9 + 3 * i + j) * e_count + t] = bd[i][j];
+        }
+}
+
+__host__ __device__ constexpr int pair_index(int a, int b) { return a * 8 - (a * (a - 1)) / 2 + (b - a); }   // a<=b, 0-based
+// fixed slot of the neighbour at (dy,dx,dz): 0 self, 1..13 = CCU_LO order, -1 upper neighbour
+__host__ __device__ constexpr int lo_slot(int dy, int dx, int dz)
+{
+    return (dy == 0 && dx == 0 && dz == 0) ? 0
+         : (dy == -1) ? (1 + (dx + 1) * 3 + (dz + 1))
+         : (dy == 0 && dx == -1) ? (10 + (dz + 1))
+         : (dy == 0 && dx == 0 && dz == -1) ? 13 : -1;
+}
+
+// construct_node_ks + build_diagonal_of_K + get_aug_k (Construct_arrays.c:359-535, Element_calculations.c:624,1127):
+// one thread per node gathers its <= 8 elements in ascending order; every half-matrix entry is a float
+// accumulator exactly as Eqn_k1-3 are; BI accumulates the (augmented) element diagonals in double.
+template <int OY, int OX, int OZ>
+__device__ __forceinline__ void node_gather_element(const CcuGeom &g, const int e_rel, const int e_count, const double *__restrict__ blocks,
+                                                    const float *__restrict__ gdel, const double visc_aug, const int use_aug,
+                                                    const unsigned char fn, const unsigned char *__restrict__ flags, const int i, const int j,
+                                                    const int k, float (&acc)[14][9], double (&diag)[3])
+{
+    constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    constexpr int OFFS[9][3] = CCU_OFFS_INIT;
+    constexpr int a = LUT[OZ][OX][OY] - 1;            // local index of this node in the element
+    const double w[3] = { (fn & CCU_F_VBX) ? 0.0 : 1.0, (fn & CCU_F_VBY) ? 0.0 : 1.0, (fn & CCU_F_VBZ) ? 0.0 : 1.0 };
+#pragma unroll
+    for(int b = 0; b < 8; b++)
+    {
+        const int dz = OFFS[b + 1][0] - OZ, dx = OFFS[b + 1][1] - OX, dy = OFFS[b + 1][2] - OY;
+        const int slot = lo_slot(dy, dx, dz);
+        if(slot < 0) continue;
+        const unsigned char fb = flags[ccu_sidx(g, i + dy, j + dx, k + dz)];
+        const double ww[3] = { (fb & CCU_F_VBX) ? 0.0 : 1.0, (fb & CCU_F_VBY) ? 0.0 : 1.0, (fb & CCU_F_VBZ) ? 0.0 : 1.0 };
+        const int pr = (a <= b) ? pair_index(a, b) : pair_index(b, a);
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+#pragma unroll
+            for(int cc = 0; cc < 3; cc++)
+            {
+                // elt_k[(a,r),(b,cc)]: stored block is bdbmu_{min,max}; transposed when a > b (:270-288)
+                double v = (a <= b) ? blocks[(size_t)(pr * 9 + 3 * r + cc) * e_count + e_rel] : blocks[(size_t)(pr * 9 + 3 * cc + r) * e_count + e_rel];
+                if(use_aug) v += visc_aug * gdel[3 * a + r] * gdel[3 * b + cc];
+                acc[slot][3 * r + cc] = (float)((double)acc[slot][3 * r + cc] + w[r] * ww[cc] * v);
+                if(slot == 0 && r == cc) diag[r] += v;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(64) bk_node_ks(const CcuGeom g, const int i_begin, const int i_end, const int ey_begin, const int e_count,
+                                                const double *__restrict__ blocks, const float *__restrict__ elt_del,
+                                                const float *__restrict__ EVI, const unsigned char *__restrict__ flags,
+                                                const int use_aug, const double augmented, float *K, double *BI)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = g.nox * g.noz;
+    if(t >= (i_end - i_begin) * plane) return;
+    const int i = i_begin + t / plane, rem = t % plane, j = rem / g.noz, k = rem % g.noz;
+    const int s = ccu_sidx(g, i, j, k);
+    const unsigned char fn = flags[s];
+    float acc[14][9];
+    double diag[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+    for(int q = 0; q < 14; q++)
+#pragma unroll
+        for(int r = 0; r < 9; r++) acc[q][r] = 0.0f;
+#define GATHER(OY, OX, OZ) { const int ey = i - OY, ex = j - OX, ez = k - OZ; \
+        if(ey >= 0 && ey < g.ely && ex >= 0 && ex < g.elx && ez >= 0 && ez < g.elz) { \
+            const int e = ez + g.elz * (ex + g.elx * ey); \
+            double va = 0.0; \
+            if(use_aug) { for(int q = 0; q < 8; q++) va += EVI[(size_t)e * 8 + q]; va = va / 8; va = va * augmented; } \
+            node_gather_element<OY, OX, OZ>(g, e - ey_begin * g.elx * g.elz, e_count, blocks, elt_del + (size_t)e * 24, va, use_aug, fn, flags, i, j, k, acc, diag); } }
+    // ascending element number: ey = i-1 first (OY = 1), then ex = j-1 (OX = 1), then ez = k-1 (OZ = 1)
+    GATHER(1, 1, 1) GATHER(1, 1, 0) GATHER(1, 0, 1) GATHER(1, 0, 0) GATHER(0, 1, 1) GATHER(0, 1, 0) GATHER(0, 0, 1) GATHER(0, 0, 0)
+#undef GATHER
+    const size_t NS = (size_t)g.NS;
+#pragma unroll
+    for(int q = 0; q < 14; q++)
+#pragma unroll
+        for(int r = 0; r < 9; r++) K[(size_t)(q * 9 + r) * NS + s] = acc[q][r];
+    for(int d = 0; d < 3; d++) BI[(size_t)d * NS + s] = 1.0 / diag[d];
+}
+
+// build_diagonal_of_Ahat / assemble_dAhatp_entry (Element_calculations.c:654-685, 771-824)
+__global__ void __launch_bounds__(128) bk_BPI(const CcuGeom g, const float *__restrict__ elt_del, const double *__restrict__ BI,
+                                              const int precondition, double *BPI)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    if(!precondition) { BPI[e] = 1.0; return; }
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    const float *gd = elt_del + (size_t)e * 24;
+    double gradP[24];
+    for(int a = 1; a <= 8; a++)
+    {
+        const int s = ccu_sidx(g, ey + c_OFFS[a][2], ex + c_OFFS[a][1], ez + c_OFFS[a][0]);
+        for(int d = 0; d < 3; d++) gradP[3 * (a - 1) + d] = 0.0 + BI[(size_t)d * g.NS + s] * gd[3 * (a - 1) + d];
+    }
+    double divU = 0.0;
+    for(int p = 0; p < 24; p++) divU += gd[p] * gradP[p];
+    BPI[e] = (divU != 0.0) ? 1.0 / divU : 1.0;
+}
+
+// assemble_forces + get_elt_f (Element_calculations.c:74-125, 989-1070), CART3D without imposed non-zero
+// velocities: F(3n+2) = sum over elements (ascending) of sum_j force_at_gs[j] N(a,j) gDA[j] w[j]; stripped.
+__global__ void __launch_bounds__(128) bk_forces(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ buoy,
+                                                 const unsigned char *__restrict__ flags, double *F)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    double f = 0.0;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int a = LUT[k - ez][j - ex][i - ey] - 1;
+                float X[3][8], gnx[3][8], force[8];
+                load_elt_coords(g, XX, ey, ex, ez, X);
+                for(int q = 1; q <= 8; q++) force[q - 1] = buoy[elt_node(g, ey, ex, ez, q)];
+                double ef = 0.0;
+                for(int q = 0; q < 8; q++)
+                {
+                    double fg = 0.0;
+                    for(int kk = 0; kk < 8; kk++) fg += force[kk] * c_sh.Nv[8 * kk + q];       // float * float
+                    const float gda = (float)gp_geom(X, c_sh.Nxv + q, 64, 8, gnx);
+                    ef += fg * c_sh.Nv[8 * a + q] * gda * 1.0f;
+                }
+                f += ef;
+            }
+        }
+    }
+    const int s = ccu_sidx(g, i, j, k);
+    const unsigned char fl = flags[s];
+    F[s] = 0.0;
+    F[(size_t)g.NS + s] = 0.0;
+    F[2 * (size_t)g.NS + s] = (fl & CCU_F_VBZ) ? 0.0 : f;
+}
+
+// device K -> reference layout Eqn_k1-3 (test / drop-in read-back)
+__global__ void bk_stiffness_to_ref(const CcuGeom g, const float *__restrict__ K, float *k1, float *k2, float *k3)
+{
+    const int LO[13][3] = CCU_LO_INIT;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    const size_t NS = (size_t)g.NS, base = (size_t)n * 42;
+    float *kk[3] = { k1 + base, k2 + base, k3 + base };
+    for(int q = 0; q < 42; q++) { kk[0][q] = 0.0f; kk[1][q] = 0.0f; kk[2][q] = 0.0f; }
+    for(int a = 0; a < 3; a++) for(int b = 0; b < 3; b++) kk[a][b] = K[(size_t)(a * 3 + b) * NS + s];
+    int rs = 0;
+    for(int q = 0; q < 13; q++)
+    {
+        const int ii = i + LO[q][0], jj = j + LO[q][1], kz = k + LO[q][2];
+        if(!(ii >= 0 && jj >= 0 && jj < g.nox && kz >= 0 && kz < g.noz)) continue;
+        rs++;
+        for(int a = 0; a < 3; a++) for(int b = 0; b < 3; b++) kk[a][3 * rs + b] = K[(size_t)((q + 1) * 9 + a * 3 + b) * NS + s];
+    }
+}
+__global__ void bk_vec_to_nat(const CcuGeom g, const double *__restrict__ dev, double *nat)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    for(int d = 0; d < 3; d++) nat[3 * (size_t)n + d] = dev[(size_t)d * g.NS + s];
+}
+
+// ================================================================= host side
+static bool g_tables_ready = false;
+static int ensure_tables(ccu_ctx *c)
+{
+    (void)c;
+    if(g_tables_ready) return 0;
+    ShapeTables t;
+    make_shape_tables(t);
+    CK(cudaMemcpyToSymbol(c_sh, &t, sizeof(t)));
+    g_tables_ready = true;
+    return 0;
+}
+
+int ccu_set_coordinates(ccu_ctx *c, int lev, const float *X1, const float *X2, const float *X3)
+{
+    if(ccu_check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    const size_t n = (size_t)L.g.nno;
+    if(!L.XX) CK(cudaMalloc(&L.XX, sizeof(float) * 3 * n));
+    CK(cudaMemcpyAsync(L.XX, X1, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.XX + n, X2, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.XX + 2 * n, X3, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    L.have_xx = true;
+    return 0;
+}
+
+int ccu_build_geometry(ccu_ctx *c)
+{
+    if(!c) FAIL("null context");
+    if(ensure_tables(c)) return 1;
+    for(int lev = c->cfg.levmin; lev <= c->cfg.levmax; lev++)
+    {
+        Level &L = c->L[lev];
+        if(!L.have_xx) FAIL("build_geometry: coordinates missing");
+        if(ccu_ensure_stage(c, sizeof(double) * 8 * (size_t)L.g.nel)) return 1;
+        LAUNCH(c, bk_elt_geometry, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.TWW, (double *)c->stage, L.eco, L.elt_del);
+        LAUNCH(c, bk_mass, cdiv(L.g.nno, 128), 128, L.g, (const double *)c->stage, L.MASS);
+        CK(cudaStreamSynchronize(c->st));
+        L.have_tw = true;
+    }
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int ccu_set_viscosity_law(ccu_ctx *c, int tdepv, int rheol, int num_mat, const float *N0, const float *E, const float *T, const float *Z,
+                          int vmin, float min_value, int vmax, float max_value, int smooth_cycles)
+{
+    if(!c) FAIL("null context");
+    if(num_mat < 1 || num_mat > 40) FAIL("bad num_mat");
+    if(tdepv && !(rheol == 0 || rheol == 1 || rheol == 3)) FAIL("viscosity law: only rheol 0, 1, 3 are implemented on the device");
+    if(smooth_cycles != 1) FAIL("project_viscosity: only visc_smooth_cycles=1 is implemented on the device");
+    CcuViscParams &v = c->visc;
+    v.tdepv = tdepv; v.rheol = rheol; v.num_mat = num_mat; v.vmin = vmin; v.vmax = vmax; v.min_value = min_value; v.max_value = max_value;
+    v.smooth_cycles = smooth_cycles;
+    for(int i = 0; i < num_mat; i++) { v.N0[i] = N0[i]; v.E[i] = E[i]; v.T[i] = T[i]; v.Z[i] = Z[i]; }
+    return 0;
+}
+
+int ccu_set_material(ccu_ctx *c, const int *mat)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(!c->mat) CK(cudaMalloc(&c->mat, sizeof(int) * (size_t)L.g.nel));
+    CK(cudaMemcpyAsync(c->mat, mat, sizeof(int) * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+static int ensure_nodal(ccu_ctx *c)
+{
+    Level &L = c->L[c->cfg.levmax];
+    if(!c->T) CK(cudaMalloc(&c->T, sizeof(float) * (size_t)L.g.nno));
+    if(!c->buoy) CK(cudaMalloc(&c->buoy, sizeof(float) * (size_t)L.g.nno));
+    if(!c->nodal_tmp) CK(cudaMalloc(&c->nodal_tmp, sizeof(float) * (size_t)L.g.nno));
+    if(!c->nodal_tmp2) CK(cudaMalloc(&c->nodal_tmp2, sizeof(float) * (size_t)L.g.nno));
+    for(int lev = c->cfg.levmin; lev <= c->cfg.levmax; lev++)
+        if(!c->L[lev].EVI) CK(cudaMalloc(&c->L[lev].EVI, sizeof(float) * 8 * (size_t)c->L[lev].g.nel));
+    return 0;
+}
+
+int ccu_set_temperature(ccu_ctx *c, const float *T)
+{
+    if(!c) FAIL("null context");
+    if(ensure_nodal(c)) return 1;
+    CK(cudaMemcpyAsync(c->T, T, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int ccu_set_element_viscosity(ccu_ctx *c, int lev, const float *EVI)
+{
+    if(ccu_check_lev(c, lev)) return 2;
+    if(ensure_nodal(c)) return 1;
+    Level &L = c->L[lev];
+    CK(cudaMemcpyAsync(L.EVI, EVI, sizeof(float) * 8 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    L.have_evi = true;
+    return 0;
+}
+
+// get_system_viscosity (Viscosity_structures.c:369) at the finest level from the resident temperature
+int ccu_get_system_viscosity(ccu_ctx *c)
+{
+    if(!c) FAIL("null context");
+    if(ensure_tables(c) || ensure_nodal(c)) return 1;
+    if(!c->mat) FAIL("get_system_viscosity: material groups missing");
+    Level &L = c->L[c->cfg.levmax];
+    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.EVI);
+    CK(cudaGetLastError());
+    L.have_evi = true;
+    return 0;
+}
+
+// construct_stiffness_B_matrix (Construct_arrays.c:834-889): project_viscosity, node_ks, BI, BPI on every level
+int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augmented, int precondition)
+{
+    if(!c) FAIL("null context");
+    if(ensure_tables(c) || ensure_nodal(c)) return 1;
+    const int levmax = c->cfg.levmax, levmin = c->cfg.levmin;
+    if(!c->L[levmax].have_evi) FAIL("construct_stiffness_B_matrix: finest-level viscosity missing");
+    // project_viscosity, visc_smooth_cycles == 1 (Solver_multigrid.c:449-454)
+    for(int lv = levmax; lv > levmin; lv--)
+    {
+        Level &Lf = c->L[lv], &Lc = c->L[lv - 1];
+        if(!Lf.have_tw || !Lc.have_tw) FAIL("construct_stiffness_B_matrix: geometry not built");
+        LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, Lf.MASS, c->nodal_tmp);
+        LAUNCH(c, bk_project_scalar, cdiv(Lc.g.nno, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, c->nodal_tmp, c->nodal_tmp2);
+        LAUNCH(c, bk_nodes_to_gint, cdiv(Lc.g.nel, 128), 128, Lc.g, c->nodal_tmp2, Lc.EVI);
+        Lc.have_evi = true;
+    }
+    // scratch for element blocks: chunks of node planes, budget ~3 GB
+    const size_t budget_elems = ((size_t)3 << 30) / (324 * sizeof(double));
+    for(int lev = levmax; lev >= levmin; lev--)
+    {
+        Level &L = c->L[lev];
+        if(!L.have_flags || !L.have_xx) FAIL("construct_stiffness_B_matrix: flags/coordinates missing");
+        const CcuGeom &g = L.g;
+        const size_t per_plane = (size_t)g.elx * g.elz;
+        int planes = (int)(budget_elems / per_plane);
+        if(planes < 2) planes = 2;
+        if(planes > g.ely) planes = g.ely;
+        const size_t need = per_plane * planes;
+        if(need > c->eltK_elems)
+        {
+            if(c->eltK) cudaFree(c->eltK);
+            c->eltK = nullptr; c->eltK_elems = 0;
+            CK(cudaMalloc(&c->eltK, sizeof(double) * 324 * need));
+            c->eltK_elems = need;
+        }
+        // node planes [i0, i1) need element planes [max(i0-1,0), min(i1, ely))
+        int i0 = 0;
+        while(i0 < g.noy)
+        {
+            const int ey0 = i0 > 0 ? i0 - 1 : 0;
+            int ey1 = ey0 + planes; if(ey1 > g.ely) ey1 = g.ely;
+            int i1 = (ey1 == g.ely) ? g.noy : ey1;          // nodes of plane ey1 would need element plane ey1
+            const int e_count = (int)(per_plane * (ey1 - ey0));
+            LAUNCH(c, bk_elt_k, cdiv(e_count, 64), 64, g, L.XX, L.EVI, (int)(per_plane * ey0), e_count, c->eltK);
+            const size_t nn = (size_t)(i1 - i0) * g.nox * g.noz;
+            LAUNCH(c, bk_node_ks, cdiv(nn, 64), 64, g, i0, i1, ey0, e_count, c->eltK, L.elt_del, L.EVI, L.flags, augmented_Lagr, augmented, L.K, L.BI);
+            i0 = i1;
+        }
+        LAUNCH(c, bk_BPI, cdiv(g.nel, 128), 128, g, L.elt_del, L.BI, precondition, L.BPI);
+        L.have_K = true; L.have_p = true;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// assemble_forces (Element_calculations.c:74): buoyancy[nno] -> resident F (CCU_VEC_F); optional host copy
+int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_tables(c) || ensure_nodal(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    if(!L.have_xx || !L.have_flags) FAIL("assemble_forces: coordinates/flags missing");
+    if(buoyancy) CK(cudaMemcpyAsync(c->buoy, buoyancy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, bk_forces, cdiv(L.g.nno, 128), 128, L.g, L.XX, c->buoy, L.flags, L.vec[CCU_VEC_F]);
+    if(F_out)
+    {
+        if(ccu_ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
+        LAUNCH(c, bk_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, L.vec[CCU_VEC_F], (double *)c->stage);
+        CK(cudaMemcpyAsync(F_out, c->stage, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ---- read-back in the reference's layouts (tests, drop-in diagnostics)
+int ccu_get_stiffness(ccu_ctx *c, int lev, float *k1, float *k2, float *k3, double *BI)
+{
+    if(ccu_check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    const size_t n42 = (size_t)L.g.nno * 42;
+    if(ccu_ensure_stage(c, sizeof(float) * 3 * n42 + sizeof(double) * L.g.neq)) return 1;
+    float *s = (float *)c->stage;
+    LAUNCH(c, bk_stiffness_to_ref, cdiv(L.g.nno, 128), 128, L.g, L.K, s, s + n42, s + 2 * n42);
+    CK(cudaMemcpyAsync(k1, s, sizeof(float) * n42, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(k2, s + n42, sizeof(float) * n42, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(k3, s + 2 * n42, sizeof(float) * n42, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if(BI)
+    {
+        double *sb = (double *)c->stage;
+        LAUNCH(c, bk_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, L.BI, sb);
+        CK(cudaMemcpyAsync(BI, sb, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+    }
+    return 0;
+}
+
+int ccu_get_level_array(ccu_ctx *c, int lev, int which, void *out)
+{
+    if(ccu_check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    const void *src = nullptr; size_t bytes = 0;
+    switch(which)
+    {
+    case CCU_ARR_TWW: src = L.TWW; bytes = sizeof(float) * 8 * (size_t)L.g.nel; break;
+    case CCU_ARR_MASS: src = L.MASS; bytes = sizeof(float) * (size_t)L.g.nno; break;
+    case CCU_ARR_ECO_SIZE: src = L.eco; bytes = sizeof(float) * 3 * (size_t)L.g.nel; break;
+    case CCU_ARR_ELT_DEL: src = L.elt_del; bytes = sizeof(float) * 24 * (size_t)L.g.nel; break;
+    case CCU_ARR_BPI: src = L.BPI; bytes = sizeof(double) * (size_t)L.g.npno; break;
+    case CCU_ARR_EVI: src = L.EVI; bytes = sizeof(float) * 8 * (size_t)L.g.nel; break;
+    default: FAIL("get_level_array: unknown array id");
+    }
+    if(!src) FAIL("get_level_array: array not allocated");
+    CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}

@@ -1,0 +1,68 @@
+// ccu_ctx.cuh -- device context shared by the translation units of libcitcomcu_b200.so
+#pragma once
+#include "../../include/citcomcu_b200.h"
+#include "ccu_layout.cuh"
+#include <cuda_runtime.h>
+#include <string>
+
+extern thread_local std::string g_ccu_err;
+
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+    g_ccu_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__); return 1; } } while(0)
+#define FAIL(msg) do { g_ccu_err = (msg); return 2; } while(0)
+
+enum { S_DOT0 = 0, S_DOT1, S_DOT2, S_R1Z1, S_R0Z0, S_S2AH, S_VDOTV, S_PDOTP, S_AHAH, S_S2S2, S_U1U1, S_TMP, S_ONE, S_COUNT = 32 };
+
+// viscosity law parameters (E->viscosity.*, Viscosity_structures.c:57-326)
+struct CcuViscParams
+{
+    int rheol = 0, tdepv = 0, num_mat = 1, vmin = 0, vmax = 0, smooth_cycles = 1;
+    float N0[40] = { 1.0f }, E[40] = { 0 }, T[40] = { 0 }, Z[40] = { 0 };
+    float min_value = 0, max_value = 0;
+};
+
+struct Level
+{
+    CcuGeom g;
+    float *K = nullptr;
+    double *BI = nullptr;
+    unsigned char *flags = nullptr;
+    float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
+    double *BPI = nullptr;
+    double *vec[CCU_VEC_COUNT] = { nullptr };
+    // operator construction (ccu_build.cu)
+    float *XX = nullptr;          // [3][nno] node coordinates, natural order (E->XX[lev][1..3])
+    float *EVI = nullptr;         // [nel*8] viscosity at Gauss points
+    unsigned *node = nullptr;     // [nno] raw NODE flags, natural order
+    bool have_K = false, have_flags = false, have_tw = false, have_p = false, have_xx = false, have_evi = false;
+    size_t vlen() const { return 3 * (size_t)g.NS; }
+};
+
+struct ccu_ctx
+{
+    ccu_config cfg;
+    cudaStream_t st = 0;
+    Level L[CCU_MAX_LEVELS];
+    double *scal = nullptr;        // device scalars
+    double *partial = nullptr;     // dot partials
+    void *stage = nullptr;         // upload/download staging
+    size_t stage_bytes = 0;
+    // finest-level Uzawa work space (solve_Ahat_p_fhat's statics, Stokes_flow_Incomp.c:325-336)
+    double *uzAh = nullptr, *uzU1 = nullptr;
+    double *P = nullptr, *r0 = nullptr, *r1 = nullptr, *r2 = nullptr, *z0 = nullptr, *z1 = nullptr, *s1 = nullptr, *s2 = nullptr, *pAh = nullptr;
+    // operator construction state
+    CcuViscParams visc;
+    int *mat = nullptr;            // [nel] material group per element (E->mat), finest level
+    float *T = nullptr;            // [nno] temperature, natural order, finest level
+    float *buoy = nullptr;         // [nno]
+    float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
+    double *eltK = nullptr;        // element-block scratch for the stiffness build
+    size_t eltK_elems = 0;
+    long long launches = 0;
+};
+
+#define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->st>>>(__VA_ARGS__); (ctx)->launches++; } while(0)
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+int ccu_ensure_stage(ccu_ctx *c, size_t bytes);
+int ccu_check_lev(ccu_ctx *c, int lev);

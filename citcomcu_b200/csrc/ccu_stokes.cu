@@ -3,7 +3,7 @@
 // kernels of ccu_kernels.cuh.  Scalars of the iteration (dot products, line-search alpha, CG alpha
 // and delta) stay in device memory; the host reads back only the convergence monitors the
 // reference's control flow branches on.
-#include "../../include/citcomcu_b200.h"
+#include "ccu_ctx.cuh"
 #include "ccu_kernels.cuh"
 #include <cmath>
 #include <cstdio>
@@ -12,49 +12,11 @@
 #include <string>
 #include <vector>
 
-static thread_local std::string g_err;
-const char *ccu_last_error(void) { return g_err.c_str(); }
+thread_local std::string g_ccu_err;
+const char *ccu_last_error(void) { return g_ccu_err.c_str(); }
 
-#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
-    g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__); return 1; } } while(0)
-#define FAIL(msg) do { g_err = (msg); return 2; } while(0)
 
-enum { S_DOT0 = 0, S_DOT1, S_DOT2, S_R1Z1, S_R0Z0, S_S2AH, S_VDOTV, S_PDOTP, S_AHAH, S_S2S2, S_U1U1, S_TMP, S_ONE, S_COUNT = 32 };
-
-struct Level
-{
-    CcuGeom g;
-    float *K = nullptr;
-    double *BI = nullptr;
-    unsigned char *flags = nullptr;
-    float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
-    double *BPI = nullptr;
-    double *vec[CCU_VEC_COUNT] = { nullptr };
-    bool have_K = false, have_flags = false, have_tw = false, have_p = false;
-    CcuLevelDev dev() const { return CcuLevelDev{ g, K, BI, flags, MASS, TWW, eco, elt_del, BPI }; }
-    size_t vlen() const { return 3 * (size_t)g.NS; }
-};
-
-struct ccu_ctx
-{
-    ccu_config cfg;
-    cudaStream_t st = 0;
-    Level L[CCU_MAX_LEVELS];
-    double *scal = nullptr;        // device scalars
-    double *partial = nullptr;     // dot partials
-    void *stage = nullptr;         // upload/download staging
-    size_t stage_bytes = 0;
-    // finest-level Uzawa work space (solve_Ahat_p_fhat's statics, Stokes_flow_Incomp.c:325-336)
-    double *uzAh = nullptr, *uzU1 = nullptr;
-    double *P = nullptr, *r0 = nullptr, *r1 = nullptr, *r2 = nullptr, *z0 = nullptr, *z1 = nullptr, *s1 = nullptr, *s2 = nullptr, *pAh = nullptr;
-    long long launches = 0;
-};
-
-#define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->st>>>(__VA_ARGS__); (ctx)->launches++; } while(0)
-
-static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
-
-static int ensure_stage(ccu_ctx *c, size_t bytes)
+int ccu_ensure_stage(ccu_ctx *c, size_t bytes)
 {
     if(bytes <= c->stage_bytes) return 0;
     if(c->stage) cudaFree(c->stage);
@@ -64,7 +26,7 @@ static int ensure_stage(ccu_ctx *c, size_t bytes)
     return 0;
 }
 
-static int check_lev(ccu_ctx *c, int lev)
+int ccu_check_lev(ccu_ctx *c, int lev)
 {
     if(!c) FAIL("null context");
     if(lev < c->cfg.levmin || lev > c->cfg.levmax) FAIL("level out of range");
@@ -99,6 +61,8 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
         CK(cudaMalloc(&L.MASS, sizeof(float) * L.g.nno));
         CK(cudaMalloc(&L.TWW, sizeof(float) * 8 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.eco, sizeof(float) * 3 * (size_t)L.g.nel));
+        CK(cudaMalloc(&L.elt_del, sizeof(float) * 24 * (size_t)L.g.nel));
+        CK(cudaMalloc(&L.BPI, sizeof(double) * (size_t)L.g.npno));
         const int nvec = (lev == cfg->levmax) ? CCU_VEC_COUNT : CCU_VEC_U;   // U, F, T* only at the top level
         for(int v = 0; v < nvec; v++)
         {
@@ -109,8 +73,6 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     {
         Level &L = c->L[cfg->levmax];
         const size_t NS = (size_t)L.g.NS, np = (size_t)L.g.npno;
-        CK(cudaMalloc(&L.elt_del, sizeof(float) * 24 * np));
-        CK(cudaMalloc(&L.BPI, sizeof(double) * np));
         CK(cudaMalloc(&c->uzAh, sizeof(double) * 3 * NS)); CK(cudaMemsetAsync(c->uzAh, 0, sizeof(double) * 3 * NS, c->st));
         CK(cudaMalloc(&c->uzU1, sizeof(double) * 3 * NS)); CK(cudaMemsetAsync(c->uzU1, 0, sizeof(double) * 3 * NS, c->st));
         double **pv[] = { &c->P, &c->r0, &c->r1, &c->r2, &c->z0, &c->z1, &c->s1, &c->s2, &c->pAh };
@@ -132,8 +94,10 @@ void ccu_destroy(ccu_ctx *c)
     {
         Level &L = c->L[lev];
         cudaFree(L.K); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.BPI);
+        cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node);
         for(auto v : L.vec) cudaFree(v);
     }
+    cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
     cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
@@ -146,9 +110,9 @@ long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
 // ------------------------------------------------------------------ uploads
 int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
-    if(ensure_stage(c, sizeof(unsigned) * L.g.nno)) return 1;
+    if(ccu_ensure_stage(c, sizeof(unsigned) * L.g.nno)) return 1;
     CK(cudaMemcpyAsync(c->stage, node, sizeof(unsigned) * L.g.nno, cudaMemcpyHostToDevice, c->st));
     LAUNCH(c, ccu_k_flags_to_dev, cdiv(L.g.nno, 256), 256, L.g, (const unsigned *)c->stage, L.flags);
     CK(cudaStreamSynchronize(c->st));
@@ -158,14 +122,14 @@ int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
 
 static int vec_h2d(ccu_ctx *c, Level &L, const double *host, double *dev)
 {
-    if(ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
+    if(ccu_ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
     CK(cudaMemcpyAsync(c->stage, host, sizeof(double) * L.g.neq, cudaMemcpyHostToDevice, c->st));
     LAUNCH(c, ccu_k_vec_to_dev, cdiv(L.g.nno, 256), 256, L.g, (const double *)c->stage, dev);
     return 0;
 }
 static int vec_d2h(ccu_ctx *c, Level &L, const double *dev, double *host)
 {
-    if(ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
+    if(ccu_ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
     LAUNCH(c, ccu_k_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, dev, (double *)c->stage);
     CK(cudaMemcpyAsync(host, c->stage, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
@@ -174,10 +138,10 @@ static int vec_d2h(ccu_ctx *c, Level &L, const double *dev, double *host)
 
 int ccu_set_stiffness(ccu_ctx *c, int lev, const float *k1, const float *k2, const float *k3, const double *BI)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     const size_t n42 = (size_t)L.g.nno * 42;
-    if(ensure_stage(c, sizeof(float) * 3 * n42)) return 1;
+    if(ccu_ensure_stage(c, sizeof(float) * 3 * n42)) return 1;
     float *s = (float *)c->stage;
     CK(cudaMemcpyAsync(s, k1, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(s + n42, k2, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
@@ -192,8 +156,7 @@ int ccu_set_stiffness(ccu_ctx *c, int lev, const float *k1, const float *k2, con
 
 int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double *BPI)
 {
-    if(check_lev(c, lev)) return 2;
-    if(lev != c->cfg.levmax) return 0;          // only the finest level's div/grad/BPI are on the hot path
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     CK(cudaMemcpyAsync(L.elt_del, elt_del, sizeof(float) * 24 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.BPI, BPI, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
@@ -204,7 +167,7 @@ int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double
 
 int ccu_set_transfer_weights(ccu_ctx *c, int lev, const float *TWW, const float *MASS, const float *eco)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     CK(cudaMemcpyAsync(L.TWW, TWW, sizeof(float) * 8 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.MASS, MASS, sizeof(float) * L.g.nno, cudaMemcpyHostToDevice, c->st));
@@ -364,7 +327,7 @@ static int d_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, i
         if(read_scal(c, S_DOT0, 1, &rr)) return 1;
         residual = sqrt(rr / gneq);
         count++;
-        if(!(residual == residual) || count > 500) { g_err = "solve_del2_u: multigrid diverged or stalled"; return 3; }
+        if(!(residual == residual) || count > 500) { g_ccu_err = "solve_del2_u: multigrid diverged or stalled"; return 3; }
     }
     if(cycles_out) *cycles_out = count;
     return 0;
@@ -470,7 +433,7 @@ static double *vecp(ccu_ctx *c, int lev, int v)
 
 int ccu_vec_upload(ccu_ctx *c, int lev, int v, const double *host)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     VEC(p, lev, v);
     if(vec_h2d(c, c->L[lev], host, p)) return 1;
     CK(cudaStreamSynchronize(c->st));
@@ -478,7 +441,7 @@ int ccu_vec_upload(ccu_ctx *c, int lev, int v, const double *host)
 }
 int ccu_vec_download(ccu_ctx *c, int lev, int v, double *host)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     VEC(p, lev, v);
     return vec_d2h(c, c->L[lev], p, host);
 }
@@ -498,7 +461,7 @@ int ccu_pvec_download(ccu_ctx *c, double *host)
 }
 int ccu_dev_matvec(ccu_ctx *c, int lev, int vu, int vAu, int strip)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     VEC(u, lev, vu); VEC(Au, lev, vAu);
     d_matvec(c, c->L[lev], u, Au, strip);
     CK(cudaGetLastError());
@@ -506,7 +469,7 @@ int ccu_dev_matvec(ccu_ctx *c, int lev, int vu, int vAu, int strip)
 }
 int ccu_dev_gauss_seidel(ccu_ctx *c, int lev, int vd, int vF, int vAd, int cycles, int guess)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     VEC(d0, lev, vd); VEC(F, lev, vF); VEC(Ad, lev, vAd);
     d_gauss_seidel(c, c->L[lev], d0, F, Ad, cycles, guess);
     CK(cudaGetLastError());
@@ -514,7 +477,7 @@ int ccu_dev_gauss_seidel(ccu_ctx *c, int lev, int vd, int vF, int vAd, int cycle
 }
 int ccu_dev_relax_sweeps(ccu_ctx *c, int lev, int vd, int vF, int cycles)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     VEC(d0, lev, vd); VEC(F, lev, vF);
     d_relax_sweeps(c, c->L[lev], d0, F, cycles);
     CK(cudaGetLastError());
@@ -540,7 +503,7 @@ int ccu_dev_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *res
 // ------------------------------------------------------------------ C ABI: host-vector forms
 int ccu_n_assemble_del2_u(ccu_ctx *c, int lev, const double *u, double *Au, int strip)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     if(vec_h2d(c, L, u, L.vec[CCU_VEC_VEL])) return 1;
     d_matvec(c, L, L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_AU], strip);
@@ -548,7 +511,7 @@ int ccu_n_assemble_del2_u(ccu_ctx *c, int lev, const double *u, double *Au, int 
 }
 int ccu_gauss_seidel(ccu_ctx *c, int lev, double *d0, const double *F, double *Ad, int cycles, int guess)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     if(guess && vec_h2d(c, L, d0, L.vec[CCU_VEC_VEL])) return 1;
     if(vec_h2d(c, L, F, L.vec[CCU_VEC_RHS])) return 1;
@@ -558,21 +521,21 @@ int ccu_gauss_seidel(ccu_ctx *c, int lev, double *d0, const double *F, double *A
 }
 int ccu_project_vector(ccu_ctx *c, int lev, const double *AU, double *AD)
 {
-    if(check_lev(c, lev) || check_lev(c, lev - 1)) return 2;
+    if(ccu_check_lev(c, lev) || ccu_check_lev(c, lev - 1)) return 2;
     if(vec_h2d(c, c->L[lev], AU, c->L[lev].vec[CCU_VEC_RES])) return 1;
     d_project(c, lev, c->L[lev].vec[CCU_VEC_RES], c->L[lev - 1].vec[CCU_VEC_RHS], 0);
     return vec_d2h(c, c->L[lev - 1], c->L[lev - 1].vec[CCU_VEC_RHS], AD);
 }
 int ccu_interp_vector(ccu_ctx *c, int lev, const double *AD, double *AU)
 {
-    if(check_lev(c, lev) || check_lev(c, lev + 1)) return 2;
+    if(ccu_check_lev(c, lev) || ccu_check_lev(c, lev + 1)) return 2;
     if(vec_h2d(c, c->L[lev], AD, c->L[lev].vec[CCU_VEC_VEL])) return 1;
     d_interp(c, lev, c->L[lev].vec[CCU_VEC_VEL], c->L[lev + 1].vec[CCU_VEC_DEL_VEL], 0);
     return vec_d2h(c, c->L[lev + 1], c->L[lev + 1].vec[CCU_VEC_DEL_VEL], AU);
 }
 int ccu_strip_bcs_from_residual(ccu_ctx *c, int lev, double *res)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     if(vec_h2d(c, L, res, L.vec[CCU_VEC_RES])) return 1;
     d_strip(c, L, L.vec[CCU_VEC_RES]);
@@ -580,7 +543,7 @@ int ccu_strip_bcs_from_residual(ccu_ctx *c, int lev, double *res)
 }
 int ccu_assemble_div_u(ccu_ctx *c, int lev, const double *U, double *divU)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     if(lev != c->cfg.levmax) FAIL("div_u: only the finest level is resident");
     Level &L = c->L[lev];
     if(vec_h2d(c, L, U, L.vec[CCU_VEC_VEL])) return 1;
@@ -591,7 +554,7 @@ int ccu_assemble_div_u(ccu_ctx *c, int lev, const double *U, double *divU)
 }
 int ccu_assemble_grad_p(ccu_ctx *c, int lev, const double *P, double *gradP)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     if(lev != c->cfg.levmax) FAIL("grad_p: only the finest level is resident");
     Level &L = c->L[lev];
     CK(cudaMemcpyAsync(c->pAh, P, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
@@ -600,7 +563,7 @@ int ccu_assemble_grad_p(ccu_ctx *c, int lev, const double *P, double *gradP)
 }
 int ccu_global_vdot(ccu_ctx *c, int lev, const double *A, const double *B, double *out)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     if(vec_h2d(c, L, A, L.vec[CCU_VEC_VEL])) return 1;
     CK(cudaStreamSynchronize(c->st));
@@ -610,7 +573,7 @@ int ccu_global_vdot(ccu_ctx *c, int lev, const double *A, const double *B, doubl
 }
 int ccu_global_pdot(ccu_ctx *c, int lev, const double *A, const double *B, double *out)
 {
-    if(check_lev(c, lev)) return 2;
+    if(ccu_check_lev(c, lev)) return 2;
     if(lev != c->cfg.levmax) FAIL("pdot: only the finest level is resident");
     const size_t np = (size_t)c->L[lev].g.npno;
     CK(cudaMemcpyAsync(c->pAh, A, sizeof(double) * np, cudaMemcpyHostToDevice, c->st));

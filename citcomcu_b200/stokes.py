@@ -113,6 +113,67 @@ class StokesContext:
         lm = self.levmax
         self.set_pressure_ops(lm, src[f"L{lm}_elt_del"], src[f"L{lm}_BPI"])
 
+    # -- operator construction on the device
+    def set_coordinates(self, lev, X1, X2, X3):
+        xs = [np.ascontiguousarray(x, dtype=np.float32) for x in (X1, X2, X3)]
+        for x in xs:
+            assert x.size == self.nno(lev)
+        check(self.lib.ccu_set_coordinates(self._ctx, lev, *[x.ctypes.data_as(C.c_void_p) for x in xs]))
+
+    def build_geometry(self):
+        check(self.lib.ccu_build_geometry(self._ctx))
+
+    def set_viscosity_law(self, tdepv, rheol, N0, E, T, Z, vmin=0, min_value=0.0, vmax=0, max_value=0.0, smooth_cycles=1):
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (N0, E, T, Z)]
+        check(self.lib.ccu_set_viscosity_law(self._ctx, int(tdepv), int(rheol), len(arrs[0]),
+                                             *[a.ctypes.data_as(C.c_void_p) for a in arrs], int(vmin), C.c_float(min_value),
+                                             int(vmax), C.c_float(max_value), int(smooth_cycles)))
+
+    def set_material(self, mat):
+        m = np.ascontiguousarray(mat, dtype=np.int32)
+        assert m.size == self.nel(self.levmax)
+        check(self.lib.ccu_set_material(self._ctx, m.ctypes.data_as(C.c_void_p)))
+
+    def set_temperature(self, T):
+        t = np.ascontiguousarray(T, dtype=np.float32)
+        assert t.size == self.nno(self.levmax)
+        check(self.lib.ccu_set_temperature(self._ctx, t.ctypes.data_as(C.c_void_p)))
+
+    def set_element_viscosity(self, lev, EVI):
+        e = np.ascontiguousarray(EVI, dtype=np.float32)
+        assert e.size == 8 * self.nel(lev)
+        check(self.lib.ccu_set_element_viscosity(self._ctx, lev, e.ctypes.data_as(C.c_void_p)))
+
+    def get_system_viscosity(self):
+        check(self.lib.ccu_get_system_viscosity(self._ctx))
+
+    def construct_stiffness_B_matrix(self, augmented_Lagr=1, augmented=1.0e3, precondition=1):
+        check(self.lib.ccu_construct_stiffness_B_matrix(self._ctx, int(augmented_Lagr), C.c_double(augmented), int(precondition)))
+
+    def assemble_forces(self, buoyancy=None, want_host=True):
+        b = None if buoyancy is None else np.ascontiguousarray(buoyancy, dtype=np.float32)
+        out = np.empty(self.neq(self.levmax)) if want_host else None
+        check(self.lib.ccu_assemble_forces(self._ctx, None if b is None else b.ctypes.data_as(C.c_void_p),
+                                           None if out is None else out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_stiffness(self, lev):
+        n = self.nno(lev) * 42
+        ks = [np.empty(n, dtype=np.float32) for _ in range(3)]
+        BI = np.empty(self.neq(lev))
+        check(self.lib.ccu_get_stiffness(self._ctx, lev, *[k.ctypes.data_as(C.c_void_p) for k in ks], BI.ctypes.data_as(C.c_void_p)))
+        return ks[0], ks[1], ks[2], BI
+
+    _ARR = dict(TWW=(0, np.float32, lambda s, l: 8 * s.nel(l)), MASS=(1, np.float32, lambda s, l: s.nno(l)),
+                eco_size=(2, np.float32, lambda s, l: 3 * s.nel(l)), elt_del=(3, np.float32, lambda s, l: 24 * s.nel(l)),
+                BPI=(4, np.float64, lambda s, l: s.nel(l)), EVI=(5, np.float32, lambda s, l: 8 * s.nel(l)))
+
+    def get_level_array(self, lev, name):
+        idx, dt, size = self._ARR[name]
+        out = np.empty(size(self, lev), dtype=dt)
+        check(self.lib.ccu_get_level_array(self._ctx, lev, idx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # -- reference-named operators (host vectors in/out)
     def n_assemble_del2_u(self, u, level, strip_bcs=1):
         u, up = _f64(u)

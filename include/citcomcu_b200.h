@@ -59,6 +59,29 @@ int ccu_set_pressure_ops(ccu_ctx *ctx, int lev, const float *elt_del /*[nel*24]*
 int ccu_set_transfer_weights(ccu_ctx *ctx, int lev, const float *TWW /*[nel*8]*/, const float *MASS /*[nno]*/,
                              const float *eco_size /*[nel*3]*/);
 
+/* ---- operator construction on the device (rebuilt every `update_every_steps` when TDEPV) ---- */
+/* node coordinates E->XX[lev][1..3]+1 (x, y, z), natural node order (Nodal_mesh.c:53 node_locations) */
+int ccu_set_coordinates(ccu_ctx *ctx, int lev, const float *X1, const float *X2, const float *X3 /*[nno] each*/);
+/* mass_matrix (Size_does_matter.c:618): TWW, MASS, ECO.size; construct_elt_gs / get_elt_g (Element_calculations.c:831): elt_del; all levels */
+int ccu_build_geometry(ccu_ctx *ctx);
+/* E->viscosity.{TDEPV,RHEOL,num_mat,N0,E,T,Z,MIN,min_value,MAX,max_value,smooth_cycles} (Viscosity_structures.c:57-326) */
+int ccu_set_viscosity_law(ccu_ctx *ctx, int tdepv, int rheol, int num_mat, const float *N0, const float *E, const float *T,
+                          const float *Z, int vmin, float min_value, int vmax, float max_value, int smooth_cycles);
+int ccu_set_material(ccu_ctx *ctx, const int *mat /*[nel] = E->mat+1*/);
+int ccu_set_temperature(ccu_ctx *ctx, const float *T /*[nno] = E->T+1*/);
+int ccu_set_element_viscosity(ccu_ctx *ctx, int lev, const float *EVI /*[nel*8] = E->EVI[lev]+1*/);
+/* get_system_viscosity (Viscosity_structures.c:369): EVI[levmax] from the resident temperature / material groups */
+int ccu_get_system_viscosity(ccu_ctx *ctx);
+/* construct_stiffness_B_matrix (Construct_arrays.c:834): project_viscosity, get_elt_k + get_aug_k -> node-stored K,
+ * BI (build_diagonal_of_K), BPI (build_diagonal_of_Ahat) on every level, from the resident EVI[levmax] */
+int ccu_construct_stiffness_B_matrix(ccu_ctx *ctx, int augmented_Lagr, double augmented, int precondition);
+/* assemble_forces (Element_calculations.c:74): buoyancy[nno] (NULL = resident) -> resident F (CCU_VEC_F); F_out optional */
+int ccu_assemble_forces(ccu_ctx *ctx, const float *buoyancy, double *F_out /*[neq] or NULL*/);
+/* read-back in the reference's layouts (tests / drop-in diagnostics) */
+int ccu_get_stiffness(ccu_ctx *ctx, int lev, float *eqn_k1, float *eqn_k2, float *eqn_k3 /*[nno*42]*/, double *BI /*[neq] or NULL*/);
+enum { CCU_ARR_TWW = 0, CCU_ARR_MASS = 1, CCU_ARR_ECO_SIZE = 2, CCU_ARR_ELT_DEL = 3, CCU_ARR_BPI = 4, CCU_ARR_EVI = 5 };
+int ccu_get_level_array(ccu_ctx *ctx, int lev, int which, void *out);
+
 /* ---- hot-path operators, host vectors in / out (drop-in granularity of SURVEY.md 8b) ---- */
 /* n_assemble_del2_u / assemble_del2_u (Element_calculations.c:552, :480) */
 int ccu_n_assemble_del2_u(ccu_ctx *ctx, int lev, const double *u, double *Au, int strip_bcs);

@@ -106,6 +106,7 @@ static void dump_fields(struct All_variables *E, const char *tag)
     char nm[200];
     const int nno = E->lmesh.nno, neq = E->lmesh.neq, npno = E->lmesh.npno, nel = E->lmesh.nel;
     int d;
+    snprintf(nm, sizeof nm, "%s_mat", tag); DUMP_I32(nm, E->mat + 1, nel);
     snprintf(nm, sizeof nm, "%s_F", tag); DUMP_F64(nm, E->F, neq);
     snprintf(nm, sizeof nm, "%s_U", tag); DUMP_F64(nm, E->U, neq);
     snprintf(nm, sizeof nm, "%s_P", tag); DUMP_F64(nm, E->P + 1, npno);

@@ -1,0 +1,72 @@
+"""GPU tests: operator construction on the device vs the arrays the reference's host code builds
+(mass_matrix, get_elt_g, get_system_viscosity, project_viscosity, construct_node_ks,
+build_diagonal_of_Ahat, assemble_forces).  Bar: bit-exact (integer-like comparison of the fp32
+coefficient arrays); `exp` in the viscosity law may differ from glibc in the last double bit, so
+EVI / K allow a vanishing fraction of 1-ulp fp32 differences and report it."""
+import numpy as np
+import pytest
+
+from conftest import get_case, CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def build_ctx(d, tdepv, viscE):
+    from citcomcu_b200.stokes import StokesContext
+    ctl = d.control()
+    nox, noy, noz = {}, {}, {}
+    for lev in range(ctl["levmin"], ctl["levmax"] + 1):
+        dm = d.dims(lev)
+        nox[lev], noy[lev], noz[lev] = dm["nox"], dm["noy"], dm["noz"]
+    ctx = StokesContext(ctl["levmin"], ctl["levmax"], nox, noy, noz, v_steps_low=ctl["v_steps_low"],
+                        v_steps_high=ctl["v_steps_high"], down_heavy=ctl["down_heavy"], up_heavy=ctl["up_heavy"],
+                        mg_cycle=ctl["mg_cycle"], p_iterations=ctl["p_iterations"], accuracy=ctl["accuracy"])
+    for lev in range(ctl["levmin"], ctl["levmax"] + 1):
+        ctx.set_node_flags(lev, d[f"L{lev}_NODE"])
+        ctx.set_coordinates(lev, d[f"L{lev}_XX1"], d[f"L{lev}_XX2"], d[f"L{lev}_XX3"])
+    ctx.build_geometry()
+    ctx.set_viscosity_law(tdepv, 0, [1, 1, 1, 1], [viscE] * 4, [273] * 4, [5e-6] * 4)
+    ctx.set_material(d["s0_mat"])
+    ctx.set_temperature(d["s0_T"])
+    ctx.get_system_viscosity()
+    ctx.construct_stiffness_B_matrix(ctl["augmented_Lagr"], ctl["augmented"], ctl["precondition"])
+    return ctx
+
+
+def frac_diff(a, b):
+    return float(np.mean(a != b))
+
+
+@pytest.mark.parametrize("name,tdepv,viscE", [("busse_l3", 0, 0.0), ("tdepv_l3", 1, 11.512925)])
+def test_device_operator_construction_bit_exact(name, tdepv, viscE):
+    d = get_case(name)[0]
+    ctx = build_ctx(d, tdepv, viscE)
+    rep = {}
+    for lev in range(d.levmin, d.levmax + 1):
+        for arr in ("TWW", "MASS", "eco_size", "elt_del"):
+            assert np.array_equal(ctx.get_level_array(lev, arr), d[f"L{lev}_{arr}"]), (lev, arr)
+        evi = ctx.get_level_array(lev, "EVI")
+        ref = d[f"L{lev}_EVI"]
+        rep[f"EVI{lev}"] = frac_diff(evi, ref)
+        assert np.allclose(evi, ref, rtol=3e-7, atol=0) and rep[f"EVI{lev}"] < 1e-3
+        k1, k2, k3, BI = ctx.get_stiffness(lev)
+        for k, nm in ((k1, "Eqn_k1"), (k2, "Eqn_k2"), (k3, "Eqn_k3")):
+            ref = d[f"L{lev}_{nm}"]
+            rep[f"{nm}_{lev}"] = frac_diff(k, ref)
+            assert np.allclose(k, ref, rtol=1e-6, atol=1e-6 * np.abs(ref).max())
+            if not tdepv:
+                assert np.array_equal(k, ref), (lev, nm)
+        refBI = d[f"L{lev}_BI"]
+        assert np.allclose(BI, refBI, rtol=1e-6 if tdepv else 1e-14, atol=0)
+        bpi = ctx.get_level_array(lev, "BPI")
+        assert np.allclose(bpi, d[f"L{lev}_BPI"], rtol=1e-6 if tdepv else 1e-13, atol=0)
+    F = ctx.assemble_forces(d["s0_buoyancy"])
+    assert np.allclose(F, d["s0_F"], rtol=1e-13, atol=1e-15 * np.abs(d["s0_F"]).max())
+    print("fraction of entries differing:", {k: v for k, v in rep.items() if v})
+    # and the solve on the device-built operator lands on the reference's solution
+    lm = d.levmax
+    n, npno = d.dims(lm)["neq"], d.dims(lm)["npno"]
+    acc = d.control()["accuracy"]
+    V, P, steps, res, hist = ctx.solve_Ahat_p_fhat(np.zeros(n), np.zeros(npno), F, acc, 375)
+    assert np.linalg.norm(V - d["s0_U"]) < 20 * acc * np.linalg.norm(d["s0_U"])
+    ctx.close()
