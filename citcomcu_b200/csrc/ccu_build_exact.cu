@@ -22,7 +22,8 @@
 
 // master-element tables (construct_shape_functions, Shape_functions.c:53; indices GNVINDEX / GNVXINDEX,
 // element_definitions.h:59-63): Nv[8*(n-1)+(v-1)], Nxv[64*d + 8*(n-1) + (v-1)], Np[n-1], Nxp[8*d + (n-1)]
-struct ShapeTables { float Nv[64], Nxv[192], Np[8], Nxp[24]; };
+// N is double, Nx float in the reference (global_defs.h:258-269)
+struct ShapeTables { double Nv[64], Np[8]; float Nxv[192], Nxp[24]; };
 __constant__ ShapeTables c_sh;
 
 static double h_lpoly(int p, double y) { return p == 1 ? 0.5 * (1 - y) : (p == 2 ? 0.5 * (1 + y) : 0.0); }
@@ -37,8 +38,8 @@ static void make_shape_tables(ShapeTables &t)
     {
         for(int j = 1; j <= 8; j++)
         {
-            float n = 1.0f;
-            for(int d = 0; d < 3; d++) n = (float)((double)n * h_lpoly(bb[d][i], (double)gx[j][d]));
+            double n = 1.0;
+            for(int d = 0; d < 3; d++) n *= h_lpoly(bb[d][i], (double)gx[j][d]);
             t.Nv[8 * (i - 1) + (j - 1)] = n;
             for(int dd = 0; dd < 3; dd++)
             {
@@ -48,8 +49,8 @@ static void make_shape_tables(ShapeTables &t)
             }
         }
         {
-            float n = 1.0f;
-            for(int d = 0; d < 3; d++) n = (float)((double)n * h_lpoly(bb[d][i], 0.0));
+            double n = 1.0;
+            for(int d = 0; d < 3; d++) n *= h_lpoly(bb[d][i], 0.0);
             t.Np[i - 1] = n;
             for(int dd = 0; dd < 3; dd++)
             {
@@ -124,17 +125,17 @@ __global__ void __launch_bounds__(128) bk_elt_geometry(const CcuGeom g, const fl
     for(int k = 0; k < 8; k++)
     {
         const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gnx);
-        for(int a = 0; a < 8; a++) temp[a] += gda * 1.0f * c_sh.Nv[8 * a + k];          // float*float*float
+        for(int a = 0; a < 8; a++) temp[a] += gda * 1.0f * c_sh.Nv[8 * a + k];          // (float*float)*double
     }
     for(int a = 0; a < 8; a++) { TWW[(size_t)e * 8 + a] = (float)temp[a]; TWWd[(size_t)e * 8 + a] = temp[a]; }
     {   // element sizes: n[] are 1-based local nodes in the reference expressions (:688-695)
         const float *x1 = X[0], *x2 = X[1], *x3 = X[2];
         float d;
-        d = (float)(0.25 * ((double)x1[1] + x1[2] + x1[5] + x1[6] - x1[0] - x1[3] - x1[4] - x1[7]));
+        d = (float)(0.25 * (double)(x1[1] + x1[2] + x1[5] + x1[6] - x1[0] - x1[3] - x1[4] - x1[7]));   // float sum, double scale
         eco[(size_t)e * 3 + 0] = (float)sqrt((double)(d * d));
-        d = (float)(0.25 * ((double)x2[2] + x2[3] + x2[6] + x2[7] - x2[0] - x2[1] - x2[4] - x2[5]));
+        d = (float)(0.25 * (double)(x2[2] + x2[3] + x2[6] + x2[7] - x2[0] - x2[1] - x2[4] - x2[5]));
         eco[(size_t)e * 3 + 1] = (float)sqrt((double)(d * d));
-        d = (float)(0.25 * ((double)x3[4] + x3[5] + x3[6] + x3[7] - x3[0] - x3[1] - x3[2] - x3[3]));
+        d = (float)(0.25 * (double)(x3[4] + x3[5] + x3[6] + x3[7] - x3[0] - x3[1] - x3[2] - x3[3]));
         eco[(size_t)e * 3 + 2] = (float)sqrt((double)(d * d));
     }
     {   // pressure point: elt_del[p+d] = -GNX.ppt(d,a) * (p_point weight * GDA.ppt)
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscPar
         else
         {
             float temp = 1.0e-32f;
-            for(int kk = 0; kk < 8; kk++) temp += fmaxf(0.0f, TT[kk]) * c_sh.Nv[8 * kk + jj];
+            for(int kk = 0; kk < 8; kk++) temp = (float)((double)temp + fmaxf(0.0f, TT[kk]) * c_sh.Nv[8 * kk + jj]);   // float*double
             if(vp.rheol == 0) v = (float)((double)tempa * exp((double)(vp.E[l] * (1.0f - temp))));
             else if(vp.rheol == 1) v = (float)((double)tempa * exp((double)(vp.E[l] / (temp + vp.T[l]))));
             else v = (float)((double)tempa * exp((double)(vp.E[l] * (vp.T[l] - temp))));      // rheol 3
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(128) bk_nodes_to_gint(const CcuGeom g, const f
     for(int i = 0; i < 8; i++)
     {
         double tv = 0.0;
-        for(int j = 0; j < 8; j++) tv += c_sh.Nv[8 * j + i] * vn[j];     // float * float
+        for(int j = 0; j < 8; j++) tv += c_sh.Nv[8 * j + i] * vn[j];     // double * float
         EVI[(size_t)e * 8 + i] = (float)tv;
     }
 }
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(128) bk_forces(const CcuGeom g, const float *_
                 for(int q = 0; q < 8; q++)
                 {
                     double fg = 0.0;
-                    for(int kk = 0; kk < 8; kk++) fg += force[kk] * c_sh.Nv[8 * kk + q];       // float * float
+                    for(int kk = 0; kk < 8; kk++) fg += (double)force[kk] * c_sh.Nv[8 * kk + q];       // force[] is double in get_elt_f
                     const float gda = (float)gp_geom(X, c_sh.Nxv + q, 64, 8, gnx);
                     ef += fg * c_sh.Nv[8 * a + q] * gda * 1.0f;
                 }
