@@ -4,6 +4,7 @@
 #include "ccu_layout.cuh"
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 
 extern thread_local std::string g_ccu_err;
 
@@ -59,6 +60,35 @@ struct ccu_ctx
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;
     long long launches = 0;
+    // CUDA-event profiling of kernel classes (ccu_profile_*)
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t e0, e1; long long n; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[CCU_PROF_COUNT] = { 0 };
+    long long prof_n[CCU_PROF_COUNT] = { 0 };
+};
+
+// scoped event pair around a group of launches of one class
+struct CcuProfScope
+{
+    ccu_ctx *c; int cls; long long n0; cudaEvent_t e0 = nullptr;
+    CcuProfScope(ccu_ctx *ctx, int cls_, bool active) : c(active && ctx->prof_on ? ctx : nullptr), cls(cls_), n0(ctx->launches)
+    {
+        if(!c) return;
+        e0 = get(); cudaEventRecord(e0, c->st);
+    }
+    ~CcuProfScope()
+    {
+        if(!c) return;
+        cudaEvent_t e1 = get(); cudaEventRecord(e1, c->st);
+        c->prof_recs.push_back({ cls, e0, e1, c->launches - n0 });
+    }
+    cudaEvent_t get()
+    {
+        if(!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
 };
 
 #define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->st>>>(__VA_ARGS__); (ctx)->launches++; } while(0)

@@ -99,6 +99,8 @@ void ccu_destroy(ccu_ctx *c)
     }
     cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
     cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
+    for(auto &r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for(auto e : c->prof_pool) cudaEventDestroy(e);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }
@@ -215,16 +217,19 @@ static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cd
 
 static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int strip)
 {
+    CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
 }
 // out = rhs - K u, boundary rows of K u stripped first (the reference's res = rhs - AU with AU stripped)
 static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs, double *out)
 {
+    CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     LAUNCH(c, ccu_k_matvec<1>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, rhs, out, 1);
 }
 
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
+    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax]);
     const unsigned grid = cdiv(L.g.NC, 128);
     for(int s = 0; s < cycles; s++)
     {   // colours 7..0: odd-odd-odd nodes first, the coarse-grid nodes (colour 0) last
@@ -420,6 +425,74 @@ static int d_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *re
     }
     c->s1 = s1; c->s2 = s2; c->r0 = r0; c->r1 = r1; c->r2 = r2; c->z0 = z0; c->z1 = z1;
     *steps_max = count;
+    return 0;
+}
+
+// ------------------------------------------------------------------ profiling
+int ccu_profile_enable(ccu_ctx *c, int on) { if(!c) FAIL("null context"); c->prof_on = on != 0; return 0; }
+static int prof_fold(ccu_ctx *c)
+{
+    CK(cudaStreamSynchronize(c->st));
+    for(auto &r : c->prof_recs)
+    {
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        c->prof_ms[r.cls] += ms; c->prof_n[r.cls] += r.n;
+        c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+    }
+    c->prof_recs.clear();
+    return 0;
+}
+int ccu_profile_read(ccu_ctx *c, int cls, double *ms_total, long long *launches)
+{
+    if(!c) FAIL("null context");
+    if(cls < 0 || cls >= CCU_PROF_COUNT) FAIL("profile_read: bad class");
+    if(prof_fold(c)) return 1;
+    if(ms_total) *ms_total = c->prof_ms[cls];
+    if(launches) *launches = c->prof_n[cls];
+    return 0;
+}
+int ccu_profile_reset(ccu_ctx *c)
+{
+    if(!c) FAIL("null context");
+    if(prof_fold(c)) return 1;
+    for(int i = 0; i < CCU_PROF_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+    return 0;
+}
+
+// ------------------------------------------------------------------ general_stokes_solver (Drive_solvers.c:45-162)
+int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy, int rebuild, int augmented_Lagr, double augmented,
+                              int precondition, int guess, double *U, double *P, int *iterations_out, float *residual_out)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(T && ccu_set_temperature(c, T)) return 1;
+    if(ccu_assemble_forces(c, buoyancy, nullptr)) return 1;
+    if(rebuild)
+    {
+        CcuProfScope ps(c, CCU_PROF_BUILD, true);
+        if(c->visc.tdepv || !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
+        if(ccu_construct_stiffness_B_matrix(c, augmented_Lagr, augmented, precondition)) return 1;
+    }
+    if(!L.have_K || !L.have_flags || !L.have_p) FAIL("general_stokes_solver: operator not built");
+    if(guess == 0)
+    {
+        CK(cudaMemsetAsync(L.vec[CCU_VEC_U], 0, sizeof(double) * L.vlen(), c->st));
+        CK(cudaMemsetAsync(c->P, 0, sizeof(double) * L.g.npno, c->st));
+    }
+    else if(guess == 1)
+    {
+        if(!U || !P) FAIL("general_stokes_solver: guess == 1 needs U and P");
+        if(vec_h2d(c, L, U, L.vec[CCU_VEC_U])) return 1;
+        CK(cudaMemcpyAsync(c->P, P, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
+    }
+    d_strip(c, L, L.vec[CCU_VEC_U]);            // velocities_conform_bcs with zero imposed velocities
+    int steps = c->cfg.p_iterations;
+    if(d_solve_Ahat_p_fhat(c, c->cfg.accuracy, &steps, residual_out, nullptr)) return 1;
+    if(iterations_out) *iterations_out = steps;
+    if(P) CK(cudaMemcpyAsync(P, c->P, sizeof(double) * L.g.npno, cudaMemcpyDeviceToHost, c->st));
+    if(U) return vec_d2h(c, L, L.vec[CCU_VEC_U], U);
+    CK(cudaStreamSynchronize(c->st));
     return 0;
 }
 

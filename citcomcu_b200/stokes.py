@@ -262,6 +262,38 @@ class StokesContext:
                                              C.c_double(imp), C.byref(steps), C.byref(res), hist.ctypes.data_as(C.c_void_p)))
         return Vw, Pw, steps.value, res.value, hist[:steps.value]
 
+    def general_stokes_solver(self, T=None, buoyancy=None, *, rebuild=1, augmented_Lagr=1, augmented=1.0e3, precondition=1,
+                              guess=0, U=None, P=None, want_host=True):
+        """general_stokes_solver (Drive_solvers.c:45): returns (U, P, iterations, residual); U, P are None when
+        want_host is False (results stay in HBM)."""
+        t = None if T is None else np.ascontiguousarray(T, dtype=np.float32)
+        b = None if buoyancy is None else np.ascontiguousarray(buoyancy, dtype=np.float32)
+        lm = self.levmax
+        if want_host:
+            U = np.zeros(self.neq(lm)) if U is None else np.ascontiguousarray(U, dtype=np.float64)
+            P = np.zeros(self.nel(lm)) if P is None else np.ascontiguousarray(P, dtype=np.float64)
+        else:
+            U = P = None
+        it, res = C.c_int(), C.c_float()
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(self.lib.ccu_general_stokes_solver(self._ctx, ptr(t), ptr(b), int(rebuild), int(augmented_Lagr), C.c_double(augmented),
+                                                 int(precondition), int(guess), ptr(U), ptr(P), C.byref(it), C.byref(res)))
+        return U, P, it.value, res.value
+
+    # -- CUDA-event profile of the finest-level kernels
+    PROF = dict(relax_fine=0, matvec_fine=1, build=2)
+
+    def profile_enable(self, on=True):
+        check(self.lib.ccu_profile_enable(self._ctx, int(on)))
+
+    def profile_reset(self):
+        check(self.lib.ccu_profile_reset(self._ctx))
+
+    def profile_read(self, cls):
+        ms, n = C.c_double(), C.c_longlong()
+        check(self.lib.ccu_profile_read(self._ctx, self.PROF[cls], C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # -- device-resident forms
     def vec_upload(self, lev, vec, host):
         h, p = _f64(host)
@@ -316,4 +348,22 @@ def context_from_dump(dump, **overrides) -> StokesContext:
     kw.update(overrides)
     ctx = StokesContext(ctl["levmin"], ctl["levmax"], nox, noy, noz, **kw)
     ctx.load_operator_from(dump)
+    return ctx
+
+
+def context_from_problem(prob, device=0, **overrides) -> StokesContext:
+    """Build a context for one subdomain of a `citcomcu_b200.problem.CartesianProblem`: mesh, flags and
+    coordinates go up, every operator array is then constructed on the device (ccu_build_geometry here,
+    viscosity / stiffness at the first general_stokes_solver call)."""
+    kw = {k: prob.control[k] for k in ("v_steps_low", "v_steps_high", "down_heavy", "up_heavy", "mg_cycle", "p_iterations", "accuracy")}
+    kw.update(overrides)
+    ctx = StokesContext(prob.levmin, prob.levmax, prob.nox, prob.noy, prob.noz, device=device, **kw)
+    for lev in range(prob.levmin, prob.levmax + 1):
+        ctx.set_node_flags(lev, prob.node_flags(lev))
+        ctx.set_coordinates(lev, *prob.coordinates(lev))
+    ctx.build_geometry()
+    v = prob.visc
+    ctx.set_viscosity_law(v["tdepv"], v["rheol"], v["N0"], v["E"], v["T"], v["Z"], v["vmin"], v["min_value"], v["vmax"],
+                          v["max_value"], v["smooth_cycles"])
+    ctx.set_material(prob.material())
     return ctx

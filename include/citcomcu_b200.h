@@ -122,6 +122,26 @@ int ccu_dev_multi_grid(ccu_ctx *ctx, int vec_d1, int vec_F, double *residual_out
 /* whole Stokes solve on resident CCU_VEC_U (in/out), CCU_VEC_F (in) and the resident pressure */
 int ccu_dev_solve_Ahat_p_fhat(ccu_ctx *ctx, double imp, int *steps_max, float *residual_out, double *hist);
 
+
+/* ---- one timestep's Stokes work: general_stokes_solver (Drive_solvers.c:45-162), Newtonian rheologies ----
+ * velocities_conform_bcs + assemble_forces + [get_system_viscosity + construct_stiffness_B_matrix] + solve_Ahat_p_fhat
+ * + (v_from_vector is the caller's: U is returned in the reference's equation numbering).
+ *   T, buoyancy : host float[nno] (= E->T+1, E->buoyancy+1) or NULL to use the device-resident fields
+ *   rebuild     : 1 = viscosity + stiffness are rebuilt (the reference does so on the first call and then every
+ *                 `update_every_steps` when VISC_UPDATE is on, Construct_arrays.c:849), 0 = keep the resident operator
+ *   guess       : 0 = U = P = 0; 1 = U, P hold the initial guess on entry (E->U, E->P + 1); 2 = resident U, P of the last solve
+ *   U, P        : host double[neq] / double[npno]; out (and in when guess == 1); NULL leaves the result on the device only */
+int ccu_general_stokes_solver(ccu_ctx *ctx, const float *T, const float *buoyancy, int rebuild, int augmented_Lagr,
+                              double augmented, int precondition, int guess, double *U, double *P,
+                              int *iterations_out, float *residual_out);
+
+/* ---- CUDA-event timing of the finest-level kernels inside a solve (bench.py's live roofline) ---- */
+enum { CCU_PROF_RELAX_FINE = 0, CCU_PROF_MATVEC_FINE = 1, CCU_PROF_BUILD = 2, CCU_PROF_COUNT = 3 };
+int ccu_profile_enable(ccu_ctx *ctx, int on);
+/* synchronises; total milliseconds and kernel launches recorded for class `cls` since the last reset */
+int ccu_profile_read(ccu_ctx *ctx, int cls, double *ms_total, long long *launches);
+int ccu_profile_reset(ccu_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

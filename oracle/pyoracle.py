@@ -123,6 +123,20 @@ def run_timing(input_text: str, workdir, nsteps: int, nproc: int = 1, timeout: f
     return out
 
 
+def run_timezero(input_text: str, workdir, repeats: int, nproc: int = 1, timeout: float = 3600.0):
+    """`ref_harness timezero`: seconds of each of `repeats` step-0 general_stokes_solver calls (zero guess)."""
+    workdir = Path(workdir)
+    (workdir / "out").mkdir(parents=True, exist_ok=True)
+    (workdir / "in.input").write_text(input_text)
+    env = dict(os.environ)
+    env["CCU_MPI_NP"] = str(nproc)
+    r = subprocess.run([str(REFDIR / "ref_harness"), "timezero", "in.input", str(repeats)], cwd=workdir, env=env,
+                       capture_output=True, text=True, timeout=timeout)
+    if r.returncode not in (0, 8):
+        raise RuntimeError(f"ref_harness timezero failed rc={r.returncode}\n{r.stderr[-4000:]}")
+    return [float(line.split()[4]) for line in r.stdout.split("\n") if line.startswith("CCU_TIME")]
+
+
 # ---------------------------------------------------------------- restatement (ctypes)
 class _Level(C.Structure):
     _fields_ = [("nox", C.c_int), ("noy", C.c_int), ("noz", C.c_int),

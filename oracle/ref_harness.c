@@ -10,6 +10,7 @@
  *
  *   ref_harness dump <input> <outdir> <nsteps> [kat]
  *   ref_harness time <input> <nsteps>
+ *   ref_harness timezero <input> <repeats>      (step-0 Stokes solve repeated from a zero guess)
  *
  * Dump format: <outdir>/<name>.bin raw little-endian + manifest.txt lines
  * "name dtype count".
@@ -261,6 +262,26 @@ int main(int argc, char **argv)
 
     if(argc < 4) { fprintf(stderr, "usage: ref_harness dump <input> <outdir> <nsteps> [kat] | time <input> <nsteps>\n"); return 2; }
 
+    if(strcmp(argv[1], "timezero") == 0)
+    {   /* repeat the step-0 general_stokes_solver from a zero guess (bench.py's step, identical work each time) */
+        int rep, i;
+        nsteps = atoi(argv[3]);
+        setup(&E, &argc, &argv, argv[2]);
+        for(rep = 0; rep < nsteps; rep++)
+        {
+            for(i = 0; i < E.lmesh.neq + 2; i++) E.U[i] = 0.0;
+            for(i = 0; i <= E.lmesh.npno; i++) E.P[i] = 0.0;
+            MPI_Barrier(MPI_COMM_WORLD);
+            t0 = MPI_Wtime();
+            general_stokes_solver(&E);
+            MPI_Barrier(MPI_COMM_WORLD);
+            t1 = MPI_Wtime();
+            if(E.parallel.me == 0) printf("CCU_TIME step %d stokes_s %.6f\n", rep, t1 - t0);
+        }
+        fflush(stdout);
+        MPI_Finalize();
+        return 0;
+    }
     if(strcmp(argv[1], "time") == 0)
     {
         nsteps = atoi(argv[3]);
