@@ -42,7 +42,12 @@ struct Level
 struct ccu_ctx
 {
     ccu_config cfg;
-    cudaStream_t st = 0;
+    cudaStream_t st = 0, own_stream = 0;
+    struct GraphSeg { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+    GraphSeg seg[4];
+    bool use_graphs = true;
+    // kernel selection by level size (lanes per node), ccu_set_option
+    int opt_small_nodes = 3000, opt_warp_nodes = 30000, opt_quad_nodes = 2000000, opt_lanes_large = 1;
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials

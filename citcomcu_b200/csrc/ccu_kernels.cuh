@@ -79,28 +79,153 @@ __device__ __forceinline__ void ccu_row_product(const CcuGeom &g, const float *_
     a0 = r0; a1 = r1; a2 = r2;
 }
 
-// One colour pass of the 8-colour Gauss-Seidel smoother (replaces the lexicographic node loop of
-// gauss_seidel, General_matrix_functions.c:1231-1260).  Same per-node update as the reference:
-// all three equations of a node relaxed together with the scalar inverse diagonal BI and the
-// correction rounded to fp32 (`higher_precision *temp`, :1172,1250-1252).
-template <int C>
-__global__ void __launch_bounds__(128) ccu_k_relax(const CcuGeom g, const float *__restrict__ K,
-                                                    const double *__restrict__ BI, const double *__restrict__ F, double *x)
-{
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if(cell >= g.NC) return;
-    int i, j, k;
-    if(!ccu_decode(g, C, cell, i, j, k)) return;
-    double a0, a1, a2;
-    ccu_row_product<C>(g, K, x, cell, a0, a1, a2);
+// ------------------------------------------------------------------------------------------
+// The same row product split over T lanes per node (T = 4 or 32): lane q takes blocks q, q+T, ... of the 27.
+// One thread per node walks 27 blocks x 12 loads as a chain of dependent round trips; on the coarse levels
+// (too few nodes to hide that latency with occupancy) the chain IS the kernel time.  T lanes cut the chain T-fold;
+// a warp of T=4 covers 8 consecutive cells so every 32-byte sector it touches is still fully used.
+// Block numbering: 0 self, 1..13 own blocks (lower neighbour CCU_LO[b-1]), 14..26 the transposed blocks stored at
+// the upper neighbours (-CCU_LO[b-14]).  The T partial sums are folded with an xor-shuffle tree (deterministic).
+// ------------------------------------------------------------------------------------------
+template <int T, int C>
+__device__ __forceinline__ void ccu_row_product_lanes(const CcuGeom &g, const float *__restrict__ K, const double *x,
+                                                      const int cell, const int q, const bool valid, double &a0, double &a1, double &a2)
+{   // every lane of the warp must arrive here (the shuffles below name the full mask); `valid` gates the loads
+    constexpr int pi = (C >> 2) & 1, pj = (C >> 1) & 1, pk = C & 1;
     const size_t NS = (size_t)g.NS;
     const int s = C * g.NC + cell;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+    for(int it = 0; it < (27 + T - 1) / T; it++)
+    {
+        const int b = q + it * T;
+        if(valid && b < 27)
+        {
+            const bool tr = b >= 14;
+            const int t = tr ? b - 14 : b - 1;                 // index into CCU_LO, -1 for the self block
+            int di = 0, dj = 0, dk = 0;
+            if(t >= 0)
+            {
+                if(t < 9) { di = -1; dj = t / 3 - 1; dk = t % 3 - 1; }
+                else if(t < 12) { dj = -1; dk = t - 10; }
+                else dk = -1;
+            }
+            if(tr) { di = -di; dj = -dj; dk = -dk; }
+            const int slot = (b == 0) ? 0 : t + 1;
+            const int cm = C ^ (((di != 0) << 2) | ((dj != 0) << 1) | (dk != 0));
+            const int sm = cm * g.NC + cell + ccu_shift(pi, di) * g.JK + ccu_shift(pj, dj) * g.Kd + ccu_shift(pk, dk);
+            const float *Kp = K + (size_t)(slot * 9) * NS + (tr ? sm : s);
+            float k[9];
+#pragma unroll
+            for(int e = 0; e < 9; e++) k[e] = __ldg(Kp + (size_t)e * NS);
+            const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
+            if(!tr)
+            {
+                r0 += (double)k[0] * x0 + (double)k[1] * x1 + (double)k[2] * x2;
+                r1 += (double)k[3] * x0 + (double)k[4] * x1 + (double)k[5] * x2;
+                r2 += (double)k[6] * x0 + (double)k[7] * x1 + (double)k[8] * x2;
+            }
+            else
+            {
+                r0 += (double)k[0] * x0 + (double)k[3] * x1 + (double)k[6] * x2;
+                r1 += (double)k[1] * x0 + (double)k[4] * x1 + (double)k[7] * x2;
+                r2 += (double)k[2] * x0 + (double)k[5] * x1 + (double)k[8] * x2;
+            }
+        }
+    }
+#pragma unroll
+    for(int o = T / 2; o > 0; o >>= 1)
+    {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    a0 = r0; a1 = r1; a2 = r2;
+}
+
+// the per-node update of the smoother (General_matrix_functions.c:1250-1259): scalar BI per equation, correction
+// rounded to fp32 (`higher_precision *temp`, :1172)
+__device__ __forceinline__ void ccu_relax_update(const CcuGeom &g, const double *__restrict__ BI, const double *__restrict__ F,
+                                                 double *x, const int s, const double a0, const double a1, const double a2)
+{
+    const size_t NS = (size_t)g.NS;
     const float t0 = (float)((F[s] - a0) * BI[s]);
     const float t1 = (float)((F[NS + s] - a1) * BI[NS + s]);
     const float t2 = (float)((F[2 * NS + s] - a2) * BI[2 * NS + s]);
     x[s] += (double)t0;
     x[NS + s] += (double)t1;
     x[2 * NS + s] += (double)t2;
+}
+
+template <int C>
+__device__ __forceinline__ void ccu_relax_cell(const CcuGeom &g, const float *__restrict__ K, const double *__restrict__ BI,
+                                               const double *__restrict__ F, double *x, const int cell)
+{
+    int i, j, k;
+    if(!ccu_decode(g, C, cell, i, j, k)) return;
+    double a0, a1, a2;
+    ccu_row_product<C>(g, K, x, cell, a0, a1, a2);
+    ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
+}
+
+// One colour pass of the 8-colour Gauss-Seidel smoother, one thread per node (replaces the lexicographic node
+// loop of gauss_seidel, General_matrix_functions.c:1231-1260).
+template <int C>
+__global__ void __launch_bounds__(128) ccu_k_relax(const CcuGeom g, const float *__restrict__ K,
+                                                    const double *__restrict__ BI, const double *__restrict__ F, double *x)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if(cell >= g.NC) return;
+    ccu_relax_cell<C>(g, K, BI, F, x, cell);
+}
+
+// T lanes per node, one colour per launch (mid-size levels)
+template <int T, int C>
+__global__ void __launch_bounds__(128) ccu_k_relax_lanes(const CcuGeom g, const float *__restrict__ K, const double *__restrict__ BI,
+                                                          const double *__restrict__ F, double *x)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cell = tid / T, q = tid % T;
+    int i, j, k;
+    const bool valid = cell < g.NC && ccu_decode(g, C, cell, i, j, k);
+    double a0, a1, a2;
+    ccu_row_product_lanes<T, C>(g, K, x, cell, q, valid, a0, a1, a2);
+    if(valid && q == 0) ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
+}
+
+// Coarsest levels (a few thousand nodes at most): all sweeps and all eight colour passes in ONE launch of one
+// CTA, a warp per node (a lane per stencil block), __syncthreads() between colours -- instead of 8*cycles
+// launches (v_steps_low = 20 sweeps at the bottom of every V-cycle, General_matrix_functions.c:572-574, 611-613).
+template <int C>
+__device__ __forceinline__ void ccu_relax_pass_cta(const CcuGeom &g, const float *__restrict__ K, const double *__restrict__ BI,
+                                                   const double *__restrict__ F, double *x)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for(int cell = warp; cell < g.NC; cell += nwarps)
+    {
+        int i, j, k;
+        if(!ccu_decode(g, C, cell, i, j, k)) continue;
+        double a0, a1, a2;
+        ccu_row_product_lanes<32, C>(g, K, x, cell, lane, true, a0, a1, a2);
+        if(lane == 0) ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(1024) ccu_k_relax_small(const CcuGeom g, const float *__restrict__ K, const double *__restrict__ BI,
+                                                           const double *__restrict__ F, double *x, const int cycles, const int zero_first)
+{
+    if(zero_first)
+    {
+        for(int s = threadIdx.x; s < 3 * g.NS; s += blockDim.x) x[s] = 0.0;
+        __syncthreads();
+    }
+    for(int sw = 0; sw < cycles; sw++)
+    {
+        ccu_relax_pass_cta<7>(g, K, BI, F, x); ccu_relax_pass_cta<6>(g, K, BI, F, x);
+        ccu_relax_pass_cta<5>(g, K, BI, F, x); ccu_relax_pass_cta<4>(g, K, BI, F, x);
+        ccu_relax_pass_cta<3>(g, K, BI, F, x); ccu_relax_pass_cta<2>(g, K, BI, F, x);
+        ccu_relax_pass_cta<1>(g, K, BI, F, x); ccu_relax_pass_cta<0>(g, K, BI, F, x);
+    }
 }
 
 // Au = K*u for all nodes (n_assemble_del2_u, Element_calculations.c:552).  One warp per colour,
@@ -129,6 +254,43 @@ __global__ void __launch_bounds__(256) ccu_k_matvec(const CcuGeom g, const float
     case 6: ccu_row_product<6>(g, K, u, cell, a0, a1, a2); break;
     default: ccu_row_product<7>(g, K, u, cell, a0, a1, a2); break;
     }
+    const size_t NS = (size_t)g.NS;
+    const int s = c * g.NC + cell;
+    if(strip)
+    {
+        const unsigned char f = flags[s];
+        if(f & CCU_F_VBX) a0 = 0.0;
+        if(f & CCU_F_VBY) a1 = 0.0;
+        if(f & CCU_F_VBZ) a2 = 0.0;
+    }
+    if(MODE == 0) { out[s] = a0; out[NS + s] = a1; out[2 * NS + s] = a2; }
+    else { out[s] = rhs[s] - a0; out[NS + s] = rhs[NS + s] - a1; out[2 * NS + s] = rhs[2 * NS + s] - a2; }
+}
+
+// T lanes per node variant of the matvec (coarse and mid levels): thread -> (colour, cell, lane)
+template <int T, int MODE>
+__global__ void __launch_bounds__(256) ccu_k_matvec_lanes(const CcuGeom g, const float *__restrict__ K,
+                                                           const unsigned char *__restrict__ flags, const double *u,
+                                                           const double *rhs, double *out, const int strip)
+{
+    const int c = threadIdx.x >> 5;                               // one warp per colour, 32/T cells per warp
+    const int lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * (32 / T) + lane / T, q = lane % T;
+    int i, j, k;
+    const bool valid = cell < g.NC && ccu_decode(g, c, cell, i, j, k);
+    double a0, a1, a2;
+    switch(c)
+    {
+    case 0: ccu_row_product_lanes<T, 0>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    case 1: ccu_row_product_lanes<T, 1>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    case 2: ccu_row_product_lanes<T, 2>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    case 3: ccu_row_product_lanes<T, 3>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    case 4: ccu_row_product_lanes<T, 4>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    case 5: ccu_row_product_lanes<T, 5>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    case 6: ccu_row_product_lanes<T, 6>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    default: ccu_row_product_lanes<T, 7>(g, K, u, cell, q, valid, a0, a1, a2); break;
+    }
+    if(!valid || q != 0) return;
     const size_t NS = (size_t)g.NS;
     const int s = c * g.NC + cell;
     if(strip)

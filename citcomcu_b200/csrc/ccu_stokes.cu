@@ -42,6 +42,8 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     CK(cudaSetDevice(cfg->device));
     ccu_ctx *c = new ccu_ctx();
     c->cfg = *cfg;
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));   // own stream: the legacy stream cannot be captured
+    c->own_stream = c->st;
     for(int lev = cfg->levmin; lev <= cfg->levmax; lev++)
     {
         Level &L = c->L[lev];
@@ -87,6 +89,11 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     return 0;
 }
 
+static void drop_graphs(ccu_ctx *c)
+{
+    for(auto &g : c->seg) { if(g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.launches = 0; }
+}
+
 void ccu_destroy(ccu_ctx *c)
 {
     if(!c) return;
@@ -99,13 +106,34 @@ void ccu_destroy(ccu_ctx *c)
     }
     cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
     cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
+    drop_graphs(c);
+    if(c->own_stream) cudaStreamDestroy(c->own_stream);
     for(auto &r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for(auto e : c->prof_pool) cudaEventDestroy(e);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }
 
-int ccu_set_stream(ccu_ctx *c, void *s) { if(!c) FAIL("null context"); c->st = (cudaStream_t)s; return 0; }
+int ccu_set_stream(ccu_ctx *c, void *s)
+{
+    if(!c) FAIL("null context");
+    CK(cudaStreamSynchronize(c->st));
+    c->st = s ? (cudaStream_t)s : c->own_stream;     // NULL selects the context's own stream again
+    return 0;
+}
+int ccu_set_option(ccu_ctx *c, int option, int value)
+{
+    if(!c) FAIL("null context");
+    switch(option)
+    {
+    case CCU_OPT_GRAPHS: c->use_graphs = value != 0; drop_graphs(c); return 0;
+    case CCU_OPT_SMALL_NODES: c->opt_small_nodes = value; drop_graphs(c); return 0;
+    case CCU_OPT_WARP_NODES: c->opt_warp_nodes = value; drop_graphs(c); return 0;
+    case CCU_OPT_QUAD_NODES: c->opt_quad_nodes = value; drop_graphs(c); return 0;
+    case CCU_OPT_LANES_LARGE: if(value != 1 && value != 4) FAIL("lanes must be 1 or 4"); c->opt_lanes_large = value; drop_graphs(c); return 0;
+    default: FAIL("set_option: unknown option");
+    }
+}
 int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); CK(cudaStreamSynchronize(c->st)); return 0; }
 long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
 
@@ -215,24 +243,60 @@ static int read_scal(ccu_ctx *c, int first, int count, double *out)
 
 static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cdiv(L.g.NS, 256), 256, L.g, L.flags, v); }
 
+// Lanes per node by level size: the smaller the level, the more the per-node chain of dependent loads is the
+// whole kernel time, so it is split over more lanes (ccu_kernels.cuh).  Tunable through ccu_set_option.
+static int lanes_for(const ccu_ctx *c, const Level &L)
+{
+    if(L.g.nno <= c->opt_small_nodes) return 0;          // single-CTA fused kernel
+    if(L.g.nno <= c->opt_warp_nodes) return 32;
+    if(L.g.nno <= c->opt_quad_nodes) return 4;
+    return c->opt_lanes_large;
+}
 static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int strip)
 {
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
+    const int T = lanes_for(c, L);
+    if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip); return; }
+    if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip); return; }
     LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
 }
 // out = rhs - K u, boundary rows of K u stripped first (the reference's res = rhs - AU with AU stripped)
 static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs, double *out)
 {
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
+    const int T = lanes_for(c, L);
+    if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
+    if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     LAUNCH(c, ccu_k_matvec<1>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, rhs, out, 1);
 }
 
+template <int T>
+static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F)
+{
+    const unsigned grid = cdiv((size_t)L.g.NC * T, 128);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 7>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 6>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 5>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 4>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 3>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 2>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 1>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 0>), grid, 128, L.g, L.K, L.BI, F, x);
+}
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
     CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax]);
+    const int T = lanes_for(c, L);
+    if(T == 0)
+    {   // one CTA does every sweep and colour of a tiny level in a single launch
+        LAUNCH(c, ccu_k_relax_small, 1, 1024, L.g, L.K, L.BI, F, x, cycles, 0);
+        return;
+    }
     const unsigned grid = cdiv(L.g.NC, 128);
     for(int s = 0; s < cycles; s++)
     {   // colours 7..0: odd-odd-odd nodes first, the coarse-grid nodes (colour 0) last
+        if(T == 32) { launch_relax_lanes<32>(c, L, x, F); continue; }
+        if(T == 4) { launch_relax_lanes<4>(c, L, x, F); continue; }
         LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x);
         LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x);
         LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x);
@@ -264,49 +328,118 @@ static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, in
     LAUNCH(c, ccu_k_interp, cdiv(8 * (size_t)Lf.g.NC, 128), 128, Lc.g, Lf.g, Lf.eco, Lf.flags, coarse, fine, strip);
 }
 
-// multi_grid (General_matrix_functions.c:525-653).  F: in rhs, out residual; d1: out correction.
-// Returns through scal[S_DOT0] the squared residual norm (host divides / roots).
-static void d_multi_grid(ccu_ctx *c, double *d1, double *F)
+// A fixed launch sequence captured once into a CUDA graph and replayed: the coarse levels of the
+// multigrid cycle are hundreds of microsecond-scale kernels, bound by launch latency when issued one by one.
+template <class F>
+static int run_segment(ccu_ctx *c, int id, F body)
+{
+    if(!c->use_graphs) { body(); return 0; }
+    ccu_ctx::GraphSeg &s = c->seg[id];
+    if(!s.exec)
+    {
+        const long long l0 = c->launches;
+        const bool prof = c->prof_on;
+        c->prof_on = false;
+        CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+        body();
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamEndCapture(c->st, &g));
+        c->prof_on = prof;
+        s.launches = c->launches - l0;
+        c->launches = l0;
+        CK(cudaGraphInstantiate(&s.exec, g, 0));
+        cudaGraphDestroy(g);
+    }
+    CK(cudaGraphLaunch(s.exec, c->st));
+    c->launches += s.launches;
+    return 0;
+}
+
+// multi_grid (General_matrix_functions.c:525-653), one V-cycle on level `lev` split in three so that the part
+// below the finest level can be replayed as a graph:
+//   mg_down_top : smooth on lev (warm start), res = rhs - K vel, restrict to rhs[lev-1]            (:590-605, dlev == lev)
+//   mg_inner    : down-stroke lev-1 .. levmin+1 from zero, bottom solve, up-stroke levmin+1 .. lev-1  (:590-636)
+//   mg_up_top   : interpolate the correction, smooth, line search alpha, update vel (and res on levmax) (:618-636, ulev == lev)
+static void mg_down(ccu_ctx *c, int dlev, bool warm)
+{
+    Level *L = c->L;
+    Level &D = L[dlev];
+    const int cycles = (dlev == c->cfg.levmax) ? c->cfg.v_steps_high : c->cfg.down_heavy;
+    if(!warm) d_zero(c, D.vec[CCU_VEC_VEL], D.vlen());
+    d_relax_sweeps(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], cycles);
+    d_residual(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], D.vec[CCU_VEC_RES]);   // res = rhs - AU
+    d_project(c, dlev, D.vec[CCU_VEC_RES], L[dlev - 1].vec[CCU_VEC_RHS], 1);
+}
+static void mg_up(ccu_ctx *c, int ulev)
+{
+    Level *L = c->L;
+    Level &U = L[ulev];
+    const int cycles = (ulev == c->cfg.levmax) ? c->cfg.v_steps_high : c->cfg.up_heavy;
+    d_interp(c, ulev - 1, L[ulev - 1].vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], 1);
+    d_gauss_seidel(c, U, U.vec[CCU_VEC_DEL_VEL], U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], cycles, 1);
+    // alpha = <AU,res>/<AU,AU>  (line search, :626-627); both dots share one pass
+    d_dot3(c, U.vlen(), U.vec[CCU_VEC_AU], U.vec[CCU_VEC_AU], S_DOT1, U.vec[CCU_VEC_AU], U.vec[CCU_VEC_RES], S_DOT2);
+    d_axpby(c, U.vlen(), U.vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], coef(c->scal + S_DOT2, c->scal + S_DOT1, 1.0), C_ONE);
+    if(ulev == c->cfg.levmax)
+        d_axpby(c, U.vlen(), U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], coef(c->scal + S_DOT2, c->scal + S_DOT1, -1.0), C_ONE);
+}
+static void mg_bottom(ccu_ctx *c)
+{
+    Level &B = c->L[c->cfg.levmin];
+    d_gauss_seidel(c, B, B.vec[CCU_VEC_VEL], B.vec[CCU_VEC_RHS], B.vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+}
+static void mg_inner(ccu_ctx *c, int lev)       // everything of a V-cycle on `lev` that lives below it
+{
+    for(int dlev = lev - 1; dlev >= c->cfg.levmin + 1; dlev--) mg_down(c, dlev, false);
+    mg_bottom(c);
+    for(int ulev = c->cfg.levmin + 1; ulev <= lev - 1; ulev++) mg_up(c, ulev);
+}
+
+// F: in rhs, out residual; d1: out correction.  Leaves the squared residual norm in scal[S_DOT0].
+static int d_multi_grid(ccu_ctx *c, double *d1, double *F)
 {
     const int levmin = c->cfg.levmin, levmax = c->cfg.levmax;
     Level *L = c->L;
     d_copy(c, L[levmax].vec[CCU_VEC_FL], F, L[levmax].vlen());
-    for(int lev = levmax; lev > levmin; lev--)
-        d_project(c, lev, L[lev].vec[CCU_VEC_FL], L[lev - 1].vec[CCU_VEC_FL], 1);
-    d_gauss_seidel(c, L[levmin], L[levmin].vec[CCU_VEC_VEL], L[levmin].vec[CCU_VEC_FL], L[levmin].vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
-    for(int lev = levmin + 1; lev <= levmax; lev++)
+    if(levmax > levmin)
     {
-        d_interp(c, lev - 1, L[lev - 1].vec[CCU_VEC_VEL], L[lev].vec[CCU_VEC_VEL], 1);
-        d_copy(c, L[lev].vec[CCU_VEC_RHS], L[lev].vec[CCU_VEC_FL], L[lev].vlen());
+        d_project(c, levmax, L[levmax].vec[CCU_VEC_FL], L[levmax - 1].vec[CCU_VEC_FL], 1);
+        // full multigrid below the finest level: restrict fl, bottom solve, nested V-cycles (:559-640)
+        if(run_segment(c, 0, [&]() {
+            for(int lev = levmax - 1; lev > levmin; lev--)
+                d_project(c, lev, L[lev].vec[CCU_VEC_FL], L[lev - 1].vec[CCU_VEC_FL], 1);
+            d_gauss_seidel(c, L[levmin], L[levmin].vec[CCU_VEC_VEL], L[levmin].vec[CCU_VEC_FL], L[levmin].vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+            for(int lev = levmin + 1; lev < levmax; lev++)
+            {
+                d_interp(c, lev - 1, L[lev - 1].vec[CCU_VEC_VEL], L[lev].vec[CCU_VEC_VEL], 1);
+                d_copy(c, L[lev].vec[CCU_VEC_RHS], L[lev].vec[CCU_VEC_FL], L[lev].vlen());
+                for(int Vn = 1; Vn <= c->cfg.mg_cycle; Vn++)
+                {
+                    mg_down(c, lev, true);
+                    mg_inner(c, lev);
+                    mg_up(c, lev);
+                }
+            }
+        })) return 1;
+        d_interp(c, levmax - 1, L[levmax - 1].vec[CCU_VEC_VEL], L[levmax].vec[CCU_VEC_VEL], 1);
+        d_copy(c, L[levmax].vec[CCU_VEC_RHS], L[levmax].vec[CCU_VEC_FL], L[levmax].vlen());
         for(int Vn = 1; Vn <= c->cfg.mg_cycle; Vn++)
         {
-            for(int dlev = lev; dlev >= levmin + 1; dlev--)
-            {
-                const int cycles = (dlev == levmax) ? c->cfg.v_steps_high : c->cfg.down_heavy;
-                Level &D = L[dlev];
-                if(dlev != lev) d_zero(c, D.vec[CCU_VEC_VEL], D.vlen());
-                d_relax_sweeps(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], cycles);
-                d_residual(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], D.vec[CCU_VEC_RES]);   // res = rhs - AU
-                d_project(c, dlev, D.vec[CCU_VEC_RES], L[dlev - 1].vec[CCU_VEC_RHS], 1);
-            }
-            d_gauss_seidel(c, L[levmin], L[levmin].vec[CCU_VEC_VEL], L[levmin].vec[CCU_VEC_RHS], L[levmin].vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
-            for(int ulev = levmin + 1; ulev <= lev; ulev++)
-            {
-                const int cycles = (ulev == levmax) ? c->cfg.v_steps_high : c->cfg.up_heavy;
-                Level &U = L[ulev];
-                d_interp(c, ulev - 1, L[ulev - 1].vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], 1);
-                d_gauss_seidel(c, U, U.vec[CCU_VEC_DEL_VEL], U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], cycles, 1);
-                // alpha = <AU,res>/<AU,AU>  (line search, :626-627); both dots share one pass
-                d_dot3(c, U.vlen(), U.vec[CCU_VEC_AU], U.vec[CCU_VEC_AU], S_DOT1, U.vec[CCU_VEC_AU], U.vec[CCU_VEC_RES], S_DOT2);
-                d_axpby(c, U.vlen(), U.vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], coef(c->scal + S_DOT2, c->scal + S_DOT1, 1.0), C_ONE);
-                if(ulev == levmax)
-                    d_axpby(c, U.vlen(), U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], coef(c->scal + S_DOT2, c->scal + S_DOT1, -1.0), C_ONE);
-            }
+            mg_down(c, levmax, true);
+            if(run_segment(c, 1, [&]() { mg_inner(c, levmax); })) return 1;
+            mg_up(c, levmax);
         }
+    }
+    else
+    {   // single level: the "multigrid" is the bottom smoother (:572-574) and res = F - AU
+        Level &B = L[levmin];
+        d_gauss_seidel(c, B, B.vec[CCU_VEC_VEL], B.vec[CCU_VEC_FL], B.vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+        d_waxpby(c, B.vlen(), B.vec[CCU_VEC_RES], B.vec[CCU_VEC_FL], B.vec[CCU_VEC_AU], C_ONE, C_MINUS);
     }
     d_copy(c, F, L[levmax].vec[CCU_VEC_RES], L[levmax].vlen());
     d_copy(c, d1, L[levmax].vec[CCU_VEC_VEL], L[levmax].vlen());
     d_dot3(c, L[levmax].vlen(), F, F, S_DOT0);
+    return 0;
 }
 
 // solve_del2_u (General_matrix_functions.c:368-520), multigrid branch.  d0 out, F in (device).
@@ -327,7 +460,7 @@ static int d_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, i
     int count = 0;
     while(residual > acc)
     {
-        d_multi_grid(c, D1, r);
+        if(d_multi_grid(c, D1, r)) return 1;
         d_axpby(c, L.vlen(), d0, D1, C_ONE, C_ONE);
         if(read_scal(c, S_DOT0, 1, &rr)) return 1;
         residual = sqrt(rr / gneq);
@@ -561,7 +694,7 @@ int ccu_dev_multi_grid(ccu_ctx *c, int vd1, int vF, double *residual_out)
     if(!c) FAIL("null context");
     const int lev = c->cfg.levmax;
     VEC(d1, lev, vd1); VEC(F, lev, vF);
-    d_multi_grid(c, d1, F);
+    if(d_multi_grid(c, d1, F)) return 1;
     double rr;
     if(read_scal(c, S_DOT0, 1, &rr)) return 1;
     if(residual_out) *residual_out = sqrt(rr / (double)c->L[lev].g.neq);

@@ -68,6 +68,9 @@ class StokesContext:
     def set_stream(self, cuda_stream: int):
         check(self.lib.ccu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
+    def set_option(self, name, value):
+        check(self.lib.ccu_set_option(self._ctx, dict(graphs=0, small_nodes=1, warp_nodes=2, quad_nodes=3, lanes_large=4)[name], int(value)))
+
     def synchronize(self):
         check(self.lib.ccu_synchronize(self._ctx))
 

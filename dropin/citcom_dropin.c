@@ -1,0 +1,103 @@
+/* citcom_dropin.c -- reference-side binding of libcitcomcu_b200.so.
+ *
+ * Defines `general_stokes_solver` with the reference's own signature (src/prototypes.h,
+ * Drive_solvers.c:45) on top of the C ABI in include/citcomcu_b200.h.  A maintainer either adds this
+ * file to src/Makefile's CFILES in place of the body of Drive_solvers.c:general_stokes_solver, or --
+ * without touching the reference at all -- preloads it:
+ *
+ *     LD_PRELOAD=dropin/libcitcomcu_dropin.so  citcom.mpi  input_file
+ *
+ * (the reference's objects are position independent, so the call sites in Citcom.c:97,136 resolve to
+ * this definition).  It is compiled against the reference's own headers where they lie
+ * (-I$(REF)/src); nothing of the reference is copied into this repository.
+ *
+ * Per call: E->T and E->buoyancy go to the device, viscosity / stiffness / BI / BPI are rebuilt there
+ * when the reference would rebuild them (Construct_arrays.c:849), the Uzawa + full-multigrid solve runs
+ * on the device from the previous E->U / E->P, and E->U, E->P, E->V and E->EVI[levmax] come back for
+ * the reference's diagnostics and its energy step.
+ *
+ * Unsupported configurations stop the run loudly (there is no CPU fallback): spherical geometry,
+ * stress- or composition-dependent viscosity, periodic side walls, more than one MPI rank.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "global_defs.h"
+#include "prototypes.h"
+#include "citcomcu_b200.h"
+
+static ccu_ctx *g_ctx = NULL;
+static int g_calls = 0;
+
+static void die(const char *msg)
+{
+    fprintf(stderr, "citcomcu_b200 drop-in: %s\n", msg);
+    exit(9);
+}
+#define CCU(call) do { if((call) != 0) { fprintf(stderr, "citcomcu_b200 drop-in: %s failed: %s\n", #call, ccu_last_error()); exit(9); } } while(0)
+
+static void dropin_init(struct All_variables *E)
+{
+    ccu_config cfg;
+    int lev;
+    const char *dev = getenv("CCU_DEVICE");
+    if(!E->control.CART3D) die("only Geometry=cart3d is accelerated");
+    if(E->parallel.nproc != 1) die("multi-rank runs need the NCCL build (one rank per GPU); run with nproc*=1");
+    if(E->viscosity.SDEPV || E->viscosity.CDEPV || E->viscosity.BDEPV) die("stress/composition/Byerlee viscosity is not on the device path");
+    if(E->mesh.periodic_x || E->mesh.periodic_y) die("periodic side walls are not on the device path");
+    if(!E->control.NMULTIGRID) die("Solver=multigrid is required");
+    {
+        int n, d;
+        for(d = 1; d <= 3; d++)
+            for(n = 1; n <= E->lmesh.nno; n++)
+                if(E->VB[d][n] != 0.0) die("non-zero imposed velocities (VB) are not on the device path");
+    }
+    memset(&cfg, 0, sizeof cfg);
+    cfg.levmin = E->mesh.levmin; cfg.levmax = E->mesh.levmax;
+    for(lev = cfg.levmin; lev <= cfg.levmax; lev++)
+    {
+        cfg.nox[lev] = E->lmesh.NOX[lev]; cfg.noy[lev] = E->lmesh.NOY[lev]; cfg.noz[lev] = E->lmesh.NOZ[lev];
+    }
+    cfg.v_steps_low = E->control.v_steps_low; cfg.v_steps_high = E->control.v_steps_high;
+    cfg.down_heavy = E->control.down_heavy; cfg.up_heavy = E->control.up_heavy; cfg.mg_cycle = E->control.mg_cycle;
+    cfg.p_iterations = E->control.p_iterations; cfg.accuracy = E->control.accuracy;
+    cfg.device = dev ? atoi(dev) : 0;
+    CCU(ccu_create(&cfg, &g_ctx));
+    for(lev = cfg.levmin; lev <= cfg.levmax; lev++)
+    {
+        CCU(ccu_set_node_flags(g_ctx, lev, E->NODE[lev] + 1));
+        CCU(ccu_set_coordinates(g_ctx, lev, E->XX[lev][1] + 1, E->XX[lev][2] + 1, E->XX[lev][3] + 1));
+    }
+    CCU(ccu_build_geometry(g_ctx));
+    CCU(ccu_set_viscosity_law(g_ctx, E->viscosity.TDEPV, E->viscosity.RHEOL, E->viscosity.num_mat, E->viscosity.N0, E->viscosity.E,
+                              E->viscosity.T, E->viscosity.Z, E->viscosity.MIN, E->viscosity.min_value, E->viscosity.MAX,
+                              E->viscosity.max_value, E->viscosity.smooth_cycles));
+    CCU(ccu_set_material(g_ctx, E->mat + 1));
+    if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: Stokes solve on CUDA device %d\n", cfg.device);
+}
+
+void general_stokes_solver(struct All_variables *E)
+{
+    int rebuild, its = 0, i;
+    float res = 0.0f;
+    double t0 = CPU_time0();
+    const int lm = E->mesh.levmax;
+    if(!g_ctx) dropin_init(E);
+    E->monitor.elapsed_time_vsoln1 = E->monitor.elapsed_time_vsoln;
+    E->monitor.elapsed_time_vsoln = E->monitor.elapsed_time;
+    /* Construct_arrays.c:849: first call, or viscosity updates allowed and step % update_every_steps == 0 */
+    rebuild = (g_calls == 0) || (E->viscosity.update_allowed && E->monitor.solution_cycles % E->control.KERNEL == 0);
+    velocities_conform_bcs(E, E->U);
+    CCU(ccu_general_stokes_solver(g_ctx, E->T + 1, E->buoyancy + 1, rebuild, E->control.augmented_Lagr, E->control.augmented,
+                                  E->control.precondition, 1, E->U, E->P + 1, &its, &res));
+    if(rebuild) CCU(ccu_get_level_array(g_ctx, lm, CCU_ARR_EVI, E->EVI[lm] + 1));
+    v_from_vector(E, E->V, E->U);
+    E->monitor.visc_iter_count = 1;
+    g_calls++;
+    if(E->control.print_convergence && E->parallel.me == 0)
+    {
+        fprintf(stderr, "citcomcu_b200: after (%03d) pressure loops and %g sec for step %d\n", its, CPU_time0() - t0, E->monitor.solution_cycles);
+        fprintf(E->fp, "citcomcu_b200: after (%03d) pressure loops and %g sec for step %d\n", its, CPU_time0() - t0, E->monitor.solution_cycles);
+    }
+    (void)i;
+}

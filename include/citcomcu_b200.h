@@ -41,9 +41,15 @@ typedef struct {
 const char *ccu_last_error(void);
 int ccu_create(const ccu_config *cfg, ccu_ctx **out);
 void ccu_destroy(ccu_ctx *ctx);
-/* run all kernels on this CUDA stream (cudaStream_t cast to void*); default: legacy stream 0 */
+/* run all kernels on this CUDA stream (cudaStream_t cast to void*, not the legacy stream 0: it cannot be captured into
+ * CUDA graphs); NULL = the context's own non-blocking stream (the default) */
 int ccu_set_stream(ccu_ctx *ctx, void *cuda_stream);
 int ccu_synchronize(ccu_ctx *ctx);
+/* CCU_OPT_GRAPHS (default 1): replay the coarse-level part of the multigrid cycle as CUDA graphs */
+/* kernel selection by level size: levels with nno <= SMALL_NODES run all sweeps in one single-CTA launch, <= WARP_NODES
+ * use a warp per node, <= QUAD_NODES four lanes per node, larger levels LANES_LARGE (1 or 4) lanes per node */
+enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_OPT_QUAD_NODES = 3, CCU_OPT_LANES_LARGE = 4 };
+int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);
 

@@ -69,6 +69,7 @@ static void dump_level_arrays(struct All_variables *E)
                          E->lmesh.ELZ[lev], nno, nel, neq, npno };
         snprintf(nm, sizeof nm, "L%d_dims", lev); DUMP_I32(nm, dims, 10);
         snprintf(nm, sizeof nm, "L%d_NODE", lev); DUMP_U32(nm, E->NODE[lev] + 1, nno);
+        if(!E->Eqn_k1[lev] || !E->Node_map[lev]) continue;   /* operator lives on the device (drop-in preloaded) */
         snprintf(nm, sizeof nm, "L%d_Eqn_k1", lev); DUMP_F32(nm, E->Eqn_k1[lev], (size_t)nno * 42);
         snprintf(nm, sizeof nm, "L%d_Eqn_k2", lev); DUMP_F32(nm, E->Eqn_k2[lev], (size_t)nno * 42);
         snprintf(nm, sizeof nm, "L%d_Eqn_k3", lev); DUMP_F32(nm, E->Eqn_k3[lev], (size_t)nno * 42);

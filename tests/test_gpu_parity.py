@@ -148,3 +148,29 @@ def test_empty_rhs_is_a_noop(case):
     n = d.dims(d.levmax)["neq"]
     d0, valid, cyc = ctx.solve_del2_u(np.zeros(n), 1e-12)
     assert valid == 0 and cyc == 0 and not d0.any()
+
+
+@pytest.mark.parametrize("opts", [dict(small_nodes=0, warp_nodes=0, quad_nodes=0, lanes_large=1),     # one thread per node
+                                  dict(small_nodes=0, warp_nodes=0, quad_nodes=10**9),                  # four lanes per node
+                                  dict(small_nodes=0, warp_nodes=10**9),                                # a warp per node
+                                  dict(small_nodes=10**9),                                              # single-CTA fused sweeps
+                                  dict(graphs=0)])
+def test_kernel_variants_agree(case, opts):
+    """Every lanes-per-node variant of the smoother / matvec and the CUDA-graph replay give the same answers."""
+    from citcomcu_b200.stokes import context_from_dump
+    d, _ = case
+    ctx = context_from_dump(d)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    R = po.Restate(d, smoother=1)
+    for lev in range(d.levmin, d.levmax + 1):
+        f, u = d[f"kat_L{lev}_f"], d[f"kat_L{lev}_u"]
+        assert rel(ctx.n_assemble_del2_u(u, lev, 1), d[f"kat_L{lev}_Au"]) < 1e-12
+        dm, Adm = R.gauss_seidel(lev, f, 3, 1, d0=u, mc=True)
+        dg, Adg = ctx.gauss_seidel(f, 3, lev, 1, d0=u)
+        assert rel(dg, dm) < 1e-6 and rel(Adg, Adm) < 1e-6
+    d1m, resm, rm = R.multi_grid(d["kat_solve_f"])
+    for _ in range(2):                      # second call replays the captured graphs
+        d1g, resg, rg = ctx.multi_grid(d["kat_solve_f"])
+        assert rel2(d1g, d1m) < 1e-5 and abs(rg - rm) < 1e-4 * rm
+    ctx.close()
