@@ -171,11 +171,12 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args, mesh):
+def workload_config(args, mesh, nproc=(1, 1, 1)):
     return {"workload": f"BASELINE config 3: 3-D Cartesian {mesh[0]}x{mesh[1]}x{mesh[2]} elements, Ra=1e7, TDEPV contrast 1e5, "
                         f"free slip, {args.levels} multigrid levels; step = general_stokes_solver from a zero guess "
                         "(viscosity + stiffness rebuild + forces + Uzawa/FMG solve to accuracy 1e-3)",
-            "mesh": list(mesh), "levels": args.levels, "nproc": [1, 1, 1],
+            "mesh": list(mesh), "levels": args.levels, "nproc": list(nproc),
+            "partition": "one subdomain per GPU, the reference's nprocx x nprocy x nprocz block decomposition; halo sums + allreduce over NCCL",
             "l2": "inputs larger than L2 (finest-level stiffness alone is > 4 GB)"}
 
 
@@ -194,13 +195,22 @@ def run_ours(args):
             raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; citcomcu_b200 has no CPU fallback")
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU subdomain exchange is not implemented yet in this build")
     torch.cuda.set_device(local)
     mesh = mesh_tuple(args.mesh)
     t_setup = time.time()
-    prob = CartesianProblem(inputfile.tdepv_box(*mesh, args.levels, maxstep=1))
-    ctx = context_from_problem(prob, device=local)
+    from citcomcu_b200 import decomp
+    from citcomcu_b200.stokes import StokesContext
+    f = 2 ** (args.levels - 1)
+    nproc = decomp.nproc_for(world, (mesh[0] // f, mesh[1] // f, mesh[2] // f))
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [StokesContext.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    text = inputfile.tdepv_box(*mesh, args.levels, nproc=nproc, maxstep=1)
+    prob = CartesianProblem(text, me_loc=decomp.me_loc_of(rank, nproc))
+    ctx = context_from_problem(prob, device=local, unique_id=uid)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     lm = prob.levmax
@@ -213,8 +223,11 @@ def run_ours(args):
         n[...] = a
         return t, n
 
-    T_t, T_h = pinned(prob.initial_temperature())
-    b_t, b_h = pinned(prob.buoyancy(T_h))
+    gp = prob.global_problem()                      # T and the layer-averaged buoyancy are global fields
+    Tg = gp.initial_temperature()
+    T_t, T_h = pinned(prob.local_slice(Tg))
+    b_t, b_h = pinned(prob.local_slice(gp.buoyancy(Tg)))
+    del Tg
     U_t, U_h = pinned(np.zeros(neq))
     P_t, P_h = pinned(np.zeros(npno))
     kw = dict(rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"], guess=0)
@@ -232,12 +245,21 @@ def run_ours(args):
     def timed(fn, k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             e0.record(stream)
             its = [fn()[2] for _ in range(k)]
             e1.record(stream)
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / 1e3, its
+        sec = e0.elapsed_time(e1) / 1e3
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks
+            sec = float(t.item())
+        return sec, its
 
     for _ in range(args.warmup):
         step_resident()
@@ -271,7 +293,7 @@ def run_ours(args):
             traffic = None
     line = {"metric": "stokes_solve_s_per_timestep", "value": s_per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh, nproc),
             "roofline": {"bound": "hbm", "kernel": "ccu_k_relax<C> (finest-level 8-colour Gauss-Seidel pass)",
                          "achieved": relax_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": relax_gbs / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": relax_bytes_per_launch,
@@ -281,9 +303,9 @@ def run_ours(args):
             "matvec": {"achieved": mv_gbs, "frac": mv_gbs / peak, "launches": mv_n, "avg_launch_ms": mv_ms / max(mv_n, 1),
                        "share_of_step": mv_ms / (total_s * 1e3)},
             "operator_rebuild_ms_per_step": build_ms / args.steps,
-            "uzawa_iterations": its, "gpu_launches": launches, "clocks": clk, "setup_s": setup_s,
-            "e2e": {"value": e2e_s / args.steps, "unit": "s", "h2d_bytes_per_step": int(T_h.nbytes + b_h.nbytes),
-                    "d2h_bytes_per_step": int(U_h.nbytes + P_h.nbytes)}}
+            "uzawa_iterations": its, "gpu_launches": launches * world, "clocks": clk, "setup_s": setup_s,
+            "e2e": {"value": e2e_s / args.steps, "unit": "s", "h2d_bytes_per_step": int(T_h.nbytes + b_h.nbytes) * world,
+                    "d2h_bytes_per_step": int(U_h.nbytes + P_h.nbytes) * world}}
     if not args.no_cpu_baseline and rank == 0:
         try:
             ref_mesh = mesh_tuple(args.ref_mesh)
@@ -295,8 +317,11 @@ def run_ours(args):
                                               f"configuration, {nranks} ranks; {times[-1]:.3f} s measured, scaled x{scale:g} by element count"}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

@@ -168,7 +168,22 @@ __global__ void __launch_bounds__(128) bk_mass(const CcuGeom g, const double *__
             }
         }
     }
-    MASS[n] = (float)(1.0 / (double)m);
+    MASS[n] = m;                 // the lumped mass; inverted by bk_invert after the halo sum (Size_does_matter.c:733-739)
+}
+__global__ void __launch_bounds__(128) bk_invert(const int n, float *v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) v[i] = (float)(1.0 / (double)v[i]);
+}
+__global__ void __launch_bounds__(128) bk_mul(const int n, float *v, const float *__restrict__ w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) v[i] = v[i] * w[i];
+}
+__global__ void __launch_bounds__(128) bk_invert_BI(const size_t n, double *v)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if(i < n) v[i] = (v[i] != 0.0) ? 1.0 / v[i] : 0.0;       // halo / padding slots stay zero
 }
 
 // ---------------------------------------------------------------- viscosity
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(128) bk_gint_to_nodes(const CcuGeom g, const f
             }
         }
     }
-    VN[n] = v * MASS[n];
+    VN[n] = MASS ? v * MASS[n] : v;
 }
 // project_scalar (Solver_multigrid.c:344-388): fine nodal field -> coarse nodal field
 __global__ void __launch_bounds__(128) bk_project_scalar(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ TWWc,
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(128) bk_project_scalar(const CcuGeom gc, const
             }
         }
     }
-    AD[n] = ad * MASSc[n];
+    AD[n] = MASSc ? ad * MASSc[n] : ad;
 }
 // visc_from_nodes_to_gint (Nodal_mesh.c:617-640)
 __global__ void __launch_bounds__(128) bk_nodes_to_gint(const CcuGeom g, const float *__restrict__ VN, float *EVI)
@@ -362,7 +377,7 @@ __device__ __forceinline__ void node_gather_element(const CcuGeom &g, const int 
 __global__ void __launch_bounds__(64) bk_node_ks(const CcuGeom g, const int i_begin, const int i_end, const int ey_begin, const int e_count,
                                                 const double *__restrict__ blocks, const float *__restrict__ elt_del,
                                                 const float *__restrict__ EVI, const unsigned char *__restrict__ flags,
-                                                const int use_aug, const double augmented, float *K, double *BI)
+                                                const int use_aug, const double augmented, float *K, double *BI, const int invert)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int plane = g.nox * g.noz;
@@ -390,7 +405,7 @@ __global__ void __launch_bounds__(64) bk_node_ks(const CcuGeom g, const int i_be
     for(int q = 0; q < 14; q++)
 #pragma unroll
         for(int r = 0; r < 9; r++) K[(size_t)(q * 9 + r) * NS + s] = acc[q][r];
-    for(int d = 0; d < 3; d++) BI[(size_t)d * NS + s] = 1.0 / diag[d];
+    for(int d = 0; d < 3; d++) BI[(size_t)d * NS + s] = invert ? 1.0 / diag[d] : diag[d];
 }
 
 // build_diagonal_of_Ahat / assemble_dAhatp_entry (Element_calculations.c:654-685, 771-824)
@@ -523,6 +538,8 @@ int ccu_build_geometry(ccu_ctx *c)
         if(ccu_ensure_stage(c, sizeof(double) * 8 * (size_t)L.g.nel)) return 1;
         LAUNCH(c, bk_elt_geometry, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.TWW, (double *)c->stage, L.eco, L.elt_del);
         LAUNCH(c, bk_mass, cdiv(L.g.nno, 128), 128, L.g, (const double *)c->stage, L.MASS);
+        if(ccu_halo_sum_nodal(c, lev, L.MASS)) return 1;                  // exchange_node_f20 (Size_does_matter.c:733)
+        LAUNCH(c, bk_invert, cdiv(L.g.nno, 128), 128, L.g.nno, L.MASS);
         CK(cudaStreamSynchronize(c->st));
         L.have_tw = true;
     }
@@ -611,8 +628,20 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
     {
         Level &Lf = c->L[lv], &Lc = c->L[lv - 1];
         if(!Lf.have_tw || !Lc.have_tw) FAIL("construct_stiffness_B_matrix: geometry not built");
-        LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, Lf.MASS, c->nodal_tmp);
-        LAUNCH(c, bk_project_scalar, cdiv(Lc.g.nno, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, c->nodal_tmp, c->nodal_tmp2);
+        if(!c->multi())
+        {
+            LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, Lf.MASS, c->nodal_tmp);
+            LAUNCH(c, bk_project_scalar, cdiv(Lc.g.nno, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, c->nodal_tmp, c->nodal_tmp2);
+        }
+        else
+        {   // exchange_node_f20 between the element gather and the mass factor (Nodal_mesh.c:607-612, Solver_multigrid.c:380-386)
+            LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, (const float *)nullptr, c->nodal_tmp);
+            if(ccu_halo_sum_nodal(c, lv, c->nodal_tmp)) return 1;
+            LAUNCH(c, bk_mul, cdiv(Lf.g.nno, 128), 128, Lf.g.nno, c->nodal_tmp, Lf.MASS);
+            LAUNCH(c, bk_project_scalar, cdiv(Lc.g.nno, 128), 128, Lc.g, Lf.g, Lc.TWW, (const float *)nullptr, c->nodal_tmp, c->nodal_tmp2);
+            if(ccu_halo_sum_nodal(c, lv - 1, c->nodal_tmp2)) return 1;
+            LAUNCH(c, bk_mul, cdiv(Lc.g.nno, 128), 128, Lc.g.nno, c->nodal_tmp2, Lc.MASS);
+        }
         LAUNCH(c, bk_nodes_to_gint, cdiv(Lc.g.nel, 128), 128, Lc.g, c->nodal_tmp2, Lc.EVI);
         Lc.have_evi = true;
     }
@@ -645,10 +674,16 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
             const int e_count = (int)(per_plane * (ey1 - ey0));
             LAUNCH(c, bk_elt_k, cdiv(e_count, 64), 64, g, L.XX, L.EVI, (int)(per_plane * ey0), e_count, c->eltK);
             const size_t nn = (size_t)(i1 - i0) * g.nox * g.noz;
-            LAUNCH(c, bk_node_ks, cdiv(nn, 64), 64, g, i0, i1, ey0, e_count, c->eltK, L.elt_del, L.EVI, L.flags, augmented_Lagr, augmented, L.K, L.BI);
+            LAUNCH(c, bk_node_ks, cdiv(nn, 64), 64, g, i0, i1, ey0, e_count, c->eltK, L.elt_del, L.EVI, L.flags, augmented_Lagr, augmented, L.K, L.BI, c->multi() ? 0 : 1);
             i0 = i1;
         }
+        if(c->multi())
+        {   // the diagonal of a duplicated node is the sum over its owners (exchange_id_d20, Construct_arrays.c:497)
+            if(ccu_halo_sum_vec(c, lev, L.BI)) return 1;
+            LAUNCH(c, bk_invert_BI, cdiv(L.vlen(), 128), 128, L.vlen(), L.BI);
+        }
         LAUNCH(c, bk_BPI, cdiv(g.nel, 128), 128, g, L.elt_del, L.BI, precondition, L.BPI);
+        if(c->multi() && ccu_damp_face_BI(c, lev)) return 1;              // rebuild_BI_on_boundary (Construct_arrays.c:892)
         L.have_K = true; L.have_p = true;
     }
     CK(cudaGetLastError());
@@ -665,6 +700,7 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
     if(!L.have_xx || !L.have_flags) FAIL("assemble_forces: coordinates/flags missing");
     if(buoyancy) CK(cudaMemcpyAsync(c->buoy, buoyancy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyHostToDevice, c->st));
     LAUNCH(c, bk_forces, cdiv(L.g.nno, 128), 128, L.g, L.XX, c->buoy, L.flags, L.vec[CCU_VEC_F]);
+    if(ccu_halo_sum_vec(c, c->cfg.levmax, L.vec[CCU_VEC_F])) return 1;   // exchange_id_d20 (Element_calculations.c:119)
     if(F_out)
     {
         if(ccu_ensure_stage(c, sizeof(double) * L.g.neq)) return 1;

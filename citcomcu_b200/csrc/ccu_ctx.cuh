@@ -39,6 +39,26 @@ struct Level
     size_t vlen() const { return 3 * (size_t)g.NS; }
 };
 
+// duplicated-node tables of one level on the device (ccu_comm.cu)
+struct CcuHalo
+{
+    std::vector<int> nb_rank, nb_off, nb_cnt;
+    int n_send = 0, n_shared = 0;
+    int *sh_s = nullptr, *sh_n = nullptr, *sh_ptr = nullptr, *sh_src = nullptr;   // per duplicated node: storage / natural index, CSR of contributions
+    int *send_s = nullptr, *send_n = nullptr, *send_t = nullptr;                     // per packed node: storage / natural / compact index
+    unsigned char *bits = nullptr;   // [NS] bit0 = owned for dot products, bit1 = duplicated (OFFSIDE)
+    double *face = nullptr;          // [3][n_shared] partial rows of the duplicated nodes (smoother)
+};
+struct CcuComm
+{
+    int nranks = 1, rank = 0, nproc[3] = { 1, 1, 1 }, me[3] = { 0, 0, 0 };
+    void *nccl = nullptr;            // ncclComm_t
+    CcuHalo halo[CCU_MAX_LEVELS];
+    void *sendbuf = nullptr, *recvbuf = nullptr;
+    double *dotstage = nullptr;
+    long long gneq = 0, gnpno = 0;   // global equation / pressure counts (E->mesh.neq, E->mesh.npno)
+};
+
 struct ccu_ctx
 {
     ccu_config cfg;
@@ -47,7 +67,7 @@ struct ccu_ctx
     GraphSeg seg[4];
     bool use_graphs = true;
     // kernel selection by level size (lanes per node), ccu_set_option
-    int opt_small_nodes = 3000, opt_warp_nodes = 30000, opt_quad_nodes = 2000000, opt_lanes_large = 1;
+    int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 2000000, opt_lanes_large = 1;
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials
@@ -65,6 +85,8 @@ struct ccu_ctx
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;
     long long launches = 0;
+    CcuComm *comm = nullptr;       // null = single subdomain
+    bool multi() const { return comm && comm->nranks > 1; }
     // CUDA-event profiling of kernel classes (ccu_profile_*)
     bool prof_on = false;
     struct ProfRec { int cls; cudaEvent_t e0, e1; long long n; };
@@ -100,4 +122,13 @@ struct CcuProfScope
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int ccu_ensure_stage(ccu_ctx *c, size_t bytes);
+void ccu_drop_graphs(ccu_ctx *c);
+// ccu_comm.cu
+void ccu_comm_destroy(ccu_ctx *c);
+int ccu_halo_sum_vec(ccu_ctx *c, int lev, double *vec);       // exchange_id_d20
+int ccu_halo_sum_face(ccu_ctx *c, int lev);                   // partial rows of the duplicated nodes -> recvbuf
+int ccu_halo_sum_nodal(ccu_ctx *c, int lev, float *field);    // exchange_node_f20
+int ccu_allreduce_dots(ccu_ctx *c, int count, double *o0, double *o1, double *o2);
+int ccu_allreduce_buffer(ccu_ctx *c, double *buf, int count, int op_max);
+int ccu_damp_face_BI(ccu_ctx *c, int lev);                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);

@@ -157,12 +157,18 @@ __device__ __forceinline__ void ccu_relax_update(const CcuGeom &g, const double 
     x[2 * NS + s] += (double)t2;
 }
 
+// `bits` (multi-subdomain runs only, else null): bit 1 marks nodes duplicated on a neighbouring subdomain (the
+// reference's OFFSIDE flag); those are relaxed separately from their summed rows (ccu_k_face_update), not here.
+#define CCU_B_OWNED 1
+#define CCU_B_SHARED 2
 template <int C>
 __device__ __forceinline__ void ccu_relax_cell(const CcuGeom &g, const float *__restrict__ K, const double *__restrict__ BI,
-                                               const double *__restrict__ F, double *x, const int cell)
+                                               const double *__restrict__ F, double *x, const int cell,
+                                               const unsigned char *__restrict__ bits)
 {
     int i, j, k;
     if(!ccu_decode(g, C, cell, i, j, k)) return;
+    if(bits && (bits[C * g.NC + cell] & CCU_B_SHARED)) return;
     double a0, a1, a2;
     ccu_row_product<C>(g, K, x, cell, a0, a1, a2);
     ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
@@ -172,22 +178,23 @@ __device__ __forceinline__ void ccu_relax_cell(const CcuGeom &g, const float *__
 // loop of gauss_seidel, General_matrix_functions.c:1231-1260).
 template <int C>
 __global__ void __launch_bounds__(128) ccu_k_relax(const CcuGeom g, const float *__restrict__ K,
-                                                    const double *__restrict__ BI, const double *__restrict__ F, double *x)
+                                                    const double *__restrict__ BI, const double *__restrict__ F, double *x,
+                                                    const unsigned char *__restrict__ bits)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if(cell >= g.NC) return;
-    ccu_relax_cell<C>(g, K, BI, F, x, cell);
+    ccu_relax_cell<C>(g, K, BI, F, x, cell, bits);
 }
 
 // T lanes per node, one colour per launch (mid-size levels)
 template <int T, int C>
 __global__ void __launch_bounds__(128) ccu_k_relax_lanes(const CcuGeom g, const float *__restrict__ K, const double *__restrict__ BI,
-                                                          const double *__restrict__ F, double *x)
+                                                          const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int cell = tid / T, q = tid % T;
     int i, j, k;
-    const bool valid = cell < g.NC && ccu_decode(g, C, cell, i, j, k);
+    const bool valid = cell < g.NC && ccu_decode(g, C, cell, i, j, k) && !(bits && (bits[C * g.NC + cell] & CCU_B_SHARED));
     double a0, a1, a2;
     ccu_row_product_lanes<T, C>(g, K, x, cell, q, valid, a0, a1, a2);
     if(valid && q == 0) ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
@@ -225,6 +232,110 @@ __global__ void __launch_bounds__(1024) ccu_k_relax_small(const CcuGeom g, const
         ccu_relax_pass_cta<5>(g, K, BI, F, x); ccu_relax_pass_cta<4>(g, K, BI, F, x);
         ccu_relax_pass_cta<3>(g, K, BI, F, x); ccu_relax_pass_cta<2>(g, K, BI, F, x);
         ccu_relax_pass_cta<1>(g, K, BI, F, x); ccu_relax_pass_cta<0>(g, K, BI, F, x);
+    }
+}
+
+// ---------------------------------------------------------------- duplicated (inter-subdomain face) nodes
+// Row product of one node with run-time colour, one warp per node, lane b = stencil block b (0 self, 1..13 own,
+// 14..26 transposed).  ABS = 1 gives the absolute row sums sum_j |K_ij| (rebuild_BI_on_boundary, Construct_arrays.c:892).
+template <int ABS>
+__device__ __forceinline__ void ccu_row_product_warp(const CcuGeom &g, const float *__restrict__ K, const double *x, const int s,
+                                                     const int lane, double &a0, double &a1, double &a2)
+{
+    const size_t NS = (size_t)g.NS;
+    const int c = s / g.NC, cell = s - c * g.NC;
+    const int pi = (c >> 2) & 1, pj = (c >> 1) & 1, pk = c & 1;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    const int b = lane;
+    if(b < 27)
+    {
+        const bool tr = b >= 14;
+        const int t = tr ? b - 14 : b - 1;
+        int di = 0, dj = 0, dk = 0;
+        if(t >= 0)
+        {
+            if(t < 9) { di = -1; dj = t / 3 - 1; dk = t % 3 - 1; }
+            else if(t < 12) { dj = -1; dk = t - 10; }
+            else dk = -1;
+        }
+        if(tr) { di = -di; dj = -dj; dk = -dk; }
+        const int slot = (b == 0) ? 0 : t + 1;
+        const int cm = c ^ (((di != 0) << 2) | ((dj != 0) << 1) | (dk != 0));
+        const int sm = cm * g.NC + cell + ccu_shift(pi, di) * g.JK + ccu_shift(pj, dj) * g.Kd + ccu_shift(pk, dk);
+        const float *Kp = K + (size_t)(slot * 9) * NS + (tr ? sm : s);
+        double k[9];
+#pragma unroll
+        for(int e = 0; e < 9; e++) { const double v = (double)__ldg(Kp + (size_t)e * NS); k[e] = ABS ? fabs(v) : v; }
+        const double x0 = ABS ? 1.0 : x[sm], x1 = ABS ? 1.0 : x[NS + sm], x2 = ABS ? 1.0 : x[2 * NS + sm];
+        if(!tr) { r0 = k[0] * x0 + k[1] * x1 + k[2] * x2; r1 = k[3] * x0 + k[4] * x1 + k[5] * x2; r2 = k[6] * x0 + k[7] * x1 + k[8] * x2; }
+        else { r0 = k[0] * x0 + k[3] * x1 + k[6] * x2; r1 = k[1] * x0 + k[4] * x1 + k[7] * x2; r2 = k[2] * x0 + k[5] * x1 + k[8] * x2; }
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
+    a0 = r0; a1 = r1; a2 = r2;
+}
+// this subdomain's part of (K x) [or of sum|K|] at every duplicated node -> face[d*n + t]
+template <int ABS>
+__global__ void __launch_bounds__(128) ccu_k_face_rows(const CcuGeom g, const float *__restrict__ K, const double *x, const int n,
+                                                        const int *__restrict__ sh_s, double *face)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(t >= n) return;
+    double a0, a1, a2;
+    ccu_row_product_warp<ABS>(g, K, x, sh_s[t], lane, a0, a1, a2);
+    if(lane == 0) { face[t] = a0; face[(size_t)n + t] = a1; face[2 * (size_t)n + t] = a2; }
+}
+// all owners' parts of a duplicated node's row, added in ascending rank order (bitwise the same on every owner)
+__device__ __forceinline__ double ccu_face_total(const int t, const int d, const int n, const int *__restrict__ ptr, const int *__restrict__ src,
+                                                 const double *__restrict__ face, const double *__restrict__ recv)
+{
+    double acc = 0.0;
+    for(int e = ptr[t]; e < ptr[t + 1]; e++)
+    {
+        const int q = src[e];
+        const double v = (q < 0) ? face[(size_t)d * n + t] : recv[(size_t)q * 3 + d];
+        acc = (e == ptr[t]) ? v : acc + v;
+    }
+    return acc;
+}
+// Jacobi update of the duplicated nodes from their summed rows with the damped BI (the reference's treatment of
+// OFFSIDE nodes, General_matrix_functions.c:1218-1230; BI from rebuild_BI_on_boundary)
+__global__ void __launch_bounds__(128) ccu_k_face_update(const CcuGeom g, const int n, const int *__restrict__ sh_s, const int *__restrict__ ptr,
+                                                          const int *__restrict__ src, const double *__restrict__ face,
+                                                          const double *__restrict__ recv, const double *__restrict__ BI,
+                                                          const double *__restrict__ F, double *x)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= n) return;
+    const int s = sh_s[t];
+    const size_t NS = (size_t)g.NS;
+#pragma unroll
+    for(int d = 0; d < 3; d++)
+    {
+        const double a = ccu_face_total(t, d, n, ptr, src, face, recv);
+        const float tt = (float)((F[d * NS + s] - a) * BI[d * NS + s]);
+        x[d * NS + s] += (double)tt;
+    }
+}
+// rebuild_BI_on_boundary (Construct_arrays.c:892-952): BI of a duplicated node = 1 / (sum_j |K_ij| - K_ii)
+__global__ void __launch_bounds__(128) ccu_k_face_damp_BI(const CcuGeom g, const int n, const int *__restrict__ sh_s, const int *__restrict__ ptr,
+                                                           const int *__restrict__ src, const double *__restrict__ face,
+                                                           const double *__restrict__ recv, double *BI)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= n) return;
+    const int s = sh_s[t];
+    const size_t NS = (size_t)g.NS;
+#pragma unroll
+    for(int d = 0; d < 3; d++)
+    {
+        const double a = ccu_face_total(t, d, n, ptr, src, face, recv);
+        BI[d * NS + s] = 1.0 / (a - 1.0 / BI[d * NS + s]);
     }
 }
 
@@ -399,14 +510,17 @@ __global__ void ccu_k_mul(const size_t n, double *z, const double *__restrict__ 
 // the partials (global_vdot / global_pdot, Global_operations.c:339-375).  Up to 3 dots per pass so
 // the pairs the callers need together share one read of the vectors.
 #define CCU_DOT_BLOCKS 592
+// `own` (multi-subdomain runs, nodal vectors only): bit 0 of own[i % ns] says this subdomain counts the node
+// (the reference's IDD ownership mask, Construct_arrays.c:169-191)
 __global__ void __launch_bounds__(256) ccu_k_dot_partial(const size_t n, const double *__restrict__ a0, const double *__restrict__ b0,
                                                           const double *__restrict__ a1, const double *__restrict__ b1,
                                                           const double *__restrict__ a2, const double *__restrict__ b2,
-                                                          double *partial)
+                                                          double *partial, const unsigned char *__restrict__ own, const size_t ns)
 {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for(size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     {
+        if(own && !(own[i % ns] & CCU_B_OWNED)) continue;
         s0 += a0[i] * b0[i];
         if(a1) s1 += a1[i] * b1[i];
         if(a2) s2 += a2[i] * b2[i];
@@ -454,7 +568,8 @@ __global__ void __launch_bounds__(256) ccu_k_dot_final(const double *__restrict_
 // elements around it in the reference's accumulation order (ascending element number), each
 // contributing TWW * (sum of the 8 nodes of the fine sub-element in that octant); then * MASS.
 __global__ void __launch_bounds__(128) ccu_k_project(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ TWW,
-                                                      const float *__restrict__ MASS, const double *__restrict__ fine, double *coarse)
+                                                      const float *__restrict__ MASS, const double *__restrict__ fine, double *coarse,
+                                                      const int apply_mass)
 {
     constexpr int OFFS[9][3] = CCU_OFFS_INIT;
     constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };   // [dz][dx][dy] -> local node
@@ -489,9 +604,21 @@ __global__ void __launch_bounds__(128) ccu_k_project(const CcuGeom gc, const Ccu
             }
         }
     }
-    const double m = (double)MASS[Kz + gc.noz * (J + gc.nox * I)];
+    const double m = apply_mass ? (double)MASS[Kz + gc.noz * (J + gc.nox * I)] : 1.0;
     const int sc = c * gc.NC + cell;
     coarse[sc] = s0 * m; coarse[(size_t)gc.NS + sc] = s1 * m; coarse[2 * (size_t)gc.NS + sc] = s2 * m;
+}
+// second half of project_vector when the halo sum sits between the gather and the mass factor (Solver_multigrid.c:150-157)
+__global__ void __launch_bounds__(128) ccu_k_mass_mul(const CcuGeom g, const float *__restrict__ MASS, double *v)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= 8 * g.NC) return;
+    const int c = t / g.NC, cell = t - c * g.NC;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    const double m = (double)MASS[k + g.noz * (j + g.nox * i)];
+    const int s = c * g.NC + cell;
+    v[s] *= m; v[(size_t)g.NS + s] *= m; v[2 * (size_t)g.NS + s] *= m;
 }
 
 // interp_vector + un_inject_vector (Solver_multigrid.c:173-298, 581-634): the reference fills x,

@@ -5,6 +5,7 @@
 // reference's control flow branches on.
 #include "ccu_ctx.cuh"
 #include "ccu_kernels.cuh"
+#include "ccu_comm.cuh"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -89,10 +90,11 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     return 0;
 }
 
-static void drop_graphs(ccu_ctx *c)
+void ccu_drop_graphs(ccu_ctx *c)
 {
     for(auto &g : c->seg) { if(g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.launches = 0; }
 }
+static void drop_graphs(ccu_ctx *c) { ccu_drop_graphs(c); }
 
 void ccu_destroy(ccu_ctx *c)
 {
@@ -107,6 +109,7 @@ void ccu_destroy(ccu_ctx *c)
     cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
     cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
     drop_graphs(c);
+    ccu_comm_destroy(c);
     if(c->own_stream) cudaStreamDestroy(c->own_stream);
     for(auto &r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for(auto e : c->prof_pool) cudaEventDestroy(e);
@@ -227,12 +230,30 @@ static void d_waxpby(ccu_ctx *c, size_t n, double *z, const double *x, const dou
     LAUNCH(c, ccu_k_waxpby, min(cdiv(n, 256), 148u * 16u), 256, n, z, x, y, a, b);
 }
 // up to three dots in one pass over the vectors; results land in scal[slot*]
+// `maskL` = the level whose nodal vectors are being dotted (ownership mask in multi-subdomain runs), null for
+// element (pressure) vectors.  Multi-subdomain: local sums -> one ncclAllReduce of the (<= 3) scalars -> slots.
+static void d_dot3m(ccu_ctx *c, const Level *maskL, size_t n, const double *a0, const double *b0, int s0, const double *a1 = nullptr,
+                    const double *b1 = nullptr, int s1 = -1, const double *a2 = nullptr, const double *b2 = nullptr, int s2 = -1)
+{
+    const int nb = (int)min((size_t)CCU_DOT_BLOCKS, (size_t)cdiv(n, 256));
+    double *o0 = c->scal + s0, *o1 = s1 >= 0 ? c->scal + s1 : nullptr, *o2 = s2 >= 0 ? c->scal + s2 : nullptr;
+    if(!c->multi())
+    {
+        LAUNCH(c, ccu_k_dot_partial, nb, 256, n, a0, b0, a1, b1, a2, b2, c->partial, (const unsigned char *)nullptr, (size_t)1);
+        LAUNCH(c, ccu_k_dot_final, 1, 256, c->partial, nb, o0, o1, o2);
+        return;
+    }
+    const unsigned char *own = nullptr; size_t ns = 1;
+    if(maskL) { own = c->comm->halo[maskL - c->L].bits; ns = (size_t)maskL->g.NS; }
+    double *st = c->comm->dotstage;
+    LAUNCH(c, ccu_k_dot_partial, nb, 256, n, a0, b0, a1, b1, a2, b2, c->partial, own, ns);
+    LAUNCH(c, ccu_k_dot_final, 1, 256, c->partial, nb, st, o1 ? st + 1 : nullptr, o2 ? st + 2 : nullptr);
+    ccu_allreduce_dots(c, 1 + (o1 ? 1 : 0) + (o2 ? 1 : 0), o0, o1, o2);
+}
 static void d_dot3(ccu_ctx *c, size_t n, const double *a0, const double *b0, int s0, const double *a1 = nullptr, const double *b1 = nullptr,
                    int s1 = -1, const double *a2 = nullptr, const double *b2 = nullptr, int s2 = -1)
 {
-    const int nb = (int)min((size_t)CCU_DOT_BLOCKS, (size_t)cdiv(n, 256));
-    LAUNCH(c, ccu_k_dot_partial, nb, 256, n, a0, b0, a1, b1, a2, b2, c->partial);
-    LAUNCH(c, ccu_k_dot_final, 1, 256, c->partial, nb, c->scal + s0, s1 >= 0 ? c->scal + s1 : nullptr, s2 >= 0 ? c->scal + s2 : nullptr);
+    d_dot3m(c, nullptr, n, a0, b0, s0, a1, b1, s1, a2, b2, s2);
 }
 static int read_scal(ccu_ctx *c, int first, int count, double *out)
 {
@@ -247,7 +268,7 @@ static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cd
 // whole kernel time, so it is split over more lanes (ccu_kernels.cuh).  Tunable through ccu_set_option.
 static int lanes_for(const ccu_ctx *c, const Level &L)
 {
-    if(L.g.nno <= c->opt_small_nodes) return 0;          // single-CTA fused kernel
+    if(L.g.nno <= c->opt_small_nodes) return c->multi() ? 32 : 0;          // single-CTA fused kernel (one exchange per sweep rules it out)
     if(L.g.nno <= c->opt_warp_nodes) return 32;
     if(L.g.nno <= c->opt_quad_nodes) return 4;
     return c->opt_lanes_large;
@@ -256,13 +277,20 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
 {
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     const int T = lanes_for(c, L);
-    if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip); return; }
-    if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip); return; }
-    LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    else LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    if(c->multi()) ccu_halo_sum_vec(c, (int)(&L - c->L), Au);      // exchange_id_d20 (Element_calculations.c:612)
 }
 // out = rhs - K u, boundary rows of K u stripped first (the reference's res = rhs - AU with AU stripped)
 static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs, double *out)
 {
+    if(c->multi())
+    {   // the halo sum sits between the product and the subtraction
+        d_matvec(c, L, u, out, 1);
+        d_axpby(c, L.vlen(), out, rhs, C_ONE, C_MINUS);
+        return;
+    }
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     const int T = lanes_for(c, L);
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
@@ -271,17 +299,30 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
 }
 
 template <int T>
-static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F)
+static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F, const unsigned char *bits)
 {
     const unsigned grid = cdiv((size_t)L.g.NC * T, 128);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 7>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 6>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 5>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 4>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 3>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 2>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 1>), grid, 128, L.g, L.K, L.BI, F, x);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 0>), grid, 128, L.g, L.K, L.BI, F, x);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 7>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 6>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 5>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 4>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 3>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 2>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 1>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 0>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+}
+// Multi-subdomain sweeps start with the duplicated face nodes: every owner computes its part of their rows, one halo
+// round sums the parts, and all owners apply the same damped-Jacobi update (the reference's OFFSIDE treatment,
+// General_matrix_functions.c:1218-1230, 1262-1284: one exchange per sweep).  The colour passes then skip those nodes.
+static void relax_faces(ccu_ctx *c, Level &L, double *x, const double *F)
+{
+    const int lev = (int)(&L - c->L);
+    const CcuHalo &H = c->comm->halo[lev];
+    if(H.n_shared == 0) return;
+    LAUNCH(c, ccu_k_face_rows<0>, cdiv((size_t)H.n_shared * 32, 128), 128, L.g, L.K, x, H.n_shared, H.sh_s, H.face);
+    ccu_halo_sum_face(c, lev);
+    LAUNCH(c, ccu_k_face_update, cdiv(H.n_shared, 128), 128, L.g, H.n_shared, H.sh_s, H.sh_ptr, H.sh_src, H.face,
+           (const double *)c->comm->recvbuf, L.BI, F, x);
 }
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
@@ -293,19 +334,35 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         return;
     }
     const unsigned grid = cdiv(L.g.NC, 128);
+    const unsigned char *bits = c->multi() ? c->comm->halo[&L - c->L].bits : nullptr;
     for(int s = 0; s < cycles; s++)
     {   // colours 7..0: odd-odd-odd nodes first, the coarse-grid nodes (colour 0) last
-        if(T == 32) { launch_relax_lanes<32>(c, L, x, F); continue; }
-        if(T == 4) { launch_relax_lanes<4>(c, L, x, F); continue; }
-        LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<4>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<3>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<2>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<1>, grid, 128, L.g, L.K, L.BI, F, x);
-        LAUNCH(c, ccu_k_relax<0>, grid, 128, L.g, L.K, L.BI, F, x);
+        if(bits) relax_faces(c, L, x, F);
+        if(T == 32) { launch_relax_lanes<32>(c, L, x, F, bits); continue; }
+        if(T == 4) { launch_relax_lanes<4>(c, L, x, F, bits); continue; }
+        LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<4>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<3>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<2>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<1>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<0>, grid, 128, L.g, L.K, L.BI, F, x, bits);
     }
+}
+
+// rebuild_BI_on_boundary (Construct_arrays.c:892-952): damped inverse diagonal on the duplicated nodes
+int ccu_damp_face_BI(ccu_ctx *c, int lev)
+{
+    if(!c->multi()) return 0;
+    Level &L = c->L[lev];
+    const CcuHalo &H = c->comm->halo[lev];
+    if(H.n_shared == 0) return 0;
+    LAUNCH(c, ccu_k_face_rows<1>, cdiv((size_t)H.n_shared * 32, 128), 128, L.g, L.K, (const double *)nullptr, H.n_shared, H.sh_s, H.face);
+    if(ccu_halo_sum_face(c, lev)) return 1;
+    LAUNCH(c, ccu_k_face_damp_BI, cdiv(H.n_shared, 128), 128, L.g, H.n_shared, H.sh_s, H.sh_ptr, H.sh_src, H.face,
+           (const double *)c->comm->recvbuf, L.BI);
+    return 0;
 }
 
 // gauss_seidel (General_matrix_functions.c:1160): d0, Ad = K d0
@@ -319,7 +376,13 @@ static void d_gauss_seidel(ccu_ctx *c, Level &L, double *d0, const double *F, do
 static void d_project(ccu_ctx *c, int lev, const double *fine, double *coarse, int strip)
 {
     Level &Lf = c->L[lev], &Lc = c->L[lev - 1];
-    LAUNCH(c, ccu_k_project, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse);
+    const int multi = c->multi() ? 1 : 0;
+    LAUNCH(c, ccu_k_project, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse, multi ? 0 : 1);
+    if(multi)
+    {   // exchange_id_d20 before the mass factor (Solver_multigrid.c:150-157)
+        ccu_halo_sum_vec(c, lev - 1, coarse);
+        LAUNCH(c, ccu_k_mass_mul, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lc.MASS, coarse);
+    }
     if(strip) d_strip(c, Lc, coarse);
 }
 static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, int strip)
@@ -378,7 +441,7 @@ static void mg_up(ccu_ctx *c, int ulev)
     d_interp(c, ulev - 1, L[ulev - 1].vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], 1);
     d_gauss_seidel(c, U, U.vec[CCU_VEC_DEL_VEL], U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], cycles, 1);
     // alpha = <AU,res>/<AU,AU>  (line search, :626-627); both dots share one pass
-    d_dot3(c, U.vlen(), U.vec[CCU_VEC_AU], U.vec[CCU_VEC_AU], S_DOT1, U.vec[CCU_VEC_AU], U.vec[CCU_VEC_RES], S_DOT2);
+    d_dot3m(c, &U, U.vlen(), U.vec[CCU_VEC_AU], U.vec[CCU_VEC_AU], S_DOT1, U.vec[CCU_VEC_AU], U.vec[CCU_VEC_RES], S_DOT2);
     d_axpby(c, U.vlen(), U.vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], coef(c->scal + S_DOT2, c->scal + S_DOT1, 1.0), C_ONE);
     if(ulev == c->cfg.levmax)
         d_axpby(c, U.vlen(), U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], coef(c->scal + S_DOT2, c->scal + S_DOT1, -1.0), C_ONE);
@@ -438,7 +501,7 @@ static int d_multi_grid(ccu_ctx *c, double *d1, double *F)
     }
     d_copy(c, F, L[levmax].vec[CCU_VEC_RES], L[levmax].vlen());
     d_copy(c, d1, L[levmax].vec[CCU_VEC_VEL], L[levmax].vlen());
-    d_dot3(c, L[levmax].vlen(), F, F, S_DOT0);
+    d_dot3m(c, &L[levmax], L[levmax].vlen(), F, F, S_DOT0);
     return 0;
 }
 
@@ -447,10 +510,10 @@ static int d_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, i
 {
     Level &L = c->L[c->cfg.levmax];
     double *r = L.vec[CCU_VEC_T0], *D1 = L.vec[CCU_VEC_T1];
-    const double gneq = (double)L.g.neq;
+    const double gneq = c->comm ? (double)c->comm->gneq : (double)L.g.neq;
     d_copy(c, r, F, L.vlen());
     d_zero(c, d0, L.vlen());
-    d_dot3(c, L.vlen(), r, r, S_DOT0);
+    d_dot3m(c, &L, L.vlen(), r, r, S_DOT0);
     double rr;
     if(read_scal(c, S_DOT0, 1, &rr)) return 1;
     double residual = sqrt(rr / gneq);
@@ -478,6 +541,7 @@ static void d_div_u(ccu_ctx *c, Level &L, const double *U, double *divU)
 static void d_grad_p(ccu_ctx *c, Level &L, const double *P, double *gradP)
 {
     LAUNCH(c, ccu_k_grad_p, cdiv(8 * (size_t)L.g.NC, 128), 128, L.g, L.elt_del, L.flags, P, gradP);
+    if(c->multi()) ccu_halo_sum_vec(c, (int)(&L - c->L), gradP);      // exchange_id_d20 (Element_calculations.c:764)
 }
 
 // solve_Ahat_p_fhat (Stokes_flow_Incomp.c:295-497) on resident V (= vec U), P, F.
@@ -485,13 +549,14 @@ static int d_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *re
 {
     Level &L = c->L[c->cfg.levmax];
     const size_t nv = L.vlen(), np = (size_t)L.g.npno;
-    const double gneq = (double)L.g.neq, gnpno = (double)L.g.npno;
+    const long long ineq = c->comm ? c->comm->gneq : (long long)L.g.neq, inpno = c->comm ? c->comm->gnpno : (long long)L.g.npno;
+    const double gneq = (double)ineq, gnpno = (double)inpno;
     double *V = L.vec[CCU_VEC_U], *F = L.vec[CCU_VEC_F], *Ah = c->uzAh, *u1 = c->uzU1;
     double *r0 = c->r0, *r1 = c->r1, *r2 = c->r2, *z0 = c->z0, *z1 = c->z1, *s1 = c->s1, *s2 = c->s2, *P = c->P, *pAh = c->pAh;
     double h[8];
     int valid = 1;
 
-    d_dot3(c, nv, F, F, S_DOT0);
+    d_dot3m(c, &L, nv, F, F, S_DOT0);
     if(read_scal(c, S_DOT0, 1, h)) return 1;
     const double v_res = sqrt(h[0] / gneq);
 
@@ -536,13 +601,13 @@ static int d_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *re
         d_axpby(c, np, P, s2, alpha, C_ONE);
         d_axpby(c, nv, V, u1, malpha, C_ONE);
         d_div_u(c, L, V, pAh);
-        d_dot3(c, nv, V, V, S_VDOTV, u1, u1, S_U1U1);
+        d_dot3m(c, &L, nv, V, V, S_VDOTV, u1, u1, S_U1U1);
         d_dot3(c, np, P, P, S_PDOTP, pAh, pAh, S_AHAH, s2, s2, S_S2S2);
         if(read_scal(c, S_R1Z1, S_U1U1 - S_R1Z1 + 1, h)) return 1;
         const double r1z1 = h[0], s2ah = h[S_S2AH - S_R1Z1], vdotv = h[S_VDOTV - S_R1Z1], pdotp = h[S_PDOTP - S_R1Z1];
         const double ahah = h[S_AHAH - S_R1Z1], s2s2 = h[S_S2S2 - S_R1Z1], u1u1 = h[S_U1U1 - S_R1Z1];
         const double al = valid ? r1z1 / s2ah : 0.0;
-        const float incomp = (float)sqrt((double)(L.g.neq / L.g.npno) * (1.0e-32 + ahah / (1.0e-32 + (double)(float)vdotv)));
+        const float incomp = (float)sqrt((double)(ineq / inpno) * (1.0e-32 + ahah / (1.0e-32 + (double)(float)vdotv)));
         dpressure = (float)(al * sqrt(s2s2 / (1.0e-32 + (double)(float)pdotp)));
         dvelocity = (float)(al * sqrt(u1u1 / (1.0e-32 + (double)(float)vdotv)));
         if(hist)
@@ -774,7 +839,7 @@ int ccu_global_vdot(ccu_ctx *c, int lev, const double *A, const double *B, doubl
     if(vec_h2d(c, L, A, L.vec[CCU_VEC_VEL])) return 1;
     CK(cudaStreamSynchronize(c->st));
     if(vec_h2d(c, L, B, L.vec[CCU_VEC_RES])) return 1;
-    d_dot3(c, L.vlen(), L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_RES], S_TMP);
+    d_dot3m(c, &L, L.vlen(), L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_RES], S_TMP);
     return read_scal(c, S_TMP, 1, out);
 }
 int ccu_global_pdot(ccu_ctx *c, int lev, const double *A, const double *B, double *out)

@@ -66,6 +66,7 @@ class CartesianProblem:
     rank = z + nprocz*x + nprocz*nprocx*y (Parallel_related.c:108-121)."""
 
     def __init__(self, text: str, me_loc=(0, 0, 0)):
+        self.text = text
         p = self.params = parse_input(text)
         g = lambda k, d=None: p.get(k, d)  # noqa: E731
         if g("Geometry", "cart3d") != "cart3d":
@@ -297,5 +298,27 @@ class CartesianProblem:
         W = np.outer(w1(ys), w1(xs))
         H = np.tensordot(W, b.astype(np.float64), axes=([0, 1], [0, 1])) / W.sum()
         if self.nproc[0] * self.nproc[1] != 1:
-            raise NotImplementedError("buoyancy(): layer average across ranks is done by the caller")
+            raise NotImplementedError("buoyancy(): the layer average spans ranks; use global_problem().buoyancy + local_slice")
         return (b - H.astype(f32)[None, None, :]).astype(f32).reshape(-1)
+
+    # ---------------------------------------------------------------- global <-> subdomain views
+    def global_problem(self) -> "CartesianProblem":
+        """The same input file seen by a single rank owning the whole mesh."""
+        if self.nproc == (1, 1, 1):
+            return self
+        return CartesianProblem(self.text + "nprocx=1\nnprocy=1\nnprocz=1\n")
+
+    def local_slice(self, field, lev=None, per_node=1):
+        """This subdomain's part (duplicated faces included) of a nodal field given on the global mesh."""
+        lev = self.levmax if lev is None else lev
+        nox, noy, noz = self.dims(lev)
+        a = np.asarray(field).reshape(self.NOY[lev], self.NOX[lev], self.NOZ[lev], per_node)
+        i0, j0, k0 = self.NYS[lev] - 1, self.NXS[lev] - 1, self.NZS[lev] - 1
+        return np.ascontiguousarray(a[i0:i0 + noy, j0:j0 + nox, k0:k0 + noz]).reshape(-1)
+
+    def local_slice_elements(self, field, lev=None, per_elt=1):
+        lev = self.levmax if lev is None else lev
+        nox, noy, noz = self.dims(lev)
+        a = np.asarray(field).reshape(self.NOY[lev] - 1, self.NOX[lev] - 1, self.NOZ[lev] - 1, per_elt)
+        i0, j0, k0 = self.NYS[lev] - 1, self.NXS[lev] - 1, self.NZS[lev] - 1
+        return np.ascontiguousarray(a[i0:i0 + noy - 1, j0:j0 + nox - 1, k0:k0 + noz - 1]).reshape(-1)

@@ -74,6 +74,21 @@ class StokesContext:
     def synchronize(self):
         check(self.lib.ccu_synchronize(self._ctx))
 
+    # -- subdomain-per-GPU runs
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.lib().ccu_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nproc, me_loc, unique_id: bytes | None):
+        """Collective over all ranks: duplicated-node tables + NCCL communicator (parallel_domain_decomp1 /
+        parallel_communication_routs1, Parallel_related.c:80,477).  Must precede the operator construction."""
+        uid = None if unique_id is None else C.create_string_buffer(bytes(unique_id), 128)
+        check(self.lib.ccu_comm_init(self._ctx, int(nproc[0]), int(nproc[1]), int(nproc[2]), int(me_loc[0]), int(me_loc[1]),
+                                     int(me_loc[2]), uid))
+        self.nproc, self.me_loc = tuple(nproc), tuple(me_loc)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ccu_launch_count(self._ctx))
@@ -354,13 +369,15 @@ def context_from_dump(dump, **overrides) -> StokesContext:
     return ctx
 
 
-def context_from_problem(prob, device=0, **overrides) -> StokesContext:
+def context_from_problem(prob, device=0, unique_id=None, **overrides) -> StokesContext:
     """Build a context for one subdomain of a `citcomcu_b200.problem.CartesianProblem`: mesh, flags and
     coordinates go up, every operator array is then constructed on the device (ccu_build_geometry here,
     viscosity / stiffness at the first general_stokes_solver call)."""
     kw = {k: prob.control[k] for k in ("v_steps_low", "v_steps_high", "down_heavy", "up_heavy", "mg_cycle", "p_iterations", "accuracy")}
     kw.update(overrides)
     ctx = StokesContext(prob.levmin, prob.levmax, prob.nox, prob.noy, prob.noz, device=device, **kw)
+    if prob.nproc != (1, 1, 1):
+        ctx.comm_init(prob.nproc, prob.me_loc, unique_id)
     for lev in range(prob.levmin, prob.levmax + 1):
         ctx.set_node_flags(lev, prob.node_flags(lev))
         ctx.set_coordinates(lev, *prob.coordinates(lev))

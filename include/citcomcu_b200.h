@@ -53,6 +53,23 @@ int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);
 
+/* ---- subdomain-per-GPU runs: the reference's nprocx x nprocy x nprocz block decomposition
+ * (Parallel_related.c:80-173), one process and one ccu_ctx per GPU, rank = z + nprocz*x + nprocz*nprocx*y.
+ * Every level's mesh sizes in ccu_config are the LOCAL ones (E->lmesh.*), face nodes duplicated as in the reference.
+ * ccu_comm_unique_id: rank 0 obtains a 128-byte NCCL id and hands it to all ranks by any means (the reference's
+ * MPI_Bcast, torch.distributed, a file); ccu_comm_init: collective over all ranks, replaces parallel_domain_decomp1 /
+ * parallel_communication_routs1 (Parallel_related.c:80,477): builds the duplicated-node tables of every level and the
+ * NCCL communicator.  After it, every entry point below performs the halo sums (exchange_id_d20 / exchange_node_f20,
+ * Parallel_related.c:1181,1270) and global reductions (global_vdot / global_pdot) of the reference internally.
+ * nproc = 1x1x1 is allowed (no NCCL needed) and is the default when ccu_comm_init is never called. */
+int ccu_comm_unique_id(char *out128);
+int ccu_comm_init(ccu_ctx *ctx, int nprocx, int nprocy, int nprocz, int me_x, int me_y, int me_z, const char *unique_id128);
+/* host-only table builders behind ccu_comm_init (no GPU needed; tests/test_decomp.py): sizes = {neighbours, packed nodes,
+ * duplicated nodes, contributions}; see csrc/ccu_comm.cuh for the meaning of the arrays */
+int ccu_halo_sizes(const int nproc[3], const int me[3], int nox, int noy, int noz, int sizes[4]);
+int ccu_halo_tables(const int nproc[3], const int me[3], int nox, int noy, int noz, int *nb_rank, int *nb_off, int *nb_cnt,
+                    int *send_n, int *sh_n, int *sh_ptr, int *sh_src, unsigned char *owned);
+
 /* ---- operator upload (what construct_stiffness_B_matrix, Construct_arrays.c:834, leaves in E) ---- */
 /* E->NODE[lev]+1 : flag bits VBX 0x2, VBZ 0x4, VBY 0x8 (global_defs.h:65-89) */
 int ccu_set_node_flags(ccu_ctx *ctx, int lev, const unsigned *node /*[nno]*/);

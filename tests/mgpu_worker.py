@@ -1,0 +1,72 @@
+"""One rank of a multi-GPU parity run (spawned by tests/test_gpu_multi.py, one process per GPU).
+
+Every rank builds its subdomain of the same input file, joins the library's NCCL communicator, and returns
+its part of: a matvec on a seeded global vector, a smoother call, and the converged Stokes solve."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def seeded_global_vector(gp, lev, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, 3 * gp.nno(lev))
+
+
+def run_rank(rank, world, text, uid_q, out_q, accuracy, device_of_rank=None):
+    try:
+        from citcomcu_b200 import decomp
+        from citcomcu_b200.problem import CartesianProblem
+        from citcomcu_b200.stokes import StokesContext, context_from_problem
+        nproc = CartesianProblem(text).nproc
+        me = decomp.me_loc_of(rank, nproc)
+        prob = CartesianProblem(text, me_loc=me)
+        gp = prob.global_problem()
+        if rank == 0:
+            uid = StokesContext.comm_unique_id()
+            for _ in range(world - 1):
+                uid_q.put(uid)
+        else:
+            uid = uid_q.get(timeout=120)
+        dev = rank if device_of_rank is None else device_of_rank[rank]
+        ctx = context_from_problem(prob, device=dev, unique_id=uid, accuracy=accuracy)
+        lm = prob.levmax
+        Tg = gp.initial_temperature()
+        bg = gp.buoyancy(Tg)
+        T, b = prob.local_slice(Tg), prob.local_slice(bg)
+        ctl = prob.control
+        res = {"rank": rank, "me": me}
+        ctx.set_temperature(T)
+        res["F"] = ctx.assemble_forces(b)
+        ctx.get_system_viscosity()
+        ctx.construct_stiffness_B_matrix(ctl["augmented_Lagr"], ctl["augmented"], ctl["precondition"])
+        for lev in range(prob.levmin, prob.levmax + 1):
+            ug = seeded_global_vector(gp, lev, 100 + lev)
+            u = prob.local_slice(ug, lev, 3)
+            res[f"Au{lev}"] = ctx.n_assemble_del2_u(u, lev, 1)
+            res[f"dot{lev}"] = ctx.global_vdot(u, u, lev)
+            if lev > prob.levmin:
+                res[f"proj{lev}"] = ctx.project_vector(lev, u)
+            if lev < prob.levmax:
+                res[f"interp{lev}"] = ctx.interp_vector(lev, u)
+        pg = np.random.default_rng(7).uniform(-1, 1, gp.nel(lm))
+        res["gradp"] = ctx.assemble_grad_p(prob.local_slice_elements(pg), lm)
+        res["MASS"] = ctx.get_level_array(lm, "MASS")
+        res["BPI"] = ctx.get_level_array(lm, "BPI")
+        fg = seeded_global_vector(gp, lm, 55)
+        f = ctx.strip_bcs_from_residual(prob.local_slice(fg, lm, 3), lm)
+        d0, Ad = ctx.gauss_seidel(f, 2, lm, 0)
+        res["gs_d0"], res["gs_Ad"] = d0, Ad
+        res["gs_KD"] = ctx.n_assemble_del2_u(d0, lm, 1)
+        U, P, its, r = ctx.general_stokes_solver(T, b, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
+                                                 precondition=ctl["precondition"], guess=0)
+        res["U"], res["P"], res["its"] = U, P, its
+        res["launches"] = ctx.launch_count
+        ctx.close()
+        out_q.put(res)
+    except Exception as e:  # surface the failure in the parent instead of hanging it
+        import traceback
+        out_q.put({"rank": rank, "error": f"{e}\n{traceback.format_exc()}"})

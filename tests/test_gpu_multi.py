@@ -1,0 +1,105 @@
+"""Multi-GPU parity (needs >= 2 GPUs; one process per GPU over the library's NCCL communicator).
+
+Checker: (1) the same operators on ONE GPU owning the whole mesh (decomposition must not change K u, dots,
+transfers beyond summation order); (2) the unmodified reference run with the same processor grid over the
+oracle's process-based MPI shim: converged U, P within 1e-6 relative L2 (north star) at accuracy 1e-8."""
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import has_gpu, po
+from citcomcu_b200 import inputfile
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def spawn(text, world, accuracy):
+    import torch.multiprocessing as mp
+    from mgpu_worker import run_rank
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=run_rank, args=(r, world, text, uid_q, out_q, accuracy)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for r in res:
+        assert "error" not in r, r["error"]
+    return sorted(res, key=lambda r: r["rank"])
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("nproc", [(2, 1, 1), (1, 1, 2), (1, 2, 1)])
+def test_two_subdomains_match_single_gpu_and_reference(nproc):
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    from mgpu_worker import seeded_global_vector
+    acc = 1e-8
+    text = inputfile.tdepv_box(16, 16, 8, 3, nproc=nproc, maxstep=1, accuracy=acc)
+    res = spawn(text, 2, acc)
+    # single-GPU run of the whole mesh
+    gp = CartesianProblem(text).global_problem()
+    ctx = context_from_problem(gp, accuracy=acc)
+    Tg = gp.initial_temperature()
+    bg = gp.buoyancy(Tg)
+    ctl = gp.control
+    ctx.set_temperature(Tg)
+    Fg = ctx.assemble_forces(bg)
+    ctx.get_system_viscosity()
+    ctx.construct_stiffness_B_matrix(ctl["augmented_Lagr"], ctl["augmented"], ctl["precondition"])
+    lm = gp.levmax
+    for r in res:
+        prob = CartesianProblem(text, me_loc=r["me"])
+        assert rel(r["F"], prob.local_slice(Fg, lm, 3)) < 1e-12
+        assert rel(r["MASS"], prob.local_slice(ctx.get_level_array(lm, "MASS"))) < 1e-6
+        assert rel(r["BPI"], prob.local_slice_elements(ctx.get_level_array(lm, "BPI"))) < 1e-6
+        for lev in range(gp.levmin, gp.levmax + 1):
+            ug = seeded_global_vector(gp, lev, 100 + lev)
+            # K is stored in fp32 from a different (per-subdomain) summation order on the duplicated faces
+            assert rel(r[f"Au{lev}"], prob.local_slice(ctx.n_assemble_del2_u(ug, lev, 1), lev, 3)) < 2e-6
+            assert abs(r[f"dot{lev}"] - ug @ ug) < 1e-12 * (ug @ ug)
+            if lev > gp.levmin:
+                assert rel(r[f"proj{lev}"], prob.local_slice(ctx.project_vector(lev, ug), lev - 1, 3)) < 1e-6
+            if lev < gp.levmax:
+                assert rel(r[f"interp{lev}"], prob.local_slice(ctx.interp_vector(lev, ug), lev + 1, 3)) < 1e-12
+        pg = np.random.default_rng(7).uniform(-1, 1, gp.nel(lm))
+        assert rel(r["gradp"], prob.local_slice(ctx.assemble_grad_p(pg, lm), lm, 3)) < 1e-12
+        # gauss_seidel returns Ad = K d0 also across subdomains
+        assert rel(r["gs_Ad"], r["gs_KD"]) < 1e-12
+    Ug, Pg, its_g, _ = ctx.general_stokes_solver(Tg, bg, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
+                                                 precondition=ctl["precondition"], guess=0)
+    ctx.close()
+    num_u = den_u = num_p = den_p = 0.0
+    for r in res:
+        prob = CartesianProblem(text, me_loc=r["me"])
+        own = __import__("citcomcu_b200.decomp", fromlist=["x"]).halo_tables(nproc, r["me"], *prob.dims(lm))["owned"].astype(bool)
+        ul = prob.local_slice(Ug, lm, 3).reshape(-1, 3)
+        num_u += ((r["U"].reshape(-1, 3) - ul)[own] ** 2).sum(); den_u += (ul[own] ** 2).sum()
+        pl = prob.local_slice_elements(Pg)
+        num_p += ((r["P"] - pl) ** 2).sum(); den_p += (pl ** 2).sum()
+    assert np.sqrt(num_u / den_u) < 1e-6 and np.sqrt(num_p / den_p) < 1e-6
+    assert abs(res[0]["its"] - its_g) <= 3
+    # the unmodified reference on the same processor grid
+    if po.have_ref():
+        dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_mgpu_")), nsteps=0, nproc=2)
+        num_u = den_u = num_p = den_p = 0.0
+        for r, d in zip(res, dumps):
+            assert tuple(d.control()["me_loc"]) == tuple(r["me"])
+            num_u += ((r["U"] - d["s0_U"]) ** 2).sum(); den_u += (d["s0_U"] ** 2).sum()
+            num_p += ((r["P"] - d["s0_P"]) ** 2).sum(); den_p += (d["s0_P"] ** 2).sum()
+        assert np.sqrt(num_u / den_u) < 1e-6 and np.sqrt(num_p / den_p) < 1e-6
