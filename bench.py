@@ -274,6 +274,8 @@ def run_ours(args):
     relax_ms, relax_n = ctx.profile_read("relax_fine")
     mv_ms, mv_n = ctx.profile_read("matvec_fine")
     build_ms, _ = ctx.profile_read("build")
+    coarse_ms, coarse_n = ctx.profile_read("coarse")
+    transfer_ms, _ = ctx.profile_read("transfer_fine")
     ctx.profile_enable(False)
     clk = clocks.stop()
     # e2e: host buffers through the C ABI
@@ -303,6 +305,9 @@ def run_ours(args):
             "matvec": {"achieved": mv_gbs, "frac": mv_gbs / peak, "launches": mv_n, "avg_launch_ms": mv_ms / max(mv_n, 1),
                        "share_of_step": mv_ms / (total_s * 1e3)},
             "operator_rebuild_ms_per_step": build_ms / args.steps,
+            "step_breakdown_ms": {"relax_fine": relax_ms / args.steps, "matvec_fine": mv_ms / args.steps, "build": build_ms / args.steps,
+                                  "coarse_levels": coarse_ms / args.steps, "transfer_fine": transfer_ms / args.steps,
+                                  "other_fine_vector_ops_and_sync": (total_s * 1e3 - relax_ms - mv_ms - build_ms - coarse_ms - transfer_ms) / args.steps},
             "uzawa_iterations": its, "gpu_launches": launches * world, "clocks": clk, "setup_s": setup_s,
             "e2e": {"value": e2e_s / args.steps, "unit": "s", "h2d_bytes_per_step": int(T_h.nbytes + b_h.nbytes) * world,
                     "d2h_bytes_per_step": int(U_h.nbytes + P_h.nbytes) * world}}

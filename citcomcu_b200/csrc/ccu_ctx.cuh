@@ -35,6 +35,8 @@ struct Level
     float *XX = nullptr;          // [3][nno] node coordinates, natural order (E->XX[lev][1..3])
     float *EVI = nullptr;         // [nel*8] viscosity at Gauss points
     unsigned *node = nullptr;     // [nno] raw NODE flags, natural order
+    // shared-memory resident bottom smoother (ccu_k_relax_smem): compact tables, built on first use
+    int sm_n = 0, sm_cstart[9] = { 0 }; int *sm_s = nullptr; unsigned short *sm_nbr = nullptr;
     bool have_K = false, have_flags = false, have_tw = false, have_p = false, have_xx = false, have_evi = false;
     size_t vlen() const { return 3 * (size_t)g.NS; }
 };
@@ -67,7 +69,8 @@ struct ccu_ctx
     GraphSeg seg[4];
     bool use_graphs = true;
     // kernel selection by level size (lanes per node), ccu_set_option
-    int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 2000000, opt_lanes_large = 1;
+    int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
+    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 439, opt_matvec_tab_nodes = 10000;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials
@@ -99,8 +102,9 @@ struct ccu_ctx
 // scoped event pair around a group of launches of one class
 struct CcuProfScope
 {
-    ccu_ctx *c; int cls; long long n0; cudaEvent_t e0 = nullptr;
-    CcuProfScope(ccu_ctx *ctx, int cls_, bool active) : c(active && ctx->prof_on ? ctx : nullptr), cls(cls_), n0(ctx->launches)
+    ccu_ctx *c; int cls; long long units; cudaEvent_t e0 = nullptr;
+    // `units` = what the class counts per scope (colour-pass launches of the smoother, products of the matvec, ...)
+    CcuProfScope(ccu_ctx *ctx, int cls_, bool active, long long units_ = 1) : c(active && ctx->prof_on ? ctx : nullptr), cls(cls_), units(units_)
     {
         if(!c) return;
         e0 = get(); cudaEventRecord(e0, c->st);
@@ -109,7 +113,7 @@ struct CcuProfScope
     {
         if(!c) return;
         cudaEvent_t e1 = get(); cudaEventRecord(e1, c->st);
-        c->prof_recs.push_back({ cls, e0, e1, c->launches - n0 });
+        c->prof_recs.push_back({ cls, e0, e1, units });
     }
     cudaEvent_t get()
     {

@@ -339,6 +339,89 @@ __global__ void __launch_bounds__(128) ccu_k_face_damp_BI(const CcuGeom g, const
     }
 }
 
+// ---------------------------------------------------------------- bottom level, shared-memory resident
+// The coarsest level (a few hundred nodes: 9x9x5 at 256x256x128 / 6 levels) is smoothed v_steps_low = 20 times at the
+// bottom of every V-cycle (General_matrix_functions.c:572-574, 611-613).  Its whole half-matrix fits in ONE SM's shared
+// memory (126 floats * n <= 227 KB for n <= 439), so a single CTA loads it once, keeps the solution in shared memory
+// and runs every sweep and colour phase out of it: one thread per node, nodes sorted by colour so that a phase is a
+// contiguous thread range reading consecutive shared-memory words.  Column n of the tables is a zero dummy that
+// out-of-grid neighbours point at (the reference's "equation neq+1", Construct_arrays.c:305-309).
+struct CcuSmemLevel
+{
+    int n = 0;                       // nodes
+    int cstart[9] = { 0 };           // thread range of each colour
+    int *s = nullptr;                // [n] storage slot of compact node t
+    unsigned short *nbr = nullptr;   // [27][n] compact index of block b's neighbour (n = none)
+};
+__global__ void __launch_bounds__(512) ccu_k_relax_smem(const CcuGeom g, const CcuSmemLevel sl, const float *__restrict__ K,
+                                                         const double *__restrict__ BI, const double *__restrict__ F, double *x,
+                                                         const int cycles, const int zero_first)
+{
+    extern __shared__ double smem_d[];
+    const int n = sl.n, n1 = n + 1, t = threadIdx.x;
+    const size_t NS = (size_t)g.NS;
+    double *xs = smem_d;                               // [3][n1]
+    float *Ks = (float *)(smem_d + 3 * n1);            // [126][n1]
+    if(t < n)
+    {   // every thread streams its own node's 126 coefficients (independent loads, consecutive threads ~ consecutive slots)
+        const int st = sl.s[t];
+#pragma unroll 18
+        for(int q = 0; q < 126; q++) Ks[q * n1 + t] = __ldg(K + (size_t)q * NS + st);
+    }
+    for(int q = t; q < 126; q += blockDim.x) Ks[q * n1 + n] = 0.0f;
+    for(int idx = t; idx < 3 * n1; idx += blockDim.x)
+    {
+        const int d = idx / n1, tt = idx - d * n1;
+        xs[idx] = (tt < n && !zero_first) ? x[d * NS + sl.s[tt]] : 0.0;
+    }
+    int col = -1, s = 0;
+    double f0 = 0, f1 = 0, f2 = 0, b0 = 0, b1 = 0, b2 = 0;
+    unsigned short nb[27];
+    if(t < n)
+    {
+        s = sl.s[t];
+        for(int c = 0; c < 8; c++) if(t >= sl.cstart[c] && t < sl.cstart[c + 1]) col = c;
+        f0 = F[s]; f1 = F[NS + s]; f2 = F[2 * NS + s];
+        b0 = BI[s]; b1 = BI[NS + s]; b2 = BI[2 * NS + s];
+#pragma unroll
+        for(int b = 0; b < 27; b++) nb[b] = sl.nbr[b * n + t];
+    }
+    __syncthreads();
+    for(int sw = 0; sw < cycles; sw++)
+        for(int c = 7; c >= 0; c--)
+        {
+            if(col == c)
+            {
+                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll
+                for(int b = 0; b < 14; b++)
+                {
+                    const int m = nb[b];
+                    const float *kp = Ks + (b * 9) * n1 + t;
+                    const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
+                    r0 += (double)kp[0] * x0 + (double)kp[n1] * x1 + (double)kp[2 * n1] * x2;
+                    r1 += (double)kp[3 * n1] * x0 + (double)kp[4 * n1] * x1 + (double)kp[5 * n1] * x2;
+                    r2 += (double)kp[6 * n1] * x0 + (double)kp[7 * n1] * x1 + (double)kp[8 * n1] * x2;
+                }
+#pragma unroll
+                for(int b = 14; b < 27; b++)
+                {
+                    const int m = nb[b];
+                    const float *kp = Ks + ((b - 13) * 9) * n1 + m;
+                    const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
+                    r0 += (double)kp[0] * x0 + (double)kp[3 * n1] * x1 + (double)kp[6 * n1] * x2;
+                    r1 += (double)kp[n1] * x0 + (double)kp[4 * n1] * x1 + (double)kp[7 * n1] * x2;
+                    r2 += (double)kp[2 * n1] * x0 + (double)kp[5 * n1] * x1 + (double)kp[8 * n1] * x2;
+                }
+                xs[t] += (double)(float)((f0 - r0) * b0);
+                xs[n1 + t] += (double)(float)((f1 - r1) * b1);
+                xs[2 * n1 + t] += (double)(float)((f2 - r2) * b2);
+            }
+            __syncthreads();
+        }
+    if(t < n) { x[s] = xs[t]; x[NS + s] = xs[n1 + t]; x[2 * NS + s] = xs[2 * n1 + t]; }
+}
+
 // Au = K*u for all nodes (n_assemble_del2_u, Element_calculations.c:552).  One warp per colour,
 // the eight warps of a block cover the same 32 cells, so the transposed reads of a block hit
 // lines its sibling warps stream in at the same time: each coefficient crosses HBM once.
@@ -376,6 +459,108 @@ __global__ void __launch_bounds__(256) ccu_k_matvec(const CcuGeom g, const float
     }
     if(MODE == 0) { out[s] = a0; out[NS + s] = a1; out[2 * NS + s] = a2; }
     else { out[s] = rhs[s] - a0; out[NS + s] = rhs[NS + s] - a1; out[2 * NS + s] = rhs[2 * NS + s] - a2; }
+}
+
+// ---------------------------------------------------------------- table-driven row product (large levels)
+// The fully unrolled ccu_row_product<C> is ~2000 instructions per colour; a kernel that runs all eight colours side
+// by side (the matvec: one warp per colour so that sibling warps share the transposed lines) then thrashes the
+// instruction cache (ncu r01: `no_instruction` was its top stall, 17 % of DRAM peak).  Here the 27 neighbour offsets
+// of every colour come from a per-level table in the kernel parameters (constant bank, warp-uniform index) and one
+// short loop serves all colours.
+struct CcuStencil
+{
+    int off[8][27];      // storage-slot offset of block b's neighbour relative to the node's own slot, by colour
+};
+__host__ inline CcuStencil ccu_make_stencil(const CcuGeom &g)
+{
+    const int LO[13][3] = CCU_LO_INIT;
+    CcuStencil st;
+    for(int c = 0; c < 8; c++)
+    {
+        const int pi = (c >> 2) & 1, pj = (c >> 1) & 1, pk = c & 1;
+        for(int b = 0; b < 27; b++)
+        {
+            int di = 0, dj = 0, dk = 0;
+            if(b >= 1 && b <= 13) { di = LO[b - 1][0]; dj = LO[b - 1][1]; dk = LO[b - 1][2]; }
+            if(b >= 14) { di = -LO[b - 14][0]; dj = -LO[b - 14][1]; dk = -LO[b - 14][2]; }
+            const int cm = c ^ (((di != 0) << 2) | ((dj != 0) << 1) | (dk != 0));
+            st.off[c][b] = (cm - c) * g.NC + ccu_shift(pi, di) * g.JK + ccu_shift(pj, dj) * g.Kd + ccu_shift(pk, dk);
+        }
+    }
+    return st;
+}
+template <int U>
+__device__ __forceinline__ void ccu_row_product_tab(const size_t NS, const int *__restrict__ off, const float *__restrict__ K,
+                                                    const double *x, const int s, double &a0, double &a1, double &a2)
+{
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll U
+    for(int b = 0; b < 14; b++)
+    {   // self + own blocks, stored at this node
+        const int sm = s + off[b];
+        const float *Kp = K + (size_t)(b * 9) * NS + s;
+        float k[9];
+#pragma unroll
+        for(int e = 0; e < 9; e++) k[e] = __ldg(Kp + (size_t)e * NS);
+        const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
+        r0 += (double)k[0] * x0 + (double)k[1] * x1 + (double)k[2] * x2;
+        r1 += (double)k[3] * x0 + (double)k[4] * x1 + (double)k[5] * x2;
+        r2 += (double)k[6] * x0 + (double)k[7] * x1 + (double)k[8] * x2;
+    }
+#pragma unroll U
+    for(int b = 14; b < 27; b++)
+    {   // transposed blocks, stored at the upper neighbours
+        const int sm = s + off[b];
+        const float *Kp = K + (size_t)((b - 13) * 9) * NS + sm;
+        float k[9];
+#pragma unroll
+        for(int e = 0; e < 9; e++) k[e] = __ldg(Kp + (size_t)e * NS);
+        const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
+        r0 += (double)k[0] * x0 + (double)k[3] * x1 + (double)k[6] * x2;
+        r1 += (double)k[1] * x0 + (double)k[4] * x1 + (double)k[7] * x2;
+        r2 += (double)k[2] * x0 + (double)k[5] * x1 + (double)k[8] * x2;
+    }
+    a0 = r0; a1 = r1; a2 = r2;
+}
+template <int MODE, int U>
+__global__ void __launch_bounds__(256) ccu_k_matvec_tab(const CcuGeom g, const __grid_constant__ CcuStencil st, const float *__restrict__ K,
+                                                         const unsigned char *__restrict__ flags, const double *u,
+                                                         const double *rhs, double *out, const int strip)
+{
+    const int c = threadIdx.x >> 5;
+    const int cell = blockIdx.x * 32 + (threadIdx.x & 31);
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    const size_t NS = (size_t)g.NS;
+    const int s = c * g.NC + cell;
+    double a0, a1, a2;
+    ccu_row_product_tab<U>(NS, st.off[c], K, u, s, a0, a1, a2);
+    if(strip)
+    {
+        const unsigned char f = flags[s];
+        if(f & CCU_F_VBX) a0 = 0.0;
+        if(f & CCU_F_VBY) a1 = 0.0;
+        if(f & CCU_F_VBZ) a2 = 0.0;
+    }
+    if(MODE == 0) { out[s] = a0; out[NS + s] = a1; out[2 * NS + s] = a2; }
+    else { out[s] = rhs[s] - a0; out[NS + s] = rhs[NS + s] - a1; out[2 * NS + s] = rhs[2 * NS + s] - a2; }
+}
+// one colour pass of the smoother with the same table-driven row (colour = kernel argument)
+template <int U>
+__global__ void __launch_bounds__(128) ccu_k_relax_tab(const CcuGeom g, const __grid_constant__ CcuStencil st, const int c,
+                                                        const float *__restrict__ K, const double *__restrict__ BI,
+                                                        const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    const int s = c * g.NC + cell;
+    if(bits && (bits[s] & CCU_B_SHARED)) return;
+    double a0, a1, a2;
+    ccu_row_product_tab<U>((size_t)g.NS, st.off[c], K, x, s, a0, a1, a2);
+    ccu_relax_update(g, BI, F, x, s, a0, a1, a2);
 }
 
 // T lanes per node variant of the matvec (coarse and mid levels): thread -> (colour, cell, lane)

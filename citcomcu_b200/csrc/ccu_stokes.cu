@@ -34,6 +34,8 @@ int ccu_check_lev(ccu_ctx *c, int lev)
     return 0;
 }
 
+static int ensure_smem_tables(ccu_ctx *c, Level &L);
+
 int ccu_create(const ccu_config *cfg, ccu_ctx **out)
 {
     if(!cfg || !out) FAIL("ccu_create: null argument");
@@ -81,6 +83,8 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
         double **pv[] = { &c->P, &c->r0, &c->r1, &c->r2, &c->z0, &c->z1, &c->s1, &c->s2, &c->pAh };
         for(auto p : pv) { CK(cudaMalloc(p, sizeof(double) * np)); CK(cudaMemsetAsync(*p, 0, sizeof(double) * np, c->st)); }
     }
+    for(int lev = cfg->levmin; lev <= cfg->levmax; lev++)
+        if(c->L[lev].g.nno <= 439 && ensure_smem_tables(c, c->L[lev])) return 1;
     CK(cudaMalloc(&c->scal, sizeof(double) * S_COUNT));
     CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_COUNT, c->st));
     { const double one = 1.0; CK(cudaMemcpyAsync(c->scal + S_ONE, &one, sizeof(double), cudaMemcpyHostToDevice, c->st)); }
@@ -103,7 +107,7 @@ void ccu_destroy(ccu_ctx *c)
     {
         Level &L = c->L[lev];
         cudaFree(L.K); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.BPI);
-        cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node);
+        cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
     cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
@@ -134,6 +138,9 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_WARP_NODES: c->opt_warp_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_QUAD_NODES: c->opt_quad_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_LANES_LARGE: if(value != 1 && value != 4) FAIL("lanes must be 1 or 4"); c->opt_lanes_large = value; drop_graphs(c); return 0;
+    case CCU_OPT_SMEM_NODES: c->opt_smem_nodes = value > 439 ? 439 : value; drop_graphs(c); return 0;
+    case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
+    case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
     default: FAIL("set_option: unknown option");
     }
 }
@@ -276,9 +283,11 @@ static int lanes_for(const ccu_ctx *c, const Level &L)
 static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int strip)
 {
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
-    const int T = lanes_for(c, L);
+    const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);   // the table-driven kernel wins from ~1e4 nodes up
     if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    else if(c->opt_matvec_tab >= 4) LAUNCH(c, (ccu_k_matvec_tab<0, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
+    else if(c->opt_matvec_tab) LAUNCH(c, (ccu_k_matvec_tab<0, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     if(c->multi()) ccu_halo_sum_vec(c, (int)(&L - c->L), Au);      // exchange_id_d20 (Element_calculations.c:612)
 }
@@ -292,10 +301,61 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
         return;
     }
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
-    const int T = lanes_for(c, L);
+    const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
+    if(c->opt_matvec_tab >= 4) { LAUNCH(c, (ccu_k_matvec_tab<1, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
+    if(c->opt_matvec_tab) { LAUNCH(c, (ccu_k_matvec_tab<1, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     LAUNCH(c, ccu_k_matvec<1>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, rhs, out, 1);
+}
+
+// compact colour-sorted tables of a tiny level for ccu_k_relax_smem
+static int ensure_smem_tables(ccu_ctx *c, Level &L)
+{
+    if(L.sm_s) return 0;
+    const CcuGeom &g = L.g;
+    const int LO[13][3] = CCU_LO_INIT;
+    const int n = g.nno;
+    std::vector<int> s(n), compact((size_t)g.NS, n);
+    int t = 0;
+    for(int col = 0; col < 8; col++)
+    {
+        L.sm_cstart[col] = t;
+        for(int cell = 0; cell < g.NC; cell++)
+        {
+            int i, j, k;
+            if(!ccu_decode(g, col, cell, i, j, k)) continue;
+            s[t] = col * g.NC + cell;
+            compact[s[t]] = t;
+            t++;
+        }
+    }
+    L.sm_cstart[8] = t;
+    if(t != n) FAIL("smem tables: node count mismatch");
+    std::vector<unsigned short> nbr((size_t)27 * n);
+    for(int tt = 0; tt < n; tt++)
+    {
+        const int col = s[tt] / g.NC, cell = s[tt] % g.NC;
+        int i, j, k;
+        ccu_decode(g, col, cell, i, j, k);
+        for(int b = 0; b < 27; b++)
+        {
+            int di = 0, dj = 0, dk = 0;
+            if(b >= 1 && b <= 13) { di = LO[b - 1][0]; dj = LO[b - 1][1]; dk = LO[b - 1][2]; }
+            if(b >= 14) { di = -LO[b - 14][0]; dj = -LO[b - 14][1]; dk = -LO[b - 14][2]; }
+            const int ii = i + di, jj = j + dj, kk = k + dk;
+            const bool in = ii >= 0 && ii < g.noy && jj >= 0 && jj < g.nox && kk >= 0 && kk < g.noz;
+            nbr[(size_t)b * n + tt] = (unsigned short)(in ? compact[ccu_sidx(g, ii, jj, kk)] : n);
+        }
+    }
+    CK(cudaMalloc(&L.sm_s, sizeof(int) * n));
+    CK(cudaMalloc(&L.sm_nbr, sizeof(unsigned short) * 27 * n));
+    CK(cudaMemcpy(L.sm_s, s.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.sm_nbr, nbr.data(), sizeof(unsigned short) * 27 * n, cudaMemcpyHostToDevice));
+    L.sm_n = n;
+    static bool attr_set = false;
+    if(!attr_set) { CK(cudaFuncSetAttribute(ccu_k_relax_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); attr_set = true; }
+    return 0;
 }
 
 template <int T>
@@ -326,10 +386,19 @@ static void relax_faces(ccu_ctx *c, Level &L, double *x, const double *F)
 }
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
-    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax]);
+    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], 8LL * cycles);
     const int T = lanes_for(c, L);
     if(T == 0)
     {   // one CTA does every sweep and colour of a tiny level in a single launch
+        if(L.g.nno <= c->opt_smem_nodes && L.sm_s)
+        {   // ... out of shared memory when the whole half-matrix fits
+            CcuSmemLevel sl; sl.n = L.sm_n; sl.s = L.sm_s; sl.nbr = L.sm_nbr;
+            for(int q = 0; q < 9; q++) sl.cstart[q] = L.sm_cstart[q];
+            const size_t bytes = (size_t)(L.sm_n + 1) * (3 * sizeof(double) + 126 * sizeof(float));
+            ccu_k_relax_smem<<<1, 512, bytes, c->st>>>(L.g, sl, L.K, L.BI, F, x, cycles, 0);
+            c->launches++;
+            return;
+        }
         LAUNCH(c, ccu_k_relax_small, 1, 1024, L.g, L.K, L.BI, F, x, cycles, 0);
         return;
     }
@@ -340,6 +409,17 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         if(bits) relax_faces(c, L, x, F);
         if(T == 32) { launch_relax_lanes<32>(c, L, x, F, bits); continue; }
         if(T == 4) { launch_relax_lanes<4>(c, L, x, F, bits); continue; }
+        if(c->opt_relax_tab)
+        {
+            const CcuStencil st = ccu_make_stencil(L.g);
+            for(int col = 7; col >= 0; col--)
+            {
+                if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                else if(c->opt_relax_tab >= 4) LAUNCH(c, ccu_k_relax_tab<4>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                else LAUNCH(c, ccu_k_relax_tab<2>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+            }
+            continue;
+        }
         LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x, bits);
         LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x, bits);
         LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x, bits);
@@ -376,6 +456,7 @@ static void d_gauss_seidel(ccu_ctx *c, Level &L, double *d0, const double *F, do
 static void d_project(ccu_ctx *c, int lev, const double *fine, double *coarse, int strip)
 {
     Level &Lf = c->L[lev], &Lc = c->L[lev - 1];
+    CcuProfScope ps(c, CCU_PROF_TRANSFER_FINE, lev == c->cfg.levmax);
     const int multi = c->multi() ? 1 : 0;
     LAUNCH(c, ccu_k_project, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse, multi ? 0 : 1);
     if(multi)
@@ -388,6 +469,7 @@ static void d_project(ccu_ctx *c, int lev, const double *fine, double *coarse, i
 static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, int strip)
 {
     Level &Lc = c->L[lev], &Lf = c->L[lev + 1];
+    CcuProfScope ps(c, CCU_PROF_TRANSFER_FINE, lev + 1 == c->cfg.levmax);
     LAUNCH(c, ccu_k_interp, cdiv(8 * (size_t)Lf.g.NC, 128), 128, Lc.g, Lf.g, Lf.eco, Lf.flags, coarse, fine, strip);
 }
 
@@ -396,7 +478,8 @@ static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, in
 template <class F>
 static int run_segment(ccu_ctx *c, int id, F body)
 {
-    if(!c->use_graphs) { body(); return 0; }
+    CcuProfScope ps(c, CCU_PROF_COARSE, true);
+    if(!c->use_graphs) { const bool prof = c->prof_on; c->prof_on = false; body(); c->prof_on = prof; return 0; }
     ccu_ctx::GraphSeg &s = c->seg[id];
     if(!s.exec)
     {

@@ -69,7 +69,7 @@ class StokesContext:
         check(self.lib.ccu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
     def set_option(self, name, value):
-        check(self.lib.ccu_set_option(self._ctx, dict(graphs=0, small_nodes=1, warp_nodes=2, quad_nodes=3, lanes_large=4)[name], int(value)))
+        check(self.lib.ccu_set_option(self._ctx, dict(graphs=0, small_nodes=1, warp_nodes=2, quad_nodes=3, lanes_large=4, matvec_tab=5, relax_tab=6, smem_nodes=7)[name], int(value)))
 
     def synchronize(self):
         check(self.lib.ccu_synchronize(self._ctx))
@@ -299,7 +299,7 @@ class StokesContext:
         return U, P, it.value, res.value
 
     # -- CUDA-event profile of the finest-level kernels
-    PROF = dict(relax_fine=0, matvec_fine=1, build=2)
+    PROF = dict(relax_fine=0, matvec_fine=1, build=2, coarse=3, transfer_fine=4)
 
     def profile_enable(self, on=True):
         check(self.lib.ccu_profile_enable(self._ctx, int(on)))

@@ -48,7 +48,10 @@ int ccu_synchronize(ccu_ctx *ctx);
 /* CCU_OPT_GRAPHS (default 1): replay the coarse-level part of the multigrid cycle as CUDA graphs */
 /* kernel selection by level size: levels with nno <= SMALL_NODES run all sweeps in one single-CTA launch, <= WARP_NODES
  * use a warp per node, <= QUAD_NODES four lanes per node, larger levels LANES_LARGE (1 or 4) lanes per node */
-enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_OPT_QUAD_NODES = 3, CCU_OPT_LANES_LARGE = 4 };
+/* MATVEC_TAB / RELAX_TAB: table-driven (compact code) row kernels on levels above QUAD_NODES */
+enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_OPT_QUAD_NODES = 3, CCU_OPT_LANES_LARGE = 4,
+       CCU_OPT_MATVEC_TAB = 5, CCU_OPT_RELAX_TAB = 6,
+       CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 439) run all sweeps out of one SM's shared memory */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);
@@ -159,9 +162,12 @@ int ccu_general_stokes_solver(ccu_ctx *ctx, const float *T, const float *buoyanc
                               int *iterations_out, float *residual_out);
 
 /* ---- CUDA-event timing of the finest-level kernels inside a solve (bench.py's live roofline) ---- */
-enum { CCU_PROF_RELAX_FINE = 0, CCU_PROF_MATVEC_FINE = 1, CCU_PROF_BUILD = 2, CCU_PROF_COUNT = 3 };
+/* classes: finest-level smoother (units = colour-pass launches), finest-level matvec / residual (units = products),
+ * operator rebuild, everything below the finest level (units = graph segments), finest-level transfers (project / interp) */
+enum { CCU_PROF_RELAX_FINE = 0, CCU_PROF_MATVEC_FINE = 1, CCU_PROF_BUILD = 2, CCU_PROF_COARSE = 3, CCU_PROF_TRANSFER_FINE = 4,
+       CCU_PROF_COUNT = 5 };
 int ccu_profile_enable(ccu_ctx *ctx, int on);
-/* synchronises; total milliseconds and kernel launches recorded for class `cls` since the last reset */
+/* synchronises; total milliseconds and units (see above) recorded for class `cls` since the last reset */
 int ccu_profile_read(ccu_ctx *ctx, int cls, double *ms_total, long long *launches);
 int ccu_profile_reset(ccu_ctx *ctx);
 

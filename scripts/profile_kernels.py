@@ -48,12 +48,34 @@ def timeit(fn, reps=reps, warm=2):
 
 
 out = {"mesh": [elx, ely, elz], "nno": nno}
-for lanes in (1, 4):
-    ctx.set_option("lanes_large", lanes)
+for name, opts in (("base", dict(matvec_tab=0, relax_tab=0)), ("tab2", dict(matvec_tab=2, relax_tab=2)),
+                   ("tab4", dict(matvec_tab=4, relax_tab=4)), ("tab7", dict(matvec_tab=4, relax_tab=7))):
+    for k, v in opts.items():
+        ctx.set_option(k, v)
     ms = timeit(lambda: ctx.dev_relax_sweeps(lm, "VEL", "RHS", 1))
-    out[f"gs_sweep_ms_lanes{lanes}"] = ms
-    out[f"gs_sweep_GBs_lanes{lanes}"] = 648 * nno / ms / 1e6
+    out[f"gs_sweep_ms_{name}"] = round(ms, 4)
+    out[f"gs_sweep_GBs_{name}"] = round(648 * nno / ms / 1e6, 1)
     ms = timeit(lambda: ctx.dev_matvec(lm, "VEL", "AU", 1))
-    out[f"matvec_ms_lanes{lanes}"] = ms
-    out[f"matvec_GBs_lanes{lanes}"] = 552 * nno / ms / 1e6
+    out[f"matvec_ms_{name}"] = round(ms, 4)
+    out[f"matvec_GBs_{name}"] = round(552 * nno / ms / 1e6, 1)
 print(json.dumps(out))
+
+# ---- per-level smoother / matvec timings by kernel variant (threshold tuning)
+variants = {"smem_or_cta": dict(small_nodes=10**9), "warp": dict(small_nodes=0, warp_nodes=10**9), "quad": dict(small_nodes=0, warp_nodes=0, quad_nodes=10**9),
+            "tab2": dict(small_nodes=0, warp_nodes=0, quad_nodes=0, relax_tab=2, matvec_tab=4),
+            "unrolled": dict(small_nodes=0, warp_nodes=0, quad_nodes=0, relax_tab=0, matvec_tab=0)}
+lv = {}
+for lev in range(prob.levmin, prob.levmax + 1):
+    n = prob.nno(lev)
+    row = {"nno": n}
+    for name, opts in variants.items():
+        if name == "smem_or_cta" and n > 3000:
+            continue
+        if name == "warp" and n > 300000:
+            continue
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        row[f"sweep3_us_{name}"] = round(timeit(lambda: ctx.dev_relax_sweeps(lev, "VEL", "RHS", 3), reps=10) * 1e3, 1)
+        row[f"matvec_us_{name}"] = round(timeit(lambda: ctx.dev_matvec(lev, "VEL", "AU", 1), reps=10) * 1e3, 1)
+    lv[lev] = row
+print(json.dumps({"levels": lv}))
