@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--ref-mesh", default="64x64x32", help="bounded sample mesh for the CPU reference")
     ap.add_argument("--ref-levels", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="diagnostic: launch coarse levels kernel by kernel and report per-level times")
+    ap.add_argument("--opt", action="append", default=[], help="diagnostic: library option name=value (ccu_set_option)")
     return ap.parse_args()
 
 
@@ -213,6 +215,11 @@ def run_ours(args):
     ctx = context_from_problem(prob, device=local, unique_id=uid)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    if args.no_graphs:
+        ctx.set_option("graphs", 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     lm = prob.levmax
     nno, neq, npno = prob.nno(lm), 3 * prob.nno(lm), prob.nel(lm)
     ctl = prob.control
@@ -276,6 +283,7 @@ def run_ours(args):
     build_ms, _ = ctx.profile_read("build")
     coarse_ms, coarse_n = ctx.profile_read("coarse")
     transfer_ms, _ = ctx.profile_read("transfer_fine")
+    level_ms = {lev: ctx.profile_read(lev) for lev in range(prob.levmin, prob.levmax + 1)} if args.no_graphs else None
     ctx.profile_enable(False)
     clk = clocks.stop()
     # e2e: host buffers through the C ABI
@@ -311,6 +319,8 @@ def run_ours(args):
             "uzawa_iterations": its, "gpu_launches": launches * world, "clocks": clk, "setup_s": setup_s,
             "e2e": {"value": e2e_s / args.steps, "unit": "s", "h2d_bytes_per_step": int(T_h.nbytes + b_h.nbytes) * world,
                     "d2h_bytes_per_step": int(U_h.nbytes + P_h.nbytes) * world}}
+    if level_ms:
+        line["level_ms_per_step"] = {str(k): {"ms": v[0] / args.steps, "sweeps": v[1] / args.steps} for k, v in level_ms.items()}
     if not args.no_cpu_baseline and rank == 0:
         try:
             ref_mesh = mesh_tuple(args.ref_mesh)

@@ -500,6 +500,226 @@ __global__ void bk_vec_to_nat(const CcuGeom g, const double *__restrict__ dev, d
     for(int d = 0; d < 3; d++) nat[3 * (size_t)n + d] = dev[(size_t)d * g.NS + s];
 }
 
+// ================================================================= energy step
+#define CCU_TB_ANY (0x10u | 0x20u | 0x40u)     // TBX | TBZ | TBY (global_defs.h:65-89)
+#define CCU_FBZ 0x100000u
+
+// v_from_vector (Stokes_flow_Incomp.c:530-552): V[d][node] = (float) U[eq]; imposed velocities are zero here
+__global__ void __launch_bounds__(128) ek_v_from_vector(const CcuGeom g, const double *__restrict__ U, float *V)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    for(int d = 0; d < 3; d++) V[(size_t)d * g.nno + n] = (float)U[(size_t)d * g.NS + s];
+}
+
+__device__ __forceinline__ void atomic_min_pos_float(float *addr, float v) { atomicMin((int *)addr, __float_as_int(v)); }   // v > 0
+__device__ __forceinline__ void atomic_max_float(float *addr, float v)
+{   // any sign: ints order like floats for >= 0, reversed for < 0
+    if(v >= 0.0f) atomicMax((int *)addr, __float_as_int(v)); else atomicMin((unsigned *)addr, __float_as_uint(v));
+}
+
+// std_timestep (Advection_diffusion.c:737-810): mode 0 = min over elements of size^2 (diffusive limit, once),
+// mode 1 = min over elements of 0.5 / (|uc1|/dx + |uc2|/dy + |uc3|/dz); float/double operand types as the reference
+__global__ void __launch_bounds__(128) ek_timestep(const CcuGeom g, const float *__restrict__ eco, const float *__restrict__ V,
+                                                   const int mode, float *red)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    float best = 1.0e8f;
+    if(e < g.nel)
+    {
+        if(mode == 0)
+        {
+            for(int d = 0; d < 3; d++) { const float ts = eco[(size_t)e * 3 + d] * eco[(size_t)e * 3 + d]; if(best > ts) best = ts; }
+        }
+        else
+        {
+            const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+            float uc1 = 0.0f, uc2 = 0.0f, uc3 = 0.0f;
+            for(int a = 1; a <= 8; a++)
+            {
+                const int n = elt_node(g, ey, ex, ez, a);
+                uc1 = (float)((double)uc1 + c_sh.Np[a - 1] * (double)V[n]);
+                uc2 = (float)((double)uc2 + c_sh.Np[a - 1] * (double)V[(size_t)g.nno + n]);
+                uc3 = (float)((double)uc3 + c_sh.Np[a - 1] * (double)V[2 * (size_t)g.nno + n]);
+            }
+            const float uc = (float)(fabs((double)uc1) / (double)eco[(size_t)e * 3] + fabs((double)uc2) / (double)eco[(size_t)e * 3 + 1] +
+                                     fabs((double)uc3) / (double)eco[(size_t)e * 3 + 2]);
+            const float step = (float)(0.5 / (double)uc);
+            best = fminf(best, step);
+        }
+    }
+    for(int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if((threadIdx.x & 31) == 0) atomic_min_pos_float(red, best);
+}
+__global__ void ek_set_red(float *red, float vmin, float vmax) { red[0] = vmin; red[1] = vmax; }
+__global__ void __launch_bounds__(256) ek_max(const int n, const float *__restrict__ T, float *red)
+{
+    float best = -10.0f;                      // Tmax (Global_operations.c:394)
+    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) best = fmaxf(T[i], best);
+    for(int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if((threadIdx.x & 31) == 0) atomic_max_float(red + 1, best);
+}
+
+// predictor / corrector (Advection_diffusion.c:352-392)
+__global__ void __launch_bounds__(256) ek_predictor(const int n, const unsigned *__restrict__ node, const float multiplier, float *field, float *fielddot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    if(!(node[i] & CCU_TB_ANY)) field[i] = field[i] + multiplier * fielddot[i];
+    fielddot[i] = 0.0f;
+}
+__global__ void __launch_bounds__(256) ek_corrector(const int n, const unsigned *__restrict__ node, const float multiplier, float *field, float *fielddot,
+                                                    const float *__restrict__ Dfielddot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    if(!(node[i] & CCU_TB_ANY)) field[i] = field[i] + multiplier * Dfielddot[i];
+    fielddot[i] = fielddot[i] + Dfielddot[i];
+}
+
+// pg_shape_fn + element_residual (Advection_diffusion.c:448-557, 564-735), CART3D, no FBZ flux term: Eres[8] per element.
+// The Petrov-Galerkin weights PG(j,i) = N(j,i) + adiff * (u_i . grad N_j) are formed on the fly per Gauss point
+// (u_i is the same sum the reference forms twice, in pg_shape_fn and as v1..v3 in element_residual).
+__global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ eco,
+                                                          const unsigned *__restrict__ node, const float *__restrict__ T,
+                                                          const float *__restrict__ Tdot, const float *__restrict__ V,
+                                                          const float *__restrict__ diffusivity, const float Q0, double *Eres)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8], gnx[3][8], vel[3][8];
+    double Tn[8], DTn[8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        Tn[a - 1] = (double)T[n];
+        DTn[a - 1] = (node[n] & CCU_TB_ANY) ? 0.0 : (double)Tdot[n];
+        for(int d = 0; d < 3; d++) vel[d][a - 1] = V[(size_t)d * g.nno + n];
+    }
+    const float diff = (float)((double)(diffusivity[ez] + diffusivity[ez + 1]) * 0.5);
+    // upwind parameter (pg_shape_fn :476-504)
+    const double twodiff = 2.0 * (double)diff;
+    double uc1 = 0.0, uc2 = 0.0, uc3 = 0.0;
+    for(int a = 0; a < 8; a++)
+    {
+        uc1 += c_sh.Np[a] * (double)vel[0][a];
+        uc2 += c_sh.Np[a] * (double)vel[1][a];
+        uc3 += c_sh.Np[a] * (double)vel[2][a];
+    }
+    const double uxse = fabs(uc1 * (double)eco[(size_t)e * 3]), ueta = fabs(uc2 * (double)eco[(size_t)e * 3 + 1]),
+                 ufai = fabs(uc3 * (double)eco[(size_t)e * 3 + 2]);
+    const double xse = (uxse > twodiff) ? (1.0 - twodiff / uxse) : 0.0;
+    const double eta = (ueta > twodiff) ? (1.0 - twodiff / ueta) : 0.0;
+    const double fai = (ufai > twodiff) ? (1.0 - twodiff / ufai) : 0.0;
+    const double unorm = uc1 * uc1 + uc2 * uc2 + uc3 * uc3;
+    const double adiff = (unorm > 0.000001) ? ((uxse * xse + ueta * eta + ufai * fai) / (2.0 * unorm)) : 0.0;
+    const double Q = ((double)Q0 - (double)0.0f + (double)0.0f) * (double)1.0f;       // heating_adi = heating_visc = 0, heating_latent = 1
+    const bool diffusion = (diff != 0.0f);
+    const float dl = diff * 1.0f;                                                      // diff * heating_latent[el]  (float * float)
+    double res[8];
+    for(int j = 0; j < 8; j++) res[j] = 0.0;
+    for(int i = 0; i < 8; i++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + i, 64, 8, gnx);
+        double dT = 0.0, tx1 = 0.0, tx2 = 0.0, tx3 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for(int j = 0; j < 8; j++)
+        {
+            const double sfn = c_sh.Nv[8 * j + i];
+            dT += DTn[j] * sfn;
+            tx1 += (double)gnx[0][j] * Tn[j];
+            tx2 += (double)gnx[1][j] * Tn[j];
+            tx3 += (double)gnx[2][j] * Tn[j];
+            v1 += (double)vel[0][j] * sfn;
+            v2 += (double)vel[1][j] * sfn;
+            v3 += (double)vel[2][j] * sfn;
+        }
+        const double adv = dT - Q + v1 * tx1 + v2 * tx2 + v3 * tx3;
+        for(int j = 0; j < 8; j++)
+        {
+            const double prod1 = v1 * (double)gnx[0][j] + v2 * (double)gnx[1][j] + v3 * (double)gnx[2][j];
+            const double pg = c_sh.Nv[8 * j + i] + adiff * prod1;
+            double term = pg * (double)gda * adv;
+            if(diffusion) term = term + (double)(dl * gda) * ((double)gnx[0][j] * tx1 + (double)gnx[1][j] * tx2 + (double)gnx[2][j] * tx3);
+            res[j] -= term;
+        }
+    }
+    for(int j = 0; j < 8; j++) Eres[(size_t)e * 8 + j] = res[j];
+}
+// the scatter DTdot[node] += Eres[a] of pg_solver (:425-429) as a gather in ascending element order, float accumulator
+__global__ void __launch_bounds__(128) ek_gather_residual(const CcuGeom g, const double *__restrict__ Eres, const float *__restrict__ MASS, float *DTdot)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    float acc = 0.0f;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                acc = (float)((double)acc + Eres[(size_t)e * 8 + LUT[k - ez][j - ex][i - ey] - 1]);
+            }
+        }
+    }
+    DTdot[n] = MASS ? acc * MASS[n] : acc;
+}
+
+// thermal_buoyancy (thermal only) and the layer sums of return_horiz_ave (Global_operations.c:133-252).  For the
+// rectangular faces of a Cartesian mesh the 2x2 Gauss quadrature of the bilinear interpolant is the trapezoid rule:
+// node (j, k) of a layer carries the weight wx[j] * wy[k], w = half the sum of the adjacent spacings.
+__global__ void __launch_bounds__(256) ek_buoyancy(const CcuGeom g, const float Atemp, const float *__restrict__ T,
+                                                   const float *__restrict__ expansivity, float *buoy)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    buoy[n] = Atemp * T[n] * expansivity[n % g.noz];
+}
+__global__ void __launch_bounds__(256) ek_layer_sums(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ X, double *layer)
+{
+    const int kz = blockIdx.x;                       // one block per z layer
+    double s = 0.0, w = 0.0;
+    for(int t = threadIdx.x; t < g.nox * g.noy; t += blockDim.x)
+    {
+        const int j = t % g.nox, i = t / g.nox;
+        const float *x1 = XX, *x2 = XX + g.nno;
+        const int n0 = g.noz * (j + g.nox * i);      // node (i, j, 0): coordinates do not depend on z in a box
+        double wx = 0.0, wy = 0.0;
+        if(j > 0) wx += 0.5 * ((double)x1[n0] - (double)x1[n0 - g.noz]);
+        if(j < g.nox - 1) wx += 0.5 * ((double)x1[n0 + g.noz] - (double)x1[n0]);
+        if(i > 0) wy += 0.5 * ((double)x2[n0] - (double)x2[n0 - g.noz * g.nox]);
+        if(i < g.noy - 1) wy += 0.5 * ((double)x2[n0 + g.noz * g.nox] - (double)x2[n0]);
+        s += (double)X[n0 + kz] * wx * wy;
+        w += wx * wy;
+    }
+    __shared__ double sh[2][8];
+    for(int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); w += __shfl_down_sync(0xffffffffu, w, o); }
+    if((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = w; }
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        double a = 0.0, b = 0.0;
+        for(int q = 0; q < 8; q++) { a += sh[0][q]; b += sh[1][q]; }
+        layer[kz] = a; layer[g.noz + kz] = b;
+    }
+}
+__global__ void __launch_bounds__(256) ek_remove_layer_ave(const CcuGeom g, const double *__restrict__ layer, float *X)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int kz = n % g.noz;
+    if(layer[g.noz + kz] != 0.0) X[n] = X[n] - (float)(layer[kz] / layer[g.noz + kz]);
+}
+
 // ================================================================= host side
 static bool g_tables_ready = false;
 static int ensure_tables(ccu_ctx *c)
@@ -751,6 +971,234 @@ int ccu_get_level_array(ccu_ctx *c, int lev, int which, void *out)
     }
     if(!src) FAIL("get_level_array: array not allocated");
     CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ================================================================= energy step, host side
+static int ensure_energy(ccu_ctx *c)
+{
+    if(ensure_tables(c) || ensure_nodal(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    const size_t nno = (size_t)L.g.nno;
+    if(!E.Tdot)
+    {
+        CK(cudaMalloc(&E.Tdot, sizeof(float) * nno)); CK(cudaMemsetAsync(E.Tdot, 0, sizeof(float) * nno, c->st));
+        CK(cudaMalloc(&E.DTdot, sizeof(float) * nno));
+        CK(cudaMalloc(&E.V, sizeof(float) * 3 * nno)); CK(cudaMemsetAsync(E.V, 0, sizeof(float) * 3 * nno, c->st));
+        CK(cudaMalloc(&E.T1, sizeof(float) * nno)); CK(cudaMalloc(&E.Tdot1, sizeof(float) * nno));
+        CK(cudaMalloc(&E.diffusivity, sizeof(float) * L.g.noz)); CK(cudaMalloc(&E.expansivity, sizeof(float) * L.g.noz));
+        CK(cudaMalloc(&E.Eres, sizeof(double) * 8 * (size_t)L.g.nel));
+        CK(cudaMalloc(&E.layer, sizeof(double) * 2 * L.g.noz));
+        CK(cudaMalloc(&E.red, sizeof(float) * 4));
+    }
+    return 0;
+}
+int ccu_set_energy_params(ccu_ctx *c, float fine_tune_dt, float fixed_timestep, float gamma, int temp_iterations,
+                          const float *diffusivity, const float *expansivity, float Q0)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    E.fine_tune_dt = fine_tune_dt; E.fixed_timestep = fixed_timestep; E.gamma = gamma; E.temp_iterations = temp_iterations; E.Q0 = Q0;
+    CK(cudaMemcpyAsync(E.diffusivity, diffusivity, sizeof(float) * L.g.noz, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(E.expansivity, expansivity, sizeof(float) * L.g.noz, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    E.have_params = true; E.diff_timestep = -1.0f;
+    return 0;
+}
+int ccu_set_tdot(ccu_ctx *c, const float *Tdot)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    const size_t nno = (size_t)c->L[c->cfg.levmax].g.nno;
+    if(Tdot) CK(cudaMemcpyAsync(c->en.Tdot, Tdot, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
+    else CK(cudaMemsetAsync(c->en.Tdot, 0, sizeof(float) * nno, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_set_velocity(ccu_ctx *c, const float *V1, const float *V2, const float *V3)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    const size_t nno = (size_t)c->L[c->cfg.levmax].g.nno;
+    CK(cudaMemcpyAsync(c->en.V, V1, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->en.V + nno, V2, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->en.V + 2 * nno, V3, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->en.have_v = true;
+    return 0;
+}
+int ccu_v_from_vector(ccu_ctx *c, float *V_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    LAUNCH(c, ek_v_from_vector, cdiv(L.g.nno, 128), 128, L.g, (const double *)L.vec[CCU_VEC_U], c->en.V);
+    c->en.have_v = true;
+    if(V_out) CK(cudaMemcpyAsync(V_out, c->en.V, sizeof(float) * 3 * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+// global_fmin / global_fmax (Global_operations.c:409,416) of the device scalar red[which]
+static int reduce_scalar(ccu_ctx *c, int which, float *out)
+{
+    float v;
+    CK(cudaMemcpyAsync(&v, c->en.red + which, sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if(c->multi())
+    {
+        double *buf = c->comm->dotstage;
+        double d = (which == 0) ? -(double)v : (double)v;        // min through max
+        CK(cudaMemcpyAsync(buf, &d, sizeof(double), cudaMemcpyHostToDevice, c->st));
+        if(ccu_allreduce_buffer(c, buf, 1, 1)) return 1;
+        CK(cudaMemcpyAsync(&d, buf, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        v = (float)((which == 0) ? -d : d);
+    }
+    *out = v;
+    return 0;
+}
+static int std_timestep(ccu_ctx *c, float *dt)
+{
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    if(!E.have_params || !E.have_v) FAIL("std_timestep: energy parameters / velocity missing");
+    if(E.fixed_timestep != 0.0f) { *dt = E.fixed_timestep; return 0; }
+    if(E.diff_timestep < 0.0f)
+    {
+        LAUNCH(c, ek_set_red, 1, 1, E.red, 1.0e8f, -10.0f);
+        LAUNCH(c, ek_timestep, cdiv(L.g.nel, 128), 128, L.g, L.eco, E.V, 0, E.red);
+        float m;
+        if(reduce_scalar(c, 0, &m)) return 1;
+        E.diff_timestep = (float)(0.5 * (double)m);
+    }
+    LAUNCH(c, ek_set_red, 1, 1, E.red, 1.0e8f, -10.0f);
+    LAUNCH(c, ek_timestep, cdiv(L.g.nel, 128), 128, L.g, L.eco, E.V, 1, E.red);
+    float adv;
+    CK(cudaMemcpyAsync(&adv, E.red, sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const float prod = E.fine_tune_dt * adv;
+    adv = (float)(1.0e-32 + (double)(prod < E.diff_timestep ? prod : E.diff_timestep));
+    // global_fmin of the per-rank candidates
+    CK(cudaMemcpyAsync(E.red, &adv, sizeof(float), cudaMemcpyHostToDevice, c->st));
+    return reduce_scalar(c, 0, dt);
+}
+int ccu_std_timestep(ccu_ctx *c, float *dt_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    return std_timestep(c, dt_out);
+}
+static int pg_solver(ccu_ctx *c)
+{
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    LAUNCH(c, ek_element_residual, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.eco, L.node, c->T, E.Tdot, E.V, E.diffusivity, E.Q0, E.Eres);
+    if(!c->multi()) { LAUNCH(c, ek_gather_residual, cdiv(L.g.nno, 128), 128, L.g, E.Eres, L.MASS, E.DTdot); return 0; }
+    LAUNCH(c, ek_gather_residual, cdiv(L.g.nno, 128), 128, L.g, E.Eres, (const float *)nullptr, E.DTdot);
+    if(ccu_halo_sum_nodal(c, c->cfg.levmax, E.DTdot)) return 1;      // exchange_node_f20 (Advection_diffusion.c:432)
+    LAUNCH(c, bk_mul, cdiv(L.g.nno, 128), 128, L.g.nno, E.DTdot, L.MASS);
+    return 0;
+}
+static int energy_ready(ccu_ctx *c)
+{
+    Level &L = c->L[c->cfg.levmax];
+    if(!c->en.have_params || !c->en.have_v) FAIL("energy step: ccu_set_energy_params and a velocity (ccu_v_from_vector / ccu_set_velocity) are needed first");
+    if(!L.have_xx || !L.have_tw || !L.node) FAIL("energy step: coordinates / geometry / node flags missing");
+    return 0;
+}
+int ccu_pg_solver(ccu_ctx *c, float *DTdot_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c) || energy_ready(c)) return 1;
+    if(pg_solver(c)) return 1;
+    if(DTdot_out) CK(cudaMemcpyAsync(DTdot_out, c->en.DTdot, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nno, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+static int tmax(ccu_ctx *c, float *out)
+{
+    Level &L = c->L[c->cfg.levmax];
+    LAUNCH(c, ek_set_red, 1, 1, c->en.red, 1.0e8f, -10.0f);
+    LAUNCH(c, ek_max, min(cdiv(L.g.nno, 256), 148u * 8u), 256, L.g.nno, (const float *)c->T, c->en.red);
+    return reduce_scalar(c, 1, out);
+}
+int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_interior_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c) || energy_ready(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    const size_t nno = (size_t)L.g.nno;
+    if(T) CK(cudaMemcpyAsync(c->T, T, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
+    if(Tdot) CK(cudaMemcpyAsync(E.Tdot, Tdot, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
+    float timestep;
+    if(std_timestep(c, &timestep)) return 1;
+    CK(cudaMemcpyAsync(E.T1, c->T, sizeof(float) * nno, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(E.Tdot1, E.Tdot, sizeof(float) * nno, cudaMemcpyDeviceToDevice, c->st));
+    const float T_maxvaried = (float)1.01;
+    float T_interior1, T_interior = 0.0f;
+    if(tmax(c, &T_interior1)) return 1;
+    float dt_reduced = 1.0f;
+    int last_sub_iterations = 1, iredo;
+    do
+    {
+        timestep = timestep * dt_reduced;
+        iredo = 0;
+        const float mult_p = (float)((1.0 - (double)E.gamma) * (double)timestep);
+        LAUNCH(c, ek_predictor, cdiv(nno, 256), 256, (int)nno, L.node, mult_p, c->T, E.Tdot);
+        for(int pass = 0; pass < E.temp_iterations; pass++)
+        {
+            if(pg_solver(c)) return 1;
+            LAUNCH(c, ek_corrector, cdiv(nno, 256), 256, (int)nno, L.node, E.gamma * timestep, c->T, E.Tdot, (const float *)E.DTdot);
+        }
+        if(tmax(c, &T_interior)) return 1;
+        if(T_interior / T_interior1 > T_maxvaried)
+        {
+            CK(cudaMemcpyAsync(c->T, E.T1, sizeof(float) * nno, cudaMemcpyDeviceToDevice, c->st));
+            CK(cudaMemcpyAsync(E.Tdot, E.Tdot1, sizeof(float) * nno, cudaMemcpyDeviceToDevice, c->st));
+            iredo = 1;
+            dt_reduced = (float)((double)dt_reduced * 0.5);
+            last_sub_iterations++;
+        }
+    } while(iredo == 1 && last_sub_iterations <= 5);
+    if(dt_out) *dt_out = timestep;
+    if(T_interior_out) *T_interior_out = T_interior;
+    if(T) CK(cudaMemcpyAsync(T, c->T, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
+    if(Tdot) CK(cudaMemcpyAsync(Tdot, E.Tdot, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    if(!E.have_params || !L.have_xx) FAIL("thermal_buoyancy: energy parameters / coordinates missing");
+    LAUNCH(c, ek_buoyancy, cdiv(L.g.nno, 256), 256, L.g, Atemp, (const float *)c->T, (const float *)E.expansivity, c->buoy);
+    LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->buoy, E.layer);
+    if(c->multi())
+    {   // return_horiz_ave sums over the ranks of one horizontal plane (same z position); here: slot me_z of a global table
+        FAIL("thermal_buoyancy: multi-subdomain layer averages are not implemented yet (pass the buoyancy from the host)");
+    }
+    LAUNCH(c, ek_remove_layer_ave, cdiv(L.g.nno, 256), 256, L.g, (const double *)E.layer, c->buoy);
+    if(buoyancy_out) CK(cudaMemcpyAsync(buoyancy_out, c->buoy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_get_temperature(ccu_ctx *c, float *T, float *Tdot)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    const size_t nno = (size_t)c->L[c->cfg.levmax].g.nno;
+    if(T) CK(cudaMemcpyAsync(T, c->T, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
+    if(Tdot) CK(cudaMemcpyAsync(Tdot, c->en.Tdot, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }

@@ -87,6 +87,19 @@ struct ccu_ctx
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;
+    // energy step state (ccu_build_exact.cu, PG_timestep): finest level, natural node order
+    struct Energy
+    {
+        float *Tdot = nullptr, *DTdot = nullptr, *V = nullptr;     // [nno], [nno], [3][nno]
+        float *T1 = nullptr, *Tdot1 = nullptr;                     // saved fields of the Tmax safeguard
+        float *diffusivity = nullptr, *expansivity = nullptr;      // [noz]
+        double *Eres = nullptr;                                    // [nel][8] element residuals
+        double *layer = nullptr;                                   // [2][noz] layer sums of remove_horiz_ave
+        float *red = nullptr;                                      // device scalars: [0] min, [1] max
+        float fine_tune_dt = 0.9f, fixed_timestep = 0.0f, gamma = 0.5f, Q0 = 0.0f, diff_timestep = -1.0f;
+        int temp_iterations = 2;
+        bool have_params = false, have_v = false;
+    } en;
     long long launches = 0;
     CcuComm *comm = nullptr;       // null = single subdomain
     bool multi() const { return comm && comm->nranks > 1; }

@@ -374,51 +374,58 @@ __global__ void __launch_bounds__(512) ccu_k_relax_smem(const CcuGeom g, const C
         const int d = idx / n1, tt = idx - d * n1;
         xs[idx] = (tt < n && !zero_first) ? x[d * NS + sl.s[tt]] : 0.0;
     }
-    int col = -1, s = 0;
-    double f0 = 0, f1 = 0, f2 = 0, b0 = 0, b1 = 0, b2 = 0;
-    unsigned short nb[27];
-    if(t < n)
-    {
-        s = sl.s[t];
-        for(int c = 0; c < 8; c++) if(t >= sl.cstart[c] && t < sl.cstart[c + 1]) col = c;
-        f0 = F[s]; f1 = F[NS + s]; f2 = F[2 * NS + s];
-        b0 = BI[s]; b1 = BI[NS + s]; b2 = BI[2 * NS + s];
-#pragma unroll
-        for(int b = 0; b < 27; b++) nb[b] = sl.nbr[b * n + t];
-    }
     __syncthreads();
+    // a phase = one colour; 8 lanes per node (lane q takes stencil blocks q, q+8, q+16, q+24), so the ~50 nodes of a
+    // phase keep ~13 warps busy instead of 2 and the per-node chain of shared-memory loads is cut eightfold
+    const int q = t & 7, grp = t >> 3;
     for(int sw = 0; sw < cycles; sw++)
         for(int c = 7; c >= 0; c--)
         {
-            if(col == c)
+            for(int base = sl.cstart[c]; base < sl.cstart[c + 1]; base += (int)(blockDim.x >> 3))
             {
+                const int tt = base + grp;
+                const bool act = tt < sl.cstart[c + 1];
                 double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-#pragma unroll
-                for(int b = 0; b < 14; b++)
+                if(act)
                 {
-                    const int m = nb[b];
-                    const float *kp = Ks + (b * 9) * n1 + t;
-                    const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
-                    r0 += (double)kp[0] * x0 + (double)kp[n1] * x1 + (double)kp[2 * n1] * x2;
-                    r1 += (double)kp[3 * n1] * x0 + (double)kp[4 * n1] * x1 + (double)kp[5 * n1] * x2;
-                    r2 += (double)kp[6 * n1] * x0 + (double)kp[7 * n1] * x1 + (double)kp[8 * n1] * x2;
+#pragma unroll
+                    for(int b = q; b < 27; b += 8)
+                    {
+                        const int m = sl.nbr[b * n + tt];
+                        const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
+                        if(b < 14)
+                        {
+                            const float *kp = Ks + (b * 9) * n1 + tt;
+                            r0 += (double)kp[0] * x0 + (double)kp[n1] * x1 + (double)kp[2 * n1] * x2;
+                            r1 += (double)kp[3 * n1] * x0 + (double)kp[4 * n1] * x1 + (double)kp[5 * n1] * x2;
+                            r2 += (double)kp[6 * n1] * x0 + (double)kp[7 * n1] * x1 + (double)kp[8 * n1] * x2;
+                        }
+                        else
+                        {
+                            const float *kp = Ks + ((b - 13) * 9) * n1 + m;
+                            r0 += (double)kp[0] * x0 + (double)kp[3 * n1] * x1 + (double)kp[6 * n1] * x2;
+                            r1 += (double)kp[n1] * x0 + (double)kp[4 * n1] * x1 + (double)kp[7 * n1] * x2;
+                            r2 += (double)kp[2 * n1] * x0 + (double)kp[5 * n1] * x1 + (double)kp[8 * n1] * x2;
+                        }
+                    }
                 }
 #pragma unroll
-                for(int b = 14; b < 27; b++)
+                for(int o = 4; o > 0; o >>= 1)
                 {
-                    const int m = nb[b];
-                    const float *kp = Ks + ((b - 13) * 9) * n1 + m;
-                    const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
-                    r0 += (double)kp[0] * x0 + (double)kp[3 * n1] * x1 + (double)kp[6 * n1] * x2;
-                    r1 += (double)kp[n1] * x0 + (double)kp[4 * n1] * x1 + (double)kp[7 * n1] * x2;
-                    r2 += (double)kp[2 * n1] * x0 + (double)kp[5 * n1] * x1 + (double)kp[8 * n1] * x2;
+                    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+                    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+                    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
                 }
-                xs[t] += (double)(float)((f0 - r0) * b0);
-                xs[n1 + t] += (double)(float)((f1 - r1) * b1);
-                xs[2 * n1 + t] += (double)(float)((f2 - r2) * b2);
+                if(act && q < 3)
+                {   // lanes 0..2 of the group update one equation each
+                    const int sn = sl.s[tt];
+                    const double r = q == 0 ? r0 : (q == 1 ? r1 : r2);
+                    xs[q * n1 + tt] += (double)(float)((F[q * NS + sn] - r) * BI[q * NS + sn]);
+                }
             }
             __syncthreads();
         }
+    const int s = (t < n) ? sl.s[t] : 0;
     if(t < n) { x[s] = xs[t]; x[NS + s] = xs[n1 + t]; x[2 * NS + s] = xs[2 * n1 + t]; }
 }
 

@@ -110,6 +110,8 @@ void ccu_destroy(ccu_ctx *c)
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
+    cudaFree(c->en.Tdot); cudaFree(c->en.DTdot); cudaFree(c->en.V); cudaFree(c->en.T1); cudaFree(c->en.Tdot1); cudaFree(c->en.diffusivity);
+    cudaFree(c->en.expansivity); cudaFree(c->en.Eres); cudaFree(c->en.layer); cudaFree(c->en.red);
     cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
     cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
     drop_graphs(c);
@@ -155,6 +157,8 @@ int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
     if(ccu_ensure_stage(c, sizeof(unsigned) * L.g.nno)) return 1;
     CK(cudaMemcpyAsync(c->stage, node, sizeof(unsigned) * L.g.nno, cudaMemcpyHostToDevice, c->st));
     LAUNCH(c, ccu_k_flags_to_dev, cdiv(L.g.nno, 256), 256, L.g, (const unsigned *)c->stage, L.flags);
+    if(!L.node) CK(cudaMalloc(&L.node, sizeof(unsigned) * L.g.nno));        // raw bits (temperature BCs of the energy step)
+    CK(cudaMemcpyAsync(L.node, c->stage, sizeof(unsigned) * L.g.nno, cudaMemcpyDeviceToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
     L.have_flags = true;
     return 0;
@@ -283,6 +287,7 @@ static int lanes_for(const ccu_ctx *c, const Level &L)
 static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int strip)
 {
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
+    CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);   // the table-driven kernel wins from ~1e4 nodes up
     if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
@@ -301,6 +306,7 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
         return;
     }
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
+    CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
@@ -387,6 +393,7 @@ static void relax_faces(ccu_ctx *c, Level &L, double *x, const double *F)
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
     CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], 8LL * cycles);
+    CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, cycles);
     const int T = lanes_for(c, L);
     if(T == 0)
     {   // one CTA does every sweep and colour of a tiny level in a single launch
@@ -457,6 +464,7 @@ static void d_project(ccu_ctx *c, int lev, const double *fine, double *coarse, i
 {
     Level &Lf = c->L[lev], &Lc = c->L[lev - 1];
     CcuProfScope ps(c, CCU_PROF_TRANSFER_FINE, lev == c->cfg.levmax);
+    CcuProfScope pl(c, CCU_PROF_LEVEL0 + lev, true, 0);
     const int multi = c->multi() ? 1 : 0;
     LAUNCH(c, ccu_k_project, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse, multi ? 0 : 1);
     if(multi)
@@ -470,6 +478,7 @@ static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, in
 {
     Level &Lc = c->L[lev], &Lf = c->L[lev + 1];
     CcuProfScope ps(c, CCU_PROF_TRANSFER_FINE, lev + 1 == c->cfg.levmax);
+    CcuProfScope pl(c, CCU_PROF_LEVEL0 + lev + 1, true, 0);
     LAUNCH(c, ccu_k_interp, cdiv(8 * (size_t)Lf.g.NC, 128), 128, Lc.g, Lf.g, Lf.eco, Lf.flags, coarse, fine, strip);
 }
 
@@ -479,7 +488,7 @@ template <class F>
 static int run_segment(ccu_ctx *c, int id, F body)
 {
     CcuProfScope ps(c, CCU_PROF_COARSE, true);
-    if(!c->use_graphs) { const bool prof = c->prof_on; c->prof_on = false; body(); c->prof_on = prof; return 0; }
+    if(!c->use_graphs) { body(); return 0; }
     ccu_ctx::GraphSeg &s = c->seg[id];
     if(!s.exec)
     {

@@ -298,6 +298,62 @@ class StokesContext:
                                                  int(precondition), int(guess), ptr(U), ptr(P), C.byref(it), C.byref(res)))
         return U, P, it.value, res.value
 
+    # -- energy step (PG_timestep and its parts, Advection_diffusion.c)
+    def set_energy_params(self, fine_tune_dt, fixed_timestep, gamma, temp_iterations, diffusivity, expansivity, Q0=0.0):
+        noz = self.dims[self.levmax][2]
+        dz = np.ascontiguousarray(diffusivity, dtype=np.float32)
+        ex = np.ascontiguousarray(expansivity, dtype=np.float32)
+        assert dz.size == noz and ex.size == noz
+        check(self.lib.ccu_set_energy_params(self._ctx, C.c_float(fine_tune_dt), C.c_float(fixed_timestep), C.c_float(gamma),
+                                             int(temp_iterations), dz.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p), C.c_float(Q0)))
+
+    def set_tdot(self, Tdot=None):
+        t = None if Tdot is None else np.ascontiguousarray(Tdot, dtype=np.float32)
+        check(self.lib.ccu_set_tdot(self._ctx, None if t is None else t.ctypes.data_as(C.c_void_p)))
+
+    def set_velocity(self, V1, V2, V3):
+        vs = [np.ascontiguousarray(v, dtype=np.float32) for v in (V1, V2, V3)]
+        for v in vs:
+            assert v.size == self.nno(self.levmax)
+        check(self.lib.ccu_set_velocity(self._ctx, *[v.ctypes.data_as(C.c_void_p) for v in vs]))
+
+    def v_from_vector(self, want_host=True):
+        """v_from_vector (Stokes_flow_Incomp.c:530) on the resident U; returns (V1, V2, V3) float32 or None."""
+        out = np.empty(3 * self.nno(self.levmax), dtype=np.float32) if want_host else None
+        check(self.lib.ccu_v_from_vector(self._ctx, None if out is None else out.ctypes.data_as(C.c_void_p)))
+        return None if out is None else tuple(out.reshape(3, -1))
+
+    def std_timestep(self):
+        dt = C.c_float()
+        check(self.lib.ccu_std_timestep(self._ctx, C.byref(dt)))
+        return np.float32(dt.value)
+
+    def pg_solver(self):
+        out = np.empty(self.nno(self.levmax), dtype=np.float32)
+        check(self.lib.ccu_pg_solver(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def PG_timestep(self, T=None, Tdot=None):
+        """PG_timestep (Advection_diffusion.c:251): returns (T, Tdot, dt, T_interior); T, Tdot None = resident fields
+        (then the returned fields are None as well)."""
+        t = None if T is None else np.array(T, dtype=np.float32)
+        td = None if Tdot is None else np.array(Tdot, dtype=np.float32)
+        dt, ti = C.c_float(), C.c_float()
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(self.lib.ccu_PG_timestep(self._ctx, ptr(t), ptr(td), C.byref(dt), C.byref(ti)))
+        return t, td, np.float32(dt.value), np.float32(ti.value)
+
+    def thermal_buoyancy(self, Atemp, want_host=True):
+        out = np.empty(self.nno(self.levmax), dtype=np.float32) if want_host else None
+        check(self.lib.ccu_thermal_buoyancy(self._ctx, C.c_float(Atemp), None if out is None else out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_temperature(self, want_tdot=False):
+        T = np.empty(self.nno(self.levmax), dtype=np.float32)
+        Td = np.empty_like(T) if want_tdot else None
+        check(self.lib.ccu_get_temperature(self._ctx, T.ctypes.data_as(C.c_void_p), None if Td is None else Td.ctypes.data_as(C.c_void_p)))
+        return (T, Td) if want_tdot else T
+
     # -- CUDA-event profile of the finest-level kernels
     PROF = dict(relax_fine=0, matvec_fine=1, build=2, coarse=3, transfer_fine=4)
 
@@ -308,8 +364,10 @@ class StokesContext:
         check(self.lib.ccu_profile_reset(self._ctx))
 
     def profile_read(self, cls):
+        """cls: a class name of PROF or an int multigrid level (per-level totals; recorded with graphs off)."""
         ms, n = C.c_double(), C.c_longlong()
-        check(self.lib.ccu_profile_read(self._ctx, self.PROF[cls], C.byref(ms), C.byref(n)))
+        cid = 5 + cls if isinstance(cls, int) else self.PROF[cls]
+        check(self.lib.ccu_profile_read(self._ctx, cid, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     # -- device-resident forms

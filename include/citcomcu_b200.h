@@ -161,11 +161,34 @@ int ccu_general_stokes_solver(ccu_ctx *ctx, const float *T, const float *buoyanc
                               double augmented, int precondition, int guess, double *U, double *P,
                               int *iterations_out, float *residual_out);
 
+/* ---- energy step: PG_timestep (Advection_diffusion.c:251-349), Cartesian, fixed-temperature or zero-flux walls ----
+ * All fields are float[nno] in the reference's node order (E->T+1, E->Tdot+1, E->V[d]+1, E->buoyancy+1). */
+/* advection_diffusion_parameters (Advection_diffusion.c:63-110): E->advection.{fine_tune_dt, fixed_timestep, gamma,
+ * temp_iterations}; E->diffusivity+1, E->expansivity+1 (float[noz], Instructions.c:1096-1120); E->control.Q0 */
+int ccu_set_energy_params(ccu_ctx *ctx, float fine_tune_dt, float fixed_timestep, float gamma, int temp_iterations,
+                          const float *diffusivity /*[noz]*/, const float *expansivity /*[noz]*/, float Q0);
+int ccu_set_tdot(ccu_ctx *ctx, const float *Tdot /*[nno] or NULL = zero*/);
+int ccu_set_velocity(ccu_ctx *ctx, const float *V1, const float *V2, const float *V3 /*[nno] each*/);
+/* v_from_vector (Stokes_flow_Incomp.c:530): fp32 nodal velocity from the resident solution U; V_out = float[3*nno] or NULL */
+int ccu_v_from_vector(ccu_ctx *ctx, float *V_out);
+/* std_timestep (Advection_diffusion.c:737-810) from the resident velocity */
+int ccu_std_timestep(ccu_ctx *ctx, float *dt_out);
+/* pg_solver (Advection_diffusion.c:398-441; pg_shape_fn :448, element_residual :564) on the resident T, Tdot, V */
+int ccu_pg_solver(ccu_ctx *ctx, float *DTdot_out /*[nno]*/);
+/* PG_timestep: std_timestep, predictor, temp_iterations x (pg_solver, corrector), the Tmax safeguard (restore, halve dt,
+ * up to 5 times).  T, Tdot: host in/out, or NULL to work on the resident fields only. */
+int ccu_PG_timestep(ccu_ctx *ctx, float *T, float *Tdot, float *dt_out, float *T_interior_out);
+/* thermal_buoyancy (Pan_problem_misc_functions.c:83), thermal only: Atemp * T * expansivity[z] minus its layer average
+ * (remove_horiz_ave / return_horiz_ave, Global_operations.c:55,133); updates the resident buoyancy; host copy optional */
+int ccu_thermal_buoyancy(ccu_ctx *ctx, float Atemp, float *buoyancy_out /*[nno] or NULL*/);
+int ccu_get_temperature(ccu_ctx *ctx, float *T /*[nno]*/, float *Tdot /*[nno] or NULL*/);
+
 /* ---- CUDA-event timing of the finest-level kernels inside a solve (bench.py's live roofline) ---- */
 /* classes: finest-level smoother (units = colour-pass launches), finest-level matvec / residual (units = products),
  * operator rebuild, everything below the finest level (units = graph segments), finest-level transfers (project / interp) */
 enum { CCU_PROF_RELAX_FINE = 0, CCU_PROF_MATVEC_FINE = 1, CCU_PROF_BUILD = 2, CCU_PROF_COARSE = 3, CCU_PROF_TRANSFER_FINE = 4,
-       CCU_PROF_COUNT = 5 };
+       CCU_PROF_LEVEL0 = 5 /* + lev: smoother + matvec + transfers of multigrid level lev; only recorded with CCU_OPT_GRAPHS = 0 */,
+       CCU_PROF_COUNT = 5 + CCU_MAX_LEVELS };
 int ccu_profile_enable(ccu_ctx *ctx, int on);
 /* synchronises; total milliseconds and units (see above) recorded for class `cls` since the last reset */
 int ccu_profile_read(ccu_ctx *ctx, int cls, double *ms_total, long long *launches);

@@ -215,6 +215,23 @@ static void dump_kats(struct All_variables *E)
         dump_scalar_i("kat_solve_valid", valid);
     }
     free(u); free(Au); free(f); free(d0); free(w); free(p); free(q);
+    {   /* energy step known answers on the state after the step-0 Stokes solve: std_timestep (Advection_diffusion.c:737)
+         * and one pg_solver call (:398) exactly as PG_timestep invokes it (:303) */
+        const int nno = E->lmesh.nno;
+        float *DTdot = (float *)calloc(nno + 2, sizeof(float));
+        double adv[6];
+        std_timestep(E);
+        pg_solver(E, E->T, E->Tdot, DTdot, E->V, E->convection.heat_sources, 1.0, 1, E->TB, E->node);
+        adv[0] = E->advection.fine_tune_dt; adv[1] = E->advection.fixed_timestep; adv[2] = E->advection.gamma;
+        adv[3] = E->advection.temp_iterations; adv[4] = E->control.Q0; adv[5] = E->control.Atemp;
+        DUMP_F64("kat_adv_params", adv, 6);
+        dump_scalar_d("kat_dt", (double)E->advection.timestep);
+        DUMP_F32("kat_pg_DTdot", DTdot + 1, nno);
+        DUMP_F32("kat_diffusivity", E->diffusivity + 1, E->lmesh.noz);
+        DUMP_F32("kat_expansivity", E->expansivity + 1, E->lmesh.noz);
+        DUMP_U32("kat_node", E->node + 1, nno);
+        free(DTdot);
+    }
 }
 
 static void setup(struct All_variables *E, int *argc, char ***argv, char *input)

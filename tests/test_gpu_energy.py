@@ -1,0 +1,99 @@
+"""GPU parity of the energy step against the unmodified reference:
+std_timestep, pg_solver, PG_timestep, thermal_buoyancy on the reference's own state after its step-0 Stokes solve,
+then the coupled timestep loop (energy -> buoyancy -> Stokes) against the reference's T after N steps (north star:
+temperature within 0.1 %).  The kernels restate the reference's operand types (ccu_build_exact.cu, -fmad=false), so
+the single-kernel checks are bit-exact or within 1 ulp(fp32)."""
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import po
+from citcomcu_b200 import inputfile
+
+pytestmark = pytest.mark.gpu
+
+
+def ulps(a, b):
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) / np.finfo(np.float32).eps
+
+
+@pytest.fixture(scope="module", params=["tdepv", "busse"])
+def state(request):
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    text = inputfile.tdepv_box(16, 16, 8, 3, maxstep=4) if request.param == "tdepv" else inputfile.busse1a(levels=3, maxstep=4)
+    dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_energy_")), nsteps=3, kat=True)
+    d = dumps[0]
+    prob = CartesianProblem(text)
+    ctx = context_from_problem(prob)
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    yield d, prob, ctx, float(adv[5])
+    ctx.close()
+
+
+def load_s0(d, ctx):
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_tdot(d["s0_Tdot"])
+    ctx.set_velocity(d["s0_V1"], d["s0_V2"], d["s0_V3"])
+
+
+def test_v_from_vector(state):
+    d, prob, ctx, _ = state
+    ctx.vec_upload(prob.levmax, "U", d["s0_U"])
+    V = ctx.v_from_vector()
+    for a in range(3):
+        assert np.array_equal(V[a], d[f"s0_V{a + 1}"])
+
+
+def test_std_timestep_bit_exact(state):
+    d, prob, ctx, _ = state
+    load_s0(d, ctx)
+    assert ctx.std_timestep() == np.float32(d["kat_dt"][0])
+
+
+def test_pg_solver(state):
+    d, prob, ctx, _ = state
+    load_s0(d, ctx)
+    assert ulps(ctx.pg_solver(), d["kat_pg_DTdot"]) <= 2.0
+
+
+def test_PG_timestep_and_buoyancy(state):
+    d, prob, ctx, Atemp = state
+    load_s0(d, ctx)
+    T, Tdot, dt, Tint = ctx.PG_timestep(d["s0_T"], d["s0_Tdot"])
+    assert dt == np.float32(d["s1_scalars"][1])
+    assert ulps(T, d["s1_T"]) <= 4.0
+    assert ulps(Tdot, d["s1_Tdot"]) <= 8.0
+    b = ctx.thermal_buoyancy(Atemp)
+    assert np.abs(b - d["s1_buoyancy"]).max() <= 4e-7 * np.abs(d["s1_buoyancy"]).max()
+
+
+def test_coupled_timesteps_match_reference(state):
+    """main()'s loop (Citcom.c:111-161) on the device: PG_timestep, thermal_buoyancy, general_stokes_solver,
+    v_from_vector.  T after 3 steps within 0.1 % (relative L2) of the reference run with the same input."""
+    d, prob, ctx, Atemp = state
+    ctl = prob.control
+    kw = dict(augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"])
+    T0 = d["s0_T"]
+    ctx.set_temperature(T0)
+    ctx.set_tdot(None)
+    ctx.assemble_forces(d["s0_buoyancy"], want_host=False)
+    ctx.general_stokes_solver(None, None, rebuild=1, guess=0, want_host=False, **kw)
+    ctx.v_from_vector(want_host=False)
+    rebuild = 1 if prob.visc["tdepv"] else 0
+    for step in (1, 2, 3):
+        _, _, dt, _ = ctx.PG_timestep()
+        ctx.thermal_buoyancy(Atemp, want_host=False)
+        ctx.general_stokes_solver(None, None, rebuild=rebuild, guess=2, want_host=False, **kw)
+        ctx.v_from_vector(want_host=False)
+        T = ctx.get_temperature()
+        ref = d[f"s{step}_T"]
+        assert abs(dt - d[f"s{step}_scalars"][1]) <= 2e-3 * d[f"s{step}_scalars"][1]
+        assert np.linalg.norm(T - ref) <= 1e-3 * np.linalg.norm(ref)
