@@ -70,7 +70,7 @@ struct ccu_ctx
     bool use_graphs = true;
     // kernel selection by level size (lanes per node), ccu_set_option
     int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
-    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 439, opt_matvec_tab_nodes = 10000;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
+    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials

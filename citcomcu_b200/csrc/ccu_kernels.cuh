@@ -353,47 +353,70 @@ struct CcuSmemLevel
     int *s = nullptr;                // [n] storage slot of compact node t
     unsigned short *nbr = nullptr;   // [27][n] compact index of block b's neighbour (n = none)
 };
-__global__ void __launch_bounds__(512) ccu_k_relax_smem(const CcuGeom g, const CcuSmemLevel sl, const float *__restrict__ K,
-                                                         const double *__restrict__ BI, const double *__restrict__ F, double *x,
-                                                         const int cycles, const int zero_first)
+__global__ void __launch_bounds__(1024) ccu_k_relax_smem(const CcuGeom g, const CcuSmemLevel sl, const float *__restrict__ K,
+                                                          const double *__restrict__ BI, const double *__restrict__ F, double *x,
+                                                          const int cycles, const int zero_first)
 {
     extern __shared__ double smem_d[];
     const int n = sl.n, n1 = n + 1, t = threadIdx.x;
     const size_t NS = (size_t)g.NS;
-    double *xs = smem_d;                               // [3][n1]
-    float *Ks = (float *)(smem_d + 3 * n1);            // [126][n1]
+    double *xs = smem_d;                                   // [3][n1]
+    float *Ks = (float *)(smem_d + 3 * n1);                // [126][n1]
+    unsigned *pk = (unsigned *)(Ks + 126 * n1);            // [n] node indices i | j << 8 | k << 16 of compact node t
+    unsigned short *cmp = (unsigned short *)(pk + n);      // [nno] natural index -> compact index
+    int s = 0;
     if(t < n)
     {   // every thread streams its own node's 126 coefficients (independent loads, consecutive threads ~ consecutive slots)
-        const int st = sl.s[t];
+        s = sl.s[t];
 #pragma unroll 18
-        for(int q = 0; q < 126; q++) Ks[q * n1 + t] = __ldg(K + (size_t)q * NS + st);
+        for(int q = 0; q < 126; q++) Ks[q * n1 + t] = __ldg(K + (size_t)q * NS + s);
+        int i, j, k;
+        ccu_decode(g, s / g.NC, s % g.NC, i, j, k);
+        pk[t] = (unsigned)i | ((unsigned)j << 8) | ((unsigned)k << 16);
+        cmp[k + g.noz * (j + g.nox * i)] = (unsigned short)t;
+#pragma unroll
+        for(int d = 0; d < 3; d++) xs[d * n1 + t] = zero_first ? 0.0 : x[d * NS + s];
     }
     for(int q = t; q < 126; q += blockDim.x) Ks[q * n1 + n] = 0.0f;
-    for(int idx = t; idx < 3 * n1; idx += blockDim.x)
-    {
-        const int d = idx / n1, tt = idx - d * n1;
-        xs[idx] = (tt < n && !zero_first) ? x[d * NS + sl.s[tt]] : 0.0;
-    }
+    if(t < 3) xs[t * n1 + n] = 0.0;
     __syncthreads();
-    // a phase = one colour; 8 lanes per node (lane q takes stencil blocks q, q+8, q+16, q+24), so the ~50 nodes of a
-    // phase keep ~13 warps busy instead of 2 and the per-node chain of shared-memory loads is cut eightfold
+    // A phase = one colour.  8 lanes per node (lane q takes stencil blocks q, q+8, q+16, q+24) and 128 node groups per
+    // CTA keep all ~50-75 nodes of a phase in flight at once.  Nothing in a phase's dependent chain leaves shared
+    // memory: neighbours are found through the natural-index table (the L1 left beside a 227 KB carve-out is too small
+    // to serve table lookups from global memory); F and BI of the three updating lanes are requested up front.
     const int q = t & 7, grp = t >> 3;
     for(int sw = 0; sw < cycles; sw++)
         for(int c = 7; c >= 0; c--)
         {
-            for(int base = sl.cstart[c]; base < sl.cstart[c + 1]; base += (int)(blockDim.x >> 3))
+            const int tt = sl.cstart[c] + grp;
+            const bool act = tt < sl.cstart[c + 1];
+            double fq = 0.0, bq = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            if(act)
             {
-                const int tt = base + grp;
-                const bool act = tt < sl.cstart[c + 1];
-                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-                if(act)
-                {
+                if(q < 3) { const int sn = sl.s[tt]; fq = F[q * NS + sn]; bq = BI[q * NS + sn]; }
+                const unsigned p = pk[tt];
+                const int i = p & 255, j = (p >> 8) & 255, k = (p >> 16) & 255;
 #pragma unroll
-                    for(int b = q; b < 27; b += 8)
+                for(int it = 0; it < 4; it++)
+                {
+                    const int b = q + 8 * it;
+                    if(b < 27)
                     {
-                        const int m = sl.nbr[b * n + tt];
+                        const bool tr = b >= 14;
+                        const int u = tr ? b - 14 : b - 1;         // index into CCU_LO, -1 for the self block
+                        int di = 0, dj = 0, dk = 0;
+                        if(u >= 0)
+                        {
+                            if(u < 9) { di = -1; dj = u / 3 - 1; dk = u % 3 - 1; }
+                            else if(u < 12) { dj = -1; dk = u - 10; }
+                            else dk = -1;
+                        }
+                        if(tr) { di = -di; dj = -dj; dk = -dk; }
+                        const int ii = i + di, jj = j + dj, kk = k + dk;
+                        const bool in = ii >= 0 && ii < g.noy && jj >= 0 && jj < g.nox && kk >= 0 && kk < g.noz;
+                        const int m = in ? (int)cmp[kk + g.noz * (jj + g.nox * ii)] : n;
                         const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
-                        if(b < 14)
+                        if(!tr)
                         {
                             const float *kp = Ks + (b * 9) * n1 + tt;
                             r0 += (double)kp[0] * x0 + (double)kp[n1] * x1 + (double)kp[2 * n1] * x2;
@@ -409,23 +432,21 @@ __global__ void __launch_bounds__(512) ccu_k_relax_smem(const CcuGeom g, const C
                         }
                     }
                 }
+            }
 #pragma unroll
-                for(int o = 4; o > 0; o >>= 1)
-                {
-                    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-                    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-                    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-                }
-                if(act && q < 3)
-                {   // lanes 0..2 of the group update one equation each
-                    const int sn = sl.s[tt];
-                    const double r = q == 0 ? r0 : (q == 1 ? r1 : r2);
-                    xs[q * n1 + tt] += (double)(float)((F[q * NS + sn] - r) * BI[q * NS + sn]);
-                }
+            for(int o = 4; o > 0; o >>= 1)
+            {
+                r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+                r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+                r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+            }
+            if(act && q < 3)
+            {   // lanes 0..2 of the group update one equation each
+                const double r = q == 0 ? r0 : (q == 1 ? r1 : r2);
+                xs[q * n1 + tt] += (double)(float)((fq - r) * bq);
             }
             __syncthreads();
         }
-    const int s = (t < n) ? sl.s[t] : 0;
     if(t < n) { x[s] = xs[t]; x[NS + s] = xs[n1 + t]; x[2 * NS + s] = xs[2 * n1 + t]; }
 }
 

@@ -84,7 +84,7 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
         for(auto p : pv) { CK(cudaMalloc(p, sizeof(double) * np)); CK(cudaMemsetAsync(*p, 0, sizeof(double) * np, c->st)); }
     }
     for(int lev = cfg->levmin; lev <= cfg->levmax; lev++)
-        if(c->L[lev].g.nno <= 439 && ensure_smem_tables(c, c->L[lev])) return 1;
+        if(c->L[lev].g.nno <= 434 && ensure_smem_tables(c, c->L[lev])) return 1;
     CK(cudaMalloc(&c->scal, sizeof(double) * S_COUNT));
     CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_COUNT, c->st));
     { const double one = 1.0; CK(cudaMemcpyAsync(c->scal + S_ONE, &one, sizeof(double), cudaMemcpyHostToDevice, c->st)); }
@@ -140,7 +140,7 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_WARP_NODES: c->opt_warp_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_QUAD_NODES: c->opt_quad_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_LANES_LARGE: if(value != 1 && value != 4) FAIL("lanes must be 1 or 4"); c->opt_lanes_large = value; drop_graphs(c); return 0;
-    case CCU_OPT_SMEM_NODES: c->opt_smem_nodes = value > 439 ? 439 : value; drop_graphs(c); return 0;
+    case CCU_OPT_SMEM_NODES: c->opt_smem_nodes = value > 434 ? 434 : value; drop_graphs(c); return 0;
     case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
     default: FAIL("set_option: unknown option");
@@ -338,6 +338,8 @@ static int ensure_smem_tables(ccu_ctx *c, Level &L)
     }
     L.sm_cstart[8] = t;
     if(t != n) FAIL("smem tables: node count mismatch");
+    for(int col = 0; col < 8; col++)
+        if(L.sm_cstart[col + 1] - L.sm_cstart[col] > 128) return 0;      // more nodes per colour than the kernel's 128 groups: not eligible
     std::vector<unsigned short> nbr((size_t)27 * n);
     for(int tt = 0; tt < n; tt++)
     {
@@ -401,8 +403,8 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         {   // ... out of shared memory when the whole half-matrix fits
             CcuSmemLevel sl; sl.n = L.sm_n; sl.s = L.sm_s; sl.nbr = L.sm_nbr;
             for(int q = 0; q < 9; q++) sl.cstart[q] = L.sm_cstart[q];
-            const size_t bytes = (size_t)(L.sm_n + 1) * (3 * sizeof(double) + 126 * sizeof(float));
-            ccu_k_relax_smem<<<1, 512, bytes, c->st>>>(L.g, sl, L.K, L.BI, F, x, cycles, 0);
+            const size_t bytes = (size_t)(L.sm_n + 1) * (3 * sizeof(double) + 126 * sizeof(float)) + (size_t)L.sm_n * 6 + 16;
+            ccu_k_relax_smem<<<1, 1024, bytes, c->st>>>(L.g, sl, L.K, L.BI, F, x, cycles, 0);
             c->launches++;
             return;
         }

@@ -51,7 +51,7 @@ int ccu_synchronize(ccu_ctx *ctx);
 /* MATVEC_TAB / RELAX_TAB: table-driven (compact code) row kernels on levels above QUAD_NODES */
 enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_OPT_QUAD_NODES = 3, CCU_OPT_LANES_LARGE = 4,
        CCU_OPT_MATVEC_TAB = 5, CCU_OPT_RELAX_TAB = 6,
-       CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 439) run all sweeps out of one SM's shared memory */ };
+       CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);
