@@ -908,6 +908,14 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));
+    if(c->coarse)
+    {   // replicated coarse levels: their operators are built from the gathered viscosity of level agg_lev, exactly as a
+        // single subdomain owning the whole mesh would build them
+        if(ensure_nodal(c->coarse)) return 1;
+        c->coarse->visc = c->visc;
+        if(ccu_agg_gather_evi(c)) return 1;
+        return ccu_construct_stiffness_B_matrix(c->coarse, augmented_Lagr, augmented, precondition);
+    }
     return 0;
 }
 

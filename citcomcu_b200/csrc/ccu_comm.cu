@@ -133,6 +133,7 @@ struct NcclApi
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -148,7 +149,7 @@ int load_nccl()
     if(!h) FAIL(std::string("cannot load libnccl.so.2: ") + dlerror());
 #define BIND(field, sym) do { *(void **)(&g_nccl.field) = dlsym(h, sym); if(!g_nccl.field) FAIL(std::string("libnccl lacks ") + sym); } while(0)
     BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
-    BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv"); BIND(AllReduce, "ncclAllReduce");
+    BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv"); BIND(AllReduce, "ncclAllReduce"); BIND(AllGather, "ncclAllGather");
     BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd"); BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
     g_nccl.handle = h;
@@ -361,5 +362,14 @@ int ccu_allreduce_buffer(ccu_ctx *c, double *buf, int count, int op_max)
 {
     CcuComm *m = c->comm;
     if(m && m->nranks > 1) NK(g_nccl.AllReduce(buf, buf, (size_t)count, ncclDouble, op_max ? ncclMax : ncclSum, (ncclComm_t)m->nccl, c->st));
+    return 0;
+}
+
+// every rank's `bytes_per_rank` block, concatenated in rank order, on every rank
+int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_rank)
+{
+    CcuComm *m = c->comm;
+    if(!m || m->nranks == 1) { CK(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, c->st)); return 0; }
+    NK(g_nccl.AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t)m->nccl, c->st));
     return 0;
 }

@@ -102,6 +102,15 @@ struct ccu_ctx
     } en;
     long long launches = 0;
     CcuComm *comm = nullptr;       // null = single subdomain
+    // Replicated coarse levels (multi-subdomain runs): levels <= agg_lev of the multigrid hierarchy live in `coarse`, a
+    // single-subdomain context holding the GLOBAL mesh of those levels on every GPU.  One all-gather hands the
+    // restricted right-hand side to all ranks, every rank runs the identical coarse part of the cycle without any
+    // further communication, and takes its own piece of the correction back (ccu_stokes.cu, mg_inner).
+    ccu_ctx *coarse = nullptr;
+    int agg_lev = -1;
+    bool replica = false;          // this context IS such a coarse replica (its top level is not the finest level)
+    void *agg_buf = nullptr;       // all-gather landing zone
+    size_t agg_bytes = 0;
     bool multi() const { return comm && comm->nranks > 1; }
     // CUDA-event profiling of kernel classes (ccu_profile_*)
     bool prof_on = false;
@@ -147,5 +156,7 @@ int ccu_halo_sum_face(ccu_ctx *c, int lev);                   // partial rows of
 int ccu_halo_sum_nodal(ccu_ctx *c, int lev, float *field);    // exchange_node_f20
 int ccu_allreduce_dots(ccu_ctx *c, int count, double *o0, double *o1, double *o2);
 int ccu_allreduce_buffer(ccu_ctx *c, double *buf, int count, int op_max);
-int ccu_damp_face_BI(ccu_ctx *c, int lev);                  // rebuild_BI_on_boundary (ccu_stokes.cu)
+int ccu_damp_face_BI(ccu_ctx *c, int lev);
+int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_rank);
+int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of all subdomains -> coarse replica (ccu_stokes.cu)                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);

@@ -943,3 +943,44 @@ __global__ void __launch_bounds__(128) ccu_k_grad_p(const CcuGeom g, const float
     gradP[(size_t)g.NS + s] = (f & CCU_F_VBY) ? 0.0 : s1;
     gradP[2 * (size_t)g.NS + s] = (f & CCU_F_VBZ) ? 0.0 : s2;
 }
+
+// ---------------------------------------------------------------- replicated coarse levels (multi-subdomain runs)
+// Block decomposition arithmetic (Parallel_related.c:139-170): subdomain (px, py, pz) holds elements
+// [p*el_local, (p+1)*el_local) per axis; rank = pz + npz*px + npz*npx*py.
+struct CcuAgg { int npx, npy, npz, mex, mey, mez; };
+// all subdomains' level vectors (colour layout, gathered in rank order) -> the global level vector
+__global__ void __launch_bounds__(128) ccu_k_agg_scatter_vec(const CcuGeom gl, const CcuGeom gg, const CcuAgg a, const double *__restrict__ buf, double *gvec)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= gg.nno) return;
+    const int K = n % gg.noz, J = (n / gg.noz) % gg.nox, I = n / (gg.noz * gg.nox);
+    const int px = min(J / gl.elx, a.npx - 1), py = min(I / gl.ely, a.npy - 1), pz = min(K / gl.elz, a.npz - 1);
+    const int r = pz + a.npz * px + a.npz * a.npx * py;
+    const int sl = ccu_sidx(gl, I - py * gl.ely, J - px * gl.elx, K - pz * gl.elz), sg = ccu_sidx(gg, I, J, K);
+    const double *src = buf + (size_t)r * 3 * gl.NS;
+#pragma unroll
+    for(int d = 0; d < 3; d++) gvec[(size_t)d * gg.NS + sg] = src[(size_t)d * gl.NS + sl];
+}
+// this subdomain's piece of a global level vector
+__global__ void __launch_bounds__(128) ccu_k_agg_extract_vec(const CcuGeom gl, const CcuGeom gg, const CcuAgg a, const double *__restrict__ gvec, double *lvec)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= gl.nno) return;
+    const int k = n % gl.noz, j = (n / gl.noz) % gl.nox, i = n / (gl.noz * gl.nox);
+    const int sl = ccu_sidx(gl, i, j, k), sg = ccu_sidx(gg, i + a.mey * gl.ely, j + a.mex * gl.elx, k + a.mez * gl.elz);
+#pragma unroll
+    for(int d = 0; d < 3; d++) lvec[(size_t)d * gl.NS + sl] = gvec[(size_t)d * gg.NS + sg];
+}
+// element viscosities EVI[nel*8] of all subdomains -> global element order
+__global__ void __launch_bounds__(128) ccu_k_agg_scatter_evi(const CcuGeom gl, const CcuGeom gg, const CcuAgg a, const float *__restrict__ buf, float *gEVI)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= gg.nel) return;
+    const int ez = e % gg.elz, ex = (e / gg.elz) % gg.elx, ey = e / (gg.elz * gg.elx);
+    const int px = ex / gl.elx, py = ey / gl.ely, pz = ez / gl.elz;
+    const int r = pz + a.npz * px + a.npz * a.npx * py;
+    const int el = (ez - pz * gl.elz) + gl.elz * ((ex - px * gl.elx) + gl.elx * (ey - py * gl.ely));
+    const float *src = buf + ((size_t)r * gl.nel + el) * 8;
+#pragma unroll
+    for(int q = 0; q < 8; q++) gEVI[(size_t)e * 8 + q] = src[q];
+}

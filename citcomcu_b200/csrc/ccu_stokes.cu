@@ -6,6 +6,7 @@
 #include "ccu_ctx.cuh"
 #include "ccu_kernels.cuh"
 #include "ccu_comm.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -103,6 +104,8 @@ static void drop_graphs(ccu_ctx *c) { ccu_drop_graphs(c); }
 void ccu_destroy(ccu_ctx *c)
 {
     if(!c) return;
+    if(c->coarse) { ccu_destroy(c->coarse); c->coarse = nullptr; }
+    cudaFree(c->agg_buf);
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
@@ -128,6 +131,7 @@ int ccu_set_stream(ccu_ctx *c, void *s)
     if(!c) FAIL("null context");
     CK(cudaStreamSynchronize(c->st));
     c->st = s ? (cudaStream_t)s : c->own_stream;     // NULL selects the context's own stream again
+    if(c->coarse) { drop_graphs(c); c->coarse->st = c->st; }
     return 0;
 }
 int ccu_set_option(ccu_ctx *c, int option, int value)
@@ -148,6 +152,39 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
 }
 int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); CK(cudaStreamSynchronize(c->st)); return 0; }
 long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------ replicated coarse levels
+int ccu_agglomerate(ccu_ctx *c, int agg_lev, ccu_ctx **coarse_out)
+{
+    if(!c) FAIL("null context");
+    if(!c->multi()) FAIL("agglomerate: only meaningful after ccu_comm_init with more than one subdomain");
+    if(c->coarse) FAIL("agglomerate: already set up");
+    if(agg_lev < c->cfg.levmin || agg_lev >= c->cfg.levmax) FAIL("agglomerate: level must be below the finest level");
+    ccu_config cfg = c->cfg;
+    cfg.levmax = agg_lev;
+    const int *np = c->comm->nproc;
+    for(int lev = cfg.levmin; lev <= agg_lev; lev++)
+    {
+        cfg.nox[lev] = c->L[lev].g.elx * np[0] + 1;
+        cfg.noy[lev] = c->L[lev].g.ely * np[1] + 1;
+        cfg.noz[lev] = c->L[lev].g.elz * np[2] + 1;
+    }
+    ccu_ctx *g = nullptr;
+    if(ccu_create(&cfg, &g)) return 1;
+    g->replica = true;
+    g->use_graphs = false;                       // its kernels are captured into the owner's graphs
+    cudaStreamDestroy(g->own_stream);
+    g->own_stream = 0; g->st = c->st;
+    g->visc = c->visc;
+    Level &Ll = c->L[agg_lev];
+    const size_t need = std::max(sizeof(double) * Ll.vlen(), sizeof(float) * 8 * (size_t)Ll.g.nel) * (size_t)c->comm->nranks;
+    CK(cudaMalloc(&c->agg_buf, need));
+    c->agg_bytes = need;
+    c->coarse = g; c->agg_lev = agg_lev;
+    drop_graphs(c);
+    if(coarse_out) *coarse_out = g;
+    return 0;
+}
 
 // ------------------------------------------------------------------ uploads
 int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
@@ -494,7 +531,7 @@ static int run_segment(ccu_ctx *c, int id, F body)
     ccu_ctx::GraphSeg &s = c->seg[id];
     if(!s.exec)
     {
-        const long long l0 = c->launches;
+        const long long l0 = c->launches, g0 = c->coarse ? c->coarse->launches : 0;
         const bool prof = c->prof_on;
         c->prof_on = false;
         CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
@@ -502,8 +539,9 @@ static int run_segment(ccu_ctx *c, int id, F body)
         cudaGraph_t g = nullptr;
         CK(cudaStreamEndCapture(c->st, &g));
         c->prof_on = prof;
-        s.launches = c->launches - l0;
+        s.launches = c->launches - l0 + (c->coarse ? c->coarse->launches - g0 : 0);
         c->launches = l0;
+        if(c->coarse) c->coarse->launches = g0;
         CK(cudaGraphInstantiate(&s.exec, g, 0));
         cudaGraphDestroy(g);
     }
@@ -521,7 +559,7 @@ static void mg_down(ccu_ctx *c, int dlev, bool warm)
 {
     Level *L = c->L;
     Level &D = L[dlev];
-    const int cycles = (dlev == c->cfg.levmax) ? c->cfg.v_steps_high : c->cfg.down_heavy;
+    const int cycles = (dlev == c->cfg.levmax && !c->replica) ? c->cfg.v_steps_high : c->cfg.down_heavy;
     if(!warm) d_zero(c, D.vec[CCU_VEC_VEL], D.vlen());
     d_relax_sweeps(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], cycles);
     d_residual(c, D, D.vec[CCU_VEC_VEL], D.vec[CCU_VEC_RHS], D.vec[CCU_VEC_RES]);   // res = rhs - AU
@@ -531,13 +569,13 @@ static void mg_up(ccu_ctx *c, int ulev)
 {
     Level *L = c->L;
     Level &U = L[ulev];
-    const int cycles = (ulev == c->cfg.levmax) ? c->cfg.v_steps_high : c->cfg.up_heavy;
+    const int cycles = (ulev == c->cfg.levmax && !c->replica) ? c->cfg.v_steps_high : c->cfg.up_heavy;
     d_interp(c, ulev - 1, L[ulev - 1].vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], 1);
     d_gauss_seidel(c, U, U.vec[CCU_VEC_DEL_VEL], U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], cycles, 1);
     // alpha = <AU,res>/<AU,AU>  (line search, :626-627); both dots share one pass
     d_dot3m(c, &U, U.vlen(), U.vec[CCU_VEC_AU], U.vec[CCU_VEC_AU], S_DOT1, U.vec[CCU_VEC_AU], U.vec[CCU_VEC_RES], S_DOT2);
     d_axpby(c, U.vlen(), U.vec[CCU_VEC_VEL], U.vec[CCU_VEC_DEL_VEL], coef(c->scal + S_DOT2, c->scal + S_DOT1, 1.0), C_ONE);
-    if(ulev == c->cfg.levmax)
+    if(ulev == c->cfg.levmax && !c->replica)
         d_axpby(c, U.vlen(), U.vec[CCU_VEC_RES], U.vec[CCU_VEC_AU], coef(c->scal + S_DOT2, c->scal + S_DOT1, -1.0), C_ONE);
 }
 static void mg_bottom(ccu_ctx *c)
@@ -545,11 +583,55 @@ static void mg_bottom(ccu_ctx *c)
     Level &B = c->L[c->cfg.levmin];
     d_gauss_seidel(c, B, B.vec[CCU_VEC_VEL], B.vec[CCU_VEC_RHS], B.vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
 }
+// replicated coarse levels: vector `v` of level agg_lev, subdomain pieces -> global copy in the replica, and back
+static CcuAgg agg_info(const ccu_ctx *c)
+{
+    const CcuComm *m = c->comm;
+    return CcuAgg{ m->nproc[0], m->nproc[1], m->nproc[2], m->me[0], m->me[1], m->me[2] };
+}
+static int agg_gather(ccu_ctx *c, int v)
+{
+    ccu_ctx *g = c->coarse;
+    Level &Ll = c->L[c->agg_lev], &Lg = g->L[c->agg_lev];
+    if(ccu_allgather(c, Ll.vec[v], c->agg_buf, sizeof(double) * Ll.vlen())) return 1;
+    LAUNCH(g, ccu_k_agg_scatter_vec, cdiv(Lg.g.nno, 128), 128, Ll.g, Lg.g, agg_info(c), (const double *)c->agg_buf, Lg.vec[v]);
+    return 0;
+}
+static void agg_extract(ccu_ctx *c, int v)
+{
+    ccu_ctx *g = c->coarse;
+    Level &Ll = c->L[c->agg_lev], &Lg = g->L[c->agg_lev];
+    LAUNCH(g, ccu_k_agg_extract_vec, cdiv(Ll.g.nno, 128), 128, Ll.g, Lg.g, agg_info(c), (const double *)Lg.vec[v], Ll.vec[v]);
+}
+int ccu_agg_gather_evi(ccu_ctx *c)
+{
+    ccu_ctx *g = c->coarse;
+    Level &Ll = c->L[c->agg_lev], &Lg = g->L[c->agg_lev];
+    if(!Ll.EVI || !Lg.EVI) FAIL("agglomeration: element viscosity arrays missing");
+    if(ccu_allgather(c, Ll.EVI, c->agg_buf, sizeof(float) * 8 * (size_t)Ll.g.nel)) return 1;
+    LAUNCH(g, ccu_k_agg_scatter_evi, cdiv(Lg.g.nel, 128), 128, Ll.g, Lg.g, agg_info(c), (const float *)c->agg_buf, Lg.EVI);
+    Lg.have_evi = true;
+    return 0;
+}
+
 static void mg_inner(ccu_ctx *c, int lev)       // everything of a V-cycle on `lev` that lives below it
 {
-    for(int dlev = lev - 1; dlev >= c->cfg.levmin + 1; dlev--) mg_down(c, dlev, false);
-    mg_bottom(c);
-    for(int ulev = c->cfg.levmin + 1; ulev <= lev - 1; ulev++) mg_up(c, ulev);
+    ccu_ctx *g = c->coarse;
+    if(!g)
+    {
+        for(int dlev = lev - 1; dlev >= c->cfg.levmin + 1; dlev--) mg_down(c, dlev, false);
+        mg_bottom(c);
+        for(int ulev = c->cfg.levmin + 1; ulev <= lev - 1; ulev++) mg_up(c, ulev);
+        return;
+    }
+    const int La = c->agg_lev;                   // lev > La: levels lev-1 .. La+1 are distributed, La .. levmin replicated
+    for(int dlev = lev - 1; dlev > La; dlev--) mg_down(c, dlev, false);
+    agg_gather(c, CCU_VEC_RHS);
+    for(int dlev = La; dlev >= g->cfg.levmin + 1; dlev--) mg_down(g, dlev, false);
+    mg_bottom(g);
+    for(int ulev = g->cfg.levmin + 1; ulev <= La; ulev++) mg_up(g, ulev);
+    agg_extract(c, CCU_VEC_VEL);
+    for(int ulev = La + 1; ulev <= lev - 1; ulev++) mg_up(c, ulev);
 }
 
 // F: in rhs, out residual; d1: out correction.  Leaves the squared residual norm in scal[S_DOT0].
@@ -563,19 +645,35 @@ static int d_multi_grid(ccu_ctx *c, double *d1, double *F)
         d_project(c, levmax, L[levmax].vec[CCU_VEC_FL], L[levmax - 1].vec[CCU_VEC_FL], 1);
         // full multigrid below the finest level: restrict fl, bottom solve, nested V-cycles (:559-640)
         if(run_segment(c, 0, [&]() {
+            // levels <= La are replicated in `g` (g == c, La == levmin - 1 ... without agglomeration everything is `c`)
+            ccu_ctx *g = c->coarse ? c->coarse : c;
+            const int La = c->coarse ? c->agg_lev : levmax;
+            auto X = [&](int lev) { return lev <= La ? g : c; };
             for(int lev = levmax - 1; lev > levmin; lev--)
-                d_project(c, lev, L[lev].vec[CCU_VEC_FL], L[lev - 1].vec[CCU_VEC_FL], 1);
-            d_gauss_seidel(c, L[levmin], L[levmin].vec[CCU_VEC_VEL], L[levmin].vec[CCU_VEC_FL], L[levmin].vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+            {
+                if(c->coarse && lev == La) agg_gather(c, CCU_VEC_FL);
+                ccu_ctx *x = X(lev);
+                d_project(x, lev, x->L[lev].vec[CCU_VEC_FL], x->L[lev - 1].vec[CCU_VEC_FL], 1);
+            }
+            if(c->coarse && La == levmin) agg_gather(c, CCU_VEC_FL);
+            {
+                Level &B = g->L[levmin];
+                d_gauss_seidel(g, B, B.vec[CCU_VEC_VEL], B.vec[CCU_VEC_FL], B.vec[CCU_VEC_AU], c->cfg.v_steps_low, 0);
+            }
+            if(c->coarse && La == levmin) agg_extract(c, CCU_VEC_VEL);
             for(int lev = levmin + 1; lev < levmax; lev++)
             {
-                d_interp(c, lev - 1, L[lev - 1].vec[CCU_VEC_VEL], L[lev].vec[CCU_VEC_VEL], 1);
-                d_copy(c, L[lev].vec[CCU_VEC_RHS], L[lev].vec[CCU_VEC_FL], L[lev].vlen());
+                ccu_ctx *x = X(lev);
+                Level *XL = x->L;
+                d_interp(x, lev - 1, XL[lev - 1].vec[CCU_VEC_VEL], XL[lev].vec[CCU_VEC_VEL], 1);
+                d_copy(x, XL[lev].vec[CCU_VEC_RHS], XL[lev].vec[CCU_VEC_FL], XL[lev].vlen());
                 for(int Vn = 1; Vn <= c->cfg.mg_cycle; Vn++)
                 {
-                    mg_down(c, lev, true);
-                    mg_inner(c, lev);
-                    mg_up(c, lev);
+                    mg_down(x, lev, true);
+                    mg_inner(x, lev);
+                    mg_up(x, lev);
                 }
+                if(c->coarse && lev == La) agg_extract(c, CCU_VEC_VEL);
             }
         })) return 1;
         d_interp(c, levmax - 1, L[levmax - 1].vec[CCU_VEC_VEL], L[levmax].vec[CCU_VEC_VEL], 1);

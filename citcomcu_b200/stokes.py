@@ -55,9 +55,9 @@ class StokesContext:
         return (x - 1) * (y - 1) * (z - 1)
 
     def close(self):
-        if self._ctx:
+        if self._ctx and getattr(self, "_owned", True):
             self.lib.ccu_destroy(self._ctx)
-            self._ctx = C.c_void_p()
+        self._ctx = C.c_void_p()
 
     def __del__(self):
         try:
@@ -88,6 +88,19 @@ class StokesContext:
         check(self.lib.ccu_comm_init(self._ctx, int(nproc[0]), int(nproc[1]), int(nproc[2]), int(me_loc[0]), int(me_loc[1]),
                                      int(me_loc[2]), uid))
         self.nproc, self.me_loc = tuple(nproc), tuple(me_loc)
+
+    def agglomerate(self, agg_lev, global_dims):
+        """Replicate the multigrid levels <= agg_lev on every rank (ccu_agglomerate).  Returns a non-owning
+        StokesContext for the GLOBAL mesh of those levels: give it the global node flags and coordinates, then
+        build_geometry().  `global_dims[lev]` = (nox, noy, noz) of the global mesh."""
+        out = C.c_void_p()
+        check(self.lib.ccu_agglomerate(self._ctx, int(agg_lev), C.byref(out)))
+        g = StokesContext.__new__(StokesContext)
+        g.lib, g._ctx, g._owned = self.lib, out, False
+        g.levmin, g.levmax = self.levmin, agg_lev
+        g.dims = {lev: tuple(global_dims[lev]) for lev in range(self.levmin, agg_lev + 1)}
+        self.coarse = g
+        return g
 
     @property
     def launch_count(self) -> int:
@@ -427,7 +440,10 @@ def context_from_dump(dump, **overrides) -> StokesContext:
     return ctx
 
 
-def context_from_problem(prob, device=0, unique_id=None, **overrides) -> StokesContext:
+AGG_NODES = 30000      # multigrid levels whose GLOBAL mesh has at most this many nodes are solved replicated on every rank
+
+
+def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, **overrides) -> StokesContext:
     """Build a context for one subdomain of a `citcomcu_b200.problem.CartesianProblem`: mesh, flags and
     coordinates go up, every operator array is then constructed on the device (ccu_build_geometry here,
     viscosity / stiffness at the first general_stokes_solver call)."""
@@ -440,6 +456,15 @@ def context_from_problem(prob, device=0, unique_id=None, **overrides) -> StokesC
         ctx.set_node_flags(lev, prob.node_flags(lev))
         ctx.set_coordinates(lev, *prob.coordinates(lev))
     ctx.build_geometry()
+    if prob.nproc != (1, 1, 1) and agglomerate:
+        gp = prob.global_problem()
+        levs = [lev for lev in range(prob.levmin, prob.levmax) if gp.nno(lev) <= AGG_NODES]
+        if levs:
+            g = ctx.agglomerate(max(levs), {lev: gp.dims(lev) for lev in range(gp.levmin, gp.levmax + 1)})
+            for lev in range(g.levmin, g.levmax + 1):
+                g.set_node_flags(lev, gp.node_flags(lev))
+                g.set_coordinates(lev, *gp.coordinates(lev))
+            g.build_geometry()
     v = prob.visc
     ctx.set_viscosity_law(v["tdepv"], v["rheol"], v["N0"], v["E"], v["T"], v["Z"], v["vmin"], v["min_value"], v["vmax"],
                           v["max_value"], v["smooth_cycles"])

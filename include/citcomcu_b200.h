@@ -67,6 +67,14 @@ long long ccu_launch_count(ccu_ctx *ctx);
  * nproc = 1x1x1 is allowed (no NCCL needed) and is the default when ccu_comm_init is never called. */
 int ccu_comm_unique_id(char *out128);
 int ccu_comm_init(ccu_ctx *ctx, int nprocx, int nprocy, int nprocz, int me_x, int me_y, int me_z, const char *unique_id128);
+/* Replicated coarse levels: below a few ten thousand nodes a multigrid level is pure latency, and a halo exchange per
+ * smoother sweep makes it worse.  After ccu_agglomerate(ctx, lev) the levels <= lev are solved REPLICATED: every rank
+ * holds the GLOBAL mesh of those levels in the returned context, one all-gather per visit hands over the restricted
+ * right-hand side, all ranks run the identical coarse part of the cycle with no further communication, and each takes
+ * its piece of the correction back.  The caller gives the returned context the global node flags and coordinates of
+ * levels levmin..lev (ccu_set_node_flags, ccu_set_coordinates) and calls ccu_build_geometry on it; the operators are
+ * then (re)built together with ctx's.  The returned context is owned by ctx (do not destroy it). */
+int ccu_agglomerate(ccu_ctx *ctx, int agg_lev, ccu_ctx **coarse_out);
 /* host-only table builders behind ccu_comm_init (no GPU needed; tests/test_decomp.py): sizes = {neighbours, packed nodes,
  * duplicated nodes, contributions}; see csrc/ccu_comm.cuh for the meaning of the arrays */
 int ccu_halo_sizes(const int nproc[3], const int me[3], int nox, int noy, int noz, int sizes[4]);

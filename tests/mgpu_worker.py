@@ -16,7 +16,7 @@ def seeded_global_vector(gp, lev, seed):
     return rng.uniform(-1.0, 1.0, 3 * gp.nno(lev))
 
 
-def run_rank(rank, world, text, uid_q, out_q, accuracy, device_of_rank=None):
+def run_rank(rank, world, text, uid_q, out_q, accuracy, agglomerate=True, device_of_rank=None):
     try:
         from citcomcu_b200 import decomp
         from citcomcu_b200.problem import CartesianProblem
@@ -32,7 +32,7 @@ def run_rank(rank, world, text, uid_q, out_q, accuracy, device_of_rank=None):
         else:
             uid = uid_q.get(timeout=120)
         dev = rank if device_of_rank is None else device_of_rank[rank]
-        ctx = context_from_problem(prob, device=dev, unique_id=uid, accuracy=accuracy)
+        ctx = context_from_problem(prob, device=dev, unique_id=uid, accuracy=accuracy, agglomerate=agglomerate)
         lm = prob.levmax
         Tg = gp.initial_temperature()
         bg = gp.buoyancy(Tg)

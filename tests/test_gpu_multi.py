@@ -23,12 +23,12 @@ def ngpus():
         return 0
 
 
-def spawn(text, world, accuracy):
+def spawn(text, world, accuracy, agglomerate=True):
     import torch.multiprocessing as mp
     from mgpu_worker import run_rank
     ctx = mp.get_context("spawn")
     uid_q, out_q = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=run_rank, args=(r, world, text, uid_q, out_q, accuracy)) for r in range(world)]
+    procs = [ctx.Process(target=run_rank, args=(r, world, text, uid_q, out_q, accuracy, agglomerate)) for r in range(world)]
     for p in procs:
         p.start()
     res = [out_q.get(timeout=600) for _ in procs]
@@ -44,14 +44,14 @@ def rel(a, b):
 
 
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("nproc", [(2, 1, 1), (1, 1, 2), (1, 2, 1)])
-def test_two_subdomains_match_single_gpu_and_reference(nproc):
+@pytest.mark.parametrize("nproc,agglomerate", [((2, 1, 1), True), ((1, 1, 2), True), ((1, 2, 1), False), ((2, 1, 1), False)])
+def test_two_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
     from citcomcu_b200.problem import CartesianProblem
     from citcomcu_b200.stokes import context_from_problem
     from mgpu_worker import seeded_global_vector
     acc = 1e-8
     text = inputfile.tdepv_box(16, 16, 8, 3, nproc=nproc, maxstep=1, accuracy=acc)
-    res = spawn(text, 2, acc)
+    res = spawn(text, 2, acc, agglomerate)
     # single-GPU run of the whole mesh
     gp = CartesianProblem(text).global_problem()
     ctx = context_from_problem(gp, accuracy=acc)
