@@ -720,6 +720,152 @@ __global__ void __launch_bounds__(256) ek_remove_layer_ave(const CcuGeom g, cons
     if(layer[g.noz + kz] != 0.0) X[n] = X[n] - (float)(layer[kz] / layer[g.noz + kz]);
 }
 
+// ================================================================= markers
+#define CCU_SIDEE 0x800000u
+struct MkGrid
+{
+    const double *XP1, *XP2, *XP3;   // 1-D node coordinates (0-based here: XP[d][i] of the reference is XPd[i-1])
+    const int *RG3;                   // RG[3][0..rnoz]
+    double dx, dy, dzz;
+    int rnoz;
+};
+// get_element (Composition_adv.c:1086-1180): uniform spacing in x and y, table lookup in z; returns the 1-based element
+// number (0 if the marker fell out of the z table); dX = offsets from the element's first node
+__device__ __forceinline__ int mk_get_element(const CcuGeom &g, const MkGrid &m, const double x1, const double x2, const double x3, double dX[3])
+{
+    double t = (x1 - m.XP1[0]) / m.dx + 1;
+    const int IX = (int)(t < (double)g.elx ? t : (double)g.elx);
+    dX[0] = x1 - m.XP1[IX - 1];
+    t = (x2 - m.XP2[0]) / m.dy + 1;
+    const int IY = (int)(t < (double)g.ely ? t : (double)g.ely);
+    dX[1] = x2 - m.XP2[IY - 1];
+    t = (x3 - m.XP3[0]) / m.dzz + 1;
+    const int i1 = (int)(t < (double)(m.rnoz - 1) ? t : (double)(m.rnoz - 1));
+    int IZ = m.RG3[i1];
+    dX[2] = 0.0;
+    if(IZ) dX[2] = x3 - m.XP3[IZ - 1];
+    else
+        for(int i = 0; i <= 2; i += 2)
+        {
+            const int j1 = m.RG3[i1 - 1 + i];
+            if(j1 >= 1 && j1 <= g.elz && x3 >= m.XP3[j1 - 1] && x3 <= m.XP3[j1]) { IZ = j1; dX[2] = x3 - m.XP3[IZ - 1]; }
+        }
+    if(!IZ) return 0;
+    return IZ + (IX - 1) * g.elz + (IY - 1) * g.elz * g.elx;
+}
+// velocity_markers (Composition_adv.c:990-1075): trilinear interpolation of the nodal velocity at XMC (con 0 -> VO) or
+// XMCpred (con 1 -> Vpred); also records the element
+__global__ void __launch_bounds__(128) mk_velocity(const CcuGeom g, const MkGrid m, const int n, const int cap, const double *__restrict__ X,
+                                                   const float *__restrict__ eco, const float *__restrict__ V, float *Vout, int *CElement, int *err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    double dX[3];
+    const int el = mk_get_element(g, m, X[i], X[(size_t)cap + i], X[2 * (size_t)cap + i], dX);
+    if(!el) { atomicAdd(err, 1); return; }
+    const int e = el - 1;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    const double sz = (double)eco[(size_t)e * 3 + 2];
+    const double w[8] = { (m.dx - dX[0]) * (m.dy - dX[1]) * (sz - dX[2]), dX[0] * (m.dy - dX[1]) * (sz - dX[2]), dX[0] * dX[1] * (sz - dX[2]),
+                          (m.dx - dX[0]) * dX[1] * (sz - dX[2]), (m.dx - dX[0]) * (m.dy - dX[1]) * dX[2], dX[0] * (m.dy - dX[1]) * dX[2],
+                          dX[0] * dX[1] * dX[2], (m.dx - dX[0]) * dX[1] * dX[2] };
+    const double area = m.dx * m.dy * sz;
+    int nd[8];
+    for(int a = 1; a <= 8; a++) nd[a - 1] = elt_node(g, ey, ex, ez, a);
+    for(int d = 0; d < 3; d++)
+    {
+        const float *Vd = V + (size_t)d * g.nno;
+        double s = w[0] * (double)Vd[nd[0]];
+        for(int a = 1; a < 8; a++) s = s + w[a] * (double)Vd[nd[a]];
+        Vout[(size_t)d * cap + i] = (float)(s / area);
+    }
+    CElement[i] = el;
+}
+// Euler predictor / modified-Euler corrector of the positions (Composition_adv.c:115-121, 71-77): dt*VO is a FLOAT product
+__global__ void __launch_bounds__(256) mk_advance(const int n, const int cap, const float dt, const int corrector, const float *__restrict__ VO,
+                                                  const float *__restrict__ Vpred, double *X, double *Xpred)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    for(int d = 0; d < 3; d++)
+    {
+        const size_t q = (size_t)d * cap + i;
+        if(!corrector) Xpred[q] = X[q] + (double)(dt * VO[q]);
+        else X[q] = X[q] + 0.5 * (double)dt * (double)(VO[q] + Vpred[q]);
+    }
+}
+// move_tracers_to_neighbors (Composition_adv.c:218-400), one subdomain: markers of boundary (SIDEE) elements are clamped
+// into [XG1, XG2]
+__global__ void __launch_bounds__(256) mk_clamp(const int n, const int cap, const unsigned *__restrict__ Element, const int *__restrict__ CElement,
+                                                const double g1x, const double g1y, const double g1z, const double g2x, const double g2y,
+                                                const double g2z, double *X)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    if(!(Element[CElement[i] - 1] & CCU_SIDEE)) return;
+    const double lo[3] = { g1x, g1y, g1z }, hi[3] = { g2x, g2y, g2z };
+    for(int d = 0; d < 3; d++)
+    {
+        double v = X[(size_t)d * cap + i];
+        v = v < hi[d] ? v : hi[d];
+        v = v > lo[d] ? v : lo[d];
+        X[(size_t)d * cap + i] = v;
+    }
+}
+// element_markers (Composition_adv.c:960-985) + the per-element counts of get_C_from_markers (:757-760)
+__global__ void __launch_bounds__(128) mk_assign_count(const CcuGeom g, const MkGrid m, const int n, const int cap, const double *__restrict__ X,
+                                                       const int *__restrict__ C12, int *CElement, int *count, int *err)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    double dX[3];
+    const int el = mk_get_element(g, m, X[i], X[(size_t)cap + i], X[2 * (size_t)cap + i], dX);
+    if(!el) { atomicAdd(err, 1); return; }
+    CElement[i] = el;
+    atomicAdd(count + (size_t)C12[i] * g.nel + (el - 1), 1);
+}
+// ratio method (Composition_adv.c:786-803): CE = dense / (regular + dense), elements without markers keep their CE
+__global__ void __launch_bounds__(256) mk_element_C(const int nel, const int *__restrict__ count, float *CE)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= nel) return;
+    const int c0 = count[e], c1 = count[(size_t)nel + e];
+    if(c0 || c1) { const float t0 = (float)c0, t1 = (float)c1; CE[e] = t1 / (t0 + t1); }
+}
+// C[node] = Mass * sum over its elements (ascending) of TWW * CE   (:797-811), float accumulator
+__global__ void __launch_bounds__(128) mk_nodal_C(const CcuGeom g, const float *__restrict__ TWW, const float *__restrict__ MASS,
+                                                  const float *__restrict__ CE, float *C)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    float acc = 0.0f;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                acc = acc + TWW[(size_t)e * 8 + LUT[k - ez][j - ex][i - ey] - 1] * CE[e];
+            }
+        }
+    }
+    C[n] = acc * MASS[n];
+}
+// thermo-chemical buoyancy (Pan_problem_misc_functions.c:125-128): Atemp*T*expansivity - Acomp*C
+__global__ void __launch_bounds__(256) ek_buoyancy_comp(const CcuGeom g, const float Atemp, const float Acomp, const float *__restrict__ T,
+                                                        const float *__restrict__ C, const float *__restrict__ expansivity, float *buoy)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    buoy[n] = Atemp * T[n] * expansivity[n % g.noz] - Acomp * C[n];
+}
+
 // ================================================================= host side
 static bool g_tables_ready = false;
 static int ensure_tables(ccu_ctx *c)
@@ -1188,7 +1334,8 @@ int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
     if(!E.have_params || !L.have_xx) FAIL("thermal_buoyancy: energy parameters / coordinates missing");
-    LAUNCH(c, ek_buoyancy, cdiv(L.g.nno, 256), 256, L.g, Atemp, (const float *)c->T, (const float *)E.expansivity, c->buoy);
+    if(c->mk.ready) LAUNCH(c, ek_buoyancy_comp, cdiv(L.g.nno, 256), 256, L.g, Atemp, c->mk.Acomp, (const float *)c->T, (const float *)c->mk.C, (const float *)E.expansivity, c->buoy);
+    else LAUNCH(c, ek_buoyancy, cdiv(L.g.nno, 256), 256, L.g, Atemp, (const float *)c->T, (const float *)E.expansivity, c->buoy);
     LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->buoy, E.layer);
     if(c->multi())
     {   // return_horiz_ave sums over the ranks of one horizontal plane (same z position); here: slot me_z of a global table
@@ -1210,3 +1357,139 @@ int ccu_get_temperature(ccu_ctx *c, float *T, float *Tdot)
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
+
+// ================================================================= markers, host side
+int ccu_markers_setup(ccu_ctx *c, int capacity, int markers_per_ele, int rnoz, const double *XP1, const double *XP2, const double *XP3,
+                      const int *RG3, const double *XG1, const double *XG2, const unsigned *Element, float Acomp)
+{
+    if(!c) FAIL("null context");
+    if(c->multi()) FAIL("markers: marker exchange between subdomains is not implemented in this build");
+    if(ensure_energy(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &M = c->mk;
+    if(M.X) FAIL("markers: already set up");
+    if(capacity < 1) FAIL("markers: bad capacity");
+    const size_t cap = (size_t)capacity, nel = (size_t)L.g.nel, nno = (size_t)L.g.nno;
+    M.cap = capacity; M.markers_per_ele = markers_per_ele; M.rnoz = rnoz; M.Acomp = Acomp;
+    CK(cudaMalloc(&M.X, sizeof(double) * 3 * cap)); CK(cudaMalloc(&M.Xpred, sizeof(double) * 3 * cap));
+    CK(cudaMalloc(&M.VO, sizeof(float) * 3 * cap)); CK(cudaMalloc(&M.Vpred, sizeof(float) * 3 * cap));
+    CK(cudaMemsetAsync(M.Xpred, 0, sizeof(double) * 3 * cap, c->st)); CK(cudaMemsetAsync(M.VO, 0, sizeof(float) * 3 * cap, c->st));
+    CK(cudaMemsetAsync(M.Vpred, 0, sizeof(float) * 3 * cap, c->st));
+    CK(cudaMalloc(&M.C12, sizeof(int) * cap)); CK(cudaMalloc(&M.CElement, sizeof(int) * cap));
+    CK(cudaMalloc(&M.count, sizeof(int) * 2 * nel));
+    CK(cudaMalloc(&M.CE, sizeof(float) * nel)); CK(cudaMemsetAsync(M.CE, 0, sizeof(float) * nel, c->st));
+    CK(cudaMalloc(&M.C, sizeof(float) * nno)); CK(cudaMemsetAsync(M.C, 0, sizeof(float) * nno, c->st));
+    const int nx = L.g.nox, ny = L.g.noy, nz = L.g.noz;
+    CK(cudaMalloc(&M.XP, sizeof(double) * (nx + ny + nz)));
+    CK(cudaMemcpyAsync(M.XP, XP1, sizeof(double) * nx, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(M.XP + nx, XP2, sizeof(double) * ny, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(M.XP + nx + ny, XP3, sizeof(double) * nz, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMalloc(&M.RG3, sizeof(int) * (rnoz + 1)));
+    CK(cudaMemcpyAsync(M.RG3, RG3, sizeof(int) * (rnoz + 1), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMalloc(&M.Element, sizeof(unsigned) * nel));
+    CK(cudaMemcpyAsync(M.Element, Element, sizeof(unsigned) * nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMalloc(&M.err, sizeof(int))); CK(cudaMemsetAsync(M.err, 0, sizeof(int), c->st));
+    for(int d = 0; d < 3; d++) { M.XG1[d] = XG1[d]; M.XG2[d] = XG2[d]; }
+    // dx, dy, dzz exactly as get_element's statics (Composition_adv.c:1113-1116)
+    CK(cudaStreamSynchronize(c->st));
+    M.ready = true;
+    return 0;
+}
+static MkGrid mk_grid(ccu_ctx *c, const double *h_ends)
+{
+    Level &L = c->L[c->cfg.levmax];
+    auto &M = c->mk;
+    MkGrid m;
+    m.XP1 = M.XP; m.XP2 = M.XP + L.g.nox; m.XP3 = M.XP + L.g.nox + L.g.noy; m.RG3 = M.RG3; m.rnoz = M.rnoz;
+    m.dx = (h_ends[1] - h_ends[0]) / L.g.elx;
+    m.dy = (h_ends[3] - h_ends[2]) / L.g.ely;
+    m.dzz = (h_ends[5] - h_ends[4]) / (M.rnoz - 1);
+    return m;
+}
+static int mk_ends(ccu_ctx *c, double e[6])
+{
+    Level &L = c->L[c->cfg.levmax];
+    const int nx = L.g.nox, ny = L.g.noy, nz = L.g.noz;
+    const int idx[6] = { 0, nx - 1, nx, nx + ny - 1, nx + ny, nx + ny + nz - 1 };
+    for(int q = 0; q < 6; q++) CK(cudaMemcpyAsync(e + q, c->mk.XP + idx[q], sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_markers_upload(ccu_ctx *c, int n, const double *X1, const double *X2, const double *X3, const int *C12, const int *CElement, const float *CE)
+{
+    if(!c) FAIL("null context");
+    auto &M = c->mk;
+    if(!M.ready) FAIL("markers: ccu_markers_setup first");
+    if(n < 0 || n > M.cap) FAIL("markers: more markers than the capacity (markers_uplimit)");
+    const size_t cap = (size_t)M.cap;
+    M.n = n;
+    CK(cudaMemcpyAsync(M.X, X1, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(M.X + cap, X2, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(M.X + 2 * cap, X3, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(M.C12, C12, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(M.CElement, CElement, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
+    if(CE) CK(cudaMemcpyAsync(M.CE, CE, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nel, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_markers_download(ccu_ctx *c, double *X, double *Xpred, float *VO, float *Vpred, int *CElement, float *C, float *CE)
+{
+    if(!c) FAIL("null context");
+    auto &M = c->mk;
+    if(!M.ready) FAIL("markers: ccu_markers_setup first");
+    Level &L = c->L[c->cfg.levmax];
+    const size_t cap = (size_t)M.cap, n = (size_t)M.n;
+    for(int d = 0; d < 3; d++)
+    {
+        if(X) CK(cudaMemcpyAsync(X + d * n, M.X + d * cap, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+        if(Xpred) CK(cudaMemcpyAsync(Xpred + d * n, M.Xpred + d * cap, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+        if(VO) CK(cudaMemcpyAsync(VO + d * n, M.VO + d * cap, sizeof(float) * n, cudaMemcpyDeviceToHost, c->st));
+        if(Vpred) CK(cudaMemcpyAsync(Vpred + d * n, M.Vpred + d * cap, sizeof(float) * n, cudaMemcpyDeviceToHost, c->st));
+    }
+    if(CElement) CK(cudaMemcpyAsync(CElement, M.CElement, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st));
+    if(C) CK(cudaMemcpyAsync(C, M.C, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
+    if(CE) CK(cudaMemcpyAsync(CE, M.CE, sizeof(float) * (size_t)L.g.nel, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+// transfer_marker_properties (Composition_adv.c:682-704), one subdomain: clamp, element_markers, get_C_from_markers
+static int mk_transfer(ccu_ctx *c, const MkGrid &m, double *Xuse)
+{
+    Level &L = c->L[c->cfg.levmax];
+    auto &M = c->mk;
+    const int n = M.n;
+    LAUNCH(c, mk_clamp, cdiv(n, 256), 256, n, M.cap, (const unsigned *)M.Element, (const int *)M.CElement, M.XG1[0], M.XG1[1], M.XG1[2], M.XG2[0],
+           M.XG2[1], M.XG2[2], Xuse);
+    CK(cudaMemsetAsync(M.count, 0, sizeof(int) * 2 * (size_t)L.g.nel, c->st));
+    LAUNCH(c, mk_assign_count, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)Xuse, (const int *)M.C12, M.CElement, M.count, M.err);
+    LAUNCH(c, mk_element_C, cdiv(L.g.nel, 256), 256, L.g.nel, (const int *)M.count, M.CE);
+    LAUNCH(c, mk_nodal_C, cdiv(L.g.nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const float *)M.CE, M.C);
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, M.err, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if(err) FAIL("markers: " + std::to_string(err) + " marker(s) left the z lookup table (the reference terminates here: '!!!overflow', Composition_adv.c:1176)");
+    return 0;
+}
+static int mk_step(ccu_ctx *c, float timestep, int corrector)
+{
+    if(!c) FAIL("null context");
+    auto &M = c->mk;
+    if(!M.ready || M.n == 0) FAIL("markers: no markers resident");
+    if(!c->en.have_v) FAIL("markers: a velocity (ccu_v_from_vector / ccu_set_velocity) is needed first");
+    Level &L = c->L[c->cfg.levmax];
+    double ends[6];
+    if(mk_ends(c, ends)) return 1;
+    const MkGrid m = mk_grid(c, ends);
+    const int n = M.n;
+    if(!corrector)
+    {
+        LAUNCH(c, mk_velocity, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)M.X, (const float *)L.eco, (const float *)c->en.V, M.VO, M.CElement, M.err);
+        LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 0, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred);
+        return mk_transfer(c, m, M.Xpred);
+    }
+    LAUNCH(c, mk_velocity, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)M.Xpred, (const float *)L.eco, (const float *)c->en.V, M.Vpred, M.CElement, M.err);
+    LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 1, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred);
+    return mk_transfer(c, m, M.X);
+}
+int ccu_Euler(ccu_ctx *c, float timestep) { return mk_step(c, timestep, 0); }
+int ccu_Runge_Kutta(ccu_ctx *c, float timestep) { return mk_step(c, timestep, 1); }

@@ -70,7 +70,7 @@ struct ccu_ctx
     bool use_graphs = true;
     // kernel selection by level size (lanes per node), ccu_set_option
     int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
-    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
+    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials
@@ -100,6 +100,23 @@ struct ccu_ctx
         int temp_iterations = 2;
         bool have_params = false, have_v = false;
     } en;
+    // marker (tracer) state of the compositional field (ccu_build_exact.cu; Composition_adv.c), single subdomain
+    struct Markers
+    {
+        int n = 0, cap = 0, markers_per_ele = 0, rnoz = 0;
+        double *X = nullptr, *Xpred = nullptr;          // [3][cap] XMC, XMCpred
+        float *VO = nullptr, *Vpred = nullptr;           // [3][cap]
+        int *C12 = nullptr, *CElement = nullptr;         // [cap]
+        int *count = nullptr;                            // [2][nel] regular / dense markers per element
+        float *CE = nullptr, *C = nullptr;               // [nel], [nno]
+        double *XP = nullptr;                            // XP[1] | XP[2] | XP[3]: 1-D node coordinates (nox + noy + noz)
+        int *RG3 = nullptr;                              // [rnoz+1] z lookup table
+        unsigned *Element = nullptr;                     // [nel] element flags (SIDEE)
+        int *err = nullptr;                              // device error counter (markers that fell out of the z table)
+        double XG1[3] = { 0, 0, 0 }, XG2[3] = { 0, 0, 0 };
+        float Acomp = 0.0f;
+        bool ready = false;
+    } mk;
     long long launches = 0;
     CcuComm *comm = nullptr;       // null = single subdomain
     // Replicated coarse levels (multi-subdomain runs): levels <= agg_lev of the multigrid hierarchy live in `coarse`, a

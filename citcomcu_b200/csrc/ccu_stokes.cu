@@ -115,6 +115,8 @@ void ccu_destroy(ccu_ctx *c)
     }
     cudaFree(c->en.Tdot); cudaFree(c->en.DTdot); cudaFree(c->en.V); cudaFree(c->en.T1); cudaFree(c->en.Tdot1); cudaFree(c->en.diffusivity);
     cudaFree(c->en.expansivity); cudaFree(c->en.Eres); cudaFree(c->en.layer); cudaFree(c->en.red);
+    { auto &M = c->mk; cudaFree(M.X); cudaFree(M.Xpred); cudaFree(M.VO); cudaFree(M.Vpred); cudaFree(M.C12); cudaFree(M.CElement); cudaFree(M.count);
+      cudaFree(M.CE); cudaFree(M.C); cudaFree(M.XP); cudaFree(M.RG3); cudaFree(M.Element); cudaFree(M.err); }
     cudaFree(c->mat); cudaFree(c->T); cudaFree(c->buoy); cudaFree(c->nodal_tmp); cudaFree(c->nodal_tmp2); cudaFree(c->eltK);
     cudaFree(c->scal); cudaFree(c->partial); cudaFree(c->stage); cudaFree(c->uzAh); cudaFree(c->uzU1);
     drop_graphs(c);
@@ -145,6 +147,7 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_QUAD_NODES: c->opt_quad_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_LANES_LARGE: if(value != 1 && value != 4) FAIL("lanes must be 1 or 4"); c->opt_lanes_large = value; drop_graphs(c); return 0;
     case CCU_OPT_SMEM_NODES: c->opt_smem_nodes = value > 434 ? 434 : value; drop_graphs(c); return 0;
+    case CCU_OPT_CLUSTER_NODES: c->opt_cluster_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
     default: FAIL("set_option: unknown option");
@@ -446,6 +449,13 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
             return;
         }
         LAUNCH(c, ccu_k_relax_small, 1, 1024, L.g, L.K, L.BI, F, x, cycles, 0);
+        return;
+    }
+    if(!c->multi() && L.g.nno <= c->opt_cluster_nodes)
+    {   // small level: the whole call in one cluster launch (warp per node below ~4000 nodes, else four lanes per node)
+        const CcuStencil st = ccu_make_stencil(L.g);
+        if(L.g.nno <= 4000) LAUNCH(c, ccu_k_relax_cluster<32>, 8, 1024, L.g, st, L.K, L.BI, F, x, cycles, 0);
+        else LAUNCH(c, ccu_k_relax_cluster<4>, 8, 1024, L.g, st, L.K, L.BI, F, x, cycles, 0);
         return;
     }
     const unsigned grid = cdiv(L.g.NC, 128);

@@ -69,7 +69,7 @@ class StokesContext:
         check(self.lib.ccu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
     def set_option(self, name, value):
-        check(self.lib.ccu_set_option(self._ctx, dict(graphs=0, small_nodes=1, warp_nodes=2, quad_nodes=3, lanes_large=4, matvec_tab=5, relax_tab=6, smem_nodes=7)[name], int(value)))
+        check(self.lib.ccu_set_option(self._ctx, dict(graphs=0, small_nodes=1, warp_nodes=2, quad_nodes=3, lanes_large=4, matvec_tab=5, relax_tab=6, smem_nodes=7, cluster_nodes=8)[name], int(value)))
 
     def synchronize(self):
         check(self.lib.ccu_synchronize(self._ctx))
@@ -366,6 +366,43 @@ class StokesContext:
         Td = np.empty_like(T) if want_tdot else None
         check(self.lib.ccu_get_temperature(self._ctx, T.ctypes.data_as(C.c_void_p), None if Td is None else Td.ctypes.data_as(C.c_void_p)))
         return (T, Td) if want_tdot else T
+
+    # -- markers of the compositional field (Composition_adv.c)
+    def markers_setup(self, capacity, markers_per_ele, rnoz, XP1, XP2, XP3, RG3, XG1, XG2, Element, Acomp=0.0):
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        xs = [f64(XP1), f64(XP2), f64(XP3)]
+        rg = np.ascontiguousarray(RG3, dtype=np.int32)
+        g1, g2 = f64(XG1), f64(XG2)
+        el = np.ascontiguousarray(Element, dtype=np.uint32)
+        assert rg.size == rnoz + 1 and el.size == self.nel(self.levmax)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(self.lib.ccu_markers_setup(self._ctx, int(capacity), int(markers_per_ele), int(rnoz), p(xs[0]), p(xs[1]), p(xs[2]), p(rg),
+                                         p(g1), p(g2), p(el), C.c_float(Acomp)))
+
+    def markers_upload(self, XMC1, XMC2, XMC3, C12, CElement, CE=None):
+        xs = [np.ascontiguousarray(a, dtype=np.float64) for a in (XMC1, XMC2, XMC3)]
+        c12 = np.ascontiguousarray(C12, dtype=np.int32)
+        ce = np.ascontiguousarray(CElement, dtype=np.int32)
+        cef = None if CE is None else np.ascontiguousarray(CE, dtype=np.float32)
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        self._nmarkers = xs[0].size
+        check(self.lib.ccu_markers_upload(self._ctx, int(xs[0].size), p(xs[0]), p(xs[1]), p(xs[2]), p(c12), p(ce), p(cef)))
+
+    def markers_download(self):
+        """dict with XMC, XMCpred (float64 [3, n]), VO, Vpred (float32 [3, n]), CElement, C (nodal), CE (elemental)."""
+        n, lm = self._nmarkers, self.levmax
+        out = dict(XMC=np.empty((3, n)), XMCpred=np.empty((3, n)), VO=np.empty((3, n), np.float32), Vpred=np.empty((3, n), np.float32),
+                   CElement=np.empty(n, np.int32), C=np.empty(self.nno(lm), np.float32), CE=np.empty(self.nel(lm), np.float32))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(self.lib.ccu_markers_download(self._ctx, p(out["XMC"]), p(out["XMCpred"]), p(out["VO"]), p(out["Vpred"]), p(out["CElement"]),
+                                            p(out["C"]), p(out["CE"])))
+        return out
+
+    def Euler(self, timestep):
+        check(self.lib.ccu_Euler(self._ctx, C.c_float(timestep)))
+
+    def Runge_Kutta(self, timestep):
+        check(self.lib.ccu_Runge_Kutta(self._ctx, C.c_float(timestep)))
 
     # -- CUDA-event profile of the finest-level kernels
     PROF = dict(relax_fine=0, matvec_fine=1, build=2, coarse=3, transfer_fine=4)

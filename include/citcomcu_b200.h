@@ -51,6 +51,7 @@ int ccu_synchronize(ccu_ctx *ctx);
 /* MATVEC_TAB / RELAX_TAB: table-driven (compact code) row kernels on levels above QUAD_NODES */
 enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_OPT_QUAD_NODES = 3, CCU_OPT_LANES_LARGE = 4,
        CCU_OPT_MATVEC_TAB = 5, CCU_OPT_RELAX_TAB = 6,
+       CCU_OPT_CLUSTER_NODES = 8 /* single-subdomain levels with nno <= this run a whole smoother call in one 8-CTA cluster launch */,
        CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
@@ -190,6 +191,23 @@ int ccu_PG_timestep(ccu_ctx *ctx, float *T, float *Tdot, float *dt_out, float *T
  * (remove_horiz_ave / return_horiz_ave, Global_operations.c:55,133); updates the resident buoyancy; host copy optional */
 int ccu_thermal_buoyancy(ccu_ctx *ctx, float Atemp, float *buoyancy_out /*[nno] or NULL*/);
 int ccu_get_temperature(ccu_ctx *ctx, float *T /*[nno]*/, float *Tdot /*[nno] or NULL*/);
+
+/* ---- markers of the compositional field (Composition_adv.c), Cartesian, one subdomain ----
+ * E->advection.markers / markers_uplimit / markers_per_ele, E->lmesh.rnoz, E->XP[d]+1 (double[nox|noy|noz]), E->RG[3]
+ * (int[rnoz+1], Nodal_mesh.c:284 pre_interpolation), E->XG1[1..3], E->XG2[1..3], E->Element+1 (SIDEE = 0x800000),
+ * E->control.Acomp */
+int ccu_markers_setup(ccu_ctx *ctx, int capacity, int markers_per_ele, int rnoz, const double *XP1, const double *XP2,
+                      const double *XP3, const int *RG3, const double *XG1, const double *XG2, const unsigned *Element, float Acomp);
+/* E->XMC[d]+1, E->C12+1, E->CElement+1 (1-based element numbers as in the reference), E->CE+1 */
+int ccu_markers_upload(ccu_ctx *ctx, int n, const double *XMC1, const double *XMC2, const double *XMC3, const int *C12,
+                       const int *CElement, const float *CE);
+/* any pointer may be NULL; X / Xpred are double[3*n] (component-major), VO / Vpred float[3*n], C float[nno], CE float[nel] */
+int ccu_markers_download(ccu_ctx *ctx, double *X, double *Xpred, float *VO, float *Vpred, int *CElement, float *C, float *CE);
+/* Euler (Composition_adv.c:108): velocity_markers (:990, get_element :1086) at XMC, XMCpred = XMC + dt*VO,
+ * transfer_marker_properties (:682): boundary clamp, element_markers (:960), get_C_from_markers (:709, ratio method) */
+int ccu_Euler(ccu_ctx *ctx, float timestep);
+/* Runge_Kutta (Composition_adv.c:61): velocity at XMCpred, XMC += dt/2 (VO + Vpred), transfer_marker_properties */
+int ccu_Runge_Kutta(ccu_ctx *ctx, float timestep);
 
 /* ---- CUDA-event timing of the finest-level kernels inside a solve (bench.py's live roofline) ---- */
 /* classes: finest-level smoother (units = colour-pass launches), finest-level matvec / residual (units = products),

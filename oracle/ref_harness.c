@@ -105,7 +105,7 @@ static void dump_level_arrays(struct All_variables *E)
 
 static void dump_fields(struct All_variables *E, const char *tag)
 {
-    char nm[200];
+    char nm[200], nm_[200];
     const int nno = E->lmesh.nno, neq = E->lmesh.neq, npno = E->lmesh.npno, nel = E->lmesh.nel;
     int d;
     snprintf(nm, sizeof nm, "%s_mat", tag); DUMP_I32(nm, E->mat + 1, nel);
@@ -119,6 +119,22 @@ static void dump_fields(struct All_variables *E, const char *tag)
     for(d = 1; d <= 3; d++)
     {
         snprintf(nm, sizeof nm, "%s_V%d", tag, d); DUMP_F32(nm, E->V[d] + 1, nno);
+    }
+    if(E->control.composition && E->advection.markers > 0)
+    {   /* marker state (Composition_adv.c): positions, dense/regular flag, element assignment, nodal and elemental C */
+        const int nm = E->advection.markers;
+        int nmv = nm;
+        snprintf(nm_, sizeof nm_, "%s_nmarkers", tag); DUMP_I32(nm_, &nmv, 1);
+        for(d = 1; d <= 3; d++)
+        {
+            snprintf(nm_, sizeof nm_, "%s_XMC%d", tag, d); DUMP_F64(nm_, E->XMC[d] + 1, nm);
+            snprintf(nm_, sizeof nm_, "%s_XMCpred%d", tag, d); DUMP_F64(nm_, E->XMCpred[d] + 1, nm);
+            snprintf(nm_, sizeof nm_, "%s_VO%d", tag, d); DUMP_F32(nm_, E->VO[d] + 1, nm);
+        }
+        snprintf(nm_, sizeof nm_, "%s_C12", tag); DUMP_I32(nm_, E->C12 + 1, nm);
+        snprintf(nm_, sizeof nm_, "%s_CElement", tag); DUMP_I32(nm_, E->CElement + 1, nm);
+        snprintf(nm_, sizeof nm_, "%s_C", tag); DUMP_F32(nm_, E->C + 1, nno);
+        snprintf(nm_, sizeof nm_, "%s_CE", tag); DUMP_F32(nm_, E->CE + 1, nel);
     }
     {
         double sc[8] = { E->monitor.elapsed_time, E->advection.timestep, E->slice.Nut, E->slice.Nub,
@@ -369,6 +385,37 @@ int main(int argc, char **argv)
         one_timestep(&E);
         snprintf(tag, sizeof tag, "s%d", step);
         dump_fields(&E, tag);
+    }
+    if(E.control.composition && E.advection.markers > 0 && want_kat)
+    {   /* marker known answers on the final state: the lookup tables, then Euler and Runge_Kutta (Composition_adv.c:108,61)
+         * with the current velocity, exactly as PG_timestep_particle calls them (Advection_diffusion.c:229,162) */
+        const int nm = E.advection.markers, nno = E.lmesh.nno, nel = E.lmesh.nel;
+        int d, ip[4] = { E.lmesh.rnoz, E.advection.markers_per_ele, E.advection.markers, E.advection.markers_uplimit };
+        double dp[8] = { E.XG1[1], E.XG1[2], E.XG1[3], E.XG2[1], E.XG2[2], E.XG2[3], E.advection.timestep, E.control.Acomp };
+        char nm_[100];
+        DUMP_I32("mk_ints", ip, 4);
+        DUMP_F64("mk_doubles", dp, 8);
+        DUMP_F64("mk_XP1", E.XP[1] + 1, E.lmesh.nox); DUMP_F64("mk_XP2", E.XP[2] + 1, E.lmesh.noy); DUMP_F64("mk_XP3", E.XP[3] + 1, E.lmesh.noz);
+        DUMP_I32("mk_RG3", E.RG[3], E.lmesh.rnoz + 1);
+        DUMP_U32("mk_Element", E.Element + 1, nel);
+        for(d = 1; d <= 3; d++) { snprintf(nm_, sizeof nm_, "mk_in_XMC%d", d); DUMP_F64(nm_, E.XMC[d] + 1, nm); }
+        DUMP_I32("mk_in_C12", E.C12 + 1, nm); DUMP_I32("mk_in_CElement", E.CElement + 1, nm); DUMP_F32("mk_in_CE", E.CE + 1, nel);
+        for(d = 1; d <= 3; d++) { snprintf(nm_, sizeof nm_, "mk_in_V%d", d); DUMP_F32(nm_, E.V[d] + 1, nno); }
+        Euler(&E, E.C, E.V, 0);
+        for(d = 1; d <= 3; d++)
+        {
+            snprintf(nm_, sizeof nm_, "mk_euler_XMCpred%d", d); DUMP_F64(nm_, E.XMCpred[d] + 1, nm);
+            snprintf(nm_, sizeof nm_, "mk_euler_VO%d", d); DUMP_F32(nm_, E.VO[d] + 1, nm);
+        }
+        DUMP_I32("mk_euler_CElement", E.CElement + 1, nm); DUMP_F32("mk_euler_C", E.C + 1, nno); DUMP_F32("mk_euler_CE", E.CE + 1, nel);
+        Runge_Kutta(&E, E.C, E.V, 1);
+        for(d = 1; d <= 3; d++)
+        {
+            snprintf(nm_, sizeof nm_, "mk_rk_XMC%d", d); DUMP_F64(nm_, E.XMC[d] + 1, nm);
+            snprintf(nm_, sizeof nm_, "mk_rk_Vpred%d", d); DUMP_F32(nm_, E.Vpred[d] + 1, nm);
+        }
+        DUMP_I32("mk_rk_CElement", E.CElement + 1, nm); DUMP_F32("mk_rk_C", E.C + 1, nno); DUMP_F32("mk_rk_CE", E.CE + 1, nel);
+        dump_scalar_i("mk_rk_nmarkers", E.advection.markers);
     }
     fclose(g_manifest);
     fflush(NULL);

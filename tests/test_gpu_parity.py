@@ -150,11 +150,15 @@ def test_empty_rhs_is_a_noop(case):
     assert valid == 0 and cyc == 0 and not d0.any()
 
 
-@pytest.mark.parametrize("opts", [dict(small_nodes=0, warp_nodes=0, quad_nodes=0, lanes_large=1),     # one thread per node
-                                  dict(small_nodes=0, warp_nodes=0, quad_nodes=10**9),                  # four lanes per node
-                                  dict(small_nodes=0, warp_nodes=10**9),                                # a warp per node
-                                  dict(small_nodes=10**9),                                              # single-CTA fused sweeps
-                                  dict(graphs=0)])
+@pytest.mark.parametrize("opts", [
+    dict(small_nodes=0, warp_nodes=0, quad_nodes=0, cluster_nodes=0, lanes_large=1, relax_tab=0, matvec_tab=0),   # unrolled rows, one thread per node
+    dict(small_nodes=0, warp_nodes=0, quad_nodes=0, cluster_nodes=0),                                              # table-driven rows
+    dict(small_nodes=0, warp_nodes=0, quad_nodes=10**9, cluster_nodes=0, matvec_tab=0),                            # four lanes per node
+    dict(small_nodes=0, warp_nodes=10**9, cluster_nodes=0, matvec_tab=0),                                          # a warp per node
+    dict(small_nodes=0, cluster_nodes=10**9),                                                                      # one cluster launch per smoother call
+    dict(small_nodes=10**9, smem_nodes=0),                                                                         # single-CTA fused sweeps
+    dict(small_nodes=10**9),                                                                                       # shared-memory resident where it fits
+    dict(graphs=0)])
 def test_kernel_variants_agree(case, opts):
     """Every lanes-per-node variant of the smoother / matvec and the CUDA-graph replay give the same answers."""
     from citcomcu_b200.stokes import context_from_dump
