@@ -13,9 +13,10 @@ does identical work).  Synthetic data: the reference's analytic initial temperat
           library's stream, max over ranks)
   e2e     the same call through the C ABI with pinned HOST buffers: T and buoyancy go host->device,
           U and P come back device->host inside the timed region
-  roofline  finest-level 8-colour Gauss-Seidel relaxation kernel (ccu_k_relax): algorithmic bytes
+  roofline  finest-level 8-colour Gauss-Seidel relaxation kernel (ccu_k_relax_tab): algorithmic bytes
           648 B/node/sweep / 8 colour passes per launch, over its mean launch
-          duration measured live with CUDA events inside the timed region
+          duration measured live with CUDA events inside the timed region; `traffic` = DRAM bytes
+          per launch from the committed ncu --set full capture (profiles/traffic.json)
   cpu_baseline / --impl reference  the UNMODIFIED reference (oracle/_ref, built from
           /root/reference by oracle/Makefile over a process-based MPI shim) running the same step on
           the host cores on a bounded sample (a 1/64-size mesh of the same configuration), scaled
@@ -298,13 +299,14 @@ def run_ours(args):
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("ccu_k_relax", {}).get(args.mesh)
+            t = json.loads(tf.read_text()).get("ccu_k_relax_tab", {}).get(args.mesh) if world == 1 else None
+            traffic = None if t is None else t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
         except Exception:
             traffic = None
     line = {"metric": "stokes_solve_s_per_timestep", "value": s_per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh, nproc),
-            "roofline": {"bound": "hbm", "kernel": "ccu_k_relax<C> (finest-level 8-colour Gauss-Seidel pass)",
+            "roofline": {"bound": "hbm", "kernel": "ccu_k_relax_tab<2> (one colour pass of the finest-level 8-colour Gauss-Seidel smoother)",
                          "achieved": relax_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": relax_gbs / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": relax_bytes_per_launch,
                          "launches": relax_n, "avg_launch_ms": relax_ms / max(relax_n, 1),

@@ -16,6 +16,10 @@
 #pragma once
 #include <cstdint>
 
+#ifndef CCU_KD_ALIGN
+#define CCU_KD_ALIGN 1
+#endif
+
 struct CcuGeom
 {
     int nox, noy, noz;       // nodes in x, y, z
@@ -34,6 +38,7 @@ __host__ __device__ inline CcuGeom ccu_make_geom(int nox, int noy, int noz)
     g.elx = nox - 1; g.ely = noy - 1; g.elz = noz - 1;
     g.nno = nox * noy * noz; g.nel = g.elx * g.ely * g.elz; g.neq = 3 * g.nno; g.npno = g.nel;
     g.Kd = (noz + 1) / 2 + 2; g.Jd = (nox + 1) / 2 + 2; g.Id = (noy + 1) / 2 + 2;
+    if(g.Kd > 16) g.Kd = ((g.Kd + CCU_KD_ALIGN - 1) / CCU_KD_ALIGN) * CCU_KD_ALIGN;   // z rows start on a 32-byte sector (fp32) boundary
     g.JK = g.Jd * g.Kd;
     g.NC = g.Id * g.JK;
     g.NS = ((8 * g.NC + 63) / 64) * 64;

@@ -404,6 +404,35 @@ class StokesContext:
     def Runge_Kutta(self, timestep):
         check(self.lib.ccu_Runge_Kutta(self._ctx, C.c_float(timestep)))
 
+    # -- one pass of main()'s time loop (Citcom.c:111-161), everything resident on the device
+    def PG_timestep_particle(self, Atemp):
+        """PG_timestep_particle (Advection_diffusion.c:128): alternates, like the reference's static `on_off`, between
+        (0) std_timestep + thermal step + Euler marker predictor and (1) the Runge_Kutta marker corrector with the new
+        velocity; both end with thermal_buoyancy."""
+        on_off = getattr(self, "_on_off", 0)
+        if on_off == 0:
+            _, _, self._dt, _ = self.PG_timestep()
+            self.Euler(self._dt)
+        else:
+            self.Runge_Kutta(self._dt)
+        self.thermal_buoyancy(Atemp, want_host=False)
+        self._on_off = 1 - on_off
+        return self._dt
+
+    def advance(self, Atemp, *, composition=False, rebuild=1, **stokes_kw):
+        """One timestep as main() runs it: next_buoyancy_field (PG_timestep or PG_timestep_particle), general_stokes_solver
+        from the previous solution, v_from_vector, and with markers the second next_buoyancy_field call.  Returns dt."""
+        if composition:
+            dt = self.PG_timestep_particle(Atemp)
+        else:
+            _, _, dt, _ = self.PG_timestep()
+            self.thermal_buoyancy(Atemp, want_host=False)
+        _, _, its, _ = self.general_stokes_solver(None, None, rebuild=rebuild, guess=2, want_host=False, **stokes_kw)
+        self.v_from_vector(want_host=False)
+        if composition:
+            self.PG_timestep_particle(Atemp)
+        return dt, its
+
     # -- CUDA-event profile of the finest-level kernels
     PROF = dict(relax_fine=0, matvec_fine=1, build=2, coarse=3, transfer_fine=4)
 

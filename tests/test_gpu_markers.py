@@ -68,3 +68,34 @@ def test_counts_are_conserved(state):
     total = np.bincount(m["CElement"] - 1, minlength=nel).astype(np.float32)
     has = total > 0
     assert np.array_equal(m["CE"][has], dense[has] / total[has])
+
+
+def test_coupled_thermochemical_timesteps(state):
+    """main()'s loop with markers (PG_timestep_particle before and after the Stokes solve) for two steps from the
+    reference's step-0 state: temperature within 0.1 % (north star); markers within 1e-3 of an element size and >= 99 %
+    of them in the reference's element (the Stokes solutions agree to the solver tolerance, not bitwise)."""
+    d, prob, ctx, _ = state
+    ctl = prob.control
+    kw = dict(augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"])
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    Atemp = float(adv[5])
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_tdot(None)
+    ctx.markers_upload(d["s0_XMC1"], d["s0_XMC2"], d["s0_XMC3"], d["s0_C12"], d["s0_CElement"], d["s0_CE"])
+    ctx._on_off = 0
+    ctx.assemble_forces(d["s0_buoyancy"], want_host=False)
+    ctx.general_stokes_solver(None, None, rebuild=1, guess=0, want_host=False, **kw)
+    ctx.v_from_vector(want_host=False)
+    for step in (1, 2):
+        dt, its = ctx.advance(Atemp, composition=True, rebuild=1, **kw)
+        T = ctx.get_temperature()
+        ref = d[f"s{step}_T"]
+        assert abs(dt - d[f"s{step}_scalars"][1]) <= 2e-3 * d[f"s{step}_scalars"][1]
+        assert np.linalg.norm(T - ref) <= 1e-3 * np.linalg.norm(ref)
+        m = ctx.markers_download()
+        h = 2.0 / 16
+        for a in range(3):
+            assert np.abs(m["XMC"][a] - d[f"s{step}_XMC{a + 1}"]).max() <= 1e-3 * h
+        assert (m["CElement"] == d[f"s{step}_CElement"]).mean() >= 0.99
+        assert np.abs(m["C"] - d[f"s{step}_C"]).mean() <= 1e-3
