@@ -5,6 +5,7 @@
 // reference's control flow branches on.
 #include "ccu_ctx.cuh"
 #include "ccu_kernels.cuh"
+#include "ccu_tile.cuh"
 #include "ccu_comm.cuh"
 #include <algorithm>
 #include <cmath>
@@ -150,6 +151,11 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_CLUSTER_NODES: c->opt_cluster_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
+    case CCU_OPT_TILE_NODES: c->opt_tile_nodes = value; drop_graphs(c); return 0;
+    case CCU_OPT_RELAX_TILE: c->opt_relax_tile = value; drop_graphs(c); return 0;
+    case CCU_OPT_MATVEC_TILE: c->opt_matvec_tile = value; drop_graphs(c); return 0;
+    case CCU_OPT_TILE_HINT: c->opt_tile_hint = value; drop_graphs(c); return 0;
+    case CCU_OPT_TILE_SHAPE: if(value < 0 || value > 2) FAIL("tile shape must be 0, 1 or 2"); c->opt_tile_shape = value; drop_graphs(c); return 0;
     default: FAIL("set_option: unknown option");
     }
 }
@@ -315,6 +321,32 @@ static int read_scal(ccu_ctx *c, int first, int count, double *out)
 
 static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cdiv(L.g.NS, 256), 256, L.g, L.flags, v); }
 
+// ---- tile-resident kernels (ccu_tile.cuh)
+typedef CcuTileShape<2, 4, 16, 8> TileA;
+typedef CcuTileShape<2, 2, 24, 8> TileB;
+typedef CcuTileShape<2, 4, 16, 6> TileC;
+template <class S, int MODE>
+static void launch_tile(ccu_ctx *c, Level &L, int tcol, const double *F, double *x, double *out, const unsigned char *fl, int strip)
+{
+    static bool attr = false;
+    if(!attr) { cudaFuncSetAttribute(ccu_k_tile<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM); attr = true; }
+    const CcuGeom &g = L.g;
+    const int nti = (g.Id + S::TI - 1) / S::TI, ntj = (g.Jd + S::TJ - 1) / S::TJ, ntk = (g.Kd + S::TK - 1) / S::TK;
+    dim3 grid(ntk, ntj, nti);
+    if(MODE == 0) grid = dim3((ntk - (tcol & 1) + 1) / 2, (ntj - ((tcol >> 1) & 1) + 1) / 2, (nti - ((tcol >> 2) & 1) + 1) / 2);
+    if(!grid.x || !grid.y || !grid.z) return;
+    ccu_k_tile<S, MODE><<<grid, S::THREADS, S::SMEM, c->st>>>(g, ccu_make_tile_tab<S>(g), tcol, L.K, L.BI, F, x, out, fl, strip, c->opt_tile_hint);
+    c->launches++;
+}
+template <int MODE>
+static void launch_tile_shape(ccu_ctx *c, Level &L, int tcol, const double *F, double *x, double *out, const unsigned char *fl, int strip)
+{
+    if(c->opt_tile_shape == 1) launch_tile<TileB, MODE>(c, L, tcol, F, x, out, fl, strip);
+    else if(c->opt_tile_shape == 2) launch_tile<TileC, MODE>(c, L, tcol, F, x, out, fl, strip);
+    else launch_tile<TileA, MODE>(c, L, tcol, F, x, out, fl, strip);
+}
+static bool use_tile(const ccu_ctx *c, const Level &L, int on) { return on && L.g.nno > c->opt_tile_nodes; }
+
 // Lanes per node by level size: the smaller the level, the more the per-node chain of dependent loads is the
 // whole kernel time, so it is split over more lanes (ccu_kernels.cuh).  Tunable through ccu_set_option.
 static int lanes_for(const ccu_ctx *c, const Level &L)
@@ -329,7 +361,8 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);   // the table-driven kernel wins from ~1e4 nodes up
-    if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    if(use_tile(c, L, c->opt_matvec_tile)) launch_tile_shape<1>(c, L, 0, nullptr, const_cast<double *>(u), Au, L.flags, strip);
+    else if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab >= 4) LAUNCH(c, (ccu_k_matvec_tab<0, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab) LAUNCH(c, (ccu_k_matvec_tab<0, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
@@ -348,6 +381,7 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);
+    if(use_tile(c, L, c->opt_matvec_tile)) { launch_tile_shape<2>(c, L, 0, rhs, const_cast<double *>(u), out, L.flags, 1); return; }
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab >= 4) { LAUNCH(c, (ccu_k_matvec_tab<1, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
@@ -436,6 +470,16 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
 {
     CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], 8LL * cycles);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, cycles);
+    if(use_tile(c, L, c->opt_relax_tile))
+    {   // tile order: tile colours 7..0, the eight node colours inside each tile (ccu_tile.cuh)
+        const unsigned char *tbits = c->multi() ? c->comm->halo[&L - c->L].bits : nullptr;
+        for(int s = 0; s < cycles; s++)
+        {
+            if(tbits) relax_faces(c, L, x, F);
+            for(int tcol = 7; tcol >= 0; tcol--) launch_tile_shape<0>(c, L, tcol, F, x, nullptr, tbits, 0);
+        }
+        return;
+    }
     const int T = lanes_for(c, L);
     if(T == 0)
     {   // one CTA does every sweep and colour of a tiny level in a single launch

@@ -198,7 +198,22 @@ class Restate:
         (self.lib.ccu_r_mc_matvec if mc else self.lib.ccu_r_matvec)(self.L(lev), _p(u), _p(Au), C.c_int(strip))
         return Au[:self.neq(lev)]
 
-    def gauss_seidel(self, lev, F, cycles, guess, d0=None, mc=False):
+    def set_tile(self, ti, tj, tk):
+        """Tile shape (colour cells) of the tile-ordered smoother model (ccu_r_ordered_gs mode 9; smoother=19)."""
+        t = (C.c_int * 3).in_dll(self.lib, "g_ccu_r_tile")
+        t[0], t[1], t[2] = ti, tj, tk
+
+    def gauss_seidel(self, lev, F, cycles, guess, d0=None, mc=False, tile=None):
+        if tile is not None:
+            self.set_tile(*tile)
+            n = self.neq(lev)
+            d = np.zeros(n + 2)
+            if d0 is not None:
+                d[:n] = d0
+            Ad = np.zeros(n + 2)
+            F = np.ascontiguousarray(F, dtype=np.float64)
+            self.lib.ccu_r_ordered_gs(self.L(lev), _p(d), _p(F), _p(Ad), C.c_int(cycles), C.c_int(guess), C.c_int(9))
+            return d[:n], Ad[:n]
         n = self.neq(lev)
         d = np.zeros(n + 2)
         if d0 is not None:

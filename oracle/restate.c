@@ -529,6 +529,9 @@ float ccu_r_solve_Ahat_p_fhat(const ccu_r_mg *M, double *V, double *P, const dou
  *   mode 2 8-colour symmetric             mode 3 lexicographic symmetric
  *   mode 4 4-colour (x,y parity) lines, z ascending within a line, forward
  *   mode 5 as 4 but symmetric (z descending on backward sweeps)
+ *   mode 9 tile-ordered 8-colour: tiles of g_ccu_r_tile[] = TI x TJ x TK colour cells (cell = (index>>1)+1, the
+ *          device layout's halo offset), tile colours 7..0 outside, node colours 7..0 inside each tile -- the order
+ *          of ccu_k_relax_tile (csrc/ccu_tile.cuh); THIS mode is a checker for that kernel
  * ------------------------------------------------------------------------------------------ */
 static void full_row(const ccu_r_level *L, int n, const double *x, double out[3])
 {
@@ -536,9 +539,18 @@ static void full_row(const ccu_r_level *L, int n, const double *x, double out[3]
     tri_product(L, n, x, -1, lo); tri_product(L, n, x, +1, up); self_product(L, n, x, s);
     for(a = 0; a < 3; a++) out[a] = lo[a] + s[a] + up[a];
 }
+int g_ccu_r_tile[3] = { 2, 4, 16 };      /* TI (y), TJ (x), TK (z) colour cells per tile */
 static int ord_key(const ccu_r_level *L, int n, int mode, int back)
 {
     int i, j, k; nijk(L, n, &i, &j, &k);
+    if(mode == 9)
+    {
+        const int ti = ((i >> 1) + 1) / g_ccu_r_tile[0], tj = ((j >> 1) + 1) / g_ccu_r_tile[1], tk = ((k >> 1) + 1) / g_ccu_r_tile[2];
+        const int ntj = ((L->nox + 1) / 2 + 2) / g_ccu_r_tile[1] + 1, ntk = ((L->noz + 1) / 2 + 2) / g_ccu_r_tile[2] + 1;
+        const int tc = ((ti & 1) << 2) | ((tj & 1) << 1) | (tk & 1);
+        const int tile = tk + ntk * (tj + ntj * ti);
+        return ((7 - tc) * (1 << 20) + tile) * 8 + (7 - colour_of(i, j, k));
+    }
     if(mode == 0 || mode == 3) return back ? (L->nno - 1 - n) : n;
     if(mode == 1 || mode == 2) { int c = colour_of(i, j, k); return back ? 7 - c : c; }
     if(mode == 8) { int c = colour_of(i, j, k); return back ? c : 7 - c; }            /* sym starting 7..0 */
