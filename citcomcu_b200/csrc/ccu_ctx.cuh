@@ -26,6 +26,8 @@ struct Level
 {
     CcuGeom g;
     float *K = nullptr;
+    float *Kt = nullptr;          // tile-major copy of K for the tile kernels (ccu_tile.cuh); Kt_shape < 0: none
+    size_t Kt_elems = 0; int Kt_shape = -1;
     double *BI = nullptr;
     unsigned char *flags = nullptr;
     float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
@@ -72,7 +74,7 @@ struct ccu_ctx
     int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
     int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     // tile-resident smoother / matvec (ccu_tile.cuh) on levels above opt_tile_nodes nodes
-    int opt_tile_nodes = 500000, opt_relax_tile = 0, opt_matvec_tile = 0, opt_tile_hint = 1, opt_tile_shape = 0;
+    int opt_tile_nodes = 500000, opt_relax_tile = 0, opt_matvec_tile = 0, opt_tile_hint = 1, opt_tile_shape = 0, opt_tile_pad = 0;
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials
@@ -179,3 +181,4 @@ int ccu_damp_face_BI(ccu_ctx *c, int lev);
 int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_rank);
 int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of all subdomains -> coarse replica (ccu_stokes.cu)                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);
+int ccu_tile_refresh(ccu_ctx *c, int lev);                   // ccu_stokes.cu

@@ -17,7 +17,7 @@
 #include <cstdint>
 
 #ifndef CCU_KD_ALIGN
-#define CCU_KD_ALIGN 8     // z rows of a colour box start on a 32-byte sector (fp32) boundary: tile rows (ccu_tile.cuh) read whole sectors
+#define CCU_KD_ALIGN 1
 #endif
 
 struct CcuGeom

@@ -110,7 +110,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.Kt); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -137,6 +137,7 @@ int ccu_set_stream(ccu_ctx *c, void *s)
     if(c->coarse) { drop_graphs(c); c->coarse->st = c->st; }
     return 0;
 }
+static int tile_refresh_all(ccu_ctx *c);
 int ccu_set_option(ccu_ctx *c, int option, int value)
 {
     if(!c) FAIL("null context");
@@ -151,11 +152,12 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_CLUSTER_NODES: c->opt_cluster_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_NODES: c->opt_tile_nodes = value; drop_graphs(c); return 0;
-    case CCU_OPT_RELAX_TILE: c->opt_relax_tile = value; drop_graphs(c); return 0;
-    case CCU_OPT_MATVEC_TILE: c->opt_matvec_tile = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_HINT: c->opt_tile_hint = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_SHAPE: if(value < 0 || value > 2) FAIL("tile shape must be 0, 1 or 2"); c->opt_tile_shape = value; drop_graphs(c); return 0;
+    case CCU_OPT_TILE_NODES: c->opt_tile_nodes = value; drop_graphs(c); return tile_refresh_all(c);
+    case CCU_OPT_RELAX_TILE: c->opt_relax_tile = value; drop_graphs(c); return tile_refresh_all(c);
+    case CCU_OPT_MATVEC_TILE: c->opt_matvec_tile = value; drop_graphs(c); return tile_refresh_all(c);
+    case CCU_OPT_TILE_PAD: c->opt_tile_pad = value; if(c->coarse) c->coarse->opt_tile_pad = value; drop_graphs(c); return 0;
+    case CCU_OPT_TILE_HINT: c->opt_tile_hint = value; if(c->coarse) c->coarse->opt_tile_hint = value; drop_graphs(c); return 0;
+    case CCU_OPT_TILE_SHAPE: if(value < 0 || value > 3) FAIL("tile shape must be 0..3"); c->opt_tile_shape = value; drop_graphs(c); return tile_refresh_all(c);
     default: FAIL("set_option: unknown option");
     }
 }
@@ -241,7 +243,7 @@ int ccu_set_stiffness(ccu_ctx *c, int lev, const float *k1, const float *k2, con
     if(vec_h2d(c, L, BI, L.BI)) return 1;
     CK(cudaStreamSynchronize(c->st));
     L.have_K = true;
-    return 0;
+    return ccu_tile_refresh(c, lev);
 }
 
 int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double *BPI)
@@ -322,30 +324,81 @@ static int read_scal(ccu_ctx *c, int first, int count, double *out)
 static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cdiv(L.g.NS, 256), 256, L.g, L.flags, v); }
 
 // ---- tile-resident kernels (ccu_tile.cuh)
-typedef CcuTileShape<2, 4, 16, 8> TileA;
-typedef CcuTileShape<2, 2, 24, 8> TileB;
-typedef CcuTileShape<2, 4, 16, 6> TileC;
+typedef CcuTileShape<2, 4, 16, 8, 4> TileA4;
+typedef CcuTileShape<2, 4, 16, 8, 2> TileA2;
+typedef CcuTileShape<2, 2, 16, 8, 2> TileD2;
+typedef CcuTileShape<2, 2, 16, 16, 1> TileD1;     // 1024 threads, one CTA per SM: 148 tiles x 260 KB of stiffness in flight
 template <class S, int MODE>
 static void launch_tile(ccu_ctx *c, Level &L, int tcol, const double *F, double *x, double *out, const unsigned char *fl, int strip)
 {
     static bool attr = false;
-    if(!attr) { cudaFuncSetAttribute(ccu_k_tile<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM); attr = true; }
+    if(!attr)
+    {
+        cudaFuncSetAttribute(ccu_k_tile<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(ccu_k_tile<S, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr = true;
+    }
     const CcuGeom &g = L.g;
     const int nti = (g.Id + S::TI - 1) / S::TI, ntj = (g.Jd + S::TJ - 1) / S::TJ, ntk = (g.Kd + S::TK - 1) / S::TK;
     dim3 grid(ntk, ntj, nti);
     if(MODE == 0) grid = dim3((ntk - (tcol & 1) + 1) / 2, (ntj - ((tcol >> 1) & 1) + 1) / 2, (nti - ((tcol >> 2) & 1) + 1) / 2);
     if(!grid.x || !grid.y || !grid.z) return;
-    ccu_k_tile<S, MODE><<<grid, S::THREADS, S::SMEM, c->st>>>(g, ccu_make_tile_tab<S>(g), tcol, L.K, L.BI, F, x, out, fl, strip, c->opt_tile_hint);
+    ccu_k_tile<S, MODE><<<grid, S::THREADS, S::SMEM + (size_t)c->opt_tile_pad * 1024, c->st>>>(g, ccu_make_tile_tab<S>(g), tcol, L.Kt, L.BI, F, x, out, fl, strip, c->opt_tile_hint);
     c->launches++;
 }
 template <int MODE>
 static void launch_tile_shape(ccu_ctx *c, Level &L, int tcol, const double *F, double *x, double *out, const unsigned char *fl, int strip)
 {
-    if(c->opt_tile_shape == 1) launch_tile<TileB, MODE>(c, L, tcol, F, x, out, fl, strip);
-    else if(c->opt_tile_shape == 2) launch_tile<TileC, MODE>(c, L, tcol, F, x, out, fl, strip);
-    else launch_tile<TileA, MODE>(c, L, tcol, F, x, out, fl, strip);
+    if(L.Kt_shape == 1) launch_tile<TileA2, MODE>(c, L, tcol, F, x, out, fl, strip);
+    else if(L.Kt_shape == 2) launch_tile<TileD2, MODE>(c, L, tcol, F, x, out, fl, strip);
+    else if(L.Kt_shape == 3) launch_tile<TileD1, MODE>(c, L, tcol, F, x, out, fl, strip);
+    else launch_tile<TileA4, MODE>(c, L, tcol, F, x, out, fl, strip);
 }
-static bool use_tile(const ccu_ctx *c, const Level &L, int on) { return on && L.g.nno > c->opt_tile_nodes; }
+template <class S>
+static int tile_relayout(ccu_ctx *c, Level &L)
+{
+    const size_t need = ccu_tile_elems<S>(L.g);
+    if(need > L.Kt_elems)
+    {
+        if(L.Kt) cudaFree(L.Kt);
+        L.Kt = nullptr; L.Kt_elems = 0;
+        CK(cudaMalloc(&L.Kt, sizeof(float) * need));
+        L.Kt_elems = need;
+    }
+    const CcuGeom &g = L.g;
+    const int nti = (g.Id + S::TI - 1) / S::TI, ntj = (g.Jd + S::TJ - 1) / S::TJ, ntk = (g.Kd + S::TK - 1) / S::TK;
+    LAUNCH(c, ccu_k_tile_relayout<S>, (unsigned)(nti * ntj * ntk * 8), S::CT, g, ntj, ntk, L.K, L.Kt);
+    return 0;
+}
+// The tile kernels read a tile-major copy of the level's stiffness: (re)made whenever K of the level changes
+// (ccu_set_stiffness, ccu_construct_stiffness_B_matrix) or the tile options do.  Never called inside a graph capture.
+int ccu_tile_refresh(ccu_ctx *c, int lev)
+{
+    Level &L = c->L[lev];
+    L.Kt_shape = -1;
+    if(!(c->opt_relax_tile || c->opt_matvec_tile) || L.g.nno <= c->opt_tile_nodes || !L.have_K) return 0;
+    int rc;
+    if(c->opt_tile_shape == 1) rc = tile_relayout<TileA2>(c, L);
+    else if(c->opt_tile_shape == 2) rc = tile_relayout<TileD2>(c, L);
+    else if(c->opt_tile_shape == 3) rc = tile_relayout<TileD1>(c, L);
+    else rc = tile_relayout<TileA4>(c, L);
+    if(rc) return rc;
+    L.Kt_shape = c->opt_tile_shape;
+    return 0;
+}
+static int tile_refresh_all(ccu_ctx *c)
+{
+    for(int lev = c->cfg.levmin; lev <= c->cfg.levmax; lev++)
+        if(ccu_tile_refresh(c, lev)) return 1;
+    if(c->coarse)
+    {
+        c->coarse->opt_tile_nodes = c->opt_tile_nodes; c->coarse->opt_relax_tile = c->opt_relax_tile; c->coarse->opt_matvec_tile = c->opt_matvec_tile;
+        c->coarse->opt_tile_hint = c->opt_tile_hint; c->coarse->opt_tile_shape = c->opt_tile_shape;
+        return tile_refresh_all(c->coarse);
+    }
+    return 0;
+}
+static bool use_tile(const ccu_ctx *c, const Level &L, int on) { return on && L.Kt_shape >= 0; }
 
 // Lanes per node by level size: the smaller the level, the more the per-node chain of dependent loads is the
 // whole kernel time, so it is split over more lanes (ccu_kernels.cuh).  Tunable through ccu_set_option.

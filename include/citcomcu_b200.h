@@ -55,9 +55,11 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
        CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */,
        /* tile-resident kernels (csrc/ccu_tile.cuh) on levels with nno > TILE_NODES: RELAX_TILE / MATVEC_TILE switch them
         * on (1) or off (0); TILE_HINT 1 = L2 evict_last / evict_first hints on the stiffness loads; TILE_SHAPE 0 = tiles of
-        * 2x4x16 colour cells with rows split over 8 thread groups, 1 = 2x2x24 / 8 groups, 2 = 2x4x16 / 6 groups.  The tile smoother is a Gauss-Seidel sweep in tile order (tile colours 7..0,
+        * 2x4x16 colour cells with four z cells per thread, 1 = 2x4x16 / two cells, 2 = 2x2x16 / two cells,
+        * 3 = 2x2x16 / one cell with rows split over 16 groups (1024 threads, one CTA per SM).  The tile smoother is a Gauss-Seidel sweep in tile order (tile colours 7..0,
         * node colours 7..0 inside a tile) instead of plain colour order. */
-       CCU_OPT_TILE_NODES = 9, CCU_OPT_RELAX_TILE = 10, CCU_OPT_MATVEC_TILE = 11, CCU_OPT_TILE_HINT = 12, CCU_OPT_TILE_SHAPE = 13 };
+       CCU_OPT_TILE_NODES = 9, CCU_OPT_RELAX_TILE = 10, CCU_OPT_MATVEC_TILE = 11, CCU_OPT_TILE_HINT = 12, CCU_OPT_TILE_SHAPE = 13,
+       CCU_OPT_TILE_PAD = 14 /* extra KB of shared memory per tile CTA: lowers the CTAs per SM (L2 working-set experiments) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);

@@ -180,11 +180,11 @@ def test_kernel_variants_agree(case, opts):
     ctx.close()
 
 
-TILE_SHAPES = {0: (2, 4, 16), 1: (2, 2, 24), 2: (2, 4, 16)}
+TILE_SHAPES = {0: (2, 4, 16), 1: (2, 4, 16), 2: (2, 2, 16), 3: (2, 2, 16)}
 
 
 @pytest.mark.parametrize("name", ["busse_l3", "tdepv_l3", "tdepv_tall"])
-@pytest.mark.parametrize("shape", [0, 1, 2])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3])
 @pytest.mark.parametrize("hint", [0, 1])
 def test_tile_kernels_match_tile_order_model(name, shape, hint, oracle_built):
     """Tile-resident smoother / matvec (csrc/ccu_tile.cuh) forced onto every level: the matvec against the reference's
