@@ -89,6 +89,7 @@ struct ccu_ctx
     float *T = nullptr;            // [nno] temperature, natural order, finest level
     float *buoy = nullptr;         // [nno]
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
+    double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces)
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;
     // energy step state (ccu_build_exact.cu, PG_timestep): finest level, natural node order

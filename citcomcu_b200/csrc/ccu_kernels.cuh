@@ -864,39 +864,49 @@ __global__ void __launch_bounds__(128) ccu_k_project(const CcuGeom gc, const Ccu
                                                       const float *__restrict__ MASS, const double *__restrict__ fine, double *coarse,
                                                       const int apply_mass)
 {
-    constexpr int OFFS[9][3] = CCU_OFFS_INIT;
     constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };   // [dz][dx][dy] -> local node
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if(t >= 8 * gc.NC) return;
     const int c = t / gc.NC, cell = t - c * gc.NC;
     int I, J, Kz;
     if(!ccu_decode(gc, c, cell, I, J, Kz)) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for(int ey = I - 1; ey <= I; ey++)
-    {
-        if(ey < 0 || ey >= gc.ely) continue;
-        for(int ex = J - 1; ex <= J; ex++)
-        {
-            if(ex < 0 || ex >= gc.elx) continue;
-            for(int ez = Kz - 1; ez <= Kz; ez++)
-            {
-                if(ez < 0 || ez >= gc.elz) continue;
-                const int oy = I - ey, ox = J - ex, oz = Kz - ez;
-                const int a = LUT[oz][ox][oy];
-                const int el = ez + gc.elz * (ex + gc.elx * ey);
-                const int fy = 2 * ey + oy, fx = 2 * ex + ox, fz = 2 * ez + oz;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    // The eight sub-elements around fine node (2I, 2J, 2Kz) overlap: their 64 nodal values are 27 distinct fine nodes.
+    // W[ay][ax][az] = TWW of the coarse element in octant (ay, ax, az) (0 outside the mesh); fine node at offset
+    // (dy, dx, dz) collects the weights of every octant whose sub-element holds it, so each fine value is read once.
+    float W[2][2][2];
 #pragma unroll
-                for(int q = 1; q <= 8; q++)
-                {
-                    const int sf = ccu_sidx(gf, fy + OFFS[q][2], fx + OFFS[q][1], fz + OFFS[q][0]);
-                    a0 += fine[sf]; a1 += fine[(size_t)gf.NS + sf]; a2 += fine[2 * (size_t)gf.NS + sf];
-                }
-                const double w = (double)TWW[(size_t)el * 8 + a - 1];
-                s0 += w * a0; s1 += w * a1; s2 += w * a2;
+    for(int ay = 0; ay < 2; ay++)
+#pragma unroll
+        for(int ax = 0; ax < 2; ax++)
+#pragma unroll
+            for(int az = 0; az < 2; az++)
+            {
+                const int ey = I - 1 + ay, ex = J - 1 + ax, ez = Kz - 1 + az;
+                const bool in = ey >= 0 && ey < gc.ely && ex >= 0 && ex < gc.elx && ez >= 0 && ez < gc.elz;
+                W[ay][ax][az] = in ? TWW[(size_t)(ez + gc.elz * (ex + gc.elx * ey)) * 8 + LUT[1 - az][1 - ax][1 - ay] - 1] : 0.0f;
             }
-        }
-    }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for(int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for(int dx = -1; dx <= 1; dx++)
+#pragma unroll
+            for(int dz = -1; dz <= 1; dz++)
+            {
+                double w = 0.0;
+#pragma unroll
+                for(int ay = (dy > 0); ay <= (dy >= 0); ay++)
+#pragma unroll
+                    for(int ax = (dx > 0); ax <= (dx >= 0); ax++)
+#pragma unroll
+                        for(int az = (dz > 0); az <= (dz >= 0); az++) w += (double)W[ay][ax][az];
+                const int fy = 2 * I + dy, fx = 2 * J + dx, fz = 2 * Kz + dz;
+                if(w != 0.0 && fy >= 0 && fy < gf.noy && fx >= 0 && fx < gf.nox && fz >= 0 && fz < gf.noz)
+                {
+                    const int sf = ccu_sidx(gf, fy, fx, fz);
+                    s0 += w * fine[sf]; s1 += w * fine[(size_t)gf.NS + sf]; s2 += w * fine[2 * (size_t)gf.NS + sf];
+                }
+            }
     const double m = apply_mass ? (double)MASS[Kz + gc.noz * (J + gc.nox * I)] : 1.0;
     const int sc = c * gc.NC + cell;
     coarse[sc] = s0 * m; coarse[(size_t)gc.NS + sc] = s1 * m; coarse[2 * (size_t)gc.NS + sc] = s2 * m;
@@ -916,7 +926,8 @@ __global__ void __launch_bounds__(128) ccu_k_mass_mul(const CcuGeom g, const flo
 
 // interp_vector + un_inject_vector (Solver_multigrid.c:173-298, 581-634): the reference fills x,
 // then z, then y gaps in place; evaluated here per fine node as the same nested two-point
-// interpolations (fp32 weights from the element sizes the reference looks up, Appendix A #8).
+// interpolations (fp32 weights from the element sizes the reference looks up, Appendix A #8):
+// along x between the coarse nodes, then along z between those results, then along y.
 __device__ __forceinline__ int ccu_first_elt(const CcuGeom &g, int i, int j, int k)
 {
     return (k > 0 ? k - 1 : 0) + g.elz * ((j > 0 ? j - 1 : 0) + g.elx * (i > 0 ? i - 1 : 0));
@@ -926,21 +937,11 @@ __device__ __forceinline__ void ccu_w12(const float *__restrict__ eco, int e1, i
     const float x1 = eco[(size_t)e1 * 3 + dir], x2 = eco[(size_t)e2 * 3 + dir];
     w1 = x2 / (x1 + x2); w2 = x1 / (x1 + x2);
 }
-__device__ __forceinline__ double ccu_interp_x(const CcuGeom &gf, const CcuGeom &gc, const float *__restrict__ eco,
-                                               const double *__restrict__ cv, int i, int j, int k)   // i, k even
+// weights are evaluated once per node and applied to the three dofs (they are the same for each)
+struct CcuInterpW { float w1, w2; };
+__device__ __forceinline__ CcuInterpW ccu_wpair(const float *__restrict__ eco, int e1, int e2, int dir)
 {
-    if(!(j & 1)) return cv[ccu_sidx(gc, i >> 1, j >> 1, k >> 1)];
-    float w1, w2;
-    ccu_w12(eco, ccu_first_elt(gf, i, j - 1, k), ccu_first_elt(gf, i, j + 1, k), 0, w1, w2);
-    return (double)w1 * cv[ccu_sidx(gc, i >> 1, (j - 1) >> 1, k >> 1)] + (double)w2 * cv[ccu_sidx(gc, i >> 1, (j + 1) >> 1, k >> 1)];
-}
-__device__ __forceinline__ double ccu_interp_z(const CcuGeom &gf, const CcuGeom &gc, const float *__restrict__ eco,
-                                               const double *__restrict__ cv, int i, int j, int k)   // i even
-{
-    if(!(k & 1)) return ccu_interp_x(gf, gc, eco, cv, i, j, k);
-    float w1, w2;
-    ccu_w12(eco, ccu_first_elt(gf, i, j, k - 1), ccu_first_elt(gf, i, j, k + 1), 2, w1, w2);
-    return (double)w1 * ccu_interp_x(gf, gc, eco, cv, i, j, k - 1) + (double)w2 * ccu_interp_x(gf, gc, eco, cv, i, j, k + 1);
+    CcuInterpW w; ccu_w12(eco, e1, e2, dir, w.w1, w.w2); return w;
 }
 __global__ void __launch_bounds__(128) ccu_k_interp(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ eco_f,
                                                      const unsigned char *__restrict__ flags_f, const double *__restrict__ coarse,
@@ -953,17 +954,54 @@ __global__ void __launch_bounds__(128) ccu_k_interp(const CcuGeom gc, const CcuG
     if(!ccu_decode(gf, c, cell, i, j, k)) return;
     const int s = c * gf.NC + cell;
     const unsigned char f = strip ? flags_f[s] : 0;
+    const bool oi = i & 1, oj = j & 1, ok = k & 1;
+    // rows i0 (and i1 when i is odd), columns k0 (k1), x positions j0 (j1): up to eight coarse nodes
+    const int i0 = oi ? i - 1 : i, i1 = i + 1, k0 = ok ? k - 1 : k, k1 = k + 1, j0 = oj ? j - 1 : j, j1 = j + 1;
+    CcuInterpW wy = { 1.0f, 0.0f }, wz[2] = { { 1.0f, 0.0f }, { 1.0f, 0.0f } }, wx[2][2] = { { { 1.0f, 0.0f }, { 1.0f, 0.0f } }, { { 1.0f, 0.0f }, { 1.0f, 0.0f } } };
+    if(oi) wy = ccu_wpair(eco_f, ccu_first_elt(gf, i - 1, j, k), ccu_first_elt(gf, i + 1, j, k), 1);
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+    {
+        if(a && !oi) break;
+        const int ii = a ? i1 : i0;
+        if(ok) wz[a] = ccu_wpair(eco_f, ccu_first_elt(gf, ii, j, k - 1), ccu_first_elt(gf, ii, j, k + 1), 2);
+#pragma unroll
+        for(int b = 0; b < 2; b++)
+        {
+            if(b && !ok) break;
+            const int kk = b ? k1 : k0;
+            if(oj) wx[a][b] = ccu_wpair(eco_f, ccu_first_elt(gf, ii, j - 1, kk), ccu_first_elt(gf, ii, j + 1, kk), 0);
+        }
+    }
+    // coarse storage slots of the (up to) eight corners
+    int sc[2][2][2];
+#pragma unroll
+    for(int a = 0; a < 2; a++)
+#pragma unroll
+        for(int b = 0; b < 2; b++)
+#pragma unroll
+            for(int e = 0; e < 2; e++)
+                sc[a][b][e] = ccu_sidx(gc, (a && oi ? i1 : i0) >> 1, (e && oj ? j1 : j0) >> 1, (b && ok ? k1 : k0) >> 1);
+#pragma unroll
     for(int d = 0; d < 3; d++)
     {
         const double *cv = coarse + (size_t)d * gc.NS;
-        double v;
-        if(!(i & 1)) v = ccu_interp_z(gf, gc, eco_f, cv, i, j, k);
-        else
+        double vy[2];
+#pragma unroll
+        for(int a = 0; a < 2; a++)
         {
-            float w1, w2;
-            ccu_w12(eco_f, ccu_first_elt(gf, i - 1, j, k), ccu_first_elt(gf, i + 1, j, k), 1, w1, w2);
-            v = (double)w1 * ccu_interp_z(gf, gc, eco_f, cv, i - 1, j, k) + (double)w2 * ccu_interp_z(gf, gc, eco_f, cv, i + 1, j, k);
+            if(a && !oi) { vy[a] = 0.0; break; }
+            double vz[2];
+#pragma unroll
+            for(int b = 0; b < 2; b++)
+            {
+                if(b && !ok) { vz[b] = 0.0; break; }
+                // interp along x (Solver_multigrid.c:195-226): even j copies the coarse value
+                vz[b] = oj ? (double)wx[a][b].w1 * cv[sc[a][b][0]] + (double)wx[a][b].w2 * cv[sc[a][b][1]] : cv[sc[a][b][0]];
+            }
+            vy[a] = ok ? (double)wz[a].w1 * vz[0] + (double)wz[a].w2 * vz[1] : vz[0];
         }
+        double v = oi ? (double)wy.w1 * vy[0] + (double)wy.w2 * vy[1] : vy[0];
         if(f & (d == 0 ? CCU_F_VBX : (d == 1 ? CCU_F_VBY : CCU_F_VBZ))) v = 0.0;
         fine[(size_t)d * gf.NS + s] = v;
     }

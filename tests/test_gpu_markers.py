@@ -19,7 +19,8 @@ def state():
         pytest.skip("needs the prebuilt reference (oracle/_ref)")
     from citcomcu_b200.problem import CartesianProblem
     from citcomcu_b200.stokes import context_from_problem
-    text = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, composition=1, rayleigh_comp=5e6, markers_per_ele=8, comp_depth=0.4)
+    text = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, composition=1, rayleigh_comp=5e6, markers_per_ele=8, comp_depth=0.4,
+                               accuracy=1e-6)   # both Stokes solves converged well below the position tolerance of the coupled test
     dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_markers_")), nsteps=2, kat=True)
     d = dumps[0]
     prob = CartesianProblem(text)
