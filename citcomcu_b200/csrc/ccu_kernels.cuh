@@ -381,19 +381,29 @@ __global__ void __launch_bounds__(1024) ccu_k_relax_smem(const CcuGeom g, const 
     if(t < 3) xs[t * n1 + n] = 0.0;
     __syncthreads();
     // A phase = one colour.  8 lanes per node (lane q takes stencil blocks q, q+8, q+16, q+24) and 128 node groups per
-    // CTA keep all ~50-75 nodes of a phase in flight at once.  Nothing in a phase's dependent chain leaves shared
-    // memory: neighbours are found through the natural-index table (the L1 left beside a 227 KB carve-out is too small
-    // to serve table lookups from global memory); F and BI of the three updating lanes are requested up front.
+    // CTA keep all ~50-75 nodes of a phase in flight at once.  Nothing in a phase's dependent chain leaves the SM:
+    // neighbours are found through the natural-index table in shared memory, and the right-hand side and inverse
+    // diagonal of the eight nodes a group relaxes (one per colour) sit in the registers of its three updating lanes --
+    // loaded once per call, not once per phase (a phase is ~1000 cycles; an L2 round trip per phase doubled it).
     const int q = t & 7, grp = t >> 3;
+    double fr[8], br[8];
+#pragma unroll
+    for(int c = 0; c < 8; c++)
+    {
+        const int tt = sl.cstart[c] + grp;
+        fr[c] = 0.0; br[c] = 0.0;
+        if(q < 3 && tt < sl.cstart[c + 1]) { const int sn = sl.s[tt]; fr[c] = F[q * NS + sn]; br[c] = BI[q * NS + sn]; }
+    }
     for(int sw = 0; sw < cycles; sw++)
+#pragma unroll
         for(int c = 7; c >= 0; c--)
         {
             const int tt = sl.cstart[c] + grp;
             const bool act = tt < sl.cstart[c + 1];
-            double fq = 0.0, bq = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            const double fq = fr[c], bq = br[c];
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
             if(act)
             {
-                if(q < 3) { const int sn = sl.s[tt]; fq = F[q * NS + sn]; bq = BI[q * NS + sn]; }
                 const unsigned p = pk[tt];
                 const int i = p & 255, j = (p >> 8) & 255, k = (p >> 16) & 255;
 #pragma unroll

@@ -834,6 +834,52 @@ static int d_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, i
     return 0;
 }
 
+// conj_grad (General_matrix_functions.c:661-770): Jacobi-preconditioned CG on K at level `lev` (the reference's
+// Solver=cgrad path).  The loop condition and alpha's zero test branch on global reductions, so the scalars come back
+// to the host each iteration exactly where the reference's control flow needs them.  Work vectors: the level's
+// multigrid slots (d0 = VEL, r = RES, z = FL, p = DEL_VEL, Ap = AU; the reference's r0/r2, z0, p1 shuffles are in place).
+static int d_conj_grad(ccu_ctx *c, int lev, const double *F, double acc, int *cycles, double *residual_out)
+{
+    if(c->multi()) FAIL("conj_grad: single-subdomain contexts only");
+    Level &L = c->L[lev];
+    const size_t nv = L.vlen();
+    double *d0 = L.vec[CCU_VEC_VEL], *r = L.vec[CCU_VEC_RES], *z = L.vec[CCU_VEC_FL], *p = L.vec[CCU_VEC_DEL_VEL], *Ap = L.vec[CCU_VEC_AU];
+    const double neq = (double)L.g.neq;
+    const int steps = *cycles;
+    double h[2], r1z1, r0z0 = 0.0;
+    d_copy(c, r, F, nv);
+    d_zero(c, d0, nv);
+    d_dot3m(c, &L, nv, r, r, S_DOT0);
+    if(read_scal(c, S_DOT0, 1, h)) return 1;
+    double residual = sqrt(h[0] / neq);
+    if(residual == 0.0) FAIL("conj_grad: initial residual is zero");        // the reference asserts (:707)
+    int count = 0;
+    while((residual > acc && count < steps) || count == 0)
+    {
+        LAUNCH(c, ccu_k_mul, min(cdiv(nv, 256), 148u * 16u), 256, nv, z, L.BI, r);
+        d_dot3m(c, &L, nv, r, z, S_DOT0);
+        if(read_scal(c, S_DOT0, 1, h)) return 1;
+        r1z1 = h[0];
+        if(count == 0) d_copy(c, p, z, nv);
+        else d_axpby(c, nv, p, z, C_ONE, coef(nullptr, nullptr, r1z1 / r0z0));     // p = z + beta p
+        r0z0 = r1z1;
+        d_matvec(c, L, p, Ap, 1);
+        d_dot3m(c, &L, nv, p, Ap, S_DOT0);
+        if(read_scal(c, S_DOT0, 1, h)) return 1;
+        const double alpha = (h[0] == 0.0) ? 1.0e-3 : r1z1 / h[0];
+        d_axpby(c, nv, d0, p, coef(nullptr, nullptr, alpha), C_ONE);
+        d_axpby(c, nv, r, Ap, coef(nullptr, nullptr, -alpha), C_ONE);
+        d_dot3m(c, &L, nv, r, r, S_DOT0);
+        if(read_scal(c, S_DOT0, 1, h)) return 1;
+        residual = sqrt(h[0] / neq);
+        count++;
+    }
+    *cycles = count;
+    d_strip(c, L, d0);
+    if(residual_out) *residual_out = residual;
+    return 0;
+}
+
 static void d_div_u(ccu_ctx *c, Level &L, const double *U, double *divU)
 {
     LAUNCH(c, ccu_k_div_u, cdiv(L.g.nel, 128), 128, L.g, L.elt_del, U, divU);
@@ -1160,6 +1206,19 @@ int ccu_multi_grid(ccu_ctx *c, double *d1, double *F, double *residual_out)
     if(ccu_dev_multi_grid(c, CCU_VEC_T1, CCU_VEC_T0, residual_out)) return 1;
     if(vec_d2h(c, L, L.vec[CCU_VEC_T0], F)) return 1;
     return vec_d2h(c, L, L.vec[CCU_VEC_T1], d1);
+}
+int ccu_conj_grad(ccu_ctx *c, int lev, double *d0, const double *F, double acc, int *cycles, double *residual_out)
+{
+    if(ccu_check_lev(c, lev)) return 2;
+    if(!cycles) FAIL("conj_grad: cycles is null");
+    Level &L = c->L[lev];
+    if(vec_h2d(c, L, F, L.vec[CCU_VEC_RHS])) return 1;
+    if(d_conj_grad(c, lev, L.vec[CCU_VEC_RHS], acc, cycles, residual_out)) return 1;
+    return vec_d2h(c, L, L.vec[CCU_VEC_VEL], d0);
+}
+int ccu_e_assemble_del2_u(ccu_ctx *c, int lev, const double *u, double *Au, int strip_bcs)
+{   // the element-by-element product equals the node-stored one (assemble_del2_u dispatch, Element_calculations.c:480-488)
+    return ccu_n_assemble_del2_u(c, lev, u, Au, strip_bcs);
 }
 int ccu_solve_del2_u(ccu_ctx *c, double *d0, const double *F, double acc, int *valid_out, int *cycles_out)
 {

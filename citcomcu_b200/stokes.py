@@ -214,6 +214,23 @@ class StokesContext:
 
     assemble_del2_u = n_assemble_del2_u
 
+    def e_assemble_del2_u(self, u, level, strip_bcs=1):
+        u, up = _f64(u)
+        Au = np.empty(self.neq(level))
+        check(self.lib.ccu_e_assemble_del2_u(self._ctx, level, up, Au.ctypes.data_as(C.c_void_p), int(strip_bcs)))
+        return Au
+
+    def conj_grad(self, F, acc, cycles, level):
+        """conj_grad (General_matrix_functions.c:661): returns (d0, residual, cycles done)."""
+        n = self.neq(level)
+        d = np.zeros(n)
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        cyc = C.c_int(int(cycles))
+        res = C.c_double(0.0)
+        check(self.lib.ccu_conj_grad(self._ctx, int(level), d.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p),
+                                     C.c_double(acc), C.byref(cyc), C.byref(res)))
+        return d, res.value, cyc.value
+
     def gauss_seidel(self, F, cycles, level, guess, d0=None):
         n = self.neq(level)
         d = np.zeros(n) if d0 is None else np.array(d0, dtype=np.float64)

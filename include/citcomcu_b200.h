@@ -127,6 +127,12 @@ int ccu_get_level_array(ccu_ctx *ctx, int lev, int which, void *out);
 /* ---- hot-path operators, host vectors in / out (drop-in granularity of SURVEY.md 8b) ---- */
 /* n_assemble_del2_u / assemble_del2_u (Element_calculations.c:552, :480) */
 int ccu_n_assemble_del2_u(ccu_ctx *ctx, int lev, const double *u, double *Au, int strip_bcs);
+/* e_assemble_del2_u (Element_calculations.c:494): the element-by-element form of the same product (Solver=multigrid-el or
+ * cgrad without node_assemble); evaluated from the node-stored matrix, which holds the same assembled coefficients */
+int ccu_e_assemble_del2_u(ccu_ctx *ctx, int lev, const double *u, double *Au, int strip_bcs);
+/* conj_grad (General_matrix_functions.c:661): Jacobi-preconditioned CG on K at level lev (Solver=cgrad); d0 out (zero
+ * start), *cycles in = max iterations / out = iterations done, residual_out = sqrt(r.r/neq) as the reference returns */
+int ccu_conj_grad(ccu_ctx *ctx, int lev, double *d0, const double *F, double acc, int *cycles, double *residual_out);
 /* gauss_seidel (General_matrix_functions.c:1160): `cycles` 8-colour sweeps; d0 in/out (in only if guess), Ad = K*d0 out */
 int ccu_gauss_seidel(ccu_ctx *ctx, int lev, double *d0, const double *F, double *Ad, int cycles, int guess);
 /* project_vector (Solver_multigrid.c:72): fine level `lev` -> lev-1 */

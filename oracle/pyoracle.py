@@ -253,6 +253,15 @@ class Restate:
         b = np.ascontiguousarray(b, dtype=np.float64)
         return self.lib.ccu_r_vdot(self.L(lev), _p(a), _p(b))
 
+    def conj_grad(self, lev, F, acc, cycles):
+        n = self.neq(lev)
+        d0 = np.zeros(n + 2)
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        cyc = C.c_int(cycles)
+        self.lib.ccu_r_conj_grad.restype = C.c_double
+        res = self.lib.ccu_r_conj_grad(self.L(lev), _p(d0), _p(F), C.c_double(acc), C.byref(cyc))
+        return d0[:n], res, cyc.value
+
     def multi_grid(self, F):
         n = self.neq(self.mg.levmax)
         d1 = np.zeros(n + 2)

@@ -229,6 +229,15 @@ static void dump_kats(struct All_variables *E)
         E->control.accuracy = acc_save;
         DUMP_F64("kat_solve_d0", d0, neq);
         dump_scalar_i("kat_solve_valid", valid);
+        {   /* conj_grad (General_matrix_functions.c:661): 25 iterations of the Jacobi-preconditioned CG on the same rhs */
+            int cyc = 25;
+            double r;
+            for(i = 0; i < neq; i++) { w[i] = f[i]; d0[i] = 0.0; }
+            r = conj_grad(E, d0, w, Au, 1e-30, &cyc, levmax);
+            DUMP_F64("kat_cg_d0", d0, neq);
+            dump_scalar_d("kat_cg_residual", r);
+            dump_scalar_i("kat_cg_cycles", cyc);
+        }
     }
     free(u); free(Au); free(f); free(d0); free(w); free(p); free(q);
     {   /* energy step known answers on the state after the step-0 Stokes solve: std_timestep (Advection_diffusion.c:737)

@@ -522,6 +522,39 @@ float ccu_r_solve_Ahat_p_fhat(const ccu_r_mg *M, double *V, double *P, const dou
     return (float)residual;
 }
 
+/* General_matrix_functions.c:661-770: Jacobi-preconditioned conjugate gradients on K (Solver=cgrad).
+ * d0 out (zeroed first), returns the residual norm sqrt(r.r/neq); *cycles in = max iterations, out = done. */
+double ccu_r_conj_grad(const ccu_r_level *L, double *d0, const double *F, double acc, int *cycles)
+{
+    const int n = L->neq, steps = *cycles;
+    double *r1 = calloc(n + 2, 8), *r2 = calloc(n + 2, 8), *z1 = calloc(n + 2, 8), *p1 = calloc(n + 2, 8), *p2 = calloc(n + 2, 8),
+           *Ap = calloc(n + 2, 8), *sh;
+    double residual, alpha, beta, dotprod, dotr1z1, dotr0z0 = 0.0;
+    int i, count = 0;
+    for(i = 0; i < n; i++) { r1[i] = F[i]; d0[i] = 0.0; }
+    residual = sqrt(ccu_r_vdot(L, r1, r1) / n);
+    while(((residual > acc) && (count < steps)) || count == 0)
+    {
+        for(i = 0; i < n; i++) z1[i] = L->BI[i] * r1[i];
+        dotr1z1 = ccu_r_vdot(L, r1, z1);
+        if(count == 0) for(i = 0; i < n; i++) p2[i] = z1[i];
+        else { beta = dotr1z1 / dotr0z0; for(i = 0; i < n; i++) p2[i] = z1[i] + beta * p1[i]; }
+        dotr0z0 = dotr1z1;
+        ccu_r_matvec(L, p2, Ap, 1);
+        dotprod = ccu_r_vdot(L, p2, Ap);
+        alpha = (dotprod == 0.0) ? 1.0e-3 : dotr1z1 / dotprod;
+        for(i = 0; i < n; i++) { d0[i] += alpha * p2[i]; r2[i] = r1[i] - alpha * Ap[i]; }
+        residual = sqrt(ccu_r_vdot(L, r2, r2) / n);
+        sh = r1; r1 = r2; r2 = sh;
+        sh = p1; p1 = p2; p2 = sh;
+        count++;
+    }
+    *cycles = count;
+    ccu_r_strip_bcs(L, d0);
+    free(r1); free(r2); free(z1); free(p1); free(p2); free(Ap);
+    return residual;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Experimental orderings (design studies only; not a checker): point-block GS with the
  * reference's scalar-BI update, nodes visited in a chosen order, residual from full rows.

@@ -53,6 +53,7 @@ void ccu_r_div_u(const ccu_r_level *L, const double *U, double *divU);
 void ccu_r_grad_p(const ccu_r_level *L, const double *P, double *gradP);
 double ccu_r_vdot(const ccu_r_level *L, const double *a, const double *b);
 double ccu_r_pdot(const ccu_r_level *L, const double *a, const double *b);
+double ccu_r_conj_grad(const ccu_r_level *L, double *d0, const double *F, double acc, int *cycles);
 double ccu_r_multi_grid(const ccu_r_mg *M, double *d1, double *F, double acc);
 int ccu_r_solve_del2_u(const ccu_r_mg *M, double *d0, const double *F, double acc, int *mg_cycles_out);
 float ccu_r_solve_Ahat_p_fhat(const ccu_r_mg *M, double *V, double *P, const double *F, double imp,

@@ -142,6 +142,21 @@ def test_stokes_solve_default_tolerance_iterations(case):
     assert rel2(V, d["s0_U"]) < 20 * acc and rel2(P, d["s0_P"]) < 20 * acc
 
 
+def test_conj_grad_matches_reference(case):
+    """conj_grad (Solver=cgrad path): 25 iterations against the reference's own function on the same rhs; summation
+    order differs (coloured storage, tree reductions), so 1e-8 after 25 iterations; e_assemble_del2_u = the same product."""
+    d, ctx = case
+    if "kat_cg_d0" not in d:
+        pytest.skip("fixture predates the conj_grad known answer")
+    lm = d.levmax
+    d0, res, cyc = ctx.conj_grad(d["kat_solve_f"], 1e-30, 25, lm)
+    assert cyc == int(d["kat_cg_cycles"][0])
+    assert abs(res - d["kat_cg_residual"][0]) <= 1e-8 * d["kat_cg_residual"][0]
+    assert rel(d0, d["kat_cg_d0"]) < 1e-8
+    u = d[f"kat_L{lm}_u"]
+    assert rel(ctx.e_assemble_del2_u(u, lm, 1), d[f"kat_L{lm}_Au"]) < 1e-12
+
+
 def test_empty_rhs_is_a_noop(case):
     """Edge case the reference handles via `valid` (Appendix A #2): zero residual -> valid=0, d0=0."""
     d, ctx = case

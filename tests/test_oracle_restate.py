@@ -46,6 +46,17 @@ def test_restated_multigrid_and_solve_bit_exact(case):
     assert np.array_equal(d0, d["kat_solve_d0"]) and valid == int(d["kat_solve_valid"][0])
 
 
+def test_restated_conj_grad_bit_exact(case):
+    """conj_grad (General_matrix_functions.c:661) restated: 25 iterations on the seeded rhs, bit for bit."""
+    d = case
+    if "kat_cg_d0" not in d:
+        pytest.skip("fixture predates the conj_grad known answer")
+    R = po.Restate(d, smoother=0)
+    d0, res, cyc = R.conj_grad(d.levmax, d["kat_solve_f"], 1e-30, 25)
+    assert cyc == int(d["kat_cg_cycles"][0]) and res == d["kat_cg_residual"][0]
+    assert np.array_equal(d0, d["kat_cg_d0"])
+
+
 def test_restated_uzawa_bit_exact(case):
     d = case
     lm = d.levmax
