@@ -4,6 +4,7 @@
 #pragma once
 #include "ccu_layout.cuh"
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #define CCU_VBX 0x2u
 #define CCU_VBZ 0x4u
@@ -458,6 +459,124 @@ __global__ void __launch_bounds__(1024) ccu_k_relax_smem(const CcuGeom g, const 
             __syncthreads();
         }
     if(t < n) { x[s] = xs[t]; x[NS + s] = xs[n1 + t]; x[2 * NS + s] = xs[2 * n1 + t]; }
+}
+
+// ---------------------------------------------------------------- bottom level, one 8-CTA cluster, fp64 rows in shared memory
+// ccu_k_relax_smem above runs on ONE SM and re-converts every fp32 coefficient to fp64 at each use (40 times per call:
+// 20 sweeps x own + transposed use); ncu/timing showed it bound by that SM's conversion pipe (~350 us per call, 126 calls
+// per Stokes solve at 256x256x128 = 7 % of the step).  Here the level is spread over the eight SMs of a thread-block
+// cluster: CTA r owns every eighth node of each colour and keeps their FULL rows (27 blocks, transposed blocks already
+// transposed) in its shared memory as fp64 -- converted once per call --, every CTA holds a replica of the solution,
+// a warp relaxes one node per phase (lane = stencil block), and the three updating lanes publish the new values to all
+// eight replicas through distributed shared memory before the cluster barrier that ends the phase.
+#define CCU_BOT_CTAS 8
+#define CCU_BOT_THREADS 512
+#define CCU_BOT_LD 28            // 27 blocks padded
+__global__ void __cluster_dims__(CCU_BOT_CTAS, 1, 1) __launch_bounds__(CCU_BOT_THREADS)
+ccu_k_relax_bottom(const CcuGeom g, const CcuSmemLevel sl, const int maxrows, const float *__restrict__ K, const double *__restrict__ BI,
+                   const double *__restrict__ F, double *x, const int cycles, const int zero_first)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int r = (int)cl.block_rank();
+    extern __shared__ double smem_d[];
+    const int n = sl.n, n1 = n + 1, t = threadIdx.x;
+    const size_t NS = (size_t)g.NS;
+    double *xs = smem_d;                                         // [3][n1] replica of the solution (+ zero dummy column n)
+    double *Kd = xs + 3 * n1;                                    // [maxrows][9][CCU_BOT_LD] full rows of this CTA's nodes
+    double *Fl = Kd + (size_t)maxrows * 9 * CCU_BOT_LD;          // [maxrows][3]
+    double *Bl = Fl + maxrows * 3;                               // [maxrows][3]
+    unsigned short *nb = (unsigned short *)(Bl + maxrows * 3);   // [maxrows][CCU_BOT_LD] compact index of block b's neighbour
+    int cnt[8], base[8], rows = 0;
+#pragma unroll
+    for(int c = 0; c < 8; c++)
+    {
+        const int nc = sl.cstart[c + 1] - sl.cstart[c];
+        cnt[c] = (nc - r + CCU_BOT_CTAS - 1) / CCU_BOT_CTAS;     // nodes idx = r, r+8, ... of colour c
+        if(cnt[c] < 0) cnt[c] = 0;
+        base[c] = rows; rows += cnt[c];
+    }
+    // ---- once per call: rows -> fp64, neighbour table, F, BI, solution replica
+    for(int w = t; w < rows * CCU_BOT_LD; w += CCU_BOT_THREADS)
+    {
+        const int row = w / CCU_BOT_LD, b = w - row * CCU_BOT_LD;
+        int c = 0;
+#pragma unroll
+        for(int q = 1; q < 8; q++) if(row >= base[q]) c = q;
+        const int tt = sl.cstart[c] + r + CCU_BOT_CTAS * (row - base[c]);
+        if(b < 27)
+        {
+            const int m = sl.nbr[b * n + tt];
+            nb[row * CCU_BOT_LD + b] = (unsigned short)m;
+            const bool tr = b >= 14;
+            const int slot = tr ? b - 13 : b;
+            const int sn = tr ? (m < n ? sl.s[m] : -1) : sl.s[tt];
+#pragma unroll
+            for(int e = 0; e < 9; e++)
+            {
+                const int es = tr ? 3 * (e % 3) + e / 3 : e;        // transposed block: K_nm = (K_mn)^T
+                Kd[((size_t)row * 9 + e) * CCU_BOT_LD + b] = sn >= 0 ? (double)__ldg(K + (size_t)(slot * 9 + es) * NS + sn) : 0.0;
+            }
+        }
+        else
+        {
+            nb[row * CCU_BOT_LD + b] = (unsigned short)n;
+            for(int e = 0; e < 9; e++) Kd[((size_t)row * 9 + e) * CCU_BOT_LD + b] = 0.0;
+        }
+        if(b < 3) { const int sn = sl.s[tt]; Fl[row * 3 + b] = F[b * NS + sn]; Bl[row * 3 + b] = BI[b * NS + sn]; }
+    }
+    for(int w = t; w < 3 * n1; w += CCU_BOT_THREADS)
+    {
+        const int d = w / n1, m = w - d * n1;
+        xs[w] = (m < n && !zero_first) ? x[d * NS + sl.s[m]] : 0.0;
+    }
+    cl.sync();
+    // ---- phases: one colour each; warp w relaxes the CTA's w-th node of the colour, lane = stencil block
+    const int warp = t >> 5, lane = t & 31;
+    for(int sw = 0; sw < cycles; sw++)
+#pragma unroll
+        for(int c = 7; c >= 0; c--)
+        {
+            if(warp < cnt[c])
+            {
+                const int row = base[c] + warp, tt = sl.cstart[c] + r + CCU_BOT_CTAS * warp;
+                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+                if(lane < 27)
+                {
+                    const int m = nb[row * CCU_BOT_LD + lane];
+                    const double x0 = xs[m], x1 = xs[n1 + m], x2 = xs[2 * n1 + m];
+                    const double *kp = Kd + (size_t)row * 9 * CCU_BOT_LD + lane;
+                    r0 = kp[0] * x0 + kp[CCU_BOT_LD] * x1 + kp[2 * CCU_BOT_LD] * x2;
+                    r1 = kp[3 * CCU_BOT_LD] * x0 + kp[4 * CCU_BOT_LD] * x1 + kp[5 * CCU_BOT_LD] * x2;
+                    r2 = kp[6 * CCU_BOT_LD] * x0 + kp[7 * CCU_BOT_LD] * x1 + kp[8 * CCU_BOT_LD] * x2;
+                }
+#pragma unroll
+                for(int o = 16; o > 0; o >>= 1)
+                {
+                    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+                    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+                    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+                }
+                if(lane < 3)
+                {   // General_matrix_functions.c:1250-1259: scalar BI per equation, correction rounded to fp32
+                    const double rr = lane == 0 ? r0 : (lane == 1 ? r1 : r2);
+                    const double xn = xs[lane * n1 + tt] + (double)(float)((Fl[row * 3 + lane] - rr) * Bl[row * 3 + lane]);
+#pragma unroll
+                    for(int q = 0; q < CCU_BOT_CTAS; q++) cl.map_shared_rank(xs, q)[lane * n1 + tt] = xn;
+                }
+            }
+            cl.sync();
+        }
+    // every CTA writes back the nodes it owns
+    for(int w = t; w < rows * 3; w += CCU_BOT_THREADS)
+    {
+        const int row = w / 3, d = w - row * 3;
+        int c = 0;
+#pragma unroll
+        for(int q = 1; q < 8; q++) if(row >= base[q]) c = q;
+        const int tt = sl.cstart[c] + r + CCU_BOT_CTAS * (row - base[c]);
+        x[d * NS + sl.s[tt]] = xs[d * n1 + tt];
+    }
 }
 
 // Au = K*u for all nodes (n_assemble_del2_u, Element_calculations.c:552).  One warp per colour,

@@ -156,6 +156,7 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_TILE_NODES: c->opt_tile_nodes = value; drop_graphs(c); return tile_refresh_all(c);
     case CCU_OPT_RELAX_TILE: c->opt_relax_tile = value; drop_graphs(c); return tile_refresh_all(c);
     case CCU_OPT_MATVEC_TILE: c->opt_matvec_tile = value; drop_graphs(c); return tile_refresh_all(c);
+    case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
     case CCU_OPT_TILE_PAD: c->opt_tile_pad = value; if(c->coarse) c->coarse->opt_tile_pad = value; drop_graphs(c); return 0;
     case CCU_OPT_TILE_HINT: c->opt_tile_hint = value; if(c->coarse) c->coarse->opt_tile_hint = value; drop_graphs(c); return 0;
     case CCU_OPT_TILE_SHAPE: if(value < 0 || value > 3) FAIL("tile shape must be 0..3"); c->opt_tile_shape = value; drop_graphs(c); return tile_refresh_all(c);
@@ -537,6 +538,20 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
     const int T = lanes_for(c, L);
     if(T == 0)
     {   // one CTA does every sweep and colour of a tiny level in a single launch
+        if(L.g.nno <= c->opt_smem_nodes && L.sm_s && c->opt_bottom_cluster)
+        {   // ... spread over an 8-CTA cluster, fp64 rows resident in distributed shared memory (ccu_k_relax_bottom)
+            CcuSmemLevel sl; sl.n = L.sm_n; sl.s = L.sm_s; sl.nbr = L.sm_nbr;
+            for(int q = 0; q < 9; q++) sl.cstart[q] = L.sm_cstart[q];
+            int maxrows = 0;
+            for(int q = 0; q < 8; q++) maxrows += (L.sm_cstart[q + 1] - L.sm_cstart[q] + CCU_BOT_CTAS - 1) / CCU_BOT_CTAS;
+            const size_t bytes = sizeof(double) * (3 * (size_t)(L.sm_n + 1) + (size_t)maxrows * 9 * CCU_BOT_LD + 6 * (size_t)maxrows)
+                                 + sizeof(unsigned short) * (size_t)maxrows * CCU_BOT_LD + 16;
+            static bool attr_set = false;
+            if(!attr_set) { cudaFuncSetAttribute(ccu_k_relax_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+            ccu_k_relax_bottom<<<CCU_BOT_CTAS, CCU_BOT_THREADS, bytes, c->st>>>(L.g, sl, maxrows, L.K, L.BI, F, x, cycles, 0);
+            c->launches++;
+            return;
+        }
         if(L.g.nno <= c->opt_smem_nodes && L.sm_s)
         {   // ... out of shared memory when the whole half-matrix fits
             CcuSmemLevel sl; sl.n = L.sm_n; sl.s = L.sm_s; sl.nbr = L.sm_nbr;

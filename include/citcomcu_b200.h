@@ -59,6 +59,8 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
         * 3 = 2x2x16 / one cell with rows split over 16 groups (1024 threads, one CTA per SM).  The tile smoother is a Gauss-Seidel sweep in tile order (tile colours 7..0,
         * node colours 7..0 inside a tile) instead of plain colour order. */
        CCU_OPT_TILE_NODES = 9, CCU_OPT_RELAX_TILE = 10, CCU_OPT_MATVEC_TILE = 11, CCU_OPT_TILE_HINT = 12, CCU_OPT_TILE_SHAPE = 13,
+       CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
+        * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */,
        CCU_OPT_TILE_PAD = 14 /* extra KB of shared memory per tile CTA: lowers the CTAs per SM (L2 working-set experiments) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */

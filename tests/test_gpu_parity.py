@@ -172,7 +172,8 @@ def test_empty_rhs_is_a_noop(case):
     dict(small_nodes=0, warp_nodes=10**9, cluster_nodes=0, matvec_tab=0),                                          # a warp per node
     dict(small_nodes=0, cluster_nodes=10**9),                                                                      # one cluster launch per smoother call
     dict(small_nodes=10**9, smem_nodes=0),                                                                         # single-CTA fused sweeps
-    dict(small_nodes=10**9),                                                                                       # shared-memory resident where it fits
+    dict(small_nodes=10**9),                                                                                       # 8-CTA cluster, fp64 rows in distributed shared memory
+    dict(small_nodes=10**9, bottom_cluster=0),                                                                     # one SM, shared-memory resident half-matrix
     dict(graphs=0)])
 def test_kernel_variants_agree(case, opts):
     """Every lanes-per-node variant of the smoother / matvec and the CUDA-graph replay give the same answers."""
