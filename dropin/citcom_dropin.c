@@ -1,7 +1,7 @@
 /* citcom_dropin.c -- reference-side binding of libcitcomcu_b200.so.
  *
- * Defines `general_stokes_solver` with the reference's own signature (src/prototypes.h,
- * Drive_solvers.c:45) on top of the C ABI in include/citcomcu_b200.h.  A maintainer either adds this
+ * Defines `general_stokes_solver` (Drive_solvers.c:45) and `PG_timestep` (Advection_diffusion.c:251) with the
+ * reference's own signatures (src/prototypes.h) on top of the C ABI in include/citcomcu_b200.h.  A maintainer either adds this
  * file to src/Makefile's CFILES in place of the body of Drive_solvers.c:general_stokes_solver, or --
  * without touching the reference at all -- preloads it:
  *
@@ -16,12 +16,18 @@
  * on the device from the previous E->U / E->P, and E->U, E->P, E->V and E->EVI[levmax] come back for
  * the reference's diagnostics and its energy step.
  *
+ * PG_timestep: E->V, E->T, E->Tdot go to the device, std_timestep + predictor + (pg_solver, corrector) x temp_iterations
+ * with the Tmax safeguard run there, T / Tdot come back; temperatures_conform_bcs and thermal_buoyancy stay the
+ * reference's (they are O(nno) host loops whose results the host needs anyway).  CCU_DROPIN_ENERGY=0 keeps the
+ * reference's own energy step.
+ *
  * Unsupported configurations stop the run loudly (there is no CPU fallback): spherical geometry,
  * stress- or composition-dependent viscosity, periodic side walls, more than one MPI rank.
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <dlfcn.h>
 #include "global_defs.h"
 #include "prototypes.h"
 #include "citcomcu_b200.h"
@@ -100,4 +106,50 @@ void general_stokes_solver(struct All_variables *E)
         fprintf(E->fp, "citcomcu_b200: after (%03d) pressure loops and %g sec for step %d\n", its, CPU_time0() - t0, E->monitor.solution_cycles);
     }
     (void)i;
+}
+
+/* ---- energy step (Advection_diffusion.c:251-349) ---- */
+static int g_energy = 0;
+typedef void (*pg_fn)(struct All_variables *);
+
+void PG_timestep(struct All_variables *E)
+{
+    float dt = 0.0f, Tint = 0.0f;
+    int n;
+    {   /* CCU_DROPIN_ENERGY=0: leave the energy step to the reference's own definition (preload builds only) */
+        const char *sw = getenv("CCU_DROPIN_ENERGY");
+        if(sw && atoi(sw) == 0)
+        {
+            static pg_fn next = NULL;
+            if(!next) next = (pg_fn)dlsym(RTLD_NEXT, "PG_timestep");
+            if(!next) die("CCU_DROPIN_ENERGY=0 but no other PG_timestep is linked");
+            next(E);
+            return;
+        }
+    }
+    if(!g_ctx) dropin_init(E);
+    if(!g_energy)
+    {
+        if(E->control.adi_heating || E->control.visc_heating) die("adiabatic / viscous heating is not on the device path");
+        if(E->control.Ra_410 != 0.0 || E->control.Ra_670 != 0.0) die("phase changes are not on the device path");
+        if(!E->advection.ADVECTION) die("ADVECTION=off is not on the device path");
+        for(n = 1; n <= E->lmesh.nno; n++)
+            if(E->node[n] & FBZ) die("heat-flux boundary conditions are not on the device path");
+        CCU(ccu_set_energy_params(g_ctx, E->advection.fine_tune_dt, E->advection.fixed_timestep, E->advection.gamma,
+                                  E->advection.temp_iterations, E->diffusivity + 1, E->expansivity + 1, E->control.Q0));
+        g_energy = 1;
+        if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: energy step on the CUDA device\n");
+    }
+    E->advection.timesteps++;
+    CCU(ccu_set_velocity(g_ctx, E->V[1] + 1, E->V[2] + 1, E->V[3] + 1));
+    CCU(ccu_PG_timestep(g_ctx, E->T + 1, E->Tdot + 1, &dt, &Tint));
+    E->advection.timestep = dt;
+    E->monitor.T_interior = Tint;
+    E->advection.dt_reduced = 1.0;
+    E->advection.total_timesteps++;
+    E->monitor.elapsed_time += E->advection.timestep;
+    temperatures_conform_bcs(E);
+    thermal_buoyancy(E);
+    E->advection.last_sub_iterations = 1;
+    E->control.keep_going = (E->monitor.solution_cycles < E->advection.max_timesteps) ? 1 : 0;
 }

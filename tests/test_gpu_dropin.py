@@ -1,6 +1,6 @@
 """GPU test of the drop-in boundary: the UNMODIFIED reference time loop (oracle/_ref/ref_harness = main()'s
-sequence, Citcom.c:54-175) with `general_stokes_solver` interposed by dropin/libcitcomcu_dropin.so, against
-the same run without the preload.  North-star tolerances: temperature after N steps, Nusselt numbers within
+sequence, Citcom.c:54-175) with `general_stokes_solver` -- and, in the second variant, `PG_timestep` as well --
+interposed by dropin/libcitcomcu_dropin.so, against the same run without the preload.  North-star tolerances: temperature after N steps, Nusselt numbers within
 0.1 %; velocities within the solver tolerance of the input file."""
 from pathlib import Path
 import tempfile
@@ -20,13 +20,16 @@ DROPIN = ROOT / "dropin" / "libcitcomcu_dropin.so"
     ("busse", inputfile.busse1a(levels=4, maxstep=6, accuracy=1e-4)),
     ("tdepv", inputfile.tdepv_box(32, 32, 16, 4, maxstep=6, accuracy=1e-4)),
 ], ids=["busse", "tdepv"])
-def test_reference_time_loop_with_gpu_stokes(name, txt):
+@pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
+def test_reference_time_loop_with_gpu_stokes(name, txt, energy, monkeypatch):
     if not po.have_ref() or not DROPIN.exists():
         pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
     nsteps = 5
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", str(energy))
     ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix=f"ccu_ref_{name}_"), nsteps=nsteps)
     gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix=f"ccu_gpu_{name}_"), nsteps=nsteps, preload=str(DROPIN))
     assert "citcomcu_b200 drop-in: Stokes solve on CUDA device" in err
+    assert ("citcomcu_b200 drop-in: energy step on the CUDA device" in err) == bool(energy)
     r, g = ref[0], gpu[0]
     acc = r.control()["accuracy"]
     for k in range(nsteps + 1):
