@@ -72,7 +72,7 @@ struct ccu_ctx
     bool use_graphs = true;
     // kernel selection by level size (lanes per node), ccu_set_option
     int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
-    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0, opt_bottom_cluster = 1;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
+    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0, opt_bottom_cluster = 1, opt_coop_nodes = 0, opt_mid_lanes = 4;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     // tile-resident smoother / matvec (ccu_tile.cuh) on levels above opt_tile_nodes nodes
     int opt_tile_nodes = 500000, opt_relax_tile = 0, opt_matvec_tile = 0, opt_tile_hint = 1, opt_tile_shape = 0, opt_tile_pad = 0;
     Level L[CCU_MAX_LEVELS];
@@ -89,6 +89,8 @@ struct ccu_ctx
     float *T = nullptr;            // [nno] temperature, natural order, finest level
     float *buoy = nullptr;         // [nno]
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
+    unsigned *coop_bar = nullptr;  // grid-barrier counter of the cooperative smoother (ccu_k_relax_coop)
+    int coop_sms = 0, coop_per_sm[3] = { 0, 0, 0 };   // SM count, co-resident CTAs per SM of the T = 32 / 8 / 4 variants
     double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces)
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;

@@ -38,6 +38,7 @@ int ccu_check_lev(ccu_ctx *c, int lev)
 
 static int ensure_smem_tables(ccu_ctx *c, Level &L);
 
+static int coop_init(ccu_ctx *c);
 int ccu_create(const ccu_config *cfg, ccu_ctx **out)
 {
     if(!cfg || !out) FAIL("ccu_create: null argument");
@@ -91,6 +92,7 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_COUNT, c->st));
     { const double one = 1.0; CK(cudaMemcpyAsync(c->scal + S_ONE, &one, sizeof(double), cudaMemcpyHostToDevice, c->st)); }
     CK(cudaMalloc(&c->partial, sizeof(double) * 3 * CCU_DOT_BLOCKS));
+    if(coop_init(c)) return 1;
     CK(cudaStreamSynchronize(c->st));
     *out = c;
     return 0;
@@ -125,7 +127,7 @@ void ccu_destroy(ccu_ctx *c)
     if(c->own_stream) cudaStreamDestroy(c->own_stream);
     for(auto &r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for(auto e : c->prof_pool) cudaEventDestroy(e);
-    cudaFree(c->forceEF);
+    cudaFree(c->forceEF); cudaFree(c->coop_bar);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }
@@ -157,6 +159,8 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_RELAX_TILE: c->opt_relax_tile = value; drop_graphs(c); return tile_refresh_all(c);
     case CCU_OPT_MATVEC_TILE: c->opt_matvec_tile = value; drop_graphs(c); return tile_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
+    case CCU_OPT_COOP_NODES: c->opt_coop_nodes = value; if(c->coarse) c->coarse->opt_coop_nodes = value; drop_graphs(c); return 0;
+    case CCU_OPT_MID_LANES: if(value != 4 && value != 8 && value != 16) FAIL("mid lanes must be 4, 8 or 16"); c->opt_mid_lanes = value; if(c->coarse) c->coarse->opt_mid_lanes = value; drop_graphs(c); return 0;
     case CCU_OPT_TILE_PAD: c->opt_tile_pad = value; if(c->coarse) c->coarse->opt_tile_pad = value; drop_graphs(c); return 0;
     case CCU_OPT_TILE_HINT: c->opt_tile_hint = value; if(c->coarse) c->coarse->opt_tile_hint = value; drop_graphs(c); return 0;
     case CCU_OPT_TILE_SHAPE: if(value < 0 || value > 3) FAIL("tile shape must be 0..3"); c->opt_tile_shape = value; drop_graphs(c); return tile_refresh_all(c);
@@ -495,6 +499,59 @@ static int ensure_smem_tables(ccu_ctx *c, Level &L)
     return 0;
 }
 
+// cooperative smoother launch (ccu_k_relax_coop): T lanes per node and m CTAs per SM sized to the level; returns
+// non-zero (and launches nothing) when the device cannot hold the grid
+template <int T>
+static int coop_occupancy()
+{
+    int per_sm = 0;
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccu_k_relax_coop<T>, 256, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return per_sm;
+}
+// queried once at context creation (nothing here may run inside a graph capture)
+static int coop_init(ccu_ctx *c)
+{
+    int dev = 0, coop = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    CK(cudaDeviceGetAttribute(&c->coop_sms, cudaDevAttrMultiProcessorCount, dev));
+    c->coop_per_sm[0] = coop ? coop_occupancy<32>() : 0;
+    c->coop_per_sm[1] = coop ? coop_occupancy<8>() : 0;
+    c->coop_per_sm[2] = coop ? coop_occupancy<4>() : 0;
+    CK(cudaMalloc(&c->coop_bar, sizeof(unsigned)));
+    return 0;
+}
+template <int T>
+static int launch_relax_coop_T(ccu_ctx *c, Level &L, double *x, const double *F, int cycles, int per_sm)
+{
+    if(per_sm <= 0 || !c->coop_bar) return 1;
+    const int sms = c->coop_sms;
+    const size_t items = (size_t)L.g.NC * T;
+    int m = (int)((items + (size_t)sms * 256 - 1) / ((size_t)sms * 256));
+    if(m < 1) m = 1;
+    if(m > 4) m = 4;
+    if(m > per_sm) m = per_sm;
+    cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned), c->st);
+    CcuGeom g = L.g;
+    CcuStencil st = ccu_make_stencil(L.g);
+    const float *K = L.K; const double *BI = L.BI;
+    unsigned *bar = c->coop_bar;
+    void *args[] = { &g, &st, &K, &BI, &F, &x, &cycles, &bar };
+    if(cudaLaunchCooperativeKernel((const void *)ccu_k_relax_coop<T>, dim3(sms * m), dim3(256), args, 0, c->st) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 1;
+    }
+    c->launches++;
+    return 0;
+}
+static int launch_relax_coop(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
+{
+    if(L.g.nno <= 4000) return launch_relax_coop_T<32>(c, L, x, F, cycles, c->coop_per_sm[0]);
+    if(L.g.nno <= 40000) return launch_relax_coop_T<8>(c, L, x, F, cycles, c->coop_per_sm[1]);
+    return launch_relax_coop_T<4>(c, L, x, F, cycles, c->coop_per_sm[2]);
+}
+
 template <int T>
 static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F, const unsigned char *bits)
 {
@@ -564,6 +621,10 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         LAUNCH(c, ccu_k_relax_small, 1, 1024, L.g, L.K, L.BI, F, x, cycles, 0);
         return;
     }
+    if(!c->multi() && c->opt_coop_nodes > 0 && L.g.nno <= c->opt_coop_nodes)
+    {   // mid level: every sweep and colour of the call in ONE cooperative launch, grid barriers between the passes
+        if(launch_relax_coop(c, L, x, F, cycles) == 0) return;
+    }
     if(!c->multi() && L.g.nno <= c->opt_cluster_nodes)
     {   // small level: the whole call in one cluster launch (warp per node below ~4000 nodes, else four lanes per node)
         const CcuStencil st = ccu_make_stencil(L.g);
@@ -577,7 +638,13 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
     {   // colours 7..0: odd-odd-odd nodes first, the coarse-grid nodes (colour 0) last
         if(bits) relax_faces(c, L, x, F);
         if(T == 32) { launch_relax_lanes<32>(c, L, x, F, bits); continue; }
-        if(T == 4) { launch_relax_lanes<4>(c, L, x, F, bits); continue; }
+        if(T == 4)
+        {   // mid levels: 4, 8 or 16 lanes per node (CCU_OPT_MID_LANES)
+            if(c->opt_mid_lanes == 16) launch_relax_lanes<16>(c, L, x, F, bits);
+            else if(c->opt_mid_lanes == 8) launch_relax_lanes<8>(c, L, x, F, bits);
+            else launch_relax_lanes<4>(c, L, x, F, bits);
+            continue;
+        }
         if(c->opt_relax_tab)
         {
             const CcuStencil st = ccu_make_stencil(L.g);

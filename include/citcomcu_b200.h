@@ -61,6 +61,9 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
        CCU_OPT_TILE_NODES = 9, CCU_OPT_RELAX_TILE = 10, CCU_OPT_MATVEC_TILE = 11, CCU_OPT_TILE_HINT = 12, CCU_OPT_TILE_SHAPE = 13,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */,
+       CCU_OPT_COOP_NODES = 16 /* single-subdomain levels with SMALL_NODES < nno <= this (default 0 = off: measured no faster than the graph-replayed per-pass launches) run each smoother call as one
+        * cooperative launch with grid barriers between the colour passes (ccu_k_relax_coop); 0 = per-pass launches */,
+       CCU_OPT_MID_LANES = 17 /* lanes per node (4, 8 or 16) of the smoother on levels between WARP_NODES and QUAD_NODES */,
        CCU_OPT_TILE_PAD = 14 /* extra KB of shared memory per tile CTA: lowers the CTAs per SM (L2 working-set experiments) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
