@@ -595,7 +595,9 @@ __global__ void __launch_bounds__(256) ek_corrector(const int n, const unsigned 
 __global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ eco,
                                                           const unsigned *__restrict__ node, const float *__restrict__ T,
                                                           const float *__restrict__ Tdot, const float *__restrict__ V,
-                                                          const float *__restrict__ diffusivity, const float Q0, double *Eres)
+                                                          const float *__restrict__ diffusivity, const float Q0,
+                                                          const float *__restrict__ heat_adi, const float *__restrict__ heat_visc,
+                                                          const float *__restrict__ heat_latent, double *Eres)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -627,9 +629,12 @@ __global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const
     const double fai = (ufai > twodiff) ? (1.0 - twodiff / ufai) : 0.0;
     const double unorm = uc1 * uc1 + uc2 * uc2 + uc3 * uc3;
     const double adiff = (unorm > 0.000001) ? ((uxse * xse + ueta * eta + ufai * fai) / (2.0 * unorm)) : 0.0;
-    const double Q = ((double)Q0 - (double)0.0f + (double)0.0f) * (double)1.0f;       // heating_adi = heating_visc = 0, heating_latent = 1
+    // Q = (rad_heat.total - heating_adi[el] + heating_visc[el]) * heating_latent[el]  (:643-647; the arrays hold 0, 0, 1
+    // unless process_heating filled them)
+    const float h_adi = heat_adi ? heat_adi[e] : 0.0f, h_visc = heat_visc ? heat_visc[e] : 0.0f, h_lat = heat_latent ? heat_latent[e] : 1.0f;
+    const double Q = ((double)Q0 - (double)h_adi + (double)h_visc) * (double)h_lat;
     const bool diffusion = (diff != 0.0f);
-    const float dl = diff * 1.0f;                                                      // diff * heating_latent[el]  (float * float)
+    const float dl = diff * h_lat;                                                     // diff * heating_latent[el]  (float * float)
     double res[8];
     for(int j = 0; j < 8; j++) res[j] = 0.0;
     for(int i = 0; i < 8; i++)
@@ -659,6 +664,60 @@ __global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const
     }
     for(int j = 0; j < 8; j++) Eres[(size_t)e * 8 + j] = res[j];
 }
+// process_heating (Advection_diffusion.c:813-957), CART3D, without phase changes: per element
+//   heating_visc = (Di/Atemp) * mean_gp(EVI) * 0.5 * (second invariant of the strain rate at the element centre)^2-sum
+//                  (strain_rate_2_inv, Viscosity_structures.c:1043-1088, SQRT = 0),
+//   heating_adi  = mean_nodes( Vz (T + Ts) Di ) * (expansivity[ez] + expansivity[ez+1]) / 2,   heating_latent = 1.
+// Operand types as the reference: products of float operands are float, sums run in double.
+__global__ void __launch_bounds__(64) ek_process_heating(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ EVI,
+                                                         const float *__restrict__ T, const float *__restrict__ V,
+                                                         const float *__restrict__ expansivity, const int adi_on, const int visc_on,
+                                                         const float disptn, const float surf_temp, const float Atemp,
+                                                         float *heat_adi, float *heat_visc, float *heat_latent)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    const double temp1 = (double)(disptn / Atemp);                       // float division, kept in a double
+    if(visc_on)
+    {
+        float X[3][8], gnx[3][8], VV[3][8];
+        load_elt_coords(g, XX, ey, ex, ez, X);
+        gp_geom(X, c_sh.Nxp, 8, 1, gnx);                                 // gNX[e].ppt: derivatives at the pressure point
+        for(int a = 1; a <= 8; a++)
+        {
+            const int n = elt_node(g, ey, ex, ez, a);
+            for(int d = 0; d < 3; d++) VV[d][a - 1] = V[(size_t)d * g.nno + n];
+        }
+        double dudx[3][3];
+        for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) dudx[p][q] = 0.0;
+        for(int i = 0; i < 8; i++)
+            for(int p = 0; p < 3; p++)
+                for(int q = 0; q < 3; q++) dudx[p][q] += VV[p][i] * gnx[q][i];          // float * float
+        double ed[3][3];
+        for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) ed[p][q] = 0.5 * (dudx[p][q] + dudx[q][p]);
+        float eedot = (float)(ed[0][0] * ed[0][0] + ed[0][1] * ed[0][1] * 2.0 + ed[1][1] * ed[1][1] + ed[1][2] * ed[1][2] * 2.0 +
+                              ed[2][2] * ed[2][2] + ed[0][2] * ed[0][2] * 2.0);
+        eedot = (float)((double)eedot * 0.5);
+        double temp2 = 0.0;
+        for(int i = 0; i < 8; i++) temp2 += EVI[(size_t)e * 8 + i];
+        temp2 = temp2 / 8;
+        heat_visc[e] = (float)(temp1 * temp2 * (double)eedot);
+    }
+    if(adi_on)
+    {
+        double temp2 = 0.0;
+        for(int a = 1; a <= 8; a++)
+        {
+            const int n = elt_node(g, ey, ex, ez, a);
+            temp2 = temp2 + (double)(V[2 * (size_t)g.nno + n] * (T[n] + surf_temp) * disptn);   // float expression
+        }
+        temp2 = temp2 / 8;
+        heat_adi[e] = (float)(temp2 * (double)(expansivity[ez] + expansivity[ez + 1]) * 0.5);
+    }
+    (void)heat_latent;
+}
+
 // the scatter DTdot[node] += Eres[a] of pg_solver (:425-429) as a gather in ascending element order, float accumulator
 __global__ void __launch_bounds__(128) ek_gather_residual(const CcuGeom g, const double *__restrict__ Eres, const float *__restrict__ MASS, float *DTdot)
 {
@@ -913,6 +972,7 @@ int ccu_build_geometry(ccu_ctx *c)
         if(!L.have_xx) FAIL("build_geometry: coordinates missing");
         if(ccu_ensure_stage(c, sizeof(double) * 8 * (size_t)L.g.nel)) return 1;
         LAUNCH(c, bk_elt_geometry, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.TWW, (double *)c->stage, L.eco, L.elt_del);
+        ccu_elt_del_changed(c, lev);
         LAUNCH(c, bk_mass, cdiv(L.g.nno, 128), 128, L.g, (const double *)c->stage, L.MASS);
         if(ccu_halo_sum_nodal(c, lev, L.MASS)) return 1;                  // exchange_node_f20 (Size_does_matter.c:733)
         LAUNCH(c, bk_invert, cdiv(L.g.nno, 128), 128, L.g.nno, L.MASS);
@@ -1176,6 +1236,41 @@ int ccu_set_energy_params(ccu_ctx *c, float fine_tune_dt, float fixed_timestep, 
     E.have_params = true; E.diff_timestep = -1.0f;
     return 0;
 }
+// E->control.{adi_heating, visc_heating, Atemp}, E->data.{disptn_number, surf_temp}: extended-Boussinesq heating terms
+int ccu_set_heating_params(ccu_ctx *c, int adi_heating, int visc_heating, float disptn_number, float surf_temp, float Atemp)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    auto &E = c->en;
+    E.adi_heating = adi_heating; E.visc_heating = visc_heating; E.disptn = disptn_number; E.surf_temp = surf_temp; E.Atemp_heat = Atemp;
+    const size_t nel = (size_t)c->L[c->cfg.levmax].g.nel;
+    if((adi_heating || visc_heating) && !E.heat_adi)
+    {
+        CK(cudaMalloc(&E.heat_adi, sizeof(float) * nel)); CK(cudaMemsetAsync(E.heat_adi, 0, sizeof(float) * nel, c->st));
+        CK(cudaMalloc(&E.heat_visc, sizeof(float) * nel)); CK(cudaMemsetAsync(E.heat_visc, 0, sizeof(float) * nel, c->st));
+    }
+    return 0;
+}
+// process_heating (Advection_diffusion.c:813) from the resident T, V and EVI[levmax]; outputs optional (float[nel])
+int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    auto &E = c->en;
+    Level &L = c->L[c->cfg.levmax];
+    if(!(E.adi_heating || E.visc_heating)) return 0;
+    if(!E.have_v) FAIL("process_heating: velocity missing (ccu_set_velocity / ccu_v_from_vector)");
+    if(E.visc_heating && !L.have_evi) FAIL("process_heating: viscosity missing");
+    if(!E.have_params) FAIL("process_heating: ccu_set_energy_params first (expansivity)");
+    LAUNCH(c, ek_process_heating, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.EVI, c->T, E.V, E.expansivity, E.adi_heating, E.visc_heating,
+           E.disptn, E.surf_temp, E.Atemp_heat, E.heat_adi, E.heat_visc, (float *)nullptr);
+    const size_t nel = (size_t)L.g.nel;
+    if(heating_adi_out) CK(cudaMemcpyAsync(heating_adi_out, E.heat_adi, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
+    if(heating_visc_out) CK(cudaMemcpyAsync(heating_visc_out, E.heat_visc, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
 int ccu_set_tdot(ccu_ctx *c, const float *Tdot)
 {
     if(!c) FAIL("null context");
@@ -1263,7 +1358,8 @@ static int pg_solver(ccu_ctx *c)
 {
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
-    LAUNCH(c, ek_element_residual, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.eco, L.node, c->T, E.Tdot, E.V, E.diffusivity, E.Q0, E.Eres);
+    LAUNCH(c, ek_element_residual, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.eco, L.node, c->T, E.Tdot, E.V, E.diffusivity, E.Q0,
+           (const float *)E.heat_adi, (const float *)E.heat_visc, (const float *)E.heat_latent, E.Eres);
     if(!c->multi()) { LAUNCH(c, ek_gather_residual, cdiv(L.g.nno, 128), 128, L.g, E.Eres, L.MASS, E.DTdot); return 0; }
     LAUNCH(c, ek_gather_residual, cdiv(L.g.nno, 128), 128, L.g, E.Eres, (const float *)nullptr, E.DTdot);
     if(ccu_halo_sum_nodal(c, c->cfg.levmax, E.DTdot)) return 1;      // exchange_node_f20 (Advection_diffusion.c:432)

@@ -31,6 +31,7 @@ struct Level
     double *BI = nullptr;
     unsigned char *flags = nullptr;
     float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
+    float *elt_delT = nullptr;    // [24][nel] coefficient-major copy of elt_del (div_u / grad_p read it)
     double *BPI = nullptr;
     double *vec[CCU_VEC_COUNT] = { nullptr };
     // operator construction (ccu_build.cu)
@@ -100,6 +101,8 @@ struct ccu_ctx
         float *Tdot = nullptr, *DTdot = nullptr, *V = nullptr;     // [nno], [nno], [3][nno]
         float *T1 = nullptr, *Tdot1 = nullptr;                     // saved fields of the Tmax safeguard
         float *diffusivity = nullptr, *expansivity = nullptr;      // [noz]
+        float *heat_adi = nullptr, *heat_visc = nullptr, *heat_latent = nullptr;   // [nel] process_heating; null = 0, 0, 1
+        int adi_heating = 0, visc_heating = 0; float disptn = 0.0f, surf_temp = 0.0f, Atemp_heat = 1.0f;
         double *Eres = nullptr;                                    // [nel][8] element residuals
         double *layer = nullptr;                                   // [2][noz] layer sums of remove_horiz_ave
         float *red = nullptr;                                      // device scalars: [0] min, [1] max
@@ -184,4 +187,5 @@ int ccu_damp_face_BI(ccu_ctx *c, int lev);
 int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_rank);
 int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of all subdomains -> coarse replica (ccu_stokes.cu)                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);
-int ccu_tile_refresh(ccu_ctx *c, int lev);                   // ccu_stokes.cu
+int ccu_tile_refresh(ccu_ctx *c, int lev);
+void ccu_elt_del_changed(ccu_ctx *c, int lev);                // ccu_stokes.cu                   // ccu_stokes.cu

@@ -1225,27 +1225,39 @@ __global__ void __launch_bounds__(128) ccu_k_interp(const CcuGeom gc, const CcuG
 }
 
 // ---------------------------------------------------------------- pressure coupling
+// elt_del[nel][24] (the reference's element-major layout) -> eltT[24][nel]: consecutive elements of one coefficient are
+// contiguous, so the element / node threads of div_u / grad_p read whole sectors (the element-major array costs a
+// 96-byte stride per thread: 24 wavefronts per load instruction, which made both kernels LSU-bound)
+__global__ void __launch_bounds__(256) ccu_k_elt_del_transpose(const int nel, const float *__restrict__ elt_del, float *__restrict__ eltT)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if(t >= (size_t)nel * 24) return;
+    const int p = (int)(t / nel), e = (int)(t - (size_t)p * nel);
+    eltT[t] = elt_del[(size_t)e * 24 + p];
+}
 // assemble_div_u (Element_calculations.c:691-720): one thread per element, local nodes in order.
-__global__ void __launch_bounds__(128) ccu_k_div_u(const CcuGeom g, const float *__restrict__ elt_del, const double *__restrict__ U, double *divU)
+__global__ void __launch_bounds__(128) ccu_k_div_u(const CcuGeom g, const float *__restrict__ eltT, const double *__restrict__ U, double *divU)
 {
     constexpr int OFFS[9][3] = CCU_OFFS_INIT;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
     const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
-    const float *gg = elt_del + (size_t)e * 24;
+    const float *gg = eltT + e;
+    const size_t nel = (size_t)g.nel;
     double s = 0.0;
 #pragma unroll
     for(int a = 1; a <= 8; a++)
     {
         const int sn = ccu_sidx(g, ey + OFFS[a][2], ex + OFFS[a][1], ez + OFFS[a][0]);
-        s += (double)gg[3 * (a - 1)] * U[sn] + (double)gg[3 * (a - 1) + 1] * U[(size_t)g.NS + sn] + (double)gg[3 * (a - 1) + 2] * U[2 * (size_t)g.NS + sn];
+        s += (double)__ldg(gg + (3 * (a - 1)) * nel) * U[sn] + (double)__ldg(gg + (3 * (a - 1) + 1) * nel) * U[(size_t)g.NS + sn] +
+             (double)__ldg(gg + (3 * (a - 1) + 2) * nel) * U[2 * (size_t)g.NS + sn];
     }
     divU[e] = s;
 }
 // assemble_grad_p (Element_calculations.c:727-769) as a gather: one thread per node sums its <= 8
 // elements in ascending element order (the order the reference's element loop adds them), then
 // strips the boundary dofs.
-__global__ void __launch_bounds__(128) ccu_k_grad_p(const CcuGeom g, const float *__restrict__ elt_del, const unsigned char *__restrict__ flags,
+__global__ void __launch_bounds__(128) ccu_k_grad_p(const CcuGeom g, const float *__restrict__ eltT, const unsigned char *__restrict__ flags,
                                                      const double *__restrict__ P, double *gradP)
 {
     constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
@@ -1267,8 +1279,8 @@ __global__ void __launch_bounds__(128) ccu_k_grad_p(const CcuGeom g, const float
                 const int e = ez + g.elz * (ex + g.elx * ey);
                 const int a = LUT[k - ez][j - ex][i - ey];
                 const double p = P[e];
-                const float *gg = elt_del + (size_t)e * 24 + 3 * (a - 1);
-                s0 += (double)gg[0] * p; s1 += (double)gg[1] * p; s2 += (double)gg[2] * p;
+                const float *gg = eltT + (size_t)(3 * (a - 1)) * g.nel + e;
+                s0 += (double)__ldg(gg) * p; s1 += (double)__ldg(gg + g.nel) * p; s2 += (double)__ldg(gg + 2 * (size_t)g.nel) * p;
             }
         }
     }

@@ -70,6 +70,7 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
         CK(cudaMalloc(&L.TWW, sizeof(float) * 8 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.eco, sizeof(float) * 3 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.elt_del, sizeof(float) * 24 * (size_t)L.g.nel));
+        CK(cudaMalloc(&L.elt_delT, sizeof(float) * 24 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.BPI, sizeof(double) * (size_t)L.g.npno));
         const int nvec = (lev == cfg->levmax) ? CCU_VEC_COUNT : CCU_VEC_U;   // U, F, T* only at the top level
         for(int v = 0; v < nvec; v++)
@@ -112,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.Kt); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.Kt); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -257,6 +258,7 @@ int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double
     if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     CK(cudaMemcpyAsync(L.elt_del, elt_del, sizeof(float) * 24 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    ccu_elt_del_changed(c, lev);
     CK(cudaMemcpyAsync(L.BPI, BPI, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
     L.have_p = true;
@@ -273,6 +275,13 @@ int ccu_set_transfer_weights(ccu_ctx *c, int lev, const float *TWW, const float 
     CK(cudaStreamSynchronize(c->st));
     L.have_tw = true;
     return 0;
+}
+
+// coefficient-major copy of elt_del for div_u / grad_p; call after every write of L.elt_del
+void ccu_elt_del_changed(ccu_ctx *c, int lev)
+{
+    Level &L = c->L[lev];
+    LAUNCH(c, ccu_k_elt_del_transpose, cdiv((size_t)L.g.nel * 24, 256), 256, L.g.nel, L.elt_del, L.elt_delT);
 }
 
 // ------------------------------------------------------------------ device-side building blocks
@@ -964,11 +973,11 @@ static int d_conj_grad(ccu_ctx *c, int lev, const double *F, double acc, int *cy
 
 static void d_div_u(ccu_ctx *c, Level &L, const double *U, double *divU)
 {
-    LAUNCH(c, ccu_k_div_u, cdiv(L.g.nel, 128), 128, L.g, L.elt_del, U, divU);
+    LAUNCH(c, ccu_k_div_u, cdiv(L.g.nel, 128), 128, L.g, L.elt_delT, U, divU);
 }
 static void d_grad_p(ccu_ctx *c, Level &L, const double *P, double *gradP)
 {
-    LAUNCH(c, ccu_k_grad_p, cdiv(8 * (size_t)L.g.NC, 128), 128, L.g, L.elt_del, L.flags, P, gradP);
+    LAUNCH(c, ccu_k_grad_p, cdiv(8 * (size_t)L.g.NC, 128), 128, L.g, L.elt_delT, L.flags, P, gradP);
     if(c->multi()) ccu_halo_sum_vec(c, (int)(&L - c->L), gradP);      // exchange_id_d20 (Element_calculations.c:764)
 }
 

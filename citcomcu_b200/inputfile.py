@@ -103,3 +103,20 @@ def tdepv_box(elx: int, ely: int, elz: int, levels: int, *, nproc=(1, 1, 1), **o
     )
     p.update(overrides)
     return cartesian_box(elx, ely, elz, levels, dimx=2.0, dimy=2.0, dimz=1.0, nproc=nproc, **p)
+
+
+def input1_cart(levels: int = 4, maxstep: int = 5, **overrides) -> str:
+    """BASELINE config 2: examples/input1 as a single-rank Cartesian run -- unit box, mgunit 6x6x6
+    (48^3 elements at levels=4), NON-UNIFORM z spacing (refined boundary layers: zz=0,0.1,0.9,1 / nz=1,7,43,49),
+    Ra=10.97394e5, constant viscosity with the cutoffs on, free slip, augmented Lagrangian 1e3 with the preconditioner.
+    Smaller `levels` keep the same layer proportions (1/8, 3/4, 1/8 of the elements)."""
+    n = 6 * 2 ** (levels - 1)
+    a = n // 8
+    p = dict(
+        rayleigh=10.97394e5, TDEPV="off", VISC_UPDATE="off", update_every_steps=2, viscE="6.9077553,6.9077553,6.9077553,6.9077553",
+        VMIN="on", visc_min=5.0e-2, VMAX="on", visc_max=2.0e04, topvbc=0, botvbc=0, perturbmag=0.001, perturbk=1.0, perturbl=6.0,
+        aug_lagr="on", aug_number=1.0e3, precond="on", dissipation_number=2.601, accuracy=1.0e-3,
+        z_grid_layers=4, zz="0.0,0.1,0.9,1.0", nz=f"1,{1 + a},{1 + n - a},{1 + n}",
+    )
+    p.update(overrides)
+    return cartesian_box(n, n, n, levels, dimx=1.0, dimy=1.0, dimz=1.0, maxstep=maxstep, **p)

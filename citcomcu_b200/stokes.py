@@ -337,6 +337,20 @@ class StokesContext:
         check(self.lib.ccu_set_energy_params(self._ctx, C.c_float(fine_tune_dt), C.c_float(fixed_timestep), C.c_float(gamma),
                                              int(temp_iterations), dz.ctypes.data_as(C.c_void_p), ex.ctypes.data_as(C.c_void_p), C.c_float(Q0)))
 
+    def set_heating_params(self, adi_heating, visc_heating, disptn_number, surf_temp, Atemp):
+        check(self.lib.ccu_set_heating_params(self._ctx, int(adi_heating), int(visc_heating), C.c_float(disptn_number),
+                                              C.c_float(surf_temp), C.c_float(Atemp)))
+        self._heating = bool(adi_heating or visc_heating)
+
+    def process_heating(self, want_host=True):
+        """process_heating (Advection_diffusion.c:813): returns (heating_adi, heating_visc) float32[nel] or None."""
+        nel = self.nel(self.levmax)
+        a = np.empty(nel, dtype=np.float32) if want_host else None
+        v = np.empty(nel, dtype=np.float32) if want_host else None
+        ptr = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        check(self.lib.ccu_process_heating(self._ctx, ptr(a), ptr(v)))
+        return (a, v) if want_host else None
+
     def set_tdot(self, Tdot=None):
         t = None if Tdot is None else np.ascontiguousarray(Tdot, dtype=np.float32)
         check(self.lib.ccu_set_tdot(self._ctx, None if t is None else t.ctypes.data_as(C.c_void_p)))
@@ -439,6 +453,8 @@ class StokesContext:
     def advance(self, Atemp, *, composition=False, rebuild=1, **stokes_kw):
         """One timestep as main() runs it: next_buoyancy_field (PG_timestep or PG_timestep_particle), general_stokes_solver
         from the previous solution, v_from_vector, and with markers the second next_buoyancy_field call.  Returns dt."""
+        if getattr(self, "_heating", False):
+            self.process_heating(want_host=False)           # Citcom.c:116, before next_buoyancy_field
         if composition:
             dt = self.PG_timestep_particle(Atemp)
         else:

@@ -195,6 +195,12 @@ int ccu_general_stokes_solver(ccu_ctx *ctx, const float *T, const float *buoyanc
 int ccu_set_energy_params(ccu_ctx *ctx, float fine_tune_dt, float fixed_timestep, float gamma, int temp_iterations,
                           const float *diffusivity /*[noz]*/, const float *expansivity /*[noz]*/, float Q0);
 int ccu_set_tdot(ccu_ctx *ctx, const float *Tdot /*[nno] or NULL = zero*/);
+/* extended-Boussinesq heating: E->control.{adi_heating, visc_heating, Atemp}, E->data.{disptn_number, surf_temp} */
+int ccu_set_heating_params(ccu_ctx *ctx, int adi_heating, int visc_heating, float disptn_number, float surf_temp, float Atemp);
+/* process_heating (Advection_diffusion.c:813; strain_rate_2_inv Viscosity_structures.c:979), Cartesian, no phase changes:
+ * element heating terms from the resident T, velocity and EVI[levmax]; they enter pg_solver's element residuals
+ * (Advection_diffusion.c:643-647).  heating_*_out: float[nel] or NULL */
+int ccu_process_heating(ccu_ctx *ctx, float *heating_adi_out, float *heating_visc_out);
 int ccu_set_velocity(ccu_ctx *ctx, const float *V1, const float *V2, const float *V3 /*[nno] each*/);
 /* v_from_vector (Stokes_flow_Incomp.c:530): fp32 nodal velocity from the resident solution U; V_out = float[3*nno] or NULL */
 int ccu_v_from_vector(ccu_ctx *ctx, float *V_out);

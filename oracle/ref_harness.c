@@ -136,6 +136,14 @@ static void dump_fields(struct All_variables *E, const char *tag)
         snprintf(nm_, sizeof nm_, "%s_C", tag); DUMP_F32(nm_, E->C + 1, nno);
         snprintf(nm_, sizeof nm_, "%s_CE", tag); DUMP_F32(nm_, E->CE + 1, nel);
     }
+    if(E->control.adi_heating || E->control.visc_heating)
+    {   /* extended-Boussinesq heating terms as process_heating (Advection_diffusion.c:813) left them for the step just taken */
+        double eb[4] = { E->data.disptn_number, E->data.surf_temp, E->control.Atemp, E->control.Q0 };
+        snprintf(nm, sizeof nm, "%s_heating_adi", tag); DUMP_F32(nm, E->heating_adi + 1, nel);
+        snprintf(nm, sizeof nm, "%s_heating_visc", tag); DUMP_F32(nm, E->heating_visc + 1, nel);
+        snprintf(nm, sizeof nm, "%s_heating_latent", tag); DUMP_F32(nm, E->heating_latent + 1, nel);
+        snprintf(nm, sizeof nm, "%s_eba", tag); DUMP_F64(nm, eb, 4);
+    }
     {
         double sc[8] = { E->monitor.elapsed_time, E->advection.timestep, E->slice.Nut, E->slice.Nub,
                          E->monitor.T_interior, (double)E->monitor.solution_cycles, E->monitor.vdotv, E->monitor.pdotp };

@@ -32,6 +32,8 @@ CASES = {
     "busse_l4_tight": lambda: (inputfile.busse1a(levels=4, maxstep=1, accuracy=1e-8), 0, True),
     "tdepv_l3_tight": lambda: (inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, accuracy=1e-8), 0, True),
     "tdepv_l3": lambda: (inputfile.tdepv_box(16, 16, 8, 3, maxstep=2), 1, True),
+    # BASELINE config 2 (examples/input1 as Cartesian): non-uniform z spacing -> non-trivial interpolation weights / element sizes
+    "input1_cart_l3": lambda: (inputfile.input1_cart(levels=3, maxstep=1), 0, True),
     # tall box: several tiles of the tile-resident kernels along z as well (csrc/ccu_tile.cuh)
     "tdepv_tall": lambda: (inputfile.tdepv_box(8, 16, 64, 3, maxstep=1), 0, True),
 }

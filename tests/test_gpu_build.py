@@ -37,7 +37,7 @@ def frac_diff(a, b):
     return float(np.mean(a != b))
 
 
-@pytest.mark.parametrize("name,tdepv,viscE", [("busse_l3", 0, 0.0), ("tdepv_l3", 1, 11.512925)])
+@pytest.mark.parametrize("name,tdepv,viscE", [("busse_l3", 0, 0.0), ("tdepv_l3", 1, 11.512925), ("input1_cart_l3", 0, 0.0)])
 def test_device_operator_construction_bit_exact(name, tdepv, viscE):
     d = get_case(name)[0]
     ctx = build_ctx(d, tdepv, viscE)

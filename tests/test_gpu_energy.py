@@ -97,3 +97,59 @@ def test_coupled_timesteps_match_reference(state):
         ref = d[f"s{step}_T"]
         assert abs(dt - d[f"s{step}_scalars"][1]) <= 2e-3 * d[f"s{step}_scalars"][1]
         assert np.linalg.norm(T - ref) <= 1e-3 * np.linalg.norm(ref)
+
+
+# ---------------------------------------------------------------- extended-Boussinesq heating
+@pytest.fixture(scope="module")
+def eba_state():
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    text = inputfile.tdepv_box(16, 16, 8, 3, maxstep=4, adi_heating=1, visc_heating=1, dissipation_number=0.5, accuracy=1e-6)
+    dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_eba_")), nsteps=3, kat=True)
+    d = dumps[0]
+    prob = CartesianProblem(text)
+    ctx = context_from_problem(prob)
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    eb = d["s1_eba"]
+    ctx.set_heating_params(1, 1, eb[0], eb[1], eb[2])
+    yield d, prob, ctx, float(adv[5])
+    ctx.close()
+
+
+def test_process_heating_and_heated_timestep(eba_state):
+    """process_heating (adiabatic + viscous heating, strain_rate_2_inv) on the reference's step-0 state, then the
+    PG_timestep that consumes it: element heating terms within 2 ulp(fp32), T after the step within 4 ulp."""
+    d, prob, ctx, Atemp = eba_state
+    load_s0(d, ctx)
+    ctx.set_element_viscosity(prob.levmax, d["s0_EVI"])
+    adi, visc = ctx.process_heating()
+    assert np.abs(d["s1_heating_adi"]).max() > 0 and np.abs(d["s1_heating_visc"]).max() > 0
+    assert ulps(adi, d["s1_heating_adi"]) <= 2.0
+    assert ulps(visc, d["s1_heating_visc"]) <= 2.0
+    T, Tdot, dt, Tint = ctx.PG_timestep(d["s0_T"], d["s0_Tdot"])
+    assert dt == np.float32(d["s1_scalars"][1])
+    assert ulps(T, d["s1_T"]) <= 4.0
+
+
+def test_coupled_timesteps_with_heating(eba_state):
+    """main()'s loop with process_heating at the head of every step: T after 3 steps within 0.1 % of the reference."""
+    d, prob, ctx, Atemp = eba_state
+    ctl = prob.control
+    kw = dict(augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"])
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_tdot(None)
+    ctx.assemble_forces(d["s0_buoyancy"], want_host=False)
+    ctx.general_stokes_solver(None, None, rebuild=1, guess=0, want_host=False, **kw)
+    ctx.v_from_vector(want_host=False)
+    for step in (1, 2, 3):
+        dt, its = ctx.advance(Atemp, rebuild=1, **kw)
+        T = ctx.get_temperature()
+        ref = d[f"s{step}_T"]
+        assert abs(dt - d[f"s{step}_scalars"][1]) <= 2e-3 * d[f"s{step}_scalars"][1]
+        assert np.linalg.norm(T - ref) <= 1e-3 * np.linalg.norm(ref)
+        adi, visc = ctx.process_heating() if step < 3 else (None, None)
+        if adi is not None:   # the terms the NEXT step will use, against the reference's next-step dump
+            assert np.linalg.norm(adi - d[f"s{step + 1}_heating_adi"]) <= 2e-3 * np.linalg.norm(d[f"s{step + 1}_heating_adi"])

@@ -22,7 +22,7 @@ def rel2(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-@pytest.fixture(scope="module", params=["busse_l3", "tdepv_l3"])
+@pytest.fixture(scope="module", params=["busse_l3", "tdepv_l3", "input1_cart_l3"])
 def case(request, oracle_built):
     from citcomcu_b200.stokes import context_from_dump
     d = get_case(request.param)[0]
