@@ -1251,6 +1251,25 @@ int ccu_set_heating_params(ccu_ctx *c, int adi_heating, int visc_heating, float 
     }
     return 0;
 }
+// the reference's own E->heating_adi / heating_visc / heating_latent (float[nel] = ptr + 1), e.g. when process_heating stays
+// on the host (phase-change latent heating); NULL leaves the resident array (or the neutral value) in place
+int ccu_set_heating_arrays(ccu_ctx *c, const float *heating_adi, const float *heating_visc, const float *heating_latent)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    auto &E = c->en;
+    const size_t nel = (size_t)c->L[c->cfg.levmax].g.nel;
+    const float *src[3] = { heating_adi, heating_visc, heating_latent };
+    float **dst[3] = { &E.heat_adi, &E.heat_visc, &E.heat_latent };
+    for(int q = 0; q < 3; q++)
+    {
+        if(!src[q]) continue;
+        if(!*dst[q]) CK(cudaMalloc(dst[q], sizeof(float) * nel));
+        CK(cudaMemcpyAsync(*dst[q], src[q], sizeof(float) * nel, cudaMemcpyHostToDevice, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
 // process_heating (Advection_diffusion.c:813) from the resident T, V and EVI[levmax]; outputs optional (float[nel])
 int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
 {

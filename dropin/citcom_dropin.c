@@ -18,7 +18,8 @@
  *
  * PG_timestep: E->V, E->T, E->Tdot go to the device, std_timestep + predictor + (pg_solver, corrector) x temp_iterations
  * with the Tmax safeguard run there, T / Tdot come back; temperatures_conform_bcs and thermal_buoyancy stay the
- * reference's (they are O(nno) host loops whose results the host needs anyway).  CCU_DROPIN_ENERGY=0 keeps the
+ * reference's (they are O(nno) host loops whose results the host needs anyway), and so does process_heating: its element
+ * heating arrays (adiabatic, viscous, phase-change latent) are uploaded before the step.  CCU_DROPIN_ENERGY=0 keeps the
  * reference's own energy step.
  *
  * Unsupported configurations stop the run loudly (there is no CPU fallback): spherical geometry,
@@ -130,8 +131,6 @@ void PG_timestep(struct All_variables *E)
     if(!g_ctx) dropin_init(E);
     if(!g_energy)
     {
-        if(E->control.adi_heating || E->control.visc_heating) die("adiabatic / viscous heating is not on the device path");
-        if(E->control.Ra_410 != 0.0 || E->control.Ra_670 != 0.0) die("phase changes are not on the device path");
         if(!E->advection.ADVECTION) die("ADVECTION=off is not on the device path");
         for(n = 1; n <= E->lmesh.nno; n++)
             if(E->node[n] & FBZ) die("heat-flux boundary conditions are not on the device path");
@@ -141,6 +140,9 @@ void PG_timestep(struct All_variables *E)
         if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: energy step on the CUDA device\n");
     }
     E->advection.timesteps++;
+    /* extended-Boussinesq / phase-change heating terms: the reference's process_heating (Citcom.c:116) has just filled them */
+    if(E->control.adi_heating || E->control.visc_heating || E->control.Ra_410 != 0.0 || E->control.Ra_670 != 0.0)
+        CCU(ccu_set_heating_arrays(g_ctx, E->heating_adi + 1, E->heating_visc + 1, E->heating_latent + 1));
     CCU(ccu_set_velocity(g_ctx, E->V[1] + 1, E->V[2] + 1, E->V[3] + 1));
     CCU(ccu_PG_timestep(g_ctx, E->T + 1, E->Tdot + 1, &dt, &Tint));
     E->advection.timestep = dt;

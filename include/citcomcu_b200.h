@@ -201,6 +201,9 @@ int ccu_set_heating_params(ccu_ctx *ctx, int adi_heating, int visc_heating, floa
  * element heating terms from the resident T, velocity and EVI[levmax]; they enter pg_solver's element residuals
  * (Advection_diffusion.c:643-647).  heating_*_out: float[nel] or NULL */
 int ccu_process_heating(ccu_ctx *ctx, float *heating_adi_out, float *heating_visc_out);
+/* upload E->heating_adi+1, E->heating_visc+1, E->heating_latent+1 (float[nel], any may be NULL) when the reference's own
+ * process_heating computed them on the host (phase-change latent heating is not evaluated on the device) */
+int ccu_set_heating_arrays(ccu_ctx *ctx, const float *heating_adi, const float *heating_visc, const float *heating_latent);
 int ccu_set_velocity(ccu_ctx *ctx, const float *V1, const float *V2, const float *V3 /*[nno] each*/);
 /* v_from_vector (Stokes_flow_Incomp.c:530): fp32 nodal velocity from the resident solution U; V_out = float[3*nno] or NULL */
 int ccu_v_from_vector(ccu_ctx *ctx, float *V_out);

@@ -19,7 +19,10 @@ DROPIN = ROOT / "dropin" / "libcitcomcu_dropin.so"
 @pytest.mark.parametrize("name,txt", [
     ("busse", inputfile.busse1a(levels=4, maxstep=6, accuracy=1e-4)),
     ("tdepv", inputfile.tdepv_box(32, 32, 16, 4, maxstep=6, accuracy=1e-4)),
-], ids=["busse", "tdepv"])
+    # extended-Boussinesq: adiabatic + viscous heating and both phase changes (latent heating, phase buoyancy on the host)
+    ("eba", inputfile.tdepv_box(16, 16, 8, 3, maxstep=6, accuracy=1e-5, adi_heating=1, visc_heating=1, dissipation_number=0.5,
+                                Ra_410=100.0, Ra_670=-100.0)),
+], ids=["busse", "tdepv", "eba"])
 @pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
 def test_reference_time_loop_with_gpu_stokes(name, txt, energy, monkeypatch):
     if not po.have_ref() or not DROPIN.exists():
