@@ -718,6 +718,80 @@ __global__ void __launch_bounds__(64) ek_process_heating(const CcuGeom g, const 
     (void)heat_latent;
 }
 
+__global__ void bk_fill_f32(const size_t n, const float v, float *x)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if(i < n) x[i] = v;
+}
+// phase_change (Phase_change.c:43-165), CART3D: Fas = 0.5 (1 + tanh(width * (z_phase - z - clapeyron (T - transT))))
+struct CcuPhase { float zlm, z410, Ra670, clap670, width670, transT670, Ra410, clap410, width410, transT410; };
+// transition temperatures: the layer-average temperature interpolated to the phase depth (:84-110); layer = sums | weights
+__global__ void ek_phase_transT(const CcuGeom g, const float *__restrict__ XX, const double *__restrict__ layer, const float zlm, const float z410, float *transT)
+{
+    if(threadIdx.x > 1 || blockIdx.x) return;
+    const float zp = threadIdx.x == 0 ? zlm : z410;
+    const float *x3 = XX + 2 * (size_t)g.nno;                         // z of nodes 0 .. noz-1 (the first column)
+    double temp1 = 0.0;
+    for(int i = 0; i < g.noz - 1; i++)
+        if(zp <= x3[i + 1] && zp >= x3[i])
+        {
+            const float H0 = (float)(layer[i] / layer[g.noz + i]), H1 = (float)(layer[i + 1] / layer[g.noz + i + 1]);
+            temp1 = (double)(H0 + (H1 - H0) * (zp - x3[i]) / (x3[i + 1] - x3[i]));      // float expression
+            break;
+        }
+    transT[threadIdx.x] = (float)temp1;
+}
+__global__ void __launch_bounds__(256) ek_phase_functions(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ T,
+                                                          const CcuPhase ph, const float *__restrict__ transT, float *Fas670, float *Fas410)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const float z = XX[2 * (size_t)g.nno + n];
+    double ep = (double)(ph.zlm - z - ph.clap670 * (T[n] - transT[0]));                 // float expression
+    Fas670[n] = (float)(0.5 * (1.0 + tanh((double)ph.width670 * ep)));
+    ep = (double)(ph.z410 - z - ph.clap410 * (T[n] - transT[1]));
+    Fas410[n] = (float)(0.5 * (1.0 + tanh((double)ph.width410 * ep)));
+}
+__global__ void __launch_bounds__(256) ek_phase_buoyancy(const int nno, const float Ra670, const float Ra410, const float *__restrict__ Fas670,
+                                                         const float *__restrict__ Fas410, float *buoy)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= nno) return;
+    buoy[n] -= Ra670 * Fas670[n] + Ra410 * Fas410[n];
+}
+// latent-heating part of process_heating (Advection_diffusion.c:889-946): 670 first, then 410, then latent = 1 / latent
+__global__ void __launch_bounds__(64) ek_latent_heating(const CcuGeom g, const float *__restrict__ T, const float *__restrict__ V,
+                                                        const float *__restrict__ Fas670, const float *__restrict__ Fas410, const CcuPhase ph,
+                                                        const float disptn, const float surf_temp, const float Atemp,
+                                                        float *heat_adi, float *heat_latent)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float adi = heat_adi[e], lat = 1.0f;
+    for(int which = 0; which < 2; which++)
+    {
+        const float Ra = which ? ph.Ra410 : ph.Ra670, clap = which ? ph.clap410 : ph.clap670, width = which ? ph.width410 : ph.width670;
+        const float *Fas = which ? Fas410 : Fas670;
+        if(Ra == 0.0f) continue;
+        const double temp1 = 2.0 * width * clap * Ra / Atemp;
+        double temp2 = 0.0, temp3 = 0.0;
+        for(int a = 1; a <= 8; a++)
+        {
+            const int j = elt_node(g, ey, ex, ez, a);
+            const float ts = T[j] + surf_temp;
+            temp2 = temp2 + temp1 * (1.0 - Fas[j]) * Fas[j] * V[2 * (size_t)g.nno + j] * ts * disptn;
+            temp3 = temp3 + temp1 * clap * (1.0 - Fas[j]) * Fas[j] * ts * disptn;
+        }
+        temp2 = temp2 / 8;
+        temp3 = temp3 / 8;
+        adi = (float)((double)adi + temp2);
+        lat = (float)((double)lat + temp3);
+    }
+    heat_adi[e] = adi;
+    heat_latent[e] = (float)(1.0 / lat);
+}
+
 // the scatter DTdot[node] += Eres[a] of pg_solver (:425-429) as a gather in ascending element order, float accumulator
 __global__ void __launch_bounds__(128) ek_gather_residual(const CcuGeom g, const double *__restrict__ Eres, const float *__restrict__ MASS, float *DTdot)
 {
@@ -1270,22 +1344,79 @@ int ccu_set_heating_arrays(ccu_ctx *c, const float *heating_adi, const float *he
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
-// process_heating (Advection_diffusion.c:813) from the resident T, V and EVI[levmax]; outputs optional (float[nel])
-int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
+// phase changes: E->viscosity.{zlm, z410} and E->control.{Ra_670, clapeyron670, width670, Ra_410, clapeyron410, width410} AS THE
+// REFERENCE HOLDS THEM AFTER ITS FIRST phase_change CALL (Phase_change.c:51-67 rescales them once, in place)
+int ccu_set_phase_params(ccu_ctx *c, float zlm, float z410, float Ra_670, float clapeyron670, float width670,
+                         float Ra_410, float clapeyron410, float width410)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    auto &E = c->en;
+    E.ph.zlm = zlm; E.ph.z410 = z410; E.ph.Ra670 = Ra_670; E.ph.clap670 = clapeyron670; E.ph.width670 = width670;
+    E.ph.Ra410 = Ra_410; E.ph.clap410 = clapeyron410; E.ph.width410 = width410;
+    E.phase_on = (Ra_670 != 0.0f || Ra_410 != 0.0f);
+    const size_t nno = (size_t)c->L[c->cfg.levmax].g.nno, nel = (size_t)c->L[c->cfg.levmax].g.nel;
+    if(E.phase_on && !E.Fas670)
+    {
+        CK(cudaMalloc(&E.Fas670, sizeof(float) * nno)); CK(cudaMalloc(&E.Fas410, sizeof(float) * nno));
+        CK(cudaMalloc(&E.transT, sizeof(float) * 2)); CK(cudaMemsetAsync(E.transT, 0, sizeof(float) * 2, c->st));
+        if(!E.heat_adi) { CK(cudaMalloc(&E.heat_adi, sizeof(float) * nel)); CK(cudaMemsetAsync(E.heat_adi, 0, sizeof(float) * nel, c->st)); }
+        if(!E.heat_latent) CK(cudaMalloc(&E.heat_latent, sizeof(float) * nel));
+        LAUNCH(c, bk_fill_f32, cdiv(nel, 256), 256, nel, 1.0f, E.heat_latent);
+    }
+    return 0;
+}
+// phase_change (Phase_change.c:43) on the resident T: the transition temperatures are re-read from the layer-average T
+// when update_transT (the reference: first call and every 10th step, :82), then the nodal phase functions
+int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fas410_out, float *transT_out /*[2]: 670, 410*/)
 {
     if(!c) FAIL("null context");
     if(ensure_energy(c)) return 1;
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
-    if(!(E.adi_heating || E.visc_heating)) return 0;
+    if(!E.phase_on) FAIL("phase_change: ccu_set_phase_params first");
+    if(c->multi()) FAIL("phase_change: multi-subdomain layer averages are not implemented");
+    if(update_transT)
+    {
+        LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->T, E.layer);
+        LAUNCH(c, ek_phase_transT, 1, 32, L.g, (const float *)L.XX, (const double *)E.layer, E.ph.zlm, E.ph.z410, E.transT);
+    }
+    CcuPhase ph; ph.zlm = E.ph.zlm; ph.z410 = E.ph.z410; ph.Ra670 = E.ph.Ra670; ph.clap670 = E.ph.clap670; ph.width670 = E.ph.width670;
+    ph.Ra410 = E.ph.Ra410; ph.clap410 = E.ph.clap410; ph.width410 = E.ph.width410; ph.transT670 = 0; ph.transT410 = 0;
+    LAUNCH(c, ek_phase_functions, cdiv(L.g.nno, 256), 256, L.g, (const float *)L.XX, (const float *)c->T, ph, (const float *)E.transT, E.Fas670, E.Fas410);
+    const size_t nno = (size_t)L.g.nno;
+    if(Fas670_out) CK(cudaMemcpyAsync(Fas670_out, E.Fas670, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
+    if(Fas410_out) CK(cudaMemcpyAsync(Fas410_out, E.Fas410, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
+    if(transT_out) CK(cudaMemcpyAsync(transT_out, E.transT, sizeof(float) * 2, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+// process_heating (Advection_diffusion.c:813) from the resident T, V and EVI[levmax]; outputs optional (float[nel])
+int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
+{   // (heating_latent: ccu_get_heating_latent)
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    auto &E = c->en;
+    Level &L = c->L[c->cfg.levmax];
+    if(!(E.adi_heating || E.visc_heating || E.phase_on)) return 0;
     if(!E.have_v) FAIL("process_heating: velocity missing (ccu_set_velocity / ccu_v_from_vector)");
     if(E.visc_heating && !L.have_evi) FAIL("process_heating: viscosity missing");
     if(!E.have_params) FAIL("process_heating: ccu_set_energy_params first (expansivity)");
-    LAUNCH(c, ek_process_heating, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.EVI, c->T, E.V, E.expansivity, E.adi_heating, E.visc_heating,
-           E.disptn, E.surf_temp, E.Atemp_heat, E.heat_adi, E.heat_visc, (float *)nullptr);
+    if(E.adi_heating || E.visc_heating)
+        LAUNCH(c, ek_process_heating, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.EVI, c->T, E.V, E.expansivity, E.adi_heating, E.visc_heating,
+               E.disptn, E.surf_temp, E.Atemp_heat, E.heat_adi, E.heat_visc, (float *)nullptr);
+    if(E.phase_on)
+    {   // latent heating from the phase functions of the last phase_change call (the reference reads E->Fas670 / Fas410 as they stand)
+        CcuPhase ph; ph.zlm = E.ph.zlm; ph.z410 = E.ph.z410; ph.Ra670 = E.ph.Ra670; ph.clap670 = E.ph.clap670; ph.width670 = E.ph.width670;
+        ph.Ra410 = E.ph.Ra410; ph.clap410 = E.ph.clap410; ph.width410 = E.ph.width410; ph.transT670 = 0; ph.transT410 = 0;
+        if(!E.adi_heating) CK(cudaMemsetAsync(E.heat_adi, 0, sizeof(float) * (size_t)L.g.nel, c->st));
+        LAUNCH(c, ek_latent_heating, cdiv(L.g.nel, 64), 64, L.g, (const float *)c->T, (const float *)E.V, (const float *)E.Fas670,
+               (const float *)E.Fas410, ph, E.disptn, E.surf_temp, E.Atemp_heat, E.heat_adi, E.heat_latent);
+    }
     const size_t nel = (size_t)L.g.nel;
     if(heating_adi_out) CK(cudaMemcpyAsync(heating_adi_out, E.heat_adi, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
-    if(heating_visc_out) CK(cudaMemcpyAsync(heating_visc_out, E.heat_visc, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
+    if(heating_visc_out && E.heat_visc) CK(cudaMemcpyAsync(heating_visc_out, E.heat_visc, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));
     return 0;
@@ -1464,6 +1595,11 @@ int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
     if(!E.have_params || !L.have_xx) FAIL("thermal_buoyancy: energy parameters / coordinates missing");
     if(c->mk.ready) LAUNCH(c, ek_buoyancy_comp, cdiv(L.g.nno, 256), 256, L.g, Atemp, c->mk.Acomp, (const float *)c->T, (const float *)c->mk.C, (const float *)E.expansivity, c->buoy);
     else LAUNCH(c, ek_buoyancy, cdiv(L.g.nno, 256), 256, L.g, Atemp, (const float *)c->T, (const float *)E.expansivity, c->buoy);
+    if(E.phase_on)
+    {   // phase_change + buoyancy -= Ra_670 Fas670 + Ra_410 Fas410 (Pan_problem_misc_functions.c:129-134)
+        if(ccu_phase_change(c, (E.step % 10 == 0) ? 1 : 0, nullptr, nullptr, nullptr)) return 1;
+        LAUNCH(c, ek_phase_buoyancy, cdiv(L.g.nno, 256), 256, L.g.nno, E.ph.Ra670, E.ph.Ra410, (const float *)E.Fas670, (const float *)E.Fas410, c->buoy);
+    }
     LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->buoy, E.layer);
     if(c->multi())
     {   // return_horiz_ave sums over the ranks of one horizontal plane (same z position); here: slot me_z of a global table
@@ -1472,6 +1608,20 @@ int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
     LAUNCH(c, ek_remove_layer_ave, cdiv(L.g.nno, 256), 256, L.g, (const double *)E.layer, c->buoy);
     if(buoyancy_out) CK(cudaMemcpyAsync(buoyancy_out, c->buoy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_set_step(ccu_ctx *c, int solution_cycles)
+{
+    if(!c) FAIL("null context");
+    c->en.step = solution_cycles;
+    return 0;
+}
+int ccu_get_heating_latent(ccu_ctx *c, float *heating_latent_out)
+{
+    if(!c) FAIL("null context");
+    if(!c->en.heat_latent) FAIL("get_heating_latent: no phase changes configured");
+    CK(cudaMemcpyAsync(heating_latent_out, c->en.heat_latent, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nel, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }

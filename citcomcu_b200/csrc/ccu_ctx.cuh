@@ -103,6 +103,10 @@ struct ccu_ctx
         float *diffusivity = nullptr, *expansivity = nullptr;      // [noz]
         float *heat_adi = nullptr, *heat_visc = nullptr, *heat_latent = nullptr;   // [nel] process_heating; null = 0, 0, 1
         int adi_heating = 0, visc_heating = 0; float disptn = 0.0f, surf_temp = 0.0f, Atemp_heat = 1.0f;
+        // phase changes (Phase_change.c): rescaled parameters, nodal phase functions, transition temperatures {670, 410}
+        struct { float zlm = 0, z410 = 0, Ra670 = 0, clap670 = 0, width670 = 0, Ra410 = 0, clap410 = 0, width410 = 0; } ph;
+        bool phase_on = false; float *Fas670 = nullptr, *Fas410 = nullptr, *transT = nullptr;
+        int step = 0;                                              // E->monitor.solution_cycles (ccu_set_step)
         double *Eres = nullptr;                                    // [nel][8] element residuals
         double *layer = nullptr;                                   // [2][noz] layer sums of remove_horiz_ave
         float *red = nullptr;                                      // device scalars: [0] min, [1] max

@@ -342,6 +342,30 @@ class StokesContext:
                                               C.c_float(surf_temp), C.c_float(Atemp)))
         self._heating = bool(adi_heating or visc_heating)
 
+    def set_phase_params(self, zlm, z410, Ra_670, clapeyron670, width670, Ra_410, clapeyron410, width410):
+        """Phase-change parameters as the reference holds them after its first phase_change call (Phase_change.c:51-67)."""
+        f = C.c_float
+        check(self.lib.ccu_set_phase_params(self._ctx, f(zlm), f(z410), f(Ra_670), f(clapeyron670), f(width670), f(Ra_410),
+                                            f(clapeyron410), f(width410)))
+        self._heating = True
+
+    def set_step(self, solution_cycles):
+        self._step = int(solution_cycles)
+        check(self.lib.ccu_set_step(self._ctx, self._step))
+
+    def phase_change(self, update_transT=True):
+        """phase_change (Phase_change.c:43): returns (Fas670, Fas410, (transT670, transT410))."""
+        n = self.nno(self.levmax)
+        a, b, t = np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32), np.empty(2, dtype=np.float32)
+        check(self.lib.ccu_phase_change(self._ctx, int(update_transT), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                        t.ctypes.data_as(C.c_void_p)))
+        return a, b, t
+
+    def get_heating_latent(self):
+        out = np.empty(self.nel(self.levmax), dtype=np.float32)
+        check(self.lib.ccu_get_heating_latent(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def process_heating(self, want_host=True):
         """process_heating (Advection_diffusion.c:813): returns (heating_adi, heating_visc) float32[nel] or None."""
         nel = self.nel(self.levmax)
@@ -455,6 +479,7 @@ class StokesContext:
         from the previous solution, v_from_vector, and with markers the second next_buoyancy_field call.  Returns dt."""
         if getattr(self, "_heating", False):
             self.process_heating(want_host=False)           # Citcom.c:116, before next_buoyancy_field
+        self.set_step(getattr(self, "_step", 0) + 1)        # E->monitor.solution_cycles++ (Citcom.c:120)
         if composition:
             dt = self.PG_timestep_particle(Atemp)
         else:

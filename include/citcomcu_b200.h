@@ -201,6 +201,16 @@ int ccu_set_heating_params(ccu_ctx *ctx, int adi_heating, int visc_heating, floa
  * element heating terms from the resident T, velocity and EVI[levmax]; they enter pg_solver's element residuals
  * (Advection_diffusion.c:643-647).  heating_*_out: float[nel] or NULL */
 int ccu_process_heating(ccu_ctx *ctx, float *heating_adi_out, float *heating_visc_out);
+/* phase changes (Phase_change.c:43): E->viscosity.{zlm, z410}, E->control.{Ra_670, clapeyron670, width670, Ra_410, clapeyron410,
+ * width410} as the reference holds them AFTER its first phase_change call (it rescales them once, in place, :51-67).
+ * ccu_set_step = E->monitor.solution_cycles (transition temperatures are re-read every 10th step, :82).  With phase changes
+ * configured, ccu_thermal_buoyancy evaluates the phase functions and subtracts Ra*Fas (Pan_problem_misc_functions.c:129), and
+ * ccu_process_heating adds the latent-heating terms (Advection_diffusion.c:889-946).  Cartesian, one subdomain. */
+int ccu_set_phase_params(ccu_ctx *ctx, float zlm, float z410, float Ra_670, float clapeyron670, float width670,
+                         float Ra_410, float clapeyron410, float width410);
+int ccu_set_step(ccu_ctx *ctx, int solution_cycles);
+int ccu_phase_change(ccu_ctx *ctx, int update_transT, float *Fas670_out /*[nno] or NULL*/, float *Fas410_out, float *transT_out /*[2] or NULL*/);
+int ccu_get_heating_latent(ccu_ctx *ctx, float *heating_latent_out /*[nel]*/);
 /* upload E->heating_adi+1, E->heating_visc+1, E->heating_latent+1 (float[nel], any may be NULL) when the reference's own
  * process_heating computed them on the host (phase-change latent heating is not evaluated on the device) */
 int ccu_set_heating_arrays(ccu_ctx *ctx, const float *heating_adi, const float *heating_visc, const float *heating_latent);

@@ -144,6 +144,14 @@ static void dump_fields(struct All_variables *E, const char *tag)
         snprintf(nm, sizeof nm, "%s_heating_latent", tag); DUMP_F32(nm, E->heating_latent + 1, nel);
         snprintf(nm, sizeof nm, "%s_eba", tag); DUMP_F64(nm, eb, 4);
     }
+    if(E->control.Ra_670 != 0.0 || E->control.Ra_410 != 0.0)
+    {   /* phase functions of the last phase_change call (Phase_change.c:43) and its (rescaled) parameters */
+        double ph[10] = { E->viscosity.zlm, E->viscosity.z410, E->control.Ra_670, E->control.clapeyron670, E->control.width670,
+                          E->control.transT670, E->control.Ra_410, E->control.clapeyron410, E->control.width410, E->control.transT410 };
+        snprintf(nm, sizeof nm, "%s_Fas670", tag); DUMP_F32(nm, E->Fas670 + 1, nno);
+        snprintf(nm, sizeof nm, "%s_Fas410", tag); DUMP_F32(nm, E->Fas410 + 1, nno);
+        snprintf(nm, sizeof nm, "%s_phase", tag); DUMP_F64(nm, ph, 10);
+    }
     {
         double sc[8] = { E->monitor.elapsed_time, E->advection.timestep, E->slice.Nut, E->slice.Nub,
                          E->monitor.T_interior, (double)E->monitor.solution_cycles, E->monitor.vdotv, E->monitor.pdotp };

@@ -153,3 +153,62 @@ def test_coupled_timesteps_with_heating(eba_state):
         adi, visc = ctx.process_heating() if step < 3 else (None, None)
         if adi is not None:   # the terms the NEXT step will use, against the reference's next-step dump
             assert np.linalg.norm(adi - d[f"s{step + 1}_heating_adi"]) <= 2e-3 * np.linalg.norm(d[f"s{step + 1}_heating_adi"])
+
+
+@pytest.fixture(scope="module")
+def phase_state():
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    text = inputfile.tdepv_box(16, 16, 8, 3, maxstep=4, adi_heating=1, visc_heating=1, dissipation_number=0.5, accuracy=1e-6,
+                               Ra_410=100.0, Ra_670=-100.0)
+    dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_phase_")), nsteps=3, kat=True)
+    d = dumps[0]
+    prob = CartesianProblem(text)
+    ctx = context_from_problem(prob)
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    eb, ph = d["s1_eba"], d["s1_phase"]
+    ctx.set_heating_params(1, 1, eb[0], eb[1], eb[2])
+    ctx.set_phase_params(ph[0], ph[1], ph[2], ph[3], ph[4], ph[6], ph[7], ph[8])
+    yield d, prob, ctx, float(adv[5])
+    ctx.close()
+
+
+def test_phase_change_and_latent_heating(phase_state):
+    """phase_change on the reference's step-0 temperature (phase functions, transition temperatures), the latent-heating
+    terms process_heating derives from them, and the buoyancy with the phase term."""
+    d, prob, ctx, Atemp = phase_state
+    load_s0(d, ctx)
+    ctx.set_element_viscosity(prob.levmax, d["s0_EVI"])
+    ph = d["s0_phase"]
+    F6, F4, tT = ctx.phase_change(update_transT=True)
+    assert abs(tT[0] - ph[5]) <= 1e-5 * abs(ph[5]) and abs(tT[1] - ph[9]) <= 1e-5 * abs(ph[9])
+    assert np.abs(F6 - d["s0_Fas670"]).max() <= 1e-5 and np.abs(F4 - d["s0_Fas410"]).max() <= 1e-5
+    assert d["s0_Fas670"].min() < 0.1 and d["s0_Fas670"].max() > 0.9            # the transition is inside the box
+    adi, visc = ctx.process_heating()
+    lat = ctx.get_heating_latent()
+    assert np.abs(lat - d["s1_heating_latent"]).max() <= 1e-5
+    assert np.linalg.norm(adi - d["s1_heating_adi"]) <= 1e-4 * np.linalg.norm(d["s1_heating_adi"])
+    ctx.set_step(0)
+    b = ctx.thermal_buoyancy(Atemp)
+    assert np.abs(b - d["s0_buoyancy"]).max() <= 1e-5 * np.abs(d["s0_buoyancy"]).max()
+
+
+def test_coupled_timesteps_with_phase_changes(phase_state):
+    d, prob, ctx, Atemp = phase_state
+    ctl = prob.control
+    kw = dict(augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"])
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_tdot(None)
+    ctx.set_step(0)
+    ctx.thermal_buoyancy(Atemp, want_host=False)           # also leaves the step-0 phase functions resident
+    ctx.general_stokes_solver(None, None, rebuild=1, guess=0, want_host=False, **kw)
+    ctx.v_from_vector(want_host=False)
+    for step in (1, 2, 3):
+        dt, its = ctx.advance(Atemp, rebuild=1, **kw)
+        T = ctx.get_temperature()
+        ref = d[f"s{step}_T"]
+        assert abs(dt - d[f"s{step}_scalars"][1]) <= 2e-3 * d[f"s{step}_scalars"][1]
+        assert np.linalg.norm(T - ref) <= 1e-3 * np.linalg.norm(ref)
