@@ -1344,6 +1344,23 @@ int ccu_set_heating_arrays(ccu_ctx *c, const float *heating_adi, const float *he
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
+// return_horiz_ave across subdomains (Global_operations.c:205-238): the layer sums of the ranks that share a z position
+// (the reference's horizontal sub-communicator) are added.  One allreduce over ALL ranks of a table with one slot per z
+// position does the same: every rank adds its sums into slot me_z, and reads that slot back.
+static int layer_allreduce(ccu_ctx *c)
+{
+    if(!c->multi()) return 0;
+    auto &E = c->en;
+    const CcuComm *m = c->comm;
+    const int noz = c->L[c->cfg.levmax].g.noz, npz = m->nproc[2], mez = m->me[2];
+    const size_t slot = 2 * (size_t)noz;
+    if(!E.layer_tab) CK(cudaMalloc(&E.layer_tab, sizeof(double) * slot * npz));
+    CK(cudaMemsetAsync(E.layer_tab, 0, sizeof(double) * slot * npz, c->st));
+    CK(cudaMemcpyAsync(E.layer_tab + slot * mez, E.layer, sizeof(double) * slot, cudaMemcpyDeviceToDevice, c->st));
+    if(ccu_allreduce_buffer(c, E.layer_tab, (int)(slot * npz), 0)) return 1;
+    CK(cudaMemcpyAsync(E.layer, E.layer_tab + slot * mez, sizeof(double) * slot, cudaMemcpyDeviceToDevice, c->st));
+    return 0;
+}
 // phase changes: E->viscosity.{zlm, z410} and E->control.{Ra_670, clapeyron670, width670, Ra_410, clapeyron410, width410} AS THE
 // REFERENCE HOLDS THEM AFTER ITS FIRST phase_change CALL (Phase_change.c:51-67 rescales them once, in place)
 int ccu_set_phase_params(ccu_ctx *c, float zlm, float z410, float Ra_670, float clapeyron670, float width670,
@@ -1375,10 +1392,11 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
     if(!E.phase_on) FAIL("phase_change: ccu_set_phase_params first");
-    if(c->multi()) FAIL("phase_change: multi-subdomain layer averages are not implemented");
+    if(c->multi() && c->comm->nproc[2] > 1) FAIL("phase_change: the transition depth may lie in another z subdomain (sum_across_depth): not implemented");
     if(update_transT)
     {
         LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->T, E.layer);
+        if(layer_allreduce(c)) return 1;
         LAUNCH(c, ek_phase_transT, 1, 32, L.g, (const float *)L.XX, (const double *)E.layer, E.ph.zlm, E.ph.z410, E.transT);
     }
     CcuPhase ph; ph.zlm = E.ph.zlm; ph.z410 = E.ph.z410; ph.Ra670 = E.ph.Ra670; ph.clap670 = E.ph.clap670; ph.width670 = E.ph.width670;
@@ -1601,10 +1619,7 @@ int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
         LAUNCH(c, ek_phase_buoyancy, cdiv(L.g.nno, 256), 256, L.g.nno, E.ph.Ra670, E.ph.Ra410, (const float *)E.Fas670, (const float *)E.Fas410, c->buoy);
     }
     LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->buoy, E.layer);
-    if(c->multi())
-    {   // return_horiz_ave sums over the ranks of one horizontal plane (same z position); here: slot me_z of a global table
-        FAIL("thermal_buoyancy: multi-subdomain layer averages are not implemented yet (pass the buoyancy from the host)");
-    }
+    if(layer_allreduce(c)) return 1;                                   // the ranks of one horizontal plane share their sums
     LAUNCH(c, ek_remove_layer_ave, cdiv(L.g.nno, 256), 256, L.g, (const double *)E.layer, c->buoy);
     if(buoyancy_out) CK(cudaMemcpyAsync(buoyancy_out, c->buoy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());

@@ -64,6 +64,18 @@ def run_rank(rank, world, text, uid_q, out_q, accuracy, agglomerate=True, device
         U, P, its, r = ctx.general_stokes_solver(T, b, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
                                                  precondition=ctl["precondition"], guess=0)
         res["U"], res["P"], res["its"] = U, P, its
+        # two coupled timesteps on the subdomains: energy step, buoyancy with cross-rank layer averages, Stokes solve
+        noz = prob.dims(lm)[2]
+        ctx.set_energy_params(0.75, 0.0, 0.5, 2, np.ones(noz, np.float32), np.ones(noz, np.float32), 0.0)
+        ctx.set_tdot(None)
+        ctx.v_from_vector(want_host=False)
+        kw = dict(augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"])
+        res["dt"] = []
+        for _ in range(2):
+            dt, _its = ctx.advance(float(prob.rayleigh), rebuild=1, **kw)
+            res["dt"].append(float(dt))
+        res["T2"] = ctx.get_temperature()
+        res["b2"] = ctx.thermal_buoyancy(float(prob.rayleigh))
         res["launches"] = ctx.launch_count
         ctx.close()
         out_q.put(res)

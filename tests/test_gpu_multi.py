@@ -83,6 +83,20 @@ def test_two_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
         assert rel(r["gs_Ad"], r["gs_KD"]) < 1e-12
     Ug, Pg, its_g, _ = ctx.general_stokes_solver(Tg, bg, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
                                                  precondition=ctl["precondition"], guess=0)
+    # the same two coupled timesteps on the single GPU (energy -> buoyancy -> Stokes): T and buoyancy agree to the solver tolerance
+    noz = gp.dims(lm)[2]
+    ctx.set_energy_params(0.75, 0.0, 0.5, 2, np.ones(noz, np.float32), np.ones(noz, np.float32), 0.0)
+    ctx.set_tdot(None)
+    ctx.v_from_vector(want_host=False)
+    kwg = dict(augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"], precondition=ctl["precondition"])
+    dts = [float(ctx.advance(float(gp.rayleigh), rebuild=1, **kwg)[0]) for _ in range(2)]
+    T2g = ctx.get_temperature()
+    b2g = ctx.thermal_buoyancy(float(gp.rayleigh))
+    for r in res:
+        prob = CartesianProblem(text, me_loc=r["me"])
+        assert np.allclose(r["dt"], dts, rtol=1e-5)
+        assert np.abs(r["T2"] - prob.local_slice(T2g)).max() < 1e-5
+        assert np.abs(r["b2"] - prob.local_slice(b2g)).max() < 1e-5 * np.abs(b2g).max()
     ctx.close()
     num_u = den_u = num_p = den_p = 0.0
     for r in res:
