@@ -15,6 +15,9 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <algorithm>
+#include <cub/device/device_partition.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #define CCU_F_VBX 1
 #define CCU_F_VBY 2
@@ -955,6 +958,79 @@ __global__ void __launch_bounds__(256) mk_clamp(const int n, const int cap, cons
         X[(size_t)d * cap + i] = v;
     }
 }
+// ---- markers changing subdomain (transfer_markers_processors, Composition_adv.c:148-226)
+// locate_processor (:628-669) for the markers of side elements (move_tracers_to_neighbors :382-420): the subdomain one step
+// up / down per axis when the (clamped) position lies beyond the local mesh.  code = (ox+1) + 3 (oy+1) + 9 (oz+1); 13 = stays.
+#define CCU_MK_REC 8             // doubles per migrating marker: XMC[3], XMCpred[3], {VO0, VO1}, {VO2, C12}
+__global__ void __launch_bounds__(256) mk_dest(const int n, const int cap, const unsigned *__restrict__ Element, const int *__restrict__ CElement,
+                                               const double *__restrict__ X, const double lo0, const double lo1, const double lo2,
+                                               const double hi0, const double hi1, const double hi2, const int me0, const int me1, const int me2,
+                                               const int np0, const int np1, const int np2, unsigned char *code, unsigned char *stay)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    int c = 13;
+    if(Element[CElement[i] - 1] & CCU_SIDEE)
+    {
+        const double lo[3] = { lo0, lo1, lo2 }, hi[3] = { hi0, hi1, hi2 };
+        const int me[3] = { me0, me1, me2 }, np[3] = { np0, np1, np2 };
+        int o[3];
+        for(int d = 0; d < 3; d++)
+        {
+            const double v = X[(size_t)d * cap + i];
+            int m = me[d];
+            if(v > hi[d]) m = min(np[d] - 1, me[d] + 1);
+            else if(v < lo[d]) m = max(0, me[d] - 1);
+            o[d] = m - me[d];
+        }
+        c = (o[0] + 1) + 3 * (o[1] + 1) + 9 * (o[2] + 1);
+    }
+    code[i] = (unsigned char)c;
+    stay[i] = (unsigned char)(c == 13);
+}
+// leavers (perm[n_stay .. n) in reverse order of their original index) -> (index, code) pairs for the host's stable sort
+__global__ void mk_leaver_list(const int n, const int n_stay, const int *__restrict__ perm, const unsigned char *__restrict__ code, int *lv_idx, int *lv_code)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= n - n_stay) return;
+    const int i = perm[n - 1 - q];
+    lv_idx[q] = i; lv_code[q] = code[i];
+}
+__global__ void mk_pack(const int nl, const int cap, const int *__restrict__ idx, const double *__restrict__ X, const double *__restrict__ Xpred,
+                        const float *__restrict__ VO, const int *__restrict__ C12, double *buf)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= nl) return;
+    const int i = idx[q];
+    double *r = buf + (size_t)q * CCU_MK_REC;
+    for(int d = 0; d < 3; d++) { r[d] = X[(size_t)d * cap + i]; r[3 + d] = Xpred[(size_t)d * cap + i]; }
+    float *f = (float *)(r + 6);
+    f[0] = VO[i]; f[1] = VO[(size_t)cap + i]; f[2] = VO[2 * (size_t)cap + i];
+    ((int *)f)[3] = C12[i];
+}
+__global__ void mk_unpack(const int nr, const int cap, const int first, const double *__restrict__ buf, double *X, double *Xpred, float *VO, int *C12, int *CElement)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= nr) return;
+    const int i = first + q;
+    const double *r = buf + (size_t)q * CCU_MK_REC;
+    for(int d = 0; d < 3; d++) { X[(size_t)d * cap + i] = r[d]; Xpred[(size_t)d * cap + i] = r[3 + d]; }
+    const float *f = (const float *)(r + 6);
+    VO[i] = f[0]; VO[(size_t)cap + i] = f[1]; VO[2 * (size_t)cap + i] = f[2];
+    C12[i] = ((const int *)f)[3];
+    CElement[i] = 1;                 // element_markers assigns it from the position next
+}
+// stayers keep their relative order: arrays gathered through the partition's permutation
+template <class T, int ND>
+__global__ void mk_gather(const int n_stay, const int cap, const int *__restrict__ perm, const T *__restrict__ src, T *dst)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= n_stay) return;
+    const int i = perm[q];
+#pragma unroll
+    for(int d = 0; d < ND; d++) dst[(size_t)d * cap + q] = src[(size_t)d * cap + i];
+}
+
 // element_markers (Composition_adv.c:960-985) + the per-element counts of get_C_from_markers (:757-760)
 __global__ void __launch_bounds__(128) mk_assign_count(const CcuGeom g, const MkGrid m, const int n, const int cap, const double *__restrict__ X,
                                                        const int *__restrict__ C12, int *CElement, int *count, int *err)
@@ -998,7 +1074,7 @@ __global__ void __launch_bounds__(128) mk_nodal_C(const CcuGeom g, const float *
             }
         }
     }
-    C[n] = acc * MASS[n];
+    C[n] = MASS ? acc * MASS[n] : acc;
 }
 // thermo-chemical buoyancy (Pan_problem_misc_functions.c:125-128): Atemp*T*expansivity - Acomp*C
 __global__ void __launch_bounds__(256) ek_buoyancy_comp(const CcuGeom g, const float Atemp, const float Acomp, const float *__restrict__ T,
@@ -1656,7 +1732,6 @@ int ccu_markers_setup(ccu_ctx *c, int capacity, int markers_per_ele, int rnoz, c
                       const int *RG3, const double *XG1, const double *XG2, const unsigned *Element, float Acomp)
 {
     if(!c) FAIL("null context");
-    if(c->multi()) FAIL("markers: marker exchange between subdomains is not implemented in this build");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &M = c->mk;
@@ -1745,44 +1820,185 @@ int ccu_markers_download(ccu_ctx *c, double *X, double *Xpred, float *VO, float 
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
-// transfer_marker_properties (Composition_adv.c:682-704), one subdomain: clamp, element_markers, get_C_from_markers
-static int mk_transfer(ccu_ctx *c, const MkGrid &m, double *Xuse)
+// ---- transfer_marker_properties (Composition_adv.c:682-704): clamp, [markers to their new subdomain], element_markers,
+// get_C_from_markers
+static int mk_scratch(ccu_ctx *c)
+{
+    auto &M = c->mk;
+    if(M.code) return 0;
+    const size_t cap = (size_t)M.cap;
+    CK(cudaMalloc(&M.code, cap)); CK(cudaMalloc(&M.stayf, cap));
+    CK(cudaMalloc(&M.perm, sizeof(int) * cap)); CK(cudaMalloc(&M.lv_idx, sizeof(int) * cap)); CK(cudaMalloc(&M.lv_code, sizeof(int) * cap));
+    CK(cudaMalloc(&M.nsel, sizeof(int)));
+    CK(cudaMalloc(&M.sX, sizeof(double) * 3 * cap)); CK(cudaMalloc(&M.sXpred, sizeof(double) * 3 * cap));
+    CK(cudaMalloc(&M.sVO, sizeof(float) * 3 * cap)); CK(cudaMalloc(&M.sVpred, sizeof(float) * 3 * cap));
+    CK(cudaMalloc(&M.sC12, sizeof(int) * cap)); CK(cudaMalloc(&M.sCElement, sizeof(int) * cap));
+    CK(cudaMalloc(&M.sendbuf, sizeof(double) * CCU_MK_REC * cap)); CK(cudaMalloc(&M.recvbuf, sizeof(double) * CCU_MK_REC * cap));
+    M.cub_bytes = 0;
+    cub::DevicePartition::Flagged(nullptr, M.cub_bytes, thrust::counting_iterator<int>(0), M.stayf, M.perm, M.nsel, M.cap, c->st);
+    CK(cudaMalloc(&M.cub_tmp, M.cub_bytes));
+    return 0;
+}
+static bool mk_decomposed(const ccu_ctx *c) { return c->mk.np[0] * c->mk.np[1] * c->mk.np[2] > 1; }
+// clamp + split: markers that now belong to a neighbouring subdomain are packed into M.sendbuf grouped by destination
+// code (ascending, original order inside a group); the others are compacted in place, order kept.  sendcnt[27] on the host.
+static int mk_clamp_split(ccu_ctx *c, double *&Xuse, const double ends[6], int sendcnt[27])
+{
+    auto &M = c->mk;
+    const int n = M.n;
+    const bool usePred = (Xuse == M.Xpred);
+    LAUNCH(c, mk_clamp, cdiv(n, 256), 256, n, M.cap, (const unsigned *)M.Element, (const int *)M.CElement, M.XG1[0], M.XG1[1], M.XG1[2], M.XG2[0],
+           M.XG2[1], M.XG2[2], Xuse);
+    for(int q = 0; q < 27; q++) sendcnt[q] = 0;
+    if(!mk_decomposed(c)) return 0;
+    if(mk_scratch(c)) return 1;
+    LAUNCH(c, mk_dest, cdiv(n, 256), 256, n, M.cap, (const unsigned *)M.Element, (const int *)M.CElement, (const double *)Xuse, ends[0], ends[2], ends[4],
+           ends[1], ends[3], ends[5], M.me[0], M.me[1], M.me[2], M.np[0], M.np[1], M.np[2], M.code, M.stayf);
+    size_t bytes = M.cub_bytes;
+    CK(cub::DevicePartition::Flagged(M.cub_tmp, bytes, thrust::counting_iterator<int>(0), M.stayf, M.perm, M.nsel, n, c->st));
+    c->launches++;
+    int n_stay = 0;
+    CK(cudaMemcpyAsync(&n_stay, M.nsel, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const int nl = n - n_stay;
+    if(nl == 0) return 0;
+    // leavers: stable sort by destination on the host (they are a sliver of the markers)
+    LAUNCH(c, mk_leaver_list, cdiv(nl, 256), 256, n, n_stay, (const int *)M.perm, (const unsigned char *)M.code, M.lv_idx, M.lv_code);
+    std::vector<int> idx(nl), code(nl), order(nl);
+    CK(cudaMemcpyAsync(idx.data(), M.lv_idx, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(code.data(), M.lv_code, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for(int q = 0; q < nl; q++) { order[q] = q; sendcnt[code[q]]++; }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+    std::vector<int> sorted(nl);
+    for(int q = 0; q < nl; q++) sorted[q] = idx[order[q]];
+    CK(cudaMemcpyAsync(M.lv_idx, sorted.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, mk_pack, cdiv(nl, 256), 256, nl, M.cap, (const int *)M.lv_idx, (const double *)M.X, (const double *)M.Xpred, (const float *)M.VO,
+           (const int *)M.C12, M.sendbuf);
+    // stayers, order kept
+    LAUNCH(c, (mk_gather<double, 3>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const double *)M.X, M.sX);
+    LAUNCH(c, (mk_gather<double, 3>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const double *)M.Xpred, M.sXpred);
+    LAUNCH(c, (mk_gather<float, 3>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const float *)M.VO, M.sVO);
+    LAUNCH(c, (mk_gather<float, 3>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const float *)M.Vpred, M.sVpred);
+    LAUNCH(c, (mk_gather<int, 1>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const int *)M.C12, M.sC12);
+    LAUNCH(c, (mk_gather<int, 1>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const int *)M.CElement, M.sCElement);
+    CK(cudaStreamSynchronize(c->st));                       // `sorted` must outlive the upload
+    std::swap(M.X, M.sX); std::swap(M.Xpred, M.sXpred); std::swap(M.VO, M.sVO); std::swap(M.Vpred, M.sVpred);
+    std::swap(M.C12, M.sC12); std::swap(M.CElement, M.sCElement);
+    Xuse = usePred ? M.Xpred : M.X;
+    M.n = n_stay;
+    return 0;
+}
+// arrivals (records on the device) appended behind the resident markers
+static int mk_append(ccu_ctx *c, int nrecv, const double *records_dev)
+{
+    auto &M = c->mk;
+    if(nrecv == 0) return 0;
+    if(M.n + nrecv > M.cap) FAIL("markers: number of markers over the limit (markers_uplimit), as the reference's Composition_adv.c:207");
+    LAUNCH(c, mk_unpack, cdiv(nrecv, 256), 256, nrecv, M.cap, M.n, records_dev, M.X, M.Xpred, M.VO, M.C12, M.CElement);
+    M.n += nrecv;
+    return 0;
+}
+static int mk_finish(ccu_ctx *c, const MkGrid &m, double *Xuse)
 {
     Level &L = c->L[c->cfg.levmax];
     auto &M = c->mk;
     const int n = M.n;
-    LAUNCH(c, mk_clamp, cdiv(n, 256), 256, n, M.cap, (const unsigned *)M.Element, (const int *)M.CElement, M.XG1[0], M.XG1[1], M.XG1[2], M.XG2[0],
-           M.XG2[1], M.XG2[2], Xuse);
     CK(cudaMemsetAsync(M.count, 0, sizeof(int) * 2 * (size_t)L.g.nel, c->st));
     LAUNCH(c, mk_assign_count, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)Xuse, (const int *)M.C12, M.CElement, M.count, M.err);
     LAUNCH(c, mk_element_C, cdiv(L.g.nel, 256), 256, L.g.nel, (const int *)M.count, M.CE);
-    LAUNCH(c, mk_nodal_C, cdiv(L.g.nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const float *)M.CE, M.C);
+    if(!c->multi()) LAUNCH(c, mk_nodal_C, cdiv(L.g.nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const float *)M.CE, M.C);
+    else
+    {   // exchange_node_f20 between the element sums and the mass factor (Composition_adv.c:797-800)
+        LAUNCH(c, mk_nodal_C, cdiv(L.g.nno, 128), 128, L.g, (const float *)L.TWW, (const float *)nullptr, (const float *)M.CE, M.C);
+        if(ccu_halo_sum_nodal(c, c->cfg.levmax, M.C)) return 1;
+        LAUNCH(c, bk_mul, cdiv(L.g.nno, 128), 128, L.g.nno, M.C, L.MASS);
+    }
     int err = 0;
     CK(cudaMemcpyAsync(&err, M.err, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if(err) FAIL("markers: " + std::to_string(err) + " marker(s) left the z lookup table (the reference terminates here: '!!!overflow', Composition_adv.c:1176)");
     return 0;
 }
-static int mk_step(ccu_ctx *c, float timestep, int corrector)
+// velocity at the markers and the position update of Euler (corrector = 0) / Runge_Kutta (1); returns the array that holds
+// the positions the transfer works on (XMCpred / XMC)
+static int mk_advect(ccu_ctx *c, float timestep, int corrector, MkGrid &m, double ends[6], double *&Xuse)
 {
     if(!c) FAIL("null context");
     auto &M = c->mk;
     if(!M.ready || M.n == 0) FAIL("markers: no markers resident");
     if(!c->en.have_v) FAIL("markers: a velocity (ccu_v_from_vector / ccu_set_velocity) is needed first");
     Level &L = c->L[c->cfg.levmax];
-    double ends[6];
     if(mk_ends(c, ends)) return 1;
-    const MkGrid m = mk_grid(c, ends);
+    m = mk_grid(c, ends);
     const int n = M.n;
     if(!corrector)
     {
         LAUNCH(c, mk_velocity, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)M.X, (const float *)L.eco, (const float *)c->en.V, M.VO, M.CElement, M.err);
         LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 0, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred);
-        return mk_transfer(c, m, M.Xpred);
+        Xuse = M.Xpred;
+        return 0;
     }
     LAUNCH(c, mk_velocity, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)M.Xpred, (const float *)L.eco, (const float *)c->en.V, M.Vpred, M.CElement, M.err);
     LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 1, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred);
-    return mk_transfer(c, m, M.X);
+    Xuse = M.X;
+    return 0;
 }
+static int mk_step(ccu_ctx *c, float timestep, int corrector)
+{
+    MkGrid m; double ends[6]; double *Xuse = nullptr;
+    if(mk_advect(c, timestep, corrector, m, ends, Xuse)) return 1;
+    auto &M = c->mk;
+    if(c->multi() && !mk_decomposed(c))
+    {   // subdomain-per-GPU run: the decomposition is the communicator's
+        for(int d = 0; d < 3; d++) { M.np[d] = c->comm->nproc[d]; M.me[d] = c->comm->me[d]; }
+    }
+    int sendcnt[27], recvcnt[27], nrecv = 0;
+    if(mk_clamp_split(c, Xuse, ends, sendcnt)) return 1;
+    if(mk_decomposed(c))
+    {
+        if(!c->multi()) FAIL("markers: a decomposition without a communicator: use ccu_markers_step_export / ccu_markers_import_finish");
+        if(ccu_marker_exchange(c, sendcnt, M.sendbuf, CCU_MK_REC, recvcnt, M.recvbuf, (size_t)M.cap, &nrecv)) return 1;
+        if(mk_append(c, nrecv, M.recvbuf)) return 1;
+    }
+    return mk_finish(c, m, Xuse);
+}
+// ---- the same step in two halves with the migrating markers handed over on the host (tests: two subdomains in one process)
+int ccu_markers_set_decomp(ccu_ctx *c, const int nproc[3], const int me[3])
+{
+    if(!c) FAIL("null context");
+    for(int d = 0; d < 3; d++) { c->mk.np[d] = nproc[d]; c->mk.me[d] = me[d]; }
+    return 0;
+}
+int ccu_markers_step_export(ccu_ctx *c, float timestep, int corrector, int sendcnt[27], double *records_out, int max_records)
+{
+    MkGrid m; double ends[6]; double *Xuse = nullptr;
+    if(mk_advect(c, timestep, corrector, m, ends, Xuse)) return 1;
+    if(mk_clamp_split(c, Xuse, ends, sendcnt)) return 1;
+    int nl = 0;
+    for(int q = 0; q < 27; q++) nl += sendcnt[q];
+    if(nl > max_records) FAIL("markers_step_export: record buffer too small");
+    if(nl) CK(cudaMemcpyAsync(records_out, c->mk.sendbuf, sizeof(double) * CCU_MK_REC * nl, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+int ccu_markers_import_finish(ccu_ctx *c, int corrector, int nrecv, const double *records)
+{
+    if(!c) FAIL("null context");
+    auto &M = c->mk;
+    if(!M.ready) FAIL("markers: ccu_markers_setup first");
+    if(nrecv)
+    {
+        if(mk_scratch(c)) return 1;
+        if(nrecv > M.cap) FAIL("markers_import_finish: more records than the capacity");
+        CK(cudaMemcpyAsync(M.recvbuf, records, sizeof(double) * CCU_MK_REC * nrecv, cudaMemcpyHostToDevice, c->st));
+        if(mk_append(c, nrecv, M.recvbuf)) return 1;
+    }
+    double ends[6];
+    if(mk_ends(c, ends)) return 1;
+    const MkGrid m = mk_grid(c, ends);
+    return mk_finish(c, m, corrector ? M.X : M.Xpred);
+}
+int ccu_markers_count(ccu_ctx *c) { return c ? c->mk.n : -1; }
 int ccu_Euler(ccu_ctx *c, float timestep) { return mk_step(c, timestep, 0); }
 int ccu_Runge_Kutta(ccu_ctx *c, float timestep) { return mk_step(c, timestep, 1); }

@@ -291,7 +291,7 @@ void ccu_comm_destroy(ccu_ctx *c)
         cudaFree(H.sh_s); cudaFree(H.sh_n); cudaFree(H.sh_ptr); cudaFree(H.sh_src); cudaFree(H.send_s); cudaFree(H.send_n); cudaFree(H.send_t);
         cudaFree(H.bits); cudaFree(H.face);
     }
-    cudaFree(m->sendbuf); cudaFree(m->recvbuf); cudaFree(m->dotstage);
+    cudaFree(m->sendbuf); cudaFree(m->recvbuf); cudaFree(m->dotstage); cudaFree(m->mk_counts);
     if(m->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m->nccl);
     delete m;
     c->comm = nullptr;
@@ -371,5 +371,47 @@ int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_ran
     CcuComm *m = c->comm;
     if(!m || m->nranks == 1) { CK(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, c->st)); return 0; }
     NK(g_nccl.AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t)m->nccl, c->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ markers changing subdomain
+// exchange_number_rec_markers + exchange_markers (Composition_adv.c:421-560): every rank learns how many records each
+// neighbour sends it (one all-gather of the 27 per-direction counts), then one grouped send/recv round moves the records.
+// Neighbour code = (ox+1) + 3 (oy+1) + 9 (oz+1) of the offset (ox, oy, oz); what rank R at offset o sends to me sits
+// under R's code for the opposite offset, 26 - code.  Received records are stored in ascending code order.
+int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv)
+{
+    CcuComm *m = c->comm;
+    for(int q = 0; q < 27; q++) recvcnt[q] = 0;
+    *nrecv = 0;
+    if(!m || m->nranks == 1) return 0;
+    if(!m->mk_counts) CK(cudaMalloc(&m->mk_counts, sizeof(int) * 27 * (size_t)(m->nranks + 1)));
+    int *mine = m->mk_counts, *all = m->mk_counts + 27;
+    CK(cudaMemcpyAsync(mine, sendcnt, sizeof(int) * 27, cudaMemcpyHostToDevice, c->st));
+    NK(g_nccl.AllGather(mine, all, 27 * sizeof(int), ncclChar, (ncclComm_t)m->nccl, c->st));
+    std::vector<int> h(27 * (size_t)m->nranks);
+    CK(cudaMemcpyAsync(h.data(), all, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    int nb[27];
+    for(int code = 0; code < 27; code++)
+    {
+        const int ox = code % 3 - 1, oy = (code / 3) % 3 - 1, oz = code / 9 - 1;
+        const int x = m->me[0] + ox, y = m->me[1] + oy, z = m->me[2] + oz;
+        nb[code] = -1;
+        if(code == 13 || x < 0 || y < 0 || z < 0 || x >= m->nproc[0] || y >= m->nproc[1] || z >= m->nproc[2]) continue;
+        nb[code] = ccu_rank_of(m->nproc, x, y, z);
+        recvcnt[code] = h[(size_t)nb[code] * 27 + (26 - code)];
+        *nrecv += recvcnt[code];
+    }
+    if((size_t)*nrecv > cap_records) FAIL("markers: more arriving markers than the capacity (markers_uplimit)");
+    NK(g_nccl.GroupStart());
+    size_t soff = 0, roff = 0;
+    for(int code = 0; code < 27; code++)
+    {
+        if(nb[code] >= 0 && sendcnt[code]) NK(g_nccl.Send(sendbuf + soff * rec, (size_t)sendcnt[code] * rec, ncclDouble, nb[code], (ncclComm_t)m->nccl, c->st));
+        if(nb[code] >= 0 && recvcnt[code]) NK(g_nccl.Recv(recvbuf + roff * rec, (size_t)recvcnt[code] * rec, ncclDouble, nb[code], (ncclComm_t)m->nccl, c->st));
+        soff += sendcnt[code]; roff += recvcnt[code];
+    }
+    NK(g_nccl.GroupEnd());
     return 0;
 }

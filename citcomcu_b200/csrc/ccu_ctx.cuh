@@ -61,6 +61,7 @@ struct CcuComm
     CcuHalo halo[CCU_MAX_LEVELS];
     void *sendbuf = nullptr, *recvbuf = nullptr;
     double *dotstage = nullptr;
+    int *mk_counts = nullptr;        // [27] own + [nranks][27] gathered per-direction counts of migrating markers
     long long gneq = 0, gnpno = 0;   // global equation / pressure counts (E->mesh.neq, E->mesh.npno)
 };
 
@@ -130,6 +131,13 @@ struct ccu_ctx
         int *err = nullptr;                              // device error counter (markers that fell out of the z table)
         double XG1[3] = { 0, 0, 0 }, XG2[3] = { 0, 0, 0 };
         float Acomp = 0.0f;
+        // markers changing subdomain (transfer_markers_processors): decomposition, classification / partition scratch,
+        // second set of marker arrays (the stayers are gathered into it and the sets swapped), record buffers
+        int np[3] = { 1, 1, 1 }, me[3] = { 0, 0, 0 };
+        unsigned char *code = nullptr, *stayf = nullptr; int *perm = nullptr, *lv_idx = nullptr, *lv_code = nullptr, *nsel = nullptr;
+        void *cub_tmp = nullptr; size_t cub_bytes = 0;
+        double *sX = nullptr, *sXpred = nullptr; float *sVO = nullptr, *sVpred = nullptr; int *sC12 = nullptr, *sCElement = nullptr;
+        double *sendbuf = nullptr, *recvbuf = nullptr;
         bool ready = false;
     } mk;
     long long launches = 0;
@@ -190,6 +198,8 @@ int ccu_allreduce_dots(ccu_ctx *c, int count, double *o0, double *o1, double *o2
 int ccu_allreduce_buffer(ccu_ctx *c, double *buf, int count, int op_max);
 int ccu_damp_face_BI(ccu_ctx *c, int lev);
 int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_rank);
+// variable-size exchange of records (`rec` doubles each, grouped by neighbour code in sendbuf) with the up to 26 neighbours
+int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv);
 int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of all subdomains -> coarse replica (ccu_stokes.cu)                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);
 int ccu_tile_refresh(ccu_ctx *c, int lev);

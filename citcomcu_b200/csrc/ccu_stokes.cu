@@ -129,6 +129,12 @@ void ccu_destroy(ccu_ctx *c)
     if(c->own_stream) cudaStreamDestroy(c->own_stream);
     for(auto &r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for(auto e : c->prof_pool) cudaEventDestroy(e);
+    {   // marker migration scratch
+        auto &M = c->mk;
+        cudaFree(M.code); cudaFree(M.stayf); cudaFree(M.perm); cudaFree(M.lv_idx); cudaFree(M.lv_code); cudaFree(M.nsel); cudaFree(M.cub_tmp);
+        cudaFree(M.sX); cudaFree(M.sXpred); cudaFree(M.sVO); cudaFree(M.sVpred); cudaFree(M.sC12); cudaFree(M.sCElement);
+        cudaFree(M.sendbuf); cudaFree(M.recvbuf);
+    }
     cudaFree(c->forceEF); cudaFree(c->coop_bar);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;

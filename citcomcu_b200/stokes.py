@@ -445,7 +445,7 @@ class StokesContext:
 
     def markers_download(self):
         """dict with XMC, XMCpred (float64 [3, n]), VO, Vpred (float32 [3, n]), CElement, C (nodal), CE (elemental)."""
-        n, lm = self._nmarkers, self.levmax
+        n, lm = self.markers_count(), self.levmax
         out = dict(XMC=np.empty((3, n)), XMCpred=np.empty((3, n)), VO=np.empty((3, n), np.float32), Vpred=np.empty((3, n), np.float32),
                    CElement=np.empty(n, np.int32), C=np.empty(self.nno(lm), np.float32), CE=np.empty(self.nel(lm), np.float32))
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
@@ -460,6 +460,25 @@ class StokesContext:
         check(self.lib.ccu_Runge_Kutta(self._ctx, C.c_float(timestep)))
 
     # -- one pass of main()'s time loop (Citcom.c:111-161), everything resident on the device
+    # -- markers changing subdomain, host hand-over variant (two subdomains in one process; see citcomcu_b200.h)
+    def markers_set_decomp(self, nproc, me):
+        a, b = (C.c_int * 3)(*nproc), (C.c_int * 3)(*me)
+        check(self.lib.ccu_markers_set_decomp(self._ctx, a, b))
+
+    def markers_step_export(self, timestep, corrector, max_records=1 << 20):
+        cnt = (C.c_int * 27)()
+        rec = np.empty(8 * max_records, dtype=np.float64)
+        check(self.lib.ccu_markers_step_export(self._ctx, C.c_float(timestep), int(corrector), cnt, rec.ctypes.data_as(C.c_void_p), int(max_records)))
+        cnt = np.array(cnt[:], dtype=np.int64)
+        return cnt, rec[:8 * int(cnt.sum())].reshape(-1, 8).copy()
+
+    def markers_import_finish(self, corrector, records):
+        r = np.ascontiguousarray(records, dtype=np.float64).reshape(-1, 8)
+        check(self.lib.ccu_markers_import_finish(self._ctx, int(corrector), int(r.shape[0]), r.ctypes.data_as(C.c_void_p)))
+
+    def markers_count(self):
+        return int(self.lib.ccu_markers_count(self._ctx))
+
     def PG_timestep_particle(self, Atemp):
         """PG_timestep_particle (Advection_diffusion.c:128): alternates, like the reference's static `on_off`, between
         (0) std_timestep + thermal step + Euler marker predictor and (1) the Runge_Kutta marker corrector with the new

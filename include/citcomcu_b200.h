@@ -245,6 +245,18 @@ int ccu_markers_download(ccu_ctx *ctx, double *X, double *Xpred, float *VO, floa
 int ccu_Euler(ccu_ctx *ctx, float timestep);
 /* Runge_Kutta (Composition_adv.c:61): velocity at XMCpred, XMC += dt/2 (VO + Vpred), transfer_marker_properties */
 int ccu_Runge_Kutta(ccu_ctx *ctx, float timestep);
+/* Subdomain-per-GPU runs (after ccu_comm_init): ccu_Euler / ccu_Runge_Kutta also move the markers that left the subdomain
+ * to the neighbour that now holds them (transfer_markers_processors, Composition_adv.c:148: locate_processor :628 on the
+ * markers of side elements, counts exchanged with one all-gather, records {XMC, XMCpred, VO, C12} in one grouped NCCL
+ * send/recv round) and sum the nodal composition across subdomains (exchange_node_f20, :797).
+ * The same step in two halves, with the migrating records handed over on the host -- two subdomains in ONE process for
+ * tests and for bindings that keep the reference's MPI for the markers: records are 8 doubles per marker
+ * {XMC[3], XMCpred[3], (float VO0, VO1), (float VO2, int C12)}, grouped by neighbour code (ox+1) + 3 (oy+1) + 9 (oz+1),
+ * sendcnt[code] of them each. */
+int ccu_markers_set_decomp(ccu_ctx *ctx, const int nproc[3], const int me[3]);
+int ccu_markers_step_export(ccu_ctx *ctx, float timestep, int corrector, int sendcnt[27], double *records_out, int max_records);
+int ccu_markers_import_finish(ccu_ctx *ctx, int corrector, int nrecv, const double *records);
+int ccu_markers_count(ccu_ctx *ctx);
 
 /* ---- CUDA-event timing of the finest-level kernels inside a solve (bench.py's live roofline) ---- */
 /* classes: finest-level smoother (units = colour-pass launches), finest-level matvec / residual (units = products),

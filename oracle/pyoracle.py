@@ -82,7 +82,8 @@ class Dump:
 
 
 def run_harness(input_text: str, workdir, nsteps: int = 0, kat: bool = False, nproc: int = 1,
-                preload: str | None = None, timeout: float = 600.0, quiet: bool = True, setup_only: bool = False):
+                preload: str | None = None, timeout: float = 600.0, quiet: bool = True, setup_only: bool = False,
+                marker_kat: bool = False):
     """Run the reference through ref_harness in `workdir`; returns (list of Dump per rank, stderr text)."""
     workdir = Path(workdir)
     (workdir / "out").mkdir(parents=True, exist_ok=True)
@@ -92,6 +93,8 @@ def run_harness(input_text: str, workdir, nsteps: int = 0, kat: bool = False, np
     env["CCU_MPI_NP"] = str(nproc)
     if preload:
         env["LD_PRELOAD"] = preload
+    if marker_kat:
+        env["CCU_MARKER_KAT"] = "1"          # only the marker known answers (the operator KATs are single-rank)
     if setup_only:
         env["CCU_SETUP_ONLY"] = "1"
     cmd = [str(REFDIR / "ref_harness"), "dump", "in.input", "dump", str(nsteps)] + (["kat"] if kat else [])

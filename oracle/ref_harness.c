@@ -411,7 +411,7 @@ int main(int argc, char **argv)
         snprintf(tag, sizeof tag, "s%d", step);
         dump_fields(&E, tag);
     }
-    if(E.control.composition && E.advection.markers > 0 && want_kat)
+    if(E.control.composition && E.advection.markers > 0 && (want_kat || getenv("CCU_MARKER_KAT")))
     {   /* marker known answers on the final state: the lookup tables, then Euler and Runge_Kutta (Composition_adv.c:108,61)
          * with the current velocity, exactly as PG_timestep_particle calls them (Advection_diffusion.c:229,162) */
         const int nm = E.advection.markers, nno = E.lmesh.nno, nel = E.lmesh.nel;
@@ -427,19 +427,28 @@ int main(int argc, char **argv)
         DUMP_I32("mk_in_C12", E.C12 + 1, nm); DUMP_I32("mk_in_CElement", E.CElement + 1, nm); DUMP_F32("mk_in_CE", E.CE + 1, nel);
         for(d = 1; d <= 3; d++) { snprintf(nm_, sizeof nm_, "mk_in_V%d", d); DUMP_F32(nm_, E.V[d] + 1, nno); }
         Euler(&E, E.C, E.V, 0);
+        {   /* several ranks: markers changed owner inside Euler (transfer_markers_processors), the count with them */
+            const int nm = E.advection.markers;
+            dump_scalar_i("mk_euler_nmarkers", nm);
+            for(d = 1; d <= 3; d++) { snprintf(nm_, sizeof nm_, "mk_euler_XMC%d", d); DUMP_F64(nm_, E.XMC[d] + 1, nm); }
+            DUMP_I32("mk_euler_C12", E.C12 + 1, nm);
         for(d = 1; d <= 3; d++)
         {
             snprintf(nm_, sizeof nm_, "mk_euler_XMCpred%d", d); DUMP_F64(nm_, E.XMCpred[d] + 1, nm);
             snprintf(nm_, sizeof nm_, "mk_euler_VO%d", d); DUMP_F32(nm_, E.VO[d] + 1, nm);
         }
-        DUMP_I32("mk_euler_CElement", E.CElement + 1, nm); DUMP_F32("mk_euler_C", E.C + 1, nno); DUMP_F32("mk_euler_CE", E.CE + 1, nel);
+        DUMP_I32("mk_euler_CElement", E.CElement + 1, nm);
+        } DUMP_F32("mk_euler_C", E.C + 1, nno); DUMP_F32("mk_euler_CE", E.CE + 1, nel);
         Runge_Kutta(&E, E.C, E.V, 1);
+        {
+            const int nm = E.advection.markers;
         for(d = 1; d <= 3; d++)
         {
             snprintf(nm_, sizeof nm_, "mk_rk_XMC%d", d); DUMP_F64(nm_, E.XMC[d] + 1, nm);
             snprintf(nm_, sizeof nm_, "mk_rk_Vpred%d", d); DUMP_F32(nm_, E.Vpred[d] + 1, nm);
         }
-        DUMP_I32("mk_rk_CElement", E.CElement + 1, nm); DUMP_F32("mk_rk_C", E.C + 1, nno); DUMP_F32("mk_rk_CE", E.CE + 1, nel);
+        DUMP_I32("mk_rk_CElement", E.CElement + 1, nm);
+        } DUMP_F32("mk_rk_C", E.C + 1, nno); DUMP_F32("mk_rk_CE", E.CE + 1, nel);
         dump_scalar_i("mk_rk_nmarkers", E.advection.markers);
     }
     fclose(g_manifest);

@@ -82,3 +82,38 @@ def run_rank(rank, world, text, uid_q, out_q, accuracy, agglomerate=True, device
     except Exception as e:  # surface the failure in the parent instead of hanging it
         import traceback
         out_q.put({"rank": rank, "error": f"{e}\n{traceback.format_exc()}"})
+
+
+def run_rank_markers(rank, world, text, uid_q, out_q, setup):
+    """Marker Euler / Runge_Kutta across subdomains over NCCL: `setup` = this rank's arrays of the reference dump."""
+    try:
+        from citcomcu_b200 import decomp
+        from citcomcu_b200.problem import CartesianProblem
+        from citcomcu_b200.stokes import StokesContext, context_from_problem
+        nproc = CartesianProblem(text).nproc
+        me = decomp.me_loc_of(rank, nproc)
+        prob = CartesianProblem(text, me_loc=me)
+        if rank == 0:
+            uid = StokesContext.comm_unique_id()
+            for _ in range(world - 1):
+                uid_q.put(uid)
+        else:
+            uid = uid_q.get(timeout=120)
+        ctx = context_from_problem(prob, device=rank, unique_id=uid, agglomerate=False)
+        d = setup
+        ip, dp = d["mk_ints"], d["mk_doubles"]
+        ctx.markers_setup(int(ip[3]), int(ip[1]), int(ip[0]), d["mk_XP1"], d["mk_XP2"], d["mk_XP3"], d["mk_RG3"], dp[0:3], dp[3:6],
+                          d["mk_Element"], Acomp=float(dp[7]))
+        ctx.markers_upload(d["mk_in_XMC1"], d["mk_in_XMC2"], d["mk_in_XMC3"], d["mk_in_C12"], d["mk_in_CElement"], d["mk_in_CE"])
+        ctx.set_velocity(d["mk_in_V1"], d["mk_in_V2"], d["mk_in_V3"])
+        dt = np.float32(dp[6])
+        res = {"rank": rank}
+        ctx.Euler(dt)
+        res["euler"] = ctx.markers_download()
+        ctx.Runge_Kutta(dt)
+        res["rk"] = ctx.markers_download()
+        ctx.close()
+        out_q.put(res)
+    except Exception as e:
+        import traceback
+        out_q.put({"rank": rank, "error": f"{e}\n{traceback.format_exc()}"})

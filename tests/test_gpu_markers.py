@@ -100,3 +100,72 @@ def test_coupled_thermochemical_timesteps(state):
             assert np.abs(m["XMC"][a] - d[f"s{step}_XMC{a + 1}"]).max() <= 1e-3 * h
         assert (m["CElement"] == d[f"s{step}_CElement"]).mean() >= 0.99
         assert np.abs(m["C"] - d[f"s{step}_C"]).mean() <= 1e-3
+
+
+# ---------------------------------------------------------------- markers changing subdomain (transfer_markers_processors)
+MK_TEXT = dict(elx=16, ely=16, elz=8, levels=3, nproc=(2, 1, 1), maxstep=4, composition=1, rayleigh_comp=5e6, markers_per_ele=8,
+               comp_depth=0.4, accuracy=1e-6)
+
+
+def _mk_text():
+    k = dict(MK_TEXT)
+    return inputfile.tdepv_box(k.pop("elx"), k.pop("ely"), k.pop("elz"), k.pop("levels"), **k)
+
+
+def _rows(a):
+    a = np.asarray(a)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def _setup_rank(ctx, d, nproc, me):
+    ip, dp = d["mk_ints"], d["mk_doubles"]
+    ctx.markers_setup(int(ip[3]), int(ip[1]), int(ip[0]), d["mk_XP1"], d["mk_XP2"], d["mk_XP3"], d["mk_RG3"], dp[0:3], dp[3:6],
+                      d["mk_Element"], Acomp=float(dp[7]))
+    if nproc is not None:
+        ctx.markers_set_decomp(nproc, me)
+    ctx.markers_upload(d["mk_in_XMC1"], d["mk_in_XMC2"], d["mk_in_XMC3"], d["mk_in_C12"], d["mk_in_CElement"], d["mk_in_CE"])
+    ctx.set_velocity(d["mk_in_V1"], d["mk_in_V2"], d["mk_in_V3"])
+
+
+def _check_rank(m, d, tag, key):
+    n_ref = int(d[f"mk_{tag}_nmarkers"][0])
+    assert m["CElement"].size == n_ref
+    ours = np.stack([m[key][a] for a in range(3)] + [m["CElement"].astype(np.float64)], 1)
+    ref = np.stack([d[f"mk_{tag}_{key}{a + 1}"] for a in range(3)] + [d[f"mk_{tag}_CElement"].astype(np.float64)], 1)
+    assert np.array_equal(_rows(ours), _rows(ref))            # the same markers (bit-exact positions), in the same elements
+    assert np.array_equal(m["CE"], d[f"mk_{tag}_CE"])
+
+
+def test_markers_change_subdomain_two_subdomains_one_process():
+    """Two subdomains of the 2-rank reference run, both on this GPU, migrating markers handed over on the host: after Euler
+    and after Runge_Kutta every subdomain holds exactly the reference rank's markers (multiset of bit-exact positions and
+    elements) and its elemental composition."""
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    from citcomcu_b200 import decomp
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    text = _mk_text()
+    dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_mk2_")), nsteps=2, marker_kat=True, nproc=2, timeout=300)
+    nproc = MK_TEXT["nproc"]
+    ctxs = []
+    for r, d in enumerate(dumps):
+        me = decomp.me_loc_of(r, nproc)
+        ctx = context_from_problem(CartesianProblem(text, me_loc=me))
+        _setup_rank(ctx, d, nproc, me)
+        ctxs.append(ctx)
+    dt = np.float32(dumps[0]["mk_doubles"][6])
+    moved = 0
+    for corrector, tag, key in ((0, "euler", "XMCpred"), (1, "rk", "XMC")):
+        outs = [ctx.markers_step_export(dt, corrector) for ctx in ctxs]
+        for r, ctx in enumerate(ctxs):
+            cnt, rec = outs[1 - r]
+            code = 14 if r == 1 else 12                        # the sender's code of the +x / -x neighbour
+            assert cnt.sum() == cnt[code]
+            ctx.markers_import_finish(corrector, rec)
+            moved += int(cnt.sum())
+        for ctx, d in zip(ctxs, dumps):
+            _check_rank(ctx.markers_download(), d, tag, key)
+    assert moved > 0
+    for ctx in ctxs:
+        ctx.close()

@@ -117,3 +117,34 @@ def test_two_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
             num_u += ((r["U"] - d["s0_U"]) ** 2).sum(); den_u += (d["s0_U"] ** 2).sum()
             num_p += ((r["P"] - d["s0_P"]) ** 2).sum(); den_p += (d["s0_P"] ** 2).sum()
         assert np.sqrt(num_u / den_u) < 1e-6 and np.sqrt(num_p / den_p) < 1e-6
+
+
+@pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
+def test_markers_change_subdomain_over_nccl():
+    """Euler and Runge_Kutta of the marker field on two GPUs: migrating markers travel over NCCL, the nodal composition is
+    summed across the interface; every rank ends with exactly the reference rank's markers, CE and (within 2 ulp) C."""
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    import torch.multiprocessing as mp
+    from mgpu_worker import run_rank_markers
+    from test_gpu_markers import _mk_text, _check_rank
+    text = _mk_text()
+    dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_mk2n_")), nsteps=2, marker_kat=True, nproc=2, timeout=300)
+    keys = ["mk_ints", "mk_doubles", "mk_XP1", "mk_XP2", "mk_XP3", "mk_RG3", "mk_Element", "mk_in_XMC1", "mk_in_XMC2", "mk_in_XMC3",
+            "mk_in_C12", "mk_in_CElement", "mk_in_CE", "mk_in_V1", "mk_in_V2", "mk_in_V3"]
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=run_rank_markers, args=(r, 2, text, uid_q, out_q, {k: np.array(dumps[r][k]) for k in keys})) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for r in res:
+        assert "error" not in r, r["error"]
+    for r in sorted(res, key=lambda r: r["rank"]):
+        d = dumps[r["rank"]]
+        _check_rank(r["euler"], d, "euler", "XMCpred")
+        _check_rank(r["rk"], d, "rk", "XMC")
+        for tag in ("euler", "rk"):
+            assert np.abs(r[tag]["C"] - d[f"mk_{tag}_C"]).max() <= 4 * np.finfo(np.float32).eps
