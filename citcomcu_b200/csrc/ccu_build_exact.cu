@@ -866,6 +866,106 @@ __global__ void __launch_bounds__(256) ek_remove_layer_ave(const CcuGeom g, cons
     if(layer[g.noz + kz] != 0.0) X[n] = X[n] - (float)(layer[kz] / layer[g.noz + kz]);
 }
 
+// ================================================================= diagnostics: heat_flux (Process_buoyancy.c:63-203), Nusselt numbers
+// per element: uT = sum_gp (u_z T - kappa dT/dz) gDA / area  (:105-131), area = ECO.area (Size_does_matter.c:712)
+__global__ void __launch_bounds__(64) hf_element(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ T, const float *__restrict__ V,
+                                                 const float *__restrict__ diffusivity, double *uT_out, float *area_out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8], gnx[3][8];
+    double VZ[8], Tn[8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        VZ[a - 1] = (double)V[2 * (size_t)g.nno + n];
+        Tn[a - 1] = (double)T[n];
+    }
+    const double diff = (double)((diffusivity[ez] + diffusivity[ez + 1]) * 0.5);
+    double uT = 0.0, area = 0.0;
+    for(int i = 0; i < 8; i++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + i, 64, 8, gnx);
+        double u = 0.0, Tg = 0.0, dTdz = 0.0;
+        for(int j = 0; j < 8; j++)
+        {
+            u += VZ[j] * c_sh.Nv[8 * j + i];
+            Tg += Tn[j] * c_sh.Nv[8 * j + i];
+            dTdz = dTdz + Tn[j] * (double)gnx[2][j];
+        }
+        uT = uT + (u * Tg - diff * dTdz) * (double)gda;
+        area += 1.0 * (double)gda;
+    }
+    const float areaf = (float)area;
+    uT /= (double)areaf;
+    uT_out[e] = uT;
+    area_out[e] = areaf;
+}
+// heatflux[node] += TWW * uT in ascending element order (float accumulator, :133-138); * Mass unless halo sums come first
+__global__ void __launch_bounds__(128) hf_nodal(const CcuGeom g, const float *__restrict__ TWW, const float *__restrict__ MASS,
+                                                const double *__restrict__ uT, float *hf)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    float acc = 0.0f;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                acc = (float)((double)acc + (double)TWW[(size_t)e * 8 + LUT[k - ez][j - ex][i - ey] - 1] * uT[e]);
+            }
+        }
+    }
+    hf[n] = MASS ? acc * MASS[n] : acc;
+}
+// surface / bottom extrapolation (:151-158) and the area-weighted sums over the surface elements (:162-176): out[0..3] =
+// hfb, areab, hft, areat of this subdomain (zero where it does not touch the bottom / top of the box)
+__global__ void __launch_bounds__(256) hf_surface_sums(const CcuGeom g, const float *__restrict__ hf, const float *__restrict__ area,
+                                                       const int at_bottom, const int at_top, double *out)
+{
+    double s[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for(int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.elx * g.ely; t += gridDim.x * blockDim.x)
+    {
+        const int ex = t % g.elx, ey = t / g.elx;
+        double tempb = 0.0, tempt = 0.0;
+        for(int q = 0; q < 4; q++)
+        {
+            const int j = ex + (q & 1), i = ey + (q >> 1);
+            const size_t col = (size_t)g.noz * (j + (size_t)g.nox * i);
+            const float sh = 2 * hf[col + g.noz - 1] - hf[col + g.noz - 2];
+            const float bh = 2 * hf[col] - hf[col + 1];
+            tempt += (double)sh; tempb += (double)bh;
+        }
+        const size_t eb = (size_t)g.elz * (ex + (size_t)g.elx * ey), et = eb + g.elz - 1;
+        if(at_bottom) { s[0] += tempb * (double)area[eb]; s[1] += (double)area[eb]; }
+        if(at_top) { s[2] += tempt * (double)area[et]; s[3] += (double)area[et]; }
+    }
+    __shared__ double sh[4][8];
+    for(int q = 0; q < 4; q++)
+    {
+        double v = s[q];
+        for(int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if(threadIdx.x < 4)
+    {
+        double v = 0.0;
+        for(int w = 0; w < 8; w++) v += sh[threadIdx.x][w];
+        out[threadIdx.x] = v;
+    }
+}
+
 // ================================================================= markers
 #define CCU_SIDEE 0x800000u
 struct MkGrid
@@ -1714,6 +1814,34 @@ int ccu_get_heating_latent(ccu_ctx *c, float *heating_latent_out)
     if(!c->en.heat_latent) FAIL("get_heating_latent: no phase changes configured");
     CK(cudaMemcpyAsync(heating_latent_out, c->en.heat_latent, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nel, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+// heat_flux (Process_buoyancy.c:63-203): Nusselt numbers at the top and bottom of the box from the resident T and velocity
+int ccu_heat_flux(ccu_ctx *c, float *Nut_out, float *Nub_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c) || energy_ready(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    const size_t nel = (size_t)L.g.nel, nno = (size_t)L.g.nno;
+    if(!E.hf) { CK(cudaMalloc(&E.hf, sizeof(float) * nno)); CK(cudaMalloc(&E.hf_area, sizeof(float) * nel)); CK(cudaMalloc(&E.hf_sums, sizeof(double) * 4)); }
+    LAUNCH(c, hf_element, cdiv(nel, 64), 64, L.g, (const float *)L.XX, (const float *)c->T, (const float *)E.V, (const float *)E.diffusivity, E.Eres, E.hf_area);
+    int at_bottom = 1, at_top = 1;
+    if(!c->multi()) LAUNCH(c, hf_nodal, cdiv(nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const double *)E.Eres, E.hf);
+    else
+    {
+        LAUNCH(c, hf_nodal, cdiv(nno, 128), 128, L.g, (const float *)L.TWW, (const float *)nullptr, (const double *)E.Eres, E.hf);
+        if(ccu_halo_sum_nodal(c, c->cfg.levmax, E.hf)) return 1;                   // exchange_node_f20 (:141)
+        LAUNCH(c, bk_mul, cdiv(nno, 128), 128, L.g.nno, E.hf, L.MASS);
+        at_bottom = c->comm->me[2] == 0; at_top = c->comm->me[2] == c->comm->nproc[2] - 1;
+    }
+    LAUNCH(c, hf_surface_sums, 1, 256, L.g, (const float *)E.hf, (const float *)E.hf_area, at_bottom, at_top, E.hf_sums);
+    if(ccu_allreduce_buffer(c, E.hf_sums, 4, 0)) return 1;                          // return_horiz_sum over every plane = global sum
+    double h[4];
+    CK(cudaMemcpyAsync(h, E.hf_sums, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if(Nub_out) *Nub_out = (float)((float)h[0] / ((float)h[1] * 4));               // inp[] / outp[] are float (:62,178-186)
+    if(Nut_out) *Nut_out = (float)((float)h[2] / ((float)h[3] * 4));
     return 0;
 }
 int ccu_get_temperature(ccu_ctx *c, float *T, float *Tdot)

@@ -110,6 +110,7 @@ struct ccu_ctx
         int step = 0;                                              // E->monitor.solution_cycles (ccu_set_step)
         double *Eres = nullptr;                                    // [nel][8] element residuals
         double *layer = nullptr;                                   // [2][noz] layer sums of remove_horiz_ave
+        float *hf = nullptr, *hf_area = nullptr; double *hf_sums = nullptr;   // heat_flux diagnostics
         double *layer_tab = nullptr;                               // [nprocz][2][noz] allreduce table of multi-subdomain runs
         float *red = nullptr;                                      // device scalars: [0] min, [1] max
         float fine_tune_dt = 0.9f, fixed_timestep = 0.0f, gamma = 0.5f, Q0 = 0.0f, diff_timestep = -1.0f;

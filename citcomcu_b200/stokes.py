@@ -416,6 +416,12 @@ class StokesContext:
         check(self.lib.ccu_thermal_buoyancy(self._ctx, C.c_float(Atemp), None if out is None else out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def heat_flux(self):
+        """heat_flux (Process_buoyancy.c:63): returns (Nut, Nub)."""
+        a, b = C.c_float(), C.c_float()
+        check(self.lib.ccu_heat_flux(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def get_temperature(self, want_tdot=False):
         T = np.empty(self.nno(self.levmax), dtype=np.float32)
         Td = np.empty_like(T) if want_tdot else None
@@ -586,20 +592,20 @@ def context_from_dump(dump, **overrides) -> StokesContext:
 AGG_NODES = 30000      # multigrid levels whose GLOBAL mesh has at most this many nodes are solved replicated on every rank
 
 
-def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, **overrides) -> StokesContext:
+def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, communicator=True, **overrides) -> StokesContext:
     """Build a context for one subdomain of a `citcomcu_b200.problem.CartesianProblem`: mesh, flags and
     coordinates go up, every operator array is then constructed on the device (ccu_build_geometry here,
     viscosity / stiffness at the first general_stokes_solver call)."""
     kw = {k: prob.control[k] for k in ("v_steps_low", "v_steps_high", "down_heavy", "up_heavy", "mg_cycle", "p_iterations", "accuracy")}
     kw.update(overrides)
     ctx = StokesContext(prob.levmin, prob.levmax, prob.nox, prob.noy, prob.noz, device=device, **kw)
-    if prob.nproc != (1, 1, 1):
+    if prob.nproc != (1, 1, 1) and communicator:      # communicator=False: a lone subdomain (tests hand data over on the host)
         ctx.comm_init(prob.nproc, prob.me_loc, unique_id)
     for lev in range(prob.levmin, prob.levmax + 1):
         ctx.set_node_flags(lev, prob.node_flags(lev))
         ctx.set_coordinates(lev, *prob.coordinates(lev))
     ctx.build_geometry()
-    if prob.nproc != (1, 1, 1) and agglomerate:
+    if prob.nproc != (1, 1, 1) and agglomerate and communicator:
         gp = prob.global_problem()
         levs = [lev for lev in range(prob.levmin, prob.levmax) if gp.nno(lev) <= AGG_NODES]
         if levs:

@@ -228,6 +228,10 @@ int ccu_PG_timestep(ccu_ctx *ctx, float *T, float *Tdot, float *dt_out, float *T
  * (remove_horiz_ave / return_horiz_ave, Global_operations.c:55,133); updates the resident buoyancy; host copy optional */
 int ccu_thermal_buoyancy(ccu_ctx *ctx, float Atemp, float *buoyancy_out /*[nno] or NULL*/);
 int ccu_get_temperature(ccu_ctx *ctx, float *T /*[nno]*/, float *Tdot /*[nno] or NULL*/);
+/* heat_flux (Process_buoyancy.c:63-203): the Nusselt numbers E->slice.Nut / Nub from the resident temperature and velocity
+ * (element heat transport, nodal projection through TWW / Mass, linear extrapolation to the top and bottom surfaces,
+ * area-weighted means); across subdomains the nodal sums and the four surface sums are reduced over NCCL */
+int ccu_heat_flux(ccu_ctx *ctx, float *Nut_out, float *Nub_out);
 
 /* ---- markers of the compositional field (Composition_adv.c), Cartesian, one subdomain ----
  * E->advection.markers / markers_uplimit / markers_per_ele, E->lmesh.rnoz, E->XP[d]+1 (double[nox|noy|noz]), E->RG[3]
