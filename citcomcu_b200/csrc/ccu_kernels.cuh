@@ -646,7 +646,16 @@ __host__ inline CcuStencil ccu_make_stencil(const CcuGeom &g)
     }
     return st;
 }
-template <int U>
+// streaming load of a coefficient that this SM will not touch again: do not let it displace the neighbour values in L1
+__device__ __forceinline__ float ccu_ldg_na(const float *p)
+{
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// NA: 0 = every coefficient load allocates in L1 (__ldg); 1 = the node's own blocks stream past L1 (each is read once per
+// pass by this SM; the transposed blocks, which sibling warps fetch as their own, still allocate); 2 = all stream past L1
+template <int U, int NA = 0>
 __device__ __forceinline__ void ccu_row_product_tab(const size_t NS, const int *__restrict__ off, const float *__restrict__ K,
                                                     const double *x, const int s, double &a0, double &a1, double &a2)
 {
@@ -658,7 +667,7 @@ __device__ __forceinline__ void ccu_row_product_tab(const size_t NS, const int *
         const float *Kp = K + (size_t)(b * 9) * NS + s;
         float k[9];
 #pragma unroll
-        for(int e = 0; e < 9; e++) k[e] = __ldg(Kp + (size_t)e * NS);
+        for(int e = 0; e < 9; e++) k[e] = NA >= 1 ? ccu_ldg_na(Kp + (size_t)e * NS) : __ldg(Kp + (size_t)e * NS);
         const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
         r0 += (double)k[0] * x0 + (double)k[1] * x1 + (double)k[2] * x2;
         r1 += (double)k[3] * x0 + (double)k[4] * x1 + (double)k[5] * x2;
@@ -671,7 +680,7 @@ __device__ __forceinline__ void ccu_row_product_tab(const size_t NS, const int *
         const float *Kp = K + (size_t)((b - 13) * 9) * NS + sm;
         float k[9];
 #pragma unroll
-        for(int e = 0; e < 9; e++) k[e] = __ldg(Kp + (size_t)e * NS);
+        for(int e = 0; e < 9; e++) k[e] = NA >= 2 ? ccu_ldg_na(Kp + (size_t)e * NS) : __ldg(Kp + (size_t)e * NS);
         const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
         r0 += (double)k[0] * x0 + (double)k[3] * x1 + (double)k[6] * x2;
         r1 += (double)k[1] * x0 + (double)k[4] * x1 + (double)k[7] * x2;
@@ -679,7 +688,7 @@ __device__ __forceinline__ void ccu_row_product_tab(const size_t NS, const int *
     }
     a0 = r0; a1 = r1; a2 = r2;
 }
-template <int MODE, int U>
+template <int MODE, int U, int NA = 0>
 __global__ void __launch_bounds__(256) ccu_k_matvec_tab(const CcuGeom g, const __grid_constant__ CcuStencil st, const float *__restrict__ K,
                                                          const unsigned char *__restrict__ flags, const double *u,
                                                          const double *rhs, double *out, const int strip)
@@ -692,7 +701,7 @@ __global__ void __launch_bounds__(256) ccu_k_matvec_tab(const CcuGeom g, const _
     const size_t NS = (size_t)g.NS;
     const int s = c * g.NC + cell;
     double a0, a1, a2;
-    ccu_row_product_tab<U>(NS, st.off[c], K, u, s, a0, a1, a2);
+    ccu_row_product_tab<U, NA>(NS, st.off[c], K, u, s, a0, a1, a2);
     if(strip)
     {
         const unsigned char f = flags[s];
@@ -704,7 +713,7 @@ __global__ void __launch_bounds__(256) ccu_k_matvec_tab(const CcuGeom g, const _
     else { out[s] = rhs[s] - a0; out[NS + s] = rhs[NS + s] - a1; out[2 * NS + s] = rhs[2 * NS + s] - a2; }
 }
 // one colour pass of the smoother with the same table-driven row (colour = kernel argument)
-template <int U>
+template <int U, int NA = 0>
 __global__ void __launch_bounds__(128) ccu_k_relax_tab(const CcuGeom g, const __grid_constant__ CcuStencil st, const int c,
                                                         const float *__restrict__ K, const double *__restrict__ BI,
                                                         const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
@@ -716,7 +725,7 @@ __global__ void __launch_bounds__(128) ccu_k_relax_tab(const CcuGeom g, const __
     const int s = c * g.NC + cell;
     if(bits && (bits[s] & CCU_B_SHARED)) return;
     double a0, a1, a2;
-    ccu_row_product_tab<U>((size_t)g.NS, st.off[c], K, x, s, a0, a1, a2);
+    ccu_row_product_tab<U, NA>((size_t)g.NS, st.off[c], K, x, s, a0, a1, a2);
     ccu_relax_update(g, BI, F, x, s, a0, a1, a2);
 }
 

@@ -439,6 +439,8 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
     if(use_tile(c, L, c->opt_matvec_tile)) launch_tile_shape<1>(c, L, 0, nullptr, const_cast<double *>(u), Au, L.flags, strip);
     else if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
+    else if(c->opt_matvec_tab == 24) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
+    else if(c->opt_matvec_tab == 14) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 1>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab >= 4) LAUNCH(c, (ccu_k_matvec_tab<0, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab) LAUNCH(c, (ccu_k_matvec_tab<0, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
@@ -459,6 +461,8 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
     if(use_tile(c, L, c->opt_matvec_tile)) { launch_tile_shape<2>(c, L, 0, rhs, const_cast<double *>(u), out, L.flags, 1); return; }
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
+    if(c->opt_matvec_tab == 24) { LAUNCH(c, (ccu_k_matvec_tab<1, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
+    if(c->opt_matvec_tab == 14) { LAUNCH(c, (ccu_k_matvec_tab<1, 4, 1>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab >= 4) { LAUNCH(c, (ccu_k_matvec_tab<1, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab) { LAUNCH(c, (ccu_k_matvec_tab<1, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     LAUNCH(c, ccu_k_matvec<1>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, rhs, out, 1);
@@ -666,7 +670,9 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
             const CcuStencil st = ccu_make_stencil(L.g);
             for(int col = 7; col >= 0; col--)
             {
-                if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                if(c->opt_relax_tab == 22) LAUNCH(c, (ccu_k_relax_tab<2, 2>), grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                else if(c->opt_relax_tab == 12) LAUNCH(c, (ccu_k_relax_tab<2, 1>), grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                else if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
                 else if(c->opt_relax_tab >= 4) LAUNCH(c, ccu_k_relax_tab<4>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
                 else LAUNCH(c, ccu_k_relax_tab<2>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
             }
