@@ -76,15 +76,16 @@ def test_PG_timestep_and_buoyancy(state):
 
 
 def test_heat_flux_nusselt_numbers(state):
-    """heat_flux on the reference's state after steps 0 and 1: Nut, Nub within 1e-4 (north star: 0.1 %); the nodal fluxes
-    are float sums and the surface value is the extrapolation 2 f(top) - f(top-1), so a few 1e-5 is rounding."""
+    """heat_flux on the reference's step-0 state (the harness, like the input files' storage_spacing, evaluates it at step 0
+    only): Nut, Nub within 1e-4 (north star: 0.1 %); the nodal fluxes are float sums and the surface value is the
+    extrapolation 2 f(top) - f(top-1), so a few 1e-5 is rounding."""
     d, prob, ctx, _ = state
-    for k in (0, 1):
-        ctx.set_temperature(d[f"s{k}_T"])
-        ctx.set_velocity(d[f"s{k}_V1"], d[f"s{k}_V2"], d[f"s{k}_V3"])
-        nut, nub = ctx.heat_flux()
-        sc = d[f"s{k}_scalars"]
-        assert abs(nut - sc[2]) <= 1e-4 * abs(sc[2]) and abs(nub - sc[3]) <= 1e-4 * abs(sc[3])
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_velocity(d["s0_V1"], d["s0_V2"], d["s0_V3"])
+    nut, nub = ctx.heat_flux()
+    sc = d["s0_scalars"]
+    assert abs(nut - sc[2]) <= 1e-4 * abs(sc[2])
+    assert abs(nub - sc[3]) <= 1e-4 * abs(sc[3])
 
 
 def test_coupled_timesteps_match_reference(state):
