@@ -98,6 +98,21 @@ def test_colour_smoother_stokes_solution_tight():
     assert np.linalg.norm(P - d["s0_P"]) <= 1e-6 * np.linalg.norm(d["s0_P"])
 
 
+def test_tile_ordered_smoother_contracts_like_the_reference(case):
+    """The tile-ordered 8-colour Gauss-Seidel (ccu_r_ordered_gs mode 9, the CPU statement of csrc/ccu_tile.cuh) inside the
+    multigrid cycle: residual after one FMG cycle within 25 % of the plain 8-colour order (better on some meshes, worse on
+    others) and within 1.5x of the reference's lexicographic smoother, for several tile shapes (small ones so this mesh holds many tiles)."""
+    d = case
+    F = d["kat_solve_f"]
+    r_lex = po.Restate(d, smoother=0).multi_grid(F)[2]
+    r_col = po.Restate(d, smoother=1).multi_grid(F)[2]
+    for tile in ((2, 4, 16), (1, 2, 4), (2, 2, 2)):
+        R = po.Restate(d, smoother=19)
+        R.set_tile(*tile)
+        r_tile = R.multi_grid(F)[2]
+        assert r_tile <= 1.25 * r_col and r_tile <= 1.5 * r_lex, (tile, r_tile, r_col, r_lex)
+
+
 def test_golden_scalars_busse1a_survey_values():
     """SURVEY.md section 4 probe values for Busse 1a step 0 (first golden values): momentum residue
     1.93359e-4 over 55539 equations; reproduced by the restated Uzawa on the reference's arrays."""

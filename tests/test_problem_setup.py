@@ -8,7 +8,7 @@ from conftest import get_case, CASES
 from citcomcu_b200.problem import CartesianProblem, BC_MASK, INTX, INTY, INTZ
 
 
-@pytest.mark.parametrize("name", ["busse_l3", "tdepv_l3"])
+@pytest.mark.parametrize("name", ["busse_l3", "tdepv_l3", "input1_cart_l3"])
 def test_setup_matches_reference(name):
     d = get_case(name)[0]
     txt = CASES[name]()[0]
