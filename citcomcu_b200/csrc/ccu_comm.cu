@@ -374,6 +374,23 @@ int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_ran
     return 0;
 }
 
+// host-only routing table of the marker exchange (no GPU needed; tests/test_decomp.py): for the subdomain `me` of an
+// nproc[0] x nproc[1] x nproc[2] grid and the gathered per-direction send counts all_counts[rank][27] of every rank,
+// nb_rank[code] = rank of the neighbour at offset code (-1: none) and recvcnt[code] = records it sends here
+extern "C" int ccu_marker_routes(const int nproc[3], const int me[3], const int *all_counts, int nb_rank[27], int recvcnt[27])
+{
+    for(int code = 0; code < 27; code++)
+    {
+        const int ox = code % 3 - 1, oy = (code / 3) % 3 - 1, oz = code / 9 - 1;
+        const int x = me[0] + ox, y = me[1] + oy, z = me[2] + oz;
+        nb_rank[code] = -1; recvcnt[code] = 0;
+        if(code == 13 || x < 0 || y < 0 || z < 0 || x >= nproc[0] || y >= nproc[1] || z >= nproc[2]) continue;
+        nb_rank[code] = ccu_rank_of(nproc, x, y, z);
+        recvcnt[code] = all_counts[(size_t)nb_rank[code] * 27 + (26 - code)];      // its code for the opposite offset
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ markers changing subdomain
 // exchange_number_rec_markers + exchange_markers (Composition_adv.c:421-560): every rank learns how many records each
 // neighbour sends it (one all-gather of the 27 per-direction counts), then one grouped send/recv round moves the records.
@@ -393,16 +410,8 @@ int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf
     CK(cudaMemcpyAsync(h.data(), all, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     int nb[27];
-    for(int code = 0; code < 27; code++)
-    {
-        const int ox = code % 3 - 1, oy = (code / 3) % 3 - 1, oz = code / 9 - 1;
-        const int x = m->me[0] + ox, y = m->me[1] + oy, z = m->me[2] + oz;
-        nb[code] = -1;
-        if(code == 13 || x < 0 || y < 0 || z < 0 || x >= m->nproc[0] || y >= m->nproc[1] || z >= m->nproc[2]) continue;
-        nb[code] = ccu_rank_of(m->nproc, x, y, z);
-        recvcnt[code] = h[(size_t)nb[code] * 27 + (26 - code)];
-        *nrecv += recvcnt[code];
-    }
+    ccu_marker_routes(m->nproc, m->me, h.data(), nb, recvcnt);
+    for(int code = 0; code < 27; code++) *nrecv += recvcnt[code];
     if((size_t)*nrecv > cap_records) FAIL("markers: more arriving markers than the capacity (markers_uplimit)");
     NK(g_nccl.GroupStart());
     size_t soff = 0, roff = 0;

@@ -261,6 +261,9 @@ int ccu_markers_set_decomp(ccu_ctx *ctx, const int nproc[3], const int me[3]);
 int ccu_markers_step_export(ccu_ctx *ctx, float timestep, int corrector, int sendcnt[27], double *records_out, int max_records);
 int ccu_markers_import_finish(ccu_ctx *ctx, int corrector, int nrecv, const double *records);
 int ccu_markers_count(ccu_ctx *ctx);
+/* host-only routing table of the marker exchange (no GPU needed): neighbour rank and arriving record count per direction
+ * code for subdomain `me`, from the gathered send counts all_counts[rank][27] of all ranks */
+int ccu_marker_routes(const int nproc[3], const int me[3], const int *all_counts, int nb_rank[27], int recvcnt[27]);
 
 /* ---- CUDA-event timing of the finest-level kernels inside a solve (bench.py's live roofline) ---- */
 /* classes: finest-level smoother (units = colour-pass launches), finest-level matvec / residual (units = products),

@@ -135,3 +135,39 @@ def test_halo_sum_two_ranks_gloo():
         for gi, v in zip(g, o):
             uniq[gi] = v
     assert abs(dot0 - sum(v * v for v in uniq.values())) < 1e-9 * dot0
+
+
+@pytest.mark.parametrize("nproc", [(2, 1, 1), (2, 2, 2), (3, 2, 2), (1, 3, 1)])
+def test_marker_exchange_routes(nproc):
+    """Routing table of the marker exchange (ccu_marker_routes, the host half of ccu_marker_exchange): every record a
+    subdomain sends under direction code c = (ox+1) + 3 (oy+1) + 9 (oz+1) is expected by exactly the neighbour at that
+    offset, under the opposite code; nothing is expected from outside the processor grid."""
+    import ctypes as C
+    lib = C.CDLL(str(_lib.LIB_PATH))
+    ranks = all_ranks(nproc)
+    n = len(ranks)
+    rng = np.random.default_rng(11)
+    send = np.zeros((n, 27), dtype=np.int32)
+    for r, me in enumerate(ranks):
+        for code in range(27):
+            o = (code % 3 - 1, (code // 3) % 3 - 1, code // 9 - 1)
+            tgt = tuple(me[d] + o[d] for d in range(3))
+            if code != 13 and all(0 <= tgt[d] < nproc[d] for d in range(3)):
+                send[r, code] = rng.integers(0, 50)
+    total_recv = 0
+    for r, me in enumerate(ranks):
+        nb, rc = (C.c_int * 27)(), (C.c_int * 27)()
+        assert lib.ccu_marker_routes((C.c_int * 3)(*nproc), (C.c_int * 3)(*me), send.ctypes.data_as(C.c_void_p), nb, rc) == 0
+        for code in range(27):
+            o = (code % 3 - 1, (code // 3) % 3 - 1, code // 9 - 1)
+            src = tuple(me[d] + o[d] for d in range(3))
+            inside = code != 13 and all(0 <= src[d] < nproc[d] for d in range(3))
+            if not inside:
+                assert nb[code] == -1 and rc[code] == 0
+                continue
+            rs = decomp.rank_of(src, nproc)
+            assert nb[code] == rs
+            back = sum((-o[d] + 1) * 3 ** d for d in range(3))         # the sender's code of the offset that points here
+            assert rc[code] == send[rs, back]
+            total_recv += rc[code]
+    assert total_recv == int(send.sum())
