@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,c
 def build_library(verbose: bool = False) -> Path:
     """Compile every CUDA source of the package for sm_100a into the in-tree shared library."""
     srcs = sorted(str(p) for p in CSRC.glob("*.cu"))
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [CSRC.parent.parent / "include" / "citcomcu_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [CSRC.parent.parent / "include" / "citcomcu_b200.h"]
     if LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return LIB_PATH
     # *_exact.cu reproduce the reference's rounding sequence: no FMA contraction there

@@ -1371,7 +1371,7 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
         LAUNCH(c, bk_BPI, cdiv(g.nel, 128), 128, g, L.elt_del, L.BI, precondition, L.BPI);
         if(c->multi() && ccu_damp_face_BI(c, lev)) return 1;              // rebuild_BI_on_boundary (Construct_arrays.c:892)
         L.have_K = true; L.have_p = true;
-        if(ccu_tile_refresh(c, lev)) return 1;                           // tile-major copy for the tile kernels (ccu_tile.cuh)
+        if(ccu_col_refresh(c, lev)) return 1;                            // column-major copy for the column kernels (ccu_col.cuh)
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));

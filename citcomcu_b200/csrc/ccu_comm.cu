@@ -279,7 +279,7 @@ int ccu_comm_init(ccu_ctx *c, int nprocx, int nprocy, int nprocz, int me_x, int 
     CK(cudaMalloc(&m->dotstage, sizeof(double) * 4));
     c->comm = m;
     ccu_drop_graphs(c);
-    return 0;
+    return ccu_col_refresh_all(c);      // the column chunks carry BI = 0 on the duplicated nodes (ccu_col.cuh)
 }
 
 void ccu_comm_destroy(ccu_ctx *c)

@@ -26,8 +26,9 @@ struct Level
 {
     CcuGeom g;
     float *K = nullptr;
-    float *Kt = nullptr;          // tile-major copy of K for the tile kernels (ccu_tile.cuh); Kt_shape < 0: none
-    size_t Kt_elems = 0; int Kt_shape = -1;
+    unsigned char *Kc = nullptr;  // column-major copy of K, BI, flags for the column kernels (ccu_col.cuh); col_shape < 0: none
+    size_t *colofs = nullptr;     // [col_nI * col_nJ] byte offset of each column's first chunk
+    size_t Kc_bytes = 0; int col_shape = -1, col_nI = 0, col_nJ = 0;
     double *BI = nullptr;
     unsigned char *flags = nullptr;
     float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
@@ -75,8 +76,8 @@ struct ccu_ctx
     // kernel selection by level size (lanes per node), ccu_set_option
     int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
     int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0, opt_bottom_cluster = 1, opt_coop_nodes = 0, opt_mid_lanes = 4;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
-    // tile-resident smoother / matvec (ccu_tile.cuh) on levels above opt_tile_nodes nodes
-    int opt_tile_nodes = 500000, opt_relax_tile = 0, opt_matvec_tile = 0, opt_tile_hint = 1, opt_tile_shape = 0, opt_tile_pad = 0;
+    // column-resident smoother / matvec (ccu_col.cuh) on levels above opt_col_nodes nodes
+    int opt_col_nodes = 500000, opt_relax_col = 1, opt_matvec_col = 1, opt_col_shape = 0;
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials
@@ -203,5 +204,6 @@ int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_ran
 int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv);
 int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of all subdomains -> coarse replica (ccu_stokes.cu)                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);
-int ccu_tile_refresh(ccu_ctx *c, int lev);
+int ccu_col_refresh(ccu_ctx *c, int lev);
+int ccu_col_refresh_all(ccu_ctx *c);
 void ccu_elt_del_changed(ccu_ctx *c, int lev);                // ccu_stokes.cu                   // ccu_stokes.cu

@@ -5,7 +5,7 @@
 // reference's control flow branches on.
 #include "ccu_ctx.cuh"
 #include "ccu_kernels.cuh"
-#include "ccu_tile.cuh"
+#include "ccu_col.cuh"
 #include "ccu_comm.cuh"
 #include <algorithm>
 #include <cmath>
@@ -113,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.Kt); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -148,7 +148,7 @@ int ccu_set_stream(ccu_ctx *c, void *s)
     if(c->coarse) { drop_graphs(c); c->coarse->st = c->st; }
     return 0;
 }
-static int tile_refresh_all(ccu_ctx *c);
+static int col_refresh_all(ccu_ctx *c);
 int ccu_set_option(ccu_ctx *c, int option, int value)
 {
     if(!c) FAIL("null context");
@@ -163,15 +163,13 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_CLUSTER_NODES: c->opt_cluster_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_NODES: c->opt_tile_nodes = value; drop_graphs(c); return tile_refresh_all(c);
-    case CCU_OPT_RELAX_TILE: c->opt_relax_tile = value; drop_graphs(c); return tile_refresh_all(c);
-    case CCU_OPT_MATVEC_TILE: c->opt_matvec_tile = value; drop_graphs(c); return tile_refresh_all(c);
+    case CCU_OPT_COL_NODES: c->opt_col_nodes = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_RELAX_COL: c->opt_relax_col = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_MATVEC_COL: c->opt_matvec_col = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_COL_SHAPE: if(value < 0 || value > 2) FAIL("column shape must be 0..2"); c->opt_col_shape = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
     case CCU_OPT_COOP_NODES: c->opt_coop_nodes = value; if(c->coarse) c->coarse->opt_coop_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_MID_LANES: if(value != 4 && value != 8 && value != 16) FAIL("mid lanes must be 4, 8 or 16"); c->opt_mid_lanes = value; if(c->coarse) c->coarse->opt_mid_lanes = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_PAD: c->opt_tile_pad = value; if(c->coarse) c->coarse->opt_tile_pad = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_HINT: c->opt_tile_hint = value; if(c->coarse) c->coarse->opt_tile_hint = value; drop_graphs(c); return 0;
-    case CCU_OPT_TILE_SHAPE: if(value < 0 || value > 3) FAIL("tile shape must be 0..3"); c->opt_tile_shape = value; drop_graphs(c); return tile_refresh_all(c);
     default: FAIL("set_option: unknown option");
     }
 }
@@ -257,7 +255,7 @@ int ccu_set_stiffness(ccu_ctx *c, int lev, const float *k1, const float *k2, con
     if(vec_h2d(c, L, BI, L.BI)) return 1;
     CK(cudaStreamSynchronize(c->st));
     L.have_K = true;
-    return ccu_tile_refresh(c, lev);
+    return ccu_col_refresh(c, lev);
 }
 
 int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double *BPI)
@@ -345,82 +343,99 @@ static int read_scal(ccu_ctx *c, int first, int count, double *out)
 
 static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cdiv(L.g.NS, 256), 256, L.g, L.flags, v); }
 
-// ---- tile-resident kernels (ccu_tile.cuh)
-typedef CcuTileShape<2, 4, 16, 8, 4> TileA4;
-typedef CcuTileShape<2, 4, 16, 8, 2> TileA2;
-typedef CcuTileShape<2, 2, 16, 8, 2> TileD2;
-typedef CcuTileShape<2, 2, 16, 16, 1> TileD1;     // 1024 threads, one CTA per SM: 148 tiles x 260 KB of stiffness in flight
-template <class S, int MODE>
-static void launch_tile(ccu_ctx *c, Level &L, int tcol, const double *F, double *x, double *out, const unsigned char *fl, int strip)
+// ---- column-resident kernels (ccu_col.cuh)
+typedef CcuColShape<8, 4, 5> ColA;      // 256 threads, 109 KB: two CTAs per SM
+typedef CcuColShape<8, 8, 5> ColB;      // 512 threads, 207 KB: one CTA per SM, 16 % halo blocks instead of 24 %
+typedef CcuColShape<4, 4, 6> ColC;      // 128 threads, 64 KB: three CTAs per SM (small subdomains: more columns)
+template <class SH, int MODE>
+static int launch_col(ccu_ctx *c, Level &L, int cc, const double *F, double *x, double *out, int strip)
 {
-    static bool attr = false;
-    if(!attr)
-    {
-        cudaFuncSetAttribute(ccu_k_tile<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(ccu_k_tile<S, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr = true;
-    }
-    const CcuGeom &g = L.g;
-    const int nti = (g.Id + S::TI - 1) / S::TI, ntj = (g.Jd + S::TJ - 1) / S::TJ, ntk = (g.Kd + S::TK - 1) / S::TK;
-    dim3 grid(ntk, ntj, nti);
-    if(MODE == 0) grid = dim3((ntk - (tcol & 1) + 1) / 2, (ntj - ((tcol >> 1) & 1) + 1) / 2, (nti - ((tcol >> 2) & 1) + 1) / 2);
-    if(!grid.x || !grid.y || !grid.z) return;
-    ccu_k_tile<S, MODE><<<grid, S::THREADS, S::SMEM + (size_t)c->opt_tile_pad * 1024, c->st>>>(g, ccu_make_tile_tab<S>(g), tcol, L.Kt, L.BI, F, x, out, fl, strip, c->opt_tile_hint);
+    CcuColArgs A;
+    A.g = L.g; A.Kc = L.Kc; A.colofs = L.colofs; A.F = F; A.x = x; A.out = out;
+    A.nI = L.col_nI; A.nJ = L.col_nJ; A.cc = cc; A.strip = strip;
+    unsigned grid = (unsigned)(A.nI * A.nJ);
+    if(MODE == 0) grid = (unsigned)(((A.nI - (cc >> 1) + 1) / 2) * ((A.nJ - (cc & 1) + 1) / 2));
+    if(!grid) return 0;
+    ccu_k_col<SH, MODE><<<grid, SH::THREADS, SH::SMEM, c->st>>>(A);
     c->launches++;
+    return 0;
 }
 template <int MODE>
-static void launch_tile_shape(ccu_ctx *c, Level &L, int tcol, const double *F, double *x, double *out, const unsigned char *fl, int strip)
+static int launch_col_shape(ccu_ctx *c, Level &L, int cc, const double *F, double *x, double *out, int strip)
 {
-    if(L.Kt_shape == 1) launch_tile<TileA2, MODE>(c, L, tcol, F, x, out, fl, strip);
-    else if(L.Kt_shape == 2) launch_tile<TileD2, MODE>(c, L, tcol, F, x, out, fl, strip);
-    else if(L.Kt_shape == 3) launch_tile<TileD1, MODE>(c, L, tcol, F, x, out, fl, strip);
-    else launch_tile<TileA4, MODE>(c, L, tcol, F, x, out, fl, strip);
+    if(L.col_shape == 1) return launch_col<ColB, MODE>(c, L, cc, F, x, out, strip);
+    if(L.col_shape == 2) return launch_col<ColC, MODE>(c, L, cc, F, x, out, strip);
+    return launch_col<ColA, MODE>(c, L, cc, F, x, out, strip);
 }
-template <class S>
-static int tile_relayout(ccu_ctx *c, Level &L)
-{
-    const size_t need = ccu_tile_elems<S>(L.g);
-    if(need > L.Kt_elems)
-    {
-        if(L.Kt) cudaFree(L.Kt);
-        L.Kt = nullptr; L.Kt_elems = 0;
-        CK(cudaMalloc(&L.Kt, sizeof(float) * need));
-        L.Kt_elems = need;
-    }
-    const CcuGeom &g = L.g;
-    const int nti = (g.Id + S::TI - 1) / S::TI, ntj = (g.Jd + S::TJ - 1) / S::TJ, ntk = (g.Kd + S::TK - 1) / S::TK;
-    LAUNCH(c, ccu_k_tile_relayout<S>, (unsigned)(nti * ntj * ntk * 8), S::CT, g, ntj, ntk, L.K, L.Kt);
+template <class SH>
+static int col_attrs()
+{   // more than 48 KB of dynamic shared memory needs the opt-in, per device; set for the current device of the caller
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
 }
-// The tile kernels read a tile-major copy of the level's stiffness: (re)made whenever K of the level changes
-// (ccu_set_stiffness, ccu_construct_stiffness_B_matrix) or the tile options do.  Never called inside a graph capture.
-int ccu_tile_refresh(ccu_ctx *c, int lev)
+template <int TI, int TJ>
+static int col_relayout(ccu_ctx *c, Level &L, int lev)
+{
+    const CcuGeom &g = L.g;
+    const int nI = (g.noy + TI - 1) / TI, nJ = (g.nox + TJ - 1) / TJ;
+    std::vector<size_t> ofs((size_t)nI * nJ);
+    size_t total = 0;
+    for(int I = 0; I < nI; I++)
+        for(int J = 0; J < nJ; J++)
+        {
+            ofs[(size_t)I * nJ + J] = total;
+            total += (size_t)(g.noz + 2) * ccu_col_dims(std::min(TI, g.noy - I * TI), std::min(TJ, g.nox - J * TJ)).cb;
+        }
+    if(total > L.Kc_bytes || L.col_nI != nI || L.col_nJ != nJ)
+    {
+        cudaFree(L.Kc); cudaFree(L.colofs);
+        L.Kc = nullptr; L.colofs = nullptr; L.Kc_bytes = 0;
+        CK(cudaMalloc(&L.Kc, total));
+        CK(cudaMalloc(&L.colofs, sizeof(size_t) * ofs.size()));
+        L.Kc_bytes = total;
+    }
+    CK(cudaMemcpyAsync(L.colofs, ofs.data(), sizeof(size_t) * ofs.size(), cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));               // `ofs` leaves scope
+    L.col_nI = nI; L.col_nJ = nJ;
+    const unsigned char *bits = c->multi() ? c->comm->halo[lev].bits : nullptr;
+    LAUNCH(c, (ccu_k_col_relayout<TI, TJ>), dim3((unsigned)(nI * nJ), (unsigned)((g.noz + 2 + 31) / 32)), 256, g, nJ, L.colofs, L.K, L.BI, L.flags, bits, L.Kc);
+    return 0;
+}
+// The column kernels read a column-major copy of the level's stiffness, inverse diagonal and flags: (re)made whenever
+// they change (ccu_set_stiffness, ccu_construct_stiffness_B_matrix, ccu_comm_init) or the column options do.
+// Never called inside a graph capture.
+int ccu_col_refresh(ccu_ctx *c, int lev)
 {
     Level &L = c->L[lev];
-    L.Kt_shape = -1;
-    if(!(c->opt_relax_tile || c->opt_matvec_tile) || L.g.nno <= c->opt_tile_nodes || !L.have_K) return 0;
+    L.col_shape = -1;
+    if(!(c->opt_relax_col || c->opt_matvec_col) || L.g.nno <= c->opt_col_nodes || !L.have_K || !L.have_flags) return 0;
     int rc;
-    if(c->opt_tile_shape == 1) rc = tile_relayout<TileA2>(c, L);
-    else if(c->opt_tile_shape == 2) rc = tile_relayout<TileD2>(c, L);
-    else if(c->opt_tile_shape == 3) rc = tile_relayout<TileD1>(c, L);
-    else rc = tile_relayout<TileA4>(c, L);
+    if(c->opt_col_shape == 1) rc = col_attrs<ColB>() || col_relayout<8, 8>(c, L, lev);
+    else if(c->opt_col_shape == 2) rc = col_attrs<ColC>() || col_relayout<4, 4>(c, L, lev);
+    else rc = col_attrs<ColA>() || col_relayout<8, 4>(c, L, lev);
     if(rc) return rc;
-    L.Kt_shape = c->opt_tile_shape;
+    L.col_shape = c->opt_col_shape;
     return 0;
 }
-static int tile_refresh_all(ccu_ctx *c)
+int ccu_col_refresh_all(ccu_ctx *c) { return col_refresh_all(c); }
+static int col_refresh_all(ccu_ctx *c)
 {
     for(int lev = c->cfg.levmin; lev <= c->cfg.levmax; lev++)
-        if(ccu_tile_refresh(c, lev)) return 1;
+        if(ccu_col_refresh(c, lev)) return 1;
     if(c->coarse)
     {
-        c->coarse->opt_tile_nodes = c->opt_tile_nodes; c->coarse->opt_relax_tile = c->opt_relax_tile; c->coarse->opt_matvec_tile = c->opt_matvec_tile;
-        c->coarse->opt_tile_hint = c->opt_tile_hint; c->coarse->opt_tile_shape = c->opt_tile_shape;
-        return tile_refresh_all(c->coarse);
+        c->coarse->opt_col_nodes = c->opt_col_nodes; c->coarse->opt_relax_col = c->opt_relax_col; c->coarse->opt_matvec_col = c->opt_matvec_col;
+        c->coarse->opt_col_shape = c->opt_col_shape;
+        return col_refresh_all(c->coarse);
     }
     return 0;
 }
-static bool use_tile(const ccu_ctx *c, const Level &L, int on) { return on && L.Kt_shape >= 0; }
+static bool use_col(const ccu_ctx *c, const Level &L, int on) { (void)c; return on && L.col_shape >= 0; }
 
 // Lanes per node by level size: the smaller the level, the more the per-node chain of dependent loads is the
 // whole kernel time, so it is split over more lanes (ccu_kernels.cuh).  Tunable through ccu_set_option.
@@ -436,7 +451,7 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);   // the table-driven kernel wins from ~1e4 nodes up
-    if(use_tile(c, L, c->opt_matvec_tile)) launch_tile_shape<1>(c, L, 0, nullptr, const_cast<double *>(u), Au, L.flags, strip);
+    if(use_col(c, L, c->opt_matvec_col)) launch_col_shape<1>(c, L, 0, nullptr, const_cast<double *>(u), Au, strip);
     else if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab == 24) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
@@ -458,7 +473,7 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);
-    if(use_tile(c, L, c->opt_matvec_tile)) { launch_tile_shape<2>(c, L, 0, rhs, const_cast<double *>(u), out, L.flags, 1); return; }
+    if(use_col(c, L, c->opt_matvec_col)) { launch_col_shape<2>(c, L, 0, rhs, const_cast<double *>(u), out, 1); return; }
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab == 24) { LAUNCH(c, (ccu_k_matvec_tab<1, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
@@ -600,15 +615,15 @@ static void relax_faces(ccu_ctx *c, Level &L, double *x, const double *F)
 }
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
-    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], 8LL * cycles);
+    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], (use_col(c, L, c->opt_relax_col) ? 4LL : 8LL) * cycles);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, cycles);
-    if(use_tile(c, L, c->opt_relax_tile))
-    {   // tile order: tile colours 7..0, the eight node colours inside each tile (ccu_tile.cuh)
-        const unsigned char *tbits = c->multi() ? c->comm->halo[&L - c->L].bits : nullptr;
+    if(use_col(c, L, c->opt_relax_col))
+    {   // column order: column colours 3..0, z ascending inside a column, (y, x)-parity colours 3..0 inside a layer (ccu_col.cuh)
+        const bool multi = c->multi();
         for(int s = 0; s < cycles; s++)
         {
-            if(tbits) relax_faces(c, L, x, F);
-            for(int tcol = 7; tcol >= 0; tcol--) launch_tile_shape<0>(c, L, tcol, F, x, nullptr, tbits, 0);
+            if(multi) relax_faces(c, L, x, F);
+            for(int cc = 3; cc >= 0; cc--) launch_col_shape<0>(c, L, cc, F, x, nullptr, 0);
         }
         return;
     }

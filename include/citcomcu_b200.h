@@ -53,18 +53,18 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
        CCU_OPT_MATVEC_TAB = 5, CCU_OPT_RELAX_TAB = 6,
        CCU_OPT_CLUSTER_NODES = 8 /* single-subdomain levels with nno <= this run a whole smoother call in one 8-CTA cluster launch */,
        CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */,
-       /* tile-resident kernels (csrc/ccu_tile.cuh) on levels with nno > TILE_NODES: RELAX_TILE / MATVEC_TILE switch them
-        * on (1) or off (0); TILE_HINT 1 = L2 evict_last / evict_first hints on the stiffness loads; TILE_SHAPE 0 = tiles of
-        * 2x4x16 colour cells with four z cells per thread, 1 = 2x4x16 / two cells, 2 = 2x2x16 / two cells,
-        * 3 = 2x2x16 / one cell with rows split over 16 groups (1024 threads, one CTA per SM).  The tile smoother is a Gauss-Seidel sweep in tile order (tile colours 7..0,
-        * node colours 7..0 inside a tile) instead of plain colour order. */
-       CCU_OPT_TILE_NODES = 9, CCU_OPT_RELAX_TILE = 10, CCU_OPT_MATVEC_TILE = 11, CCU_OPT_TILE_HINT = 12, CCU_OPT_TILE_SHAPE = 13,
+       /* column-resident kernels (csrc/ccu_col.cuh) on levels with nno > COL_NODES (default 500000): RELAX_COL / MATVEC_COL
+        * (default 1) switch them on or off; COL_SHAPE 0 = columns of 8 (y) x 4 (x) nodes, two CTAs per SM, 1 = 8 x 8, one CTA
+        * per SM, 2 = 4 x 4, three CTAs per SM.  A CTA streams the stiffness of its column through shared memory with one bulk
+        * asynchronous copy per z layer, so every coefficient crosses HBM once per sweep.  The column smoother is a Gauss-Seidel
+        * sweep in column order (column colours 3..0, z ascending, (y,x)-parity colours 3..0 inside a layer) instead of the plain
+        * 8-colour order; oracle/restate.c ccu_r_ordered_gs mode 10 is its CPU statement. */
+       CCU_OPT_COL_NODES = 9, CCU_OPT_RELAX_COL = 10, CCU_OPT_MATVEC_COL = 11, CCU_OPT_COL_SHAPE = 13,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */,
        CCU_OPT_COOP_NODES = 16 /* single-subdomain levels with SMALL_NODES < nno <= this (default 0 = off: measured no faster than the graph-replayed per-pass launches) run each smoother call as one
         * cooperative launch with grid barriers between the colour passes (ccu_k_relax_coop); 0 = per-pass launches */,
-       CCU_OPT_MID_LANES = 17 /* lanes per node (4, 8 or 16) of the smoother on levels between WARP_NODES and QUAD_NODES */,
-       CCU_OPT_TILE_PAD = 14 /* extra KB of shared memory per tile CTA: lowers the CTAs per SM (L2 working-set experiments) */ };
+       CCU_OPT_MID_LANES = 17 /* lanes per node (4, 8 or 16) of the smoother on levels between WARP_NODES and QUAD_NODES */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);

@@ -206,7 +206,22 @@ class Restate:
         t = (C.c_int * 3).in_dll(self.lib, "g_ccu_r_tile")
         t[0], t[1], t[2] = ti, tj, tk
 
-    def gauss_seidel(self, lev, F, cycles, guess, d0=None, mc=False, tile=None):
+    def set_col(self, ti, tj):
+        """Column shape (nodes in y, x) of the column-ordered smoother model (ccu_r_ordered_gs mode 10; smoother=20)."""
+        t = (C.c_int * 2).in_dll(self.lib, "g_ccu_r_col")
+        t[0], t[1] = ti, tj
+
+    def gauss_seidel(self, lev, F, cycles, guess, d0=None, mc=False, tile=None, col=None):
+        if col is not None:
+            self.set_col(*col)
+            n = self.neq(lev)
+            d = np.zeros(n + 2)
+            if d0 is not None:
+                d[:n] = d0
+            Ad = np.zeros(n + 2)
+            F = np.ascontiguousarray(F, dtype=np.float64)
+            self.lib.ccu_r_ordered_gs(self.L(lev), _p(d), _p(F), _p(Ad), C.c_int(cycles), C.c_int(guess), C.c_int(10))
+            return d[:n], Ad[:n]
         if tile is not None:
             self.set_tile(*tile)
             n = self.neq(lev)

@@ -564,7 +564,10 @@ double ccu_r_conj_grad(const ccu_r_level *L, double *d0, const double *F, double
  *   mode 5 as 4 but symmetric (z descending on backward sweeps)
  *   mode 9 tile-ordered 8-colour: tiles of g_ccu_r_tile[] = TI x TJ x TK colour cells (cell = (index>>1)+1, the
  *          device layout's halo offset), tile colours 7..0 outside, node colours 7..0 inside each tile -- the order
- *          of ccu_k_relax_tile (csrc/ccu_tile.cuh); THIS mode is a checker for that kernel
+ *          of the round-1 tile kernels (removed in round 2; kept as an ordering study)
+ *   mode 10 column-ordered: columns of g_ccu_r_col[] = TI (y) x TJ (x) NODES spanning all of z, 4-coloured by the parity
+ *          of their column indices (colours 3..0); inside a column the z layers ascending, and inside a layer the four
+ *          (y,x)-parity colours 3..0 -- the order of ccu_k_col (csrc/ccu_col.cuh); THIS mode is the checker for that kernel
  * ------------------------------------------------------------------------------------------ */
 static void full_row(const ccu_r_level *L, int n, const double *x, double out[3])
 {
@@ -573,6 +576,7 @@ static void full_row(const ccu_r_level *L, int n, const double *x, double out[3]
     for(a = 0; a < 3; a++) out[a] = lo[a] + s[a] + up[a];
 }
 int g_ccu_r_tile[3] = { 2, 4, 16 };      /* TI (y), TJ (x), TK (z) colour cells per tile */
+int g_ccu_r_col[2] = { 8, 4 };           /* TI (y), TJ (x) nodes per column (mode 10) */
 static int ord_key(const ccu_r_level *L, int n, int mode, int back)
 {
     int i, j, k; nijk(L, n, &i, &j, &k);
@@ -583,6 +587,13 @@ static int ord_key(const ccu_r_level *L, int n, int mode, int back)
         const int tc = ((ti & 1) << 2) | ((tj & 1) << 1) | (tk & 1);
         const int tile = tk + ntk * (tj + ntj * ti);
         return ((7 - tc) * (1 << 20) + tile) * 8 + (7 - colour_of(i, j, k));
+    }
+    if(mode == 10)
+    {
+        const int I = i / g_ccu_r_col[0], J = j / g_ccu_r_col[1];
+        const int nJ = (L->nox + g_ccu_r_col[1] - 1) / g_ccu_r_col[1], nI = (L->noy + g_ccu_r_col[0] - 1) / g_ccu_r_col[0];
+        const int cc = ((I & 1) << 1) | (J & 1), c2 = ((i & 1) << 1) | (j & 1);
+        return ((((3 - cc) * nI * nJ + I * nJ + J) * L->noz) + k) * 4 + (3 - c2);
     }
     if(mode == 0 || mode == 3) return back ? (L->nno - 1 - n) : n;
     if(mode == 1 || mode == 2) { int c = colour_of(i, j, k); return back ? 7 - c : c; }

@@ -1,0 +1,202 @@
+// col_emul.cpp -- HOST emulation of the column-resident smoother / matvec kernel (csrc/ccu_col.cuh), test infrastructure.
+//
+// It re-states the kernel's control flow (ring of S stiffness chunks filled at the kernel's own issue points, ring of S
+// solution layers, one "warp" per node with 27 lanes (d, q) x 3 directions, the shuffle fold order, the update) on
+// the CPU, using the SAME index functions (csrc/ccu_col_index.h: chunk layout, halo block ids, lane descriptors,
+// chunk fill) the device code uses.  tests/test_col_emul.py compares it with the oracle's column-ordered Gauss-Seidel
+// (oracle/restate.c mode 10) and the reference's matvec known answers, so that the index logic and the ring schedule
+// are verified without a GPU; the GPU tests then only have to prove the CUDA-specific parts.
+#include "../citcomcu_b200/csrc/ccu_col_index.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace
+{
+struct Emul
+{
+    CcuGeom g;
+    int TI, TJ, S, BJ, BOX, CH, nI, nJ;
+    std::vector<float> K;
+    std::vector<double> BI;
+    std::vector<unsigned char> flags, Kc;
+    std::vector<size_t> colofs;
+};
+
+void run_column(const Emul &E, int mode, int I, int J, const double *F, double *x, double *out, int strip)
+{
+    const CcuGeom &g = E.g;
+    const int TI = E.TI, TJ = E.TJ, S = E.S, BJ = E.BJ, BOX = E.BOX, CH = E.CH, noz = g.noz;
+    const int i0 = I * TI, j0 = J * TJ;
+    const CcuColDims cd = ccu_col_dims(std::min(TI, g.noy - i0), std::min(TJ, g.nox - j0));
+    const unsigned char *chunks = E.Kc.data() + E.colofs[I * E.nJ + J];
+    const size_t NS = (size_t)g.NS;
+    std::vector<unsigned char> stg((size_t)S * CH, 0xff);          // poison: reads of an unfilled stage show up as NaN
+    std::vector<double> xr((size_t)S * 3 * BOX, 1e300);
+    const int NW = TI * TJ / 4;
+    auto issue = [&](int layer) { memcpy(stg.data() + (size_t)((layer + S) % S) * CH, chunks + (size_t)(layer + 1) * cd.cb, cd.cb); };
+    auto xload = [&](int tid, int k) -> double
+    {
+        const int dx = tid / BOX, bn = tid % BOX, gi = i0 + bn / BJ - 1, gj = j0 + bn % BJ - 1;
+        if(!(gi >= 0 && gi < g.noy && gj >= 0 && gj < g.nox && k >= 0 && k < noz)) return 0.0;
+        const size_t xA = (size_t)dx * NS + (size_t)((4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1);
+        return x[xA + (size_t)((k & 1) * g.NC + (k >> 1))];
+    };
+    for(int layer = -1; layer <= S - 2 && layer <= noz; layer++) issue(layer);
+    for(int tid = 0; tid < 3 * BOX; tid++)
+    {
+        xr[(size_t)(S - 1) * 3 * BOX + tid] = xload(tid, -1);
+        xr[(size_t)0 * 3 * BOX + tid] = xload(tid, 0);
+        xr[(size_t)(1 % S) * 3 * BOX + tid] = xload(tid, 1);
+    }
+    std::vector<double> xpre(3 * BOX);
+    for(int k = 0; k < noz; k++)
+    {
+        const int JJ = k % S;
+        for(int tid = 0; tid < 3 * BOX; tid++) xpre[tid] = xload(tid, k + 2);
+        const int zoff = (k & 1) * g.NC + (k >> 1);
+        const unsigned char *own = stg.data() + (size_t)JJ * CH;
+        for(int ph = 0; ph < 4; ph++)
+        {
+            const int c2 = mode == 0 ? 3 - ph : ph;
+            for(int warp = 0; warp < NW; warp++)
+            {
+                const int wa = warp / (TJ / 2), wb = warp % (TJ / 2);
+                const int li = 2 * wa + (c2 >> 1), lj = 2 * wb + (c2 & 1);
+                if(!(li < cd.ti && lj < cd.tj)) continue;
+                double r[32] = { 0 };
+                for(int lane = 0; lane < 27; lane++)
+                {
+                    const int d = lane / 9, q = lane % 9;
+                    double rt[3];
+                    for(int t = 0; t < 3; t++)
+                    {
+                        const CcuColDesc ds = ccu_col_desc(cd, TJ, li, lj, d, q, t);
+                        const int ring = (JJ + t - 1 + S) % S;
+                        const unsigned char *kb = (ds.tr ? stg.data() + (size_t)ring * CH : own) + ds.kof;
+                        const int st = ds.tr ? 12 : 4;
+                        float c0, c1, c2f;
+                        memcpy(&c0, kb, 4); memcpy(&c1, kb + st, 4); memcpy(&c2f, kb + 2 * st, 4);
+                        const double *xp = (const double *)((const unsigned char *)xr.data() + (size_t)ring * 3 * BOX * 8 + ds.xof);
+                        rt[t] = (double)c0 * xp[0] + (double)c1 * xp[BOX] + (double)c2f * xp[2 * BOX];
+                    }
+                    r[lane] = (rt[0] + rt[1]) + rt[2];
+                }
+                // the kernel's shuffle fold
+                const int dl[4] = { 8, 4, 2, 1 }, lim[4] = { 1, 4, 2, 1 };
+                for(int st = 0; st < 4; st++)
+                {
+                    double o[32];
+                    for(int lane = 0; lane < 32; lane++) o[lane] = lane + dl[st] < 32 ? r[lane + dl[st]] : r[lane];
+                    for(int lane = 0; lane < 27; lane++) if(lane % 9 < lim[st]) r[lane] += o[lane];
+                }
+                const int gi = i0 + li, gj = j0 + lj;
+                const int nodeA = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
+                for(int d = 0; d < 3; d++)
+                {
+                    const size_t sn = (size_t)d * NS + (size_t)(nodeA + zoff);
+                    const double rr = r[9 * d];
+                    const int p = li * cd.tj + lj;
+                    if(mode == 0)
+                    {
+                        const double bi = ((const double *)own)[d * cd.nt + p];
+                        double *xs = xr.data() + (size_t)JJ * 3 * BOX + d * BOX + (li + 1) * BJ + (lj + 1);
+                        const double xn = *xs + (double)(float)((F[sn] - rr) * bi);
+                        *xs = xn; x[sn] = xn;
+                    }
+                    else
+                    {
+                        const unsigned char fl = own[cd.flofs + p];
+                        double a = rr;
+                        if((mode == 2 || strip) && ((fl >> d) & 1)) a = 0.0;
+                        out[sn] = mode == 1 ? a : F[sn] - a;
+                    }
+                }
+            }
+            if(ph == 3) for(int tid = 0; tid < 3 * BOX; tid++) xr[(size_t)((JJ + 2) % S) * 3 * BOX + tid] = xpre[tid];
+        }
+        if(k + S - 1 <= noz) issue(k + S - 1);
+    }
+}
+}
+
+// mode 0: `cycles` column-ordered sweeps on x (in/out) with right-hand side F; mode 1: out = K x (boundary rows zeroed if
+// strip); mode 2: out = F - K x with boundary rows of K x zeroed.  Arrays in the REFERENCE's layouts (Eqn_k1-3: 42 per
+// node; vectors 3n+d; NODE flags), exactly what ccu_set_stiffness / ccu_set_node_flags take.
+extern "C" int ccu_col_emul(int nox, int noy, int noz, int TI, int TJ, int S, int mode, const float *k1, const float *k2,
+                            const float *k3, const double *BIh, const unsigned *node, double *xh, const double *Fh, double *outh,
+                            int cycles, int strip)
+{
+    const int LO[13][3] = CCU_LO_INIT;
+    Emul E;
+    E.g = ccu_make_geom(nox, noy, noz);
+    const CcuGeom &g = E.g;
+    E.TI = TI; E.TJ = TJ; E.S = S; E.BJ = TJ + 2; E.BOX = (TI + 2) * (TJ + 2);
+    E.CH = ccu_col_dims(TI, TJ).cb;
+    E.nI = (noy + TI - 1) / TI; E.nJ = (nox + TJ - 1) / TJ;
+    const size_t NS = (size_t)g.NS;
+    E.K.assign(126 * NS, 0.0f); E.BI.assign(3 * NS, 0.0); E.flags.assign(NS, 0);
+    std::vector<double> x(3 * NS, 0.0), F(3 * NS, 0.0), out(3 * NS, 0.0);
+    for(int n = 0; n < g.nno; n++)
+    {   // ccu_k_stiffness_to_dev / ccu_k_vec_to_dev / ccu_k_flags_to_dev
+        const int k = n % noz, j = (n / noz) % nox, i = n / (noz * nox);
+        const int s = ccu_sidx(g, i, j, k);
+        const size_t base = (size_t)n * 42;
+        const float *kk[3] = { k1 + base, k2 + base, k3 + base };
+        for(int a = 0; a < 3; a++) for(int b = 0; b < 3; b++) E.K[(size_t)(a * 3 + b) * NS + s] = kk[a][b];
+        int rs = 0;
+        for(int q = 0; q < 13; q++)
+        {
+            const int ii = i + LO[q][0], jj = j + LO[q][1], kz = k + LO[q][2];
+            const bool in = ii >= 0 && jj >= 0 && jj < nox && kz >= 0 && kz < noz;
+            if(in) rs++;
+            for(int a = 0; a < 3; a++) for(int b = 0; b < 3; b++) E.K[(size_t)((q + 1) * 9 + a * 3 + b) * NS + s] = in ? kk[a][3 * rs + b] : 0.0f;
+        }
+        for(int d = 0; d < 3; d++)
+        {
+            E.BI[d * NS + s] = BIh[3 * (size_t)n + d];
+            x[d * NS + s] = xh[3 * (size_t)n + d];
+            if(Fh) F[d * NS + s] = Fh[3 * (size_t)n + d];
+        }
+        const unsigned f = node[n];
+        E.flags[s] = (unsigned char)(128 | ((f & 0x2u) ? 1 : 0) | ((f & 0x8u) ? 2 : 0) | ((f & 0x4u) ? 4 : 0));
+    }
+    E.colofs.resize((size_t)E.nI * E.nJ);
+    size_t total = 0;
+    for(int I = 0; I < E.nI; I++)
+        for(int J = 0; J < E.nJ; J++)
+        {
+            E.colofs[I * E.nJ + J] = total;
+            total += (size_t)(noz + 2) * ccu_col_dims(std::min(TI, noy - I * TI), std::min(TJ, nox - J * TJ)).cb;
+        }
+    E.Kc.assign(total, 0xee);
+    for(int I = 0; I < E.nI; I++)
+        for(int J = 0; J < E.nJ; J++)
+        {
+            const CcuColDims cd = ccu_col_dims(std::min(TI, noy - I * TI), std::min(TJ, nox - J * TJ));
+            for(int kk = 0; kk <= noz + 1; kk++)
+                ccu_col_fill_chunk(g, cd, I * TI, J * TJ, kk - 1, E.K.data(), E.BI.data(), E.flags.data(), nullptr,
+                                   E.Kc.data() + E.colofs[I * E.nJ + J] + (size_t)kk * cd.cb, 0, 1);
+        }
+    if(mode == 0)
+    {
+        for(int s = 0; s < cycles; s++)
+            for(int cc = 3; cc >= 0; cc--)
+                for(int I = cc >> 1; I < E.nI; I += 2)
+                    for(int J = cc & 1; J < E.nJ; J += 2) run_column(E, 0, I, J, F.data(), x.data(), nullptr, 0);
+    }
+    else
+        for(int I = 0; I < E.nI; I++)
+            for(int J = 0; J < E.nJ; J++) run_column(E, mode, I, J, F.data(), x.data(), out.data(), strip);
+    for(int n = 0; n < g.nno; n++)
+    {
+        const int k = n % noz, j = (n / noz) % nox, i = n / (noz * nox);
+        const int s = ccu_sidx(g, i, j, k);
+        for(int d = 0; d < 3; d++)
+        {
+            if(mode == 0) xh[3 * (size_t)n + d] = x[d * NS + s];
+            else outh[3 * (size_t)n + d] = out[d * NS + s];
+        }
+    }
+    return 0;
+}

@@ -34,7 +34,7 @@ CASES = {
     "tdepv_l3": lambda: (inputfile.tdepv_box(16, 16, 8, 3, maxstep=2), 1, True),
     # BASELINE config 2 (examples/input1 as Cartesian): non-uniform z spacing -> non-trivial interpolation weights / element sizes
     "input1_cart_l3": lambda: (inputfile.input1_cart(levels=3, maxstep=1), 0, True),
-    # tall box: several tiles of the tile-resident kernels along z as well (csrc/ccu_tile.cuh)
+    # tall box: many z layers per column of the column-resident kernels (csrc/ccu_col.cuh), several ring turns
     "tdepv_tall": lambda: (inputfile.tdepv_box(8, 16, 64, 3, maxstep=1), 0, True),
 }
 
