@@ -80,15 +80,17 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
                         const double *xp = (const double *)((const unsigned char *)xr.data() + (size_t)ring * 3 * BOX * 8 + ds.xof);
                         rt[t] = (double)c0 * xp[0] + (double)c1 * xp[BOX] + (double)c2f * xp[2 * BOX];
                     }
-                    r[lane] = (rt[0] + rt[1]) + rt[2];
+                    r[lane] = (rt[0] + rt[2]) + rt[1];      // pre-phase (layers below and above) first, then the same-layer block
                 }
-                // the kernel's shuffle fold
-                const int dl[4] = { 8, 4, 2, 1 }, lim[4] = { 1, 4, 2, 1 };
-                for(int st = 0; st < 4; st++)
+                // the kernel's shuffle fold (ccu_col_fold9): lane 8 aside, a three-step tree over lanes 0..7, then + lane 8
+                for(int d = 0; d < 3; d++)
                 {
-                    double o[32];
-                    for(int lane = 0; lane < 32; lane++) o[lane] = lane + dl[st] < 32 ? r[lane + dl[st]] : r[lane];
-                    for(int lane = 0; lane < 27; lane++) if(lane % 9 < lim[st]) r[lane] += o[lane];
+                    double *v = r + 9 * d;
+                    const double e = v[8];
+                    for(int i = 0; i < 4; i++) v[i] += v[i + 4];
+                    for(int i = 0; i < 2; i++) v[i] += v[i + 2];
+                    v[0] += v[1];
+                    v[0] += e;
                 }
                 const int gi = i0 + li, gj = j0 + lj;
                 const int nodeA = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
