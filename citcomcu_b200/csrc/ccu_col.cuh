@@ -6,57 +6,69 @@
 // neighbour -- plus uncached neighbour values: 2.5x the 600 B/node a sweep has to move (ncu, profiles/r01_*).
 // Here a CTA owns a COLUMN of TI x TJ nodes over all z layers and marches through it layer by layer:
 //   * the stiffness of a layer arrives as ONE bulk asynchronous copy (cp.async.bulk + mbarrier, the TMA engine) of a
-//     chunk that was laid out in HBM exactly as it is used in shared memory (ccu_col_index.h); a ring of S chunks
-//     holds the layers k-1, k, k+1 the row products of layer k read and S-3 layers in flight;
-//   * the solution values of the column plus a one-node rim, and the right-hand side, live in two more rings of S
-//     layers in shared memory, filled two layers ahead by plain loads (their sectors are shared by 8 layers: L2 hits);
+//     chunk that was laid out in HBM exactly as it is used in shared memory (ccu_col_index.h); chunk k holds the
+//     in-plane blocks of layer k and every block between the layers k and k+1, so the rows of layer k read the chunks
+//     k-1 and k: a ring of three holds two in use and one in flight;
+//   * the solution values of the column plus a one-node rim live in a ring of three layers in shared memory, filled two
+//     layers ahead by plain loads (their sectors are shared by the layers of equal parity: L2 hits);
+//   * NINE lanes relax one node (three nodes per warp): lane q owns the in-plane direction (q/3-1, q%3-1) and
+//     multiplies the three 3x3 blocks towards the layers below, same and above with the neighbour's three values
+//     for all three rows; a block is two 128-bit and one 32-bit shared-memory loads, used as stored or transposed
+//     (six selects); the nine partial row triples are folded with four double shuffles, after which lane q < 3 holds
+//     row q and applies the reference's update (scalar BI per equation, correction rounded to fp32,
+//     General_matrix_functions.c:1250-1259);
 //   * per layer, the products with the layers below and above (2/3 of a row, independent of this layer's colour phases)
-//     are formed for all four colours at once; a colour phase then only adds the same-layer blocks;
-//   * a warp relaxes one node: lane (d, q) multiplies row d of the three 3x3 blocks in the directions
-//     (q/3-1, q%3-1, -1|0|+1), nine lanes fold their sums with four shuffles, lane q = 0 applies the reference's
-//     update (scalar BI per equation, correction rounded to fp32, General_matrix_functions.c:1250-1259);
-//   * every stiffness byte is read from HBM once per sweep (+ the duplicated halo blocks, 24 % for 8 x 4 columns).
-// Gauss-Seidel order: columns are 4-coloured by the parity of their column indices, one launch per column colour
-// (3..0); inside a column z ascends; inside a layer the four (y, x)-parity colours 3..0.  All nodes relaxed
-// concurrently share no stencil neighbour, so this is a Gauss-Seidel ordering of the same point-block smoother
-// (General_matrix_functions.c:1231-1260); oracle/restate.c `ccu_r_ordered_gs` mode 10 states it on the CPU and
-// contracts like the lexicographic order inside the multigrid cycle (tests/test_oracle_restate.py).
+//     are formed for all four in-plane colours at once; a colour phase then only adds the same-layer blocks;
+//   * every stiffness byte is read from HBM once per sweep (+ the duplicated halo blocks, 19 % for 6 x 8 columns).
+// Gauss-Seidel order: columns are 4-coloured by the parity of their column indices, colours 3..0; inside a column z
+// ascends; inside a layer the four (y, x)-parity colours 3..0.  All nodes relaxed concurrently share no stencil
+// neighbour, so this is a Gauss-Seidel ordering of the same point-block smoother (General_matrix_functions.c:1231-1260);
+// oracle/restate.c `ccu_r_ordered_gs` mode 10 states it on the CPU and contracts like the lexicographic order inside
+// the multigrid cycle (tests/test_oracle_restate.py).
+// The four column colours run in ONE launch (WF = 1): CTAs draw columns from a ticket counter in colour order and a
+// column waits, layer by layer, until the columns of earlier colours around it are three layers ahead (a progress word
+// per column, release/acquire at gpu scope).  A ticket only ever waits for lower tickets, which are running or done,
+// so the launch cannot deadlock however the CTAs are scheduled; results are bitwise those of four launches (WF = 0).
 // MODE 1 / 2 run the same march without colours: Au = K u, or rhs - K u with boundary rows stripped
 // (n_assemble_del2_u, Element_calculations.c:552).
 #pragma once
 #include "ccu_kernels.cuh"
 #include "ccu_col_index.h"
 
-template <int TI_, int TJ_, int S_>
+template <int TI_, int TJ_, int CTAS_>
 struct CcuColShape
 {
-    static constexpr int TI = TI_, TJ = TJ_, S = S_;
+    static constexpr int TI = TI_, TJ = TJ_, S = 3, CTAS = CTAS_;
     static constexpr int NT = TI * TJ;                    // nodes of one layer of a full column
-    static constexpr int NW = NT / 4;                     // warps = nodes of one in-plane colour
+    static constexpr int NQ = NT / 4;                     // nodes of one in-plane colour
+    static constexpr int NW = (NQ + 2) / 3;               // warps: three nodes each
     static constexpr int THREADS = NW * 32;
     static constexpr int BJ = TJ + 2, BOX = (TI + 2) * BJ; // solution window of one layer (column + rim)
-    static constexpr int NH = 9 * TI + 9 * TJ;
-    static constexpr int CHUNK = (24 * NT + 36 * (14 * NT + NH) + NT + 15) & ~15;   // bytes of a full column's chunk
+    static constexpr int XE = (3 * BOX + THREADS - 1) / THREADS;   // window entries per thread
+    static constexpr int CHUNK = ccu_col_dims(TI_, TJ_).cb;        // bytes of a full column's chunk
     static constexpr int XLAYER = 3 * BOX * 8;            // bytes of one layer of the solution ring
-    static constexpr int FLAYER = 3 * NT * 8;             // bytes of one layer of the right-hand-side ring
-    static constexpr size_t SMEM = (size_t)S * CHUNK + (size_t)S * XLAYER + (size_t)S * FLAYER + (size_t)S * 8;
+    static constexpr size_t SMEM = (size_t)S * CHUNK + (size_t)S * XLAYER + (size_t)S * 8;
     static_assert(TI_ % 2 == 0 && TJ_ % 2 == 0, "column extents must be even (in-plane colours)");
-    static_assert(3 * BOX <= THREADS, "one thread per solution-window entry");
-    static_assert(S_ >= 4, "ring: three layers in use and at least one in flight");
 };
 
 struct CcuColArgs
 {
     CcuGeom g;
-    const unsigned char *Kc;      // chunks: column-major, per column layers -1 .. noz
+    const unsigned char *Kc;      // chunks: column-major, per column layers 0 .. noz-1
     const size_t *colofs;         // [nI * nJ] byte offset of a column's first chunk
     const double *F;              // MODE 0: right-hand side; MODE 2: rhs of the residual
     double *x;                    // MODE 0: solution (in/out); MODE 1, 2: the vector to multiply
     double *out;                  // MODE 1, 2: result
     int nI, nJ;                   // columns along y and x
-    int cc;                       // MODE 0: column colour of this launch
+    int cc;                       // MODE 0, WF 0: column colour of this launch
     int strip;                    // MODE 1: zero the boundary rows of the product
+    // MODE 0, WF 1: one launch for the four column colours
+    int cstart[5];                // first ticket of the colours 3, 2, 1, 0 and the ticket count
+    unsigned *ticket;             // [4] next ticket, finished CTAs (the last one resets both), epoch (the last one bumps it), pad
+    unsigned *progress;           // [nI * nJ] epoch * CCU_COL_EPOCH + layers finished; the epoch lives on the device so that a
+                                  // launch replayed from a CUDA graph still gets a fresh one and the words never need a reset
 };
+#define CCU_COL_EPOCH 4096u       // > noz of any level
 
 __device__ __forceinline__ unsigned ccu_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ccu_mbar_init(unsigned bar, unsigned count)
@@ -72,10 +84,6 @@ __device__ __forceinline__ void ccu_bulk_g2s(unsigned dst, const void *src, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// Returns v, but the compiler may not assume the value is the same as last time: keeps it from hoisting the dozens of
-// loop-invariant shared-memory addresses derived from v out of the layer loop (they spilled to local memory, and every
-// reload was an L2 round trip in front of an LDS -- ncu r02: 35 % long-scoreboard stalls).
-__device__ __forceinline__ int ccu_opaque(int v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ void ccu_mbar_wait(unsigned bar, unsigned parity)
 {
     unsigned ok;
@@ -85,31 +93,69 @@ __device__ __forceinline__ void ccu_mbar_wait(unsigned bar, unsigned parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while(!ok);
 }
-
-// sum of r over the nine direction lanes q = 0..8 of a row, valid on lane q = 0 (fixed order: deterministic)
-__device__ __forceinline__ double ccu_col_fold9(double r, const int q)
+__device__ __forceinline__ unsigned ccu_ld_acquire(const unsigned *p)
 {
-    const double e = __shfl_down_sync(0xffffffffu, r, 8);          // lane 0 <- lane 8, off the critical path of the tree below
-    double o;
-    o = __shfl_down_sync(0xffffffffu, r, 4); if(q < 4) r += o;
-    o = __shfl_down_sync(0xffffffffu, r, 2); if(q < 2) r += o;
-    o = __shfl_down_sync(0xffffffffu, r, 1); if(q < 1) r += o;
-    return r + e;
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ccu_st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <class SH, int MODE>
-__global__ void __launch_bounds__(SH::THREADS, (SH::SMEM <= 113 * 1024 ? 2 : 1)) ccu_k_col(const __grid_constant__ CcuColArgs A)
+// r[0..2] += B x  (tr = false)  or  B^T x  (tr = true), B = the 3x3 block at `A4`, `B4`, `C1` (ccu_col_coef_ofs)
+__device__ __forceinline__ void ccu_col_block(double (&r)[3], const float4 a, const float4 b, const float c, const bool tr,
+                                              const double x0, const double x1, const double x2)
 {
-    constexpr int TI = SH::TI, TJ = SH::TJ, S = SH::S, BJ = SH::BJ, BOX = SH::BOX, CH = SH::CHUNK, XL = SH::XLAYER, FL = SH::FLAYER;
+    // e = 3 row + col: a = (e0 e1 e2 e3), b = (e4 e5 e6 e7), c = e8; transposing swaps e1/e3, e2/e6, e5/e7
+    const float e1 = tr ? a.w : a.y, e3 = tr ? a.y : a.w, e2 = tr ? b.z : a.z, e6 = tr ? a.z : b.z, e5 = tr ? b.w : b.y, e7 = tr ? b.y : b.w;
+    r[0] += (double)a.x * x0; r[1] += (double)e3 * x0; r[2] += (double)e6 * x0;
+    r[0] += (double)e1 * x1;  r[1] += (double)b.x * x1; r[2] += (double)e7 * x1;
+    r[0] += (double)e2 * x2;  r[1] += (double)e5 * x2;  r[2] += (double)c * x2;
+}
+
+// Row sums over the nine lanes q = 3 tri + mm of a node: returns, on every lane, the total of row mm (taken on q < 3).
+// Within a triple each lane hands the two rows it does not keep to the lanes that keep them, then the three triples add up.
+__device__ __forceinline__ double ccu_col_fold9(const double (&r)[3], const int mm, const int srcA, const int srcB, const int src3, const int src6)
+{
+    const double own = mm == 0 ? r[0] : (mm == 1 ? r[1] : r[2]);
+    const double toA = mm == 0 ? r[2] : (mm == 1 ? r[0] : r[1]);     // row (mm+2)%3: wanted by the lane that reads me in round A
+    const double toB = mm == 0 ? r[1] : (mm == 1 ? r[2] : r[0]);     // row (mm+1)%3: wanted by the lane that reads me in round B
+    const double a = __shfl_sync(0xffffffffu, toA, srcA), b = __shfl_sync(0xffffffffu, toB, srcB);
+    const double s = (own + a) + b;
+    const double s3 = __shfl_sync(0xffffffffu, s, src3), s6 = __shfl_sync(0xffffffffu, s, src6);
+    return (s + s3) + s6;
+}
+
+template <class SH, int MODE, int WF>
+__global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_constant__ CcuColArgs A)
+{
+    constexpr int TI = SH::TI, TJ = SH::TJ, S = SH::S, BJ = SH::BJ, BOX = SH::BOX, CH = SH::CHUNK, XL = SH::XLAYER;
+    constexpr int NQ = SH::NQ, HJ = TJ / 2, XE = SH::XE, NTH = SH::THREADS;
     extern __shared__ __align__(128) unsigned char ccu_col_smem[];
+    __shared__ int s_ticket;
+    __shared__ unsigned s_epoch;
     unsigned char *stg = ccu_col_smem;                                   // [S][CH] stiffness chunks
     unsigned char *xrb = stg + (size_t)S * CH;                           // [S][3][BOX] doubles, solution ring
-    unsigned char *frb = xrb + (size_t)S * XL;                           // [S][3][NT] doubles, right-hand-side ring
-    const unsigned bar0 = ccu_smem_u32(frb + (size_t)S * FL);            // [S] mbarriers
+    const unsigned bar0 = ccu_smem_u32(xrb + (size_t)S * XL);            // [S] mbarriers
     const CcuGeom &g = A.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int I, J;
-    if(MODE == 0)
+    int I, J, mycc = 0;
+    unsigned pbase = 0u;
+    if(MODE == 0 && WF)
+    {
+        if(tid == 0) { s_ticket = (int)atomicAdd(A.ticket, 1u); s_epoch = *(volatile unsigned *)(A.ticket + 2); }
+        __syncthreads();
+        const int t = s_ticket;
+        pbase = s_epoch * CCU_COL_EPOCH;
+        int grp = 0;
+        while(grp < 3 && t >= A.cstart[grp + 1]) grp++;
+        mycc = 3 - grp;
+        const int ci = mycc >> 1, cj = mycc & 1, nJc = (A.nJ - cj + 1) / 2, r = t - A.cstart[grp];
+        I = 2 * (r / nJc) + ci; J = 2 * (r % nJc) + cj;
+    }
+    else if(MODE == 0)
     {
         const int ci = A.cc >> 1, cj = A.cc & 1, nJc = (A.nJ - cj + 1) / 2;
         I = 2 * ((int)blockIdx.x / nJc) + ci; J = 2 * ((int)blockIdx.x % nJc) + cj;
@@ -120,14 +166,17 @@ __global__ void __launch_bounds__(SH::THREADS, (SH::SMEM <= 113 * 1024 ? 2 : 1))
     const unsigned char *chunks = A.Kc + A.colofs[I * A.nJ + J];
     const size_t NS = (size_t)g.NS;
 
-    // ---- per-thread constants: what this lane reads in each in-plane colour (ccu_col_index.h)
+    // ---- per-lane constants (ccu_col_index.h)
+    const int n3 = lane / 9, q = lane % 9, tri = q / 3, mm = q % 3;
     const bool act = lane < 27;
-    const int d = act ? lane / 9 : 0, q = act ? lane % 9 : 0;
-    const bool upd = act && q == 0;
-    const int wa = warp / (TJ / 2), wb = warp % (TJ / 2);
-    int kof[4][3], xof[4], nodeA[4], xself[4], pidx[4];
-    bool nv[4];
-    bool tr[3];
+    const int m = 3 * warp + n3;                         // this lane's node among the NQ nodes of an in-plane colour
+    const int wa = m / HJ, wb = m % HJ;
+    const int lb = 9 * n3;
+    const int srcA = act ? lb + 3 * tri + (mm + 1) % 3 : lane, srcB = act ? lb + 3 * tri + (mm + 2) % 3 : lane;
+    const int src3 = act ? lb + 3 * ((tri + 1) % 3) + mm : lane, src6 = act ? lb + 3 * ((tri + 2) % 3) + mm : lane;
+    const bool upd = act && q < 3;                       // lane q < 3 ends up with row d = q
+    int kA[4][3], xof[4], nodeA[4], xself[4], pidx[4];
+    bool nv[4], tr[3];
 #pragma unroll
     for(int t = 0; t < 3; t++)
     {
@@ -138,62 +187,102 @@ __global__ void __launch_bounds__(SH::THREADS, (SH::SMEM <= 113 * 1024 ? 2 : 1))
     for(int c2 = 0; c2 < 4; c2++)
     {
         const int li = 2 * wa + (c2 >> 1), lj = 2 * wb + (c2 & 1);
-        nv[c2] = li < cd.ti && lj < cd.tj;
+        nv[c2] = act && m < NQ && li < cd.ti && lj < cd.tj;
+        xof[c2] = 0;
 #pragma unroll
         for(int t = 0; t < 3; t++)
         {
             CcuColDesc ds = { 0, 0, 0 };
-            if(nv[c2]) ds = ccu_col_desc(cd, TJ, li, lj, d, q, t);
-            kof[c2][t] = ds.kof; xof[c2] = ds.xof;
+            if(nv[c2]) ds = ccu_col_desc(cd, TJ, li, lj, q, t);
+            kA[c2][t] = cd.kofs + 16 * ds.id; xof[c2] = ds.xof;
         }
         const int gi = i0 + li, gj = j0 + lj;
         nodeA[c2] = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
         xself[c2] = (li + 1) * BJ + (lj + 1);
-        pidx[c2] = li * cd.tj + lj;
+        pidx[c2] = nv[c2] ? li * cd.tj + lj : 0;
     }
-    // ring loaders: thread `tid` owns entry (dx, bn) of every layer of the solution window and entry (fd, fp) of the rhs ring
-    const bool xl = tid < 3 * BOX;
-    const int dx = xl ? tid / BOX : 0, bn = xl ? tid % BOX : 0;
-    const int xgi = i0 + bn / BJ - 1, xgj = j0 + bn % BJ - 1;
-    const bool xin = xl && xgi >= 0 && xgi < g.noy && xgj >= 0 && xgj < g.nox;
-    const size_t xA = xin ? (size_t)dx * NS + (size_t)((4 * (xgi & 1) + 2 * (xgj & 1)) * g.NC + ((xgi >> 1) + 1) * g.JK + ((xgj >> 1) + 1) * g.Kd + 1) : 0;
-    const bool fl = MODE != 1 && tid < 3 * cd.nt;
-    const int fd = fl ? tid / cd.nt : 0, fp = fl ? tid % cd.nt : 0;
-    const int fgi = i0 + fp / cd.tj, fgj = j0 + fp % cd.tj;
-    const size_t fA = fl ? (size_t)fd * NS + (size_t)((4 * (fgi & 1) + 2 * (fgj & 1)) * g.NC + ((fgi >> 1) + 1) * g.JK + ((fgj >> 1) + 1) * g.Kd + 1) : 0;
-    auto xload = [&](int k) -> double { return (xin && k >= 0 && k < noz) ? A.x[xA + (size_t)((k & 1) * g.NC + (k >> 1))] : 0.0; };
-    auto fload = [&](int k) -> double { return (fl && k < noz) ? A.F[fA + (size_t)((k & 1) * g.NC + (k >> 1))] : 0.0; };
-    auto xslot = [&](int slot) -> double * { return (double *)(xrb + (size_t)slot * XL) + dx * BOX + bn; };
-    auto fslot = [&](int slot) -> double * { return (double *)(frb + (size_t)slot * FL) + fd * cd.nt + fp; };
-    auto issue = [&](int layer)        // thread 0: bulk copy of the chunk of `layer` (-1 .. noz) into its ring stage
+    const int oB = 16 * cd.nb, oC = 32 * cd.nb;          // from a block's A entry to its B entry; C entry = kofs + oC + 4 id
+    // solution-window loader: thread `tid` owns entries tid, tid + NTH, ... (dof plane dx, window position bn) of every layer
+    size_t xA[XE];
+    bool xin[XE];
+#pragma unroll
+    for(int e = 0; e < XE; e++)
     {
-        const int s = (layer + S) % S;
+        const int w = tid + e * NTH;
+        const bool xl = w < 3 * BOX;
+        const int dx = xl ? w / BOX : 0, bn = xl ? w % BOX : 0;
+        const int xgi = i0 + bn / BJ - 1, xgj = j0 + bn % BJ - 1;
+        xin[e] = xl && xgi >= 0 && xgi < g.noy && xgj >= 0 && xgj < g.nox;
+        xA[e] = xin[e] ? (size_t)dx * NS + (size_t)((4 * (xgi & 1) + 2 * (xgj & 1)) * g.NC + ((xgi >> 1) + 1) * g.JK + ((xgj >> 1) + 1) * g.Kd + 1) : 0;
+    }
+    auto xload = [&](int e, int k) -> double { return (xin[e] && k >= 0 && k < noz) ? __ldcg(A.x + xA[e] + (size_t)((k & 1) * g.NC + (k >> 1))) : 0.0; };
+    auto xstore = [&](int slot, const double (&v)[XE])
+    {
+#pragma unroll
+        for(int e = 0; e < XE; e++)
+            if(tid + e * NTH < 3 * BOX) ((double *)(xrb + (size_t)slot * XL))[tid + e * NTH] = v[e];
+    };
+    auto issue = [&](int layer)        // thread 0: bulk copy of chunk `layer` (0 .. noz-1) into its ring stage
+    {
+        const int s = layer % S;
         ccu_mbar_expect_tx(bar0 + 8 * s, (unsigned)cd.cb);
-        ccu_bulk_g2s(ccu_smem_u32(stg + (size_t)s * CH), chunks + (size_t)(layer + 1) * cd.cb, (unsigned)cd.cb, bar0 + 8 * s);
+        ccu_bulk_g2s(ccu_smem_u32(stg + (size_t)s * CH), chunks + (size_t)layer * cd.cb, (unsigned)cd.cb, bar0 + 8 * s);
+    };
+    // MODE 0, WF: the columns of earlier colours around this one (a column of colour (ci, cj) has the neighbour colours
+    // (ci ^ |a|, cj ^ |b|)); lane j < 8 of warp 0 watches neighbour j
+    const unsigned *watch = nullptr;
+    unsigned seen = pbase;
+    if(MODE == 0 && WF && warp == 0 && lane < 8)
+    {
+        const int a = (lane < 3) ? -1 : (lane < 5 ? 0 : 1), b = (lane < 3) ? lane - 1 : (lane < 5 ? (lane == 3 ? -1 : 1) : lane - 6);
+        const int nc = 2 * ((mycc >> 1) ^ (a & 1)) + ((mycc & 1) ^ (b & 1));
+        const int In = I + a, Jn = J + b;
+        if(nc > mycc && In >= 0 && In < A.nI && Jn >= 0 && Jn < A.nJ) watch = A.progress + (In * A.nJ + Jn);
+    }
+    auto wait_for = [&](int layers)    // warp 0: until every watched column has finished `layers` layers of this sweep
+    {
+        const unsigned need = pbase + (unsigned)min(layers, noz);
+        if(watch)
+        {   // bounded: a wait that cannot end (it never should: lower tickets run or are done) flags the launch instead of hanging the device
+            unsigned spins = 0;
+            while((int)(seen - need) < 0)
+            {
+                seen = ccu_ld_acquire(watch);
+                if((int)(seen - need) < 0) { __nanosleep(64); if(++spins > (1u << 24)) { A.ticket[3] = 1u; break; } }
+            }
+        }
+        __syncwarp();
     };
 
-    // ---- prologue: barriers, the first S chunks in flight, layers -1, 0, 1 of the solution ring, 0, 1 of the rhs ring
+    // ---- prologue: barriers, zeros where chunk -1 would be, the first S - 1 chunks in flight, layers -1, 0, 1 of the solution ring
     if(tid == 0)
     {
         for(int s = 0; s < S; s++) ccu_mbar_init(bar0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for(int w = tid; w < CH / 16; w += NTH) ((float4 *)(stg + (size_t)(S - 1) * CH))[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if(tid == 0)
-        for(int layer = -1; layer <= S - 2 && layer <= noz; layer++) issue(layer);
-    if(xl)
+        for(int layer = 0; layer <= S - 2 && layer < noz; layer++) issue(layer);
+    if(MODE == 0 && WF) { if(warp == 0) wait_for(2); __syncthreads(); }
     {
-        *xslot(S - 1) = xload(-1);
-        *xslot(0) = xload(0);
-        *xslot(1 % S) = xload(1);
+        double v[XE];
+#pragma unroll
+        for(int e = 0; e < XE; e++) v[e] = xload(e, -1);
+        xstore(S - 1, v);
+#pragma unroll
+        for(int e = 0; e < XE; e++) v[e] = xload(e, 0);
+        xstore(0, v);
+#pragma unroll
+        for(int e = 0; e < XE; e++) v[e] = xload(e, 1);
+        xstore(1, v);
     }
-    if(fl)
-    {
-        *fslot(0) = fload(0);
-        *fslot(1 % S) = fload(1);
-    }
-    ccu_mbar_wait(bar0 + 8 * (S - 1), 0);        // layer -1
-    ccu_mbar_wait(bar0, 0);                      // layer 0
+    double fnx[4] = { 0.0, 0.0, 0.0, 0.0 };                // right-hand side of this lane's rows, one layer ahead
+    if(MODE != 1 && upd)
+#pragma unroll
+        for(int c2 = 0; c2 < 4; c2++)
+            if(nv[c2]) fnx[c2] = A.F[(size_t)q * NS + (size_t)(nodeA[c2] + 0)];
     __syncthreads();
 
     for(int k0 = 0; k0 < noz; k0 += S)
@@ -203,28 +292,40 @@ __global__ void __launch_bounds__(SH::THREADS, (SH::SMEM <= 113 * 1024 ? 2 : 1))
         {
             const int k = k0 + JJ;               // k % S == JJ: ring positions are compile-time constants below
             if(k >= noz) break;
-            const double xpre = xload(k + 2), fpre = fload(k + 2);   // land in the rings before this layer's last barrier
-            ccu_mbar_wait(bar0 + 8 * ((JJ + 1) % S), (unsigned)(((k + 2) / S) & 1));     // chunk of layer k + 1
-            const int zoff = (k & 1) * g.NC + (k >> 1);
-            const unsigned char *own = stg + (size_t)JJ * CH;
-            // product of this lane's block in direction layer t - 1 with the neighbour's values, for a node of colour c2
-            auto prod = [&](const int c2, const int t) -> double
-            {
-                const int ring = (JJ + t - 1 + S) % S;               // layer k + t - 1
-                const unsigned char *kb = stg + (ccu_opaque(kof[c2][t]) + (tr[t] ? ring * CH : JJ * CH));
-                const int st = ccu_opaque(tr[t] ? 12 : 4);
-                const float c0 = *(const float *)kb, c1 = *(const float *)(kb + st), c2f = *(const float *)(kb + 2 * st);
-                const double *xp = (const double *)(xrb + (ring * XL + ccu_opaque(xof[c2])));
-                return (double)c0 * xp[0] + (double)c1 * xp[BOX] + (double)c2f * xp[2 * BOX];
-            };
-            // Everything a row needs from the layers below and above is independent of this layer's colour phases:
-            // all four colours at once, before the phases (MODE 1, 2: the whole row)
-            double acc[4];
+            const int PJ = (JJ + S - 1) % S, NJ = (JJ + 1) % S;      // ring stages of the layers k - 1 and k + 1
+            if(MODE == 0 && WF && warp == 0) wait_for(k + 3);            // layer k + 2 of the rim is final around us
+            if(MODE == 0 && WF) __syncthreads();
+            double xpre[XE], fcur[4];
+#pragma unroll
+            for(int e = 0; e < XE; e++) xpre[e] = xload(e, k + 2);       // lands in the ring before this layer's last barrier
 #pragma unroll
             for(int c2 = 0; c2 < 4; c2++)
             {
-                acc[c2] = 0.0;
-                if(nv[c2] && act) acc[c2] = MODE == 0 ? prod(c2, 0) + prod(c2, 2) : (prod(c2, 0) + prod(c2, 2)) + prod(c2, 1);
+                fcur[c2] = fnx[c2];
+                if(MODE != 1 && upd && nv[c2] && k + 1 < noz) fnx[c2] = A.F[(size_t)q * NS + (size_t)(nodeA[c2] + ((k + 1) & 1) * g.NC + ((k + 1) >> 1))];
+            }
+            ccu_mbar_wait(bar0 + 8 * JJ, (unsigned)((k / S) & 1));       // chunk k (chunk k - 1 arrived a layer ago)
+            const int zoff = (k & 1) * g.NC + (k >> 1);
+            const unsigned char *cur = stg + (size_t)JJ * CH, *prv = stg + (size_t)PJ * CH;
+            // r += the block of direction layer t - 1 times the neighbour's values, for this lane's node of colour c2
+            auto prod = [&](double (&r)[3], const int c2, const int t)
+            {
+                const unsigned char *kb = (t == 0 ? prv : cur) + kA[c2][t];
+                const float4 a = *(const float4 *)kb, b = *(const float4 *)(kb + oB);
+                const float c = *(const float *)((t == 0 ? prv : cur) + cd.kofs + oC + ((kA[c2][t] - cd.kofs) >> 2));
+                const double *xp = (const double *)(xrb + ((t == 0 ? PJ : (t == 1 ? JJ : NJ)) * XL + xof[c2]));
+                ccu_col_block(r, a, b, c, tr[t], xp[0], xp[BOX], xp[2 * BOX]);
+            };
+            // Everything a row needs from the layers below and above is independent of this layer's colour phases:
+            // all four colours at once, before the phases (MODE 1, 2: the whole row)
+            double acc[4][3];
+#pragma unroll
+            for(int c2 = 0; c2 < 4; c2++)
+            {
+                acc[c2][0] = acc[c2][1] = acc[c2][2] = 0.0;
+                prod(acc[c2], c2, 0);
+                prod(acc[c2], c2, 2);
+                if(MODE != 0) prod(acc[c2], c2, 1);
             }
             if(MODE == 0)
             {
@@ -232,27 +333,17 @@ __global__ void __launch_bounds__(SH::THREADS, (SH::SMEM <= 113 * 1024 ? 2 : 1))
                 for(int ph = 0; ph < 4; ph++)
                 {
                     const int c2 = 3 - ph;
-                    const bool v = nv[c2];                         // warp-uniform
-                    if(v)
-                    {
-                        double r = acc[c2];
-                        if(act) r += prod(c2, 1);
-                        r = ccu_col_fold9(r, q);
-                        if(upd)
-                        {   // General_matrix_functions.c:1250-1259: scalar BI per equation, correction rounded to fp32
-                            const double bi = ((const double *)own)[d * cd.nt + pidx[c2]];
-                            const double Fv = ((const double *)(frb + (size_t)JJ * FL))[d * cd.nt + pidx[c2]];
-                            double *xs = (double *)(xrb + (size_t)JJ * XL) + d * BOX + xself[c2];
-                            const double xn = *xs + (double)(float)((Fv - r) * bi);
-                            *xs = xn;
-                            A.x[(size_t)d * NS + (size_t)(nodeA[c2] + zoff)] = xn;
-                        }
+                    prod(acc[c2], c2, 1);
+                    const double r = ccu_col_fold9(acc[c2], mm, srcA, srcB, src3, src6);
+                    if(upd && nv[c2])
+                    {   // General_matrix_functions.c:1250-1259: scalar BI per equation, correction rounded to fp32
+                        const double bi = ((const double *)cur)[q * cd.nt + pidx[c2]];
+                        double *xs = (double *)(xrb + (size_t)JJ * XL) + q * BOX + xself[c2];
+                        const double xn = *xs + (double)(float)((fcur[c2] - r) * bi);
+                        *xs = xn;
+                        A.x[(size_t)q * NS + (size_t)(nodeA[c2] + zoff)] = xn;
                     }
-                    if(ph == 3)
-                    {
-                        if(xl) *xslot((JJ + 2) % S) = xpre;
-                        if(fl) *fslot((JJ + 2) % S) = fpre;
-                    }
+                    if(ph == 3) xstore((JJ + 2) % S, xpre);      // stage of layer k - 1: its last readers were the products above
                     __syncthreads();
                 }
             }
@@ -261,22 +352,29 @@ __global__ void __launch_bounds__(SH::THREADS, (SH::SMEM <= 113 * 1024 ? 2 : 1))
 #pragma unroll
                 for(int c2 = 0; c2 < 4; c2++)
                 {
-                    if(!nv[c2]) continue;                          // warp-uniform
-                    double r = ccu_col_fold9(acc[c2], q);
-                    if(upd)
+                    double r = ccu_col_fold9(acc[c2], mm, srcA, srcB, src3, src6);
+                    if(upd && nv[c2])
                     {
-                        const unsigned char flg = own[cd.flofs + pidx[c2]];
-                        if((MODE == 2 || A.strip) && ((flg >> d) & 1)) r = 0.0;
-                        if(MODE == 2) r = ((const double *)(frb + (size_t)JJ * FL))[d * cd.nt + pidx[c2]] - r;
-                        A.out[(size_t)d * NS + (size_t)(nodeA[c2] + zoff)] = r;
+                        const unsigned char flg = cur[cd.flofs + pidx[c2]];
+                        if((MODE == 2 || A.strip) && ((flg >> q) & 1)) r = 0.0;
+                        if(MODE == 2) r = fcur[c2] - r;
+                        A.out[(size_t)q * NS + (size_t)(nodeA[c2] + zoff)] = r;
                     }
                 }
-                if(xl) *xslot((JJ + 2) % S) = xpre;
-                if(fl) *fslot((JJ + 2) % S) = fpre;
+                __syncthreads();                                     // every product of this layer has read the stage of layer k - 1
+                xstore((JJ + 2) % S, xpre);
                 __syncthreads();
             }
-            if(tid == 0 && k + S - 1 <= noz) issue(k + S - 1);       // the stage of layer k - 1 is free now
+            if(tid == 0)
+            {
+                if(k + S - 1 < noz) issue(k + S - 1);                // the stage of chunk k - 1 is free now
+                if(MODE == 0 && WF) { __threadfence(); ccu_st_release(A.progress + (I * A.nJ + J), pbase + (unsigned)(k + 1)); }
+            }
         }
+    }
+    if(MODE == 0 && WF && tid == 0)
+    {   // the last CTA of the launch resets the ticket counter for the next one
+        if(atomicAdd(A.ticket + 1, 1u) + 1u == (unsigned)A.cstart[4]) { A.ticket[1] = 0u; A.ticket[0] = 0u; A.ticket[2] = s_epoch + 1u; }
     }
 }
 
@@ -289,9 +387,9 @@ __global__ void __launch_bounds__(256) ccu_k_col_relayout(const CcuGeom g, const
                                                            unsigned char *Kc)
 {
     const int col = blockIdx.x, I = col / nJ, J = col % nJ;
-    const int kk = (int)blockIdx.y * 32 + (int)(threadIdx.x & 31);                   // chunk index 0 .. noz + 1 = layer -1 .. noz
-    if(kk > g.noz + 1) return;
+    const int kk = (int)blockIdx.y * 32 + (int)(threadIdx.x & 31);                   // chunk index = layer 0 .. noz - 1
+    if(kk >= g.noz) return;
     const int i0 = I * TI, j0 = J * TJ;
     const CcuColDims cd = ccu_col_dims(min(TI, g.noy - i0), min(TJ, g.nox - j0));
-    ccu_col_fill_chunk(g, cd, i0, j0, kk - 1, K, BI, flags, bits, Kc + colofs[col] + (size_t)kk * cd.cb, threadIdx.x >> 5, blockDim.x >> 5);
+    ccu_col_fill_chunk(g, cd, i0, j0, kk, K, BI, flags, bits, Kc + colofs[col] + (size_t)kk * cd.cb, threadIdx.x >> 5, blockDim.x >> 5);
 }

@@ -5,13 +5,22 @@
 // without a GPU.
 //
 // A COLUMN is TI (y) x TJ (x) nodes spanning all z layers of a multigrid level; columns at the upper mesh edge are
-// clipped to ti x tj.  The stiffness copy `Kc` holds, per column and per z layer k = -1 .. noz (the two out-of-mesh
-// layers are all-zero chunks), one contiguous CHUNK laid out exactly as the kernel wants it in shared memory:
+// clipped to ti x tj.  The stiffness copy `Kc` holds, per column and per z layer k = 0 .. noz-1, one contiguous CHUNK
+// laid out exactly as the kernel wants it in shared memory:
 //
 //     [ BI      : 3 x nt doubles  ]   inverse diagonal (0 for nodes the sweep must skip), nt = ti*tj, p = li*tj + lj
-//     [ blocks  : (14 nt + nh) x 9 floats ]   AoS 3x3 blocks: block id = p*14 + slot for the node's own half-matrix row
-//                                            (slot 0 self, slot b+1 = lower neighbour CCU_LO[b]), then nh HALO blocks
+//     [ blocks  : nb = 14 nt + nh 3x3 blocks ]  block id = p*14 + slot for the half-matrix row of the node p (slot 0
+//                                            self, slot b+1 = lower neighbour CCU_LO[b]), then nh HALO blocks; the nine
+//                                            coefficients e = 3 a + bb of a block sit in three arrays so that a lane reads
+//                                            a whole block with two 128-bit and one 32-bit shared-memory loads:
+//                                            float4 A[nb] (e = 0..3), float4 B[nb] (e = 4..7), float C[nb] (e = 8)
 //     [ flags   : nt bytes ]           boundary-condition flag byte per node (matvec strip)
+//
+// Which LAYER a block of chunk k comes from: the blocks that couple two nodes of the same layer (self and the four
+// in-plane lower neighbours) and those that reach UP (dz = +1) are the ones stored at the nodes of layer k; the blocks
+// that reach DOWN (dz = -1) are those stored at the nodes of layer k+1.  So chunk k = "layer k in-plane" + "everything
+// between layers k and k+1", and the rows of layer k need exactly the chunks k-1 and k (not three layers of blocks):
+// a ring of three chunks in shared memory holds two in use and one in flight.
 //
 // HALO blocks are the blocks stored at nodes OUTSIDE the column (its upper neighbours in y and x) that couple to
 // nodes inside it; the row product of a boundary node needs them transposed.  They are duplicated into the chunk of
@@ -29,16 +38,24 @@
 struct CcuColDims
 {
     int ti, tj, nt, nh;     // clipped column extent, nodes per layer, halo blocks per layer
-    int kofs, flofs, cb;    // byte offsets of the block array and the flags inside a chunk, chunk bytes (multiple of 16)
+    int nb;                 // blocks per chunk
+    int kofs, flofs, cb;    // byte offsets of the block arrays and the flags inside a chunk, chunk bytes (multiple of 16)
 };
-__host__ __device__ inline CcuColDims ccu_col_dims(int ti, int tj)
+__host__ __device__ constexpr inline CcuColDims ccu_col_dims(int ti, int tj)
 {
-    CcuColDims d;
-    d.ti = ti; d.tj = tj; d.nt = ti * tj; d.nh = 9 * ti + 9 * tj;
-    d.kofs = 24 * d.nt;
-    d.flofs = d.kofs + 36 * (14 * d.nt + d.nh);
+    CcuColDims d = { ti, tj, ti * tj, 9 * ti + 9 * tj, 0, 0, 0, 0 };
+    d.nb = 14 * d.nt + d.nh;
+    d.kofs = (24 * d.nt + 15) & ~15;
+    d.flofs = d.kofs + 36 * d.nb;
     d.cb = (d.flofs + d.nt + 15) & ~15;
     return d;
+}
+// byte offset inside a chunk of coefficient e (= 3 a + bb) of block `id`
+__host__ __device__ inline int ccu_col_coef_ofs(const CcuColDims &cd, int id, int e)
+{
+    if(e < 4) return cd.kofs + 16 * id + 4 * e;
+    if(e < 8) return cd.kofs + 16 * cd.nb + 16 * id + 4 * (e - 4);
+    return cd.kofs + 32 * cd.nb + 4 * id;
 }
 
 // index of a lower-neighbour offset (dy, dx, dz) in CCU_LO (ccu_layout.cuh), -1 if the offset is not a lower neighbour
@@ -101,13 +118,14 @@ __host__ __device__ inline void ccu_col_halo_decode(int ti, int tj, int h, int &
     b = r < 3 ? r : r + 6;
 }
 
-// What lane (d, q) of the warp that relaxes node (li, lj) reads for the stencil direction (q / 3 - 1, q % 3 - 1, t - 1):
-//   kof  byte offset, inside the chunk of the layer that stores the block, of the first of its three coefficients
-//   tr   0: the block is the node's own (row d: the coefficients are 4 bytes apart, chunk of the node's layer)
-//        1: the block is stored at the upper neighbour (column d of it: 12 bytes apart, chunk of the neighbour's layer)
+// What lane q (0..8) of the nine lanes that relax node (li, lj) of layer k reads for the stencil direction
+// (di, dj, dk) = (q / 3 - 1, q % 3 - 1, t - 1):
+//   id   the block (ccu_col_coef_ofs), inside chunk k - 1 when dk = -1 and inside chunk k otherwise
+//   tr   0: the block is the node's own (rows = the node's dofs)
+//        1: the block is stored at the upper neighbour (rows = the neighbour's dofs: use it transposed)
 //   xof  byte offset of the neighbour inside one dof plane of a layer of the solution window (box of (TI+2) x (TJ+2))
-struct CcuColDesc { int kof, xof, tr; };
-__host__ __device__ inline CcuColDesc ccu_col_desc(const CcuColDims &cd, int TJ, int li, int lj, int d, int q, int t)
+struct CcuColDesc { int id, xof, tr; };
+__host__ __device__ inline CcuColDesc ccu_col_desc(const CcuColDims &cd, int TJ, int li, int lj, int q, int t)
 {
     const int di = q / 3 - 1, dj = q % 3 - 1, dk = t - 1;
     CcuColDesc r;
@@ -116,22 +134,19 @@ __host__ __device__ inline CcuColDesc ccu_col_desc(const CcuColDims &cd, int TJ,
     const int lo = ccu_lo_index(di, dj, dk);
     if(self || lo >= 0)
     {
-        const int id = (li * cd.tj + lj) * 14 + (self ? 0 : lo + 1);
+        r.id = (li * cd.tj + lj) * 14 + (self ? 0 : lo + 1);
         r.tr = 0;
-        r.kof = cd.kofs + 4 * (9 * id + 3 * d);
         return r;
     }
     const int b = ccu_lo_index(-di, -dj, -dk);                  // the upper neighbour sees this node at CCU_LO[b]
     const int sli = li + di, slj = lj + dj;
-    int id;
-    if(sli >= 0 && sli < cd.ti && slj >= 0 && slj < cd.tj) id = (sli * cd.tj + slj) * 14 + b + 1;
-    else id = 14 * cd.nt + ccu_col_halo_id(cd.ti, cd.tj, sli, slj, b);
+    if(sli >= 0 && sli < cd.ti && slj >= 0 && slj < cd.tj) r.id = (sli * cd.tj + slj) * 14 + b + 1;
+    else r.id = 14 * cd.nt + ccu_col_halo_id(cd.ti, cd.tj, sli, slj, b);
     r.tr = 1;
-    r.kof = cd.kofs + 4 * (9 * id + d);
     return r;
 }
 
-// One chunk of the column stiffness copy: layer k (-1 .. noz) of the column at (i0, j0), filled from the level's
+// One chunk of the column stiffness copy: chunk k (0 .. noz-1) of the column at (i0, j0), filled from the level's
 // coefficient-major arrays.  Work items first, first + stride, ... (a device thread group or a host loop).
 // `bits` (multi-subdomain runs, else null): nodes duplicated on a neighbouring subdomain (bit 1) get BI = 0 in the chunk --
 // the sweep leaves them alone, they are relaxed from their summed rows (ccu_k_face_update).
@@ -139,31 +154,32 @@ __host__ __device__ inline void ccu_col_fill_chunk(const CcuGeom &g, const CcuCo
                                                    const double *BI, const unsigned char *flags, const unsigned char *bits,
                                                    unsigned char *chunk, int first, int stride)
 {
-    const bool inz = k >= 0 && k < g.noz;
     const size_t NS = (size_t)g.NS;
-    for(int w = first; w < 3 * cd.nt; w += stride)
+    for(int w = first; w < cd.kofs / 8; w += stride)
     {
-        const int dd = w / cd.nt, p = w % cd.nt;
         double v = 0.0;
-        if(inz)
+        if(w < 3 * cd.nt)
         {
+            const int dd = w / cd.nt, p = w % cd.nt;
             const int s = ccu_sidx(g, i0 + p / cd.tj, j0 + p % cd.tj, k);
             v = BI[dd * NS + s];
             if(bits && (bits[s] & 2)) v = 0.0;
         }
         ((double *)chunk)[w] = v;
     }
-    float *kb = (float *)(chunk + cd.kofs);
-    for(int id = first; id < 14 * cd.nt + cd.nh; id += stride)
+    for(int id = first; id < cd.nb; id += stride)
     {
         int sli, slj, slot;
         if(id < 14 * cd.nt) { const int p = id / 14; slot = id % 14; sli = p / cd.tj; slj = p % cd.tj; }
         else { int b; ccu_col_halo_decode(cd.ti, cd.tj, id - 14 * cd.nt, sli, slj, b); slot = b + 1; }
+        int di = 0, dj = 0, dk = 0;
+        if(slot) ccu_lo_offset(slot - 1, di, dj, dk);
+        const int ks = dk < 0 ? k + 1 : k;                     // blocks that reach down belong to the layer above
         const int gi = i0 + sli, gj = j0 + slj;
-        const bool in = inz && gi >= 0 && gi < g.noy && gj >= 0 && gj < g.nox;
-        const int s = in ? ccu_sidx(g, gi, gj, k) : 0;
-        for(int e = 0; e < 9; e++) kb[9 * id + e] = in ? K[(size_t)(slot * 9 + e) * NS + s] : 0.0f;
+        const bool in = ks < g.noz && gi >= 0 && gi < g.noy && gj >= 0 && gj < g.nox;
+        const int s = in ? ccu_sidx(g, gi, gj, ks) : 0;
+        for(int e = 0; e < 9; e++) *(float *)(chunk + ccu_col_coef_ofs(cd, id, e)) = in ? K[(size_t)(slot * 9 + e) * NS + s] : 0.0f;
     }
     for(int p = first; p < cd.cb - cd.flofs; p += stride)
-        chunk[cd.flofs + p] = (inz && p < cd.nt) ? flags[ccu_sidx(g, i0 + p / cd.tj, j0 + p % cd.tj, k)] : (unsigned char)0;
+        chunk[cd.flofs + p] = p < cd.nt ? flags[ccu_sidx(g, i0 + p / cd.tj, j0 + p % cd.tj, k)] : (unsigned char)0;
 }

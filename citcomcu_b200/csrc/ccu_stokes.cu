@@ -113,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -166,6 +166,7 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_COL_NODES: c->opt_col_nodes = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_RELAX_COL: c->opt_relax_col = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_MATVEC_COL: c->opt_matvec_col = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_COL_WF: c->opt_col_wf = value != 0; if(c->coarse) c->coarse->opt_col_wf = c->opt_col_wf; drop_graphs(c); return 0;
     case CCU_OPT_COL_SHAPE: if(value < 0 || value > 2) FAIL("column shape must be 0..2"); c->opt_col_shape = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
     case CCU_OPT_COOP_NODES: c->opt_coop_nodes = value; if(c->coarse) c->coarse->opt_coop_nodes = value; drop_graphs(c); return 0;
@@ -344,44 +345,58 @@ static int read_scal(ccu_ctx *c, int first, int count, double *out)
 static void d_strip(ccu_ctx *c, Level &L, double *v) { LAUNCH(c, ccu_k_strip, cdiv(L.g.NS, 256), 256, L.g, L.flags, v); }
 
 // ---- column-resident kernels (ccu_col.cuh)
-typedef CcuColShape<8, 4, 5> ColA;      // 256 threads, 109 KB: two CTAs per SM
-typedef CcuColShape<8, 8, 5> ColB;      // 512 threads, 207 KB: one CTA per SM, 16 % halo blocks instead of 24 %
-typedef CcuColShape<4, 4, 6> ColC;      // 128 threads, 64 KB: three CTAs per SM (small subdomains: more columns)
-template <class SH, int MODE>
+typedef CcuColShape<6, 8, 2> ColA;      // 128 threads, 93 KB: two CTAs per SM, 19 % halo blocks
+typedef CcuColShape<12, 8, 1> ColB;     // 256 threads, 182 KB: one CTA per SM, 13 % halo blocks
+typedef CcuColShape<4, 8, 3> ColC;      // 96 threads, 67 KB: three CTAs per SM (small subdomains: more columns)
+template <class SH, int MODE, int WF>
 static int launch_col(ccu_ctx *c, Level &L, int cc, const double *F, double *x, double *out, int strip)
 {
     CcuColArgs A;
     A.g = L.g; A.Kc = L.Kc; A.colofs = L.colofs; A.F = F; A.x = x; A.out = out;
     A.nI = L.col_nI; A.nJ = L.col_nJ; A.cc = cc; A.strip = strip;
+    A.ticket = nullptr; A.progress = nullptr;
+    for(int q = 0; q < 5; q++) A.cstart[q] = 0;
     unsigned grid = (unsigned)(A.nI * A.nJ);
-    if(MODE == 0) grid = (unsigned)(((A.nI - (cc >> 1) + 1) / 2) * ((A.nJ - (cc & 1) + 1) / 2));
+    if(MODE == 0 && !WF) grid = (unsigned)(((A.nI - (cc >> 1) + 1) / 2) * ((A.nJ - (cc & 1) + 1) / 2));
+    if(MODE == 0 && WF)
+    {   // tickets in colour order 3, 2, 1, 0
+        for(int grp = 0; grp < 4; grp++)
+        {
+            const int col = 3 - grp;
+            A.cstart[grp + 1] = A.cstart[grp] + ((A.nI - (col >> 1) + 1) / 2) * ((A.nJ - (col & 1) + 1) / 2);
+        }
+        A.ticket = L.col_sync; A.progress = L.col_sync + 4;
+    }
     if(!grid) return 0;
-    ccu_k_col<SH, MODE><<<grid, SH::THREADS, SH::SMEM, c->st>>>(A);
+    ccu_k_col<SH, MODE, WF><<<grid, SH::THREADS, SH::SMEM, c->st>>>(A);
     c->launches++;
     return 0;
 }
-template <int MODE>
+template <int MODE, int WF>
 static int launch_col_shape(ccu_ctx *c, Level &L, int cc, const double *F, double *x, double *out, int strip)
 {
-    if(L.col_shape == 1) return launch_col<ColB, MODE>(c, L, cc, F, x, out, strip);
-    if(L.col_shape == 2) return launch_col<ColC, MODE>(c, L, cc, F, x, out, strip);
-    return launch_col<ColA, MODE>(c, L, cc, F, x, out, strip);
+    if(L.col_shape == 1) return launch_col<ColB, MODE, WF>(c, L, cc, F, x, out, strip);
+    if(L.col_shape == 2) return launch_col<ColC, MODE, WF>(c, L, cc, F, x, out, strip);
+    return launch_col<ColA, MODE, WF>(c, L, cc, F, x, out, strip);
 }
 template <class SH>
 static int col_attrs()
 {   // more than 48 KB of dynamic shared memory needs the opt-in, per device; set for the current device of the caller
-    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
-    CK(cudaFuncSetAttribute(ccu_k_col<SH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
-    CK(cudaFuncSetAttribute(ccu_k_col<SH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
-    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(ccu_k_col<SH, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(ccu_k_col<SH, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::SMEM));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(ccu_k_col<SH, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 template <int TI, int TJ>
 static int col_relayout(ccu_ctx *c, Level &L, int lev)
 {
     const CcuGeom &g = L.g;
+    if((unsigned)g.noz + 8u >= CCU_COL_EPOCH) FAIL("column kernels: more z layers than the progress words can count");
     const int nI = (g.noy + TI - 1) / TI, nJ = (g.nox + TJ - 1) / TJ;
     std::vector<size_t> ofs((size_t)nI * nJ);
     size_t total = 0;
@@ -389,21 +404,23 @@ static int col_relayout(ccu_ctx *c, Level &L, int lev)
         for(int J = 0; J < nJ; J++)
         {
             ofs[(size_t)I * nJ + J] = total;
-            total += (size_t)(g.noz + 2) * ccu_col_dims(std::min(TI, g.noy - I * TI), std::min(TJ, g.nox - J * TJ)).cb;
+            total += (size_t)g.noz * ccu_col_dims(std::min(TI, g.noy - I * TI), std::min(TJ, g.nox - J * TJ)).cb;
         }
     if(total > L.Kc_bytes || L.col_nI != nI || L.col_nJ != nJ)
     {
-        cudaFree(L.Kc); cudaFree(L.colofs);
-        L.Kc = nullptr; L.colofs = nullptr; L.Kc_bytes = 0;
+        cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync);
+        L.Kc = nullptr; L.colofs = nullptr; L.col_sync = nullptr; L.Kc_bytes = 0;
         CK(cudaMalloc(&L.Kc, total));
         CK(cudaMalloc(&L.colofs, sizeof(size_t) * ofs.size()));
+        CK(cudaMalloc(&L.col_sync, sizeof(unsigned) * (4 + ofs.size())));
+        CK(cudaMemsetAsync(L.col_sync, 0, sizeof(unsigned) * (4 + ofs.size()), c->st));
         L.Kc_bytes = total;
     }
     CK(cudaMemcpyAsync(L.colofs, ofs.data(), sizeof(size_t) * ofs.size(), cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));               // `ofs` leaves scope
     L.col_nI = nI; L.col_nJ = nJ;
     const unsigned char *bits = c->multi() ? c->comm->halo[lev].bits : nullptr;
-    LAUNCH(c, (ccu_k_col_relayout<TI, TJ>), dim3((unsigned)(nI * nJ), (unsigned)((g.noz + 2 + 31) / 32)), 256, g, nJ, L.colofs, L.K, L.BI, L.flags, bits, L.Kc);
+    LAUNCH(c, (ccu_k_col_relayout<TI, TJ>), dim3((unsigned)(nI * nJ), (unsigned)((g.noz + 31) / 32)), 256, g, nJ, L.colofs, L.K, L.BI, L.flags, bits, L.Kc);
     return 0;
 }
 // The column kernels read a column-major copy of the level's stiffness, inverse diagonal and flags: (re)made whenever
@@ -415,9 +432,9 @@ int ccu_col_refresh(ccu_ctx *c, int lev)
     L.col_shape = -1;
     if(!(c->opt_relax_col || c->opt_matvec_col) || L.g.nno <= c->opt_col_nodes || !L.have_K || !L.have_flags) return 0;
     int rc;
-    if(c->opt_col_shape == 1) rc = col_attrs<ColB>() || col_relayout<8, 8>(c, L, lev);
-    else if(c->opt_col_shape == 2) rc = col_attrs<ColC>() || col_relayout<4, 4>(c, L, lev);
-    else rc = col_attrs<ColA>() || col_relayout<8, 4>(c, L, lev);
+    if(c->opt_col_shape == 1) rc = col_attrs<ColB>() || col_relayout<ColB::TI, ColB::TJ>(c, L, lev);
+    else if(c->opt_col_shape == 2) rc = col_attrs<ColC>() || col_relayout<ColC::TI, ColC::TJ>(c, L, lev);
+    else rc = col_attrs<ColA>() || col_relayout<ColA::TI, ColA::TJ>(c, L, lev);
     if(rc) return rc;
     L.col_shape = c->opt_col_shape;
     return 0;
@@ -430,7 +447,7 @@ static int col_refresh_all(ccu_ctx *c)
     if(c->coarse)
     {
         c->coarse->opt_col_nodes = c->opt_col_nodes; c->coarse->opt_relax_col = c->opt_relax_col; c->coarse->opt_matvec_col = c->opt_matvec_col;
-        c->coarse->opt_col_shape = c->opt_col_shape;
+        c->coarse->opt_col_shape = c->opt_col_shape; c->coarse->opt_col_wf = c->opt_col_wf;
         return col_refresh_all(c->coarse);
     }
     return 0;
@@ -451,7 +468,7 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);   // the table-driven kernel wins from ~1e4 nodes up
-    if(use_col(c, L, c->opt_matvec_col)) launch_col_shape<1>(c, L, 0, nullptr, const_cast<double *>(u), Au, strip);
+    if(use_col(c, L, c->opt_matvec_col)) launch_col_shape<1, 0>(c, L, 0, nullptr, const_cast<double *>(u), Au, strip);
     else if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab == 24) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
@@ -473,7 +490,7 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);
-    if(use_col(c, L, c->opt_matvec_col)) { launch_col_shape<2>(c, L, 0, rhs, const_cast<double *>(u), out, 1); return; }
+    if(use_col(c, L, c->opt_matvec_col)) { launch_col_shape<2, 0>(c, L, 0, rhs, const_cast<double *>(u), out, 1); return; }
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab == 24) { LAUNCH(c, (ccu_k_matvec_tab<1, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
@@ -615,7 +632,7 @@ static void relax_faces(ccu_ctx *c, Level &L, double *x, const double *F)
 }
 static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
 {
-    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], (use_col(c, L, c->opt_relax_col) ? 4LL : 8LL) * cycles);
+    CcuProfScope ps(c, CCU_PROF_RELAX_FINE, &L == &c->L[c->cfg.levmax], (use_col(c, L, c->opt_relax_col) ? (c->opt_col_wf ? 1LL : 4LL) : 8LL) * cycles);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, cycles);
     if(use_col(c, L, c->opt_relax_col))
     {   // column order: column colours 3..0, z ascending inside a column, (y, x)-parity colours 3..0 inside a layer (ccu_col.cuh)
@@ -623,7 +640,9 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         for(int s = 0; s < cycles; s++)
         {
             if(multi) relax_faces(c, L, x, F);
-            for(int cc = 3; cc >= 0; cc--) launch_col_shape<0>(c, L, cc, F, x, nullptr, 0);
+            if(c->opt_col_wf) launch_col_shape<0, 1>(c, L, 0, F, x, nullptr, 0);
+            else
+                for(int cc = 3; cc >= 0; cc--) launch_col_shape<0, 0>(c, L, cc, F, x, nullptr, 0);
         }
         return;
     }

@@ -54,12 +54,14 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
        CCU_OPT_CLUSTER_NODES = 8 /* single-subdomain levels with nno <= this run a whole smoother call in one 8-CTA cluster launch */,
        CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */,
        /* column-resident kernels (csrc/ccu_col.cuh) on levels with nno > COL_NODES (default 500000): RELAX_COL / MATVEC_COL
-        * (default 1) switch them on or off; COL_SHAPE 0 = columns of 8 (y) x 4 (x) nodes, two CTAs per SM, 1 = 8 x 8, one CTA
-        * per SM, 2 = 4 x 4, three CTAs per SM.  A CTA streams the stiffness of its column through shared memory with one bulk
+        * (default 1) switch them on or off; COL_SHAPE 0 = columns of 6 (y) x 8 (x) nodes, two CTAs per SM, 1 = 12 x 8, one CTA
+        * per SM, 2 = 4 x 8, three CTAs per SM.  A CTA streams the stiffness of its column through shared memory with one bulk
         * asynchronous copy per z layer, so every coefficient crosses HBM once per sweep.  The column smoother is a Gauss-Seidel
         * sweep in column order (column colours 3..0, z ascending, (y,x)-parity colours 3..0 inside a layer) instead of the plain
-        * 8-colour order; oracle/restate.c ccu_r_ordered_gs mode 10 is its CPU statement. */
-       CCU_OPT_COL_NODES = 9, CCU_OPT_RELAX_COL = 10, CCU_OPT_MATVEC_COL = 11, CCU_OPT_COL_SHAPE = 13,
+        * 8-colour order; oracle/restate.c ccu_r_ordered_gs mode 10 is its CPU statement.  COL_WF 1 (default): the four column
+        * colours of a sweep run in one launch, columns waiting on progress words of their neighbours; 0: one launch per colour
+        * (bitwise the same result). */
+       CCU_OPT_COL_NODES = 9, CCU_OPT_RELAX_COL = 10, CCU_OPT_MATVEC_COL = 11, CCU_OPT_COL_SHAPE = 13, CCU_OPT_COL_WF = 14,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */,
        CCU_OPT_COOP_NODES = 16 /* single-subdomain levels with SMALL_NODES < nno <= this (default 0 = off: measured no faster than the graph-replayed per-pass launches) run each smoother call as one

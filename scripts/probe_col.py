@@ -73,8 +73,11 @@ print(json.dumps(out), flush=True)
 f = ctx.strip_bcs_from_residual(rng.uniform(-1, 1, 3 * nno), lm)
 ctx.vec_upload(lm, "RHS", f)
 tm = {}
-for name, opts in (("colour", dict(relax_col=0, matvec_col=0)), ("col0", dict(relax_col=1, matvec_col=1, col_shape=0)),
-                   ("col1", dict(relax_col=1, matvec_col=1, col_shape=1)), ("col2", dict(relax_col=1, matvec_col=1, col_shape=2))):
+xfin = {}
+for name, opts in (("colour", dict(relax_col=0, matvec_col=0)), ("col0", dict(relax_col=1, matvec_col=1, col_shape=0, col_wf=1)),
+                   ("col0_4l", dict(relax_col=1, matvec_col=1, col_shape=0, col_wf=0)),
+                   ("col1", dict(relax_col=1, matvec_col=1, col_shape=1, col_wf=1)), ("col1_4l", dict(relax_col=1, matvec_col=1, col_shape=1, col_wf=0)),
+                   ("col2", dict(relax_col=1, matvec_col=1, col_shape=2, col_wf=1)), ("col2_4l", dict(relax_col=1, matvec_col=1, col_shape=2, col_wf=0))):
     for k, v in opts.items():
         ctx.set_option(k, v)
     ctx.vec_upload(lm, "VEL", np.zeros(3 * nno))
@@ -87,6 +90,9 @@ for name, opts in (("colour", dict(relax_col=0, matvec_col=0)), ("col0", dict(re
     # convergence sanity: residual norm after 6 sweeps from zero
     ctx.vec_upload(lm, "VEL", np.zeros(3 * nno))
     ctx.dev_relax_sweeps(lm, "VEL", "RHS", 6)
+    xfin[name] = ctx.vec_download(lm, "VEL")
+    if name.endswith("_4l"):      # one launch per sweep (progress words) must be bitwise the four-launch result
+        tm[f"wf_bitwise_{name[:-3]}"] = bool(np.array_equal(xfin[name], xfin[name[:-3]]))
     ctx.set_option("matvec_col", 0)
     ctx.dev_matvec(lm, "VEL", "AU", 1)
     r = f - ctx.vec_download(lm, "AU")

@@ -1,7 +1,7 @@
 // col_emul.cpp -- HOST emulation of the column-resident smoother / matvec kernel (csrc/ccu_col.cuh), test infrastructure.
 //
-// It re-states the kernel's control flow (ring of S stiffness chunks filled at the kernel's own issue points, ring of S
-// solution layers, one "warp" per node with 27 lanes (d, q) x 3 directions, the shuffle fold order, the update) on
+// It re-states the kernel's control flow (ring of S = 3 stiffness chunks filled at the kernel's own issue points, ring of S
+// solution layers, nine lanes q per node x 3 layer directions x all three rows, the fold order, the update) on
 // the CPU, using the SAME index functions (csrc/ccu_col_index.h: chunk layout, halo block ids, lane descriptors,
 // chunk fill) the device code uses.  tests/test_col_emul.py compares it with the oracle's column-ordered Gauss-Seidel
 // (oracle/restate.c mode 10) and the reference's matvec known answers, so that the index logic and the ring schedule
@@ -33,8 +33,8 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
     const size_t NS = (size_t)g.NS;
     std::vector<unsigned char> stg((size_t)S * CH, 0xff);          // poison: reads of an unfilled stage show up as NaN
     std::vector<double> xr((size_t)S * 3 * BOX, 1e300);
-    const int NW = TI * TJ / 4;
-    auto issue = [&](int layer) { memcpy(stg.data() + (size_t)((layer + S) % S) * CH, chunks + (size_t)(layer + 1) * cd.cb, cd.cb); };
+    const int NQ = TI * TJ / 4, HJ = TJ / 2;
+    auto issue = [&](int layer) { memcpy(stg.data() + (size_t)(layer % S) * CH, chunks + (size_t)layer * cd.cb, cd.cb); };
     auto xload = [&](int tid, int k) -> double
     {
         const int dx = tid / BOX, bn = tid % BOX, gi = i0 + bn / BJ - 1, gj = j0 + bn % BJ - 1;
@@ -42,73 +42,74 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
         const size_t xA = (size_t)dx * NS + (size_t)((4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1);
         return x[xA + (size_t)((k & 1) * g.NC + (k >> 1))];
     };
-    for(int layer = -1; layer <= S - 2 && layer <= noz; layer++) issue(layer);
+    memset(stg.data() + (size_t)(S - 1) * CH, 0, CH);              // where chunk -1 would be
+    for(int layer = 0; layer <= S - 2 && layer < noz; layer++) issue(layer);
     for(int tid = 0; tid < 3 * BOX; tid++)
     {
         xr[(size_t)(S - 1) * 3 * BOX + tid] = xload(tid, -1);
         xr[(size_t)0 * 3 * BOX + tid] = xload(tid, 0);
-        xr[(size_t)(1 % S) * 3 * BOX + tid] = xload(tid, 1);
+        xr[(size_t)1 * 3 * BOX + tid] = xload(tid, 1);
     }
     std::vector<double> xpre(3 * BOX);
     for(int k = 0; k < noz; k++)
     {
-        const int JJ = k % S;
+        const int JJ = k % S, PJ = (JJ + S - 1) % S, NJ = (JJ + 1) % S;
         for(int tid = 0; tid < 3 * BOX; tid++) xpre[tid] = xload(tid, k + 2);
         const int zoff = (k & 1) * g.NC + (k >> 1);
-        const unsigned char *own = stg.data() + (size_t)JJ * CH;
+        const unsigned char *cur = stg.data() + (size_t)JJ * CH, *prv = stg.data() + (size_t)PJ * CH;
         for(int ph = 0; ph < 4; ph++)
         {
             const int c2 = mode == 0 ? 3 - ph : ph;
-            for(int warp = 0; warp < NW; warp++)
+            for(int m = 0; m < NQ; m++)
             {
-                const int wa = warp / (TJ / 2), wb = warp % (TJ / 2);
+                const int wa = m / HJ, wb = m % HJ;
                 const int li = 2 * wa + (c2 >> 1), lj = 2 * wb + (c2 & 1);
                 if(!(li < cd.ti && lj < cd.tj)) continue;
-                double r[32] = { 0 };
-                for(int lane = 0; lane < 27; lane++)
+                double r[9][3];
+                for(int q = 0; q < 9; q++)
                 {
-                    const int d = lane / 9, q = lane % 9;
-                    double rt[3];
-                    for(int t = 0; t < 3; t++)
+                    double acc[3] = { 0, 0, 0 };
+                    const int order[3] = { 0, 2, 1 };                // layers below and above first, then the same layer
+                    for(int oi = 0; oi < 3; oi++)
                     {
-                        const CcuColDesc ds = ccu_col_desc(cd, TJ, li, lj, d, q, t);
-                        const int ring = (JJ + t - 1 + S) % S;
-                        const unsigned char *kb = (ds.tr ? stg.data() + (size_t)ring * CH : own) + ds.kof;
-                        const int st = ds.tr ? 12 : 4;
-                        float c0, c1, c2f;
-                        memcpy(&c0, kb, 4); memcpy(&c1, kb + st, 4); memcpy(&c2f, kb + 2 * st, 4);
+                        const int t = order[oi];
+                        const CcuColDesc ds = ccu_col_desc(cd, TJ, li, lj, q, t);
+                        const unsigned char *ck = t == 0 ? prv : cur;
+                        float e[9];
+                        for(int ee = 0; ee < 9; ee++) memcpy(&e[ee], ck + ccu_col_coef_ofs(cd, ds.id, ee), 4);
+                        const int ring = t == 0 ? PJ : (t == 1 ? JJ : NJ);
                         const double *xp = (const double *)((const unsigned char *)xr.data() + (size_t)ring * 3 * BOX * 8 + ds.xof);
-                        rt[t] = (double)c0 * xp[0] + (double)c1 * xp[BOX] + (double)c2f * xp[2 * BOX];
+                        const double xv[3] = { xp[0], xp[BOX], xp[2 * BOX] };
+                        for(int bb = 0; bb < 3; bb++)
+                            for(int a = 0; a < 3; a++) acc[a] += (double)(ds.tr ? e[3 * bb + a] : e[3 * a + bb]) * xv[bb];
                     }
-                    r[lane] = (rt[0] + rt[2]) + rt[1];      // pre-phase (layers below and above) first, then the same-layer block
+                    for(int a = 0; a < 3; a++) r[q][a] = acc[a];
                 }
-                // the kernel's shuffle fold (ccu_col_fold9): lane 8 aside, a three-step tree over lanes 0..7, then + lane 8
+                // the kernel's fold (ccu_col_fold9): inside a triple of lanes, then over the three triples
+                double row[3];
                 for(int d = 0; d < 3; d++)
                 {
-                    double *v = r + 9 * d;
-                    const double e = v[8];
-                    for(int i = 0; i < 4; i++) v[i] += v[i + 4];
-                    for(int i = 0; i < 2; i++) v[i] += v[i + 2];
-                    v[0] += v[1];
-                    v[0] += e;
+                    double s[3];
+                    for(int tri = 0; tri < 3; tri++) s[tri] = (r[3 * tri + d][d] + r[3 * tri + (d + 1) % 3][d]) + r[3 * tri + (d + 2) % 3][d];
+                    row[d] = (s[0] + s[1]) + s[2];
                 }
                 const int gi = i0 + li, gj = j0 + lj;
                 const int nodeA = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
                 for(int d = 0; d < 3; d++)
                 {
                     const size_t sn = (size_t)d * NS + (size_t)(nodeA + zoff);
-                    const double rr = r[9 * d];
+                    const double rr = row[d];
                     const int p = li * cd.tj + lj;
                     if(mode == 0)
                     {
-                        const double bi = ((const double *)own)[d * cd.nt + p];
+                        const double bi = ((const double *)cur)[d * cd.nt + p];
                         double *xs = xr.data() + (size_t)JJ * 3 * BOX + d * BOX + (li + 1) * BJ + (lj + 1);
                         const double xn = *xs + (double)(float)((F[sn] - rr) * bi);
                         *xs = xn; x[sn] = xn;
                     }
                     else
                     {
-                        const unsigned char fl = own[cd.flofs + p];
+                        const unsigned char fl = cur[cd.flofs + p];
                         double a = rr;
                         if((mode == 2 || strip) && ((fl >> d) & 1)) a = 0.0;
                         out[sn] = mode == 1 ? a : F[sn] - a;
@@ -117,7 +118,7 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
             }
             if(ph == 3) for(int tid = 0; tid < 3 * BOX; tid++) xr[(size_t)((JJ + 2) % S) * 3 * BOX + tid] = xpre[tid];
         }
-        if(k + S - 1 <= noz) issue(k + S - 1);
+        if(k + S - 1 < noz) issue(k + S - 1);
     }
 }
 }
@@ -169,15 +170,15 @@ extern "C" int ccu_col_emul(int nox, int noy, int noz, int TI, int TJ, int S, in
         for(int J = 0; J < E.nJ; J++)
         {
             E.colofs[I * E.nJ + J] = total;
-            total += (size_t)(noz + 2) * ccu_col_dims(std::min(TI, noy - I * TI), std::min(TJ, nox - J * TJ)).cb;
+            total += (size_t)noz * ccu_col_dims(std::min(TI, noy - I * TI), std::min(TJ, nox - J * TJ)).cb;
         }
     E.Kc.assign(total, 0xee);
     for(int I = 0; I < E.nI; I++)
         for(int J = 0; J < E.nJ; J++)
         {
             const CcuColDims cd = ccu_col_dims(std::min(TI, noy - I * TI), std::min(TJ, nox - J * TJ));
-            for(int kk = 0; kk <= noz + 1; kk++)
-                ccu_col_fill_chunk(g, cd, I * TI, J * TJ, kk - 1, E.K.data(), E.BI.data(), E.flags.data(), nullptr,
+            for(int kk = 0; kk < noz; kk++)
+                ccu_col_fill_chunk(g, cd, I * TI, J * TJ, kk, E.K.data(), E.BI.data(), E.flags.data(), nullptr,
                                    E.Kc.data() + E.colofs[I * E.nJ + J] + (size_t)kk * cd.cb, 0, 1);
         }
     if(mode == 0)

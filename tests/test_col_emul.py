@@ -48,7 +48,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("name", ["busse_l3", "tdepv_l3", "input1_cart_l3"])
-@pytest.mark.parametrize("shape,S", [((8, 4), 5), ((8, 8), 5), ((4, 4), 4), ((2, 2), 6)])
+@pytest.mark.parametrize("shape,S", [((6, 8), 3), ((12, 8), 3), ((4, 8), 3), ((2, 2), 3)])
 def test_column_kernel_model_matches_oracle(emul, oracle_built, name, shape, S):
     d = get_case(name)[0]
     R = po.Restate(d, smoother=20)

@@ -199,7 +199,7 @@ def test_kernel_variants_agree(case, opts):
     ctx.close()
 
 
-COL_SHAPES = {0: (8, 4), 1: (8, 8), 2: (4, 4)}
+COL_SHAPES = {0: (6, 8), 1: (12, 8), 2: (4, 8)}
 
 
 @pytest.mark.parametrize("name", ["busse_l3", "tdepv_l3", "input1_cart_l3", "tdepv_tall"])
