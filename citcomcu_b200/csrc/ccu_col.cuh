@@ -11,6 +11,8 @@
 //     k-1 and k: a ring of three holds two in use and one in flight;
 //   * the solution values of the column plus a one-node rim live in a ring of three layers in shared memory, filled two
 //     layers ahead by plain loads (their sectors are shared by the layers of equal parity: L2 hits);
+//   * a CTA = two groups of compute warps (in-plane colours 3, 1 and 2, 0) + one service warp that issues the bulk
+//     copies and handles the progress words, so that no compute warp ever executes a memory fence;
 //   * NINE lanes relax one node (three nodes per warp): lane q owns the in-plane direction (q/3-1, q%3-1) and
 //     multiplies the three 3x3 blocks towards the layers below, same and above with the neighbour's three values
 //     for all three rows; a block is two 128-bit and one 32-bit shared-memory loads, used as stored or transposed
@@ -41,10 +43,11 @@ struct CcuColShape
     static constexpr int TI = TI_, TJ = TJ_, S = 3, CTAS = CTAS_;
     static constexpr int NT = TI * TJ;                    // nodes of one layer of a full column
     static constexpr int NQ = NT / 4;                     // nodes of one in-plane colour
-    static constexpr int NW = (NQ + 2) / 3;               // warps: three nodes each
-    static constexpr int THREADS = NW * 32;
+    static constexpr int NW = (NQ + 2) / 3;               // warps per colour: three nodes each
+    static constexpr int NTC = 2 * NW * 32;               // compute threads: two warp groups, two colours each
+    static constexpr int THREADS = NTC + 32;              // + the service warp (bulk copies, progress words)
     static constexpr int BJ = TJ + 2, BOX = (TI + 2) * BJ; // solution window of one layer (column + rim)
-    static constexpr int XE = (3 * BOX + THREADS - 1) / THREADS;   // window entries per thread
+    static constexpr int XE = (3 * BOX + NTC - 1) / NTC;  // window entries per compute thread
     static constexpr int CHUNK = ccu_col_dims(TI_, TJ_).cb;        // bytes of a full column's chunk
     static constexpr int XLAYER = 3 * BOX * 8;            // bytes of one layer of the solution ring
     static constexpr size_t SMEM = (size_t)S * CHUNK + (size_t)S * XLAYER + (size_t)S * 8;
@@ -128,11 +131,13 @@ __device__ __forceinline__ double ccu_col_fold9(const double (&r)[3], const int 
     return (s + s3) + s6;
 }
 
+__device__ __forceinline__ void ccu_bar_sync(const int id, const int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 template <class SH, int MODE, int WF>
 __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_constant__ CcuColArgs A)
 {
     constexpr int TI = SH::TI, TJ = SH::TJ, S = SH::S, BJ = SH::BJ, BOX = SH::BOX, CH = SH::CHUNK, XL = SH::XLAYER;
-    constexpr int NQ = SH::NQ, HJ = TJ / 2, XE = SH::XE, NTH = SH::THREADS;
+    constexpr int NQ = SH::NQ, NW = SH::NW, HJ = TJ / 2, XE = SH::XE, NTC = SH::NTC, NTH = SH::THREADS;
     extern __shared__ __align__(128) unsigned char ccu_col_smem[];
     __shared__ int s_ticket;
     __shared__ unsigned s_epoch;
@@ -164,19 +169,86 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
     const int i0 = I * TI, j0 = J * TJ, noz = g.noz;
     const CcuColDims cd = ccu_col_dims(min(TI, g.noy - i0), min(TJ, g.nox - j0));
     const unsigned char *chunks = A.Kc + A.colofs[I * A.nJ + J];
-    const size_t NS = (size_t)g.NS;
 
-    // ---- per-lane constants (ccu_col_index.h)
+    // ---- prologue: barriers, zeros where chunk -1 would be
+    if(tid == 0)
+    {
+        for(int s = 0; s < S; s++) ccu_mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for(int w = tid; w < CH / 16; w += NTH) ((float4 *)(stg + (size_t)(S - 1) * CH))[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if(warp == 2 * NW)
+    {   // ================= service warp: bulk copies of the chunks, progress words of the one-launch sweep
+        auto issue = [&](int layer)        // lane 0: chunk `layer` (0 .. noz-1) into its ring stage
+        {
+            const int s = layer % S;
+            ccu_mbar_expect_tx(bar0 + 8 * s, (unsigned)cd.cb);
+            ccu_bulk_g2s(ccu_smem_u32(stg + (size_t)s * CH), chunks + (size_t)layer * cd.cb, (unsigned)cd.cb, bar0 + 8 * s);
+        };
+        if(lane == 0)
+            for(int layer = 0; layer <= S - 2 && layer < noz; layer++) issue(layer);
+        // the columns of earlier colours around this one (a column of colour (ci, cj) has the neighbour colours
+        // (ci ^ |a|, cj ^ |b|)); lane j < 8 watches neighbour j
+        const unsigned *watch = nullptr;
+        unsigned seen = pbase;
+        if(MODE == 0 && WF && lane < 8)
+        {
+            const int a = (lane < 3) ? -1 : (lane < 5 ? 0 : 1), b = (lane < 3) ? lane - 1 : (lane < 5 ? (lane == 3 ? -1 : 1) : lane - 6);
+            const int nc = 2 * ((mycc >> 1) ^ (a & 1)) + ((mycc & 1) ^ (b & 1));
+            const int In = I + a, Jn = J + b;
+            if(nc > mycc && In >= 0 && In < A.nI && Jn >= 0 && Jn < A.nJ) watch = A.progress + (In * A.nJ + Jn);
+        }
+        auto wait_for = [&](int layers)    // until every watched column has finished `layers` layers of this sweep
+        {
+            const unsigned need = pbase + (unsigned)min(layers, noz);
+            if(watch)
+            {   // bounded: a wait that cannot end (it never should: lower tickets run or are done) flags the launch instead of hanging the device
+                unsigned spins = 0;
+                while((int)(seen - need) < 0)
+                {
+                    seen = ccu_ld_acquire(watch);
+                    if((int)(seen - need) < 0) { __nanosleep(64); if(++spins > (1u << 24)) { A.ticket[3] = 1u; break; } }
+                }
+            }
+            __syncwarp();
+        };
+        // the compute warps load the rim of the layers -1 .. 2 before their first end-of-layer barrier, and of layer k + 3
+        // right after the end-of-layer barrier of layer k: the neighbours must have finished it by then
+        if(MODE == 0 && WF) wait_for(3);
+        __syncthreads();
+        for(int k = 0; k < noz; k++)
+        {
+            if(MODE == 0 && WF) wait_for(k + 4);
+            __syncthreads();                                         // end of layer k
+            if(lane == 0)
+            {
+                if(k + S - 1 < noz) issue(k + S - 1);                // the stage of chunk k - 1 is free now
+                if(MODE == 0 && WF) ccu_st_release(A.progress + (I * A.nJ + J), pbase + (unsigned)(k + 1));
+            }
+        }
+        if(MODE == 0 && WF && lane == 0)
+        {   // the last CTA of the launch resets the ticket counter and bumps the epoch for the next one
+            if(atomicAdd(A.ticket + 1, 1u) + 1u == (unsigned)A.cstart[4]) { A.ticket[1] = 0u; A.ticket[0] = 0u; A.ticket[2] = s_epoch + 1u; }
+        }
+        return;
+    }
+
+    // ================= compute warps
+    const size_t NS = (size_t)g.NS;
+    const int grp = warp / NW, wl = warp % NW;           // group 0: in-plane colours 3 and 1, group 1: colours 2 and 0
     const int n3 = lane / 9, q = lane % 9, tri = q / 3, mm = q % 3;
     const bool act = lane < 27;
-    const int m = 3 * warp + n3;                         // this lane's node among the NQ nodes of an in-plane colour
+    const int m = 3 * wl + n3;                           // this lane's node among the NQ nodes of an in-plane colour
     const int wa = m / HJ, wb = m % HJ;
     const int lb = 9 * n3;
     const int srcA = act ? lb + 3 * tri + (mm + 1) % 3 : lane, srcB = act ? lb + 3 * tri + (mm + 2) % 3 : lane;
     const int src3 = act ? lb + 3 * ((tri + 1) % 3) + mm : lane, src6 = act ? lb + 3 * ((tri + 2) % 3) + mm : lane;
     const bool upd = act && q < 3;                       // lane q < 3 ends up with row d = q
-    int kA[4][3], xof[4], nodeA[4], xself[4], pidx[4];
-    bool nv[4], tr[3];
+    int kA[2][3], xof[2], nodeA[2], xself[2], pidx[2];
+    bool nv[2], tr[3];
 #pragma unroll
     for(int t = 0; t < 3; t++)
     {
@@ -184,31 +256,32 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
         tr[t] = !((di == 0 && dj == 0 && dk == 0) || ccu_lo_index(di, dj, dk) >= 0);
     }
 #pragma unroll
-    for(int c2 = 0; c2 < 4; c2++)
+    for(int ci = 0; ci < 2; ci++)
     {
+        const int c2 = (ci == 0 ? 3 : 1) - grp;
         const int li = 2 * wa + (c2 >> 1), lj = 2 * wb + (c2 & 1);
-        nv[c2] = act && m < NQ && li < cd.ti && lj < cd.tj;
-        xof[c2] = 0;
+        nv[ci] = act && m < NQ && li < cd.ti && lj < cd.tj;
+        xof[ci] = 0;
 #pragma unroll
         for(int t = 0; t < 3; t++)
         {
             CcuColDesc ds = { 0, 0, 0 };
-            if(nv[c2]) ds = ccu_col_desc(cd, TJ, li, lj, q, t);
-            kA[c2][t] = cd.kofs + 16 * ds.id; xof[c2] = ds.xof;
+            if(nv[ci]) ds = ccu_col_desc(cd, TJ, li, lj, q, t);
+            kA[ci][t] = cd.kofs + 16 * ds.id; xof[ci] = ds.xof;
         }
         const int gi = i0 + li, gj = j0 + lj;
-        nodeA[c2] = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
-        xself[c2] = (li + 1) * BJ + (lj + 1);
-        pidx[c2] = nv[c2] ? li * cd.tj + lj : 0;
+        nodeA[ci] = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
+        xself[ci] = (li + 1) * BJ + (lj + 1);
+        pidx[ci] = nv[ci] ? li * cd.tj + lj : 0;
     }
-    const int oB = 16 * cd.nb, oC = 32 * cd.nb;          // from a block's A entry to its B entry; C entry = kofs + oC + 4 id
-    // solution-window loader: thread `tid` owns entries tid, tid + NTH, ... (dof plane dx, window position bn) of every layer
+    const int oB = 16 * cd.nb, oC = cd.kofs + 32 * cd.nb;   // from a block's A entry to its B entry; C entry = oC + 4 id
+    // solution-window loader: compute thread `tid` owns entries tid, tid + NTC, ... (dof plane dx, window position bn) of every layer
     size_t xA[XE];
     bool xin[XE];
 #pragma unroll
     for(int e = 0; e < XE; e++)
     {
-        const int w = tid + e * NTH;
+        const int w = tid + e * NTC;
         const bool xl = w < 3 * BOX;
         const int dx = xl ? w / BOX : 0, bn = xl ? w % BOX : 0;
         const int xgi = i0 + bn / BJ - 1, xgj = j0 + bn % BJ - 1;
@@ -220,53 +293,10 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
     {
 #pragma unroll
         for(int e = 0; e < XE; e++)
-            if(tid + e * NTH < 3 * BOX) ((double *)(xrb + (size_t)slot * XL))[tid + e * NTH] = v[e];
+            if(tid + e * NTC < 3 * BOX) ((double *)(xrb + (size_t)slot * XL))[tid + e * NTC] = v[e];
     };
-    auto issue = [&](int layer)        // thread 0: bulk copy of chunk `layer` (0 .. noz-1) into its ring stage
-    {
-        const int s = layer % S;
-        ccu_mbar_expect_tx(bar0 + 8 * s, (unsigned)cd.cb);
-        ccu_bulk_g2s(ccu_smem_u32(stg + (size_t)s * CH), chunks + (size_t)layer * cd.cb, (unsigned)cd.cb, bar0 + 8 * s);
-    };
-    // MODE 0, WF: the columns of earlier colours around this one (a column of colour (ci, cj) has the neighbour colours
-    // (ci ^ |a|, cj ^ |b|)); lane j < 8 of warp 0 watches neighbour j
-    const unsigned *watch = nullptr;
-    unsigned seen = pbase;
-    if(MODE == 0 && WF && warp == 0 && lane < 8)
-    {
-        const int a = (lane < 3) ? -1 : (lane < 5 ? 0 : 1), b = (lane < 3) ? lane - 1 : (lane < 5 ? (lane == 3 ? -1 : 1) : lane - 6);
-        const int nc = 2 * ((mycc >> 1) ^ (a & 1)) + ((mycc & 1) ^ (b & 1));
-        const int In = I + a, Jn = J + b;
-        if(nc > mycc && In >= 0 && In < A.nI && Jn >= 0 && Jn < A.nJ) watch = A.progress + (In * A.nJ + Jn);
-    }
-    auto wait_for = [&](int layers)    // warp 0: until every watched column has finished `layers` layers of this sweep
-    {
-        const unsigned need = pbase + (unsigned)min(layers, noz);
-        if(watch)
-        {   // bounded: a wait that cannot end (it never should: lower tickets run or are done) flags the launch instead of hanging the device
-            unsigned spins = 0;
-            while((int)(seen - need) < 0)
-            {
-                seen = ccu_ld_acquire(watch);
-                if((int)(seen - need) < 0) { __nanosleep(64); if(++spins > (1u << 24)) { A.ticket[3] = 1u; break; } }
-            }
-        }
-        __syncwarp();
-    };
-
-    // ---- prologue: barriers, zeros where chunk -1 would be, the first S - 1 chunks in flight, layers -1, 0, 1 of the solution ring
-    if(tid == 0)
-    {
-        for(int s = 0; s < S; s++) ccu_mbar_init(bar0 + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for(int w = tid; w < CH / 16; w += NTH) ((float4 *)(stg + (size_t)(S - 1) * CH))[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if(tid == 0)
-        for(int layer = 0; layer <= S - 2 && layer < noz; layer++) issue(layer);
-    if(MODE == 0 && WF) { if(warp == 0) wait_for(2); __syncthreads(); }
-    {
+    __syncthreads();                                     // the service warp has seen the neighbours past layer 2 (one-launch sweep)
+    {   // layers -1, 0, 1 of the solution ring
         double v[XE];
 #pragma unroll
         for(int e = 0; e < XE; e++) v[e] = xload(e, -1);
@@ -278,12 +308,12 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
         for(int e = 0; e < XE; e++) v[e] = xload(e, 1);
         xstore(1, v);
     }
-    double fnx[4] = { 0.0, 0.0, 0.0, 0.0 };                // right-hand side of this lane's rows, one layer ahead
+    double fnx[2] = { 0.0, 0.0 };                          // right-hand side of this lane's rows, one layer ahead
     if(MODE != 1 && upd)
 #pragma unroll
-        for(int c2 = 0; c2 < 4; c2++)
-            if(nv[c2]) fnx[c2] = A.F[(size_t)q * NS + (size_t)(nodeA[c2] + 0)];
-    __syncthreads();
+        for(int ci = 0; ci < 2; ci++)
+            if(nv[ci]) fnx[ci] = A.F[(size_t)q * NS + (size_t)nodeA[ci]];
+    ccu_bar_sync(1, NTC);
 
     for(int k0 = 0; k0 < noz; k0 += S)
     {
@@ -292,89 +322,78 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
         {
             const int k = k0 + JJ;               // k % S == JJ: ring positions are compile-time constants below
             if(k >= noz) break;
-            const int PJ = (JJ + S - 1) % S, NJ = (JJ + 1) % S;      // ring stages of the layers k - 1 and k + 1
-            if(MODE == 0 && WF && warp == 0) wait_for(k + 3);            // layer k + 2 of the rim is final around us
-            if(MODE == 0 && WF) __syncthreads();
-            double xpre[XE], fcur[4];
+            const int PJ = (JJ + S - 1) % S, NJ = (JJ + 1) % S;          // ring stages of the layers k - 1 and k + 1
+            double xpre[XE], fcur[2];
 #pragma unroll
             for(int e = 0; e < XE; e++) xpre[e] = xload(e, k + 2);       // lands in the ring before this layer's last barrier
 #pragma unroll
-            for(int c2 = 0; c2 < 4; c2++)
+            for(int ci = 0; ci < 2; ci++)
             {
-                fcur[c2] = fnx[c2];
-                if(MODE != 1 && upd && nv[c2] && k + 1 < noz) fnx[c2] = A.F[(size_t)q * NS + (size_t)(nodeA[c2] + ((k + 1) & 1) * g.NC + ((k + 1) >> 1))];
+                fcur[ci] = fnx[ci];
+                if(MODE != 1 && upd && nv[ci] && k + 1 < noz) fnx[ci] = A.F[(size_t)q * NS + (size_t)(nodeA[ci] + ((k + 1) & 1) * g.NC + ((k + 1) >> 1))];
             }
             ccu_mbar_wait(bar0 + 8 * JJ, (unsigned)((k / S) & 1));       // chunk k (chunk k - 1 arrived a layer ago)
             const int zoff = (k & 1) * g.NC + (k >> 1);
             const unsigned char *cur = stg + (size_t)JJ * CH, *prv = stg + (size_t)PJ * CH;
-            // r += the block of direction layer t - 1 times the neighbour's values, for this lane's node of colour c2
-            auto prod = [&](double (&r)[3], const int c2, const int t)
+            // r += the block of direction layer t - 1 times the neighbour's values, for this lane's node of its colour ci
+            auto prod = [&](double (&r)[3], const int ci, const int t)
             {
-                const unsigned char *kb = (t == 0 ? prv : cur) + kA[c2][t];
+                const unsigned char *ck = t == 0 ? prv : cur;
+                const unsigned char *kb = ck + kA[ci][t];
                 const float4 a = *(const float4 *)kb, b = *(const float4 *)(kb + oB);
-                const float c = *(const float *)((t == 0 ? prv : cur) + cd.kofs + oC + ((kA[c2][t] - cd.kofs) >> 2));
-                const double *xp = (const double *)(xrb + ((t == 0 ? PJ : (t == 1 ? JJ : NJ)) * XL + xof[c2]));
+                const float c = *(const float *)(ck + oC + ((kA[ci][t] - cd.kofs) >> 2));
+                const double *xp = (const double *)(xrb + ((t == 0 ? PJ : (t == 1 ? JJ : NJ)) * XL + xof[ci]));
                 ccu_col_block(r, a, b, c, tr[t], xp[0], xp[BOX], xp[2 * BOX]);
             };
-            // Everything a row needs from the layers below and above is independent of this layer's colour phases:
-            // all four colours at once, before the phases (MODE 1, 2: the whole row)
-            double acc[4][3];
-#pragma unroll
-            for(int c2 = 0; c2 < 4; c2++)
+            double acc[3];
+            // what a row needs from the layers below and above is independent of this layer's colour phases
+            auto outer = [&](const int ci) { acc[0] = acc[1] = acc[2] = 0.0; prod(acc, ci, 0); prod(acc, ci, 2); };
+            auto phase = [&](const int ci)
             {
-                acc[c2][0] = acc[c2][1] = acc[c2][2] = 0.0;
-                prod(acc[c2], c2, 0);
-                prod(acc[c2], c2, 2);
-                if(MODE != 0) prod(acc[c2], c2, 1);
-            }
-            if(MODE == 0)
-            {
-#pragma unroll
-                for(int ph = 0; ph < 4; ph++)
-                {
-                    const int c2 = 3 - ph;
-                    prod(acc[c2], c2, 1);
-                    const double r = ccu_col_fold9(acc[c2], mm, srcA, srcB, src3, src6);
-                    if(upd && nv[c2])
-                    {   // General_matrix_functions.c:1250-1259: scalar BI per equation, correction rounded to fp32
-                        const double bi = ((const double *)cur)[q * cd.nt + pidx[c2]];
-                        double *xs = (double *)(xrb + (size_t)JJ * XL) + q * BOX + xself[c2];
-                        const double xn = *xs + (double)(float)((fcur[c2] - r) * bi);
-                        *xs = xn;
-                        A.x[(size_t)q * NS + (size_t)(nodeA[c2] + zoff)] = xn;
-                    }
-                    if(ph == 3) xstore((JJ + 2) % S, xpre);      // stage of layer k - 1: its last readers were the products above
-                    __syncthreads();
+                prod(acc, ci, 1);
+                const double r = ccu_col_fold9(acc, mm, srcA, srcB, src3, src6);
+                if(upd && nv[ci])
+                {   // General_matrix_functions.c:1250-1259: scalar BI per equation, correction rounded to fp32
+                    const double bi = ((const double *)cur)[q * cd.nt + pidx[ci]];
+                    double *xs = (double *)(xrb + (size_t)JJ * XL) + q * BOX + xself[ci];
+                    const double xn = *xs + (double)(float)((fcur[ci] - r) * bi);
+                    *xs = xn;
+                    A.x[(size_t)q * NS + (size_t)(nodeA[ci] + zoff)] = xn;
                 }
+            };
+            if(MODE == 0)
+            {   // in-plane colours 3, 2, 1, 0: the two warp groups alternate, the idle one prepares its next colour
+                outer(0);
+                if(grp == 0) phase(0);
+                ccu_bar_sync(1, NTC);
+                if(grp == 1) phase(0); else outer(1);
+                ccu_bar_sync(1, NTC);
+                if(grp == 0) phase(1); else outer(1);
+                ccu_bar_sync(1, NTC);
+                if(grp == 1) phase(1);
+                xstore(PJ, xpre);                                    // stage of layer k - 1: its last readers were the outer products
             }
             else
             {
 #pragma unroll
-                for(int c2 = 0; c2 < 4; c2++)
+                for(int ci = 0; ci < 2; ci++)
                 {
-                    double r = ccu_col_fold9(acc[c2], mm, srcA, srcB, src3, src6);
-                    if(upd && nv[c2])
+                    outer(ci);
+                    prod(acc, ci, 1);
+                    double r = ccu_col_fold9(acc, mm, srcA, srcB, src3, src6);
+                    if(upd && nv[ci])
                     {
-                        const unsigned char flg = cur[cd.flofs + pidx[c2]];
+                        const unsigned char flg = cur[cd.flofs + pidx[ci]];
                         if((MODE == 2 || A.strip) && ((flg >> q) & 1)) r = 0.0;
-                        if(MODE == 2) r = fcur[c2] - r;
-                        A.out[(size_t)q * NS + (size_t)(nodeA[c2] + zoff)] = r;
+                        if(MODE == 2) r = fcur[ci] - r;
+                        A.out[(size_t)q * NS + (size_t)(nodeA[ci] + zoff)] = r;
                     }
                 }
-                __syncthreads();                                     // every product of this layer has read the stage of layer k - 1
-                xstore((JJ + 2) % S, xpre);
-                __syncthreads();
+                ccu_bar_sync(1, NTC);                                // every product of this layer has read the stage of layer k - 1
+                xstore(PJ, xpre);
             }
-            if(tid == 0)
-            {
-                if(k + S - 1 < noz) issue(k + S - 1);                // the stage of chunk k - 1 is free now
-                if(MODE == 0 && WF) { __threadfence(); ccu_st_release(A.progress + (I * A.nJ + J), pbase + (unsigned)(k + 1)); }
-            }
+            __syncthreads();                                         // end of layer k (with the service warp)
         }
-    }
-    if(MODE == 0 && WF && tid == 0)
-    {   // the last CTA of the launch resets the ticket counter for the next one
-        if(atomicAdd(A.ticket + 1, 1u) + 1u == (unsigned)A.cstart[4]) { A.ticket[1] = 0u; A.ticket[0] = 0u; A.ticket[2] = s_epoch + 1u; }
     }
 }
 

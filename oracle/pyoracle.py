@@ -126,13 +126,17 @@ def run_timing(input_text: str, workdir, nsteps: int, nproc: int = 1, timeout: f
     return out
 
 
-def run_timezero(input_text: str, workdir, repeats: int, nproc: int = 1, timeout: float = 3600.0):
-    """`ref_harness timezero`: seconds of each of `repeats` step-0 general_stokes_solver calls (zero guess)."""
+def run_timezero(input_text: str, workdir, repeats: int, nproc: int = 1, timeout: float = 3600.0, dump_up: bool = False):
+    """`ref_harness timezero`: seconds of each of `repeats` step-0 general_stokes_solver calls (zero guess).
+    dump_up: every rank also writes its final U, P (tz_U, tz_P, tz_meta) into <workdir>/dump (read them with Dump)."""
     workdir = Path(workdir)
     (workdir / "out").mkdir(parents=True, exist_ok=True)
     (workdir / "in.input").write_text(input_text)
     env = dict(os.environ)
     env["CCU_MPI_NP"] = str(nproc)
+    if dump_up:
+        (workdir / "dump").mkdir(parents=True, exist_ok=True)
+        env["CCU_TZ_DUMP"] = "dump"
     r = subprocess.run([str(REFDIR / "ref_harness"), "timezero", "in.input", str(repeats)], cwd=workdir, env=env,
                        capture_output=True, text=True, timeout=timeout)
     if r.returncode not in (0, 8):

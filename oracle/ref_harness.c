@@ -337,6 +337,20 @@ int main(int argc, char **argv)
             t1 = MPI_Wtime();
             if(E.parallel.me == 0) printf("CCU_TIME step %d stokes_s %.6f\n", rep, t1 - t0);
         }
+        if(getenv("CCU_TZ_DUMP"))
+        {   /* bench.py's parity gate: every rank writes its converged U, P and where it sits in the processor grid */
+            char path[1400];
+            int meta[9] = { E.parallel.nprocx, E.parallel.nprocy, E.parallel.nprocz, E.parallel.me_loc[1], E.parallel.me_loc[2],
+                            E.parallel.me_loc[3], E.lmesh.nox, E.lmesh.noy, E.lmesh.noz };
+            snprintf(g_outdir, sizeof g_outdir, "%s", getenv("CCU_TZ_DUMP"));
+            snprintf(path, sizeof path, "%s/manifest.r%d.txt", g_outdir, g_rank);
+            g_manifest = fopen(path, "w");
+            if(!g_manifest) { perror(path); return 3; }
+            DUMP_I32("tz_meta", meta, 9);
+            DUMP_F64("tz_U", E.U, E.lmesh.neq);
+            DUMP_F64("tz_P", E.P + 1, E.lmesh.npno);
+            fclose(g_manifest);
+        }
         fflush(stdout);
         MPI_Finalize();
         return 0;

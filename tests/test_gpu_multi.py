@@ -44,14 +44,21 @@ def rel(a, b):
 
 
 @pytest.mark.skipif(ngpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("nproc,agglomerate", [((2, 1, 1), True), ((1, 1, 2), True), ((1, 2, 1), False), ((2, 1, 1), False)])
-def test_two_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
+@pytest.mark.parametrize("nproc,agglomerate", [((2, 1, 1), True), ((1, 1, 2), True), ((1, 2, 1), False), ((2, 1, 1), False),
+                                               ((2, 2, 1), True), ((2, 2, 2), True), ((2, 2, 2), False), ((1, 2, 2), False)])
+def test_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
+    """2, 4 and 8 subdomains (the decompositions bench.py --gpus N times: 2x1x1, 2x2x1, 2x2x2 -- edges shared by four
+    subdomains and corners shared by eight included) against one GPU owning the whole mesh and against the unmodified
+    reference on the same processor grid."""
+    world = nproc[0] * nproc[1] * nproc[2]
+    if ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     from citcomcu_b200.problem import CartesianProblem
     from citcomcu_b200.stokes import context_from_problem
     from mgpu_worker import seeded_global_vector
     acc = 1e-8
     text = inputfile.tdepv_box(16, 16, 8, 3, nproc=nproc, maxstep=1, accuracy=acc)
-    res = spawn(text, 2, acc, agglomerate)
+    res = spawn(text, world, acc, agglomerate)
     # single-GPU run of the whole mesh
     gp = CartesianProblem(text).global_problem()
     ctx = context_from_problem(gp, accuracy=acc)
@@ -110,7 +117,7 @@ def test_two_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
     assert abs(res[0]["its"] - its_g) <= 3
     # the unmodified reference on the same processor grid
     if po.have_ref():
-        dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_mgpu_")), nsteps=0, nproc=2)
+        dumps, err = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_mgpu_")), nsteps=0, nproc=world)
         num_u = den_u = num_p = den_p = 0.0
         for r, d in zip(res, dumps):
             assert tuple(d.control()["me_loc"]) == tuple(r["me"])
