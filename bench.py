@@ -13,14 +13,18 @@ does identical work).  Synthetic data: the reference's analytic initial temperat
           library's stream, max over ranks)
   e2e     the same call through the C ABI with pinned HOST buffers: T and buoyancy go host->device,
           U and P come back device->host inside the timed region
-  roofline  finest-level 8-colour Gauss-Seidel relaxation kernel (ccu_k_relax_tab): algorithmic bytes
-          648 B/node/sweep / 8 colour passes per launch, over its mean launch
-          duration measured live with CUDA events inside the timed region; `traffic` = DRAM bytes
-          per launch from the committed ncu --set full capture (profiles/traffic.json)
-  cpu_baseline / --impl reference  the UNMODIFIED reference (oracle/_ref, built from
-          /root/reference by oracle/Makefile over a process-based MPI shim) running the same step on
-          the host cores on a bounded sample (a 1/64-size mesh of the same configuration), scaled
-          to the full mesh by element count.
+  roofline  the finest-level Gauss-Seidel smoother kernel (the kernel with the largest share of the step):
+          algorithmic bytes 600 B/node/sweep (SURVEY.md 8d without Ad, which the smoother never touches:
+          K 504 + F 24 + BI 24 + d0 read/write 48) / launches per sweep, over its mean launch duration
+          measured with CUDA events in a separate profiled pass of the same steps (`value` itself is timed
+          with the per-kernel events off); `traffic` = DRAM bytes per launch from the committed
+          ncu --set full capture (profiles/traffic.json)
+  parity  every run also solves a 64x64x32 sample of the same configuration to accuracy 1e-8 on the same
+          N GPUs and compares U, P with the unmodified reference's solution of that sample (relative L2)
+  cpu_baseline / --impl reference  the UNMODIFIED reference (oracle/_ref, built from /root/reference
+          by oracle/Makefile over oracle/mpi_shim, a process-based shared-memory MPI) running the SAME
+          step on the SAME mesh on the box's host cores; repeats are capped (one warm-up + two timed
+          steps, about 30 s each on 16 cores) and the line reports the counts it actually ran.
 """
 from __future__ import annotations
 
@@ -39,7 +43,9 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-RELAX_BYTES_PER_NODE_SWEEP = 648.0     # K 504 + F 24 + BI 24 + d0 r/w 48 + Ad r/w 48
+RELAX_BYTES_PER_NODE_SWEEP = 600.0     # SURVEY.md 8(d) less Ad (never touched by the sweep): K 504 + F 24 + BI 24 + d0 r/w 48
+PARITY_MESH, PARITY_LEVELS, PARITY_ACC = (64, 64, 32), 4, 1e-8
+REF_MAX_WARMUP, REF_MAX_STEPS = 1, 2   # cap of the CPU reference arm: a full-size step takes ~30 s on 16 host cores
 MATVEC_BYTES_PER_NODE = 552.0          # K 504 + u 24 + Au 24
 
 
@@ -51,8 +57,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", default="256x256x128")
     ap.add_argument("--levels", type=int, default=6)
-    ap.add_argument("--ref-mesh", default="64x64x32", help="bounded sample mesh for the CPU reference")
-    ap.add_argument("--ref-levels", type=int, default=4)
+    ap.add_argument("--ref-mesh", default=None, help="mesh for the CPU reference (default: the benchmark mesh itself)")
+    ap.add_argument("--ref-levels", type=int, default=None)
+    ap.add_argument("--no-parity", action="store_true", help="skip the 64x64x32 parity sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="diagnostic: launch coarse levels kernel by kernel and report per-level times")
     ap.add_argument("--opt", action="append", default=[], help="diagnostic: library option name=value (ccu_set_option)")
@@ -135,8 +142,8 @@ def nproc_for_cores(cores, mg):
     return best
 
 
-def reference_times(ref_mesh, ref_levels, repeats, cores):
-    """Run the unmodified reference's general_stokes_solver (zero guess) `repeats` times on the sample mesh."""
+def reference_times(ref_mesh, ref_levels, repeats, cores, accuracy=None, dump_up=False):
+    """Run the unmodified reference's general_stokes_solver (zero guess) `repeats` times on `ref_mesh`."""
     from oracle import pyoracle as po
     from citcomcu_b200 import inputfile
     if not po.have_ref():
@@ -145,29 +152,69 @@ def reference_times(ref_mesh, ref_levels, repeats, cores):
     mg = (ref_mesh[0] // f, ref_mesh[1] // f, ref_mesh[2] // f)
     nproc = nproc_for_cores(cores, mg)
     nranks = nproc[0] * nproc[1] * nproc[2]
-    txt = inputfile.tdepv_box(*ref_mesh, ref_levels, nproc=nproc, maxstep=1)
+    kw = {} if accuracy is None else {"accuracy": accuracy}
+    txt = inputfile.tdepv_box(*ref_mesh, ref_levels, nproc=nproc, maxstep=1, **kw)
     wd = Path(tempfile.mkdtemp(prefix="ccu_refbench_"))
-    times = po.run_timezero(txt, wd, repeats, nproc=nranks)
+    times = po.run_timezero(txt, wd, repeats, nproc=nranks, dump_up=dump_up)
+    if dump_up:
+        return times, nproc, nranks, [po.Dump(wd / "dump", rank=k) for k in range(nranks)]
     return times, nproc, nranks
 
 
+def assemble_global(parts, gmesh):
+    """Global U (3 per node) and P (per element) from per-subdomain pieces [(nproc, me_loc, (nox, noy, noz), U, P)]
+    in the reference's numbering n = k + noz*(j + nox*i), e = ez + elz*(ex + elx*ey) (duplicated face nodes agree)."""
+    from citcomcu_b200 import decomp
+    gx, gy, gz = gmesh[0] + 1, gmesh[1] + 1, gmesh[2] + 1
+    U = np.zeros((gx * gy * gz, 3)); P = np.zeros(gmesh[0] * gmesh[1] * gmesh[2])
+    for nproc, me, (nox, noy, noz), u, pp in parts:
+        U[decomp.global_node_ids(nproc, me, nox, noy, noz)] = np.asarray(u).reshape(-1, 3)
+        ex, ey, ez = nox - 1, noy - 1, noz - 1
+        i = np.arange(ey)[:, None, None] + me[1] * ey
+        j = np.arange(ex)[None, :, None] + me[0] * ex
+        k = np.arange(ez)[None, None, :] + me[2] * ez
+        P[(k + gmesh[2] * (j + gmesh[0] * i)).reshape(-1)] = np.asarray(pp)
+    return U.reshape(-1), P
+
+
+def reference_parity_solution(cores):
+    """The unmodified reference's converged U, P of the parity sample (global arrays) and its seconds."""
+    times, nproc, nranks, dumps = reference_times(PARITY_MESH, PARITY_LEVELS, 1, cores, accuracy=PARITY_ACC, dump_up=True)
+    parts = []
+    for d in dumps:
+        m = [int(v) for v in d["tz_meta"]]
+        parts.append((tuple(m[0:3]), tuple(m[3:6]), tuple(m[6:9]), d["tz_U"], d["tz_P"]))
+    U, P = assemble_global(parts, PARITY_MESH)
+    from oracle import pyoracle as po
+    ref_its = po.last_pressure_loops[-1] if po.last_pressure_loops else None
+    return U, P, float(times[-1]), nranks, ref_its
+
+
 def run_reference(args):
-    mesh, ref_mesh = mesh_tuple(args.mesh), mesh_tuple(args.ref_mesh)
+    mesh = mesh_tuple(args.mesh)
+    ref_mesh = mesh_tuple(args.ref_mesh) if args.ref_mesh else mesh
+    ref_levels = args.ref_levels or args.levels
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    times, nproc, nranks = reference_times(ref_mesh, args.ref_levels, args.warmup + args.steps, cores)
-    t = times[args.warmup:]
+    warm, steps = min(args.warmup, REF_MAX_WARMUP), max(1, min(args.steps, REF_MAX_STEPS))
+    times, nproc, nranks = reference_times(ref_mesh, ref_levels, warm + steps, cores)
+    t = times[warm:]
     scale = (mesh[0] * mesh[1] * mesh[2]) / (ref_mesh[0] * ref_mesh[1] * ref_mesh[2])
     v = float(np.mean(t)) * scale
-    sample = (f"unmodified reference general_stokes_solver on a {args.ref_mesh} mesh of the same configuration, {nranks} ranks "
-              f"({nproc[0]}x{nproc[1]}x{nproc[2]}) over a shared-memory MPI shim; {float(np.mean(t)):.3f} s per step measured, "
-              f"scaled x{scale:g} by element count to {args.mesh}")
+    sample = (f"unmodified reference general_stokes_solver on the {ref_mesh[0]}x{ref_mesh[1]}x{ref_mesh[2]} mesh, {nranks} ranks "
+              f"({nproc[0]}x{nproc[1]}x{nproc[2]}) on {cores} host cores over oracle/mpi_shim (process-based shared-memory MPI: spin + "
+              f"sched_yield mailboxes, collectives through point-to-point); {warm} warm-up + {steps} timed steps "
+              f"(capped from --warmup {args.warmup} --steps {args.steps}); {float(np.mean(t)):.3f} s per step measured"
+              + ("" if scale == 1 else f", scaled x{scale:g} by element count to {args.mesh} (an ESTIMATE)"))
+    cfg = workload_config(args, mesh)
+    cfg["reference_ran"] = {"mesh": list(ref_mesh), "levels": ref_levels, "nproc": list(nproc), "host_cores": cores,
+                            "steps_timed": steps, "warmup_run": warm, "extrapolated": scale != 1}
     line = {"impl": "reference", "metric": "stokes_solve_s_per_timestep", "value": v, "unit": "s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, mesh),
+            "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": "s", "cores": nranks, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -181,6 +228,48 @@ def workload_config(args, mesh, nproc=(1, 1, 1)):
             "mesh": list(mesh), "levels": args.levels, "nproc": list(nproc),
             "partition": "one subdomain per GPU, the reference's nprocx x nprocy x nprocz block decomposition; halo sums + allreduce over NCCL",
             "l2": "inputs larger than L2 (finest-level stiffness alone is > 4 GB)"}
+
+
+def parity_gate(args, world, rank, local, nproc):
+    """Solve the parity sample on the same processor grid as the benchmark and compare with the unmodified reference."""
+    import torch.distributed as dist
+    from citcomcu_b200 import decomp, inputfile
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import StokesContext, context_from_problem
+    uid = None
+    if world > 1:
+        box = [StokesContext.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    text = inputfile.tdepv_box(*PARITY_MESH, PARITY_LEVELS, nproc=nproc, maxstep=1, accuracy=PARITY_ACC)
+    me = decomp.me_loc_of(rank, nproc)
+    prob = CartesianProblem(text, me_loc=me)
+    ctx = context_from_problem(prob, device=local, unique_id=uid, accuracy=PARITY_ACC)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    gp = prob.global_problem()
+    Tg = gp.initial_temperature()
+    ctl = prob.control
+    U, P, its, _ = ctx.general_stokes_solver(prob.local_slice(Tg), prob.local_slice(gp.buoyancy(Tg)), rebuild=1, augmented_Lagr=ctl["augmented_Lagr"],
+                                             augmented=ctl["augmented"], precondition=ctl["precondition"], guess=0)
+    lm = prob.levmax
+    col = bool(ctx.get_option("relax_col", lm))
+    ctx.close()
+    piece = (tuple(nproc), tuple(me), tuple(prob.dims(lm)), U, P)
+    if world > 1:
+        pieces = [None] * world
+        dist.all_gather_object(pieces, piece)
+    else:
+        pieces = [piece]
+    if rank != 0:
+        return None
+    Ug, Pg = assemble_global(pieces, PARITY_MESH)
+    Ur, Pr, ref_s, ref_ranks, ref_its = reference_parity_solution(os.cpu_count() or 1)
+    return {"sample": f"{PARITY_MESH[0]}x{PARITY_MESH[1]}x{PARITY_MESH[2]} elements, {PARITY_LEVELS} levels, same configuration, accuracy {PARITY_ACC:g}; "
+                      f"GPU nproc {nproc[0]}x{nproc[1]}x{nproc[2]} vs the unmodified reference on {ref_ranks} ranks",
+            "u_rel_l2": float(np.linalg.norm(Ug - Ur) / np.linalg.norm(Ur)), "p_rel_l2": float(np.linalg.norm(Pg - Pr) / np.linalg.norm(Pr)),
+            "uzawa_its": int(its), "ref_its": ref_its, "tolerance": 1e-6, "column_smoother_on_sample_finest_level": col, "reference_s": ref_s}
 
 
 def run_ours(args):
@@ -274,11 +363,18 @@ def run_ours(args):
     ctx.synchronize()
     clocks = ClockSampler(local)
     clocks.start()
-    ctx.profile_enable(True)
-    ctx.profile_reset()
+    # `value`: the K steps with the per-kernel CUDA-event profiling OFF
+    ctx.profile_enable(False)
     l0 = ctx.launch_count
     total_s, its = timed(step_resident, args.steps)
     launches = ctx.launch_count - l0
+    # e2e: host buffers through the C ABI
+    step_e2e()
+    e2e_s, _ = timed(step_e2e, args.steps)
+    # class timings (smoother / matvec launch durations, rebuild, coarse levels): a separate pass of the same K steps with the events on
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    prof_s, _ = timed(step_resident, args.steps)
     relax_ms, relax_n = ctx.profile_read("relax_fine")
     mv_ms, mv_n = ctx.profile_read("matvec_fine")
     build_ms, _ = ctx.profile_read("build")
@@ -287,56 +383,70 @@ def run_ours(args):
     level_ms = {lev: ctx.profile_read(lev) for lev in range(prob.levmin, prob.levmax + 1)} if args.no_graphs else None
     ctx.profile_enable(False)
     clk = clocks.stop()
-    # e2e: host buffers through the C ABI
-    step_e2e()
-    e2e_s, _ = timed(step_e2e, args.steps)
     s_per_step = total_s / args.steps
     peak, peak_src = measured_peak_gbs()
-    relax_bytes_per_launch = RELAX_BYTES_PER_NODE_SWEEP * nno / 8.0
+    relax_col, matvec_col, col_wf = ctx.get_option("relax_col", lm), ctx.get_option("matvec_col", lm), ctx.get_option("col_wf", lm)
+    launches_per_sweep = (1 if col_wf else 4) if relax_col else 8
+    if relax_col:
+        relax_kernel = ("ccu_k_col<.., MODE 0> (finest-level column-resident Gauss-Seidel smoother: stiffness streamed once per sweep through a "
+                        "bulk-copy ring in shared memory; " + ("one launch per sweep" if col_wf else "one launch per column colour") + ")")
+        tkey = "ccu_k_col_relax"
+    else:
+        relax_kernel = "ccu_k_relax_tab<2> (one colour pass of the finest-level 8-colour Gauss-Seidel smoother)"
+        tkey = "ccu_k_relax_tab"
+    relax_bytes_per_launch = RELAX_BYTES_PER_NODE_SWEEP * nno / launches_per_sweep
     relax_gbs = relax_bytes_per_launch * relax_n / (relax_ms * 1e-3) / 1e9 if relax_ms > 0 else 0.0
     mv_gbs = MATVEC_BYTES_PER_NODE * nno * mv_n / (mv_ms * 1e-3) / 1e9 if mv_ms > 0 else 0.0
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            t = json.loads(tf.read_text()).get("ccu_k_relax_tab", {}).get(args.mesh) if world == 1 else None
+            t = json.loads(tf.read_text()).get(tkey, {}).get(args.mesh) if world == 1 else None
             traffic = None if t is None else t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
         except Exception:
             traffic = None
+    prof_total_ms = prof_s * 1e3
     line = {"metric": "stokes_solve_s_per_timestep", "value": s_per_step, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh, nproc),
-            "roofline": {"bound": "hbm", "kernel": "ccu_k_relax_tab<2> (one colour pass of the finest-level 8-colour Gauss-Seidel smoother)",
+            "roofline": {"bound": "hbm", "kernel": relax_kernel,
                          "achieved": relax_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": relax_gbs / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": relax_bytes_per_launch,
+                         "algorithmic_bytes_per_node_sweep": RELAX_BYTES_PER_NODE_SWEEP, "launches_per_sweep": launches_per_sweep,
                          "launches": relax_n, "avg_launch_ms": relax_ms / max(relax_n, 1),
-                         "share_of_step": relax_ms / (total_s * 1e3)},
+                         "share_of_step": relax_ms / prof_total_ms},
             "smoother_gbs": relax_gbs, "matvec_gbs": mv_gbs,
-            "matvec": {"achieved": mv_gbs, "frac": mv_gbs / peak, "launches": mv_n, "avg_launch_ms": mv_ms / max(mv_n, 1),
-                       "share_of_step": mv_ms / (total_s * 1e3)},
+            "matvec": {"kernel": "ccu_k_col<.., MODE 1/2>" if matvec_col else "ccu_k_matvec_tab", "achieved": mv_gbs, "frac": mv_gbs / peak,
+                       "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_NODE * nno, "launches": mv_n, "avg_launch_ms": mv_ms / max(mv_n, 1),
+                       "share_of_step": mv_ms / prof_total_ms},
             "operator_rebuild_ms_per_step": build_ms / args.steps,
             "step_breakdown_ms": {"relax_fine": relax_ms / args.steps, "matvec_fine": mv_ms / args.steps, "build": build_ms / args.steps,
                                   "coarse_levels": coarse_ms / args.steps, "transfer_fine": transfer_ms / args.steps,
-                                  "other_fine_vector_ops_and_sync": (total_s * 1e3 - relax_ms - mv_ms - build_ms - coarse_ms - transfer_ms) / args.steps},
+                                  "other_fine_vector_ops_and_sync": (prof_total_ms - relax_ms - mv_ms - build_ms - coarse_ms - transfer_ms) / args.steps,
+                                  "profiled_pass_ms_per_step": prof_total_ms / args.steps},
             "uzawa_iterations": its, "gpu_launches": launches * world, "clocks": clk, "setup_s": setup_s,
             "e2e": {"value": e2e_s / args.steps, "unit": "s", "h2d_bytes_per_step": int(T_h.nbytes + b_h.nbytes) * world,
                     "d2h_bytes_per_step": int(U_h.nbytes + P_h.nbytes) * world}}
     if level_ms:
         line["level_ms_per_step"] = {str(k): {"ms": v[0] / args.steps, "sweeps": v[1] / args.steps} for k, v in level_ms.items()}
-    if not args.no_cpu_baseline and rank == 0:
+    ctx.close()
+    # ---- parity gate: the 64x64x32 sample of the same configuration on the same N GPUs against the unmodified reference
+    if not args.no_parity:
         try:
-            ref_mesh = mesh_tuple(args.ref_mesh)
+            line["parity"] = parity_gate(args, world, rank, local, nproc)
+        except Exception as e:
+            line["parity"] = {"error": str(e)[:400]}
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        try:
             cores = os.cpu_count() or 1
-            times, nproc, nranks = reference_times(ref_mesh, args.ref_levels, 2, cores)
-            scale = (mesh[0] * mesh[1] * mesh[2]) / (ref_mesh[0] * ref_mesh[1] * ref_mesh[2])
-            line["cpu_baseline"] = {"value": float(times[-1]) * scale, "unit": "s", "cores": nranks, "kind": "reference",
-                                    "sample": f"unmodified reference (oracle/_ref) general_stokes_solver on a {args.ref_mesh} mesh of the same "
-                                              f"configuration, {nranks} ranks; {times[-1]:.3f} s measured, scaled x{scale:g} by element count"}
+            times, rnproc, nranks = reference_times(mesh, args.levels, 1, cores)
+            line["cpu_baseline"] = {"value": float(times[-1]), "unit": "s", "cores": nranks, "kind": "reference",
+                                    "sample": f"one general_stokes_solver step of the unmodified reference (oracle/_ref) on the same {args.mesh} mesh, "
+                                              f"{nranks} ranks ({rnproc[0]}x{rnproc[1]}x{rnproc[2]}) on {cores} host cores over oracle/mpi_shim; no warm-up"}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -21,7 +21,10 @@
 //     General_matrix_functions.c:1250-1259);
 //   * per layer, the products with the layers below and above (2/3 of a row, independent of this layer's colour phases)
 //     are formed for all four in-plane colours at once; a colour phase then only adds the same-layer blocks;
-//   * every stiffness byte is read from HBM once per sweep (+ the duplicated halo blocks, 19 % for 6 x 8 columns).
+//   * every stiffness byte is read from HBM once per sweep (+ the duplicated halo blocks, 19 % for 6 x 8 columns);
+//   * the kernel's limit is the shared-memory pipe (ncu r02: l1tex data pipe 84 % busy, 44 % of it bank-conflict replays
+//     with the blocks in natural order), so the blocks of a chunk sit at permuted positions (ccu_col_perm.h, generated
+//     by scripts/gen_col_perm.py from the kernel's own access sets) and the rows of the solution window are padded.
 // Gauss-Seidel order: columns are 4-coloured by the parity of their column indices, colours 3..0; inside a column z
 // ascends; inside a layer the four (y, x)-parity colours 3..0.  All nodes relaxed concurrently share no stencil
 // neighbour, so this is a Gauss-Seidel ordering of the same point-block smoother (General_matrix_functions.c:1231-1260);
@@ -46,8 +49,9 @@ struct CcuColShape
     static constexpr int NW = (NQ + 2) / 3;               // warps per colour: three nodes each
     static constexpr int NTC = 2 * NW * 32;               // compute threads: two warp groups, two colours each
     static constexpr int THREADS = NTC + 32;              // + the service warp (bulk copies, progress words)
-    static constexpr int BJ = TJ + 2, BOX = (TI + 2) * BJ; // solution window of one layer (column + rim)
-    static constexpr int XE = (3 * BOX + NTC - 1) / NTC;  // window entries per compute thread
+    static constexpr int BJR = TJ + 2, BOXR = (TI + 2) * BJR;      // solution window of one layer (column + rim)
+    static constexpr int BJ = TJ + 3, BOX = (TI + 2) * BJ;         // ... as stored: rows padded so that the nine-point reads of a warp spread over the banks
+    static constexpr int XE = (3 * BOXR + NTC - 1) / NTC; // window entries per compute thread
     static constexpr int CHUNK = ccu_col_dims(TI_, TJ_).cb;        // bytes of a full column's chunk
     static constexpr int XLAYER = 3 * BOX * 8;            // bytes of one layer of the solution ring
     static constexpr size_t SMEM = (size_t)S * CHUNK + (size_t)S * XLAYER + (size_t)S * 8;
@@ -136,7 +140,7 @@ __device__ __forceinline__ void ccu_bar_sync(const int id, const int count) { as
 template <class SH, int MODE, int WF>
 __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_constant__ CcuColArgs A)
 {
-    constexpr int TI = SH::TI, TJ = SH::TJ, S = SH::S, BJ = SH::BJ, BOX = SH::BOX, CH = SH::CHUNK, XL = SH::XLAYER;
+    constexpr int TI = SH::TI, TJ = SH::TJ, S = SH::S, BJ = SH::BJ, BOX = SH::BOX, BJR = SH::BJR, BOXR = SH::BOXR, CH = SH::CHUNK, XL = SH::XLAYER;
     constexpr int NQ = SH::NQ, NW = SH::NW, HJ = TJ / 2, XE = SH::XE, NTC = SH::NTC, NTH = SH::THREADS;
     extern __shared__ __align__(128) unsigned char ccu_col_smem[];
     __shared__ int s_ticket;
@@ -266,25 +270,27 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
         for(int t = 0; t < 3; t++)
         {
             CcuColDesc ds = { 0, 0, 0 };
-            if(nv[ci]) ds = ccu_col_desc(cd, TJ, li, lj, q, t);
-            kA[ci][t] = cd.kofs + 16 * ds.id; xof[ci] = ds.xof;
+            if(nv[ci]) ds = ccu_col_desc(cd, BJ, li, lj, q, t);
+            kA[ci][t] = cd.kofs + 16 * ccu_col_pos(cd, ds.id); xof[ci] = ds.xof;
         }
         const int gi = i0 + li, gj = j0 + lj;
         nodeA[ci] = (4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1;
         xself[ci] = (li + 1) * BJ + (lj + 1);
         pidx[ci] = nv[ci] ? li * cd.tj + lj : 0;
     }
-    const int oB = 16 * cd.nb, oC = cd.kofs + 32 * cd.nb;   // from a block's A entry to its B entry; C entry = oC + 4 id
+    const int oB = 16 * cd.nbp, oC = cd.kofs + 32 * cd.nbp; // from a block's A entry to its B entry; C entry = oC + 4 position
     // solution-window loader: compute thread `tid` owns entries tid, tid + NTC, ... (dof plane dx, window position bn) of every layer
     size_t xA[XE];
     bool xin[XE];
+    int xdst[XE];
 #pragma unroll
     for(int e = 0; e < XE; e++)
     {
         const int w = tid + e * NTC;
-        const bool xl = w < 3 * BOX;
-        const int dx = xl ? w / BOX : 0, bn = xl ? w % BOX : 0;
-        const int xgi = i0 + bn / BJ - 1, xgj = j0 + bn % BJ - 1;
+        const bool xl = w < 3 * BOXR;
+        const int dx = xl ? w / BOXR : 0, bn = xl ? w % BOXR : 0;
+        const int xgi = i0 + bn / BJR - 1, xgj = j0 + bn % BJR - 1;
+        xdst[e] = dx * BOX + (bn / BJR) * BJ + bn % BJR;
         xin[e] = xl && xgi >= 0 && xgi < g.noy && xgj >= 0 && xgj < g.nox;
         xA[e] = xin[e] ? (size_t)dx * NS + (size_t)((4 * (xgi & 1) + 2 * (xgj & 1)) * g.NC + ((xgi >> 1) + 1) * g.JK + ((xgj >> 1) + 1) * g.Kd + 1) : 0;
     }
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
     {
 #pragma unroll
         for(int e = 0; e < XE; e++)
-            if(tid + e * NTC < 3 * BOX) ((double *)(xrb + (size_t)slot * XL))[tid + e * NTC] = v[e];
+            if(tid + e * NTC < 3 * BOXR) ((double *)(xrb + (size_t)slot * XL))[xdst[e]] = v[e];
     };
     __syncthreads();                                     // the service warp has seen the neighbours past layer 2 (one-launch sweep)
     {   // layers -1, 0, 1 of the solution ring

@@ -174,6 +174,24 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     default: FAIL("set_option: unknown option");
     }
 }
+int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
+{
+    if(!c || !value) FAIL("get_option: null argument");
+    if(lev < c->cfg.levmin || lev > c->cfg.levmax) FAIL("get_option: level out of range");
+    const bool col = c->L[lev].col_shape >= 0;
+    switch(option)
+    {
+    case CCU_OPT_GRAPHS: *value = c->use_graphs; return 0;
+    case CCU_OPT_RELAX_COL: *value = col && c->opt_relax_col; return 0;
+    case CCU_OPT_MATVEC_COL: *value = col && c->opt_matvec_col; return 0;
+    case CCU_OPT_COL_WF: *value = c->opt_col_wf; return 0;
+    case CCU_OPT_COL_SHAPE: *value = c->L[lev].col_shape; return 0;
+    case CCU_OPT_COL_NODES: *value = c->opt_col_nodes; return 0;
+    case CCU_OPT_RELAX_TAB: *value = c->opt_relax_tab; return 0;
+    case CCU_OPT_MATVEC_TAB: *value = c->opt_matvec_tab; return 0;
+    default: FAIL("get_option: option not readable");
+    }
+}
 int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); CK(cudaStreamSynchronize(c->st)); return 0; }
 long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
 
@@ -411,6 +429,7 @@ static int col_relayout(ccu_ctx *c, Level &L, int lev)
         cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync);
         L.Kc = nullptr; L.colofs = nullptr; L.col_sync = nullptr; L.Kc_bytes = 0;
         CK(cudaMalloc(&L.Kc, total));
+        CK(cudaMemsetAsync(L.Kc, 0, total, c->st));      // block positions no block maps to (ccu_col_pos) are never written again
         CK(cudaMalloc(&L.colofs, sizeof(size_t) * ofs.size()));
         CK(cudaMalloc(&L.col_sync, sizeof(unsigned) * (4 + ofs.size())));
         CK(cudaMemsetAsync(L.col_sync, 0, sizeof(unsigned) * (4 + ofs.size()), c->st));

@@ -53,7 +53,7 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
        CCU_OPT_MATVEC_TAB = 5, CCU_OPT_RELAX_TAB = 6,
        CCU_OPT_CLUSTER_NODES = 8 /* single-subdomain levels with nno <= this run a whole smoother call in one 8-CTA cluster launch */,
        CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */,
-       /* column-resident kernels (csrc/ccu_col.cuh) on levels with nno > COL_NODES (default 500000): RELAX_COL / MATVEC_COL
+       /* column-resident kernels (csrc/ccu_col.cuh) on levels with nno > COL_NODES (default 2000000: measured slower than the colour passes on the 1.08e6-node level): RELAX_COL / MATVEC_COL
         * (default 1) switch them on or off; COL_SHAPE 0 = columns of 6 (y) x 8 (x) nodes, two CTAs per SM, 1 = 12 x 8, one CTA
         * per SM, 2 = 4 x 8, three CTAs per SM.  A CTA streams the stiffness of its column through shared memory with one bulk
         * asynchronous copy per z layer, so every coefficient crosses HBM once per sweep.  The column smoother is a Gauss-Seidel
@@ -68,6 +68,9 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
         * cooperative launch with grid barriers between the colour passes (ccu_k_relax_coop); 0 = per-pass launches */,
        CCU_OPT_MID_LANES = 17 /* lanes per node (4, 8 or 16) of the smoother on levels between WARP_NODES and QUAD_NODES */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
+/* current value of an option; for the column options, *value is what is in effect on level `lev` (0 when the level is too
+ * small for the column kernels), so that a benchmark can name the kernel it timed */
+int ccu_get_option(ccu_ctx *ctx, int option, int lev, int *value);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long ccu_launch_count(ccu_ctx *ctx);
 

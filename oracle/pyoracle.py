@@ -141,7 +141,13 @@ def run_timezero(input_text: str, workdir, repeats: int, nproc: int = 1, timeout
                        capture_output=True, text=True, timeout=timeout)
     if r.returncode not in (0, 8):
         raise RuntimeError(f"ref_harness timezero failed rc={r.returncode}\n{r.stderr[-4000:]}")
+    import re
+    global last_pressure_loops        # the reference's own "after (NNN) pressure loops" lines of this run (rank 0, see_convergence)
+    last_pressure_loops = [int(m) for m in re.findall(r"after \((\d+)\) pressure loops", r.stderr)]
     return [float(line.split()[4]) for line in r.stdout.split("\n") if line.startswith("CCU_TIME")]
+
+
+last_pressure_loops = []
 
 
 # ---------------------------------------------------------------- restatement (ctypes)

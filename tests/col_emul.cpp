@@ -16,7 +16,7 @@ namespace
 struct Emul
 {
     CcuGeom g;
-    int TI, TJ, S, BJ, BOX, CH, nI, nJ;
+    int TI, TJ, S, BJ, BOX, BJR, BOXR, CH, nI, nJ;
     std::vector<float> K;
     std::vector<double> BI;
     std::vector<unsigned char> flags, Kc;
@@ -26,7 +26,7 @@ struct Emul
 void run_column(const Emul &E, int mode, int I, int J, const double *F, double *x, double *out, int strip)
 {
     const CcuGeom &g = E.g;
-    const int TI = E.TI, TJ = E.TJ, S = E.S, BJ = E.BJ, BOX = E.BOX, CH = E.CH, noz = g.noz;
+    const int TI = E.TI, TJ = E.TJ, S = E.S, BJ = E.BJ, BOX = E.BOX, BJR = E.BJR, BOXR = E.BOXR, CH = E.CH, noz = g.noz;
     const int i0 = I * TI, j0 = J * TJ;
     const CcuColDims cd = ccu_col_dims(std::min(TI, g.noy - i0), std::min(TJ, g.nox - j0));
     const unsigned char *chunks = E.Kc.data() + E.colofs[I * E.nJ + J];
@@ -35,26 +35,27 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
     std::vector<double> xr((size_t)S * 3 * BOX, 1e300);
     const int NQ = TI * TJ / 4, HJ = TJ / 2;
     auto issue = [&](int layer) { memcpy(stg.data() + (size_t)(layer % S) * CH, chunks + (size_t)layer * cd.cb, cd.cb); };
+    auto xdst = [&](int tid) { const int dx = tid / BOXR, bn = tid % BOXR; return dx * BOX + (bn / BJR) * BJ + bn % BJR; };
     auto xload = [&](int tid, int k) -> double
     {
-        const int dx = tid / BOX, bn = tid % BOX, gi = i0 + bn / BJ - 1, gj = j0 + bn % BJ - 1;
+        const int dx = tid / BOXR, bn = tid % BOXR, gi = i0 + bn / BJR - 1, gj = j0 + bn % BJR - 1;
         if(!(gi >= 0 && gi < g.noy && gj >= 0 && gj < g.nox && k >= 0 && k < noz)) return 0.0;
         const size_t xA = (size_t)dx * NS + (size_t)((4 * (gi & 1) + 2 * (gj & 1)) * g.NC + ((gi >> 1) + 1) * g.JK + ((gj >> 1) + 1) * g.Kd + 1);
         return x[xA + (size_t)((k & 1) * g.NC + (k >> 1))];
     };
     memset(stg.data() + (size_t)(S - 1) * CH, 0, CH);              // where chunk -1 would be
     for(int layer = 0; layer <= S - 2 && layer < noz; layer++) issue(layer);
-    for(int tid = 0; tid < 3 * BOX; tid++)
+    for(int tid = 0; tid < 3 * BOXR; tid++)
     {
-        xr[(size_t)(S - 1) * 3 * BOX + tid] = xload(tid, -1);
-        xr[(size_t)0 * 3 * BOX + tid] = xload(tid, 0);
-        xr[(size_t)1 * 3 * BOX + tid] = xload(tid, 1);
+        xr[(size_t)(S - 1) * 3 * BOX + xdst(tid)] = xload(tid, -1);
+        xr[(size_t)0 * 3 * BOX + xdst(tid)] = xload(tid, 0);
+        xr[(size_t)1 * 3 * BOX + xdst(tid)] = xload(tid, 1);
     }
-    std::vector<double> xpre(3 * BOX);
+    std::vector<double> xpre(3 * BOXR);
     for(int k = 0; k < noz; k++)
     {
         const int JJ = k % S, PJ = (JJ + S - 1) % S, NJ = (JJ + 1) % S;
-        for(int tid = 0; tid < 3 * BOX; tid++) xpre[tid] = xload(tid, k + 2);
+        for(int tid = 0; tid < 3 * BOXR; tid++) xpre[tid] = xload(tid, k + 2);
         const int zoff = (k & 1) * g.NC + (k >> 1);
         const unsigned char *cur = stg.data() + (size_t)JJ * CH, *prv = stg.data() + (size_t)PJ * CH;
         for(int ph = 0; ph < 4; ph++)
@@ -73,7 +74,7 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
                     for(int oi = 0; oi < 3; oi++)
                     {
                         const int t = order[oi];
-                        const CcuColDesc ds = ccu_col_desc(cd, TJ, li, lj, q, t);
+                        const CcuColDesc ds = ccu_col_desc(cd, BJ, li, lj, q, t);
                         const unsigned char *ck = t == 0 ? prv : cur;
                         float e[9];
                         for(int ee = 0; ee < 9; ee++) memcpy(&e[ee], ck + ccu_col_coef_ofs(cd, ds.id, ee), 4);
@@ -116,7 +117,7 @@ void run_column(const Emul &E, int mode, int I, int J, const double *F, double *
                     }
                 }
             }
-            if(ph == 3) for(int tid = 0; tid < 3 * BOX; tid++) xr[(size_t)((JJ + 2) % S) * 3 * BOX + tid] = xpre[tid];
+            if(ph == 3) for(int tid = 0; tid < 3 * BOXR; tid++) xr[(size_t)((JJ + 2) % S) * 3 * BOX + xdst(tid)] = xpre[tid];
         }
         if(k + S - 1 < noz) issue(k + S - 1);
     }
@@ -134,7 +135,7 @@ extern "C" int ccu_col_emul(int nox, int noy, int noz, int TI, int TJ, int S, in
     Emul E;
     E.g = ccu_make_geom(nox, noy, noz);
     const CcuGeom &g = E.g;
-    E.TI = TI; E.TJ = TJ; E.S = S; E.BJ = TJ + 2; E.BOX = (TI + 2) * (TJ + 2);
+    E.TI = TI; E.TJ = TJ; E.S = S; E.BJR = TJ + 2; E.BOXR = (TI + 2) * (TJ + 2); E.BJ = TJ + 3; E.BOX = (TI + 2) * (TJ + 3);
     E.CH = ccu_col_dims(TI, TJ).cb;
     E.nI = (noy + TI - 1) / TI; E.nJ = (nox + TJ - 1) / TJ;
     const size_t NS = (size_t)g.NS;
