@@ -403,18 +403,83 @@ __global__ void __launch_bounds__(SH::THREADS, SH::CTAS) ccu_k_col(const __grid_
     }
 }
 
-// K (coefficient-major, colour-blocked), BI, flags -> column chunks (ccu_col_fill_chunk).  grid = (columns, groups of 32
-// layers); a warp takes 32 consecutive layers of one block so that its reads of K run along z (unit stride per colour).
+// K (coefficient-major, colour-blocked), BI, flags -> column chunks: the same bytes ccu_col_fill_chunk (ccu_col_index.h, the
+// statement the host emulation uses) produces.  A CTA takes one column and 32 consecutive layers.  Reads run along z (a lane
+// per layer: the two parities of a warp read two 64-byte runs); the blocks go through a shared-memory tile in batches of 32
+// consecutive chunk POSITIONS (`inv` = position -> block id for the full column shape, identity for clipped columns), so
+// that every store to HBM is a full 512-byte (A, B halves) or 128-byte (ninth coefficients) run of one chunk.
 template <int TI, int TJ>
 __global__ void __launch_bounds__(256) ccu_k_col_relayout(const CcuGeom g, const int nJ, const size_t *__restrict__ colofs,
                                                            const float *__restrict__ K, const double *__restrict__ BI,
                                                            const unsigned char *__restrict__ flags, const unsigned char *__restrict__ bits,
-                                                           unsigned char *Kc)
+                                                           const short *__restrict__ inv, unsigned char *Kc)
 {
+    __shared__ float tile[32][32 * 9 + 1];                      // [layer][position in batch][coefficient]
     const int col = blockIdx.x, I = col / nJ, J = col % nJ;
-    const int kk = (int)blockIdx.y * 32 + (int)(threadIdx.x & 31);                   // chunk index = layer 0 .. noz - 1
-    if(kk >= g.noz) return;
+    const int k0 = (int)blockIdx.y * 32, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = I * TI, j0 = J * TJ;
     const CcuColDims cd = ccu_col_dims(min(TI, g.noy - i0), min(TJ, g.nox - j0));
-    ccu_col_fill_chunk(g, cd, i0, j0, kk, K, BI, flags, bits, Kc + colofs[col] + (size_t)kk * cd.cb, threadIdx.x >> 5, blockDim.x >> 5);
+    const bool full = cd.ti == TI && cd.tj == TJ;
+    unsigned char *chunk0 = Kc + colofs[col] + (size_t)k0 * cd.cb;
+    const size_t NS = (size_t)g.NS;
+    const int nlay = min(32, g.noz - k0);
+    // inverse diagonal and flags: thread per (layer, entry)
+    for(int w = threadIdx.x; w < nlay * (cd.kofs / 8); w += 256)
+    {
+        const int l = w / (cd.kofs / 8), e = w % (cd.kofs / 8);
+        double v = 0.0;
+        if(e < 3 * cd.nt)
+        {
+            const int dd = e / cd.nt, p = e % cd.nt;
+            const int s = ccu_sidx(g, i0 + p / cd.tj, j0 + p % cd.tj, k0 + l);
+            v = BI[dd * NS + s];
+            if(bits && (bits[s] & 2)) v = 0.0;
+        }
+        ((double *)(chunk0 + (size_t)l * cd.cb))[e] = v;
+    }
+    for(int w = threadIdx.x; w < nlay * (cd.cb - cd.flofs); w += 256)
+    {
+        const int l = w / (cd.cb - cd.flofs), p = w % (cd.cb - cd.flofs);
+        chunk0[(size_t)l * cd.cb + cd.flofs + p] = p < cd.nt ? flags[ccu_sidx(g, i0 + p / cd.tj, j0 + p % cd.tj, k0 + l)] : (unsigned char)0;
+    }
+    for(int b0 = 0; b0 < cd.nbp; b0 += 32)
+    {
+        // gather: warp w takes the positions b0 + 4 w .. + 3, lane = layer
+#pragma unroll
+        for(int pp = 0; pp < 4; pp++)
+        {
+            const int pl = 4 * warp + pp, pos = b0 + pl;
+            const int id = full ? (int)inv[pos] : (pos < cd.nb ? pos : -1);
+            float v[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+            if(id >= 0 && lane < nlay)
+            {
+                int sli, slj, slot;
+                if(id < 14 * cd.nt) { const int p = id / 14; slot = id % 14; sli = p / cd.tj; slj = p % cd.tj; }
+                else { int b; ccu_col_halo_decode(cd.ti, cd.tj, id - 14 * cd.nt, sli, slj, b); slot = b + 1; }
+                int di = 0, dj = 0, dk = 0;
+                if(slot) ccu_lo_offset(slot - 1, di, dj, dk);
+                const int ks = k0 + lane + (dk < 0 ? 1 : 0);           // blocks that reach down belong to the layer above
+                const int gi = i0 + sli, gj = j0 + slj;
+                if(ks < g.noz && gi >= 0 && gi < g.noy && gj >= 0 && gj < g.nox)
+                {
+                    const int s = ccu_sidx(g, gi, gj, ks);
+#pragma unroll
+                    for(int e = 0; e < 9; e++) v[e] = K[(size_t)(slot * 9 + e) * NS + s];
+                }
+            }
+#pragma unroll
+            for(int e = 0; e < 9; e++) tile[lane][pl * 9 + e] = v[e];
+        }
+        __syncthreads();
+        // scatter: 32 layers x 32 positions; a warp writes the 512 bytes of one layer's A (then B) halves, 128 bytes of its C entries
+        for(int l = warp; l < nlay; l += 8)
+        {
+            unsigned char *ch = chunk0 + (size_t)l * cd.cb + cd.kofs;
+            const float *t = &tile[l][lane * 9];
+            ((float4 *)(ch + 16 * b0))[lane] = make_float4(t[0], t[1], t[2], t[3]);
+            ((float4 *)(ch + 16 * cd.nbp + 16 * b0))[lane] = make_float4(t[4], t[5], t[6], t[7]);
+            ((float *)(ch + 32 * cd.nbp + 4 * b0))[lane] = t[8];
+        }
+        __syncthreads();
+    }
 }

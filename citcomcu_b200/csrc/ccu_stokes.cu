@@ -113,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.col_inv); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -432,14 +432,26 @@ static int col_relayout(ccu_ctx *c, Level &L, int lev)
         CK(cudaMemsetAsync(L.Kc, 0, total, c->st));      // block positions no block maps to (ccu_col_pos) are never written again
         CK(cudaMalloc(&L.colofs, sizeof(size_t) * ofs.size()));
         CK(cudaMalloc(&L.col_sync, sizeof(unsigned) * (4 + ofs.size())));
+
         CK(cudaMemsetAsync(L.col_sync, 0, sizeof(unsigned) * (4 + ofs.size()), c->st));
         L.Kc_bytes = total;
+    }
+    if(L.col_inv_key != TI * 100 + TJ)
+    {   // position -> block id of the full column shape (the inverse of ccu_col_pos), -1 where no block sits
+        const CcuColDims cf = ccu_col_dims(TI, TJ);
+        std::vector<short> inv((size_t)cf.nbp, (short)-1);
+        for(int id = 0; id < cf.nb; id++) inv[(size_t)ccu_col_pos(cf, id)] = (short)id;
+        cudaFree(L.col_inv); L.col_inv = nullptr;
+        CK(cudaMalloc(&L.col_inv, sizeof(short) * inv.size()));
+        CK(cudaMemcpy(L.col_inv, inv.data(), sizeof(short) * inv.size(), cudaMemcpyHostToDevice));
+        L.col_inv_key = TI * 100 + TJ;
     }
     CK(cudaMemcpyAsync(L.colofs, ofs.data(), sizeof(size_t) * ofs.size(), cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));               // `ofs` leaves scope
     L.col_nI = nI; L.col_nJ = nJ;
     const unsigned char *bits = c->multi() ? c->comm->halo[lev].bits : nullptr;
-    LAUNCH(c, (ccu_k_col_relayout<TI, TJ>), dim3((unsigned)(nI * nJ), (unsigned)((g.noz + 31) / 32)), 256, g, nJ, L.colofs, L.K, L.BI, L.flags, bits, L.Kc);
+    LAUNCH(c, (ccu_k_col_relayout<TI, TJ>), dim3((unsigned)(nI * nJ), (unsigned)((g.noz + 31) / 32)), 256, g, nJ, L.colofs, L.K, L.BI, L.flags, bits,
+           L.col_inv, L.Kc);
     return 0;
 }
 // The column kernels read a column-major copy of the level's stiffness, inverse diagonal and flags: (re)made whenever
