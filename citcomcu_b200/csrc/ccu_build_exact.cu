@@ -1207,7 +1207,7 @@ int ccu_set_coordinates(ccu_ctx *c, int lev, const float *X1, const float *X2, c
     CK(cudaMemcpyAsync(L.XX, X1, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.XX + n, X2, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.XX + 2 * n, X3, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     L.have_xx = true;
     return 0;
 }
@@ -1226,10 +1226,10 @@ int ccu_build_geometry(ccu_ctx *c)
         LAUNCH(c, bk_mass, cdiv(L.g.nno, 128), 128, L.g, (const double *)c->stage, L.MASS);
         if(ccu_halo_sum_nodal(c, lev, L.MASS)) return 1;                  // exchange_node_f20 (Size_does_matter.c:733)
         LAUNCH(c, bk_invert, cdiv(L.g.nno, 128), 128, L.g.nno, L.MASS);
-        CK(cudaStreamSynchronize(c->st));
+        SYNC(c);
         L.have_tw = true;
     }
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1253,7 +1253,7 @@ int ccu_set_material(ccu_ctx *c, const int *mat)
     Level &L = c->L[c->cfg.levmax];
     if(!c->mat) CK(cudaMalloc(&c->mat, sizeof(int) * (size_t)L.g.nel));
     CK(cudaMemcpyAsync(c->mat, mat, sizeof(int) * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1274,7 +1274,7 @@ int ccu_set_temperature(ccu_ctx *c, const float *T)
     if(!c) FAIL("null context");
     if(ensure_nodal(c)) return 1;
     CK(cudaMemcpyAsync(c->T, T, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nno, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1284,7 +1284,7 @@ int ccu_set_element_viscosity(ccu_ctx *c, int lev, const float *EVI)
     if(ensure_nodal(c)) return 1;
     Level &L = c->L[lev];
     CK(cudaMemcpyAsync(L.EVI, EVI, sizeof(float) * 8 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     L.have_evi = true;
     return 0;
 }
@@ -1374,7 +1374,7 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
         if(ccu_col_refresh(c, lev)) return 1;                            // column-major copy for the column kernels (ccu_col.cuh)
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(c->coarse)
     {   // replicated coarse levels: their operators are built from the gathered viscosity of level agg_lev, exactly as a
         // single subdomain owning the whole mesh would build them
@@ -1404,7 +1404,7 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
         LAUNCH(c, bk_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, L.vec[CCU_VEC_F], (double *)c->stage);
         CK(cudaMemcpyAsync(F_out, c->stage, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
     }
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1420,13 +1420,13 @@ int ccu_get_stiffness(ccu_ctx *c, int lev, float *k1, float *k2, float *k3, doub
     CK(cudaMemcpyAsync(k1, s, sizeof(float) * n42, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(k2, s + n42, sizeof(float) * n42, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(k3, s + 2 * n42, sizeof(float) * n42, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(BI)
     {
         double *sb = (double *)c->stage;
         LAUNCH(c, bk_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, L.BI, sb);
         CK(cudaMemcpyAsync(BI, sb, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
+        SYNC(c);
     }
     return 0;
 }
@@ -1448,7 +1448,7 @@ int ccu_get_level_array(ccu_ctx *c, int lev, int which, void *out)
     }
     if(!src) FAIL("get_level_array: array not allocated");
     CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1482,7 +1482,7 @@ int ccu_set_energy_params(ccu_ctx *c, float fine_tune_dt, float fixed_timestep, 
     E.fine_tune_dt = fine_tune_dt; E.fixed_timestep = fixed_timestep; E.gamma = gamma; E.temp_iterations = temp_iterations; E.Q0 = Q0;
     CK(cudaMemcpyAsync(E.diffusivity, diffusivity, sizeof(float) * L.g.noz, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(E.expansivity, expansivity, sizeof(float) * L.g.noz, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     E.have_params = true; E.diff_timestep = -1.0f;
     return 0;
 }
@@ -1517,7 +1517,7 @@ int ccu_set_heating_arrays(ccu_ctx *c, const float *heating_adi, const float *he
         if(!*dst[q]) CK(cudaMalloc(dst[q], sizeof(float) * nel));
         CK(cudaMemcpyAsync(*dst[q], src[q], sizeof(float) * nel, cudaMemcpyHostToDevice, c->st));
     }
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 // return_horiz_ave across subdomains (Global_operations.c:205-238): the layer sums of the ranks that share a z position
@@ -1583,7 +1583,7 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
     if(Fas410_out) CK(cudaMemcpyAsync(Fas410_out, E.Fas410, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
     if(transT_out) CK(cudaMemcpyAsync(transT_out, E.transT, sizeof(float) * 2, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 // process_heating (Advection_diffusion.c:813) from the resident T, V and EVI[levmax]; outputs optional (float[nel])
@@ -1612,7 +1612,7 @@ int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_
     if(heating_adi_out) CK(cudaMemcpyAsync(heating_adi_out, E.heat_adi, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
     if(heating_visc_out && E.heat_visc) CK(cudaMemcpyAsync(heating_visc_out, E.heat_visc, sizeof(float) * nel, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_set_tdot(ccu_ctx *c, const float *Tdot)
@@ -1622,7 +1622,7 @@ int ccu_set_tdot(ccu_ctx *c, const float *Tdot)
     const size_t nno = (size_t)c->L[c->cfg.levmax].g.nno;
     if(Tdot) CK(cudaMemcpyAsync(c->en.Tdot, Tdot, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
     else CK(cudaMemsetAsync(c->en.Tdot, 0, sizeof(float) * nno, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_set_velocity(ccu_ctx *c, const float *V1, const float *V2, const float *V3)
@@ -1633,7 +1633,7 @@ int ccu_set_velocity(ccu_ctx *c, const float *V1, const float *V2, const float *
     CK(cudaMemcpyAsync(c->en.V, V1, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->en.V + nno, V2, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->en.V + 2 * nno, V3, sizeof(float) * nno, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     c->en.have_v = true;
     return 0;
 }
@@ -1645,7 +1645,7 @@ int ccu_v_from_vector(ccu_ctx *c, float *V_out)
     LAUNCH(c, ek_v_from_vector, cdiv(L.g.nno, 128), 128, L.g, (const double *)L.vec[CCU_VEC_U], c->en.V);
     c->en.have_v = true;
     if(V_out) CK(cudaMemcpyAsync(V_out, c->en.V, sizeof(float) * 3 * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 // global_fmin / global_fmax (Global_operations.c:409,416) of the device scalar red[which]
@@ -1653,7 +1653,7 @@ static int reduce_scalar(ccu_ctx *c, int which, float *out)
 {
     float v;
     CK(cudaMemcpyAsync(&v, c->en.red + which, sizeof(float), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(c->multi())
     {
         double *buf = c->comm->dotstage;
@@ -1661,7 +1661,7 @@ static int reduce_scalar(ccu_ctx *c, int which, float *out)
         CK(cudaMemcpyAsync(buf, &d, sizeof(double), cudaMemcpyHostToDevice, c->st));
         if(ccu_allreduce_buffer(c, buf, 1, 1)) return 1;
         CK(cudaMemcpyAsync(&d, buf, sizeof(double), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
+        SYNC(c);
         v = (float)((which == 0) ? -d : d);
     }
     *out = v;
@@ -1685,7 +1685,7 @@ static int std_timestep(ccu_ctx *c, float *dt)
     LAUNCH(c, ek_timestep, cdiv(L.g.nel, 128), 128, L.g, L.eco, E.V, 1, E.red);
     float adv;
     CK(cudaMemcpyAsync(&adv, E.red, sizeof(float), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     const float prod = E.fine_tune_dt * adv;
     adv = (float)(1.0e-32 + (double)(prod < E.diff_timestep ? prod : E.diff_timestep));
     // global_fmin of the per-rank candidates
@@ -1723,7 +1723,7 @@ int ccu_pg_solver(ccu_ctx *c, float *DTdot_out)
     if(ensure_energy(c) || energy_ready(c)) return 1;
     if(pg_solver(c)) return 1;
     if(DTdot_out) CK(cudaMemcpyAsync(DTdot_out, c->en.DTdot, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nno, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 static int tmax(ccu_ctx *c, float *out)
@@ -1777,7 +1777,7 @@ int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_i
     if(T) CK(cudaMemcpyAsync(T, c->T, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
     if(Tdot) CK(cudaMemcpyAsync(Tdot, E.Tdot, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
@@ -1799,7 +1799,7 @@ int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
     LAUNCH(c, ek_remove_layer_ave, cdiv(L.g.nno, 256), 256, L.g, (const double *)E.layer, c->buoy);
     if(buoyancy_out) CK(cudaMemcpyAsync(buoyancy_out, c->buoy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_set_step(ccu_ctx *c, int solution_cycles)
@@ -1813,7 +1813,7 @@ int ccu_get_heating_latent(ccu_ctx *c, float *heating_latent_out)
     if(!c) FAIL("null context");
     if(!c->en.heat_latent) FAIL("get_heating_latent: no phase changes configured");
     CK(cudaMemcpyAsync(heating_latent_out, c->en.heat_latent, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nel, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 // heat_flux (Process_buoyancy.c:63-203): Nusselt numbers at the top and bottom of the box from the resident T and velocity
@@ -1839,7 +1839,7 @@ int ccu_heat_flux(ccu_ctx *c, float *Nut_out, float *Nub_out)
     if(ccu_allreduce_buffer(c, E.hf_sums, 4, 0)) return 1;                          // return_horiz_sum over every plane = global sum
     double h[4];
     CK(cudaMemcpyAsync(h, E.hf_sums, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(Nub_out) *Nub_out = (float)((float)h[0] / ((float)h[1] * 4));               // inp[] / outp[] are float (:62,178-186)
     if(Nut_out) *Nut_out = (float)((float)h[2] / ((float)h[3] * 4));
     return 0;
@@ -1851,7 +1851,7 @@ int ccu_get_temperature(ccu_ctx *c, float *T, float *Tdot)
     const size_t nno = (size_t)c->L[c->cfg.levmax].g.nno;
     if(T) CK(cudaMemcpyAsync(T, c->T, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
     if(Tdot) CK(cudaMemcpyAsync(Tdot, c->en.Tdot, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1887,7 +1887,7 @@ int ccu_markers_setup(ccu_ctx *c, int capacity, int markers_per_ele, int rnoz, c
     CK(cudaMalloc(&M.err, sizeof(int))); CK(cudaMemsetAsync(M.err, 0, sizeof(int), c->st));
     for(int d = 0; d < 3; d++) { M.XG1[d] = XG1[d]; M.XG2[d] = XG2[d]; }
     // dx, dy, dzz exactly as get_element's statics (Composition_adv.c:1113-1116)
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     M.ready = true;
     return 0;
 }
@@ -1908,7 +1908,7 @@ static int mk_ends(ccu_ctx *c, double e[6])
     const int nx = L.g.nox, ny = L.g.noy, nz = L.g.noz;
     const int idx[6] = { 0, nx - 1, nx, nx + ny - 1, nx + ny, nx + ny + nz - 1 };
     for(int q = 0; q < 6; q++) CK(cudaMemcpyAsync(e + q, c->mk.XP + idx[q], sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_markers_upload(ccu_ctx *c, int n, const double *X1, const double *X2, const double *X3, const int *C12, const int *CElement, const float *CE)
@@ -1925,7 +1925,7 @@ int ccu_markers_upload(ccu_ctx *c, int n, const double *X1, const double *X2, co
     CK(cudaMemcpyAsync(M.C12, C12, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(M.CElement, CElement, sizeof(int) * n, cudaMemcpyHostToDevice, c->st));
     if(CE) CK(cudaMemcpyAsync(M.CE, CE, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nel, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_markers_download(ccu_ctx *c, double *X, double *Xpred, float *VO, float *Vpred, int *CElement, float *C, float *CE)
@@ -1945,7 +1945,7 @@ int ccu_markers_download(ccu_ctx *c, double *X, double *Xpred, float *VO, float 
     if(CElement) CK(cudaMemcpyAsync(CElement, M.CElement, sizeof(int) * n, cudaMemcpyDeviceToHost, c->st));
     if(C) CK(cudaMemcpyAsync(C, M.C, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
     if(CE) CK(cudaMemcpyAsync(CE, M.CE, sizeof(float) * (size_t)L.g.nel, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 // ---- transfer_marker_properties (Composition_adv.c:682-704): clamp, [markers to their new subdomain], element_markers,
@@ -1987,7 +1987,7 @@ static int mk_clamp_split(ccu_ctx *c, double *&Xuse, const double ends[6], int s
     c->launches++;
     int n_stay = 0;
     CK(cudaMemcpyAsync(&n_stay, M.nsel, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     const int nl = n - n_stay;
     if(nl == 0) return 0;
     // leavers: stable sort by destination on the host (they are a sliver of the markers)
@@ -1995,7 +1995,7 @@ static int mk_clamp_split(ccu_ctx *c, double *&Xuse, const double ends[6], int s
     std::vector<int> idx(nl), code(nl), order(nl);
     CK(cudaMemcpyAsync(idx.data(), M.lv_idx, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(code.data(), M.lv_code, sizeof(int) * nl, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     for(int q = 0; q < nl; q++) { order[q] = q; sendcnt[code[q]]++; }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
     std::vector<int> sorted(nl);
@@ -2010,7 +2010,7 @@ static int mk_clamp_split(ccu_ctx *c, double *&Xuse, const double ends[6], int s
     LAUNCH(c, (mk_gather<float, 3>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const float *)M.Vpred, M.sVpred);
     LAUNCH(c, (mk_gather<int, 1>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const int *)M.C12, M.sC12);
     LAUNCH(c, (mk_gather<int, 1>), cdiv(n_stay, 256), 256, n_stay, M.cap, (const int *)M.perm, (const int *)M.CElement, M.sCElement);
-    CK(cudaStreamSynchronize(c->st));                       // `sorted` must outlive the upload
+    SYNC(c);                       // `sorted` must outlive the upload
     std::swap(M.X, M.sX); std::swap(M.Xpred, M.sXpred); std::swap(M.VO, M.sVO); std::swap(M.Vpred, M.sVpred);
     std::swap(M.C12, M.sC12); std::swap(M.CElement, M.sCElement);
     Xuse = usePred ? M.Xpred : M.X;
@@ -2044,7 +2044,7 @@ static int mk_finish(ccu_ctx *c, const MkGrid &m, double *Xuse)
     }
     int err = 0;
     CK(cudaMemcpyAsync(&err, M.err, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(err) FAIL("markers: " + std::to_string(err) + " marker(s) left the z lookup table (the reference terminates here: '!!!overflow', Composition_adv.c:1176)");
     return 0;
 }
@@ -2054,7 +2054,7 @@ static int mk_advect(ccu_ctx *c, float timestep, int corrector, MkGrid &m, doubl
 {
     if(!c) FAIL("null context");
     auto &M = c->mk;
-    if(!M.ready || M.n == 0) FAIL("markers: no markers resident");
+    if(!M.ready) FAIL("markers: ccu_markers_setup / ccu_markers_upload first");      // a subdomain may hold no marker: it still takes part in every collective
     if(!c->en.have_v) FAIL("markers: a velocity (ccu_v_from_vector / ccu_set_velocity) is needed first");
     Level &L = c->L[c->cfg.levmax];
     if(mk_ends(c, ends)) return 1;
@@ -2086,7 +2086,7 @@ static int mk_step(ccu_ctx *c, float timestep, int corrector)
     if(mk_decomposed(c))
     {
         if(!c->multi()) FAIL("markers: a decomposition without a communicator: use ccu_markers_step_export / ccu_markers_import_finish");
-        if(ccu_marker_exchange(c, sendcnt, M.sendbuf, CCU_MK_REC, recvcnt, M.recvbuf, (size_t)M.cap, &nrecv)) return 1;
+        if(ccu_marker_exchange(c, sendcnt, M.sendbuf, CCU_MK_REC, recvcnt, M.recvbuf, (size_t)M.cap, &nrecv, M.n)) return 1;
         if(mk_append(c, nrecv, M.recvbuf)) return 1;
     }
     return mk_finish(c, m, Xuse);
@@ -2107,7 +2107,7 @@ int ccu_markers_step_export(ccu_ctx *c, float timestep, int corrector, int sendc
     for(int q = 0; q < 27; q++) nl += sendcnt[q];
     if(nl > max_records) FAIL("markers_step_export: record buffer too small");
     if(nl) CK(cudaMemcpyAsync(records_out, c->mk.sendbuf, sizeof(double) * CCU_MK_REC * nl, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_markers_import_finish(ccu_ctx *c, int corrector, int nrecv, const double *records)

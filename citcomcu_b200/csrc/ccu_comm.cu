@@ -396,23 +396,41 @@ extern "C" int ccu_marker_routes(const int nproc[3], const int me[3], const int 
 // neighbour sends it (one all-gather of the 27 per-direction counts), then one grouped send/recv round moves the records.
 // Neighbour code = (ox+1) + 3 (oy+1) + 9 (oz+1) of the offset (ox, oy, oz); what rank R at offset o sends to me sits
 // under R's code for the opposite offset, 26 - code.  Received records are stored in ascending code order.
-int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv)
+// Capacity is decided COLLECTIVELY (n_resident = markers that stay on this rank): every rank learns through the same
+// all-gather whether any rank would overflow, and all of them fail together before the send/recv group instead of leaving
+// the others blocked in it (the reference terminates all ranks here, parallel_process_termination).
+int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv, int n_resident)
 {
     CcuComm *m = c->comm;
     for(int q = 0; q < 27; q++) recvcnt[q] = 0;
     *nrecv = 0;
     if(!m || m->nranks == 1) return 0;
-    if(!m->mk_counts) CK(cudaMalloc(&m->mk_counts, sizeof(int) * 27 * (size_t)(m->nranks + 1)));
-    int *mine = m->mk_counts, *all = m->mk_counts + 27;
-    CK(cudaMemcpyAsync(mine, sendcnt, sizeof(int) * 27, cudaMemcpyHostToDevice, c->st));
-    NK(g_nccl.AllGather(mine, all, 27 * sizeof(int), ncclChar, (ncclComm_t)m->nccl, c->st));
-    std::vector<int> h(27 * (size_t)m->nranks);
-    CK(cudaMemcpyAsync(h.data(), all, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    const int W = 29;                      // 27 per-direction counts + markers staying + capacity, per rank
+    if(!m->mk_counts) CK(cudaMalloc(&m->mk_counts, sizeof(int) * W * (size_t)(m->nranks + 1)));
+    int *mine = m->mk_counts, *all = m->mk_counts + W;
+    int mine_h[W];
+    for(int q = 0; q < 27; q++) mine_h[q] = sendcnt[q];
+    mine_h[27] = n_resident; mine_h[28] = (int)cap_records;
+    CK(cudaMemcpyAsync(mine, mine_h, sizeof(int) * W, cudaMemcpyHostToDevice, c->st));
+    NK(g_nccl.AllGather(mine, all, W * sizeof(int), ncclChar, (ncclComm_t)m->nccl, c->st));
+    std::vector<int> hw(W * (size_t)m->nranks), h(27 * (size_t)m->nranks);
+    CK(cudaMemcpyAsync(hw.data(), all, sizeof(int) * hw.size(), cudaMemcpyDeviceToHost, c->st));
+    SYNC(c);
+    for(int r = 0; r < m->nranks; r++)
+        for(int q = 0; q < 27; q++) h[27 * (size_t)r + q] = hw[W * (size_t)r + q];
     int nb[27];
+    for(int r = 0; r < m->nranks; r++)
+    {   // what arrives at every rank: the same verdict everywhere
+        const int z = r % m->nproc[2], x = (r / m->nproc[2]) % m->nproc[0], y = r / (m->nproc[2] * m->nproc[0]);
+        const int me_r[3] = { x, y, z };
+        int nb_r[27], rc_r[27], in = 0;
+        ccu_marker_routes(m->nproc, me_r, h.data(), nb_r, rc_r);
+        for(int code = 0; code < 27; code++) in += rc_r[code];
+        if(in > hw[W * (size_t)r + 28] || hw[W * (size_t)r + 27] + in > hw[W * (size_t)r + 28])
+            FAIL("markers: rank " + std::to_string(r) + " would hold more markers than its capacity (markers_uplimit); all ranks stop, as the reference's Composition_adv.c:207");
+    }
     ccu_marker_routes(m->nproc, m->me, h.data(), nb, recvcnt);
     for(int code = 0; code < 27; code++) *nrecv += recvcnt[code];
-    if((size_t)*nrecv > cap_records) FAIL("markers: more arriving markers than the capacity (markers_uplimit)");
     NK(g_nccl.GroupStart());
     size_t soff = 0, roff = 0;
     for(int code = 0; code < 27; code++)

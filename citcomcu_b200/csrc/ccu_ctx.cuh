@@ -73,6 +73,8 @@ struct ccu_ctx
 {
     ccu_config cfg;
     cudaStream_t st = 0, own_stream = 0;
+    bool bottom_attr_set = false;
+    int launch_err = 0; const char *launch_err_kernel = "";     // first failed kernel launch since the last check (LAUNCH / CK_LAUNCHES)
     struct GraphSeg { cudaGraphExec_t exec = nullptr; long long launches = 0; };
     GraphSeg seg[4];
     bool use_graphs = true;
@@ -189,7 +191,14 @@ struct CcuProfScope
     }
 };
 
-#define LAUNCH(ctx, kern, grid, block, ...) do { kern<<<(grid), (block), 0, (ctx)->st>>>(__VA_ARGS__); (ctx)->launches++; } while(0)
+// A launch over zero items is skipped (a grid of 0 is an invalid configuration); a launch that fails is remembered with the
+// kernel's name and reported by the next CK_LAUNCHES (every synchronising entry point), not at some unrelated later call.
+#define LAUNCH(ctx, kern, grid, block, ...) do { const dim3 g_(grid); if(g_.x && g_.y && g_.z) { \
+    kern<<<g_, (block), 0, (ctx)->st>>>(__VA_ARGS__); (ctx)->launches++; \
+    if(!(ctx)->launch_err) { const cudaError_t le_ = cudaPeekAtLastError(); if(le_ != cudaSuccess) { (ctx)->launch_err = (int)le_; (ctx)->launch_err_kernel = #kern; } } } } while(0)
+#define SYNC(ctx) do { CK(cudaStreamSynchronize((ctx)->st)); CK_LAUNCHES(ctx); } while(0)
+#define CK_LAUNCHES(ctx) do { if((ctx)->launch_err) { g_ccu_err = std::string("kernel launch failed: ") + (ctx)->launch_err_kernel + ": " + \
+    cudaGetErrorString((cudaError_t)(ctx)->launch_err); (ctx)->launch_err = 0; cudaGetLastError(); return 1; } } while(0)
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int ccu_ensure_stage(ccu_ctx *c, size_t bytes);
@@ -204,7 +213,7 @@ int ccu_allreduce_buffer(ccu_ctx *c, double *buf, int count, int op_max);
 int ccu_damp_face_BI(ccu_ctx *c, int lev);
 int ccu_allgather(ccu_ctx *c, const void *send, void *recv, size_t bytes_per_rank);
 // variable-size exchange of records (`rec` doubles each, grouped by neighbour code in sendbuf) with the up to 26 neighbours
-int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv);
+int ccu_marker_exchange(ccu_ctx *c, const int sendcnt[27], const double *sendbuf, int rec, int recvcnt[27], double *recvbuf, size_t cap_records, int *nrecv, int n_resident);
 int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of all subdomains -> coarse replica (ccu_stokes.cu)                  // rebuild_BI_on_boundary (ccu_stokes.cu)
 int ccu_check_lev(ccu_ctx *c, int lev);
 int ccu_col_refresh(ccu_ctx *c, int lev);

@@ -94,7 +94,7 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     { const double one = 1.0; CK(cudaMemcpyAsync(c->scal + S_ONE, &one, sizeof(double), cudaMemcpyHostToDevice, c->st)); }
     CK(cudaMalloc(&c->partial, sizeof(double) * 3 * CCU_DOT_BLOCKS));
     if(coop_init(c)) return 1;
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     *out = c;
     return 0;
 }
@@ -143,7 +143,7 @@ void ccu_destroy(ccu_ctx *c)
 int ccu_set_stream(ccu_ctx *c, void *s)
 {
     if(!c) FAIL("null context");
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     c->st = s ? (cudaStream_t)s : c->own_stream;     // NULL selects the context's own stream again
     if(c->coarse) { drop_graphs(c); c->coarse->st = c->st; }
     return 0;
@@ -192,7 +192,7 @@ int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
     default: FAIL("get_option: option not readable");
     }
 }
-int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); CK(cudaStreamSynchronize(c->st)); return 0; }
+int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); SYNC(c); return 0; }
 long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------ replicated coarse levels
@@ -238,7 +238,7 @@ int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
     LAUNCH(c, ccu_k_flags_to_dev, cdiv(L.g.nno, 256), 256, L.g, (const unsigned *)c->stage, L.flags);
     if(!L.node) CK(cudaMalloc(&L.node, sizeof(unsigned) * L.g.nno));        // raw bits (temperature BCs of the energy step)
     CK(cudaMemcpyAsync(L.node, c->stage, sizeof(unsigned) * L.g.nno, cudaMemcpyDeviceToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     L.have_flags = true;
     return 0;
 }
@@ -255,7 +255,7 @@ static int vec_d2h(ccu_ctx *c, Level &L, const double *dev, double *host)
     if(ccu_ensure_stage(c, sizeof(double) * L.g.neq)) return 1;
     LAUNCH(c, ccu_k_vec_to_nat, cdiv(L.g.nno, 256), 256, L.g, dev, (double *)c->stage);
     CK(cudaMemcpyAsync(host, c->stage, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -270,9 +270,9 @@ int ccu_set_stiffness(ccu_ctx *c, int lev, const float *k1, const float *k2, con
     CK(cudaMemcpyAsync(s + n42, k2, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(s + 2 * n42, k3, sizeof(float) * n42, cudaMemcpyHostToDevice, c->st));
     LAUNCH(c, ccu_k_stiffness_to_dev, cdiv(L.g.nno, 128), 128, L.g, s, s + n42, s + 2 * n42, L.K);
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(vec_h2d(c, L, BI, L.BI)) return 1;
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     L.have_K = true;
     return ccu_col_refresh(c, lev);
 }
@@ -284,7 +284,7 @@ int ccu_set_pressure_ops(ccu_ctx *c, int lev, const float *elt_del, const double
     CK(cudaMemcpyAsync(L.elt_del, elt_del, sizeof(float) * 24 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
     ccu_elt_del_changed(c, lev);
     CK(cudaMemcpyAsync(L.BPI, BPI, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     L.have_p = true;
     return 0;
 }
@@ -296,7 +296,7 @@ int ccu_set_transfer_weights(ccu_ctx *c, int lev, const float *TWW, const float 
     CK(cudaMemcpyAsync(L.TWW, TWW, sizeof(float) * 8 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.MASS, MASS, sizeof(float) * L.g.nno, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.eco, eco, sizeof(float) * 3 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     L.have_tw = true;
     return 0;
 }
@@ -356,7 +356,7 @@ static void d_dot3(ccu_ctx *c, size_t n, const double *a0, const double *b0, int
 static int read_scal(ccu_ctx *c, int first, int count, double *out)
 {
     CK(cudaMemcpyAsync(out, c->scal + first, sizeof(double) * count, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -447,7 +447,7 @@ static int col_relayout(ccu_ctx *c, Level &L, int lev)
         L.col_inv_key = TI * 100 + TJ;
     }
     CK(cudaMemcpyAsync(L.colofs, ofs.data(), sizeof(size_t) * ofs.size(), cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));               // `ofs` leaves scope
+    SYNC(c);               // `ofs` leaves scope
     L.col_nI = nI; L.col_nJ = nJ;
     const unsigned char *bits = c->multi() ? c->comm->halo[lev].bits : nullptr;
     LAUNCH(c, (ccu_k_col_relayout<TI, TJ>), dim3((unsigned)(nI * nJ), (unsigned)((g.noz + 31) / 32)), 256, g, nJ, L.colofs, L.K, L.BI, L.flags, bits,
@@ -688,10 +688,15 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
             for(int q = 0; q < 8; q++) maxrows += (L.sm_cstart[q + 1] - L.sm_cstart[q] + CCU_BOT_CTAS - 1) / CCU_BOT_CTAS;
             const size_t bytes = sizeof(double) * (3 * (size_t)(L.sm_n + 1) + (size_t)maxrows * 9 * CCU_BOT_LD + 6 * (size_t)maxrows)
                                  + sizeof(unsigned short) * (size_t)maxrows * CCU_BOT_LD + 16;
-            static bool attr_set = false;
-            if(!attr_set) { cudaFuncSetAttribute(ccu_k_relax_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+            if(!c->bottom_attr_set)
+            {   // the opt-in is per device: once per context (a context never changes device)
+                if(cudaFuncSetAttribute(ccu_k_relax_bottom, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess && !c->launch_err)
+                { c->launch_err = (int)cudaGetLastError(); c->launch_err_kernel = "cudaFuncSetAttribute(ccu_k_relax_bottom)"; }
+                c->bottom_attr_set = true;
+            }
             ccu_k_relax_bottom<<<CCU_BOT_CTAS, CCU_BOT_THREADS, bytes, c->st>>>(L.g, sl, maxrows, L.K, L.BI, F, x, cycles, 0);
             c->launches++;
+            if(!c->launch_err) { const cudaError_t le_ = cudaPeekAtLastError(); if(le_ != cudaSuccess) { c->launch_err = (int)le_; c->launch_err_kernel = "ccu_k_relax_bottom"; } }
             return;
         }
         if(L.g.nno <= c->opt_smem_nodes && L.sm_s)
@@ -1145,7 +1150,7 @@ static int d_solve_Ahat_p_fhat(ccu_ctx *c, double imp, int *steps_max, float *re
 int ccu_profile_enable(ccu_ctx *c, int on) { if(!c) FAIL("null context"); c->prof_on = on != 0; return 0; }
 static int prof_fold(ccu_ctx *c)
 {
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     for(auto &r : c->prof_recs)
     {
         float ms = 0.0f;
@@ -1205,7 +1210,7 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     if(iterations_out) *iterations_out = steps;
     if(P) CK(cudaMemcpyAsync(P, c->P, sizeof(double) * L.g.npno, cudaMemcpyDeviceToHost, c->st));
     if(U) return vec_d2h(c, L, L.vec[CCU_VEC_U], U);
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 
@@ -1222,7 +1227,7 @@ int ccu_vec_upload(ccu_ctx *c, int lev, int v, const double *host)
     if(ccu_check_lev(c, lev)) return 2;
     VEC(p, lev, v);
     if(vec_h2d(c, c->L[lev], host, p)) return 1;
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_vec_download(ccu_ctx *c, int lev, int v, double *host)
@@ -1235,14 +1240,14 @@ int ccu_pvec_upload(ccu_ctx *c, const double *host)
 {
     if(!c) FAIL("null context");
     CK(cudaMemcpyAsync(c->P, host, sizeof(double) * c->L[c->cfg.levmax].g.npno, cudaMemcpyHostToDevice, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_pvec_download(ccu_ctx *c, double *host)
 {
     if(!c) FAIL("null context");
     CK(cudaMemcpyAsync(host, c->P, sizeof(double) * c->L[c->cfg.levmax].g.npno, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_dev_matvec(ccu_ctx *c, int lev, int vu, int vAu, int strip)
@@ -1335,7 +1340,7 @@ int ccu_assemble_div_u(ccu_ctx *c, int lev, const double *U, double *divU)
     if(vec_h2d(c, L, U, L.vec[CCU_VEC_VEL])) return 1;
     d_div_u(c, L, L.vec[CCU_VEC_VEL], c->pAh);
     CK(cudaMemcpyAsync(divU, c->pAh, sizeof(double) * L.g.npno, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     return 0;
 }
 int ccu_assemble_grad_p(ccu_ctx *c, int lev, const double *P, double *gradP)
@@ -1352,7 +1357,7 @@ int ccu_global_vdot(ccu_ctx *c, int lev, const double *A, const double *B, doubl
     if(ccu_check_lev(c, lev)) return 2;
     Level &L = c->L[lev];
     if(vec_h2d(c, L, A, L.vec[CCU_VEC_VEL])) return 1;
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(vec_h2d(c, L, B, L.vec[CCU_VEC_RES])) return 1;
     d_dot3m(c, &L, L.vlen(), L.vec[CCU_VEC_VEL], L.vec[CCU_VEC_RES], S_TMP);
     return read_scal(c, S_TMP, 1, out);
@@ -1406,7 +1411,7 @@ int ccu_solve_Ahat_p_fhat(ccu_ctx *c, double *V, double *P, const double *F, dou
     Level &L = c->L[c->cfg.levmax];
     if(!L.have_K || !L.have_flags || !L.have_p) FAIL("solve_Ahat_p_fhat: operator not uploaded");
     if(vec_h2d(c, L, V, L.vec[CCU_VEC_U])) return 1;
-    CK(cudaStreamSynchronize(c->st));
+    SYNC(c);
     if(vec_h2d(c, L, F, L.vec[CCU_VEC_F])) return 1;
     CK(cudaMemcpyAsync(c->P, P, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
     if(d_solve_Ahat_p_fhat(c, imp, steps_max, residual_out, hist)) return 1;

@@ -22,35 +22,51 @@
  * heating arrays (adiabatic, viscous, phase-change latent) are uploaded before the step.  CCU_DROPIN_ENERGY=0 keeps the
  * reference's own energy step.
  *
+ * Several ranks: one rank per GPU (CCU_DEVICE, or rank modulo CCU_DEVICES); the reference's own MPI_Bcast carries the NCCL
+ * id once, after that the library does the halo sums and reductions over NCCL (ccu_comm_init).
+ *
  * Unsupported configurations stop the run loudly (there is no CPU fallback): spherical geometry,
- * stress- or composition-dependent viscosity, periodic side walls, more than one MPI rank.
+ * stress- or composition-dependent viscosity, viscosity smoothing, anisotropic viscosity, periodic side walls,
+ * non-zero imposed velocities.
+ *
+ * citcom_dropin_funcs.c (same library) binds the INNER functions of the path one by one (CCU_DROPIN_FUNCS).
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <dlfcn.h>
+#include <mpi.h>
 #include "global_defs.h"
 #include "prototypes.h"
 #include "citcomcu_b200.h"
 
-static ccu_ctx *g_ctx = NULL;
+ccu_ctx *g_ctx = NULL;              /* shared with citcom_dropin_funcs.c */
 static int g_calls = 0;
 
-static void die(const char *msg)
+void ccu_dropin_die(const char *msg);
+static void die(const char *msg) { ccu_dropin_die(msg); }
+void ccu_dropin_die(const char *msg)
 {
     fprintf(stderr, "citcomcu_b200 drop-in: %s\n", msg);
     exit(9);
 }
 #define CCU(call) do { if((call) != 0) { fprintf(stderr, "citcomcu_b200 drop-in: %s failed: %s\n", #call, ccu_last_error()); exit(9); } } while(0)
 
-static void dropin_init(struct All_variables *E)
+void ccu_dropin_init(struct All_variables *E);
+static void dropin_init(struct All_variables *E) { ccu_dropin_init(E); }
+void ccu_dropin_init(struct All_variables *E)
 {
     ccu_config cfg;
     int lev;
     const char *dev = getenv("CCU_DEVICE");
     if(!E->control.CART3D) die("only Geometry=cart3d is accelerated");
-    if(E->parallel.nproc != 1) die("multi-rank runs need the NCCL build (one rank per GPU); run with nproc*=1");
     if(E->viscosity.SDEPV || E->viscosity.CDEPV || E->viscosity.BDEPV) die("stress/composition/Byerlee viscosity is not on the device path");
+    /* options that change the operator and that the device build does not implement: stop, never differ silently */
+    if(E->viscosity.SMOOTH) die("viscosity smoothing (VISC_SMOOTH / apply_viscosity_smoother) is not on the device path");
+    if(E->viscosity.allow_anisotropic_viscosity) die("anisotropic viscosity is not on the device path");
+#ifdef USE_GGRD
+    if(E->control.ggrd.mat_control) die("ggrd material control (viscosity prefactors from grids) is not on the device path");
+#endif
     if(E->mesh.periodic_x || E->mesh.periodic_y) die("periodic side walls are not on the device path");
     if(!E->control.NMULTIGRID) die("Solver=multigrid is required");
     {
@@ -68,8 +84,22 @@ static void dropin_init(struct All_variables *E)
     cfg.v_steps_low = E->control.v_steps_low; cfg.v_steps_high = E->control.v_steps_high;
     cfg.down_heavy = E->control.down_heavy; cfg.up_heavy = E->control.up_heavy; cfg.mg_cycle = E->control.mg_cycle;
     cfg.p_iterations = E->control.p_iterations; cfg.accuracy = E->control.accuracy;
-    cfg.device = dev ? atoi(dev) : 0;
+    /* one rank per GPU: CCU_DEVICE pins the device, else rank modulo CCU_DEVICES (default: one device per rank up to 8) */
+    {
+        const char *nd = getenv("CCU_DEVICES");
+        const int ndev = nd ? atoi(nd) : 8;
+        cfg.device = dev ? atoi(dev) : (E->parallel.nproc > 1 ? E->parallel.me % (ndev > 0 ? ndev : 1) : 0);
+    }
     CCU(ccu_create(&cfg, &g_ctx));
+    if(E->parallel.nproc > 1)
+    {   /* the reference's own MPI carries the 128-byte NCCL id, nothing else (Parallel_related.c:80-173 decomposition) */
+        char id[128];
+        memset(id, 0, sizeof id);
+        if(E->parallel.me == 0) CCU(ccu_comm_unique_id(id));
+        MPI_Bcast(id, 128, MPI_CHAR, 0, MPI_COMM_WORLD);
+        CCU(ccu_comm_init(g_ctx, E->parallel.nprocx, E->parallel.nprocy, E->parallel.nprocz,
+                          E->parallel.me_loc[1], E->parallel.me_loc[2], E->parallel.me_loc[3], id));
+    }
     for(lev = cfg.levmin; lev <= cfg.levmax; lev++)
     {
         CCU(ccu_set_node_flags(g_ctx, lev, E->NODE[lev] + 1));
@@ -83,17 +113,32 @@ static void dropin_init(struct All_variables *E)
     if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: Stokes solve on CUDA device %d\n", cfg.device);
 }
 
+typedef void (*pg_fn)(struct All_variables *);
+
 void general_stokes_solver(struct All_variables *E)
 {
     int rebuild, its = 0, i;
     float res = 0.0f;
     double t0 = CPU_time0();
     const int lm = E->mesh.levmax;
+    {   /* CCU_DROPIN_STOKES=0: keep the reference's own driver (its inner functions may still be bound one by one,
+           citcom_dropin_funcs.c) */
+        const char *sw = getenv("CCU_DROPIN_STOKES");
+        if(sw && atoi(sw) == 0)
+        {
+            static pg_fn next = NULL;
+            if(!next) next = (pg_fn)dlsym(RTLD_NEXT, "general_stokes_solver");
+            if(!next) die("CCU_DROPIN_STOKES=0 but no other general_stokes_solver is linked");
+            next(E);
+            return;
+        }
+    }
     if(!g_ctx) dropin_init(E);
     E->monitor.elapsed_time_vsoln1 = E->monitor.elapsed_time_vsoln;
     E->monitor.elapsed_time_vsoln = E->monitor.elapsed_time;
     /* Construct_arrays.c:849: first call, or viscosity updates allowed and step % update_every_steps == 0 */
-    rebuild = (g_calls == 0) || (E->viscosity.update_allowed && E->monitor.solution_cycles % E->control.KERNEL == 0);
+    rebuild = (g_calls == 0) || (E->viscosity.update_allowed && E->monitor.solution_cycles % E->control.KERNEL == 0)
+              || (E->monitor.solution_cycles == E->control.freeze_surface_at_step);
     velocities_conform_bcs(E, E->U);
     CCU(ccu_general_stokes_solver(g_ctx, E->T + 1, E->buoyancy + 1, rebuild, E->control.augmented_Lagr, E->control.augmented,
                                   E->control.precondition, 1, E->U, E->P + 1, &its, &res));
@@ -111,7 +156,6 @@ void general_stokes_solver(struct All_variables *E)
 
 /* ---- energy step (Advection_diffusion.c:251-349) ---- */
 static int g_energy = 0;
-typedef void (*pg_fn)(struct All_variables *);
 
 void PG_timestep(struct All_variables *E)
 {
