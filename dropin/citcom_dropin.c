@@ -96,7 +96,7 @@ void ccu_dropin_init(struct All_variables *E)
         char id[128];
         memset(id, 0, sizeof id);
         if(E->parallel.me == 0) CCU(ccu_comm_unique_id(id));
-        MPI_Bcast(id, 128, MPI_CHAR, 0, MPI_COMM_WORLD);
+        MPI_Bcast(id, 32, MPI_INT, 0, MPI_COMM_WORLD);      /* 128 bytes */
         CCU(ccu_comm_init(g_ctx, E->parallel.nprocx, E->parallel.nprocy, E->parallel.nprocz,
                           E->parallel.me_loc[1], E->parallel.me_loc[2], E->parallel.me_loc[3], id));
     }

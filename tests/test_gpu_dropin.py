@@ -48,3 +48,94 @@ def test_reference_time_loop_with_gpu_stokes(name, txt, energy, monkeypatch):
     vr = np.sqrt(sum((r[f"s{nsteps}_V{d}"].astype(np.float64) ** 2).mean() for d in (1, 2, 3)))
     vg = np.sqrt(sum((g[f"s{nsteps}_V{d}"].astype(np.float64) ** 2).mean() for d in (1, 2, 3)))
     assert abs(vg - vr) < 1e-3 * vr
+
+
+FUNC_SETS = {
+    "operators": "n_assemble_del2_u,assemble_del2_u,assemble_div_u,assemble_grad_p,global_vdot,global_pdot,strip_bcs_from_residual,"
+                 "project_vector,interp_vector",
+    "smoother": "gauss_seidel",
+    "multigrid": "multi_grid",
+    "solve_del2_u": "solve_del2_u",
+    "uzawa": "solve_Ahat_p_fhat",
+}
+
+
+@pytest.mark.parametrize("which", list(FUNC_SETS))
+def test_function_level_bindings(which, monkeypatch):
+    """The reference's OWN driver (general_stokes_solver, the Uzawa loop, ...) with only the named inner functions bound to the
+    device (dropin/citcom_dropin_funcs.c, reference signatures, the reference's operator arrays uploaded after each
+    construct_stiffness_B_matrix): same solution and temperatures as the pure-CPU run within the solver tolerance."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, accuracy=1e-5)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_fref_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_STOKES", "0")
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", "0")
+    monkeypatch.setenv("CCU_DROPIN_FUNCS", FUNC_SETS[which])
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix=f"ccu_f{which}_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "Stokes solve on CUDA device" in err            # the context was created by a bound function
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    # same algorithm with another summation order (operators: the iterates agree far inside the solver tolerance), or another
+    # smoother order / device control flow (agreement at the solver tolerance)
+    tol = 1e-6 if which == "operators" else 20 * acc
+    for k in range(nsteps + 1):
+        U, Ug, P, Pg = r[f"s{k}_U"], g[f"s{k}_U"], r[f"s{k}_P"], g[f"s{k}_P"]
+        assert np.linalg.norm(Ug - U) <= tol * np.linalg.norm(U), (which, k)
+        assert np.linalg.norm(Pg - P) <= 10 * tol * np.linalg.norm(P), (which, k)
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3
+
+
+def test_marker_bindings_in_the_reference_time_loop(monkeypatch):
+    """PG_timestep_particle (with its on_off toggle), Euler and Runge_Kutta bound to the device inside the reference's own
+    time loop (thermochemical run, host Stokes solve): marker positions, element assignment and the nodal composition follow
+    the pure-CPU run."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, accuracy=1e-5, composition=1, rayleigh_comp=1e6, markers_per_ele=8, comp_depth=0.605)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_mref_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_STOKES", "0")
+    monkeypatch.setenv("CCU_DROPIN_FUNCS", "PG_timestep_particle,Euler,Runge_Kutta")
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_mgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    r, g = ref[0], gpu[0]
+    for k in range(1, nsteps + 1):
+        assert int(g[f"s{k}_nmarkers"][0]) == int(r[f"s{k}_nmarkers"][0])
+        for d in (1, 2, 3):
+            # the temperature step feeding the buoyancy differs in the last bits (device predictor-corrector), so do the velocities
+            assert np.abs(g[f"s{k}_XMC{d}"] - r[f"s{k}_XMC{d}"]).max() < 1e-5, (k, d)
+        assert (g[f"s{k}_CElement"] != r[f"s{k}_CElement"]).mean() < 1e-3
+        assert np.abs(g[f"s{k}_C"] - r[f"s{k}_C"]).max() < 0.2 and np.abs(g[f"s{k}_C"] - r[f"s{k}_C"]).mean() < 1e-4
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("nproc", [(2, 1, 1), (2, 2, 2)])
+def test_multi_rank_reference_with_gpu_stokes(nproc, monkeypatch):
+    """The unmodified reference on several MPI ranks (oracle/mpi_shim), one GPU per rank: every rank's general_stokes_solver and
+    PG_timestep run on its device, halo sums and reductions over NCCL (the id travels through the reference's own MPI_Bcast)."""
+    world = nproc[0] * nproc[1] * nproc[2]
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, nproc=nproc, maxstep=3, accuracy=1e-5)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_nref_"), nsteps=nsteps, nproc=world)
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", "1")
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_ngpu_"), nsteps=nsteps, nproc=world, preload=str(DROPIN))
+    assert "citcomcu_b200 drop-in: Stokes solve on CUDA device" in err
+    for r, g in zip(ref, gpu):
+        acc = r.control()["accuracy"]
+        for k in range(nsteps + 1):
+            U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+            assert np.linalg.norm(Ug - U) < 20 * acc * max(np.linalg.norm(U), 1e-30), k
+            assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
