@@ -391,6 +391,10 @@ def run_ours(args):
         relax_kernel = ("ccu_k_col<.., MODE 0> (finest-level column-resident Gauss-Seidel smoother: stiffness streamed once per sweep through a "
                         "bulk-copy ring in shared memory; " + ("one launch per sweep" if col_wf else "one launch per column colour") + ")")
         tkey = "ccu_k_col_relax"
+    elif ctx.get_option("relax_full", lm):
+        relax_kernel = ("ccu_k_relax_full<2> (one colour pass of the finest-level 8-colour Gauss-Seidel smoother, rows streamed from "
+                        "the full-row copy of the stiffness)")
+        tkey = "ccu_k_relax_full"
     else:
         relax_kernel = "ccu_k_relax_tab<2> (one colour pass of the finest-level 8-colour Gauss-Seidel smoother)"
         tkey = "ccu_k_relax_tab"
@@ -416,7 +420,7 @@ def run_ours(args):
                          "launches": relax_n, "avg_launch_ms": relax_ms / max(relax_n, 1),
                          "share_of_step": relax_ms / prof_total_ms},
             "smoother_gbs": relax_gbs, "matvec_gbs": mv_gbs,
-            "matvec": {"kernel": "ccu_k_col<.., MODE 1/2>" if matvec_col else "ccu_k_matvec_tab", "achieved": mv_gbs, "frac": mv_gbs / peak,
+            "matvec": {"kernel": "ccu_k_matvec_full" if ctx.get_option("matvec_full", lm) else ("ccu_k_col<.., MODE 1/2>" if matvec_col else "ccu_k_matvec_tab"), "achieved": mv_gbs, "frac": mv_gbs / peak,
                        "algorithmic_bytes_per_launch": MATVEC_BYTES_PER_NODE * nno, "launches": mv_n, "avg_launch_ms": mv_ms / max(mv_n, 1),
                        "share_of_step": mv_ms / prof_total_ms},
             "operator_rebuild_ms_per_step": build_ms / args.steps,

@@ -26,6 +26,8 @@ struct Level
 {
     CcuGeom g;
     float *K = nullptr;
+    float *KT = nullptr;          // [117][NS] the thirteen upper-neighbour blocks transposed to the node's own slot (full rows: ccu_k_relax_full); null: none
+    bool have_KT = false;
     unsigned char *Kc = nullptr;  // column-major copy of K, BI, flags for the column kernels (ccu_col.cuh); col_shape < 0: none
     size_t *colofs = nullptr;     // [col_nI * col_nJ] byte offset of each column's first chunk
     size_t Kc_bytes = 0; int col_shape = -1, col_nI = 0, col_nJ = 0;
@@ -83,6 +85,7 @@ struct ccu_ctx
     int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0, opt_bottom_cluster = 1, opt_coop_nodes = 0, opt_mid_lanes = 4;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     // column-resident smoother / matvec (ccu_col.cuh) on levels above opt_col_nodes nodes
     int opt_col_nodes = 2000000, opt_relax_col = 0, opt_matvec_col = 1, opt_col_shape = 0, opt_col_wf = 1;
+    int opt_full_nodes = 500000, opt_relax_full = 0, opt_matvec_full = 0;   // full-row copy of K on levels above opt_full_nodes nodes
     Level L[CCU_MAX_LEVELS];
     double *scal = nullptr;        // device scalars
     double *partial = nullptr;     // dot partials

@@ -688,6 +688,89 @@ __device__ __forceinline__ void ccu_row_product_tab(const size_t NS, const int *
     }
     a0 = r0; a1 = r1; a2 = r2;
 }
+// The same row from FULL storage: the thirteen blocks towards the upper neighbours were copied (transposed) to the node's own
+// slot (KT, ccu_k_build_KT), so every coefficient of the row streams with unit stride and is read from HBM once per pass --
+// the gather above reads each stored block twice per sweep (own + transposed use), 2.5x the algorithmic bytes (ncu r01).
+template <int U>
+__device__ __forceinline__ void ccu_row_product_full(const size_t NS, const int *__restrict__ off, const float *__restrict__ K,
+                                                     const float *__restrict__ KT, const double *x, const int s, double &a0, double &a1, double &a2)
+{
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+#pragma unroll U
+    for(int b = 0; b < 27; b++)
+    {
+        const int sm = s + off[b];
+        const float *Kp = (b < 14 ? K + (size_t)(b * 9) * NS : KT + (size_t)((b - 14) * 9) * NS) + s;
+        float k[9];
+#pragma unroll
+        for(int e = 0; e < 9; e++) k[e] = ccu_ldg_na(Kp + (size_t)e * NS);
+        const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
+        r0 += (double)k[0] * x0 + (double)k[1] * x1 + (double)k[2] * x2;
+        r1 += (double)k[3] * x0 + (double)k[4] * x1 + (double)k[5] * x2;
+        r2 += (double)k[6] * x0 + (double)k[7] * x1 + (double)k[8] * x2;
+    }
+    a0 = r0; a1 = r1; a2 = r2;
+}
+// KT[(t*9 + 3a + bb)][s] = K[((t+1)*9 + 3bb + a)][s + off[14+t]]: block t+1 of the upper neighbour, transposed
+__global__ void __launch_bounds__(256) ccu_k_build_KT(const CcuGeom g, const __grid_constant__ CcuStencil st, const float *__restrict__ K, float *__restrict__ KT)
+{
+    const int c = blockIdx.y;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    const size_t NS = (size_t)g.NS;
+    const int s = c * g.NC + cell;
+    for(int t = 0; t < 13; t++)
+    {
+        const int sm = s + st.off[c][14 + t];
+        const float *Kp = K + (size_t)((t + 1) * 9) * NS + sm;
+        float *o = KT + (size_t)(t * 9) * NS + s;
+#pragma unroll
+        for(int a = 0; a < 3; a++)
+#pragma unroll
+            for(int bb = 0; bb < 3; bb++) o[(size_t)(3 * a + bb) * NS] = __ldg(Kp + (size_t)(3 * bb + a) * NS);
+    }
+}
+template <int U>
+__global__ void __launch_bounds__(128) ccu_k_relax_full(const CcuGeom g, const __grid_constant__ CcuStencil st, const int c,
+                                                         const float *__restrict__ K, const float *__restrict__ KT, const double *__restrict__ BI,
+                                                         const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    const int s = c * g.NC + cell;
+    if(bits && (bits[s] & CCU_B_SHARED)) return;
+    double a0, a1, a2;
+    ccu_row_product_full<U>((size_t)g.NS, st.off[c], K, KT, x, s, a0, a1, a2);
+    ccu_relax_update(g, BI, F, x, s, a0, a1, a2);
+}
+template <int MODE, int U>
+__global__ void __launch_bounds__(256) ccu_k_matvec_full(const CcuGeom g, const __grid_constant__ CcuStencil st, const float *__restrict__ K,
+                                                          const float *__restrict__ KT, const unsigned char *__restrict__ flags, const double *u,
+                                                          const double *rhs, double *out, const int strip)
+{
+    const int c = threadIdx.x >> 5;
+    const int cell = blockIdx.x * 32 + (threadIdx.x & 31);
+    if(cell >= g.NC) return;
+    int i, j, k;
+    if(!ccu_decode(g, c, cell, i, j, k)) return;
+    const size_t NS = (size_t)g.NS;
+    const int s = c * g.NC + cell;
+    double a0, a1, a2;
+    ccu_row_product_full<U>(NS, st.off[c], K, KT, u, s, a0, a1, a2);
+    if(strip)
+    {
+        const unsigned char f = flags[s];
+        if(f & CCU_F_VBX) a0 = 0.0;
+        if(f & CCU_F_VBY) a1 = 0.0;
+        if(f & CCU_F_VBZ) a2 = 0.0;
+    }
+    if(MODE == 0) { out[s] = a0; out[NS + s] = a1; out[2 * NS + s] = a2; }
+    else { out[s] = rhs[s] - a0; out[NS + s] = rhs[NS + s] - a1; out[2 * NS + s] = rhs[2 * NS + s] - a2; }
+}
 template <int MODE, int U, int NA = 0>
 __global__ void __launch_bounds__(256) ccu_k_matvec_tab(const CcuGeom g, const __grid_constant__ CcuStencil st, const float *__restrict__ K,
                                                          const unsigned char *__restrict__ flags, const double *u,

@@ -113,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.col_inv); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.KT); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.col_inv); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -166,6 +166,9 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_COL_NODES: c->opt_col_nodes = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_RELAX_COL: c->opt_relax_col = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_MATVEC_COL: c->opt_matvec_col = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_FULL_NODES: c->opt_full_nodes = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_RELAX_FULL: c->opt_relax_full = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_MATVEC_FULL: c->opt_matvec_full = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_COL_WF: c->opt_col_wf = value != 0; if(c->coarse) c->coarse->opt_col_wf = c->opt_col_wf; drop_graphs(c); return 0;
     case CCU_OPT_COL_SHAPE: if(value < 0 || value > 2) FAIL("column shape must be 0..2"); c->opt_col_shape = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
@@ -184,6 +187,9 @@ int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
     case CCU_OPT_GRAPHS: *value = c->use_graphs; return 0;
     case CCU_OPT_RELAX_COL: *value = col && c->opt_relax_col; return 0;
     case CCU_OPT_MATVEC_COL: *value = col && c->opt_matvec_col; return 0;
+    case CCU_OPT_FULL_NODES: *value = c->opt_full_nodes; return 0;
+    case CCU_OPT_RELAX_FULL: *value = c->L[lev].have_KT && c->opt_relax_full; return 0;
+    case CCU_OPT_MATVEC_FULL: *value = c->L[lev].have_KT && c->opt_matvec_full; return 0;
     case CCU_OPT_COL_WF: *value = c->opt_col_wf; return 0;
     case CCU_OPT_COL_SHAPE: *value = c->L[lev].col_shape; return 0;
     case CCU_OPT_COL_NODES: *value = c->opt_col_nodes; return 0;
@@ -460,6 +466,18 @@ static int col_relayout(ccu_ctx *c, Level &L, int lev)
 int ccu_col_refresh(ccu_ctx *c, int lev)
 {
     Level &L = c->L[lev];
+    // full-row copy (ccu_k_build_KT)
+    L.have_KT = false;
+    if((c->opt_relax_full || c->opt_matvec_full) && L.g.nno > c->opt_full_nodes && L.have_K)
+    {
+        if(!L.KT)
+        {
+            CK(cudaMalloc(&L.KT, sizeof(float) * 117 * (size_t)L.g.NS));
+            CK(cudaMemsetAsync(L.KT, 0, sizeof(float) * 117 * (size_t)L.g.NS, c->st));
+        }
+        LAUNCH(c, ccu_k_build_KT, dim3(cdiv(L.g.NC, 256), 8), 256, L.g, ccu_make_stencil(L.g), L.K, L.KT);
+        L.have_KT = true;
+    }
     L.col_shape = -1;
     if(!(c->opt_relax_col || c->opt_matvec_col) || L.g.nno <= c->opt_col_nodes || !L.have_K || !L.have_flags) return 0;
     int rc;
@@ -479,6 +497,7 @@ static int col_refresh_all(ccu_ctx *c)
     {
         c->coarse->opt_col_nodes = c->opt_col_nodes; c->coarse->opt_relax_col = c->opt_relax_col; c->coarse->opt_matvec_col = c->opt_matvec_col;
         c->coarse->opt_col_shape = c->opt_col_shape; c->coarse->opt_col_wf = c->opt_col_wf;
+        c->coarse->opt_full_nodes = c->opt_full_nodes; c->coarse->opt_relax_full = c->opt_relax_full; c->coarse->opt_matvec_full = c->opt_matvec_full;
         return col_refresh_all(c->coarse);
     }
     return 0;
@@ -499,7 +518,8 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);   // the table-driven kernel wins from ~1e4 nodes up
-    if(use_col(c, L, c->opt_matvec_col)) launch_col_shape<1, 0>(c, L, 0, nullptr, const_cast<double *>(u), Au, strip);
+    if(c->opt_matvec_full && L.have_KT) LAUNCH(c, (ccu_k_matvec_full<0, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.KT, L.flags, u, nullptr, Au, strip);
+    else if(use_col(c, L, c->opt_matvec_col)) launch_col_shape<1, 0>(c, L, 0, nullptr, const_cast<double *>(u), Au, strip);
     else if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab == 24) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
@@ -521,6 +541,7 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
     CcuProfScope ps(c, CCU_PROF_MATVEC_FINE, &L == &c->L[c->cfg.levmax]);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + (int)(&L - c->L), true, 0);
     const int T = (c->opt_matvec_tab && L.g.nno > c->opt_matvec_tab_nodes) ? 1 : lanes_for(c, L);
+    if(c->opt_matvec_full && L.have_KT) { LAUNCH(c, (ccu_k_matvec_full<1, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.KT, L.flags, u, rhs, out, 1); return; }
     if(use_col(c, L, c->opt_matvec_col)) { launch_col_shape<2, 0>(c, L, 0, rhs, const_cast<double *>(u), out, 1); return; }
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
@@ -733,6 +754,12 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
             if(c->opt_mid_lanes == 16) launch_relax_lanes<16>(c, L, x, F, bits);
             else if(c->opt_mid_lanes == 8) launch_relax_lanes<8>(c, L, x, F, bits);
             else launch_relax_lanes<4>(c, L, x, F, bits);
+            continue;
+        }
+        if(c->opt_relax_full && L.have_KT)
+        {   // full rows: every coefficient streams once per sweep
+            const CcuStencil st = ccu_make_stencil(L.g);
+            for(int col = 7; col >= 0; col--) LAUNCH(c, ccu_k_relax_full<2>, grid, 128, L.g, st, col, L.K, L.KT, L.BI, F, x, bits);
             continue;
         }
         if(c->opt_relax_tab)

@@ -62,6 +62,11 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
         * colours of a sweep run in one launch, columns waiting on progress words of their neighbours; 0: one launch per colour
         * (bitwise the same result). */
        CCU_OPT_COL_NODES = 9, CCU_OPT_RELAX_COL = 10, CCU_OPT_MATVEC_COL = 11, CCU_OPT_COL_SHAPE = 13, CCU_OPT_COL_WF = 14,
+       /* levels with nno > FULL_NODES (default 500000) also keep the thirteen upper-neighbour blocks of every node, transposed, at the
+        * node's own slot (+468 B/node) when RELAX_FULL or MATVEC_FULL is set (both default 0): the colour-pass smoother / matvec then stream
+        * every coefficient of a row once per pass instead of gathering each stored block twice.  Measured on B200 (r02): 1.27x fewer DRAM
+        * bytes but only 3 % faster (the pass stops being DRAM-bound), the matvec slower -- kept as an option, see DESIGN.md */
+       CCU_OPT_FULL_NODES = 18, CCU_OPT_RELAX_FULL = 19, CCU_OPT_MATVEC_FULL = 20,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */,
        CCU_OPT_COOP_NODES = 16 /* single-subdomain levels with SMALL_NODES < nno <= this (default 0 = off: measured no faster than the graph-replayed per-pass launches) run each smoother call as one

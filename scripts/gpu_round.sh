@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "column" ) > gpurun_out/pytest_col.log 2>&1
+( time timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k "variants or column" ) > gpurun_out/pytest_col.log 2>&1
 tail -3 gpurun_out/pytest_col.log
-for v in "relax_col=0" "relax_col=1" "matvec_col=0"; do
+for v in "relax_full=1" "matvec_full=1" "relax_full=0"; do
   timeout 900 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-parity --opt $v > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
   python - <<PY
 import json

@@ -177,6 +177,8 @@ def test_empty_rhs_is_a_noop(case):
     dict(small_nodes=10**9, bottom_cluster=0),                                                                                   # one SM, shared-memory resident half-matrix
     dict(graphs=0),
     dict(relax_col=0, matvec_col=0),
+    dict(full_nodes=0, relax_full=1, matvec_full=1),                                                                             # full rows (upper-neighbour blocks copied to the node's own slot)
+    dict(full_nodes=0, relax_full=1, matvec_full=1, small_nodes=0, warp_nodes=0, quad_nodes=0, cluster_nodes=0, coop_nodes=0),
     dict()])                                                                                                                     # defaults
 def test_kernel_variants_agree(case, opts):
     """Every lanes-per-node variant of the smoother / matvec and the CUDA-graph replay give the same answers."""
