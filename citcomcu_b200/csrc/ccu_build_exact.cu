@@ -190,17 +190,25 @@ __global__ void __launch_bounds__(128) bk_invert_BI(const size_t n, double *v)
 }
 
 // ---------------------------------------------------------------- viscosity
-// visc_from_T (Viscosity_structures.c:491-) rheol 0/1/3 + visc_from_mat (:477) + min/max clip (:411-425)
+// visc_from_T (Viscosity_structures.c:491-742) rheol 0, 1, 2, 3, 4, 10, 11 + visc_from_mat (:477) + min/max clip (:411-425).
+// X3 = E->X[3] (Cartesian depth coordinate of the nodes) for the depth-dependent laws 2 and 4.  The operand types follow
+// the reference expression by expression (float temperature sums, double depth sums, the double constant 0.5 of law 11).
 __global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscParams vp, const int *__restrict__ mat,
-                                               const float *__restrict__ T, float *EVI)
+                                               const float *__restrict__ T, const float *__restrict__ X3, float *EVI)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
     const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
     const int l = mat[e] - 1;
     const float tempa = vp.N0[l];
-    float TT[8];
-    for(int a = 1; a <= 8; a++) TT[a - 1] = T[elt_node(g, ey, ex, ez, a)];
+    float TT[8], ZZ[8];
+    const bool depth = vp.tdepv && (vp.rheol == 2 || vp.rheol == 4);
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        TT[a - 1] = T[n];
+        ZZ[a - 1] = depth ? X3[n] : 0.0f;
+    }
     for(int jj = 0; jj < 8; jj++)
     {
         float v;
@@ -208,15 +216,70 @@ __global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscPar
         else
         {
             float temp = 1.0e-32f;
-            for(int kk = 0; kk < 8; kk++) temp = (float)((double)temp + fmaxf(0.0f, TT[kk]) * c_sh.Nv[8 * kk + jj]);   // float*double
-            if(vp.rheol == 0) v = (float)((double)tempa * exp((double)(vp.E[l] * (1.0f - temp))));
-            else if(vp.rheol == 1) v = (float)((double)tempa * exp((double)(vp.E[l] / (temp + vp.T[l]))));
-            else v = (float)((double)tempa * exp((double)(vp.E[l] * (vp.T[l] - temp))));      // rheol 3
+            double zz = 0.0;
+            for(int kk = 0; kk < 8; kk++)
+            {
+                temp = (float)((double)temp + fmaxf(0.0f, TT[kk]) * c_sh.Nv[8 * kk + jj]);   // float*double
+                if(depth) zz += ZZ[kk] * c_sh.Nv[8 * kk + jj];
+            }
+            const float El = vp.E[l], Tl = vp.T[l], Zl = vp.Z[l];
+            switch(vp.rheol)
+            {
+            case 0: v = (float)((double)tempa * exp((double)(El * (1.0f - temp)))); break;                    // eta0 exp(E (1 - T))
+            case 1: v = (float)((double)tempa * exp((double)(El / (temp + Tl)))); break;                      // eta0 exp(E / (T + T0))
+            case 2: v = (float)((double)tempa * exp(((double)El + (1 - zz) * (double)Zl) / (double)(temp + Tl))); break;   // eta0 exp((E + (1-z) Z0) / (T + T0))
+            case 3: v = (float)((double)tempa * exp((double)(El * (Tl - temp)))); break;                      // eta0 exp(E (T0 - T))
+            case 4: v = (float)((double)tempa * exp((double)(El * (Tl - temp)) + (1 - zz) * (double)Zl)); break;            // eta0 exp(E (Tc - T) + (1-z) Z)
+            case 10: v = (float)((double)tempa * exp((double)(El / (temp + Tl) + Zl))); break;                // eta0 exp(E / (T + T0) + Z)
+            default: v = (float)((double)tempa * exp((double)(El / (temp + Tl)) - (double)El / (0.5 + (double)Tl))); break; // 11: eta0 exp(E/(T+T0) - E/(0.5+T0))
+            }
         }
         if(vp.vmax && v > vp.max_value) v = vp.max_value;
         if(vp.vmin && v < vp.min_value) v = vp.min_value;
         EVI[(size_t)e * 8 + jj] = v;
     }
+}
+
+// visc_from_gint_to_ele (Nodal_mesh.c:559-581): element mean of the eight Gauss-point values (double sum)
+__global__ void __launch_bounds__(128) bk_gint_to_ele(const int nel, const float *__restrict__ EVI, float *VN)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= nel) return;
+    double t = 0.0;
+    for(int i = 0; i < 8; i++) t += EVI[(size_t)e * 8 + i];
+    t = t / 8;
+    VN[e] = (float)t;
+}
+// inject_scalar (Solver_multigrid.c:641-673): the coarse node takes the value of the coincident fine node
+__global__ void __launch_bounds__(128) bk_inject_scalar(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ AU, float *AD)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= gc.nno) return;
+    const int K = n % gc.noz, J = (n / gc.noz) % gc.nox, I = n / (gc.noz * gc.nox);
+    AD[n] = AU[2 * K + gf.noz * (2 * J + gf.nox * 2 * I)];
+}
+// inject_scalar_e (Solver_multigrid.c:675-698): Gauss point i of a coarse element = the mean of its i-th fine sub-element;
+// project_scalar_e (:306-342) + visc_from_ele_to_gint (Nodal_mesh.c:541-557): every Gauss point = the mean over the eight
+// sub-elements (float sum in the order of EL.sub, times the double weight 1/8)
+template <int AVERAGE>
+__global__ void __launch_bounds__(128) bk_scalar_e_to_gint(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ VNf, float *EVIc)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= gc.nel) return;
+    const int ez = e % gc.elz, ex = (e / gc.elz) % gc.elx, ey = e / (gc.elz * gc.elx);
+    float sub[8];
+    for(int i = 1; i <= 8; i++)      // EL[lev][e].sub[i]: fine element at twice the coarse indices plus the offset of local node i (Construct_arrays.c:659)
+        sub[i - 1] = VNf[(2 * ez + c_OFFS[i][0]) + gf.elz * ((2 * ex + c_OFFS[i][1]) + gf.elx * (2 * ey + c_OFFS[i][2]))];
+    if(AVERAGE)
+    {
+        const double weight = (double)1.0 / 8;
+        float average = 0.0f;
+        for(int i = 0; i < 8; i++) average += sub[i];
+        const float ad = (float)(average * weight);
+        for(int i = 0; i < 8; i++) EVIc[(size_t)e * 8 + i] = ad;
+    }
+    else
+        for(int i = 0; i < 8; i++) EVIc[(size_t)e * 8 + i] = sub[i];
 }
 
 // visc_from_gint_to_nodes (Nodal_mesh.c:583-615)
@@ -1238,8 +1301,9 @@ int ccu_set_viscosity_law(ccu_ctx *c, int tdepv, int rheol, int num_mat, const f
 {
     if(!c) FAIL("null context");
     if(num_mat < 1 || num_mat > 40) FAIL("bad num_mat");
-    if(tdepv && !(rheol == 0 || rheol == 1 || rheol == 3)) FAIL("viscosity law: only rheol 0, 1, 3 are implemented on the device");
-    if(smooth_cycles != 1) FAIL("project_viscosity: only visc_smooth_cycles=1 is implemented on the device");
+    if(tdepv && !(rheol == 0 || rheol == 1 || rheol == 2 || rheol == 3 || rheol == 4 || rheol == 10 || rheol == 11))
+        FAIL("viscosity law: RHEOL option undefined in TDEPV (the reference knows 0, 1, 2, 3, 4, 10, 11)");
+    if(smooth_cycles < 0 || smooth_cycles > 3) FAIL("project_viscosity: visc_smooth_cycles must be 0 .. 3");
     CcuViscParams &v = c->visc;
     v.tdepv = tdepv; v.rheol = rheol; v.num_mat = num_mat; v.vmin = vmin; v.vmax = vmax; v.min_value = min_value; v.max_value = max_value;
     v.smooth_cycles = smooth_cycles;
@@ -1296,7 +1360,8 @@ int ccu_get_system_viscosity(ccu_ctx *c)
     if(ensure_tables(c) || ensure_nodal(c)) return 1;
     if(!c->mat) FAIL("get_system_viscosity: material groups missing");
     Level &L = c->L[c->cfg.levmax];
-    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.EVI);
+    if(c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4) && !L.have_xx) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
+    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr, L.EVI);
     CK(cudaGetLastError());
     L.have_evi = true;
     return 0;
@@ -1309,11 +1374,34 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
     if(ensure_tables(c) || ensure_nodal(c)) return 1;
     const int levmax = c->cfg.levmax, levmin = c->cfg.levmin;
     if(!c->L[levmax].have_evi) FAIL("construct_stiffness_B_matrix: finest-level viscosity missing");
-    // project_viscosity, visc_smooth_cycles == 1 (Solver_multigrid.c:449-454)
+    // project_viscosity (Solver_multigrid.c:398-474), the four modes of visc_smooth_cycles
+    const int mode = c->visc.smooth_cycles;
     for(int lv = levmax; lv > levmin; lv--)
     {
         Level &Lf = c->L[lv], &Lc = c->L[lv - 1];
         if(!Lf.have_tw || !Lc.have_tw) FAIL("construct_stiffness_B_matrix: geometry not built");
+        if(mode == 2 || mode == 3)
+        {   // element means, injected per sub-element (2) or averaged over the sub-elements (3): no node sums, no exchange
+            LAUNCH(c, bk_gint_to_ele, cdiv(Lf.g.nel, 128), 128, Lf.g.nel, (const float *)Lf.EVI, c->nodal_tmp);
+            if(mode == 2) LAUNCH(c, bk_scalar_e_to_gint<0>, cdiv(Lc.g.nel, 128), 128, Lc.g, Lf.g, (const float *)c->nodal_tmp, Lc.EVI);
+            else LAUNCH(c, bk_scalar_e_to_gint<1>, cdiv(Lc.g.nel, 128), 128, Lc.g, Lf.g, (const float *)c->nodal_tmp, Lc.EVI);
+            Lc.have_evi = true;
+            continue;
+        }
+        if(mode == 0)
+        {   // nodal values of the fine level injected at the coincident nodes
+            if(!c->multi()) LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, Lf.MASS, c->nodal_tmp);
+            else
+            {
+                LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, (const float *)nullptr, c->nodal_tmp);
+                if(ccu_halo_sum_nodal(c, lv, c->nodal_tmp)) return 1;
+                LAUNCH(c, bk_mul, cdiv(Lf.g.nno, 128), 128, Lf.g.nno, c->nodal_tmp, Lf.MASS);
+            }
+            LAUNCH(c, bk_inject_scalar, cdiv(Lc.g.nno, 128), 128, Lc.g, Lf.g, (const float *)c->nodal_tmp, c->nodal_tmp2);
+            LAUNCH(c, bk_nodes_to_gint, cdiv(Lc.g.nel, 128), 128, Lc.g, c->nodal_tmp2, Lc.EVI);
+            Lc.have_evi = true;
+            continue;
+        }
         if(!c->multi())
         {
             LAUNCH(c, bk_gint_to_nodes, cdiv(Lf.g.nno, 128), 128, Lf.g, Lf.EVI, Lf.TWW, Lf.MASS, c->nodal_tmp);

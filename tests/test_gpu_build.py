@@ -70,3 +70,46 @@ def test_device_operator_construction_bit_exact(name, tdepv, viscE):
     V, P, steps, res, hist = ctx.solve_Ahat_p_fhat(np.zeros(n), np.zeros(npno), F, acc, 375)
     assert np.linalg.norm(V - d["s0_U"]) < 20 * acc * np.linalg.norm(d["s0_U"])
     ctx.close()
+
+
+RHEOL_CASES = {
+    # rheol: (viscE, viscT, viscZ) -- Viscosity_structures.c:568-742
+    2: (3.0, 0.5, 1.0),              # eta0 exp((E + (1-z) Z) / (T + T0))
+    4: (5.0, 0.5, 2.0),              # eta0 exp(E (Tc - T) + (1-z) Z)
+    10: (3.0, 0.5, 1.0),             # eta0 exp(E / (T + T0) + Z)
+    11: (74.357912, 4.507123, 5e-6), # eta0 exp(E/(T+T0) - E/(0.5+T0)): examples/Busse1993/case2.input
+    0: (11.512925, 273.0, 5e-6),
+}
+
+
+@pytest.mark.parametrize("rheol,smooth", [(2, 1), (4, 1), (10, 1), (11, 1), (0, 0), (0, 2), (0, 3), (11, 3), (4, 0)])
+def test_rheologies_and_viscosity_coarsening_modes(rheol, smooth):
+    """get_system_viscosity for every temperature-dependent law of the reference (RHEOL 0, 1, 2, 3, 4, 10, 11) and
+    project_viscosity for the four visc_smooth_cycles modes (Solver_multigrid.c:398-474), against the arrays the unmodified
+    reference builds from the same input file: Gauss-point viscosity on every level within one fp32 ulp (`exp`), stiffness 1e-6."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    E, T0, Z = RHEOL_CASES[rheol]
+    four = lambda v: ",".join([repr(float(v))] * 4)      # noqa: E731
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, rheol=rheol, visc_smooth_cycles=smooth, viscE=four(E), viscT=four(T0), viscZ=four(Z))
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix=f"ccu_rheol{rheol}_{smooth}_"), nsteps=0)[0][0]
+    prob = CartesianProblem(txt)
+    ctx = context_from_problem(prob)
+    ctl = prob.control
+    ctx.set_temperature(d["s0_T"])
+    ctx.get_system_viscosity()
+    ctx.construct_stiffness_B_matrix(ctl["augmented_Lagr"], ctl["augmented"], ctl["precondition"])
+    for lev in range(d.levmin, d.levmax + 1):
+        evi, ref = ctx.get_level_array(lev, "EVI"), d[f"L{lev}_EVI"]
+        assert np.allclose(evi, ref, rtol=3e-7, atol=0), (lev, float(np.abs(evi / ref - 1).max()))
+        assert frac_diff(evi, ref) < 2e-2
+        k1, k2, k3, BI = ctx.get_stiffness(lev)
+        for k, nm in ((k1, "Eqn_k1"), (k2, "Eqn_k2"), (k3, "Eqn_k3")):
+            ref = d[f"L{lev}_{nm}"]
+            assert np.allclose(k, ref, rtol=1e-6, atol=1e-6 * np.abs(ref).max()), (lev, nm)
+    ctx.close()

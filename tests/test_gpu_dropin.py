@@ -139,3 +139,31 @@ def test_multi_rank_reference_with_gpu_stokes(nproc, monkeypatch):
             U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
             assert np.linalg.norm(Ug - U) < 20 * acc * max(np.linalg.norm(U), 1e-30), k
             assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+
+
+def test_busse_case2_shipped_example(monkeypatch):
+    """examples/Busse1993/case2.input as shipped (rheol=11, temperature-dependent viscosity, non-uniform z, restart from the
+    shipped case2-tic temperature file; tests/golden holds copies of the two data files): the reference's time loop with the
+    Stokes solve and the energy step on the device against the pure-CPU run."""
+    import gzip
+    import shutil
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = (ROOT / "tests" / "golden" / "busse_case2.input").read_text()
+    nsteps = 2
+    runs = []
+    for tag, preload in (("ref", None), ("gpu", str(DROPIN))):
+        wd = Path(tempfile.mkdtemp(prefix=f"ccu_case2_{tag}_"))
+        with gzip.open(ROOT / "tests" / "golden" / "busse_case2-tic.temp.0.0.gz", "rb") as src, open(wd / "case2-tic.temp.0.0", "wb") as dst:
+            shutil.copyfileobj(src, dst)
+        monkeypatch.setenv("CCU_DROPIN_ENERGY", "1")
+        runs.append(po.run_harness(txt, wd, nsteps=nsteps, preload=preload, timeout=1200))
+    (ref, _), (gpu, err) = runs
+    assert "citcomcu_b200 drop-in: Stokes solve on CUDA device" in err
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    for k in range(nsteps + 1):
+        U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+        assert np.linalg.norm(Ug - U) < 20 * acc * np.linalg.norm(U), k
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+        assert np.allclose(g[f"s{k}_EVI"], r[f"s{k}_EVI"], rtol=1e-3), k      # viscosity contrast of the law: exp(+-8)
