@@ -1904,6 +1904,72 @@ int ccu_get_heating_latent(ccu_ctx *c, float *heating_latent_out)
     SYNC(c);
     return 0;
 }
+// averages (Process_velocity.c:179-224): horizontal averages per z layer of the nodal viscosity, of the composition and
+// of |V|^2 (-> layer vrms), from the resident velocity / viscosity / markers; return_horiz_ave (Global_operations.c:133) over
+// the ranks of a horizontal plane as in thermal_buoyancy.  Outputs float[noz] each, any may be NULL.
+__global__ void __launch_bounds__(256) ek_speed2(const int nno, const float *__restrict__ V, float *out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= nno) return;
+    const float a = V[n], b = V[(size_t)nno + n], cc = V[2 * (size_t)nno + n];
+    out[n] = a * a + b * b + cc * cc;                  // float arithmetic, as the reference's temp[i]
+}
+__global__ void __launch_bounds__(128) ek_layer_finish(const int noz, const double *__restrict__ layer, const int root, float *out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= noz) return;
+    float v = layer[noz + k] != 0.0 ? (float)(layer[k] / layer[noz + k]) : 0.0f;
+    if(root) v = (float)sqrt((double)v);
+    out[k] = v;
+}
+int ccu_averages(ccu_ctx *c, float *vrms_out, float *visc_out, float *C_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    if(!L.have_xx) FAIL("averages: coordinates missing");
+    const int noz = L.g.noz;
+    float *lay = nullptr;
+    CK(cudaMalloc(&lay, sizeof(float) * 3 * (size_t)noz));
+    auto one = [&](const float *field, int root, float *dev_out, float *host_out) -> int
+    {
+        LAUNCH(c, ek_layer_sums, noz, 256, L.g, (const float *)L.XX, field, E.layer);
+        if(layer_allreduce(c)) return 1;
+        LAUNCH(c, ek_layer_finish, cdiv(noz, 128), 128, noz, (const double *)E.layer, root, dev_out);
+        CK(cudaMemcpyAsync(host_out, dev_out, sizeof(float) * noz, cudaMemcpyDeviceToHost, c->st));
+        return 0;
+    };
+    int rc = 0;
+    if(vrms_out && !rc)
+    {
+        if(!E.have_v) { cudaFree(lay); FAIL("averages: velocity missing (ccu_set_velocity / ccu_v_from_vector)"); }
+        LAUNCH(c, ek_speed2, cdiv(L.g.nno, 256), 256, L.g.nno, (const float *)E.V, c->nodal_tmp);
+        rc = one(c->nodal_tmp, 1, lay, vrms_out);
+    }
+    if(visc_out && !rc)
+    {
+        if(!L.have_evi || !L.have_tw) { cudaFree(lay); FAIL("averages: viscosity missing"); }
+        if(!c->multi()) LAUNCH(c, bk_gint_to_nodes, cdiv(L.g.nno, 128), 128, L.g, L.EVI, L.TWW, L.MASS, c->nodal_tmp);
+        else
+        {
+            LAUNCH(c, bk_gint_to_nodes, cdiv(L.g.nno, 128), 128, L.g, L.EVI, L.TWW, (const float *)nullptr, c->nodal_tmp);
+            rc = ccu_halo_sum_nodal(c, c->cfg.levmax, c->nodal_tmp);
+            LAUNCH(c, bk_mul, cdiv(L.g.nno, 128), 128, L.g.nno, c->nodal_tmp, L.MASS);
+        }
+        if(!rc) rc = one(c->nodal_tmp, 0, lay + noz, visc_out);
+    }
+    if(C_out && !rc)
+    {
+        if(!c->mk.ready) { cudaFree(lay); FAIL("averages: no compositional field (markers) resident"); }
+        rc = one((const float *)c->mk.C, 0, lay + 2 * noz, C_out);
+    }
+    if(!rc) { const cudaError_t e = cudaStreamSynchronize(c->st); if(e != cudaSuccess) rc = 1; }
+    cudaFree(lay);
+    if(rc) return rc;
+    CK_LAUNCHES(c);
+    return 0;
+}
 // heat_flux (Process_buoyancy.c:63-203): Nusselt numbers at the top and bottom of the box from the resident T and velocity
 int ccu_heat_flux(ccu_ctx *c, float *Nut_out, float *Nub_out)
 {

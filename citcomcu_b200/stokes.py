@@ -493,6 +493,23 @@ class StokesContext:
     def markers_count(self):
         return int(self.lib.ccu_markers_count(self._ctx))
 
+    def averages(self, composition=False):
+        """averages (Process_velocity.c:179): layer vrms, layer mean viscosity (and composition): float[noz] arrays."""
+        noz = self.dims[self.levmax][2]
+        vr, vi = np.zeros(noz, np.float32), np.zeros(noz, np.float32)
+        cc = np.zeros(noz, np.float32) if composition else None
+        check(self.lib.ccu_averages(self._ctx, vr.ctypes.data_as(C.c_void_p), vi.ctypes.data_as(C.c_void_p),
+                                    cc.ctypes.data_as(C.c_void_p) if composition else None))
+        return (vr, vi, cc) if composition else (vr, vi)
+
+    @staticmethod
+    def volume_vrms(layer_vrms, z):
+        """Volume-weighted Vrms of a Cartesian box from the layer values: sqrt of the trapezoid z-integral of vrms(z)^2 over the
+        height (the reference keeps only the layers, SURVEY.md 8c: both arms of a parity check use this same definition)."""
+        v2 = np.asarray(layer_vrms, dtype=np.float64) ** 2
+        z = np.asarray(z, dtype=np.float64)
+        return float(np.sqrt(np.trapezoid(v2, z) / (z[-1] - z[0])))
+
     def PG_timestep_particle(self, Atemp):
         """PG_timestep_particle (Advection_diffusion.c:128): alternates, like the reference's static `on_off`, between
         (0) std_timestep + thermal step + Euler marker predictor and (1) the Runge_Kutta marker corrector with the new

@@ -242,6 +242,9 @@ int ccu_get_temperature(ccu_ctx *ctx, float *T /*[nno]*/, float *Tdot /*[nno] or
  * (element heat transport, nodal projection through TWW / Mass, linear extrapolation to the top and bottom surfaces,
  * area-weighted means); across subdomains the nodal sums and the four surface sums are reduced over NCCL */
 int ccu_heat_flux(ccu_ctx *ctx, float *Nut_out, float *Nub_out);
+/* averages (Process_velocity.c:179): horizontal averages per z layer -- E->Have.vrms (sqrt of the layer mean of |V|^2), E->Have.Vi (nodal
+ * viscosity), E->Have.C (composition) -- float[noz] each, any may be NULL; summed over the ranks of a horizontal plane */
+int ccu_averages(ccu_ctx *ctx, float *vrms_out, float *visc_out, float *C_out);
 
 /* ---- markers of the compositional field (Composition_adv.c), Cartesian, one subdomain ----
  * E->advection.markers / markers_uplimit / markers_per_ele, E->lmesh.rnoz, E->XP[d]+1 (double[nox|noy|noz]), E->RG[3]

@@ -157,6 +157,10 @@ static void dump_fields(struct All_variables *E, const char *tag)
                          E->monitor.T_interior, (double)E->monitor.solution_cycles, E->monitor.vdotv, E->monitor.pdotp };
         snprintf(nm, sizeof nm, "%s_scalars", tag); DUMP_F64(nm, sc, 8);
     }
+    /* layer averages of the reference's averages() (Process_velocity.c:179; current when storage_spacing divides the step) */
+    snprintf(nm, sizeof nm, "%s_Have_vrms", tag); DUMP_F32(nm, E->Have.vrms + 1, E->lmesh.noz);
+    snprintf(nm, sizeof nm, "%s_Have_Vi", tag); DUMP_F32(nm, E->Have.Vi + 1, E->lmesh.noz);
+    snprintf(nm, sizeof nm, "%s_XP3", tag); DUMP_F64(nm, E->XP[3] + 1, E->lmesh.noz);
 }
 
 static void strip(struct All_variables *E, double *v, int lev) { strip_bcs_from_residual(E, v, lev); }

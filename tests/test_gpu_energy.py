@@ -225,3 +225,48 @@ def test_coupled_timesteps_with_phase_changes(phase_state):
         ref = d[f"s{step}_T"]
         assert abs(dt - d[f"s{step}_scalars"][1]) <= 2e-3 * d[f"s{step}_scalars"][1]
         assert np.linalg.norm(T - ref) <= 1e-3 * np.linalg.norm(ref)
+
+
+def test_observables_on_a_developed_state():
+    """Nusselt numbers, layer vrms (averages, Process_velocity.c:179) and the volume-weighted Vrms on a DEVELOPED state: the
+    reference runs 30 timesteps from a strong perturbation with storage_spacing=1 (so that it re-evaluates heat_flux and averages on every step, not
+    only at step 0), the device evaluates the same observables from the reference's T and V of each step: 0.1 % (north star)."""
+    import tempfile
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import StokesContext, context_from_problem
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=40, accuracy=1e-4, storage_spacing=1, rayleigh=1e6, perturbmag=0.3,
+                              viscE="4.6,4.6,4.6,4.6")
+    nsteps = 30
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_obs_"), nsteps=nsteps)[0][0]
+    prob = CartesianProblem(txt)
+    ctx = context_from_problem(prob)
+    lm = prob.levmax
+    noz = prob.dims(lm)[2]
+    ctx.set_energy_params(0.75, 0.0, 0.5, 2, np.ones(noz, np.float32), np.ones(noz, np.float32), 0.0)
+    ctl = prob.control
+    seen = []
+    for k in (0, 10, 20, 30):
+        sc = d[f"s{k}_scalars"]
+        ctx.set_temperature(d[f"s{k}_T"])
+        # main()'s order (Citcom.c:111-161): energy step, process_temp_field (heat_flux with the NEW temperature and the velocity
+        # of the previous solve), Stokes solve, process_new_velocity (averages with the new velocity)
+        kv = max(k - 1, 0)
+        ctx.set_velocity(d[f"s{kv}_V1"], d[f"s{kv}_V2"], d[f"s{kv}_V3"])
+        nut, nub = ctx.heat_flux()
+        assert abs(nut - sc[2]) <= 1e-3 * abs(sc[2]) and abs(nub - sc[3]) <= 1e-3 * abs(sc[3]), (k, nut, nub, sc[2], sc[3])
+        ctx.set_velocity(d[f"s{k}_V1"], d[f"s{k}_V2"], d[f"s{k}_V3"])
+        ctx.set_element_viscosity(lm, d[f"s{k}_EVI"])
+        vr, vi = ctx.averages()
+        ref_vr, ref_vi = d[f"s{k}_Have_vrms"], d[f"s{k}_Have_Vi"]
+        assert np.abs(vr - ref_vr).max() <= 1e-3 * np.abs(ref_vr).max(), k
+        assert np.abs(vi - ref_vi).max() <= 1e-3 * np.abs(ref_vi).max(), k
+        z = d[f"s{k}_XP3"]
+        V, Vr = StokesContext.volume_vrms(vr, z), StokesContext.volume_vrms(ref_vr, z)
+        assert abs(V - Vr) <= 1e-3 * Vr
+        seen.append((float(sc[2]), Vr))
+    ctx.close()
+    # the state did develop: Nu and Vrms moved away from their step-0 values
+    assert abs(seen[-1][0] - seen[0][0]) > 1.0 and abs(seen[-1][1] - seen[0][1]) > 0.1 * seen[0][1]
