@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--ref-mesh", default=None, help="mesh for the CPU reference (default: the benchmark mesh itself)")
     ap.add_argument("--ref-levels", type=int, default=None)
     ap.add_argument("--no-parity", action="store_true", help="skip the 64x64x32 parity sample")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5],
+                    help="BASELINE config: 3 = Stokes solve at 256x256x128 (the headline), 5 = thermochemical marker advection, "
+                         "128x128x64 elements x 20 markers per element")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="diagnostic: launch coarse levels kernel by kernel and report per-level times")
     ap.add_argument("--opt", action="append", default=[], help="diagnostic: library option name=value (ccu_set_option)")
@@ -456,8 +459,171 @@ def run_ours(args):
     return 0
 
 
+MARKER_BYTES_PER_SUBSTEP = 170.0     # XMC / XMCpred / VO / Vpred / C12 / CElement read + written, per marker per substep
+
+
+def marker_setup_arrays(prob, rng, markers_per_ele, comp_depth=0.605):
+    """Synthetic marker state for one subdomain, laid out as the reference keeps it (Convection.c:650-676 seeds uniformly in
+    the box; C12 by depth, :846; pre_interpolation's z lookup table, Nodal_mesh.c:284; SIDEE flags, Parallel_related.c:1005)."""
+    lm = prob.levmax
+    nox, noy, noz = prob.dims(lm)
+    elx, ely, elz = nox - 1, noy - 1, noz - 1
+    X1, X2, X3 = prob.coordinates(lm)
+    XP1 = X1.reshape(noy, nox, noz)[0, :, 0].astype(np.float64)
+    XP2 = X2.reshape(noy, nox, noz)[:, 0, 0].astype(np.float64)
+    XP3 = X3.reshape(noy, nox, noz)[0, 0, :].astype(np.float64)
+    rnoz = 50 * elz + 1
+    XRG = XP3[0] + np.arange(rnoz) * (XP3[-1] - XP3[0]) / (rnoz - 1)
+    XRG[-1], XRG[0] = XP3[-1], XP3[0]
+    RG3 = np.zeros(rnoz + 1, dtype=np.int32)
+    for j in range(1, rnoz):                     # E->RG[3][j]: first element e with XRG[j+1] <= XP[e+1] and XRG[j] >= XP[e]
+        ok = np.nonzero((XRG[j] <= XP3[1:]) & (XRG[j - 1] >= XP3[:-1]))[0]
+        RG3[j] = ok[0] + 1 if ok.size else 0
+    gp = prob.global_problem()
+    g1, g2, g3 = gp.coordinates(lm)
+    XG1 = np.array([g1.min(), g2.min(), g3.min()], dtype=np.float64) + 1e-6     # the reference keeps the markers 1e-6 inside the box
+    XG2 = np.array([g1.max(), g2.max(), g3.max()], dtype=np.float64) - 1e-6
+    El = np.zeros((ely, elx, elz), dtype=np.uint32)
+    for sl in ((0, slice(None), slice(None)), (-1, slice(None), slice(None)), (slice(None), 0, slice(None)), (slice(None), -1, slice(None)),
+               (slice(None), slice(None), 0), (slice(None), slice(None), -1)):
+        El[sl] |= np.uint32(0x800000)            # SIDEE
+    n = markers_per_ele * elx * ely * elz
+    x = rng.uniform(XP1[0], XP1[-1], n); y = rng.uniform(XP2[0], XP2[-1], n); z = rng.uniform(XP3[0], XP3[-1], n)
+    ex = np.clip(np.searchsorted(XP1, x, side="right") - 1, 0, elx - 1)
+    ey = np.clip(np.searchsorted(XP2, y, side="right") - 1, 0, ely - 1)
+    ez = np.clip(np.searchsorted(XP3, z, side="right") - 1, 0, elz - 1)
+    CElement = (ez + elz * (ex + elx * ey) + 1).astype(np.int32)
+    C12 = (z <= 1.0 - comp_depth).astype(np.int32)
+    return dict(n=n, rnoz=rnoz, XP=(XP1, XP2, XP3), RG3=RG3, XG1=XG1, XG2=XG2, Element=El.reshape(-1), X=(x, y, z), C12=C12, CElement=CElement,
+                nodes=(X1, X2, X3))
+
+
+def run_markers(args):
+    """BASELINE config 5: thermochemical convection, composition=1, markers_per_ele=20, 128x128x64 elements.  One step = the two
+    marker substeps of a timestep (Euler predictor + Runge_Kutta corrector, Composition_adv.c:108,61: velocity at the markers,
+    position update, element lookup, markers changing subdomain over NCCL, nodal composition) in a steady cellular flow."""
+    import torch
+    import torch.distributed as dist
+    from citcomcu_b200 import decomp, inputfile
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import StokesContext, context_from_problem
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; citcomcu_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    mesh, levels, mpe = (128, 128, 64), 5, 20
+    f = 2 ** (levels - 1)
+    nproc = decomp.nproc_for(world, (mesh[0] // f, mesh[1] // f, mesh[2] // f))
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        box = [StokesContext.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    text = inputfile.tdepv_box(*mesh, levels, nproc=nproc, maxstep=1, composition=1, rayleigh_comp=1e6, markers_per_ele=mpe, comp_depth=0.605)
+    prob = CartesianProblem(text, me_loc=decomp.me_loc_of(rank, nproc))
+    ctx = context_from_problem(prob, device=local, unique_id=uid, agglomerate=False)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    M = marker_setup_arrays(prob, np.random.default_rng(1234 + rank), mpe)
+    cap = int(1.3 * M["n"]) + 1024
+    ctx.markers_setup(cap, mpe, M["rnoz"], *M["XP"], M["RG3"], M["XG1"], M["XG2"], M["Element"], Acomp=1.0)
+    ctx.markers_upload(*M["X"], M["C12"], M["CElement"])
+    X1, X2, X3 = M["nodes"]
+    Lx, Lz = float(M["XG2"][0] - M["XG1"][0]), float(M["XG2"][2] - M["XG1"][2])
+    # a steady two-cell flow (divergence free, no flow through the walls), speed ~ 1
+    V1 = (np.sin(np.pi * X1 / Lx * 2) * np.cos(np.pi * X3 / Lz)).astype(np.float32)
+    V2 = np.zeros_like(V1)
+    V3 = (-2.0 * Lz / Lx * np.cos(np.pi * X1 / Lx * 2) * np.sin(np.pi * X3 / Lz)).astype(np.float32)
+    dx = Lx / mesh[0]
+    dt = np.float32(0.5 * dx / max(1e-30, float(np.abs(V3).max()), float(np.abs(V1).max())))       # half an element per substep
+    V_t = [torch.from_numpy(v).pin_memory() for v in (V1, V2, V3)]
+    V_h = [t.numpy() for t in V_t]
+    C_t = torch.empty(prob.nno(prob.levmax), dtype=torch.float32, pin_memory=True)
+    ctx.set_velocity(*V_h)
+    n_total = M["n"] * world
+
+    def step_resident():
+        ctx.Euler(dt); ctx.Runge_Kutta(dt)
+
+    def step_e2e():
+        ctx.set_velocity(*V_h)                     # E->V in
+        ctx.Euler(dt); ctx.Runge_Kutta(dt)
+        ctx.markers_download_C(C_t.numpy())        # nodal composition E->C out (what thermal_buoyancy and the output read)
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(k):
+                fn()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) / 1e3
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return sec
+
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.synchronize()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = ctx.launch_count
+    sec = timed(step_resident, args.steps)
+    launches = ctx.launch_count - l0
+    step_e2e()
+    e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop()
+    # size-independent checks: no marker lost or duplicated, all inside the box, composition in [0, 1]
+    out = ctx.markers_download()
+    cnt = torch.tensor([ctx.markers_count()], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(cnt)
+    inside = bool(all((out["XMC"][d] >= M["XG1"][d] - 1e-12).all() and (out["XMC"][d] <= M["XG2"][d] + 1e-12).all() for d in range(3)))
+    ok = torch.tensor([1 if (inside and float(out["C"].min()) >= -1e-6 and float(out["C"].max()) <= 1 + 1e-6) else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    peak, peak_src = measured_peak_gbs()
+    substeps = 2 * args.steps
+    rate = n_total * substeps / sec
+    gbs = MARKER_BYTES_PER_SUBSTEP * (n_total / world) * substeps / sec / 1e9          # per GPU
+    line = {"metric": "marker_substeps_per_s", "value": rate, "unit": "markers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 5: thermochemical convection, composition=1, markers_per_ele=20, 128x128x64 elements "
+                                   f"({n_total} markers); step = Euler + Runge_Kutta marker substeps of one timestep in a steady two-cell flow",
+                       "mesh": list(mesh), "levels": levels, "nproc": list(nproc), "markers": n_total,
+                       "l2": "marker arrays (1.8 GB at one GPU) larger than L2"},
+            "roofline": {"bound": "hbm", "kernel": "one marker substep (mk_velocity + mk_advance + clamp/split + element assignment + nodal composition)",
+                         "achieved": gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                         "algorithmic_bytes_per_marker_substep": MARKER_BYTES_PER_SUBSTEP, "per": "GPU"},
+            "checks": {"markers_conserved": int(cnt.item()) == n_total, "inside_box_and_C_in_0_1": bool(ok.item())},
+            "gpu_launches": launches * world, "clocks": clk,
+            "e2e": {"value": n_total * substeps / e2e, "unit": "markers/s", "h2d_bytes_per_step": int(sum(v.nbytes for v in V_h)) * world,
+                    "d2h_bytes_per_step": int(C_t.numel() * 4) * world},
+            "cpu_baseline": {"value": None, "unit": "markers/s", "cores": 0, "kind": "reference",
+                             "sample": "not timed for this config (the headline and its CPU baseline are config 3)"}}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.config == 5:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "config 5 has no reference arm; the headline (config 3) has"}))
+            return 0
+        return run_markers(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -467,6 +467,11 @@ class StokesContext:
                                             p(out["C"]), p(out["CE"])))
         return out
 
+    def markers_download_C(self, out):
+        """nodal composition E->C only, into a caller-owned (pinned) float32[nno] array."""
+        assert out.dtype == np.float32 and out.size == self.nno(self.levmax)
+        check(self.lib.ccu_markers_download(self._ctx, None, None, None, None, None, out.ctypes.data_as(C.c_void_p), None))
+
     def Euler(self, timestep):
         check(self.lib.ccu_Euler(self._ctx, C.c_float(timestep)))
 
