@@ -82,7 +82,7 @@ struct ccu_ctx
     bool use_graphs = true;
     // kernel selection by level size (lanes per node), ccu_set_option
     int opt_small_nodes = 600, opt_warp_nodes = 30000, opt_quad_nodes = 500000, opt_lanes_large = 1;
-    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_cluster_nodes = 0, opt_bottom_cluster = 1, opt_coop_nodes = 0, opt_mid_lanes = 4;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
+    int opt_matvec_tab = 4, opt_relax_tab = 2, opt_smem_nodes = 434, opt_matvec_tab_nodes = 10000, opt_bottom_cluster = 1;   // table-driven row kernels on the large levels (ccu_kernels.cuh)
     // column-resident smoother / matvec (ccu_col.cuh) on levels above opt_col_nodes nodes
     int opt_col_nodes = 2000000, opt_relax_col = 0, opt_matvec_col = 1, opt_col_shape = 0, opt_col_wf = 1;
     int opt_full_nodes = 500000, opt_relax_full = 0, opt_matvec_full = 0;   // full-row copy of K on levels above opt_full_nodes nodes
@@ -100,8 +100,6 @@ struct ccu_ctx
     float *T = nullptr;            // [nno] temperature, natural order, finest level
     float *buoy = nullptr;         // [nno]
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
-    unsigned *coop_bar = nullptr;  // grid-barrier counter of the cooperative smoother (ccu_k_relax_coop)
-    int coop_sms = 0, coop_per_sm[3] = { 0, 0, 0 };   // SM count, co-resident CTAs per SM of the T = 32 / 8 / 4 variants
     double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces)
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;

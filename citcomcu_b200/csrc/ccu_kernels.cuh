@@ -812,174 +812,6 @@ __global__ void __launch_bounds__(128) ccu_k_relax_tab(const CcuGeom g, const __
     ccu_relax_update(g, BI, F, x, s, a0, a1, a2);
 }
 
-// ---------------------------------------------------------------- small levels: one thread-block cluster per call
-// Levels of ~1e3..3e4 nodes are pure latency: a colour pass is a few microseconds of work and a smoother call is
-// 8 * cycles such passes, each a kernel launch.  Here ONE launch of a single 8-CTA cluster (8192 threads) runs all
-// sweeps and colour passes of the call, separated by the hardware cluster barrier (~0.2 us, orders global memory and
-// flushes L1D across the cluster's CTAs) instead of kernel boundaries.  T lanes per node, table-driven rows.
-__device__ __forceinline__ void ccu_cluster_sync()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-template <int T>
-__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(1024) ccu_k_relax_cluster(const CcuGeom g, const __grid_constant__ CcuStencil st,
-                                                                                       const float *__restrict__ K,
-                                                                                       const double *__restrict__ BI,
-                                                                                       const double *__restrict__ F, double *x,
-                                                                                       const int cycles, const int zero_first)
-{
-    const size_t NS = (size_t)g.NS;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    if(zero_first)
-    {
-        for(size_t i = gid; i < 3 * NS; i += nthreads) x[i] = 0.0;
-        ccu_cluster_sync();
-    }
-    const int q = gid % T;
-    const int items = ((g.NC * T + 31) / 32) * 32;           // whole warps arrive at the shuffles
-    for(int sw = 0; sw < cycles; sw++)
-        for(int c = 7; c >= 0; c--)
-        {
-            const int *off = st.off[c];
-            for(int it = gid; it < items; it += nthreads)
-            {
-                const int cell = it / T;
-                int i, j, k;
-                const bool valid = cell < g.NC && ccu_decode(g, c, cell, i, j, k);
-                const int s = c * g.NC + cell;
-                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-                if(valid)
-                {
-#pragma unroll
-                    for(int u = 0; u < (27 + T - 1) / T; u++)
-                    {
-                        const int b = q + u * T;
-                        if(b < 27)
-                        {
-                            const bool tr = b >= 14;
-                            const int sm = s + off[b];
-                            const float *Kp = K + (size_t)((tr ? b - 13 : b) * 9) * NS + (tr ? sm : s);
-                            float kk[9];
-#pragma unroll
-                            for(int e = 0; e < 9; e++) kk[e] = __ldg(Kp + (size_t)e * NS);
-                            const double x0 = x[sm], x1 = x[NS + sm], x2 = x[2 * NS + sm];
-                            if(!tr)
-                            {
-                                r0 += (double)kk[0] * x0 + (double)kk[1] * x1 + (double)kk[2] * x2;
-                                r1 += (double)kk[3] * x0 + (double)kk[4] * x1 + (double)kk[5] * x2;
-                                r2 += (double)kk[6] * x0 + (double)kk[7] * x1 + (double)kk[8] * x2;
-                            }
-                            else
-                            {
-                                r0 += (double)kk[0] * x0 + (double)kk[3] * x1 + (double)kk[6] * x2;
-                                r1 += (double)kk[1] * x0 + (double)kk[4] * x1 + (double)kk[7] * x2;
-                                r2 += (double)kk[2] * x0 + (double)kk[5] * x1 + (double)kk[8] * x2;
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for(int o = T / 2; o > 0; o >>= 1)
-                {
-                    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-                    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-                    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-                }
-                if(valid && q == 0) ccu_relax_update(g, BI, F, x, s, r0, r1, r2);
-            }
-            ccu_cluster_sync();
-        }
-}
-
-// ---------------------------------------------------------------- mid levels: one cooperative launch per smoother call
-// Levels of ~1e3 .. 2e5 nodes pay 4-12 us per colour pass as separate launches (a pass is a microsecond or two of
-// L2-resident work; the rest is launch latency, even inside a replayed graph: ~50 ms of a 636 ms step at 256x256x128).
-// Here ONE cooperative launch (all CTAs co-resident: 148 x m) runs every sweep and colour of the call; passes are
-// separated by a grid barrier (one atomic per CTA on a monotonic counter + a spin on it: ~1 us) instead of kernel
-// boundaries.  Neighbour values written by other CTAs are read with ld.global.cg (L2, never a stale L1 line).
-__device__ __forceinline__ void ccu_grid_barrier(unsigned *count, const unsigned target)
-{
-    __syncthreads();
-    if(threadIdx.x == 0)
-    {
-        __threadfence();                                   // this CTA's updates are visible before it arrives
-        atomicAdd(count, 1u);
-        while(*(volatile unsigned *)count < target) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
-template <int T>
-__global__ void __launch_bounds__(256) ccu_k_relax_coop(const CcuGeom g, const __grid_constant__ CcuStencil st, const float *__restrict__ K,
-                                                         const double *__restrict__ BI, const double *__restrict__ F, double *x,
-                                                         const int cycles, unsigned *bar)
-{
-    const size_t NS = (size_t)g.NS;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    const int q = gid % T;
-    const int items = ((g.NC * T + 31) / 32) * 32;           // whole warps arrive at the shuffles
-    unsigned phase = 0;
-    for(int sw = 0; sw < cycles; sw++)
-        for(int c = 7; c >= 0; c--)
-        {
-            const int *off = st.off[c];
-            for(int it = gid; it < items; it += nthreads)
-            {
-                const int cell = it / T;
-                int i, j, k;
-                const bool valid = cell < g.NC && ccu_decode(g, c, cell, i, j, k);
-                const int s = c * g.NC + cell;
-                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-                if(valid)
-                {
-#pragma unroll
-                    for(int u = 0; u < (27 + T - 1) / T; u++)
-                    {
-                        const int b = q + u * T;
-                        if(b < 27)
-                        {
-                            const bool tr = b >= 14;
-                            const int sm = s + off[b];
-                            const float *Kp = K + (size_t)((tr ? b - 13 : b) * 9) * NS + (tr ? sm : s);
-                            float kk[9];
-#pragma unroll
-                            for(int e = 0; e < 9; e++) kk[e] = __ldg(Kp + (size_t)e * NS);
-                            const double x0 = __ldcg(x + sm), x1 = __ldcg(x + NS + sm), x2 = __ldcg(x + 2 * NS + sm);
-                            if(!tr)
-                            {
-                                r0 += (double)kk[0] * x0 + (double)kk[1] * x1 + (double)kk[2] * x2;
-                                r1 += (double)kk[3] * x0 + (double)kk[4] * x1 + (double)kk[5] * x2;
-                                r2 += (double)kk[6] * x0 + (double)kk[7] * x1 + (double)kk[8] * x2;
-                            }
-                            else
-                            {
-                                r0 += (double)kk[0] * x0 + (double)kk[3] * x1 + (double)kk[6] * x2;
-                                r1 += (double)kk[1] * x0 + (double)kk[4] * x1 + (double)kk[7] * x2;
-                                r2 += (double)kk[2] * x0 + (double)kk[5] * x1 + (double)kk[8] * x2;
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for(int o = T / 2; o > 0; o >>= 1)
-                {
-                    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-                    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-                    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-                }
-                if(valid && q < 3)
-                {   // lanes 0..2 of the node's group update one equation each (scalar BI, fp32-rounded correction)
-                    const double rr = q == 0 ? r0 : (q == 1 ? r1 : r2);
-                    const float tq = (float)((F[q * NS + s] - rr) * BI[q * NS + s]);
-                    x[q * NS + s] = __ldcg(x + q * NS + s) + (double)tq;
-                }
-            }
-            phase++;
-            if(!(sw == cycles - 1 && c == 0)) ccu_grid_barrier(bar, phase * gridDim.x);
-        }
-}
-
 // T lanes per node variant of the matvec (coarse and mid levels): thread -> (colour, cell, lane)
 template <int T, int MODE>
 __global__ void __launch_bounds__(256) ccu_k_matvec_lanes(const CcuGeom g, const float *__restrict__ K,

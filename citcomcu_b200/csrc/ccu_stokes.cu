@@ -38,7 +38,6 @@ int ccu_check_lev(ccu_ctx *c, int lev)
 
 static int ensure_smem_tables(ccu_ctx *c, Level &L);
 
-static int coop_init(ccu_ctx *c);
 int ccu_create(const ccu_config *cfg, ccu_ctx **out)
 {
     if(!cfg || !out) FAIL("ccu_create: null argument");
@@ -93,7 +92,6 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_COUNT, c->st));
     { const double one = 1.0; CK(cudaMemcpyAsync(c->scal + S_ONE, &one, sizeof(double), cudaMemcpyHostToDevice, c->st)); }
     CK(cudaMalloc(&c->partial, sizeof(double) * 3 * CCU_DOT_BLOCKS));
-    if(coop_init(c)) return 1;
     SYNC(c);
     *out = c;
     return 0;
@@ -135,7 +133,7 @@ void ccu_destroy(ccu_ctx *c)
         cudaFree(M.sX); cudaFree(M.sXpred); cudaFree(M.sVO); cudaFree(M.sVpred); cudaFree(M.sC12); cudaFree(M.sCElement);
         cudaFree(M.sendbuf); cudaFree(M.recvbuf);
     }
-    cudaFree(c->forceEF); cudaFree(c->coop_bar);
+    cudaFree(c->forceEF);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }
@@ -160,7 +158,6 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_QUAD_NODES: c->opt_quad_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_LANES_LARGE: if(value != 1 && value != 4) FAIL("lanes must be 1 or 4"); c->opt_lanes_large = value; drop_graphs(c); return 0;
     case CCU_OPT_SMEM_NODES: c->opt_smem_nodes = value > 434 ? 434 : value; drop_graphs(c); return 0;
-    case CCU_OPT_CLUSTER_NODES: c->opt_cluster_nodes = value; drop_graphs(c); return 0;
     case CCU_OPT_MATVEC_TAB: c->opt_matvec_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_RELAX_TAB: c->opt_relax_tab = value; drop_graphs(c); return 0;
     case CCU_OPT_COL_NODES: c->opt_col_nodes = value; drop_graphs(c); return col_refresh_all(c);
@@ -172,8 +169,6 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_COL_WF: c->opt_col_wf = value != 0; if(c->coarse) c->coarse->opt_col_wf = c->opt_col_wf; drop_graphs(c); return 0;
     case CCU_OPT_COL_SHAPE: if(value < 0 || value > 2) FAIL("column shape must be 0..2"); c->opt_col_shape = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
-    case CCU_OPT_COOP_NODES: c->opt_coop_nodes = value; if(c->coarse) c->coarse->opt_coop_nodes = value; drop_graphs(c); return 0;
-    case CCU_OPT_MID_LANES: if(value != 4 && value != 8 && value != 16) FAIL("mid lanes must be 4, 8 or 16"); c->opt_mid_lanes = value; if(c->coarse) c->coarse->opt_mid_lanes = value; drop_graphs(c); return 0;
     default: FAIL("set_option: unknown option");
     }
 }
@@ -522,8 +517,6 @@ static void d_matvec(ccu_ctx *c, Level &L, const double *u, double *Au, int stri
     else if(use_col(c, L, c->opt_matvec_col)) launch_col_shape<1, 0>(c, L, 0, nullptr, const_cast<double *>(u), Au, strip);
     else if(T == 0 || T == 32) LAUNCH(c, (ccu_k_matvec_lanes<32, 0>), L.g.NC, 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
     else if(T == 4) LAUNCH(c, (ccu_k_matvec_lanes<4, 0>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
-    else if(c->opt_matvec_tab == 24) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
-    else if(c->opt_matvec_tab == 14) LAUNCH(c, (ccu_k_matvec_tab<0, 4, 1>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab >= 4) LAUNCH(c, (ccu_k_matvec_tab<0, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else if(c->opt_matvec_tab) LAUNCH(c, (ccu_k_matvec_tab<0, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, nullptr, Au, strip);
     else LAUNCH(c, ccu_k_matvec<0>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, nullptr, Au, strip);
@@ -545,8 +538,6 @@ static void d_residual(ccu_ctx *c, Level &L, const double *u, const double *rhs,
     if(use_col(c, L, c->opt_matvec_col)) { launch_col_shape<2, 0>(c, L, 0, rhs, const_cast<double *>(u), out, 1); return; }
     if(T == 0 || T == 32) { LAUNCH(c, (ccu_k_matvec_lanes<32, 1>), L.g.NC, 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
     if(T == 4) { LAUNCH(c, (ccu_k_matvec_lanes<4, 1>), cdiv(L.g.NC, 8), 256, L.g, L.K, L.flags, u, rhs, out, 1); return; }
-    if(c->opt_matvec_tab == 24) { LAUNCH(c, (ccu_k_matvec_tab<1, 4, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
-    if(c->opt_matvec_tab == 14) { LAUNCH(c, (ccu_k_matvec_tab<1, 4, 1>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab >= 4) { LAUNCH(c, (ccu_k_matvec_tab<1, 4>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     if(c->opt_matvec_tab) { LAUNCH(c, (ccu_k_matvec_tab<1, 2>), cdiv(L.g.NC, 32), 256, L.g, ccu_make_stencil(L.g), L.K, L.flags, u, rhs, out, 1); return; }
     LAUNCH(c, ccu_k_matvec<1>, cdiv(L.g.NC, 32), 256, L.g, L.K, L.flags, u, rhs, out, 1);
@@ -603,58 +594,6 @@ static int ensure_smem_tables(ccu_ctx *c, Level &L)
     return 0;
 }
 
-// cooperative smoother launch (ccu_k_relax_coop): T lanes per node and m CTAs per SM sized to the level; returns
-// non-zero (and launches nothing) when the device cannot hold the grid
-template <int T>
-static int coop_occupancy()
-{
-    int per_sm = 0;
-    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccu_k_relax_coop<T>, 256, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return per_sm;
-}
-// queried once at context creation (nothing here may run inside a graph capture)
-static int coop_init(ccu_ctx *c)
-{
-    int dev = 0, coop = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    CK(cudaDeviceGetAttribute(&c->coop_sms, cudaDevAttrMultiProcessorCount, dev));
-    c->coop_per_sm[0] = coop ? coop_occupancy<32>() : 0;
-    c->coop_per_sm[1] = coop ? coop_occupancy<8>() : 0;
-    c->coop_per_sm[2] = coop ? coop_occupancy<4>() : 0;
-    CK(cudaMalloc(&c->coop_bar, sizeof(unsigned)));
-    return 0;
-}
-template <int T>
-static int launch_relax_coop_T(ccu_ctx *c, Level &L, double *x, const double *F, int cycles, int per_sm)
-{
-    if(per_sm <= 0 || !c->coop_bar) return 1;
-    const int sms = c->coop_sms;
-    const size_t items = (size_t)L.g.NC * T;
-    int m = (int)((items + (size_t)sms * 256 - 1) / ((size_t)sms * 256));
-    if(m < 1) m = 1;
-    if(m > 4) m = 4;
-    if(m > per_sm) m = per_sm;
-    cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned), c->st);
-    CcuGeom g = L.g;
-    CcuStencil st = ccu_make_stencil(L.g);
-    const float *K = L.K; const double *BI = L.BI;
-    unsigned *bar = c->coop_bar;
-    void *args[] = { &g, &st, &K, &BI, &F, &x, &cycles, &bar };
-    if(cudaLaunchCooperativeKernel((const void *)ccu_k_relax_coop<T>, dim3(sms * m), dim3(256), args, 0, c->st) != cudaSuccess)
-    {
-        cudaGetLastError();
-        return 1;
-    }
-    c->launches++;
-    return 0;
-}
-static int launch_relax_coop(ccu_ctx *c, Level &L, double *x, const double *F, int cycles)
-{
-    if(L.g.nno <= 4000) return launch_relax_coop_T<32>(c, L, x, F, cycles, c->coop_per_sm[0]);
-    if(L.g.nno <= 40000) return launch_relax_coop_T<8>(c, L, x, F, cycles, c->coop_per_sm[1]);
-    return launch_relax_coop_T<4>(c, L, x, F, cycles, c->coop_per_sm[2]);
-}
 
 template <int T>
 static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F, const unsigned char *bits)
@@ -732,17 +671,6 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         LAUNCH(c, ccu_k_relax_small, 1, 1024, L.g, L.K, L.BI, F, x, cycles, 0);
         return;
     }
-    if(!c->multi() && c->opt_coop_nodes > 0 && L.g.nno <= c->opt_coop_nodes)
-    {   // mid level: every sweep and colour of the call in ONE cooperative launch, grid barriers between the passes
-        if(launch_relax_coop(c, L, x, F, cycles) == 0) return;
-    }
-    if(!c->multi() && L.g.nno <= c->opt_cluster_nodes)
-    {   // small level: the whole call in one cluster launch (warp per node below ~4000 nodes, else four lanes per node)
-        const CcuStencil st = ccu_make_stencil(L.g);
-        if(L.g.nno <= 4000) LAUNCH(c, ccu_k_relax_cluster<32>, 8, 1024, L.g, st, L.K, L.BI, F, x, cycles, 0);
-        else LAUNCH(c, ccu_k_relax_cluster<4>, 8, 1024, L.g, st, L.K, L.BI, F, x, cycles, 0);
-        return;
-    }
     const unsigned grid = cdiv(L.g.NC, 128);
     const unsigned char *bits = c->multi() ? c->comm->halo[&L - c->L].bits : nullptr;
     for(int s = 0; s < cycles; s++)
@@ -750,10 +678,8 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
         if(bits) relax_faces(c, L, x, F);
         if(T == 32) { launch_relax_lanes<32>(c, L, x, F, bits); continue; }
         if(T == 4)
-        {   // mid levels: 4, 8 or 16 lanes per node (CCU_OPT_MID_LANES)
-            if(c->opt_mid_lanes == 16) launch_relax_lanes<16>(c, L, x, F, bits);
-            else if(c->opt_mid_lanes == 8) launch_relax_lanes<8>(c, L, x, F, bits);
-            else launch_relax_lanes<4>(c, L, x, F, bits);
+        {   // mid levels: four lanes per node
+            launch_relax_lanes<4>(c, L, x, F, bits);
             continue;
         }
         if(c->opt_relax_full && L.have_KT)
@@ -767,9 +693,7 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
             const CcuStencil st = ccu_make_stencil(L.g);
             for(int col = 7; col >= 0; col--)
             {
-                if(c->opt_relax_tab == 22) LAUNCH(c, (ccu_k_relax_tab<2, 2>), grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
-                else if(c->opt_relax_tab == 12) LAUNCH(c, (ccu_k_relax_tab<2, 1>), grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
-                else if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
                 else if(c->opt_relax_tab >= 4) LAUNCH(c, ccu_k_relax_tab<4>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
                 else LAUNCH(c, ccu_k_relax_tab<2>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
             }

@@ -51,7 +51,6 @@ int ccu_synchronize(ccu_ctx *ctx);
 /* MATVEC_TAB / RELAX_TAB: table-driven (compact code) row kernels on levels above QUAD_NODES */
 enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_OPT_QUAD_NODES = 3, CCU_OPT_LANES_LARGE = 4,
        CCU_OPT_MATVEC_TAB = 5, CCU_OPT_RELAX_TAB = 6,
-       CCU_OPT_CLUSTER_NODES = 8 /* single-subdomain levels with nno <= this run a whole smoother call in one 8-CTA cluster launch */,
        CCU_OPT_SMEM_NODES = 7 /* levels with nno <= this (max 434) run all sweeps out of one SM's shared memory */,
        /* column-resident kernels (csrc/ccu_col.cuh) on levels with nno > COL_NODES (default 2000000: measured slower than the colour passes on the 1.08e6-node level): RELAX_COL / MATVEC_COL
         * (default 1) switch them on or off; COL_SHAPE 0 = columns of 6 (y) x 8 (x) nodes, two CTAs per SM, 1 = 12 x 8, one CTA
@@ -68,10 +67,7 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
         * bytes but only 3 % faster (the pass stops being DRAM-bound), the matvec slower -- kept as an option, see DESIGN.md */
        CCU_OPT_FULL_NODES = 18, CCU_OPT_RELAX_FULL = 19, CCU_OPT_MATVEC_FULL = 20,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
-        * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */,
-       CCU_OPT_COOP_NODES = 16 /* single-subdomain levels with SMALL_NODES < nno <= this (default 0 = off: measured no faster than the graph-replayed per-pass launches) run each smoother call as one
-        * cooperative launch with grid barriers between the colour passes (ccu_k_relax_coop); 0 = per-pass launches */,
-       CCU_OPT_MID_LANES = 17 /* lanes per node (4, 8 or 16) of the smoother on levels between WARP_NODES and QUAD_NODES */ };
+        * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
 /* current value of an option; for the column options, *value is what is in effect on level `lev` (0 when the level is too
  * small for the column kernels), so that a benchmark can name the kernel it timed */

@@ -166,19 +166,17 @@ def test_empty_rhs_is_a_noop(case):
 
 
 @pytest.mark.parametrize("opts", [
-    dict(coop_nodes=0, small_nodes=0, warp_nodes=0, quad_nodes=0, cluster_nodes=0, lanes_large=1, relax_tab=0, matvec_tab=0),   # unrolled rows, one thread per node
-    dict(coop_nodes=0, small_nodes=0, warp_nodes=0, quad_nodes=0, cluster_nodes=0),                                              # table-driven rows
-    dict(coop_nodes=0, small_nodes=0, warp_nodes=0, quad_nodes=10**9, cluster_nodes=0, matvec_tab=0),                            # four lanes per node
-    dict(coop_nodes=0, small_nodes=0, warp_nodes=10**9, cluster_nodes=0, matvec_tab=0),                                          # a warp per node
-    dict(coop_nodes=0, small_nodes=0, cluster_nodes=10**9),                                                                      # one cluster launch per smoother call
-    dict(small_nodes=0, coop_nodes=10**9),                                                                                       # one cooperative launch per smoother call, grid barriers
-    dict(coop_nodes=0, small_nodes=10**9, smem_nodes=0),                                                                         # single-CTA fused sweeps
+    dict(small_nodes=0, warp_nodes=0, quad_nodes=0, lanes_large=1, relax_tab=0, matvec_tab=0),   # unrolled rows, one thread per node
+    dict(small_nodes=0, warp_nodes=0, quad_nodes=0),                                              # table-driven rows
+    dict(small_nodes=0, warp_nodes=0, quad_nodes=10**9, matvec_tab=0),                            # four lanes per node
+    dict(small_nodes=0, warp_nodes=10**9, matvec_tab=0),                                          # a warp per node
+    dict(small_nodes=10**9, smem_nodes=0),                                                                         # single-CTA fused sweeps
     dict(small_nodes=10**9),                                                                                                     # 8-CTA cluster, fp64 rows in distributed shared memory
     dict(small_nodes=10**9, bottom_cluster=0),                                                                                   # one SM, shared-memory resident half-matrix
     dict(graphs=0),
     dict(relax_col=0, matvec_col=0),
     dict(full_nodes=0, relax_full=1, matvec_full=1),                                                                             # full rows (upper-neighbour blocks copied to the node's own slot)
-    dict(full_nodes=0, relax_full=1, matvec_full=1, small_nodes=0, warp_nodes=0, quad_nodes=0, cluster_nodes=0, coop_nodes=0),
+    dict(full_nodes=0, relax_full=1, matvec_full=1, small_nodes=0, warp_nodes=0, quad_nodes=0),
     dict()])                                                                                                                     # defaults
 def test_kernel_variants_agree(case, opts):
     """Every lanes-per-node variant of the smoother / matvec and the CUDA-graph replay give the same answers."""
