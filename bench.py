@@ -229,7 +229,8 @@ def workload_config(args, mesh, nproc=(1, 1, 1)):
                         f"free slip, {args.levels} multigrid levels; step = general_stokes_solver from a zero guess "
                         "(viscosity + stiffness rebuild + forces + Uzawa/FMG solve to accuracy 1e-3)",
             "mesh": list(mesh), "levels": args.levels, "nproc": list(nproc),
-            "partition": "one subdomain per GPU, the reference's nprocx x nprocy x nprocz block decomposition; halo sums + allreduce over NCCL",
+            "partition": "one subdomain per GPU, the reference's nprocx x nprocy x nprocz block decomposition; halo sums through peer memory "
+                         "(CUDA IPC over NVLink; NCCL send/recv if unavailable), allreduce over NCCL",
             "l2": "inputs larger than L2 (finest-level stiffness alone is > 4 GB)"}
 
 
@@ -383,6 +384,7 @@ def run_ours(args):
     build_ms, _ = ctx.profile_read("build")
     coarse_ms, coarse_n = ctx.profile_read("coarse")
     transfer_ms, _ = ctx.profile_read("transfer_fine")
+    faces_ms, faces_n = ctx.profile_read("faces_fine")
     level_ms = {lev: ctx.profile_read(lev) for lev in range(prob.levmin, prob.levmax + 1)} if args.no_graphs else None
     ctx.profile_enable(False)
     clk = clocks.stop()
@@ -429,8 +431,10 @@ def run_ours(args):
             "operator_rebuild_ms_per_step": build_ms / args.steps,
             "step_breakdown_ms": {"relax_fine": relax_ms / args.steps, "matvec_fine": mv_ms / args.steps, "build": build_ms / args.steps,
                                   "coarse_levels": coarse_ms / args.steps, "transfer_fine": transfer_ms / args.steps,
+                                  "faces_fine_within_relax": faces_ms / args.steps,
                                   "other_fine_vector_ops_and_sync": (prof_total_ms - relax_ms - mv_ms - build_ms - coarse_ms - transfer_ms) / args.steps,
                                   "profiled_pass_ms_per_step": prof_total_ms / args.steps},
+            "halo_exchange": ("peer-memory" if (world > 1 and ctx.get_option("p2p_halo", lm)) else ("nccl send/recv" if world > 1 else "none")),
             "uzawa_iterations": its, "gpu_launches": launches * world, "clocks": clk, "setup_s": setup_s,
             "e2e": {"value": e2e_s / args.steps, "unit": "s", "h2d_bytes_per_step": int(T_h.nbytes + b_h.nbytes) * world,
                     "d2h_bytes_per_step": int(U_h.nbytes + P_h.nbytes) * world}}

@@ -209,6 +209,157 @@ __global__ void ccu_k_scatter_scal(const double *__restrict__ stage, double *o0,
     if(o2) *o2 = stage[2];
 }
 
+// ------------------------------------------------------------------ peer-memory exchange (NVLink / NVSwitch, CUDA IPC)
+__global__ void ccu_k_p2p_bump(unsigned *seq) { *seq += 1u; }
+// grid (segments, slices): slice `y` of the packed values for neighbour segment `x` goes straight into that neighbour's
+// landing buffer (parity = sequence number & 1); the last slice of a segment to finish raises the neighbour's flag.
+__global__ void __launch_bounds__(256) ccu_k_p2p_push(const int4 *__restrict__ seg, const int bytes_per_node, const char *__restrict__ sendbuf,
+                                                      char *const *__restrict__ peer_land, unsigned *const *__restrict__ peer_flags,
+                                                      const unsigned *__restrict__ seq, unsigned *done, const int myrank, const size_t land_half)
+{
+    const int4 sg = seg[blockIdx.x];
+    const unsigned seqv = *seq;
+    const char *srcb = sendbuf + (size_t)sg.y * bytes_per_node;
+    char *dstb = peer_land[sg.x] + (size_t)(seqv & 1u) * land_half + (size_t)sg.w * bytes_per_node;
+    const size_t bytes = (size_t)sg.z * bytes_per_node;
+    if((((size_t)srcb | (size_t)dstb | bytes) & 15) == 0)
+    {   // 128-bit stores over NVLink
+        const uint4 *src = (const uint4 *)srcb; uint4 *dst = (uint4 *)dstb;
+        for(size_t w = (size_t)blockIdx.y * blockDim.x + threadIdx.x; w < bytes / 16; w += (size_t)gridDim.y * blockDim.x) dst[w] = src[w];
+    }
+    else
+    {
+        const unsigned *src = (const unsigned *)srcb; unsigned *dst = (unsigned *)dstb;
+        for(size_t w = (size_t)blockIdx.y * blockDim.x + threadIdx.x; w < bytes / 4; w += (size_t)gridDim.y * blockDim.x) dst[w] = src[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        if(atomicAdd(done + blockIdx.x, 1u) + 1u == gridDim.y)
+        {
+            done[blockIdx.x] = 0u;
+            __threadfence_system();
+            *(volatile unsigned *)(peer_flags[sg.x] + myrank) = seqv;
+        }
+    }
+}
+// every block waits until all neighbours of this level have delivered exchange `seq`, then moves its slice of the landing
+// buffer into recvbuf (where the unpack / face kernels read)
+__global__ void __launch_bounds__(256) ccu_k_p2p_wait(const int nseg, const int4 *__restrict__ seg, const int bytes_per_node, const int n_send,
+                                                      const char *__restrict__ land, const size_t land_half, const unsigned *flags,
+                                                      const unsigned *__restrict__ seq, char *recvbuf, unsigned *err)
+{
+    const unsigned seqv = *seq;
+    if(threadIdx.x < nseg)
+    {
+        const volatile unsigned *f = flags + seg[threadIdx.x].x;
+        unsigned spins = 0;
+        while((int)(*f - seqv) < 0)
+        {
+            __nanosleep(32);
+            if(++spins > (1u << 25)) { *err = 1u; break; }        // never in a healthy run: do not hang the device
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const unsigned *src = (const unsigned *)(land + (size_t)(seqv & 1u) * land_half);
+    unsigned *dst = (unsigned *)recvbuf;
+    const size_t words = (size_t)n_send * bytes_per_node / 4;
+    for(size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) dst[w] = __ldcg(src + w);
+}
+
+// Exports this rank's landing buffers and flags through CUDA IPC, gathers everybody's handles over NCCL, maps the
+// neighbours' and builds the per-level segment tables (the neighbour's receive offset for my data comes from building ITS
+// duplicated-node tables here: they are pure index arithmetic).  Any failure leaves p2p = false (NCCL send/recv is used).
+static int ccu_p2p_setup(ccu_ctx *c, size_t max_send)
+{
+    CcuComm *m = c->comm;
+    const int nranks = m->nranks;
+    m->land_half = (sizeof(double) * 3 * std::max<size_t>(max_send, 1) + 255) & ~(size_t)255;
+    CK(cudaMalloc(&m->land, 2 * m->land_half));
+    CK(cudaMalloc(&m->flags, sizeof(unsigned) * nranks));
+    CK(cudaMalloc(&m->seq, sizeof(unsigned)));
+    CK(cudaMalloc(&m->done, sizeof(unsigned) * 32));
+    CK(cudaMalloc(&m->p2p_err, sizeof(unsigned)));
+    CK(cudaMemset(m->land, 0, 2 * m->land_half));
+    CK(cudaMemset(m->flags, 0, sizeof(unsigned) * nranks));
+    CK(cudaMemset(m->seq, 0, sizeof(unsigned)));
+    CK(cudaMemset(m->done, 0, sizeof(unsigned) * 32));
+    CK(cudaMemset(m->p2p_err, 0, sizeof(unsigned)));
+    struct Handles { cudaIpcMemHandle_t land, flags; int ok; int pad[3]; };
+    Handles mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = cudaIpcGetMemHandle(&mine.land, m->land) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, m->flags) == cudaSuccess;
+    cudaGetLastError();
+    Handles *dev = nullptr;
+    CK(cudaMalloc(&dev, sizeof(Handles) * (size_t)(nranks + 1)));
+    CK(cudaMemcpy(dev, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NK(g_nccl.AllGather(dev, dev + 1, sizeof(Handles), ncclChar, (ncclComm_t)m->nccl, c->st));
+    std::vector<Handles> all((size_t)nranks);
+    CK(cudaMemcpyAsync(all.data(), dev + 1, sizeof(Handles) * (size_t)nranks, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    cudaFree(dev);
+    bool ok = true;
+    for(int r = 0; r < nranks; r++) ok = ok && all[(size_t)r].ok;
+    std::vector<char *> pl((size_t)nranks, nullptr);
+    std::vector<unsigned *> pf((size_t)nranks, nullptr);
+    std::vector<char> is_nb((size_t)nranks, 0);
+    for(int lev = c->cfg.levmin; lev <= c->cfg.levmax; lev++)
+        for(int r : m->halo[lev].nb_rank) is_nb[(size_t)r] = 1;
+    for(int r = 0; r < nranks && ok; r++)
+    {
+        if(!is_nb[(size_t)r] || r == m->rank) continue;
+        void *a = nullptr, *b = nullptr;
+        if(cudaIpcOpenMemHandle(&a, all[(size_t)r].land, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+           cudaIpcOpenMemHandle(&b, all[(size_t)r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+        m->ipc_open.push_back(a); m->ipc_open.push_back(b);
+        pl[(size_t)r] = (char *)a; pf[(size_t)r] = (unsigned *)b;
+    }
+    // everybody must agree (a rank that falls back to NCCL while its neighbour pushes would wait forever)
+    {
+        double *flag = m->dotstage;
+        const double v = ok ? 0.0 : 1.0;
+        CK(cudaMemcpy(flag, &v, sizeof v, cudaMemcpyHostToDevice));
+        NK(g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclMax, (ncclComm_t)m->nccl, c->st));
+        double w = 0.0;
+        CK(cudaMemcpyAsync(&w, flag, sizeof w, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        ok = (w == 0.0);
+    }
+    if(!ok) { m->p2p = false; return 0; }
+    CK(cudaMalloc(&m->peer_land, sizeof(char *) * (size_t)nranks));
+    CK(cudaMalloc(&m->peer_flags, sizeof(unsigned *) * (size_t)nranks));
+    CK(cudaMemcpy(m->peer_land, pl.data(), sizeof(char *) * (size_t)nranks, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m->peer_flags, pf.data(), sizeof(unsigned *) * (size_t)nranks, cudaMemcpyHostToDevice));
+    for(int lev = c->cfg.levmin; lev <= c->cfg.levmax; lev++)
+    {
+        Level &L = c->L[lev];
+        CcuHalo &H = m->halo[lev];
+        std::vector<int4> seg(H.nb_rank.size());
+        for(size_t q = 0; q < H.nb_rank.size(); q++)
+        {
+            const int r = H.nb_rank[q];
+            const int me_r[3] = { (r / m->nproc[2]) % m->nproc[0], r / (m->nproc[2] * m->nproc[0]), r % m->nproc[2] };
+            CcuHaloHost hr;
+            ccu_build_halo_host(m->nproc, me_r, L.g.nox, L.g.noy, L.g.noz, hr);
+            int peer_off = -1;
+            for(size_t t = 0; t < hr.nb_rank.size(); t++)
+                if(hr.nb_rank[t] == m->rank) { peer_off = hr.nb_off[t]; if(hr.nb_cnt[t] != H.nb_cnt[q]) peer_off = -1; }
+            if(peer_off < 0) FAIL("peer-memory exchange: inconsistent duplicated-node tables between neighbours");
+            seg[q] = make_int4(r, H.nb_off[q], H.nb_cnt[q], peer_off);
+        }
+        if(seg.size() > 32) FAIL("peer-memory exchange: more than 32 neighbour segments");
+        CK(cudaMalloc(&H.p2p_seg, sizeof(int4) * std::max<size_t>(seg.size(), 1)));
+        if(!seg.empty()) CK(cudaMemcpy(H.p2p_seg, seg.data(), sizeof(int4) * seg.size(), cudaMemcpyHostToDevice));
+    }
+    m->p2p = true;
+    // nobody may push into a landing buffer before its owner has zeroed the flags: one barrier
+    NK(g_nccl.AllReduce(m->dotstage, m->dotstage, 1, ncclDouble, ncclMax, (ncclComm_t)m->nccl, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
 // ------------------------------------------------------------------ communicator
 int ccu_comm_init(ccu_ctx *c, int nprocx, int nprocy, int nprocz, int me_x, int me_y, int me_z, const char *unique_id128)
 {
@@ -278,6 +429,7 @@ int ccu_comm_init(ccu_ctx *c, int nprocx, int nprocy, int nprocz, int me_x, int 
     CK(cudaMalloc(&m->recvbuf, sizeof(double) * 3 * std::max<size_t>(max_send, 1)));
     CK(cudaMalloc(&m->dotstage, sizeof(double) * 4));
     c->comm = m;
+    if(nranks > 1 && ccu_p2p_setup(c, max_send)) return 1;
     ccu_drop_graphs(c);
     return ccu_col_refresh_all(c);      // the column chunks carry BI = 0 on the duplicated nodes (ccu_col.cuh)
 }
@@ -291,6 +443,9 @@ void ccu_comm_destroy(ccu_ctx *c)
         cudaFree(H.sh_s); cudaFree(H.sh_n); cudaFree(H.sh_ptr); cudaFree(H.sh_src); cudaFree(H.send_s); cudaFree(H.send_n); cudaFree(H.send_t);
         cudaFree(H.bits); cudaFree(H.face);
     }
+    for(void *p : m->ipc_open) cudaIpcCloseMemHandle(p);
+    for(auto &H : m->halo) cudaFree(H.p2p_seg);
+    cudaFree(m->land); cudaFree(m->flags); cudaFree(m->seq); cudaFree(m->done); cudaFree(m->p2p_err); cudaFree(m->peer_land); cudaFree(m->peer_flags);
     cudaFree(m->sendbuf); cudaFree(m->recvbuf); cudaFree(m->dotstage); cudaFree(m->mk_counts);
     if(m->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)m->nccl);
     delete m;
@@ -302,6 +457,17 @@ template <class T>
 static int sendrecv(ccu_ctx *c, const CcuHalo &H, int per_node)
 {
     CcuComm *m = c->comm;
+    if(m->p2p && m->opt_p2p)
+    {   // peer-memory exchange: no NCCL call, no host involvement, a few microseconds over NVLink
+        const int nseg = (int)H.nb_rank.size(), bpn = (int)sizeof(T) * per_node;
+        LAUNCH(c, ccu_k_p2p_bump, 1, 1, m->seq);
+        const unsigned slices = (unsigned)std::min<size_t>(32, std::max<size_t>(1, (size_t)H.n_send * bpn / nseg / 16384));
+        LAUNCH(c, ccu_k_p2p_push, dim3((unsigned)nseg, slices), 256, (const int4 *)H.p2p_seg, bpn, (const char *)m->sendbuf, (char *const *)m->peer_land,
+               (unsigned *const *)m->peer_flags, (const unsigned *)m->seq, m->done, m->rank, m->land_half);
+        LAUNCH(c, ccu_k_p2p_wait, std::min<unsigned>(64, std::max<unsigned>(1, (unsigned)((size_t)H.n_send * bpn / 16384))), 256, nseg, (const int4 *)H.p2p_seg, bpn, H.n_send, (const char *)m->land, m->land_half, (const unsigned *)m->flags,
+               (const unsigned *)m->seq, (char *)m->recvbuf, m->p2p_err);
+        return 0;
+    }
     const ncclDataType_t dt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
     NK(g_nccl.GroupStart());
     for(size_t q = 0; q < H.nb_rank.size(); q++)

@@ -59,6 +59,7 @@ struct CcuHalo
     int *send_s = nullptr, *send_n = nullptr, *send_t = nullptr;                     // per packed node: storage / natural / compact index
     unsigned char *bits = nullptr;   // [NS] bit0 = owned for dot products, bit1 = duplicated (OFFSIDE)
     double *face = nullptr;          // [3][n_shared] partial rows of the duplicated nodes (smoother)
+    int4 *p2p_seg = nullptr;         // [segments] {neighbour rank, my send/recv offset, node count, the neighbour's offset for my data} (peer-memory exchange)
 };
 struct CcuComm
 {
@@ -66,6 +67,20 @@ struct CcuComm
     void *nccl = nullptr;            // ncclComm_t
     CcuHalo halo[CCU_MAX_LEVELS];
     void *sendbuf = nullptr, *recvbuf = nullptr;
+    // peer-memory halo exchange over NVLink (ccu_comm.cu): every rank exports two landing buffers and a flag word per sender
+    // through CUDA IPC; a push kernel stores the packed faces straight into the neighbours' landing buffers and raises their
+    // flags, a wait kernel on the receiving side spins on its flags and moves the data into recvbuf.  p2p = false: NCCL send/recv.
+    bool p2p = false;
+    int opt_p2p = 1;
+    size_t land_half = 0;            // bytes of one landing buffer
+    char *land = nullptr;            // [2][land_half] own landing buffers (parity of the exchange sequence number)
+    unsigned *flags = nullptr;       // [nranks] sequence number of the last exchange rank r has delivered
+    unsigned *seq = nullptr;         // device: exchange sequence number (bumped by a kernel: graph replay safe)
+    unsigned *done = nullptr;        // [32] blocks finished per segment (push kernel)
+    unsigned *p2p_err = nullptr;     // set when a wait gives up
+    char **peer_land = nullptr;      // device [nranks]: the ranks' landing buffers as mapped here (null: not a neighbour)
+    unsigned **peer_flags = nullptr; // device [nranks]
+    std::vector<void *> ipc_open;    // mapped peer allocations (closed at destroy)
     double *dotstage = nullptr;
     int *mk_counts = nullptr;        // [27] own + [nranks][27] gathered per-direction counts of migrating markers
     long long gneq = 0, gnpno = 0;   // global equation / pressure counts (E->mesh.neq, E->mesh.npno)

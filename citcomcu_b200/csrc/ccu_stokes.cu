@@ -166,6 +166,7 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_FULL_NODES: c->opt_full_nodes = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_RELAX_FULL: c->opt_relax_full = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_MATVEC_FULL: c->opt_matvec_full = value; drop_graphs(c); return col_refresh_all(c);
+    case CCU_OPT_P2P_HALO: if(c->comm) c->comm->opt_p2p = value != 0; drop_graphs(c); return 0;
     case CCU_OPT_COL_WF: c->opt_col_wf = value != 0; if(c->coarse) c->coarse->opt_col_wf = c->opt_col_wf; drop_graphs(c); return 0;
     case CCU_OPT_COL_SHAPE: if(value < 0 || value > 2) FAIL("column shape must be 0..2"); c->opt_col_shape = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
@@ -185,6 +186,7 @@ int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
     case CCU_OPT_FULL_NODES: *value = c->opt_full_nodes; return 0;
     case CCU_OPT_RELAX_FULL: *value = c->L[lev].have_KT && c->opt_relax_full; return 0;
     case CCU_OPT_MATVEC_FULL: *value = c->L[lev].have_KT && c->opt_matvec_full; return 0;
+    case CCU_OPT_P2P_HALO: *value = c->comm && c->comm->p2p && c->comm->opt_p2p; return 0;
     case CCU_OPT_COL_WF: *value = c->opt_col_wf; return 0;
     case CCU_OPT_COL_SHAPE: *value = c->L[lev].col_shape; return 0;
     case CCU_OPT_COL_NODES: *value = c->opt_col_nodes; return 0;
@@ -193,7 +195,18 @@ int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
     default: FAIL("get_option: option not readable");
     }
 }
-int ccu_synchronize(ccu_ctx *c) { if(!c) FAIL("null context"); SYNC(c); return 0; }
+int ccu_synchronize(ccu_ctx *c)
+{
+    if(!c) FAIL("null context");
+    SYNC(c);
+    if(c->comm && c->comm->p2p)
+    {
+        unsigned e = 0;
+        CK(cudaMemcpy(&e, c->comm->p2p_err, sizeof e, cudaMemcpyDeviceToHost));
+        if(e) FAIL("peer-memory halo exchange: a wait for a neighbour's data gave up (a rank stopped, or the ranks ran different exchange sequences)");
+    }
+    return 0;
+}
 long long ccu_launch_count(ccu_ctx *c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------ replicated coarse levels
@@ -616,6 +629,7 @@ static void relax_faces(ccu_ctx *c, Level &L, double *x, const double *F)
     const int lev = (int)(&L - c->L);
     const CcuHalo &H = c->comm->halo[lev];
     if(H.n_shared == 0) return;
+    CcuProfScope pf(c, CCU_PROF_FACES_FINE, lev == c->cfg.levmax);
     LAUNCH(c, ccu_k_face_rows<0>, cdiv((size_t)H.n_shared * 32, 128), 128, L.g, L.K, x, H.n_shared, H.sh_s, H.face);
     ccu_halo_sum_face(c, lev);
     LAUNCH(c, ccu_k_face_update, cdiv(H.n_shared, 128), 128, L.g, H.n_shared, H.sh_s, H.sh_ptr, H.sh_src, H.face,

@@ -66,6 +66,8 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
         * every coefficient of a row once per pass instead of gathering each stored block twice.  Measured on B200 (r02): 1.27x fewer DRAM
         * bytes but only 3 % faster (the pass stops being DRAM-bound), the matvec slower -- kept as an option, see DESIGN.md */
        CCU_OPT_FULL_NODES = 18, CCU_OPT_RELAX_FULL = 19, CCU_OPT_MATVEC_FULL = 20,
+       CCU_OPT_P2P_HALO = 21 /* subdomain-per-GPU runs: 1 (default) = halo sums through peer memory (CUDA IPC landing buffers over NVLink: a push kernel,
+        * a flag per sender, a wait kernel; no NCCL call per exchange), 0 = grouped ncclSend/ncclRecv.  Set it identically on all ranks. */,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);
@@ -279,7 +281,9 @@ int ccu_marker_routes(const int nproc[3], const int me[3], const int *all_counts
  * operator rebuild, everything below the finest level (units = graph segments), finest-level transfers (project / interp) */
 enum { CCU_PROF_RELAX_FINE = 0, CCU_PROF_MATVEC_FINE = 1, CCU_PROF_BUILD = 2, CCU_PROF_COARSE = 3, CCU_PROF_TRANSFER_FINE = 4,
        CCU_PROF_LEVEL0 = 5 /* + lev: smoother + matvec + transfers of multigrid level lev; only recorded with CCU_OPT_GRAPHS = 0 */,
-       CCU_PROF_COUNT = 5 + CCU_MAX_LEVELS };
+       CCU_PROF_FACES_FINE = 5 + CCU_MAX_LEVELS /* subdomain-per-GPU runs: the duplicated-node part of the finest-level sweeps (partial rows,
+        * exchange, Jacobi update), a subset of RELAX_FINE */,
+       CCU_PROF_COUNT = 6 + CCU_MAX_LEVELS };
 int ccu_profile_enable(ccu_ctx *ctx, int on);
 /* synchronises; total milliseconds and units (see above) recorded for class `cls` since the last reset */
 int ccu_profile_read(ccu_ctx *ctx, int cls, double *ms_total, long long *launches);
