@@ -807,6 +807,8 @@ __global__ void ek_phase_transT(const CcuGeom g, const float *__restrict__ XX, c
         }
     transT[threadIdx.x] = (float)temp1;
 }
+__global__ void ek_transT_to_tab(const float *__restrict__ transT, double *slot) { if(threadIdx.x < 2) slot[threadIdx.x] = (double)transT[threadIdx.x]; }
+__global__ void ek_transT_from_tab(const double *__restrict__ slot, float *transT) { if(threadIdx.x < 2) transT[threadIdx.x] = (float)slot[threadIdx.x]; }
 __global__ void __launch_bounds__(256) ek_phase_functions(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ T,
                                                           const CcuPhase ph, const float *__restrict__ transT, float *Fas670, float *Fas410)
 {
@@ -1656,12 +1658,22 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
     if(!E.phase_on) FAIL("phase_change: ccu_set_phase_params first");
-    if(c->multi() && c->comm->nproc[2] > 1) FAIL("phase_change: the transition depth may lie in another z subdomain (sum_across_depth): not implemented");
     if(update_transT)
     {
         LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->T, E.layer);
         if(layer_allreduce(c)) return 1;
         LAUNCH(c, ek_phase_transT, 1, 32, L.g, (const float *)L.XX, (const double *)E.layer, E.ph.zlm, E.ph.z410, E.transT);
+        if(c->multi() && c->comm->nproc[2] > 1)
+        {   // sum_across_depth (Global_operations.c:763, Phase_change.c:103,116): the phase depth lies in ONE z subdomain of a
+            // vertical column of ranks (the others found 0): sum over the ranks with this rank's (x, y) through one allreduce table
+            const CcuComm *m = c->comm;
+            const int slots = 2 * m->nproc[0] * m->nproc[1], mine = 2 * (m->me[0] + m->nproc[0] * m->me[1]);
+            if(!E.transT_tab) CK(cudaMalloc(&E.transT_tab, sizeof(double) * slots));
+            CK(cudaMemsetAsync(E.transT_tab, 0, sizeof(double) * slots, c->st));
+            LAUNCH(c, ek_transT_to_tab, 1, 32, (const float *)E.transT, E.transT_tab + mine);
+            if(ccu_allreduce_buffer(c, E.transT_tab, slots, 0)) return 1;
+            LAUNCH(c, ek_transT_from_tab, 1, 32, (const double *)(E.transT_tab + mine), E.transT);
+        }
     }
     CcuPhase ph; ph.zlm = E.ph.zlm; ph.z410 = E.ph.z410; ph.Ra670 = E.ph.Ra670; ph.clap670 = E.ph.clap670; ph.width670 = E.ph.width670;
     ph.Ra410 = E.ph.Ra410; ph.clap410 = E.ph.clap410; ph.width410 = E.ph.width410; ph.transT670 = 0; ph.transT410 = 0;

@@ -116,7 +116,7 @@ void ccu_destroy(ccu_ctx *c)
         for(auto v : L.vec) cudaFree(v);
     }
     cudaFree(c->en.Tdot); cudaFree(c->en.DTdot); cudaFree(c->en.V); cudaFree(c->en.T1); cudaFree(c->en.Tdot1); cudaFree(c->en.diffusivity);
-    cudaFree(c->en.hf); cudaFree(c->en.hf_area); cudaFree(c->en.hf_sums); cudaFree(c->en.layer_tab); cudaFree(c->en.Fas670); cudaFree(c->en.Fas410); cudaFree(c->en.transT); cudaFree(c->en.heat_adi); cudaFree(c->en.heat_visc); cudaFree(c->en.heat_latent);
+    cudaFree(c->en.hf); cudaFree(c->en.hf_area); cudaFree(c->en.hf_sums); cudaFree(c->en.layer_tab); cudaFree(c->en.transT_tab); cudaFree(c->en.Fas670); cudaFree(c->en.Fas410); cudaFree(c->en.transT); cudaFree(c->en.heat_adi); cudaFree(c->en.heat_visc); cudaFree(c->en.heat_latent);
     cudaFree(c->en.expansivity); cudaFree(c->en.Eres); cudaFree(c->en.layer); cudaFree(c->en.red);
     { auto &M = c->mk; cudaFree(M.X); cudaFree(M.Xpred); cudaFree(M.VO); cudaFree(M.Vpred); cudaFree(M.C12); cudaFree(M.CElement); cudaFree(M.count);
       cudaFree(M.CE); cudaFree(M.C); cudaFree(M.XP); cudaFree(M.RG3); cudaFree(M.Element); cudaFree(M.err); }

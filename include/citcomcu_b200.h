@@ -66,8 +66,9 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
         * every coefficient of a row once per pass instead of gathering each stored block twice.  Measured on B200 (r02): 1.27x fewer DRAM
         * bytes but only 3 % faster (the pass stops being DRAM-bound), the matvec slower -- kept as an option, see DESIGN.md */
        CCU_OPT_FULL_NODES = 18, CCU_OPT_RELAX_FULL = 19, CCU_OPT_MATVEC_FULL = 20,
-       CCU_OPT_P2P_HALO = 21 /* subdomain-per-GPU runs: 1 (default) = halo sums through peer memory (CUDA IPC landing buffers over NVLink: a push kernel,
-        * a flag per sender, a wait kernel; no NCCL call per exchange), 0 = grouped ncclSend/ncclRecv.  Set it identically on all ranks. */,
+       CCU_OPT_P2P_HALO = 21 /* subdomain-per-GPU runs: 1 = halo sums through peer memory (CUDA IPC landing buffers over NVLink: a push kernel,
+        * a flag per sender, a wait kernel; no NCCL call per exchange), 0 (default: measured faster on 8 x B200) = grouped ncclSend/ncclRecv.
+        * Set it identically on all ranks. */,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);

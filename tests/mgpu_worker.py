@@ -76,6 +76,11 @@ def run_rank(rank, world, text, uid_q, out_q, accuracy, agglomerate=True, device
             res["dt"].append(float(dt))
         res["T2"] = ctx.get_temperature()
         res["b2"] = ctx.thermal_buoyancy(float(prob.rayleigh))
+        # phase changes across the subdomains: transition temperatures from the layer averages (summed over the ranks of a plane)
+        # of whichever z subdomain holds the phase depth (sum_across_depth), then the phase functions of the local nodes
+        ctx.set_phase_params(0.7665505, 0.857143, -50.0, -0.05, 30.0, 80.0, 0.07, 30.0)
+        F6, F4, tT = ctx.phase_change(update_transT=True)
+        res["Fas670"], res["Fas410"], res["transT"] = F6, F4, tT
         res["launches"] = ctx.launch_count
         ctx.close()
         out_q.put(res)

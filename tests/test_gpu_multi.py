@@ -99,11 +99,16 @@ def test_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
     dts = [float(ctx.advance(float(gp.rayleigh), rebuild=1, **kwg)[0]) for _ in range(2)]
     T2g = ctx.get_temperature()
     b2g = ctx.thermal_buoyancy(float(gp.rayleigh))
+    ctx.set_phase_params(0.7665505, 0.857143, -50.0, -0.05, 30.0, 80.0, 0.07, 30.0)
+    F6g, F4g, tTg = ctx.phase_change(update_transT=True)
     for r in res:
         prob = CartesianProblem(text, me_loc=r["me"])
         assert np.allclose(r["dt"], dts, rtol=1e-5)
         assert np.abs(r["T2"] - prob.local_slice(T2g)).max() < 1e-5
         assert np.abs(r["b2"] - prob.local_slice(b2g)).max() < 1e-5 * np.abs(b2g).max()
+        # phase_change with the phase depths in one z subdomain only (sum_across_depth, Global_operations.c:763)
+        assert np.allclose(r["transT"], tTg, rtol=1e-5, atol=1e-7), (r["me"], r["transT"], tTg)
+        assert np.abs(r["Fas670"] - prob.local_slice(F6g)).max() < 1e-4 and np.abs(r["Fas410"] - prob.local_slice(F4g)).max() < 1e-4
     ctx.close()
     num_u = den_u = num_p = den_p = 0.0
     for r in res:
