@@ -229,8 +229,8 @@ def workload_config(args, mesh, nproc=(1, 1, 1)):
                         f"free slip, {args.levels} multigrid levels; step = general_stokes_solver from a zero guess "
                         "(viscosity + stiffness rebuild + forces + Uzawa/FMG solve to accuracy 1e-3)",
             "mesh": list(mesh), "levels": args.levels, "nproc": list(nproc),
-            "partition": "one subdomain per GPU, the reference's nprocx x nprocy x nprocz block decomposition; halo sums through peer memory "
-                         "(CUDA IPC over NVLink; NCCL send/recv if unavailable), allreduce over NCCL",
+            "partition": "one subdomain per GPU, the reference's nprocx x nprocy x nprocz block decomposition; halo sums as grouped NCCL "
+                         "send/recv (or through peer memory, option p2p_halo), allreduce over NCCL",
             "l2": "inputs larger than L2 (finest-level stiffness alone is > 4 GB)"}
 
 
