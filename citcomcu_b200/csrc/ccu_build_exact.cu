@@ -1916,6 +1916,122 @@ int ccu_get_heating_latent(ccu_ctx *c, float *heating_latent_out)
     SYNC(c);
     return 0;
 }
+// ================================================================= get_stress / get_STD_topo (Topo_gravity.c:352-562, 307-335)
+// per element: S = sum_gp pre * strain rate / area - P (diagonal), pre = EVI * gDA, float arithmetic as the reference
+__global__ void __launch_bounds__(64) st_element(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ EVI, const float *__restrict__ V,
+                                                 const double *__restrict__ P, float *S6)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8], gnx[3][8], VX[8], VY[8], VZ[8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        VX[a - 1] = V[n]; VY[a - 1] = V[(size_t)g.nno + n]; VZ[a - 1] = V[2 * (size_t)g.nno + n];
+    }
+    float Sxx = 0.f, Syy = 0.f, Szz = 0.f, Sxy = 0.f, Sxz = 0.f, Szy = 0.f;
+    double area = 0.0;
+    for(int i = 0; i < 8; i++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + i, 64, 8, gnx);
+        const float pre = EVI[(size_t)e * 8 + i] * gda;
+        float Vzz = 0.f, Vxx = 0.f, Vyy = 0.f, Vxy = 0.f, Vxz = 0.f, Vzy = 0.f;
+        for(int j = 0; j < 8; j++)
+        {
+            Vzz += VZ[j] * gnx[2][j];
+            Vxx += VX[j] * gnx[0][j];
+            Vxz += (VX[j] * gnx[2][j] + VZ[j] * gnx[0][j]);
+            Vyy += VY[j] * gnx[1][j];
+            Vxy += (VX[j] * gnx[1][j] + VY[j] * gnx[0][j]);
+            Vzy += (VY[j] * gnx[2][j] + VZ[j] * gnx[1][j]);
+        }
+        Sxx = (float)((double)Sxx + 2.0 * (double)pre * (double)Vxx);
+        Syy = (float)((double)Syy + 2.0 * (double)pre * (double)Vyy);
+        Szz = (float)((double)Szz + 2.0 * (double)pre * (double)Vzz);
+        Sxy += pre * Vxy; Sxz += pre * Vxz; Szy += pre * Vzy;
+        area += 1.0 * (double)gda;
+    }
+    const float ar = (float)area;                       // E->eco[e].area (Size_does_matter.c:712)
+    Sxx /= ar; Syy /= ar; Szz /= ar; Sxz /= ar; Sxy /= ar; Szy /= ar;
+    const double p = P[e];
+    Szz = (float)((double)Szz - p); Sxx = (float)((double)Sxx - p); Syy = (float)((double)Syy - p);
+    const size_t nel = (size_t)g.nel;                   // order of the output planes: SXX, SXY, SXZ, SYY, SZY, SZZ (get_stress's arguments)
+    S6[e] = Sxx; S6[nel + e] = Sxy; S6[2 * nel + e] = Sxz; S6[3 * nel + e] = Syy; S6[4 * nel + e] = Szy; S6[5 * nel + e] = Szz;
+}
+// nodal value += TWW * element value in ascending element order, for the six components; * Mass unless a halo sum comes first
+__global__ void __launch_bounds__(128) st_nodal(const CcuGeom g, const float *__restrict__ TWW, const float *__restrict__ MASS,
+                                                const float *__restrict__ S6e, float *S6n)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    float acc[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int e = ez + g.elz * (ex + g.elx * ey);
+                const float w = TWW[(size_t)e * 8 + LUT[k - ez][j - ex][i - ey] - 1];
+                for(int q = 0; q < 6; q++) acc[q] += w * S6e[(size_t)q * g.nel + e];
+            }
+        }
+    }
+    const float mss = MASS ? MASS[n] : 1.0f;
+    for(int q = 0; q < 6; q++) S6n[(size_t)q * g.nno + n] = acc[q] * mss;
+}
+__global__ void __launch_bounds__(128) st_topo(const CcuGeom g, const float *__restrict__ SZZ, float *tpg, float *tpgb)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;       // surface node snode - 1; surf_node[snode] = snode * noz (Construct_arrays.c:116)
+    if(s >= g.nox * g.noy) return;
+    const size_t top = (size_t)s * g.noz + (g.noz - 1), bot = (size_t)s * g.noz;
+    tpg[s] = -2 * SZZ[top] + SZZ[top - 1];
+    tpgb[s] = 2 * SZZ[bot] - SZZ[bot + 1];
+}
+// S_out: float[6][nno] in the order SXX, SXY, SXZ, SYY, SZY, SZZ (may be NULL); tpg / tpgb: float[nox*noy] (may be NULL).
+// Needs the resident velocity, viscosity and pressure of the last solve (or ccu_pvec_upload).
+int ccu_get_stress_topo(ccu_ctx *c, float *S_out, float *tpg_out, float *tpgb_out)
+{
+    if(!c) FAIL("null context");
+    if(ensure_energy(c)) return 1;
+    Level &L = c->L[c->cfg.levmax];
+    auto &E = c->en;
+    if(!E.have_v) FAIL("get_stress: velocity missing (ccu_set_velocity / ccu_v_from_vector)");
+    if(!L.have_evi || !L.have_tw || !L.have_xx) FAIL("get_stress: viscosity / geometry missing");
+    if(!c->P) FAIL("get_stress: pressure missing (no Stokes solve yet; ccu_pvec_upload)");
+    const size_t nel = (size_t)L.g.nel, nno = (size_t)L.g.nno, nsf = (size_t)L.g.nox * L.g.noy;
+    float *Se = nullptr, *Sn = nullptr, *tp = nullptr;
+    CK(cudaMalloc(&Se, sizeof(float) * 6 * nel)); CK(cudaMalloc(&Sn, sizeof(float) * 6 * nno)); CK(cudaMalloc(&tp, sizeof(float) * 2 * nsf));
+    LAUNCH(c, st_element, cdiv(nel, 64), 64, L.g, (const float *)L.XX, (const float *)L.EVI, (const float *)E.V, (const double *)c->P, Se);
+    int rc = 0;
+    if(!c->multi()) LAUNCH(c, st_nodal, cdiv(nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const float *)Se, Sn);
+    else
+    {   // six exchange_node_f20 between the element sums and the mass factor (Topo_gravity.c:538-553)
+        LAUNCH(c, st_nodal, cdiv(nno, 128), 128, L.g, (const float *)L.TWW, (const float *)nullptr, (const float *)Se, Sn);
+        for(int q = 0; q < 6 && !rc; q++)
+        {
+            rc = ccu_halo_sum_nodal(c, c->cfg.levmax, Sn + q * nno);
+            LAUNCH(c, bk_mul, cdiv(nno, 128), 128, L.g.nno, Sn + q * nno, L.MASS);
+        }
+    }
+    LAUNCH(c, st_topo, cdiv(nsf, 128), 128, L.g, (const float *)(Sn + 5 * nno), tp, tp + nsf);
+    if(!rc && S_out) rc = cudaMemcpyAsync(S_out, Sn, sizeof(float) * 6 * nno, cudaMemcpyDeviceToHost, c->st) != cudaSuccess;
+    if(!rc && tpg_out) rc = cudaMemcpyAsync(tpg_out, tp, sizeof(float) * nsf, cudaMemcpyDeviceToHost, c->st) != cudaSuccess;
+    if(!rc && tpgb_out) rc = cudaMemcpyAsync(tpgb_out, tp + nsf, sizeof(float) * nsf, cudaMemcpyDeviceToHost, c->st) != cudaSuccess;
+    if(cudaStreamSynchronize(c->st) != cudaSuccess) rc = 1;
+    cudaFree(Se); cudaFree(Sn); cudaFree(tp);
+    if(rc) FAIL("get_stress: device error");
+    CK_LAUNCHES(c);
+    return 0;
+}
+
 // averages (Process_velocity.c:179-224): horizontal averages per z layer of the nodal viscosity, of the composition and
 // of |V|^2 (-> layer vrms), from the resident velocity / viscosity / markers; return_horiz_ave (Global_operations.c:133) over
 // the ranks of a horizontal plane as in thermal_buoyancy.  Outputs float[noz] each, any may be NULL.

@@ -498,6 +498,14 @@ class StokesContext:
     def markers_count(self):
         return int(self.lib.ccu_markers_count(self._ctx))
 
+    def get_stress_topo(self):
+        """get_stress + get_STD_topo (Topo_gravity.c:352,307): (S[6, nno] = SXX, SXY, SXZ, SYY, SZY, SZZ; tpg[nsf]; tpgb[nsf])."""
+        lm = self.levmax
+        nox, noy, _ = self.dims[lm]
+        S = np.empty((6, self.nno(lm)), np.float32); tpg = np.empty(nox * noy, np.float32); tpgb = np.empty(nox * noy, np.float32)
+        check(self.lib.ccu_get_stress_topo(self._ctx, S.ctypes.data_as(C.c_void_p), tpg.ctypes.data_as(C.c_void_p), tpgb.ctypes.data_as(C.c_void_p)))
+        return S, tpg, tpgb
+
     def averages(self, composition=False):
         """averages (Process_velocity.c:179): layer vrms, layer mean viscosity (and composition): float[noz] arrays."""
         noz = self.dims[self.levmax][2]

@@ -241,6 +241,10 @@ int ccu_get_temperature(ccu_ctx *ctx, float *T /*[nno]*/, float *Tdot /*[nno] or
  * (element heat transport, nodal projection through TWW / Mass, linear extrapolation to the top and bottom surfaces,
  * area-weighted means); across subdomains the nodal sums and the four surface sums are reduced over NCCL */
 int ccu_heat_flux(ccu_ctx *ctx, float *Nut_out, float *Nub_out);
+/* get_stress (Topo_gravity.c:352) and get_STD_topo (:307) from the resident velocity, viscosity and pressure: nodal stresses S_out =
+ * float[6][nno] in the order of get_stress's arguments SXX, SXY, SXZ, SYY, SZY, SZZ; dynamic topography at the top (tpg) and the bottom
+ * (tpgb), float[nox*noy] in surf_node order.  Any output may be NULL.  Cartesian. */
+int ccu_get_stress_topo(ccu_ctx *ctx, float *S_out, float *tpg_out, float *tpgb_out);
 /* averages (Process_velocity.c:179): horizontal averages per z layer -- E->Have.vrms (sqrt of the layer mean of |V|^2), E->Have.Vi (nodal
  * viscosity), E->Have.C (composition) -- float[noz] each, any may be NULL; summed over the ranks of a horizontal plane */
 int ccu_averages(ccu_ctx *ctx, float *vrms_out, float *visc_out, float *C_out);

@@ -176,6 +176,16 @@ static void dump_kats(struct All_variables *E)
     double *f = (double *)calloc(neqmax + 10, 8), *d0 = (double *)calloc(neqmax + 10, 8);
     double *w = (double *)calloc(neqmax + 10, 8);
     double *p = (double *)calloc(E->lmesh.npno + 10, 8), *q = (double *)calloc(E->lmesh.npno + 10, 8);
+    {   /* get_stress / get_STD_topo (Topo_gravity.c:352,307) on the current state (V, P, EVI of the last solve) */
+        const int nno = E->lmesh.nno, nsf = E->lmesh.nsf;
+        float *S = (float *)calloc((size_t)6 * (nno + 1), sizeof(float));
+        float *tp = (float *)calloc((size_t)2 * (nsf + 2), sizeof(float));
+        get_stress(S, S + (nno + 1), S + 2 * (nno + 1), S + 3 * (nno + 1), S + 4 * (nno + 1), S + 5 * (nno + 1), E);
+        for(i = 0; i < 6; i++) { snprintf(nm, sizeof nm, "kat_stress%d", i); DUMP_F32(nm, S + (size_t)i * (nno + 1) + 1, nno); }
+        get_STD_topo(E, tp, tp + nsf + 2, 0);
+        DUMP_F32("kat_tpg", tp + 1, nsf); DUMP_F32("kat_tpgb", tp + nsf + 2 + 1, nsf);
+        free(S); free(tp);
+    }
 
     for(lev = levmin; lev <= levmax; lev++)
     {

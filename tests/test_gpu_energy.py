@@ -270,3 +270,30 @@ def test_observables_on_a_developed_state():
     ctx.close()
     # the state did develop: Nu and Vrms moved away from their step-0 values
     assert abs(seen[-1][0] - seen[0][0]) > 1.0 and abs(seen[-1][1] - seen[0][1]) > 0.1 * seen[0][1]
+
+
+def test_stress_and_dynamic_topography():
+    """get_stress / get_STD_topo (Topo_gravity.c:352,307) on the reference's state after a Stokes solve: the six nodal stress
+    fields and the top / bottom dynamic topography within 1e-4 of the reference's own functions (float sums)."""
+    import tempfile
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=2, accuracy=1e-5, viscE="4.6,4.6,4.6,4.6")
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_stress_"), nsteps=0, kat=True)[0][0]      # the known answers are taken on the step-0 state
+    prob = CartesianProblem(txt)
+    ctx = context_from_problem(prob)
+    lm = prob.levmax
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_velocity(d["s0_V1"], d["s0_V2"], d["s0_V3"])
+    ctx.set_element_viscosity(lm, d["s0_EVI"])
+    ctx.pvec_upload(d["s0_P"])
+    S, tpg, tpgb = ctx.get_stress_topo()
+    ctx.close()
+    for q in range(6):
+        ref = d[f"kat_stress{q}"]
+        assert np.abs(S[q] - ref).max() <= 1e-4 * np.abs(ref).max(), q
+    assert np.abs(tpg - d["kat_tpg"]).max() <= 1e-4 * np.abs(d["kat_tpg"]).max()
+    assert np.abs(tpgb - d["kat_tpgb"]).max() <= 1e-4 * np.abs(d["kat_tpgb"]).max()
