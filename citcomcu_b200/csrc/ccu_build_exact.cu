@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128) bk_invert_BI(const size_t n, double *v)
 // X3 = E->X[3] (Cartesian depth coordinate of the nodes) for the depth-dependent laws 2 and 4.  The operand types follow
 // the reference expression by expression (float temperature sums, double depth sums, the double constant 0.5 of law 11).
 __global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscParams vp, const int *__restrict__ mat,
-                                               const float *__restrict__ T, const float *__restrict__ X3, float *EVI)
+                                               const float *__restrict__ T, const float *__restrict__ X3, float *EVI, const int clip)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -234,10 +234,80 @@ __global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscPar
             default: v = (float)((double)tempa * exp((double)(El / (temp + Tl)) - (double)El / (0.5 + (double)Tl))); break; // 11: eta0 exp(E/(T+T0) - E/(0.5+T0))
             }
         }
-        if(vp.vmax && v > vp.max_value) v = vp.max_value;
-        if(vp.vmin && v < vp.min_value) v = vp.min_value;
+        if(clip && vp.vmax && v > vp.max_value) v = vp.max_value;
+        if(clip && vp.vmin && v < vp.min_value) v = vp.min_value;
         EVI[(size_t)e * 8 + jj] = v;
     }
+}
+// visc_from_S (Viscosity_structures.c:744-975), sdepv_rheology 1 (power law) and 2 (the same without the leading factor two,
+// only below a transition temperature and composition): per element the second invariant of the strain rate at the pressure
+// point (strain_rate_2_inv with SQRT, :979-1090; 1 on the very first call of a run), then per Gauss point
+//     eta <- [2] eta / (1 + scale eta^(1 - 1/n)),   scale = (2 edot / sigma_trans)^(1 - 1/n)
+__global__ void __launch_bounds__(64) bk_visc_sdepv(const CcuGeom g, const CcuViscParams vp, const int first, const int *__restrict__ mat,
+                                                    const float *__restrict__ XX, const float *__restrict__ V, const float *__restrict__ T,
+                                                    const float *__restrict__ Cn, float *EVI)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float eedot = 1.0f;
+    if(!first)
+    {
+        float X[3][8], gnx[3][8], VV[3][8];
+        load_elt_coords(g, XX, ey, ex, ez, X);
+        gp_geom(X, c_sh.Nxp, 8, 1, gnx);
+        for(int a = 1; a <= 8; a++)
+        {
+            const int n = elt_node(g, ey, ex, ez, a);
+            for(int d = 0; d < 3; d++) VV[d][a - 1] = V[(size_t)d * g.nno + n];
+        }
+        double dudx[3][3];
+        for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) dudx[p][q] = 0.0;
+        for(int i = 0; i < 8; i++)
+            for(int p = 0; p < 3; p++)
+                for(int q = 0; q < 3; q++) dudx[p][q] += VV[p][i] * gnx[q][i];
+        double ed[3][3];
+        for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) ed[p][q] = 0.5 * (dudx[p][q] + dudx[q][p]);
+        const float ee = (float)(ed[0][0] * ed[0][0] + ed[0][1] * ed[0][1] * 2.0 + ed[1][1] * ed[1][1] + ed[1][2] * ed[1][2] * 2.0 +
+                                 ed[2][2] * ed[2][2] + ed[0][2] * ed[0][2] * 2.0);
+        eedot = (float)sqrt(0.5 * (double)ee);
+    }
+    const int l = mat[e] - 1;
+    const float exponent1 = (float)(1.0 - 1.0 / (double)vp.sdepv_expt[l]);
+    const float scale = (float)pow(2.0 * (double)eedot / (double)vp.sdepv_trns[l], (double)exponent1);
+    float TT[8], CC[8];
+    if(vp.sdepv_rheology == 2)
+        for(int a = 1; a <= 8; a++)
+        {
+            const int n = elt_node(g, ey, ex, ez, a);
+            TT[a - 1] = T[n]; CC[a - 1] = Cn ? Cn[n] : 0.0f;
+        }
+    for(int jj = 0; jj < 8; jj++)
+    {
+        const float eta = EVI[(size_t)e * 8 + jj];
+        if(vp.sdepv_rheology == 1)
+            EVI[(size_t)e * 8 + jj] = (float)(2.0 * (double)eta / (1.0 + (double)scale * pow((double)eta, (double)exponent1)));
+        else
+        {
+            float temp = 0.0f, comp = 0.0f;
+            for(int kk = 0; kk < 8; kk++)
+            {
+                temp = (float)((double)temp + fmax(0.0, (double)TT[kk]) * c_sh.Nv[8 * kk + jj]);
+                comp = (float)((double)comp + fmax(0.0, (double)CC[kk]) * c_sh.Nv[8 * kk + jj]);
+            }
+            if(temp < vp.sdepv_trns_T && comp < vp.sdepv_trns_c)
+                EVI[(size_t)e * 8 + jj] = (float)((double)eta / (1.0 + (double)scale * pow((double)eta, (double)exponent1)));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) bk_visc_clip(const size_t n, const CcuViscParams vp, float *EVI)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    float v = EVI[i];
+    if(vp.vmax && v > vp.max_value) v = vp.max_value;
+    if(vp.vmin && v < vp.min_value) v = vp.min_value;
+    EVI[i] = v;
 }
 
 // visc_from_gint_to_ele (Nodal_mesh.c:559-581): element mean of the eight Gauss-point values (double sum)
@@ -1313,6 +1383,20 @@ int ccu_set_viscosity_law(ccu_ctx *c, int tdepv, int rheol, int num_mat, const f
     return 0;
 }
 
+// E->viscosity.{SDEPV, sdepv_rheology, sdepv_expt, sdepv_trns, sdepv_misfit, sdepv_iter_damp, sdepv_start_from_newtonian, sdepv_trns_T,
+// sdepv_trns_c}, E->monitor.max_sdep_visc_iter (Viscosity_structures.c:150-310)
+int ccu_set_sdepv(ccu_ctx *c, int on, int rheology, const float *expt, const float *trns, float misfit, float iter_damp, int max_iter,
+                  int start_from_newtonian, float trns_T, float trns_c)
+{
+    if(!c) FAIL("null context");
+    CcuViscParams &v = c->visc;
+    if(on && rheology != 1 && rheology != 2) FAIL("stress-dependent viscosity: sdepv_rheology 1 and 2 are implemented on the device (3, the dimensional Arrhenius law, is not)");
+    v.sdepv = on != 0; v.sdepv_rheology = rheology; v.sdepv_misfit = misfit; v.sdepv_iter_damp = iter_damp; v.sdepv_max_iter = max_iter;
+    v.sdepv_start_from_newtonian = start_from_newtonian; v.sdepv_trns_T = trns_T; v.sdepv_trns_c = trns_c; v.sdepv_visits = 0;
+    for(int i = 0; i < v.num_mat && i < 40; i++) { v.sdepv_expt[i] = expt ? expt[i] : 1.0f; v.sdepv_trns[i] = trns ? trns[i] : 1.0f; }
+    return 0;
+}
+
 int ccu_set_material(ccu_ctx *c, const int *mat)
 {
     if(!c) FAIL("null context");
@@ -1363,7 +1447,20 @@ int ccu_get_system_viscosity(ccu_ctx *c)
     if(!c->mat) FAIL("get_system_viscosity: material groups missing");
     Level &L = c->L[c->cfg.levmax];
     if(c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4) && !L.have_xx) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
-    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr, L.EVI);
+    const bool sd = c->visc.sdepv != 0;
+    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr, L.EVI, sd ? 0 : 1);
+    if(sd)
+    {   // get_system_viscosity's order (Viscosity_structures.c:386-425): temperature law, stress dependence, then the min / max clip
+        CcuViscParams &v = c->visc;
+        const int first = v.sdepv_visits == 0;                     // a run that did not restart: unit strain rate on the first call
+        if(!first && !c->en.have_v) FAIL("get_system_viscosity: stress-dependent viscosity needs the velocity of the last solve (ccu_v_from_vector)");
+        if(!L.have_xx) FAIL("get_system_viscosity: coordinates missing");
+        if(!v.sdepv_start_from_newtonian || v.sdepv_visits)
+            LAUNCH(c, bk_visc_sdepv, cdiv(L.g.nel, 64), 64, L.g, c->visc, first, (const int *)c->mat, (const float *)L.XX, (const float *)c->en.V, (const float *)c->T,
+                   c->mk.ready ? (const float *)c->mk.C : (const float *)nullptr, L.EVI);
+        v.sdepv_visits++;
+        LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);
+    }
     CK(cudaGetLastError());
     L.have_evi = true;
     return 0;

@@ -20,6 +20,9 @@ struct CcuViscParams
     int rheol = 0, tdepv = 0, num_mat = 1, vmin = 0, vmax = 0, smooth_cycles = 1;
     float N0[40] = { 1.0f }, E[40] = { 0 }, T[40] = { 0 }, Z[40] = { 0 };
     float min_value = 0, max_value = 0;
+    // stress-dependent viscosity (visc_from_S, Viscosity_structures.c:744; the outer loop of Drive_solvers.c:120-159)
+    int sdepv = 0, sdepv_rheology = 1, sdepv_start_from_newtonian = 0, sdepv_max_iter = 50, sdepv_visits = 0;
+    float sdepv_expt[40] = { 1.0f }, sdepv_trns[40] = { 1.0f }, sdepv_misfit = 0.001f, sdepv_iter_damp = 1.0f, sdepv_trns_T = 0, sdepv_trns_c = 0;
 };
 
 struct Level
@@ -91,6 +94,7 @@ struct ccu_ctx
     ccu_config cfg;
     cudaStream_t st = 0, own_stream = 0;
     bool bottom_attr_set = false;
+    double *sdepv_oldU = nullptr, *sdepv_dU = nullptr; double sdepv_last_misfit = 0.0; int sdepv_last_count = 0;     // SDEPV outer loop (ccu_general_stokes_solver)
     int launch_err = 0; const char *launch_err_kernel = "";     // first failed kernel launch since the last check (LAUNCH / CK_LAUNCHES)
     struct GraphSeg { cudaGraphExec_t exec = nullptr; long long launches = 0; };
     GraphSeg seg[4];

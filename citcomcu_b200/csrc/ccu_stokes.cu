@@ -133,7 +133,7 @@ void ccu_destroy(ccu_ctx *c)
         cudaFree(M.sX); cudaFree(M.sXpred); cudaFree(M.sVO); cudaFree(M.sVpred); cudaFree(M.sC12); cudaFree(M.sCElement);
         cudaFree(M.sendbuf); cudaFree(M.recvbuf);
     }
-    cudaFree(c->forceEF);
+    cudaFree(c->forceEF); cudaFree(c->sdepv_oldU); cudaFree(c->sdepv_dU);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }
@@ -172,6 +172,13 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
     default: FAIL("set_option: unknown option");
     }
+}
+int ccu_get_sdepv_iterations(ccu_ctx *c, int *count_out, double *misfit_out)
+{
+    if(!c) FAIL("null context");
+    if(count_out) *count_out = c->sdepv_last_count;
+    if(misfit_out) *misfit_out = c->sdepv_last_misfit;
+    return 0;
 }
 int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
 {
@@ -1154,7 +1161,7 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     if(rebuild)
     {
         CcuProfScope ps(c, CCU_PROF_BUILD, true);
-        if(c->visc.tdepv || !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
+        if(c->visc.tdepv || c->visc.sdepv || !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
         if(ccu_construct_stiffness_B_matrix(c, augmented_Lagr, augmented, precondition)) return 1;
     }
     if(!L.have_K || !L.have_flags || !L.have_p) FAIL("general_stokes_solver: operator not built");
@@ -1172,6 +1179,45 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     d_strip(c, L, L.vec[CCU_VEC_U]);            // velocities_conform_bcs with zero imposed velocities
     int steps = c->cfg.p_iterations;
     if(d_solve_Ahat_p_fhat(c, c->cfg.accuracy, &steps, residual_out, nullptr)) return 1;
+    if(c->visc.sdepv)
+    {   // E->V of the solve just done (solve_constrained_flow_iterative ends with v_from_vector, before any damping): what the next
+        // visc_from_S call reads
+        if(ccu_v_from_vector(c, nullptr)) return 1;
+        // stress-dependent viscosity: viscosity <-> velocity iteration (Drive_solvers.c:120-159) with the damping of :137-141
+        if(!c->sdepv_oldU)
+        {   // oldU persists from timestep to timestep (a static of the reference's, Drive_solvers.c:53), zero at the first call
+            CK(cudaMalloc(&c->sdepv_oldU, sizeof(double) * L.vlen())); CK(cudaMalloc(&c->sdepv_dU, sizeof(double) * L.vlen()));
+            CK(cudaMemsetAsync(c->sdepv_oldU, 0, sizeof(double) * L.vlen(), c->st));
+        }
+        double *oldU = c->sdepv_oldU, *dU = c->sdepv_dU;
+        const double alpha = (double)c->visc.sdepv_iter_damp;
+        const bool damp = fabs(alpha - 1.0) > 1e-7;
+        int count = 1, total = steps;
+        for(;;)
+        {
+            if(damp) d_axpby(c, L.vlen(), L.vec[CCU_VEC_U], oldU, coef(nullptr, nullptr, 1.0 - alpha), coef(nullptr, nullptr, alpha));   // U = alpha U + (1 - alpha) oldU
+            d_waxpby(c, L.vlen(), dU, L.vec[CCU_VEC_U], oldU, C_ONE, C_MINUS);
+            d_copy(c, oldU, L.vec[CCU_VEC_U], L.vlen());
+            d_dot3m(c, &L, L.vlen(), L.vec[CCU_VEC_U], L.vec[CCU_VEC_U], S_DOT1, dU, dU, S_DOT2);
+            double uu[2];
+            if(read_scal(c, S_DOT1, 2, uu)) return 1;
+            const double Umag = sqrt(uu[0]);
+            double dmag = sqrt(uu[1]);
+            if(Umag != 0.0) dmag /= Umag;
+            c->sdepv_last_misfit = dmag; c->sdepv_last_count = count;
+            if(!(dmag > (double)c->visc.sdepv_misfit) || count >= c->visc.sdepv_max_iter) break;
+            {
+                CcuProfScope ps(c, CCU_PROF_BUILD, true);
+                if(ccu_get_system_viscosity(c)) return 1;
+                if(ccu_construct_stiffness_B_matrix(c, augmented_Lagr, augmented, precondition)) return 1;
+            }
+            steps = c->cfg.p_iterations;
+            if(d_solve_Ahat_p_fhat(c, c->cfg.accuracy, &steps, residual_out, nullptr)) return 1;
+            if(ccu_v_from_vector(c, nullptr)) return 1;
+            total += steps; count++;
+        }
+        steps = total;
+    }
     if(iterations_out) *iterations_out = steps;
     if(P) CK(cudaMemcpyAsync(P, c->P, sizeof(double) * L.g.npno, cudaMemcpyDeviceToHost, c->st));
     if(U) return vec_d2h(c, L, L.vec[CCU_VEC_U], U);

@@ -114,8 +114,14 @@ class CartesianProblem:
             T=_fvec(g("viscT", "0"), self.num_mat), Z=_fvec(g("viscZ", "0"), self.num_mat),
             vmin=int(_on(g("VMIN", "off"))), min_value=float(g("visc_min", 0.0)),
             vmax=int(_on(g("VMAX", "off"))), max_value=float(g("visc_max", 0.0)),
-            smooth_cycles=int(g("visc_smooth_cycles", 0)))
-        for k in ("N0", "E", "T", "Z"):
+            smooth_cycles=int(g("visc_smooth_cycles", 0)),
+            # stress-dependent viscosity (Viscosity_structures.c:150-310)
+            sdepv=int(_on(g("SDEPV", "off"))), sdepv_rheology=int(g("sdepv_rheology", 2)),
+            sdepv_expt=_fvec(g("sdepv_expt", "1"), self.num_mat), sdepv_trns=_fvec(g("sdepv_trns", "1"), self.num_mat),
+            sdepv_misfit=float(g("sdepv_misfit", 0.001)), sdepv_iter_damp=float(g("sdepv_iter_damp", 1.0)),
+            sdepv_max_iter=int(g("max_sdep_visc_iter", 50)), sdepv_start_from_newtonian=int(_on(g("sdepv_start_from_newtonian", "off"))),
+            sdepv_trns_T=float(g("sdepv_trns_T", 3000.0)), sdepv_trns_c=float(g("sdepv_trns_c", 2.0)))
+        for k in ("N0", "E", "T", "Z", "sdepv_expt", "sdepv_trns"):
             v = self.visc[k]
             self.visc[k] = v + [v[-1]] * (self.num_mat - len(v))
         self.zbase_layer = [f32(float(g("z_lith", 0.0))), f32(float(g("z_410", 1.0))), f32(float(g("z_lmantle", 1.0))), f32(0.55)]

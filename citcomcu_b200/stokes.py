@@ -168,6 +168,17 @@ class StokesContext:
                                              *[a.ctypes.data_as(C.c_void_p) for a in arrs], int(vmin), C.c_float(min_value),
                                              int(vmax), C.c_float(max_value), int(smooth_cycles)))
 
+    def set_sdepv(self, on, rheology, expt, trns, misfit=0.001, iter_damp=1.0, max_iter=50, start_from_newtonian=0, trns_T=0.0, trns_c=0.0):
+        """Stress-dependent viscosity (visc_from_S, sdepv_rheology 1 / 2) and its outer iteration (Drive_solvers.c:120-159)."""
+        e = np.ascontiguousarray(expt, dtype=np.float32); t = np.ascontiguousarray(trns, dtype=np.float32)
+        check(self.lib.ccu_set_sdepv(self._ctx, int(on), int(rheology), e.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_float(misfit),
+                                     C.c_float(iter_damp), int(max_iter), int(start_from_newtonian), C.c_float(trns_T), C.c_float(trns_c)))
+
+    def sdepv_iterations(self):
+        n, m = C.c_int(0), C.c_double(0.0)
+        check(self.lib.ccu_get_sdepv_iterations(self._ctx, C.byref(n), C.byref(m)))
+        return int(n.value), float(m.value)
+
     def set_material(self, mat):
         m = np.ascontiguousarray(mat, dtype=np.int32)
         assert m.size == self.nel(self.levmax)
@@ -656,4 +667,7 @@ def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, commu
     ctx.set_viscosity_law(v["tdepv"], v["rheol"], v["N0"], v["E"], v["T"], v["Z"], v["vmin"], v["min_value"], v["vmax"],
                           v["max_value"], v["smooth_cycles"])
     ctx.set_material(prob.material())
+    if v.get("sdepv"):
+        ctx.set_sdepv(1, v["sdepv_rheology"], v["sdepv_expt"], v["sdepv_trns"], v["sdepv_misfit"], v["sdepv_iter_damp"], v["sdepv_max_iter"],
+                      v["sdepv_start_from_newtonian"], v["sdepv_trns_T"], v["sdepv_trns_c"])
     return ctx

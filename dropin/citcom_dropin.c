@@ -60,7 +60,11 @@ void ccu_dropin_init(struct All_variables *E)
     int lev;
     const char *dev = getenv("CCU_DEVICE");
     if(!E->control.CART3D) die("only Geometry=cart3d is accelerated");
-    if(E->viscosity.SDEPV || E->viscosity.CDEPV || E->viscosity.BDEPV) die("stress/composition/Byerlee viscosity is not on the device path");
+    if(E->viscosity.CDEPV || E->viscosity.BDEPV) die("composition- / Byerlee-dependent viscosity is not on the device path");
+    if(E->viscosity.SDEPV && E->viscosity.sdepv_rheology != 1 && E->viscosity.sdepv_rheology != 2)
+        die("stress-dependent viscosity: sdepv_rheology 1 and 2 are on the device path, 3 (dimensional Arrhenius law) is not");
+    if(E->viscosity.SDEPV && E->control.restart) die("stress-dependent viscosity with restart (strain rate of the restart velocity) is not on the device path");
+    if(E->control.force_initial_stokes_iteration) die("force_initial_stokes_iteration is not on the device path");
     /* options that change the operator and that the device build does not implement: stop, never differ silently */
     if(E->viscosity.SMOOTH) die("viscosity smoothing (VISC_SMOOTH / apply_viscosity_smoother) is not on the device path");
     if(E->viscosity.allow_anisotropic_viscosity) die("anisotropic viscosity is not on the device path");
@@ -110,6 +114,10 @@ void ccu_dropin_init(struct All_variables *E)
                               E->viscosity.T, E->viscosity.Z, E->viscosity.MIN, E->viscosity.min_value, E->viscosity.MAX,
                               E->viscosity.max_value, E->viscosity.smooth_cycles));
     CCU(ccu_set_material(g_ctx, E->mat + 1));
+    if(E->viscosity.SDEPV)
+        CCU(ccu_set_sdepv(g_ctx, 1, E->viscosity.sdepv_rheology, E->viscosity.sdepv_expt, E->viscosity.sdepv_trns, E->viscosity.sdepv_misfit,
+                          E->viscosity.sdepv_iter_damp, E->monitor.max_sdep_visc_iter, E->viscosity.sdepv_start_from_newtonian,
+                          E->viscosity.sdepv_trns_T, E->viscosity.sdepv_trns_c));
     if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: Stokes solve on CUDA device %d\n", cfg.device);
 }
 
@@ -145,6 +153,7 @@ void general_stokes_solver(struct All_variables *E)
     if(rebuild) CCU(ccu_get_level_array(g_ctx, lm, CCU_ARR_EVI, E->EVI[lm] + 1));
     v_from_vector(E, E->V, E->U);
     E->monitor.visc_iter_count = 1;
+    if(E->viscosity.SDEPV) { double mis; CCU(ccu_get_sdepv_iterations(g_ctx, &E->monitor.visc_iter_count, &mis)); }
     g_calls++;
     if(E->control.print_convergence && E->parallel.me == 0)
     {

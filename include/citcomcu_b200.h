@@ -124,6 +124,13 @@ int ccu_build_geometry(ccu_ctx *ctx);
 int ccu_set_viscosity_law(ccu_ctx *ctx, int tdepv, int rheol, int num_mat, const float *N0, const float *E, const float *T,
                           const float *Z, int vmin, float min_value, int vmax, float max_value, int smooth_cycles);
 int ccu_set_material(ccu_ctx *ctx, const int *mat /*[nel] = E->mat+1*/);
+/* stress-dependent viscosity (visc_from_S, Viscosity_structures.c:744, sdepv_rheology 1 and 2) and the viscosity <-> velocity iteration of
+ * general_stokes_solver (Drive_solvers.c:120-159): E->viscosity.{SDEPV, sdepv_rheology, sdepv_expt, sdepv_trns, sdepv_misfit, sdepv_iter_damp,
+ * sdepv_start_from_newtonian, sdepv_trns_T, sdepv_trns_c}, E->monitor.max_sdep_visc_iter; call after ccu_set_viscosity_law */
+int ccu_set_sdepv(ccu_ctx *ctx, int on, int rheology, const float *expt, const float *trns, float misfit, float iter_damp, int max_iter,
+                  int start_from_newtonian, float trns_T, float trns_c);
+/* iterations and relative velocity change of the last stress-dependent-viscosity loop (E->monitor.visc_iter_count) */
+int ccu_get_sdepv_iterations(ccu_ctx *ctx, int *count_out, double *misfit_out);
 int ccu_set_temperature(ccu_ctx *ctx, const float *T /*[nno] = E->T+1*/);
 int ccu_set_element_viscosity(ccu_ctx *ctx, int lev, const float *EVI /*[nel*8] = E->EVI[lev]+1*/);
 /* get_system_viscosity (Viscosity_structures.c:369): EVI[levmax] from the resident temperature / material groups */
