@@ -89,9 +89,11 @@ struct CcuComm
     long long gneq = 0, gnpno = 0;   // global equation / pressure counts (E->mesh.neq, E->mesh.npno)
 };
 
+struct CcuOutput;
 struct ccu_ctx
 {
     ccu_config cfg;
+    CcuOutput *out = nullptr;          // output staging (ccu_output.cu)
     cudaStream_t st = 0, own_stream = 0;
     bool bottom_attr_set = false;
     double *sdepv_oldU = nullptr, *sdepv_dU = nullptr; double sdepv_last_misfit = 0.0; int sdepv_last_count = 0;     // SDEPV outer loop (ccu_general_stokes_solver)
@@ -223,6 +225,7 @@ struct CcuProfScope
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int ccu_ensure_stage(ccu_ctx *c, size_t bytes);
+void ccu_output_destroy(ccu_ctx *c);      // ccu_output.cu
 void ccu_drop_graphs(ccu_ctx *c);
 // ccu_comm.cu
 void ccu_comm_destroy(ccu_ctx *c);

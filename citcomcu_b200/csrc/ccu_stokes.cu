@@ -105,6 +105,7 @@ static void drop_graphs(ccu_ctx *c) { ccu_drop_graphs(c); }
 
 void ccu_destroy(ccu_ctx *c)
 {
+    if(c) ccu_output_destroy(c);
     if(!c) return;
     if(c->coarse) { ccu_destroy(c->coarse); c->coarse = nullptr; }
     cudaFree(c->agg_buf);

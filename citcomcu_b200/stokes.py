@@ -509,6 +509,15 @@ class StokesContext:
     def markers_count(self):
         return int(self.lib.ccu_markers_count(self._ctx))
 
+    def output_stage(self):
+        check(self.lib.ccu_output_stage(self._ctx))
+
+    def output_write(self, prefix, me, file_number, timesteps, elapsed_time, composition=0):
+        check(self.lib.ccu_output_write(self._ctx, str(prefix).encode(), int(me), int(file_number), int(timesteps), C.c_double(elapsed_time), int(composition)))
+
+    def output_wait(self):
+        check(self.lib.ccu_output_wait(self._ctx))
+
     def get_stress_topo(self):
         """get_stress + get_STD_topo (Topo_gravity.c:352,307): (S[6, nno] = SXX, SXY, SXZ, SYY, SZY, SZZ; tpg[nsf]; tpgb[nsf])."""
         lm = self.levmax

@@ -252,6 +252,12 @@ int ccu_heat_flux(ccu_ctx *ctx, float *Nut_out, float *Nub_out);
  * float[6][nno] in the order of get_stress's arguments SXX, SXY, SXZ, SYY, SZY, SZZ; dynamic topography at the top (tpg) and the bottom
  * (tpgb), float[nox*noy] in surf_node order.  Any output may be NULL.  Cartesian. */
 int ccu_get_stress_topo(ccu_ctx *ctx, float *S_out, float *tpg_out, float *tpgb_out);
+/* ---- output staging (Output.c:54-170): ccu_output_stage enqueues the device->host copies of T, V (C with markers, the nodal heat flux of the
+ * last ccu_heat_flux) into pinned buffers and returns at once; ccu_output_write hands them to a background thread that waits for the copies and
+ * writes <prefix>.velo.<me>.<n> and <prefix>.temp.<me>.<n> in the reference's ASCII formats while the solver continues; ccu_output_wait joins it. */
+int ccu_output_stage(ccu_ctx *ctx);
+int ccu_output_write(ccu_ctx *ctx, const char *prefix, int me, int file_number, int timesteps, double elapsed_time, int composition);
+int ccu_output_wait(ccu_ctx *ctx);
 /* averages (Process_velocity.c:179): horizontal averages per z layer -- E->Have.vrms (sqrt of the layer mean of |V|^2), E->Have.Vi (nodal
  * viscosity), E->Have.C (composition) -- float[noz] each, any may be NULL; summed over the ranks of a horizontal plane */
 int ccu_averages(ccu_ctx *ctx, float *vrms_out, float *visc_out, float *C_out);

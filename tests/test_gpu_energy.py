@@ -297,3 +297,34 @@ def test_stress_and_dynamic_topography():
         assert np.abs(S[q] - ref).max() <= 1e-4 * np.abs(ref).max(), q
     assert np.abs(tpg - d["kat_tpg"]).max() <= 1e-4 * np.abs(d["kat_tpg"]).max()
     assert np.abs(tpgb - d["kat_tpgb"]).max() <= 1e-4 * np.abs(d["kat_tpgb"]).max()
+
+
+def test_output_staging_writes_the_reference_files():
+    """Output staging (ccu_output_stage / _write / _wait): the .velo file written by the background thread from the staged device
+    fields is byte-identical to the file the reference's output_velo_related wrote for the same state; the .temp file agrees in
+    its T and Vz columns (its third column is a host-only diagnostic of the reference)."""
+    import glob
+    import tempfile
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import CartesianProblem
+    from citcomcu_b200.stokes import context_from_problem
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, storage_spacing=1)
+    wd = tempfile.mkdtemp(prefix="ccu_out_")
+    d = po.run_harness(txt, wd, nsteps=0)[0][0]
+    ref_velo = open(glob.glob(wd + "/out/*.velo.0.0")[0]).read()
+    ref_temp = open(glob.glob(wd + "/out/*.temp.0.0")[0]).read().split("\n")
+    ctx = context_from_problem(CartesianProblem(txt))
+    ctx.set_temperature(d["s0_T"])
+    ctx.set_velocity(d["s0_V1"], d["s0_V2"], d["s0_V3"])
+    ctx.output_stage()
+    pre = tempfile.mkdtemp(prefix="ccu_outdev_") + "/run"
+    ctx.output_write(pre, 0, 0, 0, 0.0)
+    ctx.output_wait()
+    ctx.close()
+    assert open(pre + ".velo.0.0").read() == ref_velo
+    mine = open(pre + ".temp.0.0").read().split("\n")
+    assert mine[0] == ref_temp[0] and len(mine) == len(ref_temp)
+    for a, b in zip(mine[1:-1], ref_temp[1:-1]):
+        assert a.split()[:2] == b.split()[:2]
