@@ -120,3 +120,22 @@ def input1_cart(levels: int = 4, maxstep: int = 5, **overrides) -> str:
     )
     p.update(overrides)
     return cartesian_box(n, n, n, levels, dimx=1.0, dimy=1.0, dimz=1.0, maxstep=maxstep, **p)
+
+
+def input1_rsphere(levels: int = 3, maxstep: int = 2, **overrides) -> str:
+    """BASELINE config 4 geometry: examples/input1's regional-spherical block (radius 0.55 .. 1, colatitude 73.5 .. 106.5 deg,
+    longitude 0 .. 36 deg, refined radial boundary layers) as a single-rank run with mgunit 6x6x6 and `levels` levels."""
+    n = 6 * 2 ** (levels - 1)
+    a = n // 8
+    p = dict(
+        Geometry="Rsphere", rayleigh=10.97394e5, TDEPV="off", VISC_UPDATE="off", update_every_steps=2, viscE="6.9077553,6.9077553,6.9077553,6.9077553",
+        VMIN="on", visc_min=5.0e-2, VMAX="on", visc_max=2.0e04, topvbc=0, botvbc=0, perturbmag=0.001, perturbk=1.0, perturbl=6.0,
+        aug_lagr="on", aug_number=1.0e3, precond="on", dissipation_number=2.601, accuracy=1.0e-3,
+        radius_inner=0.55, radius_outer=1.0, theta_north=73.5, theta_south=106.5, fi_west=0, fi_east=36.0,
+        r_grid_layers=4, rr="0.55,0.59,0.96,1.0", nr=f"1,{1 + a},{1 + n - a},{1 + n}",
+        t_grid_layers=2, tt="73.5,106.5", nt=f"1,{1 + n}", f_grid_layers=2, ff="0,36", nf=f"1,{1 + n}",
+        r_lmantle=0.89482, r_410=0.9356358, r_lith=0.984301,
+        z_grid_layers=4, zz="0.0,0.1,0.9,1.0", nz=f"1,{1 + a},{1 + n - a},{1 + n}",
+    )
+    p.update(overrides)
+    return cartesian_box(n, n, n, levels, dimx=1.0, dimy=1.0, dimz=1.0, maxstep=maxstep, **p)

@@ -41,6 +41,7 @@
 #include "citcomcu_b200.h"
 
 ccu_ctx *g_ctx = NULL;              /* shared with citcom_dropin_funcs.c */
+int g_ccu_device_geometry = 1;      /* 0: spherical mesh, only the function-level bindings (operator assembled by the reference) */
 static int g_calls = 0;
 
 void ccu_dropin_die(const char *msg);
@@ -59,7 +60,10 @@ void ccu_dropin_init(struct All_variables *E)
     ccu_config cfg;
     int lev;
     const char *dev = getenv("CCU_DEVICE");
-    if(!E->control.CART3D) die("only Geometry=cart3d is accelerated");
+    /* Regional-spherical runs: the device has no Rsphere operator construction / energy step yet.  What it can run is the SOLVER on
+       the operator the reference assembled (function-level bindings, citcom_dropin_funcs.c: the node-stored stiffness, the pressure
+       operators and the transfer weights are geometry-free once assembled), so the context is created without device geometry. */
+    g_ccu_device_geometry = E->control.CART3D ? 1 : 0;
     if(E->viscosity.CDEPV || E->viscosity.BDEPV) die("composition- / Byerlee-dependent viscosity is not on the device path");
     if(E->viscosity.SDEPV && E->viscosity.sdepv_rheology != 1 && E->viscosity.sdepv_rheology != 2)
         die("stress-dependent viscosity: sdepv_rheology 1 and 2 are on the device path, 3 (dimensional Arrhenius law) is not");
@@ -107,7 +111,12 @@ void ccu_dropin_init(struct All_variables *E)
     for(lev = cfg.levmin; lev <= cfg.levmax; lev++)
     {
         CCU(ccu_set_node_flags(g_ctx, lev, E->NODE[lev] + 1));
-        CCU(ccu_set_coordinates(g_ctx, lev, E->XX[lev][1] + 1, E->XX[lev][2] + 1, E->XX[lev][3] + 1));
+        if(g_ccu_device_geometry) CCU(ccu_set_coordinates(g_ctx, lev, E->XX[lev][1] + 1, E->XX[lev][2] + 1, E->XX[lev][3] + 1));
+    }
+    if(!g_ccu_device_geometry)
+    {
+        if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: Rsphere geometry: solver functions on CUDA device %d, operator assembly by the reference\n", cfg.device);
+        return;
     }
     CCU(ccu_build_geometry(g_ctx));
     CCU(ccu_set_viscosity_law(g_ctx, E->viscosity.TDEPV, E->viscosity.RHEOL, E->viscosity.num_mat, E->viscosity.N0, E->viscosity.E,
@@ -142,6 +151,7 @@ void general_stokes_solver(struct All_variables *E)
         }
     }
     if(!g_ctx) dropin_init(E);
+    if(!g_ccu_device_geometry) die("general_stokes_solver: only Geometry=cart3d builds its operator on the device; for Rsphere run with CCU_DROPIN_STOKES=0 CCU_DROPIN_ENERGY=0 and bind the solver functions (CCU_DROPIN_FUNCS=solve_Ahat_p_fhat)");
     E->monitor.elapsed_time_vsoln1 = E->monitor.elapsed_time_vsoln;
     E->monitor.elapsed_time_vsoln = E->monitor.elapsed_time;
     /* Construct_arrays.c:849: first call, or viscosity updates allowed and step % update_every_steps == 0 */
@@ -182,6 +192,7 @@ void PG_timestep(struct All_variables *E)
         }
     }
     if(!g_ctx) dropin_init(E);
+    if(!g_ccu_device_geometry) die("PG_timestep: the device energy step is Cartesian; run Rsphere with CCU_DROPIN_ENERGY=0");
     if(!g_energy)
     {
         if(!E->advection.ADVECTION) die("ADVECTION=off is not on the device path");

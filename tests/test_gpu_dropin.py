@@ -199,3 +199,27 @@ def test_stress_dependent_viscosity_loop(rheology, damp, monkeypatch):
     newt = po.run_harness(inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, accuracy=1e-6, viscE="4.6,4.6,4.6,4.6"),
                           tempfile.mkdtemp(prefix="ccu_snewt_"), nsteps=0)[0][0]
     assert np.abs(r["s0_EVI"] / newt["s0_EVI"] - 1).max() > 0.05
+
+
+@pytest.mark.parametrize("funcs", ["solve_Ahat_p_fhat", "n_assemble_del2_u,assemble_div_u,assemble_grad_p,gauss_seidel,global_vdot,global_pdot"])
+def test_regional_sphere_solver_on_device(funcs, monkeypatch):
+    """BASELINE config 4 geometry (examples/input1's regional-spherical block): the operator is assembled by the reference's host code
+    (the device has no Rsphere element routines yet), the SOLVER -- the Uzawa iteration with its multigrid velocity solves, or its
+    operator / smoother functions one by one -- runs on the device on the uploaded node-stored operator: same U, P as the pure-CPU run."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-5)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rsref_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_STOKES", "0")
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", "0")
+    monkeypatch.setenv("CCU_DROPIN_FUNCS", funcs)
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rsgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "Rsphere geometry: solver functions on CUDA device" in err
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    for k in range(nsteps + 1):
+        U, Ug, P, Pg = r[f"s{k}_U"], g[f"s{k}_U"], r[f"s{k}_P"], g[f"s{k}_P"]
+        assert np.linalg.norm(Ug - U) <= 20 * acc * np.linalg.norm(U), k
+        assert np.linalg.norm(Pg - P) <= 200 * acc * np.linalg.norm(P), k
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
