@@ -616,6 +616,143 @@ __global__ void __launch_bounds__(128) bk_forces_gather(const CcuGeom g, const d
     F[2 * (size_t)g.NS + s] = (fl & CCU_F_VBZ) ? 0.0 : f;
 }
 
+// ---- imposed non-zero boundary velocities: the K.VB term of get_elt_f (Element_calculations.c:1038-1063)
+// raw node bits of the reference (global_defs.h): VBX 0x2, VBZ 0x4, VBY 0x8
+__device__ __forceinline__ unsigned vb_type(int d) { return d == 0 ? 0x2u : (d == 1 ? 0x8u : 0x4u); }
+// marks the elements with a flagged node carrying a non-zero VB and hands each a slot (slot order is irrelevant: one slot, one element)
+__global__ void __launch_bounds__(128) bk_vb_mark(const CcuGeom g, const unsigned *__restrict__ node, const float *__restrict__ VB1,
+                                                   const float *__restrict__ VB2, const float *__restrict__ VB3, int *slot, int *elems, int *count)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    bool any = false;
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        const unsigned f = node[n];
+        any = any || ((f & 0x2u) && VB1[n] != 0.0f) || ((f & 0x8u) && VB2[n] != 0.0f) || ((f & 0x4u) && VB3[n] != 0.0f);
+    }
+    int sl = -1;
+    if(any) { sl = atomicAdd(count, 1); if(elems) elems[sl] = e; }
+    if(slot) slot[e] = sl;
+}
+__global__ void __launch_bounds__(128) bk_vb_slots(const int n_vb, const int *__restrict__ elems, int *slot)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t < n_vb) slot[elems[t]] = t;
+}
+// elt_f[p] -= elt_k[p][q] VB[q] over the flagged dofs q != p with VB != 0; elt_k as get_elt_k builds it (bk_elt_k above)
+__global__ void __launch_bounds__(64) bk_forces_vb_elt(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ EVI,
+                                                      const unsigned *__restrict__ node, const float *__restrict__ VB1,
+                                                      const float *__restrict__ VB2, const float *__restrict__ VB3,
+                                                      const int n_vb, const int *__restrict__ elems, double *EF)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= n_vb) return;
+    const int e = elems[t];
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    float gn[8][3][8];
+    double W[8];
+    for(int k = 0; k < 8; k++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gn[k]);
+        W[k] = (double)(1.0f * gda * EVI[(size_t)e * 8 + k]);
+    }
+    double vb[24], ef[24];
+    for(int a = 0; a < 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a + 1);
+        const unsigned f = node[n];
+        vb[3 * a + 0] = (f & 0x2u) ? (double)VB1[n] : 0.0;
+        vb[3 * a + 1] = (f & 0x8u) ? (double)VB2[n] : 0.0;
+        vb[3 * a + 2] = (f & 0x4u) ? (double)VB3[n] : 0.0;
+    }
+    for(int p = 0; p < 24; p++) ef[p] = 0.0;
+    for(int a = 0; a < 8; a++)
+        for(int b = a; b < 8; b++)
+        {
+            double bd[3][3];
+            for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) bd[i][j] = 0.0;
+            for(int k = 0; k < 8; k++)
+                for(int j = 0; j < 3; j++)
+                    for(int i = 0; i < 3; i++)
+                        bd[i][j] += W[k] * gn[k][j][a] * gn[k][i][b];
+            double temp = 0.0;
+            for(int k = 0; k < 8; k++)
+                temp += W[k] * (gn[k][0][a] * gn[k][0][b] + gn[k][1][a] * gn[k][1][b] + gn[k][2][a] * gn[k][2][b]);
+            bd[0][0] += temp; bd[1][1] += temp; bd[2][2] += temp;
+            // elt_k[3a+i][3b+j] = bd[i][j], elt_k[3b+i][3a+j] = bd[j][i] (Element_calculations.c:268-288)
+            for(int i = 0; i < 3; i++)
+                for(int j = 0; j < 3; j++)
+                {
+                    if(!(a == b && i == j)) ef[3 * a + i] -= bd[i][j] * vb[3 * b + j];
+                    if(a != b) ef[3 * b + i] -= bd[j][i] * vb[3 * a + j];
+                }
+        }
+    for(int p = 0; p < 24; p++) EF[(size_t)p * n_vb + t] = ef[p];
+}
+// adds the elements' -K.VB contributions into the free dofs of F (ascending element order), after bk_forces_gather and before the
+// interface sum
+__global__ void __launch_bounds__(128) bk_forces_vb_gather(const CcuGeom g, const int *__restrict__ slot, const double *__restrict__ EF, const int n_vb,
+                                                           const unsigned char *__restrict__ flags, double *F)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    double f[3] = { 0.0, 0.0, 0.0 };
+    bool any = false;
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int sl = slot[ez + g.elz * (ex + g.elx * ey)];
+                if(sl < 0) continue;
+                const int a = LUT[k - ez][j - ex][i - ey] - 1;
+                for(int d = 0; d < 3; d++) f[d] += EF[(size_t)(3 * a + d) * n_vb + sl];
+                any = true;
+            }
+        }
+    }
+    if(!any) return;
+    const int s = ccu_sidx(g, i, j, k);
+    const unsigned char fl = flags[s];
+    if(!(fl & CCU_F_VBX)) F[s] += f[0];
+    if(!(fl & CCU_F_VBY)) F[(size_t)g.NS + s] += f[1];
+    if(!(fl & CCU_F_VBZ)) F[2 * (size_t)g.NS + s] += f[2];
+}
+__global__ void __launch_bounds__(256) bk_strip_u(const CcuGeom g, const unsigned char *__restrict__ flags, double *U)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= g.NS) return;
+    const unsigned char fl = flags[s];
+    if(fl & CCU_F_VBX) U[s] = 0.0;
+    if(fl & CCU_F_VBY) U[(size_t)g.NS + s] = 0.0;
+    if(fl & CCU_F_VBZ) U[2 * (size_t)g.NS + s] = 0.0;
+}
+// velocities_conform_bcs (Boundary_conditions.c:993-1021) on the resident U
+__global__ void __launch_bounds__(256) bk_conform_vbcs(const CcuGeom g, const unsigned *__restrict__ node, const float *__restrict__ VB1,
+                                                       const float *__restrict__ VB2, const float *__restrict__ VB3, double *U)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const unsigned f = node[n];
+    if(!(f & 0xeu)) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    const int s = ccu_sidx(g, i, j, k);
+    if(f & 0x2u) U[s] = (double)VB1[n];
+    if(f & 0x8u) U[(size_t)g.NS + s] = (double)VB2[n];
+    if(f & 0x4u) U[2 * (size_t)g.NS + s] = (double)VB3[n];
+}
+
 // device K -> reference layout Eqn_k1-3 (test / drop-in read-back)
 __global__ void bk_stiffness_to_ref(const CcuGeom g, const float *__restrict__ K, float *k1, float *k2, float *k3)
 {
@@ -1584,6 +1721,36 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
     if(!c->forceEF) CK(cudaMalloc(&c->forceEF, sizeof(double) * 8 * (size_t)L.g.nel));
     LAUNCH(c, bk_forces_elt, cdiv(L.g.nel, 128), 128, L.g, L.XX, c->buoy, c->forceEF);
     LAUNCH(c, bk_forces_gather, cdiv(L.g.nno, 128), 128, L.g, c->forceEF, L.flags, L.vec[CCU_VEC_F]);
+    if(c->have_vb)
+    {
+        if(!L.have_evi || !L.node) FAIL("assemble_forces: the imposed-velocity term needs the viscosity as it stands (ccu_get_system_viscosity) and the node flags");
+        if(c->vb_dirty)
+        {   // which elements carry the term: counted, then listed (flags and VB only change through their setters)
+            int *cnt = nullptr;
+            CK(cudaMalloc(&cnt, sizeof(int)));
+            CK(cudaMemsetAsync(cnt, 0, sizeof(int), c->st));
+            LAUNCH(c, bk_vb_mark, cdiv(L.g.nel, 128), 128, L.g, L.node, c->VB[0], c->VB[1], c->VB[2], (int *)nullptr, (int *)nullptr, cnt);
+            CK(cudaMemcpyAsync(&c->n_vb, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+            SYNC(c);
+            cudaFree(c->vb_elems); cudaFree(c->vbEF); c->vb_elems = nullptr; c->vbEF = nullptr;
+            if(!c->vb_slot) CK(cudaMalloc(&c->vb_slot, sizeof(int) * (size_t)L.g.nel));
+            if(c->n_vb > 0)
+            {
+                CK(cudaMalloc(&c->vb_elems, sizeof(int) * (size_t)c->n_vb));
+                CK(cudaMalloc(&c->vbEF, sizeof(double) * 24 * (size_t)c->n_vb));
+                CK(cudaMemsetAsync(cnt, 0, sizeof(int), c->st));
+                LAUNCH(c, bk_vb_mark, cdiv(L.g.nel, 128), 128, L.g, L.node, c->VB[0], c->VB[1], c->VB[2], c->vb_slot, c->vb_elems, cnt);
+            }
+            SYNC(c);
+            cudaFree(cnt);
+            c->vb_dirty = false;
+        }
+        if(c->n_vb > 0)
+        {
+            LAUNCH(c, bk_forces_vb_elt, cdiv(c->n_vb, 64), 64, L.g, L.XX, L.EVI, L.node, c->VB[0], c->VB[1], c->VB[2], c->n_vb, c->vb_elems, c->vbEF);
+            LAUNCH(c, bk_forces_vb_gather, cdiv(L.g.nno, 128), 128, L.g, c->vb_slot, c->vbEF, c->n_vb, L.flags, L.vec[CCU_VEC_F]);
+        }
+    }
     if(ccu_halo_sum_vec(c, c->cfg.levmax, L.vec[CCU_VEC_F])) return 1;   // exchange_id_d20 (Element_calculations.c:119)
     if(F_out)
     {
@@ -1592,6 +1759,40 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
         CK(cudaMemcpyAsync(F_out, c->stage, sizeof(double) * L.g.neq, cudaMemcpyDeviceToHost, c->st));
     }
     SYNC(c);
+    return 0;
+}
+
+
+// E->VB (global_defs.h:1038): imposed boundary velocities, [nno] per direction in the reference's node order; all NULL clears them.
+// Non-zero values enter the force vector (the K.VB term of get_elt_f) and U (velocities_conform_bcs).
+int ccu_set_velocity_bcs(ccu_ctx *c, const float *VB1, const float *VB2, const float *VB3)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(!VB1 && !VB2 && !VB3) { c->have_vb = false; return 0; }
+    if(!VB1 || !VB2 || !VB3) FAIL("set_velocity_bcs: give all three directions or none");
+    const float *src[3] = { VB1, VB2, VB3 };
+    for(int d = 0; d < 3; d++)
+    {
+        if(!c->VB[d]) CK(cudaMalloc(&c->VB[d], sizeof(float) * (size_t)L.g.nno));
+        CK(cudaMemcpyAsync(c->VB[d], src[d], sizeof(float) * (size_t)L.g.nno, cudaMemcpyHostToDevice, c->st));
+    }
+    SYNC(c);
+    c->have_vb = true;      // also when every value is zero here: the other subdomains of a run may carry the moving boundary
+    c->vb_dirty = true;
+    return 0;
+}
+int ccu_conform_velocity_bcs(ccu_ctx *c)
+{
+    if(!c) FAIL("null context");
+    Level &L = c->L[c->cfg.levmax];
+    if(!L.have_flags || !L.node) FAIL("conform_velocity_bcs: node flags missing");
+    if(!c->have_vb)
+    {
+        LAUNCH(c, bk_strip_u, cdiv(L.g.NS, 256), 256, L.g, L.flags, L.vec[CCU_VEC_U]);
+        return 0;
+    }
+    LAUNCH(c, bk_conform_vbcs, cdiv(L.g.nno, 256), 256, L.g, L.node, c->VB[0], c->VB[1], c->VB[2], L.vec[CCU_VEC_U]);
     return 0;
 }
 

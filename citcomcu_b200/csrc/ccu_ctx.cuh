@@ -122,6 +122,13 @@ struct ccu_ctx
     float *buoy = nullptr;         // [nno]
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
     double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces)
+    // imposed non-zero boundary velocities (E->VB): the K.VB term of get_elt_f and velocities_conform_bcs
+    float *VB[3] = { nullptr, nullptr, nullptr };   // [nno] natural order, finest level
+    bool have_vb = false, vb_dirty = false;
+    int *vb_slot = nullptr;        // [nel] slot of the element in vbEF, -1 = no flagged node with a non-zero VB
+    int *vb_elems = nullptr;       // [n_vb] the elements that have one
+    int n_vb = 0;
+    double *vbEF = nullptr;        // [24][n_vb] their -K.VB contributions
     double *eltK = nullptr;        // element-block scratch for the stiffness build
     size_t eltK_elems = 0;
     // energy step state (ccu_build_exact.cu, PG_timestep): finest level, natural node order

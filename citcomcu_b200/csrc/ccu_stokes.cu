@@ -135,6 +135,8 @@ void ccu_destroy(ccu_ctx *c)
         cudaFree(M.sendbuf); cudaFree(M.recvbuf);
     }
     cudaFree(c->forceEF); cudaFree(c->sdepv_oldU); cudaFree(c->sdepv_dU);
+    for(int d = 0; d < 3; d++) cudaFree(c->VB[d]);
+    cudaFree(c->vb_slot); cudaFree(c->vb_elems); cudaFree(c->vbEF);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }
@@ -262,6 +264,7 @@ int ccu_set_node_flags(ccu_ctx *c, int lev, const unsigned *node)
     CK(cudaMemcpyAsync(L.node, c->stage, sizeof(unsigned) * L.g.nno, cudaMemcpyDeviceToDevice, c->st));
     SYNC(c);
     L.have_flags = true;
+    if(lev == c->cfg.levmax) c->vb_dirty = true;      // which elements carry the K.VB force term depends on the flags
     return 0;
 }
 
@@ -1158,6 +1161,9 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     if(!c) FAIL("null context");
     Level &L = c->L[c->cfg.levmax];
     if(T && ccu_set_temperature(c, T)) return 1;
+    // the K.VB force term reads the viscosity as it stands BEFORE this call's update (Drive_solvers.c:107 comes ahead of :124);
+    // at the very first call that is the one common_initial_fields evaluated from the initial state (Instructions.c:1233)
+    if(c->have_vb && !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
     if(ccu_assemble_forces(c, buoyancy, nullptr)) return 1;
     if(rebuild)
     {
@@ -1177,7 +1183,8 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
         if(vec_h2d(c, L, U, L.vec[CCU_VEC_U])) return 1;
         CK(cudaMemcpyAsync(c->P, P, sizeof(double) * L.g.npno, cudaMemcpyHostToDevice, c->st));
     }
-    d_strip(c, L, L.vec[CCU_VEC_U]);            // velocities_conform_bcs with zero imposed velocities
+    if(c->have_vb) { if(ccu_conform_velocity_bcs(c)) return 1; }   // velocities_conform_bcs (Boundary_conditions.c:993)
+    else d_strip(c, L, L.vec[CCU_VEC_U]);       // the same with zero imposed velocities
     int steps = c->cfg.p_iterations;
     if(d_solve_Ahat_p_fhat(c, c->cfg.accuracy, &steps, residual_out, nullptr)) return 1;
     if(c->visc.sdepv)

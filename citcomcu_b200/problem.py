@@ -102,6 +102,9 @@ class CartesianProblem:
             augmented=float(g("aug_number", 0.0)), precondition=int(_on(g("precond", "off"))))
         self.rayleigh = f32(float(g("rayleigh")))
         self.topvbc, self.botvbc = int(g("topvbc", 0)), int(g("botvbc", 0))
+        # imposed boundary velocities (Instructions.c:980-992; the top x value is plate_velocity, Boundary_conditions.c:92)
+        self.plate_vel, self.topvby = f32(float(g("plate_velocity", 0.0))), f32(float(g("topvbyval", 0.0)))
+        self.botvbx, self.botvby = f32(float(g("botvbxval", 0.0))), f32(float(g("botvbyval", 0.0)))
         self.toptbc, self.bottbc = int(g("toptbc", 1)), int(g("bottbc", 1))
         self.toptbcval, self.bottbcval = f32(float(g("toptbcval", 0.0))), f32(float(g("bottbcval", 1.0)))
         if _on(g("periodicx", "off")) or _on(g("periodicy", "off")):
@@ -182,6 +185,17 @@ class CartesianProblem:
         X2 = np.broadcast_to(ys[:, None, None], (noy, nox, noz)).reshape(-1).astype(f32)
         X3 = np.broadcast_to(zs[None, None, :], (noy, nox, noz)).reshape(-1).astype(f32)
         return X1, X2, X3
+
+    def velocity_bcs(self):
+        """E->VB at levmax (velocity_boundary_conditions, Boundary_conditions.c:44-100) where a velocity flag reads it: the no-slip rows
+        are written last, so the lid / base value also holds on the wall edges; every other flagged dof is held at zero."""
+        nox, noy, noz = self.dims(self.levmax)
+        VB = [np.zeros((noy, nox, noz), dtype=np.float32) for _ in range(3)]
+        if self.topvbc == 1 and self.me_loc[2] == self.nproc[2] - 1:
+            VB[0][:, :, noz - 1], VB[1][:, :, noz - 1] = self.plate_vel, self.topvby
+        if self.botvbc == 1 and self.me_loc[2] == 0:
+            VB[0][:, :, 0], VB[1][:, :, 0] = self.botvbx, self.botvby
+        return [v.reshape(-1) for v in VB]
 
     # ---------------------------------------------------------------- boundary-condition flags
     def node_flags(self, lev):

@@ -207,6 +207,18 @@ class StokesContext:
                                            None if out is None else out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def set_velocity_bcs(self, VB1, VB2, VB3):
+        """E->VB: imposed boundary velocities per direction, [nno] in the reference's node order; None, None, None clears them."""
+        if VB1 is None and VB2 is None and VB3 is None:
+            check(self.lib.ccu_set_velocity_bcs(self._ctx, None, None, None))
+            return
+        v = [np.ascontiguousarray(a, dtype=np.float32) for a in (VB1, VB2, VB3)]
+        assert all(a.size == self.nno(self.levmax) for a in v)
+        check(self.lib.ccu_set_velocity_bcs(self._ctx, *[a.ctypes.data_as(C.c_void_p) for a in v]))
+
+    def conform_velocity_bcs(self):
+        check(self.lib.ccu_conform_velocity_bcs(self._ctx))
+
     def get_stiffness(self, lev):
         n = self.nno(lev) * 42
         ks = [np.empty(n, dtype=np.float32) for _ in range(3)]
@@ -663,6 +675,9 @@ def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, commu
         ctx.set_node_flags(lev, prob.node_flags(lev))
         ctx.set_coordinates(lev, *prob.coordinates(lev))
     ctx.build_geometry()
+    vb = prob.velocity_bcs()
+    if any(np.any(v != 0) for v in vb) or getattr(prob, "force_velocity_bcs", False):
+        ctx.set_velocity_bcs(*vb)
     if prob.nproc != (1, 1, 1) and agglomerate and communicator:
         gp = prob.global_problem()
         levs = [lev for lev in range(prob.levmin, prob.levmax) if gp.nno(lev) <= AGG_NODES]

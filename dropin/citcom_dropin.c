@@ -26,8 +26,7 @@
  * id once, after that the library does the halo sums and reductions over NCCL (ccu_comm_init).
  *
  * Unsupported configurations stop the run loudly (there is no CPU fallback): spherical geometry,
- * stress- or composition-dependent viscosity, viscosity smoothing, anisotropic viscosity, periodic side walls,
- * non-zero imposed velocities.
+ * composition-dependent viscosity, viscosity smoothing, anisotropic viscosity, periodic side walls.
  *
  * citcom_dropin_funcs.c (same library) binds the INNER functions of the path one by one (CCU_DROPIN_FUNCS).
  */
@@ -77,12 +76,6 @@ void ccu_dropin_init(struct All_variables *E)
 #endif
     if(E->mesh.periodic_x || E->mesh.periodic_y) die("periodic side walls are not on the device path");
     if(!E->control.NMULTIGRID) die("Solver=multigrid is required");
-    {
-        int n, d;
-        for(d = 1; d <= 3; d++)
-            for(n = 1; n <= E->lmesh.nno; n++)
-                if(E->VB[d][n] != 0.0) die("non-zero imposed velocities (VB) are not on the device path");
-    }
     memset(&cfg, 0, sizeof cfg);
     cfg.levmin = E->mesh.levmin; cfg.levmax = E->mesh.levmax;
     for(lev = cfg.levmin; lev <= cfg.levmax; lev++)
@@ -123,6 +116,14 @@ void ccu_dropin_init(struct All_variables *E)
                               E->viscosity.T, E->viscosity.Z, E->viscosity.MIN, E->viscosity.min_value, E->viscosity.MAX,
                               E->viscosity.max_value, E->viscosity.smooth_cycles));
     CCU(ccu_set_material(g_ctx, E->mat + 1));
+    {   /* imposed boundary velocities: uploaded when any subdomain has a non-zero one (E->VB, Boundary_conditions.c) */
+        int n, d, any = 0, all = 0;
+        for(d = 1; d <= 3 && !any; d++)
+            for(n = 1; n <= E->lmesh.nno && !any; n++) any = E->VB[d][n] != 0.0;
+        all = any;
+        if(E->parallel.nproc > 1) MPI_Allreduce(&any, &all, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
+        if(all) CCU(ccu_set_velocity_bcs(g_ctx, E->VB[1] + 1, E->VB[2] + 1, E->VB[3] + 1));
+    }
     if(E->viscosity.SDEPV)
         CCU(ccu_set_sdepv(g_ctx, 1, E->viscosity.sdepv_rheology, E->viscosity.sdepv_expt, E->viscosity.sdepv_trns, E->viscosity.sdepv_misfit,
                           E->viscosity.sdepv_iter_damp, E->monitor.max_sdep_visc_iter, E->viscosity.sdepv_start_from_newtonian,

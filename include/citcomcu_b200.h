@@ -140,6 +140,11 @@ int ccu_get_system_viscosity(ccu_ctx *ctx);
 int ccu_construct_stiffness_B_matrix(ccu_ctx *ctx, int augmented_Lagr, double augmented, int precondition);
 /* assemble_forces (Element_calculations.c:74): buoyancy[nno] (NULL = resident) -> resident F (CCU_VEC_F); F_out optional */
 int ccu_assemble_forces(ccu_ctx *ctx, const float *buoyancy, double *F_out /*[neq] or NULL*/);
+/* E->VB (global_defs.h:1038): imposed boundary velocities, [nno] per direction in the reference's node order (all NULL clears them).
+ * Non-zero values at flagged nodes enter the force vector -- the K.VB term of get_elt_f, Element_calculations.c:1038-1063, with the
+ * viscosity as it stands when assemble_forces runs -- and the velocity vector (velocities_conform_bcs, Boundary_conditions.c:993). */
+int ccu_set_velocity_bcs(ccu_ctx *ctx, const float *VB1, const float *VB2, const float *VB3);
+int ccu_conform_velocity_bcs(ccu_ctx *ctx);      /* velocities_conform_bcs on the resident U */
 /* read-back in the reference's layouts (tests / drop-in diagnostics) */
 int ccu_get_stiffness(ccu_ctx *ctx, int lev, float *eqn_k1, float *eqn_k2, float *eqn_k3 /*[nno*42]*/, double *BI /*[neq] or NULL*/);
 enum { CCU_ARR_TWW = 0, CCU_ARR_MASS = 1, CCU_ARR_ECO_SIZE = 2, CCU_ARR_ELT_DEL = 3, CCU_ARR_BPI = 4, CCU_ARR_EVI = 5 };

@@ -69,6 +69,10 @@ static void dump_level_arrays(struct All_variables *E)
                          E->lmesh.ELZ[lev], nno, nel, neq, npno };
         snprintf(nm, sizeof nm, "L%d_dims", lev); DUMP_I32(nm, dims, 10);
         snprintf(nm, sizeof nm, "L%d_NODE", lev); DUMP_U32(nm, E->NODE[lev] + 1, nno);
+        if(lev == E->mesh.levmax)
+        {   /* imposed boundary velocities (finest level only, global_defs.h:1038) */
+            DUMP_F32("VB1", E->VB[1] + 1, nno); DUMP_F32("VB2", E->VB[2] + 1, nno); DUMP_F32("VB3", E->VB[3] + 1, nno);
+        }
         if(!E->Eqn_k1[lev] || !E->Node_map[lev]) continue;   /* operator lives on the device (drop-in preloaded) */
         snprintf(nm, sizeof nm, "L%d_Eqn_k1", lev); DUMP_F32(nm, E->Eqn_k1[lev], (size_t)nno * 42);
         snprintf(nm, sizeof nm, "L%d_Eqn_k2", lev); DUMP_F32(nm, E->Eqn_k2[lev], (size_t)nno * 42);

@@ -113,3 +113,27 @@ def test_rheologies_and_viscosity_coarsening_modes(rheol, smooth):
             ref = d[f"L{lev}_{nm}"]
             assert np.allclose(k, ref, rtol=1e-6, atol=1e-6 * np.abs(ref).max()), (lev, nm)
     ctx.close()
+
+
+def test_imposed_velocity_force_term():
+    """assemble_forces with non-zero E->VB: the -K.VB term of get_elt_f (Element_calculations.c:1038-1063) against the reference's
+    F at steps 0 and 1 (step k is assembled with the viscosity of the update before it)."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, accuracy=1e-5, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_vbF_"), nsteps=1)[0][0]
+    assert np.abs(d["VB1"]).max() == 40.0 and np.abs(d["VB2"]).max() == 15.0
+    ctx = build_ctx(d, 0, 0.0)
+    lm = d.levmax
+    ctx.set_velocity_bcs(d["VB1"], d["VB2"], d["VB3"])
+    plain = ctx.assemble_forces(d["s0_buoyancy"])              # viscosity of build_ctx (isoviscous): not the reference's
+    ctx.set_element_viscosity(lm, d["s0_EVI"])
+    for k in (0, 1):
+        F = ctx.assemble_forces(d[f"s{k}_buoyancy"])
+        ref = d[f"s{k}_F"]
+        assert np.abs(F - ref).max() < 1e-12 * np.abs(ref).max(), (k, np.abs(F - ref).max() / np.abs(ref).max())
+    assert np.abs(plain - d["s0_F"]).max() > 1e-3 * np.abs(d["s0_F"]).max()
+    ctx.close()

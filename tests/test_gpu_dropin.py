@@ -201,6 +201,36 @@ def test_stress_dependent_viscosity_loop(rheology, damp, monkeypatch):
     assert np.abs(r["s0_EVI"] / newt["s0_EVI"] - 1).max() > 0.05
 
 
+@pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
+def test_imposed_plate_velocity(energy, monkeypatch):
+    """topvbc=1 with a non-zero plate velocity: E->VB enters U (velocities_conform_bcs) and F (the K.VB term of get_elt_f,
+    Element_calculations.c:1038-1063, evaluated with the viscosity of the previous update) on the device."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    # accuracy: the hot, weak bottom layer under a driven lid is poorly conditioned -- the two arms (and the reference against itself
+    # at a tighter tolerance) differ there by about 1000 x accuracy (measured: 5.5e-3, 4e-4, 3e-5 of |U| at 1e-5, 1e-6, 1e-7), so the
+    # comparison runs at 1e-7 and allows 3e-4
+    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=4, accuracy=1e-7, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
+    nsteps = 2
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", str(energy))
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_vbref_"), nsteps=nsteps)
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_vbgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "citcomcu_b200 drop-in: Stokes solve on CUDA device" in err
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    free = po.run_harness(inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, accuracy=1e-5), tempfile.mkdtemp(prefix="ccu_vbfree_"), nsteps=0)[0][0]
+    assert np.abs(r["VB1"]).max() == 40.0 and np.abs(r["VB2"]).max() == 15.0
+    # the plate drives the flow: nothing like the free-slip solution of the same state
+    assert np.linalg.norm(r["s0_U"] - free["s0_U"]) > 0.5 * np.linalg.norm(r["s0_U"])
+    for k in range(nsteps + 1):
+        U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+        assert np.linalg.norm(Ug - U) < 3e-4 * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+        sr, sg = r[f"s{k}_scalars"], g[f"s{k}_scalars"]
+        assert abs(sg[1] - sr[1]) <= 1e-3 * abs(sr[1]) + 1e-12, ("timestep", k)
+    assert acc == 1e-7
+
+
 @pytest.mark.parametrize("funcs", ["solve_Ahat_p_fhat", "n_assemble_del2_u,assemble_div_u,assemble_grad_p,gauss_seidel,global_vdot,global_pdot"])
 def test_regional_sphere_solver_on_device(funcs, monkeypatch):
     """BASELINE config 4 geometry (examples/input1's regional-spherical block): the operator is assembled by the reference's host code

@@ -31,3 +31,23 @@ def test_setup_matches_reference(name):
     assert np.array_equal(P.material(), d["s0_mat"])
     b = P.buoyancy(d["s0_T"])
     assert np.allclose(b, d["s0_buoyancy"], rtol=0, atol=2e-6 * np.abs(d["s0_buoyancy"]).max())
+
+
+def test_imposed_velocities_match_reference(oracle_built):
+    """E->VB (no-slip lid and base with non-zero values) where a velocity flag reads it, and the flags of that configuration."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import VBX, VBY, VBZ
+    if not po.have_ref():
+        pytest.skip("needs the reference build (oracle/_ref)")
+    txt = inputfile.tdepv_box(8, 8, 8, 2, maxstep=1, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, botvbc=1, botvbxval=3.0, botvbyval=7.0)
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_vbsetup_"), nsteps=0)[0][0]
+    P = CartesianProblem(txt)
+    lm = d.levmax
+    node = d[f"L{lm}_NODE"]
+    assert np.array_equal(P.node_flags(lm) & np.uint32(BC_MASK), node & np.uint32(BC_MASK))
+    for vb, nm, bit in zip(P.velocity_bcs(), ("VB1", "VB2", "VB3"), (VBX, VBY, VBZ)):
+        m = (node & np.uint32(bit)) != 0
+        assert np.array_equal(vb[m], d[nm][m]), nm
+        assert np.abs(d[nm][m]).max() > 0 or nm == "VB3"
