@@ -149,6 +149,276 @@ __global__ void __launch_bounds__(128) bk_elt_geometry(const CcuGeom g, const fl
     }
 }
 
+
+// ---------------------------------------------------------------- regional-spherical geometry (E->control.Rsphere)
+// XX holds the CARTESIAN coordinates of the nodes, SXX their (theta, phi, r).  Velocity components at a node are (u_theta, u_phi,
+// u_r) in that node's own basis; the operators project them on the basis of the integration point (the Cc / Ccx matrices of
+// construct_c3x3matrix_el, Size_does_matter.c:253-440).  The reference evaluates Cc once per radial column of elements
+// ((el-1) % ELZ == 0) and reuses it up the column -- the colatitude / longitude of an integration point do not depend on the
+// radius in exact arithmetic, but the float node coordinates make it differ by ~1e-8 -- and the kernels do the same (sph_column_point_trig).
+struct SphTrig { double ct, st, cf, sf; };
+__device__ __forceinline__ SphTrig sph_trig(double tt, double ff) { SphTrig t; t.ct = cos(tt); t.cf = cos(ff); t.st = sin(tt); t.sf = sin(ff); return t; }
+__device__ __forceinline__ double sph_myatan(double y, double x) { double fi = atan2(y, x); if(fi < 0.0) fi += 2 * 3.14159265358979323846; return fi; }
+// point = sum_a X_a N_a   (N: master-element shape functions at the integration point, stride between nodes `sn`)
+__device__ __forceinline__ void sph_point(const float X[3][8], const double *N, int sn, double x[3])
+{
+    for(int d = 0; d < 3; d++)
+    {
+        double v = 0.0;
+        for(int i = 0; i < 8; i++) v += X[d][i] * N[i * sn];
+        x[d] = v;
+    }
+}
+// get_rtf / form_rtf_bc (Size_does_matter.c:182-250): rtf = (theta, phi, 1/r)
+__device__ __forceinline__ void sph_rtf(const double x[3], double &th, double &ph, double &ri)
+{
+    ri = 1.0 / sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    th = acos(x[2] * ri);
+    ph = sph_myatan(x[1], x[0]);
+}
+// basis of the integration point as construct_c3x3matrix_el forms it (tt = acos(x3 / rr))
+__device__ __forceinline__ SphTrig sph_point_trig(const double x[3])
+{
+    const double rr = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    return sph_trig(acos(x[2] / rr), sph_myatan(x[1], x[0]));
+}
+// derivatives with respect to (theta, phi, r) from the Cartesian ones (get_global_shape_fn sphere branch, :111-126)
+__device__ __forceinline__ void sph_rotate_gnx(const double x[3], float gnx[3][8])
+{
+    double th, ph, ri;
+    sph_rtf(x, th, ph, ri);
+    double bc[3][3];
+    bc[0][0] = x[2] * cos(ph); bc[0][1] = x[2] * sin(ph); bc[0][2] = -sin(th) / ri;
+    bc[1][0] = -x[1];          bc[1][1] = x[0];           bc[1][2] = 0.0;
+    bc[2][0] = x[0] * ri;      bc[2][1] = x[1] * ri;      bc[2][2] = x[2] * ri;
+    for(int j = 0; j < 8; j++)
+    {
+        const float g0 = gnx[0][j], g1 = gnx[1][j], g2 = gnx[2][j];
+        for(int d = 0; d < 3; d++) gnx[d][j] = (float)(bc[d][0] * g0 + bc[d][1] * g1 + bc[d][2] * g2);
+    }
+}
+// rows of the point basis u (theta-hat, phi-hat, r-hat) and their theta / phi derivatives, all dotted with row i of the node basis ua:
+//   c[m]  = Cc(m+1, i)        = ua[i] . u[m]
+//   c1[m] = Ccx(m+1, i, 1)    = ua[i] . d u[m] / d theta
+//   c2[m] = Ccx(m+1, i, 2)    = ua[i] . d u[m] / d phi
+__device__ __forceinline__ void sph_cc(const SphTrig &P, const SphTrig &A, int i, double c[3], double c1[3], double c2[3])
+{
+    double ua[3];
+    if(i == 0) { ua[0] = A.ct * A.cf; ua[1] = A.ct * A.sf; ua[2] = -A.st; }
+    else if(i == 1) { ua[0] = -A.sf; ua[1] = A.cf; ua[2] = 0.0; }
+    else { ua[0] = A.st * A.cf; ua[1] = A.st * A.sf; ua[2] = A.ct; }
+    const double u[3][3] = { { P.ct * P.cf, P.ct * P.sf, -P.st }, { -P.sf, P.cf, 0.0 }, { P.st * P.cf, P.st * P.sf, P.ct } };
+    const double ux1[3][3] = { { -P.st * P.cf, -P.st * P.sf, -P.ct }, { 0.0, 0.0, 0.0 }, { P.ct * P.cf, P.ct * P.sf, -P.st } };
+    const double ux2[3][3] = { { -P.ct * P.sf, P.ct * P.cf, 0.0 }, { -P.cf, -P.sf, 0.0 }, { -P.st * P.sf, P.st * P.cf, 0.0 } };
+    for(int m = 0; m < 3; m++)
+    {
+        c[m] = ua[0] * u[m][0] + ua[1] * u[m][1] + ua[2] * u[m][2];
+        c1[m] = ua[0] * ux1[m][0] + ua[1] * ux1[m][1] + ua[2] * ux1[m][2];
+        c2[m] = ua[0] * ux2[m][0] + ua[1] * ux2[m][1] + ua[2] * ux2[m][2];
+    }
+}
+// get_ba (Element_calculations.c:300-348), one (node, component, point): the six strain-rate rows
+__device__ __forceinline__ void sph_ba(const SphTrig &P, const SphTrig &A, int i, double gnx0, double gnx1, double gnx2, double shp,
+                                       double ra, double si, double ct, double ba[6])
+{
+    double c[3], c1[3], c2[3];
+    sph_cc(P, A, i, c, c1, c2);
+    const double cc1 = c[0], cc2 = c[1], cc3 = c[2];
+    ba[0] = ((gnx0 * cc1 + shp * c1[0]) + shp * cc3) * ra;
+    ba[1] = (shp * cc1 * ct + shp * cc3 + (gnx1 * cc2 + shp * c2[1]) * si) * ra;
+    ba[2] = gnx2 * cc3;
+    ba[3] = ((gnx0 * cc2 + shp * c1[1]) - shp * cc2 * ct + (gnx1 * cc1 + shp * c2[0]) * si) * ra;
+    ba[4] = gnx2 * cc1 + (gnx0 * cc3 + shp * (c1[2] - cc1)) * ra;
+    ba[5] = gnx2 * cc2 + ((gnx1 * cc3 + shp * c2[2]) * si - shp * cc2) * ra;
+}
+// the reference evaluates Cc / Ccx on the FIRST element of a radial column ((el-1) % ELZ == 0) and keeps them for the elements above
+// (static struct CC in get_elt_k / get_elt_g / get_elt_f): the point basis comes from that element's (float) coordinates
+__device__ __forceinline__ SphTrig sph_column_point_trig(const CcuGeom &g, const float *__restrict__ XX, int ey, int ex, int ez, const float X[3][8],
+                                                         const double *N, int sn)
+{
+    double x[3];
+    if(ez == 0) { sph_point(X, N, sn, x); return sph_point_trig(x); }
+    float X0[3][8];
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = (0 + c_OFFS[a][0]) + g.noz * ((ex + c_OFFS[a][1]) + g.nox * (ey + c_OFFS[a][2]));
+        for(int e = 0; e < 3; e++) X0[e][a - 1] = XX[(size_t)e * g.nno + n];
+    }
+    sph_point(X0, N, sn, x);
+    return sph_point_trig(x);
+}
+__device__ __forceinline__ void load_elt_sph(const CcuGeom &g, const float *__restrict__ SXX, int ey, int ex, int ez, SphTrig A[8])
+{
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        A[a - 1] = sph_trig((double)SXX[n], (double)SXX[(size_t)g.nno + n]);
+    }
+}
+// mass_matrix ECO.size (Size_does_matter.c:661-680) and get_elt_g (Element_calculations.c:896-920) for Rsphere: overwrite what
+// bk_elt_geometry wrote for these two arrays (TWW / MASS use the Jacobian of the Cartesian coordinates in both geometries)
+__global__ void __launch_bounds__(128) bk_elt_geometry_sph(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ SXX, float *eco, float *elt_del)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8], gnx[3][8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    float S[3][8];
+    for(int a = 1; a <= 8; a++)
+    {
+        const int n = elt_node(g, ey, ex, ez, a);
+        for(int d = 0; d < 3; d++) S[d][a - 1] = SXX[(size_t)d * g.nno + n];
+    }
+    {
+        double centre[3];
+        for(int i = 0; i < 3; i++)
+        {
+            double v = 0.0;
+            for(int a = 0; a < 8; a++) v += X[i][a];
+            centre[i] = v / 8;
+        }
+        const float c3 = (float)sqrt(centre[0] * centre[0] + centre[1] * centre[1] + centre[2] * centre[2]);
+        const float c1 = (float)acos(centre[2] / c3);
+        float d1 = (float)fmax(fabs((double)(S[0][2] - S[0][0])), fabs((double)(S[0][1] - S[0][3])));
+        eco[(size_t)e * 3 + 0] = d1 * c3;
+        float d2 = (float)fmax(fabs((double)(S[1][2] - S[1][0])), fabs((double)(S[1][1] - S[1][3])));
+        eco[(size_t)e * 3 + 1] = (float)((double)(d2 * c3) * sin((double)c1));
+        const float d3 = (float)(0.25 * (double)(S[2][4] + S[2][5] + S[2][6] + S[2][7] - S[2][0] - S[2][1] - S[2][2] - S[2][3]));
+        eco[(size_t)e * 3 + 2] = (float)sqrt((double)(d3 * d3));
+    }
+    {
+        const float gdap = (float)gp_geom(X, c_sh.Nxp, 8, 1, gnx);
+        double x[3];
+        sph_point(X, c_sh.Np, 1, x);
+        sph_rotate_gnx(x, gnx);
+        const double temp_p = (double)(8.0f * gdap);
+        double th, ph, ra;
+        sph_rtf(x, th, ph, ra);
+        const double si = 1.0 / sin(th), ct = cos(th) * si;
+        const SphTrig P = sph_column_point_trig(g, XX, ey, ex, ez, X, c_sh.Np, 1);
+        for(int a = 0; a < 8; a++)
+        {
+            const SphTrig A = sph_trig((double)S[0][a], (double)S[1][a]);
+            const double shp = c_sh.Np[a];
+            for(int i = 0; i < 3; i++)
+            {
+                double c[3], c1[3], c2[3];
+                sph_cc(P, A, i, c, c1, c2);
+                const double xi = gnx[2][a] * c[2] + 2.0 * ra * shp * c[2] +
+                                  ra * (gnx[0][a] * c[0] + shp * c1[0] + ct * shp * c[0] + si * (gnx[1][a] * c[1] + shp * c2[1]));
+                elt_del[(size_t)e * 24 + 3 * a + i] = (float)(-xi * temp_p);
+            }
+        }
+    }
+}
+// get_elt_k, Rsphere branch (Element_calculations.c:249-260): bdbmu[i][j] = sum_k W[k] (2 (ba1 ba1 + ba2 ba2 + ba3 ba3) + ba4 ba4 + ba5 ba5 + ba6 ba6)
+__global__ void __launch_bounds__(64) bk_elt_k_sph(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ SXX, const float *__restrict__ EVI,
+                                                  const int e_begin, const int e_count, double *blocks)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= e_count) return;
+    const int e = e_begin + t;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    SphTrig A[8], P[8];
+    load_elt_sph(g, SXX, ey, ex, ez, A);
+    float gn[8][3][8];        // [gauss point][d][node], derivatives with respect to (theta, phi, r)
+    double W[8], ra[8], si[8], ct[8];
+    for(int k = 0; k < 8; k++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gn[k]);
+        double x[3], th, ph;
+        sph_point(X, c_sh.Nv + k, 8, x);
+        sph_rotate_gnx(x, gn[k]);
+        sph_rtf(x, th, ph, ra[k]);
+        si[k] = 1.0 / sin(th);
+        ct[k] = cos(th) * si[k];
+        P[k] = sph_column_point_trig(g, XX, ey, ex, ez, X, c_sh.Nv + k, 8);
+        W[k] = (double)(1.0f * gda * EVI[(size_t)e * 8 + k]);
+    }
+    int pair = 0;
+    for(int a = 0; a < 8; a++)
+        for(int b = a; b < 8; b++, pair++)
+        {
+            double bd[3][3];
+            for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) bd[i][j] = 0.0;
+            for(int k = 0; k < 8; k++)
+            {
+                double bb[3][6];
+                for(int j = 0; j < 3; j++) sph_ba(P[k], A[b], j, gn[k][0][b], gn[k][1][b], gn[k][2][b], c_sh.Nv[8 * b + k], ra[k], si[k], ct[k], bb[j]);
+                for(int i = 0; i < 3; i++)
+                {
+                    double aa[6];
+                    sph_ba(P[k], A[a], i, gn[k][0][a], gn[k][1][a], gn[k][2][a], c_sh.Nv[8 * a + k], ra[k], si[k], ct[k], aa);
+                    for(int j = 0; j < 3; j++)
+                        bd[i][j] += W[k] * (2.0 * (aa[0] * bb[j][0] + aa[1] * bb[j][1] + aa[2] * bb[j][2]) + aa[3] * bb[j][3] + aa[4] * bb[j][4] + aa[5] * bb[j][5]);
+                }
+            }
+            for(int i = 0; i < 3; i++)
+                for(int j = 0; j < 3; j++) blocks[(size_t)(pair * 9 + 3 * i + j) * e_count + t] = bd[i][j];
+        }
+}
+// get_elt_f, Rsphere branch (Element_calculations.c:1072-1086): the radial body force projected on each node's own basis
+__global__ void __launch_bounds__(128) bk_forces_elt_sph(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ SXX,
+                                                        const float *__restrict__ buoy, double *EF)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8], gnx[3][8], force[8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    SphTrig A[8];
+    load_elt_sph(g, SXX, ey, ex, ez, A);
+    for(int q = 1; q <= 8; q++) force[q - 1] = buoy[elt_node(g, ey, ex, ez, q)];
+    double ef[24];
+    for(int p = 0; p < 24; p++) ef[p] = 0.0;
+    for(int q = 0; q < 8; q++)
+    {
+        double fg = 0.0;
+        for(int kk = 0; kk < 8; kk++) fg += (double)force[kk] * c_sh.Nv[8 * kk + q];
+        const float gda = (float)gp_geom(X, c_sh.Nxv + q, 64, 8, gnx);
+        const SphTrig P = sph_column_point_trig(g, XX, ey, ex, ez, X, c_sh.Nv + q, 8);
+        for(int a = 0; a < 8; a++)
+            for(int i = 0; i < 3; i++)
+            {
+                double c[3], c1[3], c2[3];
+                sph_cc(P, A[a], i, c, c1, c2);
+                ef[3 * a + i] += fg * c_sh.Nv[8 * a + q] * gda * 1.0f * c[2];
+            }
+    }
+    for(int p = 0; p < 24; p++) EF[(size_t)p * g.nel + e] = ef[p];
+}
+__global__ void __launch_bounds__(128) bk_forces_gather_sph(const CcuGeom g, const double *__restrict__ EF, const unsigned char *__restrict__ flags, double *F)
+{
+    const int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= g.nno) return;
+    const int k = n % g.noz, j = (n / g.noz) % g.nox, i = n / (g.noz * g.nox);
+    double f[3] = { 0.0, 0.0, 0.0 };
+    for(int ey = i - 1; ey <= i; ey++)
+    {
+        if(ey < 0 || ey >= g.ely) continue;
+        for(int ex = j - 1; ex <= j; ex++)
+        {
+            if(ex < 0 || ex >= g.elx) continue;
+            for(int ez = k - 1; ez <= k; ez++)
+            {
+                if(ez < 0 || ez >= g.elz) continue;
+                const int a = LUT[k - ez][j - ex][i - ey] - 1;
+                const size_t el = (size_t)(ez + g.elz * (ex + g.elx * ey));
+                for(int d = 0; d < 3; d++) f[d] += EF[(size_t)(3 * a + d) * g.nel + el];
+            }
+        }
+    }
+    const int s = ccu_sidx(g, i, j, k);
+    const unsigned char fl = flags[s];
+    F[s] = (fl & CCU_F_VBX) ? 0.0 : f[0];
+    F[(size_t)g.NS + s] = (fl & CCU_F_VBY) ? 0.0 : f[1];
+    F[2 * (size_t)g.NS + s] = (fl & CCU_F_VBZ) ? 0.0 : f[2];
+}
+
 // MASS[node] = 1 / sum over its elements (ascending) of TWW   (float accumulation, Size_does_matter.c:718,739)
 __global__ void __launch_bounds__(128) bk_mass(const CcuGeom g, const double *__restrict__ TWWd, float *MASS)
 {
@@ -1484,6 +1754,25 @@ int ccu_set_coordinates(ccu_ctx *c, int lev, const float *X1, const float *X2, c
     return 0;
 }
 
+// E->SXX[lev][1..3] (theta, phi, r): switches the context to regional-spherical geometry (E->control.Rsphere); ccu_set_coordinates
+// then carries the CARTESIAN coordinates of the nodes (E->XX), as in the reference.  Every level needs both before ccu_build_geometry.
+int ccu_set_spherical_coordinates(ccu_ctx *c, int lev, const float *S1, const float *S2, const float *S3)
+{
+    if(ccu_check_lev(c, lev)) return 2;
+    Level &L = c->L[lev];
+    const size_t n = (size_t)L.g.nno;
+    if(!L.SXX) CK(cudaMalloc(&L.SXX, sizeof(float) * 3 * n));
+    CK(cudaMemcpyAsync(L.SXX, S1, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.SXX + n, S2, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(L.SXX + 2 * n, S3, sizeof(float) * n, cudaMemcpyHostToDevice, c->st));
+    SYNC(c);
+    L.have_sxx = true;
+    c->rsphere = true;
+    return 0;
+}
+// the entry points that only know the Cartesian element routines
+#define CART_ONLY(c, what) do { if((c)->rsphere) FAIL(what ": Cartesian geometry only on the device (regional-spherical runs keep the reference's host routine)"); } while(0)
+
 int ccu_build_geometry(ccu_ctx *c)
 {
     if(!c) FAIL("null context");
@@ -1494,6 +1783,11 @@ int ccu_build_geometry(ccu_ctx *c)
         if(!L.have_xx) FAIL("build_geometry: coordinates missing");
         if(ccu_ensure_stage(c, sizeof(double) * 8 * (size_t)L.g.nel)) return 1;
         LAUNCH(c, bk_elt_geometry, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.TWW, (double *)c->stage, L.eco, L.elt_del);
+        if(c->rsphere)
+        {
+            if(!L.have_sxx) FAIL("build_geometry: spherical coordinates missing on a level (ccu_set_spherical_coordinates)");
+            LAUNCH(c, bk_elt_geometry_sph, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.SXX, L.eco, L.elt_del);
+        }
         ccu_elt_del_changed(c, lev);
         LAUNCH(c, bk_mass, cdiv(L.g.nno, 128), 128, L.g, (const double *)c->stage, L.MASS);
         if(ccu_halo_sum_nodal(c, lev, L.MASS)) return 1;                  // exchange_node_f20 (Size_does_matter.c:733)
@@ -1682,7 +1976,12 @@ int ccu_construct_stiffness_B_matrix(ccu_ctx *c, int augmented_Lagr, double augm
             int ey1 = ey0 + planes; if(ey1 > g.ely) ey1 = g.ely;
             int i1 = (ey1 == g.ely) ? g.noy : ey1;          // nodes of plane ey1 would need element plane ey1
             const int e_count = (int)(per_plane * (ey1 - ey0));
-            LAUNCH(c, bk_elt_k, cdiv(e_count, 64), 64, g, L.XX, L.EVI, (int)(per_plane * ey0), e_count, c->eltK);
+            if(c->rsphere)
+            {
+                if(!L.have_sxx) FAIL("construct_stiffness_B_matrix: spherical coordinates missing");
+                LAUNCH(c, bk_elt_k_sph, cdiv(e_count, 64), 64, g, L.XX, L.SXX, L.EVI, (int)(per_plane * ey0), e_count, c->eltK);
+            }
+            else LAUNCH(c, bk_elt_k, cdiv(e_count, 64), 64, g, L.XX, L.EVI, (int)(per_plane * ey0), e_count, c->eltK);
             const size_t nn = (size_t)(i1 - i0) * g.nox * g.noz;
             LAUNCH(c, bk_node_ks, cdiv(nn, 64), 64, g, i0, i1, ey0, e_count, c->eltK, L.elt_del, L.EVI, L.flags, augmented_Lagr, augmented, L.K, L.BI, c->multi() ? 0 : 1);
             i0 = i1;
@@ -1718,9 +2017,19 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
     Level &L = c->L[c->cfg.levmax];
     if(!L.have_xx || !L.have_flags) FAIL("assemble_forces: coordinates/flags missing");
     if(buoyancy) CK(cudaMemcpyAsync(c->buoy, buoyancy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyHostToDevice, c->st));
-    if(!c->forceEF) CK(cudaMalloc(&c->forceEF, sizeof(double) * 8 * (size_t)L.g.nel));
-    LAUNCH(c, bk_forces_elt, cdiv(L.g.nel, 128), 128, L.g, L.XX, c->buoy, c->forceEF);
-    LAUNCH(c, bk_forces_gather, cdiv(L.g.nno, 128), 128, L.g, c->forceEF, L.flags, L.vec[CCU_VEC_F]);
+    if(!c->forceEF) CK(cudaMalloc(&c->forceEF, sizeof(double) * (c->rsphere ? 24 : 8) * (size_t)L.g.nel));
+    if(c->rsphere)
+    {
+        if(!L.have_sxx) FAIL("assemble_forces: spherical coordinates missing");
+        if(c->have_vb) FAIL("assemble_forces: imposed non-zero velocities are Cartesian only on the device");
+        LAUNCH(c, bk_forces_elt_sph, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.SXX, c->buoy, c->forceEF);
+        LAUNCH(c, bk_forces_gather_sph, cdiv(L.g.nno, 128), 128, L.g, c->forceEF, L.flags, L.vec[CCU_VEC_F]);
+    }
+    else
+    {
+        LAUNCH(c, bk_forces_elt, cdiv(L.g.nel, 128), 128, L.g, L.XX, c->buoy, c->forceEF);
+        LAUNCH(c, bk_forces_gather, cdiv(L.g.nno, 128), 128, L.g, c->forceEF, L.flags, L.vec[CCU_VEC_F]);
+    }
     if(c->have_vb)
     {
         if(!L.have_evi || !L.node) FAIL("assemble_forces: the imposed-velocity term needs the viscosity as it stands (ccu_get_system_viscosity) and the node flags");
@@ -1952,6 +2261,7 @@ int ccu_set_phase_params(ccu_ctx *c, float zlm, float z410, float Ra_670, float 
 int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fas410_out, float *transT_out /*[2]: 670, 410*/)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "phase_change");
     if(ensure_energy(c)) return 1;
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
@@ -1988,6 +2298,7 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
 int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
 {   // (heating_latent: ccu_get_heating_latent)
     if(!c) FAIL("null context");
+    CART_ONLY(c, "process_heating");
     if(ensure_energy(c)) return 1;
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
@@ -2093,6 +2404,7 @@ static int std_timestep(ccu_ctx *c, float *dt)
 int ccu_std_timestep(ccu_ctx *c, float *dt_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "std_timestep");
     if(ensure_energy(c)) return 1;
     return std_timestep(c, dt_out);
 }
@@ -2118,6 +2430,7 @@ static int energy_ready(ccu_ctx *c)
 int ccu_pg_solver(ccu_ctx *c, float *DTdot_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "pg_solver");
     if(ensure_energy(c) || energy_ready(c)) return 1;
     if(pg_solver(c)) return 1;
     if(DTdot_out) CK(cudaMemcpyAsync(DTdot_out, c->en.DTdot, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nno, cudaMemcpyDeviceToHost, c->st));
@@ -2134,6 +2447,7 @@ static int tmax(ccu_ctx *c, float *out)
 int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_interior_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "PG_timestep");
     if(ensure_energy(c) || energy_ready(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2181,6 +2495,7 @@ int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_i
 int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "thermal_buoyancy");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2298,6 +2613,7 @@ __global__ void __launch_bounds__(128) st_topo(const CcuGeom g, const float *__r
 int ccu_get_stress_topo(ccu_ctx *c, float *S_out, float *tpg_out, float *tpgb_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "get_stress / get_STD_topo");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2351,6 +2667,7 @@ __global__ void __launch_bounds__(128) ek_layer_finish(const int noz, const doub
 int ccu_averages(ccu_ctx *c, float *vrms_out, float *visc_out, float *C_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "averages");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2400,6 +2717,7 @@ int ccu_averages(ccu_ctx *c, float *vrms_out, float *visc_out, float *C_out)
 int ccu_heat_flux(ccu_ctx *c, float *Nut_out, float *Nub_out)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "heat_flux");
     if(ensure_energy(c) || energy_ready(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2440,6 +2758,7 @@ int ccu_markers_setup(ccu_ctx *c, int capacity, int markers_per_ele, int rnoz, c
                       const int *RG3, const double *XG1, const double *XG2, const unsigned *Element, float Acomp)
 {
     if(!c) FAIL("null context");
+    CART_ONLY(c, "marker advection");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &M = c->mk;

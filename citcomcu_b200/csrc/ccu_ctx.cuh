@@ -44,7 +44,9 @@ struct Level
     double *BPI = nullptr;
     double *vec[CCU_VEC_COUNT] = { nullptr };
     // operator construction (ccu_build.cu)
-    float *XX = nullptr;          // [3][nno] node coordinates, natural order (E->XX[lev][1..3])
+    float *XX = nullptr;          // [3][nno] node coordinates, natural order (E->XX[lev][1..3]); Cartesian also for Rsphere
+    float *SXX = nullptr;         // [3][nno] (theta, phi, r) of the nodes, Rsphere only (E->SXX[lev][1..3])
+    bool have_sxx = false;
     float *EVI = nullptr;         // [nel*8] viscosity at Gauss points
     unsigned *node = nullptr;     // [nno] raw NODE flags, natural order
     // shared-memory resident bottom smoother (ccu_k_relax_smem): compact tables, built on first use
@@ -121,7 +123,8 @@ struct ccu_ctx
     float *T = nullptr;            // [nno] temperature, natural order, finest level
     float *buoy = nullptr;         // [nno]
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
-    double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces)
+    double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces); [24][nel] for Rsphere
+    bool rsphere = false;          // regional-spherical geometry (ccu_set_spherical_coordinates)
     // imposed non-zero boundary velocities (E->VB): the K.VB term of get_elt_f and velocities_conform_bcs
     float *VB[3] = { nullptr, nullptr, nullptr };   // [nno] natural order, finest level
     bool have_vb = false, vb_dirty = false;

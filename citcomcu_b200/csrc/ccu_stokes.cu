@@ -113,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     {
         Level &L = c->L[lev];
         cudaFree(L.K); cudaFree(L.KT); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.col_inv); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
-        cudaFree(L.XX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
+        cudaFree(L.XX); cudaFree(L.SXX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
     cudaFree(c->en.Tdot); cudaFree(c->en.DTdot); cudaFree(c->en.V); cudaFree(c->en.T1); cudaFree(c->en.Tdot1); cudaFree(c->en.diffusivity);
@@ -1164,6 +1164,7 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     // the K.VB force term reads the viscosity as it stands BEFORE this call's update (Drive_solvers.c:107 comes ahead of :124);
     // at the very first call that is the one common_initial_fields evaluated from the initial state (Instructions.c:1233)
     if(c->have_vb && !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
+    if(c->rsphere && c->visc.sdepv) FAIL("general_stokes_solver: stress-dependent viscosity is Cartesian only on the device (strain_rate_2_inv has no Rsphere branch here)");
     if(ccu_assemble_forces(c, buoyancy, nullptr)) return 1;
     if(rebuild)
     {

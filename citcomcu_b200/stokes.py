@@ -159,6 +159,12 @@ class StokesContext:
             assert x.size == self.nno(lev)
         check(self.lib.ccu_set_coordinates(self._ctx, lev, *[x.ctypes.data_as(C.c_void_p) for x in xs]))
 
+    def set_spherical_coordinates(self, lev, theta, phi, r):
+        """E->SXX[lev]: switches the context to the regional-spherical element routines; set_coordinates then carries E->XX (Cartesian)."""
+        S = [np.ascontiguousarray(a, dtype=np.float32) for a in (theta, phi, r)]
+        assert all(a.size == self.nno(lev) for a in S)
+        check(self.lib.ccu_set_spherical_coordinates(self._ctx, lev, *[a.ctypes.data_as(C.c_void_p) for a in S]))
+
     def build_geometry(self):
         check(self.lib.ccu_build_geometry(self._ctx))
 

@@ -40,7 +40,8 @@
 #include "citcomcu_b200.h"
 
 ccu_ctx *g_ctx = NULL;              /* shared with citcom_dropin_funcs.c */
-int g_ccu_device_geometry = 1;      /* 0: spherical mesh, only the function-level bindings (operator assembled by the reference) */
+int g_ccu_device_geometry = 1;      /* 0: spherical mesh with CCU_DROPIN_STOKES=0, only the function-level bindings (operator assembled by the reference) */
+int g_ccu_cartesian = 1;            /* 0: regional-spherical mesh: energy step, heating and markers stay the reference's host code */
 static int g_calls = 0;
 
 void ccu_dropin_die(const char *msg);
@@ -62,11 +63,19 @@ void ccu_dropin_init(struct All_variables *E)
     /* Regional-spherical runs: the device has no Rsphere operator construction / energy step yet.  What it can run is the SOLVER on
        the operator the reference assembled (function-level bindings, citcom_dropin_funcs.c: the node-stored stiffness, the pressure
        operators and the transfer weights are geometry-free once assembled), so the context is created without device geometry. */
-    g_ccu_device_geometry = E->control.CART3D ? 1 : 0;
+    g_ccu_cartesian = E->control.CART3D ? 1 : 0;
+    {   /* Rsphere: the Stokes operator is assembled on the device (Rsphere branches of get_elt_k / get_elt_g / get_elt_f) unless the run
+           keeps the reference's driver (CCU_DROPIN_STOKES=0) and binds inner functions only */
+        const char *sw = getenv("CCU_DROPIN_STOKES");
+        g_ccu_device_geometry = (g_ccu_cartesian || !(sw && atoi(sw) == 0)) ? 1 : 0;
+    }
     if(E->viscosity.CDEPV || E->viscosity.BDEPV) die("composition- / Byerlee-dependent viscosity is not on the device path");
     if(E->viscosity.SDEPV && E->viscosity.sdepv_rheology != 1 && E->viscosity.sdepv_rheology != 2)
         die("stress-dependent viscosity: sdepv_rheology 1 and 2 are on the device path, 3 (dimensional Arrhenius law) is not");
     if(E->viscosity.SDEPV && E->control.restart) die("stress-dependent viscosity with restart (strain rate of the restart velocity) is not on the device path");
+    if(!E->control.CART3D && E->viscosity.TDEPV && (E->viscosity.RHEOL == 2 || E->viscosity.RHEOL == 4))
+        die("regional-spherical geometry with a depth-dependent viscosity law (rheol 2, 4) is not on the device path");
+    if(!E->control.CART3D && E->viscosity.SDEPV) die("regional-spherical geometry with stress-dependent viscosity is not on the device path");
     if(E->control.force_initial_stokes_iteration) die("force_initial_stokes_iteration is not on the device path");
     /* options that change the operator and that the device build does not implement: stop, never differ silently */
     if(E->viscosity.SMOOTH) die("viscosity smoothing (VISC_SMOOTH / apply_viscosity_smoother) is not on the device path");
@@ -105,6 +114,7 @@ void ccu_dropin_init(struct All_variables *E)
     {
         CCU(ccu_set_node_flags(g_ctx, lev, E->NODE[lev] + 1));
         if(g_ccu_device_geometry) CCU(ccu_set_coordinates(g_ctx, lev, E->XX[lev][1] + 1, E->XX[lev][2] + 1, E->XX[lev][3] + 1));
+        if(g_ccu_device_geometry && !g_ccu_cartesian) CCU(ccu_set_spherical_coordinates(g_ctx, lev, E->SXX[lev][1] + 1, E->SXX[lev][2] + 1, E->SXX[lev][3] + 1));
     }
     if(!g_ccu_device_geometry)
     {
@@ -128,7 +138,8 @@ void ccu_dropin_init(struct All_variables *E)
         CCU(ccu_set_sdepv(g_ctx, 1, E->viscosity.sdepv_rheology, E->viscosity.sdepv_expt, E->viscosity.sdepv_trns, E->viscosity.sdepv_misfit,
                           E->viscosity.sdepv_iter_damp, E->monitor.max_sdep_visc_iter, E->viscosity.sdepv_start_from_newtonian,
                           E->viscosity.sdepv_trns_T, E->viscosity.sdepv_trns_c));
-    if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: Stokes solve on CUDA device %d\n", cfg.device);
+    if(E->parallel.me == 0) fprintf(stderr, "citcomcu_b200 drop-in: Stokes solve on CUDA device %d%s\n", cfg.device,
+                                    g_ccu_cartesian ? "" : " (regional-spherical element routines)");
 }
 
 typedef void (*pg_fn)(struct All_variables *);
@@ -152,7 +163,7 @@ void general_stokes_solver(struct All_variables *E)
         }
     }
     if(!g_ctx) dropin_init(E);
-    if(!g_ccu_device_geometry) die("general_stokes_solver: only Geometry=cart3d builds its operator on the device; for Rsphere run with CCU_DROPIN_STOKES=0 CCU_DROPIN_ENERGY=0 and bind the solver functions (CCU_DROPIN_FUNCS=solve_Ahat_p_fhat)");
+    if(!g_ccu_device_geometry) die("general_stokes_solver: the context was created without device geometry (CCU_DROPIN_STOKES=0 at the first call)");
     E->monitor.elapsed_time_vsoln1 = E->monitor.elapsed_time_vsoln;
     E->monitor.elapsed_time_vsoln = E->monitor.elapsed_time;
     /* Construct_arrays.c:849: first call, or viscosity updates allowed and step % update_every_steps == 0 */
@@ -193,7 +204,7 @@ void PG_timestep(struct All_variables *E)
         }
     }
     if(!g_ctx) dropin_init(E);
-    if(!g_ccu_device_geometry) die("PG_timestep: the device energy step is Cartesian; run Rsphere with CCU_DROPIN_ENERGY=0");
+    if(!g_ccu_cartesian) die("PG_timestep: the device energy step is Cartesian; run Rsphere with CCU_DROPIN_ENERGY=0");
     if(!g_energy)
     {
         if(!E->advection.ADVECTION) die("ADVECTION=off is not on the device path");

@@ -29,7 +29,7 @@
 #include "citcomcu_b200.h"
 
 extern ccu_ctx *g_ctx;
-extern int g_ccu_device_geometry;
+extern int g_ccu_device_geometry, g_ccu_cartesian;
 void ccu_dropin_init(struct All_variables *E);
 void ccu_dropin_die(const char *msg);
 #define CCU(call) do { if((call) != 0) { fprintf(stderr, "citcomcu_b200 drop-in: %s failed: %s\n", #call, ccu_last_error()); exit(9); } } while(0)
@@ -212,7 +212,7 @@ static int g_markers = 0;
 static void markers_to_device(struct All_variables *E)
 {
     if(!g_ctx) ccu_dropin_init(E);
-    if(!g_ccu_device_geometry) ccu_dropin_die("markers: the device marker step is Cartesian");
+    if(!g_ccu_cartesian) ccu_dropin_die("markers: the device marker step is Cartesian");
     if(!g_markers)
     {
         CCU(ccu_markers_setup(g_ctx, E->advection.markers_uplimit, E->advection.markers_per_ele, E->lmesh.rnoz, E->XP[1] + 1, E->XP[2] + 1,
@@ -267,7 +267,7 @@ void PG_timestep_particle(struct All_variables *E)
     int n;
     if(!bound("PG_timestep_particle")) { NEXT(next, "PG_timestep_particle"); next(E); return; }
     if(!g_ctx) ccu_dropin_init(E);
-    if(!g_ccu_device_geometry) ccu_dropin_die("PG_timestep_particle: the device energy / marker steps are Cartesian");
+    if(!g_ccu_cartesian) ccu_dropin_die("PG_timestep_particle: the device energy / marker steps are Cartesian");
     if(on_off == 0)
     {
         if(E->control.composition != 2)

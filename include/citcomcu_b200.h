@@ -118,6 +118,11 @@ int ccu_set_transfer_weights(ccu_ctx *ctx, int lev, const float *TWW /*[nel*8]*/
 /* ---- operator construction on the device (rebuilt every `update_every_steps` when TDEPV) ---- */
 /* node coordinates E->XX[lev][1..3]+1 (x, y, z), natural node order (Nodal_mesh.c:53 node_locations) */
 int ccu_set_coordinates(ccu_ctx *ctx, int lev, const float *X1, const float *X2, const float *X3 /*[nno] each*/);
+/* Regional-spherical geometry (E->control.Rsphere): E->SXX[lev][1..3]+1 = (theta, phi, r) of the nodes; ccu_set_coordinates then carries
+ * the CARTESIAN node coordinates E->XX[lev], as the reference keeps them.  Switches the context's element routines to the Rsphere branches
+ * of get_elt_k (Element_calculations.c:249-260), get_elt_g (:896-920), get_elt_f (:1072-1086) and mass_matrix's ECO.size
+ * (Size_does_matter.c:661-680).  The energy step, heating, stress and marker entry points stay Cartesian-only and fail on such a context. */
+int ccu_set_spherical_coordinates(ccu_ctx *ctx, int lev, const float *theta, const float *phi, const float *r);
 /* mass_matrix (Size_does_matter.c:618): TWW, MASS, ECO.size; construct_elt_gs / get_elt_g (Element_calculations.c:831): elt_del; all levels */
 int ccu_build_geometry(ccu_ctx *ctx);
 /* E->viscosity.{TDEPV,RHEOL,num_mat,N0,E,T,Z,MIN,min_value,MAX,max_value,smooth_cycles} (Viscosity_structures.c:57-326) */

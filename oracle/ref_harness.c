@@ -103,6 +103,7 @@ static void dump_level_arrays(struct All_variables *E)
         for(a = 1; a <= 3; a++)
         {
             snprintf(nm, sizeof nm, "L%d_XX%d", lev, a); DUMP_F32(nm, E->XX[lev][a] + 1, nno);
+            if(E->control.Rsphere) { snprintf(nm, sizeof nm, "L%d_SXX%d", lev, a); DUMP_F32(nm, E->SXX[lev][a] + 1, nno); }
         }
     }
 }

@@ -11,7 +11,7 @@ from conftest import get_case, CASES
 pytestmark = pytest.mark.gpu
 
 
-def build_ctx(d, tdepv, viscE):
+def build_ctx(d, tdepv, viscE, N0=None):
     from citcomcu_b200.stokes import StokesContext
     ctl = d.control()
     nox, noy, noz = {}, {}, {}
@@ -24,8 +24,10 @@ def build_ctx(d, tdepv, viscE):
     for lev in range(ctl["levmin"], ctl["levmax"] + 1):
         ctx.set_node_flags(lev, d[f"L{lev}_NODE"])
         ctx.set_coordinates(lev, d[f"L{lev}_XX1"], d[f"L{lev}_XX2"], d[f"L{lev}_XX3"])
+        if f"L{lev}_SXX1" in d:                      # regional-spherical run: XX above are the Cartesian node positions
+            ctx.set_spherical_coordinates(lev, d[f"L{lev}_SXX1"], d[f"L{lev}_SXX2"], d[f"L{lev}_SXX3"])
     ctx.build_geometry()
-    ctx.set_viscosity_law(tdepv, 0, [1, 1, 1, 1], [viscE] * 4, [273] * 4, [5e-6] * 4)
+    ctx.set_viscosity_law(tdepv, 0, N0 or [1, 1, 1, 1], [viscE] * 4, [273] * 4, [5e-6] * 4)
     ctx.set_material(d["s0_mat"])
     ctx.set_temperature(d["s0_T"])
     ctx.get_system_viscosity()
@@ -136,4 +138,52 @@ def test_imposed_velocity_force_term():
         ref = d[f"s{k}_F"]
         assert np.abs(F - ref).max() < 1e-12 * np.abs(ref).max(), (k, np.abs(F - ref).max() / np.abs(ref).max())
     assert np.abs(plain - d["s0_F"]).max() > 1e-3 * np.abs(d["s0_F"]).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("tdepv", ["off", "on"])
+def test_regional_sphere_operator_construction(tdepv):
+    """BASELINE config 4 geometry (examples/input1's regional-spherical block): the Rsphere branches of mass_matrix (ECO.size),
+    get_elt_g, get_elt_k and get_elt_f on the device against the arrays the reference's host code builds.  The reference evaluates
+    the basis-projection matrices once per radial column and reuses them; the device evaluates them per element, so the fp32 arrays
+    agree to rounding (a vanishing fraction of 1-ulp differences), not bit for bit."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    txt = inputfile.input1_rsphere(levels=3, maxstep=1, accuracy=1e-6, TDEPV=tdepv, perturbmag=0.05)
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rsbuild_"), nsteps=0)[0][0]
+    if tdepv == "on":
+        assert d[f"L{d.levmax}_EVI"].max() > 10 * d[f"L{d.levmax}_EVI"].min()
+    ctx = build_ctx(d, 0, 0.0)
+    ctx.set_element_viscosity(d.levmax, d[f"L{d.levmax}_EVI"])         # the reference's viscosity (visc_from_mat + VMIN / VMAX)
+    ctl = d.control()
+    ctx.construct_stiffness_B_matrix(ctl["augmented_Lagr"], ctl["augmented"], ctl["precondition"])
+    rep = {}
+    for lev in range(d.levmin, d.levmax + 1):
+        for arr in ("TWW", "MASS"):
+            assert np.array_equal(ctx.get_level_array(lev, arr), d[f"L{lev}_{arr}"]), (lev, arr)
+        for arr, tol in (("eco_size", 1e-6), ("elt_del", 2e-6)):
+            got, ref = ctx.get_level_array(lev, arr), d[f"L{lev}_{arr}"]
+            rep[f"{arr}{lev}"] = frac_diff(got, ref)
+            assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (lev, arr, np.abs(got - ref).max() / np.abs(ref).max())
+        assert np.allclose(ctx.get_level_array(lev, "EVI"), d[f"L{lev}_EVI"], rtol=3e-7, atol=0), lev
+        k1, k2, k3, BI = ctx.get_stiffness(lev)
+        for k, nm in ((k1, "Eqn_k1"), (k2, "Eqn_k2"), (k3, "Eqn_k3")):
+            ref = d[f"L{lev}_{nm}"]
+            rep[f"{nm}_{lev}"] = frac_diff(k, ref)
+            assert np.abs(k - ref).max() <= 2e-6 * np.abs(ref).max(), (lev, nm, np.abs(k - ref).max() / np.abs(ref).max())
+        assert np.allclose(BI, d[f"L{lev}_BI"], rtol=1e-5, atol=0), lev
+        assert np.allclose(ctx.get_level_array(lev, "BPI"), d[f"L{lev}_BPI"], rtol=1e-5, atol=0), lev
+    F = ctx.assemble_forces(d["s0_buoyancy"])
+    assert np.abs(F - d["s0_F"]).max() <= 1e-12 * np.abs(d["s0_F"]).max()
+    print("fraction of entries differing:", {k: round(v, 4) for k, v in rep.items() if v})
+    lm = d.levmax
+    n, npno = d.dims(lm)["neq"], d.dims(lm)["npno"]
+    V, P, steps, res, hist = ctx.solve_Ahat_p_fhat(np.zeros(n), np.zeros(npno), F, ctl["accuracy"], 375)
+    assert np.linalg.norm(V - d["s0_U"]) < 20 * ctl["accuracy"] * np.linalg.norm(d["s0_U"])
+    # the entry points that only know the Cartesian element routines refuse the context
+    with pytest.raises(Exception, match="Cartesian geometry only"):
+        ctx.process_heating()
     ctx.close()

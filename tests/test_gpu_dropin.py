@@ -253,3 +253,27 @@ def test_regional_sphere_solver_on_device(funcs, monkeypatch):
         assert np.linalg.norm(Ug - U) <= 20 * acc * np.linalg.norm(U), k
         assert np.linalg.norm(Pg - P) <= 200 * acc * np.linalg.norm(P), k
         assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+
+
+@pytest.mark.parametrize("tdepv", ["off", "on"])
+def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, monkeypatch):
+    """BASELINE config 4 geometry through the whole-step binding: operator assembly (Rsphere get_elt_k / get_elt_g / get_elt_f on the
+    device) and the Stokes solve on the device, the energy step stays the reference's host code (CCU_DROPIN_ENERGY=0)."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-5, TDEPV=tdepv, VISC_UPDATE="on", update_every_steps=1, storage_spacing=1)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rswref_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", "0")
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rswgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "Stokes solve on CUDA device" in err and "regional-spherical element routines" in err
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    for k in range(nsteps + 1):
+        U, Ug, P, Pg = r[f"s{k}_U"], g[f"s{k}_U"], r[f"s{k}_P"], g[f"s{k}_P"]
+        assert np.linalg.norm(Ug - U) <= 20 * acc * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
+        assert np.linalg.norm(Pg - P) <= 200 * acc * np.linalg.norm(P), k
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+        sr, sg = r[f"s{k}_scalars"], g[f"s{k}_scalars"]
+        for q in (2, 3):                                   # Nut, Nub (the reference's host heat_flux on both sides)
+            assert abs(sg[q] - sr[q]) <= 1e-3 * abs(sr[q]) + 1e-9, ("Nu", k, q)
