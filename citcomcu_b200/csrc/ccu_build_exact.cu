@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const
                                                           const float *__restrict__ Tdot, const float *__restrict__ V,
                                                           const float *__restrict__ diffusivity, const float Q0,
                                                           const float *__restrict__ heat_adi, const float *__restrict__ heat_visc,
-                                                          const float *__restrict__ heat_latent, double *Eres)
+                                                          const float *__restrict__ heat_latent, double *Eres, const int sph)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -1183,13 +1183,31 @@ __global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const
     for(int i = 0; i < 8; i++)
     {
         const float gda = (float)gp_geom(X, c_sh.Nxv + i, 64, 8, gnx);
+        // Rsphere (:506-528, 620-640, 668-674): gNX holds d/dtheta, d/dphi, d/dr; rtf3 = 1/r, rtf2 = 1/(r sin theta) scale the first two
+        double rtf3 = 1.0, rtf2 = 1.0;
+        if(sph)
+        {
+            double x[3], th, ph;
+            sph_point(X, c_sh.Nv + i, 8, x);
+            sph_rotate_gnx(x, gnx);
+            sph_rtf(x, th, ph, rtf3);
+            rtf2 = rtf3 / sin(th);
+        }
         double dT = 0.0, tx1 = 0.0, tx2 = 0.0, tx3 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
         for(int j = 0; j < 8; j++)
         {
             const double sfn = c_sh.Nv[8 * j + i];
             dT += DTn[j] * sfn;
-            tx1 += (double)gnx[0][j] * Tn[j];
-            tx2 += (double)gnx[1][j] * Tn[j];
+            if(sph)
+            {
+                tx1 += (double)gnx[0][j] * Tn[j] * rtf3;
+                tx2 += (double)gnx[1][j] * Tn[j] * rtf2;
+            }
+            else
+            {
+                tx1 += (double)gnx[0][j] * Tn[j];
+                tx2 += (double)gnx[1][j] * Tn[j];
+            }
             tx3 += (double)gnx[2][j] * Tn[j];
             v1 += (double)vel[0][j] * sfn;
             v2 += (double)vel[1][j] * sfn;
@@ -1198,10 +1216,13 @@ __global__ void __launch_bounds__(64) ek_element_residual(const CcuGeom g, const
         const double adv = dT - Q + v1 * tx1 + v2 * tx2 + v3 * tx3;
         for(int j = 0; j < 8; j++)
         {
-            const double prod1 = v1 * (double)gnx[0][j] + v2 * (double)gnx[1][j] + v3 * (double)gnx[2][j];
+            const double prod1 = sph ? (v1 * (double)gnx[0][j] * rtf3 + v2 * (double)gnx[1][j] * rtf2 + v3 * (double)gnx[2][j])
+                                     : (v1 * (double)gnx[0][j] + v2 * (double)gnx[1][j] + v3 * (double)gnx[2][j]);
             const double pg = c_sh.Nv[8 * j + i] + adiff * prod1;
             double term = pg * (double)gda * adv;
-            if(diffusion) term = term + (double)(dl * gda) * ((double)gnx[0][j] * tx1 + (double)gnx[1][j] * tx2 + (double)gnx[2][j] * tx3);
+            if(diffusion)
+                term = term + (double)(dl * gda) * (sph ? ((double)gnx[0][j] * tx1 * rtf3 + (double)gnx[1][j] * tx2 * rtf2 + (double)gnx[2][j] * tx3)
+                                                        : ((double)gnx[0][j] * tx1 + (double)gnx[1][j] * tx2 + (double)gnx[2][j] * tx3));
             res[j] -= term;
         }
     }
@@ -2404,7 +2425,6 @@ static int std_timestep(ccu_ctx *c, float *dt)
 int ccu_std_timestep(ccu_ctx *c, float *dt_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "std_timestep");
     if(ensure_energy(c)) return 1;
     return std_timestep(c, dt_out);
 }
@@ -2413,7 +2433,7 @@ static int pg_solver(ccu_ctx *c)
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
     LAUNCH(c, ek_element_residual, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.eco, L.node, c->T, E.Tdot, E.V, E.diffusivity, E.Q0,
-           (const float *)E.heat_adi, (const float *)E.heat_visc, (const float *)E.heat_latent, E.Eres);
+           (const float *)E.heat_adi, (const float *)E.heat_visc, (const float *)E.heat_latent, E.Eres, c->rsphere ? 1 : 0);
     if(!c->multi()) { LAUNCH(c, ek_gather_residual, cdiv(L.g.nno, 128), 128, L.g, E.Eres, L.MASS, E.DTdot); return 0; }
     LAUNCH(c, ek_gather_residual, cdiv(L.g.nno, 128), 128, L.g, E.Eres, (const float *)nullptr, E.DTdot);
     if(ccu_halo_sum_nodal(c, c->cfg.levmax, E.DTdot)) return 1;      // exchange_node_f20 (Advection_diffusion.c:432)
@@ -2430,7 +2450,6 @@ static int energy_ready(ccu_ctx *c)
 int ccu_pg_solver(ccu_ctx *c, float *DTdot_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "pg_solver");
     if(ensure_energy(c) || energy_ready(c)) return 1;
     if(pg_solver(c)) return 1;
     if(DTdot_out) CK(cudaMemcpyAsync(DTdot_out, c->en.DTdot, sizeof(float) * (size_t)c->L[c->cfg.levmax].g.nno, cudaMemcpyDeviceToHost, c->st));
@@ -2447,7 +2466,6 @@ static int tmax(ccu_ctx *c, float *out)
 int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_interior_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "PG_timestep");
     if(ensure_energy(c) || energy_ready(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;

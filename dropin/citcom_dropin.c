@@ -204,7 +204,7 @@ void PG_timestep(struct All_variables *E)
         }
     }
     if(!g_ctx) dropin_init(E);
-    if(!g_ccu_cartesian) die("PG_timestep: the device energy step is Cartesian; run Rsphere with CCU_DROPIN_ENERGY=0");
+    if(!g_ccu_device_geometry) die("PG_timestep: the context was created without device geometry (CCU_DROPIN_STOKES=0 on a regional-spherical run)");
     if(!g_energy)
     {
         if(!E->advection.ADVECTION) die("ADVECTION=off is not on the device path");

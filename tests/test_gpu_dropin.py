@@ -255,18 +255,22 @@ def test_regional_sphere_solver_on_device(funcs, monkeypatch):
         assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
 
 
+@pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
 @pytest.mark.parametrize("tdepv", ["off", "on"])
-def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, monkeypatch):
-    """BASELINE config 4 geometry through the whole-step binding: operator assembly (Rsphere get_elt_k / get_elt_g / get_elt_f on the
-    device) and the Stokes solve on the device, the energy step stays the reference's host code (CCU_DROPIN_ENERGY=0)."""
+def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, energy, monkeypatch):
+    """BASELINE config 4 geometry through the whole-step bindings: operator assembly (Rsphere get_elt_k / get_elt_g / get_elt_f) and the
+    Stokes solve on the device; in the second variant also the SUPG energy step with the Rsphere branches of pg_shape_fn /
+    element_residual (Advection_diffusion.c:506-528, 620-640, 668-674)."""
     if not po.have_ref() or not DROPIN.exists():
         pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
-    txt = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-5, TDEPV=tdepv, VISC_UPDATE="on", update_every_steps=1, storage_spacing=1)
-    nsteps = 2
+    txt = inputfile.input1_rsphere(levels=3, maxstep=5, accuracy=1e-5, TDEPV=tdepv, VISC_UPDATE="on", update_every_steps=1, storage_spacing=1,
+                                   perturbmag=0.05)
+    nsteps = 4
     ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rswref_"), nsteps=nsteps)
-    monkeypatch.setenv("CCU_DROPIN_ENERGY", "0")
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", str(energy))
     gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rswgpu_"), nsteps=nsteps, preload=str(DROPIN))
     assert "Stokes solve on CUDA device" in err and "regional-spherical element routines" in err
+    assert ("energy step on the CUDA device" in err) == bool(energy)
     r, g = ref[0], gpu[0]
     acc = r.control()["accuracy"]
     for k in range(nsteps + 1):
@@ -275,5 +279,8 @@ def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, monkeypatc
         assert np.linalg.norm(Pg - P) <= 200 * acc * np.linalg.norm(P), k
         assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
         sr, sg = r[f"s{k}_scalars"], g[f"s{k}_scalars"]
+        assert abs(sg[1] - sr[1]) <= 1e-3 * abs(sr[1]) + 1e-12, ("timestep", k)
         for q in (2, 3):                                   # Nut, Nub (the reference's host heat_flux on both sides)
             assert abs(sg[q] - sr[q]) <= 1e-3 * abs(sr[q]) + 1e-9, ("Nu", k, q)
+    # the temperature did move over the run (the comparison above is not between two copies of the initial field)
+    assert np.abs(r[f"s{nsteps}_T"] - r["s0_T"]).max() > 1e-3
