@@ -1592,10 +1592,28 @@ __global__ void __launch_bounds__(128) mk_velocity(const CcuGeom g, const MkGrid
 }
 // Euler predictor / modified-Euler corrector of the positions (Composition_adv.c:115-121, 71-77): dt*VO is a FLOAT product
 __global__ void __launch_bounds__(256) mk_advance(const int n, const int cap, const float dt, const int corrector, const float *__restrict__ VO,
-                                                  const float *__restrict__ Vpred, double *X, double *Xpred)
+                                                  const float *__restrict__ Vpred, double *X, double *Xpred, const int sph)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
+    if(sph)
+    {   // Rsphere (Composition_adv.c:79-92, 124-135): positions are (theta, phi, r); u_theta / r, u_phi / (r sin theta), all from the OLD position
+        const size_t q0 = i, q1 = (size_t)cap + i, q2 = 2 * (size_t)cap + i;
+        const double t = X[q0], f = X[q1], r = X[q2];
+        if(!corrector)
+        {
+            Xpred[q0] = t + (double)(dt * VO[q0]) / r;
+            Xpred[q1] = f + (double)(dt * VO[q1]) / (r * sin(t));
+            Xpred[q2] = r + (double)(dt * VO[q2]);
+        }
+        else
+        {
+            X[q0] = t + 0.5 * (double)dt * (double)(VO[q0] + Vpred[q0]) / r;
+            X[q1] = f + 0.5 * (double)dt * (double)(VO[q1] + Vpred[q1]) / (r * sin(t));
+            X[q2] = r + 0.5 * (double)dt * (double)(VO[q2] + Vpred[q2]);
+        }
+        return;
+    }
     for(int d = 0; d < 3; d++)
     {
         const size_t q = (size_t)d * cap + i;
@@ -2776,7 +2794,6 @@ int ccu_markers_setup(ccu_ctx *c, int capacity, int markers_per_ele, int rnoz, c
                       const int *RG3, const double *XG1, const double *XG2, const unsigned *Element, float Acomp)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "marker advection");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &M = c->mk;
@@ -2980,12 +2997,12 @@ static int mk_advect(ccu_ctx *c, float timestep, int corrector, MkGrid &m, doubl
     if(!corrector)
     {
         LAUNCH(c, mk_velocity, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)M.X, (const float *)L.eco, (const float *)c->en.V, M.VO, M.CElement, M.err);
-        LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 0, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred);
+        LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 0, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred, c->rsphere ? 1 : 0);
         Xuse = M.Xpred;
         return 0;
     }
     LAUNCH(c, mk_velocity, cdiv(n, 128), 128, L.g, m, n, M.cap, (const double *)M.Xpred, (const float *)L.eco, (const float *)c->en.V, M.Vpred, M.CElement, M.err);
-    LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 1, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred);
+    LAUNCH(c, mk_advance, cdiv(n, 256), 256, n, M.cap, timestep, 1, (const float *)M.VO, (const float *)M.Vpred, M.X, M.Xpred, c->rsphere ? 1 : 0);
     Xuse = M.X;
     return 0;
 }

@@ -212,7 +212,7 @@ static int g_markers = 0;
 static void markers_to_device(struct All_variables *E)
 {
     if(!g_ctx) ccu_dropin_init(E);
-    if(!g_ccu_cartesian) ccu_dropin_die("markers: the device marker step is Cartesian");
+    if(!g_ccu_device_geometry) ccu_dropin_die("markers: the context was created without device geometry (CCU_DROPIN_STOKES=0 on a regional-spherical run)");
     if(!g_markers)
     {
         CCU(ccu_markers_setup(g_ctx, E->advection.markers_uplimit, E->advection.markers_per_ele, E->lmesh.rnoz, E->XP[1] + 1, E->XP[2] + 1,
@@ -267,7 +267,7 @@ void PG_timestep_particle(struct All_variables *E)
     int n;
     if(!bound("PG_timestep_particle")) { NEXT(next, "PG_timestep_particle"); next(E); return; }
     if(!g_ctx) ccu_dropin_init(E);
-    if(!g_ccu_cartesian) ccu_dropin_die("PG_timestep_particle: the device energy / marker steps are Cartesian");
+    if(!g_ccu_device_geometry) ccu_dropin_die("PG_timestep_particle: the context was created without device geometry (CCU_DROPIN_STOKES=0 on a regional-spherical run)");
     if(on_off == 0)
     {
         if(E->control.composition != 2)

@@ -284,3 +284,31 @@ def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, energy, mo
             assert abs(sg[q] - sr[q]) <= 1e-3 * abs(sr[q]) + 1e-9, ("Nu", k, q)
     # the temperature did move over the run (the comparison above is not between two copies of the initial field)
     assert np.abs(r[f"s{nsteps}_T"] - r["s0_T"]).max() > 1e-3
+
+
+def test_regional_sphere_thermochemical_loop_on_device(monkeypatch):
+    """Regional-spherical thermochemical run: Stokes assembly + solve, the energy step and the marker advection (Euler / Runge_Kutta
+    with the 1/r, 1/(r sin theta) position update of Composition_adv.c:79-92, 124-135) on the device inside the reference's loop."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    txt = inputfile.input1_rsphere(levels=3, maxstep=5, accuracy=1e-5, composition=1, rayleigh_comp=1e6, markers_per_ele=8, comp_depth=0.3,
+                                   perturbmag=0.05)
+    nsteps = 4
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rsmref_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_FUNCS", "PG_timestep_particle,Euler,Runge_Kutta")
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rsmgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "regional-spherical element routines" in err
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    assert r[f"s{nsteps}_C"].max() > 0.9 and r[f"s{nsteps}_C"].min() < 0.1          # a two-layer composition
+    assert np.abs(r[f"s{nsteps}_XMC1"] - r["s1_XMC1"]).max() > 1e-3                 # markers did move in colatitude
+    for k in range(1, nsteps + 1):
+        assert int(g[f"s{k}_nmarkers"][0]) == int(r[f"s{k}_nmarkers"][0])
+        U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+        # both arms stop each solve at the solver tolerance; over coupled thermochemical steps the differences add up (2.8e-4 at step 4)
+        assert np.linalg.norm(Ug - U) <= 50 * acc * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
+        for d in (1, 2, 3):
+            assert np.abs(g[f"s{k}_XMC{d}"] - r[f"s{k}_XMC{d}"]).max() < 1e-5, (k, d)
+        assert (g[f"s{k}_CElement"] != r[f"s{k}_CElement"]).mean() < 1e-3
+        assert np.abs(g[f"s{k}_C"] - r[f"s{k}_C"]).max() < 0.2 and np.abs(g[f"s{k}_C"] - r[f"s{k}_C"]).mean() < 1e-4
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3
