@@ -25,8 +25,11 @@
  * Several ranks: one rank per GPU (CCU_DEVICE, or rank modulo CCU_DEVICES); the reference's own MPI_Bcast carries the NCCL
  * id once, after that the library does the halo sums and reductions over NCCL (ccu_comm_init).
  *
- * Unsupported configurations stop the run loudly (there is no CPU fallback): spherical geometry,
- * composition-dependent viscosity, viscosity smoothing, anisotropic viscosity, periodic side walls.
+ * Regional-spherical runs (Geometry=Rsphere): the node positions E->XX and E->SXX go up and the device uses the Rsphere branches of
+ * the element routines; process_heating / thermal_buoyancy / heat_flux stay the reference's host code.
+ *
+ * Unsupported configurations stop the run loudly (there is no CPU fallback): composition-dependent viscosity, viscosity smoothing,
+ * anisotropic viscosity, periodic side walls, heat-flux boundary conditions.
  *
  * citcom_dropin_funcs.c (same library) binds the INNER functions of the path one by one (CCU_DROPIN_FUNCS).
  */
