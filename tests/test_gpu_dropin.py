@@ -312,3 +312,30 @@ def test_regional_sphere_thermochemical_loop_on_device(monkeypatch):
         assert (g[f"s{k}_CElement"] != r[f"s{k}_CElement"]).mean() < 1e-3
         assert np.abs(g[f"s{k}_C"] - r[f"s{k}_C"]).max() < 0.2 and np.abs(g[f"s{k}_C"] - r[f"s{k}_C"]).mean() < 1e-4
         assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("name,txt", [
+    ("config1_busse1a", inputfile.busse1a(levels=5, maxstep=4, accuracy=1e-4, storage_spacing=1)),           # examples/Busse1993 case 1a: 32x16x32
+    ("config2_input1_cart", inputfile.input1_cart(levels=4, maxstep=4, storage_spacing=1)),                  # examples/input1 mesh as Cartesian: 48^3
+    ("config4_input1_rsphere", inputfile.input1_rsphere(levels=4, maxstep=4, storage_spacing=1)),            # examples/input1: 48^3 regional sphere
+], ids=["config1_busse1a", "config2_input1_cart", "config4_input1_rsphere"])
+def test_baseline_configs_at_shipped_sizes(name, txt, monkeypatch):
+    """The BASELINE.json parity configurations at the mesh sizes and level counts of the shipped input files (not scaled down), Stokes
+    and energy step on the device inside the reference's own time loop."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    nsteps = 3
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix=f"ccu_full_ref_{name}_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", "1")
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix=f"ccu_full_gpu_{name}_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "Stokes solve on CUDA device" in err and "energy step on the CUDA device" in err
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    for k in range(nsteps + 1):
+        U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+        assert np.linalg.norm(Ug - U) < 20 * acc * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3 * np.abs(r[f"s{k}_T"]).max(), k
+        sr, sg = r[f"s{k}_scalars"], g[f"s{k}_scalars"]
+        assert abs(sg[1] - sr[1]) <= 1e-3 * abs(sr[1]) + 1e-12, ("timestep", k)
+        for q in (2, 3):
+            assert abs(sg[q] - sr[q]) <= 1e-3 * abs(sr[q]) + 1e-9, ("Nu", k, q)
