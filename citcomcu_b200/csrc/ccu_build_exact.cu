@@ -1828,6 +1828,7 @@ int ccu_build_geometry(ccu_ctx *c)
             LAUNCH(c, bk_elt_geometry_sph, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.SXX, L.eco, L.elt_del);
         }
         ccu_elt_del_changed(c, lev);
+        ccu_eco_changed(c, lev);
         LAUNCH(c, bk_mass, cdiv(L.g.nno, 128), 128, L.g, (const double *)c->stage, L.MASS);
         if(ccu_halo_sum_nodal(c, lev, L.MASS)) return 1;                  // exchange_node_f20 (Size_does_matter.c:733)
         LAUNCH(c, bk_invert, cdiv(L.g.nno, 128), 128, L.g.nno, L.MASS);

@@ -40,6 +40,7 @@ struct Level
     double *BI = nullptr;
     unsigned char *flags = nullptr;
     float *MASS = nullptr, *TWW = nullptr, *eco = nullptr, *elt_del = nullptr;
+    float *ecoT = nullptr;        // [3][nel] the element sizes direction-major (interp_vector weights); refreshed by ccu_eco_changed
     float *elt_delT = nullptr;    // [24][nel] coefficient-major copy of elt_del (div_u / grad_p read it)
     double *BPI = nullptr;
     double *vec[CCU_VEC_COUNT] = { nullptr };
@@ -252,4 +253,5 @@ int ccu_agg_gather_evi(ccu_ctx *c);                          // EVI[agg_lev] of 
 int ccu_check_lev(ccu_ctx *c, int lev);
 int ccu_col_refresh(ccu_ctx *c, int lev);
 int ccu_col_refresh_all(ccu_ctx *c);
+void ccu_eco_changed(ccu_ctx *c, int lev);                    // ccu_stokes.cu: call after every write of L.eco
 void ccu_elt_del_changed(ccu_ctx *c, int lev);                // ccu_stokes.cu                   // ccu_stokes.cu

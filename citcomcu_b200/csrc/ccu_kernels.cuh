@@ -1006,11 +1006,12 @@ __global__ void __launch_bounds__(128) ccu_k_project(const CcuGeom gc, const Ccu
                                                       const int apply_mass)
 {
     constexpr int LUT[2][2][2] = { { {1, 4}, {2, 3} }, { {5, 8}, {6, 7} } };   // [dz][dx][dy] -> local node
+    // threads run over the coarse nodes in NATURAL order (z fastest): the fine node at a fixed offset from (2I, 2J, 2Kz) then sits
+    // at consecutive slots of one colour block of the fine vector, so all 81 loads of a warp are contiguous (the coarse-colour order
+    // made them stride-2); the coarse stores are the strided side, an eighth of the data
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if(t >= 8 * gc.NC) return;
-    const int c = t / gc.NC, cell = t - c * gc.NC;
-    int I, J, Kz;
-    if(!ccu_decode(gc, c, cell, I, J, Kz)) return;
+    if(t >= gc.nno) return;
+    const int Kz = t % gc.noz, J = (t / gc.noz) % gc.nox, I = t / (gc.noz * gc.nox);
     // The eight sub-elements around fine node (2I, 2J, 2Kz) overlap: their 64 nodal values are 27 distinct fine nodes.
     // W[ay][ax][az] = TWW of the coarse element in octant (ay, ax, az) (0 outside the mesh); fine node at offset
     // (dy, dx, dz) collects the weights of every octant whose sub-element holds it, so each fine value is read once.
@@ -1048,8 +1049,8 @@ __global__ void __launch_bounds__(128) ccu_k_project(const CcuGeom gc, const Ccu
                     s0 += w * fine[sf]; s1 += w * fine[(size_t)gf.NS + sf]; s2 += w * fine[2 * (size_t)gf.NS + sf];
                 }
             }
-    const double m = apply_mass ? (double)MASS[Kz + gc.noz * (J + gc.nox * I)] : 1.0;
-    const int sc = c * gc.NC + cell;
+    const double m = apply_mass ? (double)MASS[t] : 1.0;
+    const int sc = ccu_sidx(gc, I, J, Kz);
     coarse[sc] = s0 * m; coarse[(size_t)gc.NS + sc] = s1 * m; coarse[2 * (size_t)gc.NS + sc] = s2 * m;
 }
 // second half of project_vector when the halo sum sits between the gather and the mass factor (Solver_multigrid.c:150-157)
@@ -1065,6 +1066,13 @@ __global__ void __launch_bounds__(128) ccu_k_mass_mul(const CcuGeom g, const flo
     v[s] *= m; v[(size_t)g.NS + s] *= m; v[2 * (size_t)g.NS + s] *= m;
 }
 
+__global__ void __launch_bounds__(256) ccu_k_eco_transpose(const int nel, const float *__restrict__ eco, float *__restrict__ ecoT)
+{
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if(t >= (size_t)nel * 3) return;
+    const int d = (int)(t / nel), e = (int)(t - (size_t)d * nel);
+    ecoT[t] = eco[(size_t)e * 3 + d];
+}
 // interp_vector + un_inject_vector (Solver_multigrid.c:173-298, 581-634): the reference fills x,
 // then z, then y gaps in place; evaluated here per fine node as the same nested two-point
 // interpolations (fp32 weights from the element sizes the reference looks up, Appendix A #8):
@@ -1073,16 +1081,17 @@ __device__ __forceinline__ int ccu_first_elt(const CcuGeom &g, int i, int j, int
 {
     return (k > 0 ? k - 1 : 0) + g.elz * ((j > 0 ? j - 1 : 0) + g.elx * (i > 0 ? i - 1 : 0));
 }
-__device__ __forceinline__ void ccu_w12(const float *__restrict__ eco, int e1, int e2, int dir, float &w1, float &w2)
+// eco: element sizes direction-major, [3][nel] (Level::ecoT), so that neighbouring threads read neighbouring floats
+__device__ __forceinline__ void ccu_w12(const float *__restrict__ eco, const int nel, int e1, int e2, int dir, float &w1, float &w2)
 {
-    const float x1 = eco[(size_t)e1 * 3 + dir], x2 = eco[(size_t)e2 * 3 + dir];
+    const float x1 = eco[(size_t)dir * nel + e1], x2 = eco[(size_t)dir * nel + e2];
     w1 = x2 / (x1 + x2); w2 = x1 / (x1 + x2);
 }
 // weights are evaluated once per node and applied to the three dofs (they are the same for each)
 struct CcuInterpW { float w1, w2; };
-__device__ __forceinline__ CcuInterpW ccu_wpair(const float *__restrict__ eco, int e1, int e2, int dir)
+__device__ __forceinline__ CcuInterpW ccu_wpair(const float *__restrict__ eco, const int nel, int e1, int e2, int dir)
 {
-    CcuInterpW w; ccu_w12(eco, e1, e2, dir, w.w1, w.w2); return w;
+    CcuInterpW w; ccu_w12(eco, nel, e1, e2, dir, w.w1, w.w2); return w;
 }
 __global__ void __launch_bounds__(128) ccu_k_interp(const CcuGeom gc, const CcuGeom gf, const float *__restrict__ eco_f,
                                                      const unsigned char *__restrict__ flags_f, const double *__restrict__ coarse,
@@ -1099,19 +1108,19 @@ __global__ void __launch_bounds__(128) ccu_k_interp(const CcuGeom gc, const CcuG
     // rows i0 (and i1 when i is odd), columns k0 (k1), x positions j0 (j1): up to eight coarse nodes
     const int i0 = oi ? i - 1 : i, i1 = i + 1, k0 = ok ? k - 1 : k, k1 = k + 1, j0 = oj ? j - 1 : j, j1 = j + 1;
     CcuInterpW wy = { 1.0f, 0.0f }, wz[2] = { { 1.0f, 0.0f }, { 1.0f, 0.0f } }, wx[2][2] = { { { 1.0f, 0.0f }, { 1.0f, 0.0f } }, { { 1.0f, 0.0f }, { 1.0f, 0.0f } } };
-    if(oi) wy = ccu_wpair(eco_f, ccu_first_elt(gf, i - 1, j, k), ccu_first_elt(gf, i + 1, j, k), 1);
+    if(oi) wy = ccu_wpair(eco_f, gf.nel, ccu_first_elt(gf, i - 1, j, k), ccu_first_elt(gf, i + 1, j, k), 1);
 #pragma unroll
     for(int a = 0; a < 2; a++)
     {
         if(a && !oi) break;
         const int ii = a ? i1 : i0;
-        if(ok) wz[a] = ccu_wpair(eco_f, ccu_first_elt(gf, ii, j, k - 1), ccu_first_elt(gf, ii, j, k + 1), 2);
+        if(ok) wz[a] = ccu_wpair(eco_f, gf.nel, ccu_first_elt(gf, ii, j, k - 1), ccu_first_elt(gf, ii, j, k + 1), 2);
 #pragma unroll
         for(int b = 0; b < 2; b++)
         {
             if(b && !ok) break;
             const int kk = b ? k1 : k0;
-            if(oj) wx[a][b] = ccu_wpair(eco_f, ccu_first_elt(gf, ii, j - 1, kk), ccu_first_elt(gf, ii, j + 1, kk), 0);
+            if(oj) wx[a][b] = ccu_wpair(eco_f, gf.nel, ccu_first_elt(gf, ii, j - 1, kk), ccu_first_elt(gf, ii, j + 1, kk), 0);
         }
     }
     // coarse storage slots of the (up to) eight corners

@@ -68,6 +68,7 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
         CK(cudaMalloc(&L.MASS, sizeof(float) * L.g.nno));
         CK(cudaMalloc(&L.TWW, sizeof(float) * 8 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.eco, sizeof(float) * 3 * (size_t)L.g.nel));
+        CK(cudaMalloc(&L.ecoT, sizeof(float) * 3 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.elt_del, sizeof(float) * 24 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.elt_delT, sizeof(float) * 24 * (size_t)L.g.nel));
         CK(cudaMalloc(&L.BPI, sizeof(double) * (size_t)L.g.npno));
@@ -112,7 +113,7 @@ void ccu_destroy(ccu_ctx *c)
     for(int lev = 0; lev < CCU_MAX_LEVELS; lev++)
     {
         Level &L = c->L[lev];
-        cudaFree(L.K); cudaFree(L.KT); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.col_inv); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
+        cudaFree(L.K); cudaFree(L.KT); cudaFree(L.Kc); cudaFree(L.colofs); cudaFree(L.col_sync); cudaFree(L.col_inv); cudaFree(L.BI); cudaFree(L.flags); cudaFree(L.MASS); cudaFree(L.TWW); cudaFree(L.eco); cudaFree(L.ecoT); cudaFree(L.elt_del); cudaFree(L.elt_delT); cudaFree(L.BPI);
         cudaFree(L.XX); cudaFree(L.SXX); cudaFree(L.EVI); cudaFree(L.node); cudaFree(L.sm_s); cudaFree(L.sm_nbr);
         for(auto v : L.vec) cudaFree(v);
     }
@@ -321,12 +322,18 @@ int ccu_set_transfer_weights(ccu_ctx *c, int lev, const float *TWW, const float 
     CK(cudaMemcpyAsync(L.TWW, TWW, sizeof(float) * 8 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.MASS, MASS, sizeof(float) * L.g.nno, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(L.eco, eco, sizeof(float) * 3 * (size_t)L.g.nel, cudaMemcpyHostToDevice, c->st));
+    ccu_eco_changed(c, lev);
     SYNC(c);
     L.have_tw = true;
     return 0;
 }
 
 // coefficient-major copy of elt_del for div_u / grad_p; call after every write of L.elt_del
+void ccu_eco_changed(ccu_ctx *c, int lev)
+{
+    Level &L = c->L[lev];
+    LAUNCH(c, ccu_k_eco_transpose, cdiv((size_t)L.g.nel * 3, 256), 256, L.g.nel, L.eco, L.ecoT);
+}
 void ccu_elt_del_changed(ccu_ctx *c, int lev)
 {
     Level &L = c->L[lev];
@@ -763,7 +770,7 @@ static void d_project(ccu_ctx *c, int lev, const double *fine, double *coarse, i
     CcuProfScope ps(c, CCU_PROF_TRANSFER_FINE, lev == c->cfg.levmax);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + lev, true, 0);
     const int multi = c->multi() ? 1 : 0;
-    LAUNCH(c, ccu_k_project, cdiv(8 * (size_t)Lc.g.NC, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse, multi ? 0 : 1);
+    LAUNCH(c, ccu_k_project, cdiv(Lc.g.nno, 128), 128, Lc.g, Lf.g, Lc.TWW, Lc.MASS, fine, coarse, multi ? 0 : 1);
     if(multi)
     {   // exchange_id_d20 before the mass factor (Solver_multigrid.c:150-157)
         ccu_halo_sum_vec(c, lev - 1, coarse);
@@ -776,7 +783,7 @@ static void d_interp(ccu_ctx *c, int lev, const double *coarse, double *fine, in
     Level &Lc = c->L[lev], &Lf = c->L[lev + 1];
     CcuProfScope ps(c, CCU_PROF_TRANSFER_FINE, lev + 1 == c->cfg.levmax);
     CcuProfScope pl(c, CCU_PROF_LEVEL0 + lev + 1, true, 0);
-    LAUNCH(c, ccu_k_interp, cdiv(8 * (size_t)Lf.g.NC, 128), 128, Lc.g, Lf.g, Lf.eco, Lf.flags, coarse, fine, strip);
+    LAUNCH(c, ccu_k_interp, cdiv(8 * (size_t)Lf.g.NC, 128), 128, Lc.g, Lf.g, Lf.ecoT, Lf.flags, coarse, fine, strip);
 }
 
 // A fixed launch sequence captured once into a CUDA graph and replayed: the coarse levels of the
