@@ -580,6 +580,32 @@ __global__ void __launch_bounds__(256) bk_visc_clip(const size_t n, const CcuVis
     EVI[i] = v;
 }
 
+// visc_from_C (Viscosity_structures.c:1784-1935), the modes without flavours / lithosphere overrides: the viscosity of every
+// integration point is multiplied with exp(c log(pre_comp[1]) + (1 - c) log(pre_comp[0])), c the composition there (or, with
+// cdepv_absolute, replaced by exp(c log(pre_comp[1]) + (1 - c) log(eta)))
+__global__ void __launch_bounds__(128) bk_visc_cdepv(const CcuGeom g, const CcuViscParams vp, const int *__restrict__ mat, const float *__restrict__ C, float *EVI)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    const int l2 = 2 * (vp.cdepv_layer ? mat[e] - 1 : 0);
+    float CC[8];
+    for(int a = 1; a <= 8; a++)
+    {
+        float v = C[elt_node(g, ey, ex, ez, a)];
+        if(vp.cdepv_check_range) { if(v < 0) v = 0.0f; if(v > 1) v = 1.0f; }
+        CC[a - 1] = v;
+    }
+    for(int jj = 0; jj < 8; jj++)
+    {
+        double cc = 0.0;
+        for(int kk = 0; kk < 8; kk++) cc += CC[kk] * c_sh.Nv[8 * kk + jj];
+        const size_t q = (size_t)e * 8 + jj;
+        if(vp.cdepv_absolute) EVI[q] = (float)exp(cc * vp.cdepv_logv[l2 + 1] + (1.0 - cc) * log((double)EVI[q]));
+        else EVI[q] = (float)((double)EVI[q] * exp(cc * vp.cdepv_logv[l2 + 1] + (1.0 - cc) * vp.cdepv_logv[l2]));
+    }
+}
+
 // visc_from_gint_to_ele (Nodal_mesh.c:559-581): element mean of the eight Gauss-point values (double sum)
 __global__ void __launch_bounds__(128) bk_gint_to_ele(const int nel, const float *__restrict__ EVI, float *VN)
 {
@@ -1854,6 +1880,35 @@ int ccu_set_viscosity_law(ccu_ctx *c, int tdepv, int rheol, int num_mat, const f
     return 0;
 }
 
+// E->viscosity.{CDEPV, layer_pre_comp, pre_comp, cdepv_absolute}, E->control.check_c_irange (Viscosity_structures.c:178-281): pre_comp holds
+// 2 * num_mat values with layer_pre_comp, else 2.  The flavour / lithosphere / crust variants of visc_from_C are not implemented.
+int ccu_set_cdepv(ccu_ctx *c, int on, int layer_pre_comp, const float *pre_comp, int absolute, int check_c_irange)
+{
+    if(!c) FAIL("null context");
+    CcuViscParams &v = c->visc;
+    v.cdepv = on != 0; v.cdepv_layer = layer_pre_comp != 0; v.cdepv_absolute = absolute != 0; v.cdepv_check_range = check_c_irange != 0;
+    if(!on) return 0;
+    if(!pre_comp) FAIL("set_cdepv: pre_comp missing");
+    const int n = layer_pre_comp ? 2 * v.num_mat : 2;
+    if(n > 80) FAIL("set_cdepv: too many material layers");
+    for(int i = 0; i < n; i++)
+    {
+        if(!(pre_comp[i] > 0.0f)) FAIL("set_cdepv: pre_comp must be positive");
+        v.cdepv_logv[i] = log((double)pre_comp[i]);
+    }
+    return 0;
+}
+// E->C (nodal composition, [nno] in the reference's node order) for hosts that keep the markers themselves
+int ccu_set_composition(ccu_ctx *c, const float *C)
+{
+    if(!c || !C) FAIL("set_composition: null argument");
+    Level &L = c->L[c->cfg.levmax];
+    if(!c->Cnode) CK(cudaMalloc(&c->Cnode, sizeof(float) * (size_t)L.g.nno));
+    CK(cudaMemcpyAsync(c->Cnode, C, sizeof(float) * (size_t)L.g.nno, cudaMemcpyHostToDevice, c->st));
+    SYNC(c);
+    return 0;
+}
+
 // E->viscosity.{SDEPV, sdepv_rheology, sdepv_expt, sdepv_trns, sdepv_misfit, sdepv_iter_damp, sdepv_start_from_newtonian, sdepv_trns_T,
 // sdepv_trns_c}, E->monitor.max_sdep_visc_iter (Viscosity_structures.c:150-310)
 int ccu_set_sdepv(ccu_ctx *c, int on, int rheology, const float *expt, const float *trns, float misfit, float iter_damp, int max_iter,
@@ -1918,8 +1973,15 @@ int ccu_get_system_viscosity(ccu_ctx *c)
     if(!c->mat) FAIL("get_system_viscosity: material groups missing");
     Level &L = c->L[c->cfg.levmax];
     if(c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4) && !L.have_xx) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
-    const bool sd = c->visc.sdepv != 0;
-    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr, L.EVI, sd ? 0 : 1);
+    const bool sd = c->visc.sdepv != 0, cd = c->visc.cdepv != 0;
+    const float *Ccomp = c->mk.ready ? (const float *)c->mk.C : (const float *)c->Cnode;
+    if(cd && !Ccomp) FAIL("get_system_viscosity: composition-dependent viscosity needs the nodal composition (device markers or ccu_set_composition)");
+    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr, L.EVI, (sd || cd) ? 0 : 1);
+    if(cd && !sd)
+    {   // temperature law, composition factor, then the min / max clip (Viscosity_structures.c:386-425)
+        LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);
+        LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);
+    }
     if(sd)
     {   // get_system_viscosity's order (Viscosity_structures.c:386-425): temperature law, stress dependence, then the min / max clip
         CcuViscParams &v = c->visc;
@@ -1928,8 +1990,9 @@ int ccu_get_system_viscosity(ccu_ctx *c)
         if(!L.have_xx) FAIL("get_system_viscosity: coordinates missing");
         if(!v.sdepv_start_from_newtonian || v.sdepv_visits)
             LAUNCH(c, bk_visc_sdepv, cdiv(L.g.nel, 64), 64, L.g, c->visc, first, (const int *)c->mat, (const float *)L.XX, (const float *)c->en.V, (const float *)c->T,
-                   c->mk.ready ? (const float *)c->mk.C : (const float *)nullptr, L.EVI);
+                   Ccomp, L.EVI);
         v.sdepv_visits++;
+        if(cd) LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);
         LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);
     }
     CK(cudaGetLastError());

@@ -23,6 +23,9 @@ struct CcuViscParams
     // stress-dependent viscosity (visc_from_S, Viscosity_structures.c:744; the outer loop of Drive_solvers.c:120-159)
     int sdepv = 0, sdepv_rheology = 1, sdepv_start_from_newtonian = 0, sdepv_max_iter = 50, sdepv_visits = 0;
     float sdepv_expt[40] = { 1.0f }, sdepv_trns[40] = { 1.0f }, sdepv_misfit = 0.001f, sdepv_iter_damp = 1.0f, sdepv_trns_T = 0, sdepv_trns_c = 0;
+    // composition-dependent viscosity (visc_from_C, Viscosity_structures.c:1784-1935; the plain prefactor mode and cdepv_absolute)
+    int cdepv = 0, cdepv_layer = 0, cdepv_absolute = 0, cdepv_check_range = 0;
+    double cdepv_logv[80] = { 0 };     // log(pre_comp[2 l]), log(pre_comp[2 l + 1]) per material layer (or one pair)
 };
 
 struct Level
@@ -125,6 +128,7 @@ struct ccu_ctx
     float *buoy = nullptr;         // [nno]
     float *nodal_tmp = nullptr, *nodal_tmp2 = nullptr;   // [nno finest] scratch for project_viscosity
     double *forceEF = nullptr;     // [8][nel] element force contributions (assemble_forces); [24][nel] for Rsphere
+    float *Cnode = nullptr;        // [nno] nodal composition handed in by the host (ccu_set_composition) when no marker set lives on the device
     bool rsphere = false;          // regional-spherical geometry (ccu_set_spherical_coordinates)
     // imposed non-zero boundary velocities (E->VB): the K.VB term of get_elt_f and velocities_conform_bcs
     float *VB[3] = { nullptr, nullptr, nullptr };   // [nno] natural order, finest level

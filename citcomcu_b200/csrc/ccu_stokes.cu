@@ -137,7 +137,7 @@ void ccu_destroy(ccu_ctx *c)
     }
     cudaFree(c->forceEF); cudaFree(c->sdepv_oldU); cudaFree(c->sdepv_dU);
     for(int d = 0; d < 3; d++) cudaFree(c->VB[d]);
-    cudaFree(c->vb_slot); cudaFree(c->vb_elems); cudaFree(c->vbEF);
+    cudaFree(c->vb_slot); cudaFree(c->vb_elems); cudaFree(c->vbEF); cudaFree(c->Cnode);
     cudaFree(c->P); cudaFree(c->r0); cudaFree(c->r1); cudaFree(c->r2); cudaFree(c->z0); cudaFree(c->z1); cudaFree(c->s1); cudaFree(c->s2); cudaFree(c->pAh);
     delete c;
 }

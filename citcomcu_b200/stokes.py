@@ -180,6 +180,16 @@ class StokesContext:
         check(self.lib.ccu_set_sdepv(self._ctx, int(on), int(rheology), e.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.c_float(misfit),
                                      C.c_float(iter_damp), int(max_iter), int(start_from_newtonian), C.c_float(trns_T), C.c_float(trns_c)))
 
+    def set_cdepv(self, on, pre_comp, layer_pre_comp=0, absolute=0, check_c_irange=0):
+        """visc_from_C (prefactor mode): pre_comp = (background, second material) viscosity factors, per layer with layer_pre_comp."""
+        pc = np.ascontiguousarray(pre_comp, dtype=np.float32)
+        check(self.lib.ccu_set_cdepv(self._ctx, int(on), int(layer_pre_comp), pc.ctypes.data_as(C.c_void_p), int(absolute), int(check_c_irange)))
+
+    def set_composition(self, Cn):
+        Cn = np.ascontiguousarray(Cn, dtype=np.float32)
+        assert Cn.size == self.nno(self.levmax)
+        check(self.lib.ccu_set_composition(self._ctx, Cn.ctypes.data_as(C.c_void_p)))
+
     def sdepv_iterations(self):
         n, m = C.c_int(0), C.c_double(0.0)
         check(self.lib.ccu_get_sdepv_iterations(self._ctx, C.byref(n), C.byref(m)))

@@ -28,7 +28,7 @@
  * Regional-spherical runs (Geometry=Rsphere): the node positions E->XX and E->SXX go up and the device uses the Rsphere branches of
  * the element routines; process_heating / thermal_buoyancy / heat_flux stay the reference's host code.
  *
- * Unsupported configurations stop the run loudly (there is no CPU fallback): composition-dependent viscosity, viscosity smoothing,
+ * Unsupported configurations stop the run loudly (there is no CPU fallback): Byerlee-type plastic viscosity, viscosity smoothing,
  * anisotropic viscosity, periodic side walls, heat-flux boundary conditions.
  *
  * citcom_dropin_funcs.c (same library) binds the INNER functions of the path one by one (CCU_DROPIN_FUNCS).
@@ -72,7 +72,9 @@ void ccu_dropin_init(struct All_variables *E)
         const char *sw = getenv("CCU_DROPIN_STOKES");
         g_ccu_device_geometry = (g_ccu_cartesian || !(sw && atoi(sw) == 0)) ? 1 : 0;
     }
-    if(E->viscosity.CDEPV || E->viscosity.BDEPV) die("composition- / Byerlee-dependent viscosity is not on the device path");
+    if(E->viscosity.BDEPV) die("Byerlee-type plastic viscosity (BDEPV) is not on the device path");
+    if(E->viscosity.CDEPV && (E->viscosity.cdepv_for_flavor || E->viscosity.const_lith_visc || E->viscosity.crust_option == 2))
+        die("composition-dependent viscosity: the flavour / crust / constant-lithosphere variants of visc_from_C are not on the device path");
     if(E->viscosity.SDEPV && E->viscosity.sdepv_rheology != 1 && E->viscosity.sdepv_rheology != 2)
         die("stress-dependent viscosity: sdepv_rheology 1 and 2 are on the device path, 3 (dimensional Arrhenius law) is not");
     if(E->viscosity.SDEPV && E->control.restart) die("stress-dependent viscosity with restart (strain rate of the restart velocity) is not on the device path");
@@ -137,6 +139,8 @@ void ccu_dropin_init(struct All_variables *E)
         if(E->parallel.nproc > 1) MPI_Allreduce(&any, &all, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
         if(all) CCU(ccu_set_velocity_bcs(g_ctx, E->VB[1] + 1, E->VB[2] + 1, E->VB[3] + 1));
     }
+    if(E->viscosity.CDEPV)
+        CCU(ccu_set_cdepv(g_ctx, 1, E->viscosity.layer_pre_comp, E->viscosity.pre_comp, E->viscosity.cdepv_absolute, E->control.check_c_irange));
     if(E->viscosity.SDEPV)
         CCU(ccu_set_sdepv(g_ctx, 1, E->viscosity.sdepv_rheology, E->viscosity.sdepv_expt, E->viscosity.sdepv_trns, E->viscosity.sdepv_misfit,
                           E->viscosity.sdepv_iter_damp, E->monitor.max_sdep_visc_iter, E->viscosity.sdepv_start_from_newtonian,
@@ -173,6 +177,7 @@ void general_stokes_solver(struct All_variables *E)
     rebuild = (g_calls == 0) || (E->viscosity.update_allowed && E->monitor.solution_cycles % E->control.KERNEL == 0)
               || (E->monitor.solution_cycles == E->control.freeze_surface_at_step);
     velocities_conform_bcs(E, E->U);
+    if(E->viscosity.CDEPV) CCU(ccu_set_composition(g_ctx, E->C + 1));      /* the markers' nodal composition as the host holds it */
     CCU(ccu_general_stokes_solver(g_ctx, E->T + 1, E->buoyancy + 1, rebuild, E->control.augmented_Lagr, E->control.augmented,
                                   E->control.precondition, 1, E->U, E->P + 1, &its, &res));
     if(rebuild) CCU(ccu_get_level_array(g_ctx, lm, CCU_ARR_EVI, E->EVI[lm] + 1));

@@ -134,6 +134,11 @@ int ccu_set_material(ccu_ctx *ctx, const int *mat /*[nel] = E->mat+1*/);
  * sdepv_start_from_newtonian, sdepv_trns_T, sdepv_trns_c}, E->monitor.max_sdep_visc_iter; call after ccu_set_viscosity_law */
 int ccu_set_sdepv(ccu_ctx *ctx, int on, int rheology, const float *expt, const float *trns, float misfit, float iter_damp, int max_iter,
                   int start_from_newtonian, float trns_T, float trns_c);
+/* Composition-dependent viscosity, visc_from_C (Viscosity_structures.c:1784-1935) in its prefactor mode (and cdepv_absolute):
+ * E->viscosity.{CDEPV, layer_pre_comp, pre_comp[2 or 2*num_mat], cdepv_absolute}, E->control.check_c_irange.  The composition is the
+ * device marker set's nodal C when one lives on the device, else what ccu_set_composition handed in (E->C+1). */
+int ccu_set_cdepv(ccu_ctx *ctx, int on, int layer_pre_comp, const float *pre_comp, int absolute, int check_c_irange);
+int ccu_set_composition(ccu_ctx *ctx, const float *C /*[nno]*/);
 /* iterations and relative velocity change of the last stress-dependent-viscosity loop (E->monitor.visc_iter_count) */
 int ccu_get_sdepv_iterations(ccu_ctx *ctx, int *count_out, double *misfit_out);
 int ccu_set_temperature(ccu_ctx *ctx, const float *T /*[nno] = E->T+1*/);

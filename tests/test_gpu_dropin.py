@@ -339,3 +339,29 @@ def test_baseline_configs_at_shipped_sizes(name, txt, monkeypatch):
         assert abs(sg[1] - sr[1]) <= 1e-3 * abs(sr[1]) + 1e-12, ("timestep", k)
         for q in (2, 3):
             assert abs(sg[q] - sr[q]) <= 1e-3 * abs(sr[q]) + 1e-9, ("Nu", k, q)
+
+
+@pytest.mark.parametrize("opts", [dict(pre_comp="1.0,50.0"), dict(pre_comp="1.0,0.05", cdepv_absolute="on"),
+                                  dict(pre_comp="1.0,20.0,1.0,30.0,1.0,40.0,1.0,50.0", layer_pre_comp="on")],
+                         ids=["prefactor", "absolute", "per_layer"])
+def test_composition_dependent_viscosity(opts, monkeypatch):
+    """CDEPV: visc_from_C (Viscosity_structures.c:1784-1935, prefactor mode / cdepv_absolute / per-layer factors) on the device in a
+    thermochemical run through the drop-in; the composition reaches the device as the host's nodal field E->C."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    base = dict(maxstep=4, accuracy=1e-5, composition=1, rayleigh_comp=1e6, markers_per_ele=8, comp_depth=0.605, storage_spacing=1)
+    txt = inputfile.tdepv_box(16, 16, 8, 3, CDEPV="on", **opts, **base)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_cdref_"), nsteps=nsteps)
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_cdgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "Stokes solve on CUDA device" in err
+    plain = po.run_harness(inputfile.tdepv_box(16, 16, 8, 3, **base), tempfile.mkdtemp(prefix="ccu_cd0_"), nsteps=0)[0][0]
+    r, g = ref[0], gpu[0]
+    acc = r.control()["accuracy"]
+    ratio = r["s0_EVI"] / plain["s0_EVI"]
+    assert max(ratio.max(), 1.0 / ratio.min()) > 10.0                       # the composition did change the viscosity
+    for k in range(nsteps + 1):
+        assert np.allclose(g[f"s{k}_EVI"], r[f"s{k}_EVI"], rtol=1e-5 if k == 0 else 1e-2), k
+        U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+        assert np.linalg.norm(Ug - U) <= 50 * acc * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
