@@ -415,6 +415,29 @@ int ccu_comm_init(ccu_ctx *c, int nprocx, int nprocy, int nprocz, int me_x, int 
             bits[s] = h.owned[n] ? 1 : 0;
         }
         for(size_t t = 0; t < sh_s.size(); t++) bits[sh_s[t]] |= 2;
+        {   // bits 4-7: distance to the nearest duplicated node, capped at 15 (the split colour passes of the overlapped sweep).  The
+            // duplicated nodes of a block decomposition are whole faces of the subdomain: the faces that have a neighbour.
+            const int nox = L.g.nox, noy = L.g.noy, noz = L.g.noz;
+            const bool lo_i = me[1] > 0, hi_i = me[1] < nproc[1] - 1, lo_j = me[0] > 0, hi_j = me[0] < nproc[0] - 1, lo_k = me[2] > 0, hi_k = me[2] < nproc[2] - 1;
+            size_t zero = 0;
+            for(int i = 0; i < noy; i++)
+                for(int j = 0; j < nox; j++)
+                    for(int k = 0; k < noz; k++)
+                    {
+                        int d = 15;
+                        if(lo_i) d = std::min(d, i);
+                        if(hi_i) d = std::min(d, noy - 1 - i);
+                        if(lo_j) d = std::min(d, j);
+                        if(hi_j) d = std::min(d, nox - 1 - j);
+                        if(lo_k) d = std::min(d, k);
+                        if(hi_k) d = std::min(d, noz - 1 - k);
+                        const int s = ccu_sidx(L.g, i, j, k);
+                        if((d == 0) != ((bits[s] & 2) != 0)) { delete m; FAIL("comm_init: duplicated-node table and subdomain faces disagree"); }
+                        zero += d == 0;
+                        bits[s] |= (unsigned char)(d << 4);
+                    }
+            if(zero != sh_s.size()) { delete m; FAIL("comm_init: duplicated-node count and subdomain faces disagree"); }
+        }
         CK(cudaMalloc(&H.bits, bits.size()));
         CK(cudaMemcpy(H.bits, bits.data(), bits.size(), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&H.face, sizeof(double) * 3 * std::max<size_t>(sh_s.size(), 1)));

@@ -162,14 +162,25 @@ __device__ __forceinline__ void ccu_relax_update(const CcuGeom &g, const double 
 // reference's OFFSIDE flag); those are relaxed separately from their summed rows (ccu_k_face_update), not here.
 #define CCU_B_OWNED 1
 #define CCU_B_SHARED 2
+// bits 4-7: Chebyshev distance (in nodes, capped at 15) to the nearest duplicated node.  A colour pass takes the nodes whose distance
+// lies in [drange & 0xff, drange >> 8]: CCU_D_ALL = every node that is not duplicated; the split passes of the overlapped sweep
+// (d_relax_sweeps) take "far" and "near" shells separately.
+#define CCU_D_RANGE(lo, hi) ((lo) | ((hi) << 8))
+#define CCU_D_ALL CCU_D_RANGE(1, 15)
+__device__ __forceinline__ bool ccu_skip_node(const unsigned char *__restrict__ bits, const int s, const int drange)
+{
+    if(!bits) return false;
+    const int d = bits[s] >> 4;
+    return d < (drange & 0xff) || d > (drange >> 8);
+}
 template <int C>
 __device__ __forceinline__ void ccu_relax_cell(const CcuGeom &g, const float *__restrict__ K, const double *__restrict__ BI,
                                                const double *__restrict__ F, double *x, const int cell,
-                                               const unsigned char *__restrict__ bits)
+                                               const unsigned char *__restrict__ bits, const int drange)
 {
     int i, j, k;
     if(!ccu_decode(g, C, cell, i, j, k)) return;
-    if(bits && (bits[C * g.NC + cell] & CCU_B_SHARED)) return;
+    if(ccu_skip_node(bits, C * g.NC + cell, drange)) return;
     double a0, a1, a2;
     ccu_row_product<C>(g, K, x, cell, a0, a1, a2);
     ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
@@ -180,22 +191,23 @@ __device__ __forceinline__ void ccu_relax_cell(const CcuGeom &g, const float *__
 template <int C>
 __global__ void __launch_bounds__(128) ccu_k_relax(const CcuGeom g, const float *__restrict__ K,
                                                     const double *__restrict__ BI, const double *__restrict__ F, double *x,
-                                                    const unsigned char *__restrict__ bits)
+                                                    const unsigned char *__restrict__ bits, const int drange)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if(cell >= g.NC) return;
-    ccu_relax_cell<C>(g, K, BI, F, x, cell, bits);
+    ccu_relax_cell<C>(g, K, BI, F, x, cell, bits, drange);
 }
 
 // T lanes per node, one colour per launch (mid-size levels)
 template <int T, int C>
 __global__ void __launch_bounds__(128) ccu_k_relax_lanes(const CcuGeom g, const float *__restrict__ K, const double *__restrict__ BI,
-                                                          const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
+                                                          const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits,
+                                                          const int drange)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int cell = tid / T, q = tid % T;
     int i, j, k;
-    const bool valid = cell < g.NC && ccu_decode(g, C, cell, i, j, k) && !(bits && (bits[C * g.NC + cell] & CCU_B_SHARED));
+    const bool valid = cell < g.NC && ccu_decode(g, C, cell, i, j, k) && !ccu_skip_node(bits, C * g.NC + cell, drange);
     double a0, a1, a2;
     ccu_row_product_lanes<T, C>(g, K, x, cell, q, valid, a0, a1, a2);
     if(valid && q == 0) ccu_relax_update(g, BI, F, x, C * g.NC + cell, a0, a1, a2);
@@ -735,14 +747,15 @@ __global__ void __launch_bounds__(256) ccu_k_build_KT(const CcuGeom g, const __g
 template <int U>
 __global__ void __launch_bounds__(128) ccu_k_relax_full(const CcuGeom g, const __grid_constant__ CcuStencil st, const int c,
                                                          const float *__restrict__ K, const float *__restrict__ KT, const double *__restrict__ BI,
-                                                         const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
+                                                         const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits,
+                                                         const int drange)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if(cell >= g.NC) return;
     int i, j, k;
     if(!ccu_decode(g, c, cell, i, j, k)) return;
     const int s = c * g.NC + cell;
-    if(bits && (bits[s] & CCU_B_SHARED)) return;
+    if(ccu_skip_node(bits, s, drange)) return;
     double a0, a1, a2;
     ccu_row_product_full<U>((size_t)g.NS, st.off[c], K, KT, x, s, a0, a1, a2);
     ccu_relax_update(g, BI, F, x, s, a0, a1, a2);
@@ -799,14 +812,15 @@ __global__ void __launch_bounds__(256) ccu_k_matvec_tab(const CcuGeom g, const _
 template <int U, int NA = 0>
 __global__ void __launch_bounds__(128) ccu_k_relax_tab(const CcuGeom g, const __grid_constant__ CcuStencil st, const int c,
                                                         const float *__restrict__ K, const double *__restrict__ BI,
-                                                        const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits)
+                                                        const double *__restrict__ F, double *x, const unsigned char *__restrict__ bits,
+                                                        const int drange)
 {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if(cell >= g.NC) return;
     int i, j, k;
     if(!ccu_decode(g, c, cell, i, j, k)) return;
     const int s = c * g.NC + cell;
-    if(bits && (bits[s] & CCU_B_SHARED)) return;
+    if(ccu_skip_node(bits, s, drange)) return;
     double a0, a1, a2;
     ccu_row_product_tab<U, NA>((size_t)g.NS, st.off[c], K, x, s, a0, a1, a2);
     ccu_relax_update(g, BI, F, x, s, a0, a1, a2);

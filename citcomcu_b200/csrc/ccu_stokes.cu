@@ -49,6 +49,13 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     c->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));   // own stream: the legacy stream cannot be captured
     c->own_stream = c->st;
+    {   // highest priority: the short exchange kernels must not queue behind a full grid of colour-pass CTAs
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+    }
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for(int lev = cfg->levmin; lev <= cfg->levmax; lev++)
     {
         Level &L = c->L[lev];
@@ -127,6 +134,9 @@ void ccu_destroy(ccu_ctx *c)
     drop_graphs(c);
     ccu_comm_destroy(c);
     if(c->own_stream) cudaStreamDestroy(c->own_stream);
+    if(c->st2) cudaStreamDestroy(c->st2);
+    if(c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if(c->ev_join) cudaEventDestroy(c->ev_join);
     for(auto &r : c->prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for(auto e : c->prof_pool) cudaEventDestroy(e);
     {   // marker migration scratch
@@ -171,6 +181,7 @@ int ccu_set_option(ccu_ctx *c, int option, int value)
     case CCU_OPT_RELAX_FULL: c->opt_relax_full = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_MATVEC_FULL: c->opt_matvec_full = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_P2P_HALO: if(c->comm) c->comm->opt_p2p = value != 0; drop_graphs(c); return 0;
+    case CCU_OPT_HALO_OVERLAP: c->opt_halo_overlap = value; drop_graphs(c); return 0;
     case CCU_OPT_COL_WF: c->opt_col_wf = value != 0; if(c->coarse) c->coarse->opt_col_wf = c->opt_col_wf; drop_graphs(c); return 0;
     case CCU_OPT_COL_SHAPE: if(value < 0 || value > 2) FAIL("column shape must be 0..2"); c->opt_col_shape = value; drop_graphs(c); return col_refresh_all(c);
     case CCU_OPT_BOTTOM_CLUSTER: c->opt_bottom_cluster = value; if(c->coarse) c->coarse->opt_bottom_cluster = value; drop_graphs(c); return 0;
@@ -198,6 +209,7 @@ int ccu_get_option(ccu_ctx *c, int option, int lev, int *value)
     case CCU_OPT_RELAX_FULL: *value = c->L[lev].have_KT && c->opt_relax_full; return 0;
     case CCU_OPT_MATVEC_FULL: *value = c->L[lev].have_KT && c->opt_matvec_full; return 0;
     case CCU_OPT_P2P_HALO: *value = c->comm && c->comm->p2p && c->comm->opt_p2p; return 0;
+    case CCU_OPT_HALO_OVERLAP: *value = c->opt_halo_overlap; return 0;
     case CCU_OPT_COL_WF: *value = c->opt_col_wf; return 0;
     case CCU_OPT_COL_SHAPE: *value = c->L[lev].col_shape; return 0;
     case CCU_OPT_COL_NODES: *value = c->opt_col_nodes; return 0;
@@ -329,6 +341,16 @@ int ccu_set_transfer_weights(ccu_ctx *c, int lev, const float *TWW, const float 
 }
 
 // coefficient-major copy of elt_del for div_u / grad_p; call after every write of L.elt_del
+void ccu_fork_stream(ccu_ctx *c)
+{
+    cudaEventRecord(c->ev_fork, c->st);
+    cudaStreamWaitEvent(c->st2, c->ev_fork, 0);
+}
+void ccu_join_stream(ccu_ctx *c)
+{
+    cudaEventRecord(c->ev_join, c->st2);
+    cudaStreamWaitEvent(c->st, c->ev_join, 0);
+}
 void ccu_eco_changed(ccu_ctx *c, int lev)
 {
     Level &L = c->L[lev];
@@ -626,18 +648,28 @@ static int ensure_smem_tables(ccu_ctx *c, Level &L)
 }
 
 
+// distance window of colour `col` (passes run 7 .. 0) in the three modes of a sweep: 0 = every node that is not duplicated,
+// 1 = "far" (more than p + 1 nodes away from a duplicated node, p = 7 - col the pass number), 2 = "near" (the rest).  The far part of
+// pass p only reads nodes at distance > p, i.e. far parts of earlier passes and values no near pass or face update of this sweep has
+// touched yet, so the eight far passes can run while the duplicated nodes are exchanged; the near parts follow in pass order and
+// see exactly the values they see in the unsplit sweep (bitwise the same result, tests/test_gpu_multi.py).
+static inline int pass_window(int col, int mode)
+{
+    const int p = 7 - col;
+    return mode == 0 ? CCU_D_ALL : (mode == 1 ? CCU_D_RANGE(p + 2, 15) : CCU_D_RANGE(1, p + 1));
+}
 template <int T>
-static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F, const unsigned char *bits)
+static void launch_relax_lanes(ccu_ctx *c, Level &L, double *x, const double *F, const unsigned char *bits, int mode)
 {
     const unsigned grid = cdiv((size_t)L.g.NC * T, 128);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 7>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 6>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 5>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 4>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 3>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 2>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 1>), grid, 128, L.g, L.K, L.BI, F, x, bits);
-    LAUNCH(c, (ccu_k_relax_lanes<T, 0>), grid, 128, L.g, L.K, L.BI, F, x, bits);
+    LAUNCH(c, (ccu_k_relax_lanes<T, 7>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(7, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 6>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(6, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 5>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(5, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 4>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(4, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 3>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(3, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 2>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(2, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 1>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(1, mode));
+    LAUNCH(c, (ccu_k_relax_lanes<T, 0>), grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(0, mode));
 }
 // Multi-subdomain sweeps start with the duplicated face nodes: every owner computes its part of their rows, one halo
 // round sums the parts, and all owners apply the same damped-Jacobi update (the reference's OFFSIDE treatment,
@@ -705,40 +737,52 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
     }
     const unsigned grid = cdiv(L.g.NC, 128);
     const unsigned char *bits = c->multi() ? c->comm->halo[&L - c->L].bits : nullptr;
-    for(int s = 0; s < cycles; s++)
-    {   // colours 7..0: odd-odd-odd nodes first, the coarse-grid nodes (colour 0) last
-        if(bits) relax_faces(c, L, x, F);
-        if(T == 32) { launch_relax_lanes<32>(c, L, x, F, bits); continue; }
-        if(T == 4)
-        {   // mid levels: four lanes per node
-            launch_relax_lanes<4>(c, L, x, F, bits);
-            continue;
-        }
+    // the eight colour passes 7 .. 0 (odd-odd-odd nodes first, the coarse-grid nodes last) over the distance window of `mode`
+    auto passes = [&](int mode) {
+        if(T == 32) { launch_relax_lanes<32>(c, L, x, F, bits, mode); return; }
+        if(T == 4) { launch_relax_lanes<4>(c, L, x, F, bits, mode); return; }      // mid levels: four lanes per node
         if(c->opt_relax_full && L.have_KT)
         {   // full rows: every coefficient streams once per sweep
             const CcuStencil st = ccu_make_stencil(L.g);
-            for(int col = 7; col >= 0; col--) LAUNCH(c, ccu_k_relax_full<2>, grid, 128, L.g, st, col, L.K, L.KT, L.BI, F, x, bits);
-            continue;
+            for(int col = 7; col >= 0; col--) LAUNCH(c, ccu_k_relax_full<2>, grid, 128, L.g, st, col, L.K, L.KT, L.BI, F, x, bits, pass_window(col, mode));
+            return;
         }
         if(c->opt_relax_tab)
         {
             const CcuStencil st = ccu_make_stencil(L.g);
             for(int col = 7; col >= 0; col--)
             {
-                if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
-                else if(c->opt_relax_tab >= 4) LAUNCH(c, ccu_k_relax_tab<4>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
-                else LAUNCH(c, ccu_k_relax_tab<2>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits);
+                if(c->opt_relax_tab >= 7) LAUNCH(c, ccu_k_relax_tab<7>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits, pass_window(col, mode));
+                else if(c->opt_relax_tab >= 4) LAUNCH(c, ccu_k_relax_tab<4>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits, pass_window(col, mode));
+                else LAUNCH(c, ccu_k_relax_tab<2>, grid, 128, L.g, st, col, L.K, L.BI, F, x, bits, pass_window(col, mode));
             }
-            continue;
+            return;
         }
-        LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<4>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<3>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<2>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<1>, grid, 128, L.g, L.K, L.BI, F, x, bits);
-        LAUNCH(c, ccu_k_relax<0>, grid, 128, L.g, L.K, L.BI, F, x, bits);
+        LAUNCH(c, ccu_k_relax<7>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(7, mode));
+        LAUNCH(c, ccu_k_relax<6>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(6, mode));
+        LAUNCH(c, ccu_k_relax<5>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(5, mode));
+        LAUNCH(c, ccu_k_relax<4>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(4, mode));
+        LAUNCH(c, ccu_k_relax<3>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(3, mode));
+        LAUNCH(c, ccu_k_relax<2>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(2, mode));
+        LAUNCH(c, ccu_k_relax<1>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(1, mode));
+        LAUNCH(c, ccu_k_relax<0>, grid, 128, L.g, L.K, L.BI, F, x, bits, pass_window(0, mode));
+    };
+    // overlap pays where the far shells hold most of the level; tiny subdomains are all "near"
+    const bool overlap = bits && c->opt_halo_overlap && c->st2 && c->comm->halo[&L - c->L].n_shared > 0 &&
+                         (c->opt_halo_overlap > 1 || L.g.nno > 400000);
+    for(int s = 0; s < cycles; s++)
+    {
+        if(!bits) { passes(0); continue; }
+        if(!overlap) { relax_faces(c, L, x, F); passes(0); continue; }
+        // duplicated nodes on the second stream (partial rows, exchange, damped-Jacobi update), far shells meanwhile on the first
+        cudaStream_t st = c->st;
+        ccu_fork_stream(c);
+        c->st = c->st2;
+        relax_faces(c, L, x, F);
+        c->st = st;
+        passes(1);
+        ccu_join_stream(c);
+        passes(2);
     }
 }
 

@@ -69,7 +69,7 @@ class StokesContext:
         check(self.lib.ccu_set_stream(self._ctx, C.c_void_p(cuda_stream)))
 
     OPTIONS = dict(graphs=0, small_nodes=1, warp_nodes=2, quad_nodes=3, lanes_large=4, matvec_tab=5, relax_tab=6, smem_nodes=7,
-                   col_nodes=9, relax_col=10, matvec_col=11, col_shape=13, col_wf=14, bottom_cluster=15, full_nodes=18, relax_full=19, matvec_full=20, p2p_halo=21)
+                   col_nodes=9, relax_col=10, matvec_col=11, col_shape=13, col_wf=14, bottom_cluster=15, full_nodes=18, relax_full=19, matvec_full=20, p2p_halo=21, halo_overlap=22)
 
     def set_option(self, name, value):
         check(self.lib.ccu_set_option(self._ctx, self.OPTIONS[name], int(value)))

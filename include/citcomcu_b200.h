@@ -69,6 +69,10 @@ enum { CCU_OPT_GRAPHS = 0, CCU_OPT_SMALL_NODES = 1, CCU_OPT_WARP_NODES = 2, CCU_
        CCU_OPT_P2P_HALO = 21 /* subdomain-per-GPU runs: 1 = halo sums through peer memory (CUDA IPC landing buffers over NVLink: a push kernel,
         * a flag per sender, a wait kernel; no NCCL call per exchange), 0 (default: measured faster on 8 x B200) = grouped ncclSend/ncclRecv.
         * Set it identically on all ranks. */,
+       CCU_OPT_HALO_OVERLAP = 22 /* subdomain-per-GPU runs: 1 = the duplicated-node exchange of a smoother sweep runs on a second (high-priority)
+        * stream while the colour passes relax the nodes far enough from the subdomain faces; the passes are split by distance so that the
+        * result is bitwise that of the serial order (levels with more than 4e5 nodes per subdomain; 2 = every level).  0 (default: the
+        * split passes and the cross-stream joins cost more than the hidden exchange, measured on B200) = exchange first, then the passes. */,
        CCU_OPT_BOTTOM_CLUSTER = 15 /* 1 (default): the shared-memory bottom smoother runs on an 8-CTA cluster with fp64 rows in
         * distributed shared memory (ccu_k_relax_bottom); 0: on one SM (ccu_k_relax_smem) */ };
 int ccu_set_option(ccu_ctx *ctx, int option, int value);

@@ -61,8 +61,24 @@ def run_rank(rank, world, text, uid_q, out_q, accuracy, agglomerate=True, device
         d0, Ad = ctx.gauss_seidel(f, 2, lm, 0)
         res["gs_d0"], res["gs_Ad"] = d0, Ad
         res["gs_KD"] = ctx.n_assemble_del2_u(d0, lm, 1)
+        # overlapped sweeps (duplicated-node exchange on a second stream, colour passes split by distance from the faces) give the
+        # serial order's result bit for bit: smoother calls on the two finest levels, then the whole solve
+        same = True
+        for lev in (lm, lm - 1):
+            fl = ctx.strip_bcs_from_residual(prob.local_slice(seeded_global_vector(gp, lev, 77 + lev), lev, 3), lev)
+            out = {}
+            for mode in (0, 2):
+                ctx.set_option("halo_overlap", mode)
+                out[mode] = ctx.gauss_seidel(fl, 3, lev, 0)
+            same = same and np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
+        res["overlap_sweeps_bitwise"] = bool(same)
+        ctx.set_option("halo_overlap", 0)
+        U0, P0, its0, _ = ctx.general_stokes_solver(T, b, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
+                                                    precondition=ctl["precondition"], guess=0)
+        ctx.set_option("halo_overlap", 2)
         U, P, its, r = ctx.general_stokes_solver(T, b, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
                                                  precondition=ctl["precondition"], guess=0)
+        res["overlap_solve_bitwise"] = bool(np.array_equal(U, U0) and np.array_equal(P, P0) and its == its0)
         res["U"], res["P"], res["its"] = U, P, its
         # two coupled timesteps on the subdomains: energy step, buoyancy with cross-rank layer averages, Stokes solve
         noz = prob.dims(lm)[2]

@@ -88,6 +88,7 @@ def test_subdomains_match_single_gpu_and_reference(nproc, agglomerate):
         assert rel(r["gradp"], prob.local_slice(ctx.assemble_grad_p(pg, lm), lm, 3)) < 1e-12
         # gauss_seidel returns Ad = K d0 also across subdomains
         assert rel(r["gs_Ad"], r["gs_KD"]) < 1e-12
+        assert r["overlap_sweeps_bitwise"] and r["overlap_solve_bitwise"]
     Ug, Pg, its_g, _ = ctx.general_stokes_solver(Tg, bg, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
                                                  precondition=ctl["precondition"], guess=0)
     # the same two coupled timesteps on the single GPU (energy -> buoyancy -> Stokes): T and buoyancy agree to the solver tolerance
