@@ -171,3 +171,22 @@ def test_marker_exchange_routes(nproc):
             assert rc[code] == send[rs, back]
             total_recv += rc[code]
     assert total_recv == int(send.sum())
+
+
+@pytest.mark.parametrize("nproc", [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 1), (2, 2, 2), (3, 2, 2)])
+def test_duplicated_nodes_are_the_faces_with_a_neighbour(nproc):
+    """ccu_comm_init derives the distance-to-duplicated-node byte of the overlapped sweep from the subdomain faces that have a
+    neighbour (y faces <-> i, x faces <-> j, z faces <-> k) and refuses to start when that set differs from the duplicated-node
+    table: the two agree for every rank of every processor grid bench.py and the tests use."""
+    nox, noy, noz = 5, 7, 4
+    for me in all_ranks(nproc):
+        t = decomp.halo_tables(nproc, me, nox, noy, noz)
+        shared = np.zeros(nox * noy * noz, dtype=bool)
+        shared[t["sh_n"]] = True
+        i, j, k = np.meshgrid(np.arange(noy), np.arange(nox), np.arange(noz), indexing="ij")
+        d = np.full(i.shape, 15)
+        for has, dist in ((me[1] > 0, i), (me[1] < nproc[1] - 1, noy - 1 - i), (me[0] > 0, j), (me[0] < nproc[0] - 1, nox - 1 - j),
+                          (me[2] > 0, k), (me[2] < nproc[2] - 1, noz - 1 - k)):
+            if has:
+                d = np.minimum(d, dist)
+        assert np.array_equal((d == 0).reshape(-1), shared), me
