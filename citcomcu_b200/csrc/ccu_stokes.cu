@@ -49,10 +49,10 @@ int ccu_create(const ccu_config *cfg, ccu_ctx **out)
     c->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));   // own stream: the legacy stream cannot be captured
     c->own_stream = c->st;
-    {   // highest priority: the short exchange kernels must not queue behind a full grid of colour-pass CTAs
+    {   // lowest priority: the colour passes queued here must not starve the short exchange kernels on the context's stream
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, lo));
     }
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -774,13 +774,14 @@ static void d_relax_sweeps(ccu_ctx *c, Level &L, double *x, const double *F, int
     {
         if(!bits) { passes(0); continue; }
         if(!overlap) { relax_faces(c, L, x, F); passes(0); continue; }
-        // duplicated nodes on the second stream (partial rows, exchange, damped-Jacobi update), far shells meanwhile on the first
+        // duplicated nodes (partial rows, exchange, damped-Jacobi update) stay on the context's stream -- every NCCL call of the
+        // library is issued there -- and are queued first; the far shells relax meanwhile on the second stream
         cudaStream_t st = c->st;
         ccu_fork_stream(c);
-        c->st = c->st2;
         relax_faces(c, L, x, F);
-        c->st = st;
+        c->st = c->st2;
         passes(1);
+        c->st = st;
         ccu_join_stream(c);
         passes(2);
     }
