@@ -124,8 +124,9 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.parametrize("nproc", [(2, 1, 1), (2, 2, 2)])
-def test_multi_rank_reference_with_gpu_stokes(nproc, monkeypatch):
+@pytest.mark.parametrize("nproc,geometry", [((2, 1, 1), "cart3d"), ((2, 2, 2), "cart3d"), ((2, 1, 1), "Rsphere"), ((1, 1, 2), "Rsphere")],
+                         ids=["2x1x1", "2x2x2", "2x1x1-rsphere", "1x1x2-rsphere"])
+def test_multi_rank_reference_with_gpu_stokes(nproc, geometry, monkeypatch):
     """The unmodified reference on several MPI ranks (oracle/mpi_shim), one GPU per rank: every rank's general_stokes_solver and
     PG_timestep run on its device, halo sums and reductions over NCCL (the id travels through the reference's own MPI_Bcast)."""
     world = nproc[0] * nproc[1] * nproc[2]
@@ -133,7 +134,11 @@ def test_multi_rank_reference_with_gpu_stokes(nproc, monkeypatch):
         pytest.skip(f"needs {world} GPUs")
     if not po.have_ref() or not DROPIN.exists():
         pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
-    txt = inputfile.tdepv_box(16, 16, 8, 3, nproc=nproc, maxstep=3, accuracy=1e-5)
+    if geometry == "Rsphere":       # BASELINE config 4's regional block split over two ranks (the shipped input1 runs 2x2x1)
+        txt = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-5, nproc=nproc, TDEPV="on", VISC_UPDATE="on", update_every_steps=1,
+                                       perturbmag=0.05)
+    else:
+        txt = inputfile.tdepv_box(16, 16, 8, 3, nproc=nproc, maxstep=3, accuracy=1e-5)
     nsteps = 2
     ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_nref_"), nsteps=nsteps, nproc=world)
     monkeypatch.setenv("CCU_DROPIN_ENERGY", "1")
