@@ -261,15 +261,18 @@ def test_regional_sphere_solver_on_device(funcs, monkeypatch):
 
 
 @pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
-@pytest.mark.parametrize("tdepv", ["off", "on"])
+@pytest.mark.parametrize("tdepv", ["off", "on", "on-eba"])
 def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, energy, monkeypatch):
     """BASELINE config 4 geometry through the whole-step bindings: operator assembly (Rsphere get_elt_k / get_elt_g / get_elt_f) and the
     Stokes solve on the device; in the second variant also the SUPG energy step with the Rsphere branches of pg_shape_fn /
     element_residual (Advection_diffusion.c:506-528, 620-640, 668-674)."""
     if not po.have_ref() or not DROPIN.exists():
         pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
-    txt = inputfile.input1_rsphere(levels=3, maxstep=5, accuracy=1e-5, TDEPV=tdepv, VISC_UPDATE="on", update_every_steps=1, storage_spacing=1,
-                                   perturbmag=0.05)
+    # "on-eba": BASELINE config 4 proper, the extended-Boussinesq terms of the shipped input1 (adiabatic + viscous heating, computed by
+    # the reference's host process_heating and uploaded before each device energy step)
+    eba = dict(adi_heating=1, visc_heating=1, surf_temp=0.078947) if tdepv == "on-eba" else {}
+    txt = inputfile.input1_rsphere(levels=3, maxstep=5, accuracy=1e-5, TDEPV=tdepv.split("-")[0], VISC_UPDATE="on", update_every_steps=1,
+                                   storage_spacing=1, perturbmag=0.05, **eba)
     nsteps = 4
     ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rswref_"), nsteps=nsteps)
     monkeypatch.setenv("CCU_DROPIN_ENERGY", str(energy))
