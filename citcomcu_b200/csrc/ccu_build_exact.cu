@@ -231,6 +231,29 @@ __device__ __forceinline__ void sph_ba(const SphTrig &P, const SphTrig &A, int i
     ba[4] = gnx2 * cc1 + (gnx0 * cc3 + shp * (c1[2] - cc1)) * ra;
     ba[5] = gnx2 * cc2 + ((gnx1 * cc3 + shp * c2[2]) * si - shp * cc2) * ra;
 }
+// strain_rate_2_inv, Rsphere branch (Viscosity_structures.c:996-1040), before the SQRT / halving step: the six strain-rate components
+// at the pressure point from the nodal (u_theta, u_phi, u_r) taken as scalars, accumulated in float as the reference's Vxyz
+__device__ __forceinline__ float sph_strain2(const float X[3][8], const float VV[3][8], float gnx[3][8])
+{
+    double x[3], th, ph, ri;
+    sph_point(X, c_sh.Np, 1, x);
+    sph_rotate_gnx(x, gnx);                          // gnx comes in as the Cartesian derivatives at the pressure point
+    sph_rtf(x, th, ph, ri);
+    const double ct = cos(th), st = sin(th);
+    float v1 = 0.0f, v2 = 0.0f, v3 = 0.0f, v4 = 0.0f, v5 = 0.0f, v6 = 0.0f;
+    for(int i = 0; i < 8; i++)
+    {
+        const double N = c_sh.Np[i];
+        v1 = (float)((double)v1 + ((double)(VV[0][i] * gnx[0][i]) + VV[2][i] * N) * ri);
+        v2 = (float)((double)v2 + (((double)(VV[1][i] * gnx[1][i]) + VV[0][i] * N * ct) / st + VV[2][i] * N) * ri);
+        v3 = v3 + VV[2][i] * gnx[2][i];
+        v4 = (float)((double)v4 + (((double)(VV[0][i] * gnx[1][i]) - VV[1][i] * N * ct) / st + (double)(VV[1][i] * gnx[0][i])) * ri);
+        v5 = (float)((double)v5 + ((double)(VV[0][i] * gnx[2][i]) + ri * ((double)(VV[2][i] * gnx[0][i]) - VV[0][i] * N)));
+        v6 = (float)((double)v6 + ((double)(VV[1][i] * gnx[2][i]) + ri * ((double)(VV[2][i] * gnx[1][i]) / st - VV[1][i] * N)));
+    }
+    const double e11 = 2.0 * v1, e22 = 2.0 * v2, e33 = 2.0 * v3, e12 = v4, e13 = v5, e23 = v6;
+    return (float)(e11 * e11 + e12 * e12 * 2.0 + e22 * e22 + e23 * e23 * 2.0 + e33 * e33 + e13 * e13 * 2.0);
+}
 // the reference evaluates Cc / Ccx on the FIRST element of a radial column ((el-1) % ELZ == 0) and keeps them for the elements above
 // (static struct CC in get_elt_k / get_elt_g / get_elt_f): the point basis comes from that element's (float) coordinates
 __device__ __forceinline__ SphTrig sph_column_point_trig(const CcuGeom &g, const float *__restrict__ XX, int ey, int ex, int ez, const float X[3][8],
@@ -1263,7 +1286,7 @@ __global__ void __launch_bounds__(64) ek_process_heating(const CcuGeom g, const 
                                                          const float *__restrict__ T, const float *__restrict__ V,
                                                          const float *__restrict__ expansivity, const int adi_on, const int visc_on,
                                                          const float disptn, const float surf_temp, const float Atemp,
-                                                         float *heat_adi, float *heat_visc, float *heat_latent)
+                                                         float *heat_adi, float *heat_visc, float *heat_latent, const int sph)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -1288,6 +1311,7 @@ __global__ void __launch_bounds__(64) ek_process_heating(const CcuGeom g, const 
         for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) ed[p][q] = 0.5 * (dudx[p][q] + dudx[q][p]);
         float eedot = (float)(ed[0][0] * ed[0][0] + ed[0][1] * ed[0][1] * 2.0 + ed[1][1] * ed[1][1] + ed[1][2] * ed[1][2] * 2.0 +
                               ed[2][2] * ed[2][2] + ed[0][2] * ed[0][2] * 2.0);
+        if(sph) eedot = sph_strain2(X, VV, gnx);
         eedot = (float)((double)eedot * 0.5);
         double temp2 = 0.0;
         for(int i = 0; i < 8; i++) temp2 += EVI[(size_t)e * 8 + i];
@@ -2401,7 +2425,7 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
 int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
 {   // (heating_latent: ccu_get_heating_latent)
     if(!c) FAIL("null context");
-    CART_ONLY(c, "process_heating");
+    if(c->rsphere && c->en.phase_on) FAIL("process_heating: phase changes are Cartesian only on the device");
     if(ensure_energy(c)) return 1;
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
@@ -2411,7 +2435,7 @@ int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_
     if(!E.have_params) FAIL("process_heating: ccu_set_energy_params first (expansivity)");
     if(E.adi_heating || E.visc_heating)
         LAUNCH(c, ek_process_heating, cdiv(L.g.nel, 64), 64, L.g, L.XX, L.EVI, c->T, E.V, E.expansivity, E.adi_heating, E.visc_heating,
-               E.disptn, E.surf_temp, E.Atemp_heat, E.heat_adi, E.heat_visc, (float *)nullptr);
+               E.disptn, E.surf_temp, E.Atemp_heat, E.heat_adi, E.heat_visc, (float *)nullptr, c->rsphere ? 1 : 0);
     if(E.phase_on)
     {   // latent heating from the phase functions of the last phase_change call (the reference reads E->Fas670 / Fas410 as they stand)
         CcuPhase ph; ph.zlm = E.ph.zlm; ph.z410 = E.ph.z410; ph.Ra670 = E.ph.Ra670; ph.clap670 = E.ph.clap670; ph.width670 = E.ph.width670;

@@ -185,5 +185,5 @@ def test_regional_sphere_operator_construction(tdepv):
     assert np.linalg.norm(V - d["s0_U"]) < 20 * ctl["accuracy"] * np.linalg.norm(d["s0_U"])
     # the entry points that only know the Cartesian element routines refuse the context
     with pytest.raises(Exception, match="Cartesian geometry only"):
-        ctx.process_heating()
+        ctx.get_stress_topo()
     ctx.close()

@@ -328,3 +328,33 @@ def test_output_staging_writes_the_reference_files():
     assert mine[0] == ref_temp[0] and len(mine) == len(ref_temp)
     for a, b in zip(mine[1:-1], ref_temp[1:-1]):
         assert a.split()[:2] == b.split()[:2]
+
+
+def test_regional_sphere_heating_and_energy_step():
+    """Regional-spherical geometry, kernel level: process_heating (Rsphere branch of strain_rate_2_inv, Viscosity_structures.c:996-1040,
+    adiabatic heating from the radial velocity) and PG_timestep (Rsphere branches of pg_shape_fn / element_residual) on the
+    reference's step-0 state against its step-1 arrays."""
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    from test_gpu_build import build_ctx
+    text = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-6, TDEPV="on", perturbmag=0.05, adi_heating=1, visc_heating=1,
+                                    surf_temp=0.078947)
+    d = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_rsheat_")), nsteps=2, kat=True)[0][0]
+    ctx = build_ctx(d, 0, 0.0)
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    eb = d["s1_eba"]
+    ctx.set_heating_params(1, 1, eb[0], eb[1], eb[2])
+    load_s0(d, ctx)
+    ctx.set_element_viscosity(d.levmax, d["s0_EVI"])
+    adi, visc = ctx.process_heating()
+    assert np.abs(d["s1_heating_adi"]).max() > 0 and np.abs(d["s1_heating_visc"]).max() > 0
+    assert ulps(adi, d["s1_heating_adi"]) <= 2.0
+    assert ulps(visc, d["s1_heating_visc"]) <= 8.0, ulps(visc, d["s1_heating_visc"])
+    T, Tdot, dt, Tint = ctx.PG_timestep(d["s0_T"], d["s0_Tdot"])
+    assert abs(dt - d["s1_scalars"][1]) <= 1e-6 * d["s1_scalars"][1]
+    assert ulps(T, d["s1_T"]) <= 8.0, ulps(T, d["s1_T"])
+    # the entry points without an Rsphere branch refuse the context
+    with pytest.raises(Exception, match="Cartesian geometry only"):
+        ctx.heat_flux()
+    ctx.close()
