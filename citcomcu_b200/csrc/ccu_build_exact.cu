@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(128) bk_visc(const CcuGeom g, const CcuViscPar
 //     eta <- [2] eta / (1 + scale eta^(1 - 1/n)),   scale = (2 edot / sigma_trans)^(1 - 1/n)
 __global__ void __launch_bounds__(64) bk_visc_sdepv(const CcuGeom g, const CcuViscParams vp, const int first, const int *__restrict__ mat,
                                                     const float *__restrict__ XX, const float *__restrict__ V, const float *__restrict__ T,
-                                                    const float *__restrict__ Cn, float *EVI)
+                                                    const float *__restrict__ Cn, float *EVI, const int sph)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -561,8 +561,9 @@ __global__ void __launch_bounds__(64) bk_visc_sdepv(const CcuGeom g, const CcuVi
                 for(int q = 0; q < 3; q++) dudx[p][q] += VV[p][i] * gnx[q][i];
         double ed[3][3];
         for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) ed[p][q] = 0.5 * (dudx[p][q] + dudx[q][p]);
-        const float ee = (float)(ed[0][0] * ed[0][0] + ed[0][1] * ed[0][1] * 2.0 + ed[1][1] * ed[1][1] + ed[1][2] * ed[1][2] * 2.0 +
-                                 ed[2][2] * ed[2][2] + ed[0][2] * ed[0][2] * 2.0);
+        float ee = (float)(ed[0][0] * ed[0][0] + ed[0][1] * ed[0][1] * 2.0 + ed[1][1] * ed[1][1] + ed[1][2] * ed[1][2] * 2.0 +
+                           ed[2][2] * ed[2][2] + ed[0][2] * ed[0][2] * 2.0);
+        if(sph) ee = sph_strain2(X, VV, gnx);
         eedot = (float)sqrt(0.5 * (double)ee);
     }
     const int l = mat[e] - 1;
@@ -2014,7 +2015,7 @@ int ccu_get_system_viscosity(ccu_ctx *c)
         if(!L.have_xx) FAIL("get_system_viscosity: coordinates missing");
         if(!v.sdepv_start_from_newtonian || v.sdepv_visits)
             LAUNCH(c, bk_visc_sdepv, cdiv(L.g.nel, 64), 64, L.g, c->visc, first, (const int *)c->mat, (const float *)L.XX, (const float *)c->en.V, (const float *)c->T,
-                   Ccomp, L.EVI);
+                   Ccomp, L.EVI, c->rsphere ? 1 : 0);
         v.sdepv_visits++;
         if(cd) LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);
         LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);

@@ -1216,7 +1216,6 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     // the K.VB force term reads the viscosity as it stands BEFORE this call's update (Drive_solvers.c:107 comes ahead of :124);
     // at the very first call that is the one common_initial_fields evaluated from the initial state (Instructions.c:1233)
     if(c->have_vb && !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
-    if(c->rsphere && c->visc.sdepv) FAIL("general_stokes_solver: stress-dependent viscosity is Cartesian only on the device (strain_rate_2_inv has no Rsphere branch here)");
     if(ccu_assemble_forces(c, buoyancy, nullptr)) return 1;
     if(rebuild)
     {

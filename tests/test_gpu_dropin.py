@@ -180,15 +180,18 @@ def test_busse_case2_shipped_example(monkeypatch):
         assert np.allclose(g[f"s{k}_EVI"], r[f"s{k}_EVI"], rtol=1e-3), k      # viscosity contrast of the law: exp(+-8)
 
 
-@pytest.mark.parametrize("rheology,damp", [(1, 1.0), (2, 1.0), (1, 0.7)])
-def test_stress_dependent_viscosity_loop(rheology, damp, monkeypatch):
+@pytest.mark.parametrize("rheology,damp,geometry", [(1, 1.0, "cart3d"), (2, 1.0, "cart3d"), (1, 0.7, "cart3d"), (1, 1.0, "Rsphere")])
+def test_stress_dependent_viscosity_loop(rheology, damp, geometry, monkeypatch):
     """SDEPV: visc_from_S (power law, sdepv_rheology 1 / 2) and the viscosity <-> velocity iteration of general_stokes_solver
     (Drive_solvers.c:120-159, with and without damping) on the device, inside the reference's own time loop."""
     if not po.have_ref() or not DROPIN.exists():
         pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
-    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, accuracy=1e-6, viscE="4.6,4.6,4.6,4.6", SDEPV="on", sdepv_rheology=rheology,
-                              sdepv_expt="3,3,3,3", sdepv_trns="2e3,2e3,2e3,2e3", sdepv_misfit=1e-3, sdepv_iter_damp=damp,
-                              sdepv_trns_T=3000, sdepv_trns_c=2.0, storage_spacing=1)
+    sd = dict(maxstep=3, accuracy=1e-6, viscE="4.6,4.6,4.6,4.6", SDEPV="on", sdepv_rheology=rheology, sdepv_expt="3,3,3,3",
+              sdepv_trns="2e3,2e3,2e3,2e3", sdepv_misfit=1e-3, sdepv_iter_damp=damp, sdepv_trns_T=3000, sdepv_trns_c=2.0, storage_spacing=1)
+    if geometry == "Rsphere":      # the strain rate of visc_from_S through the Rsphere branch of strain_rate_2_inv
+        txt = inputfile.input1_rsphere(levels=3, TDEPV="on", VISC_UPDATE="on", update_every_steps=1, perturbmag=0.05, **sd)
+    else:
+        txt = inputfile.tdepv_box(16, 16, 8, 3, **sd)
     nsteps = 2
     ref, rerr = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_sref_"), nsteps=nsteps)
     monkeypatch.setenv("CCU_DROPIN_ENERGY", "1")
@@ -201,8 +204,11 @@ def test_stress_dependent_viscosity_loop(rheology, damp, monkeypatch):
         assert np.allclose(g[f"s{k}_EVI"], r[f"s{k}_EVI"], rtol=2e-2), k
         assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
     # the viscosity did become strain-rate dependent (not the Newtonian field)
-    newt = po.run_harness(inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, accuracy=1e-6, viscE="4.6,4.6,4.6,4.6"),
-                          tempfile.mkdtemp(prefix="ccu_snewt_"), nsteps=0)[0][0]
+    if geometry == "Rsphere":
+        ntxt = inputfile.input1_rsphere(levels=3, maxstep=1, accuracy=1e-6, viscE="4.6,4.6,4.6,4.6", TDEPV="on", perturbmag=0.05)
+    else:
+        ntxt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, accuracy=1e-6, viscE="4.6,4.6,4.6,4.6")
+    newt = po.run_harness(ntxt, tempfile.mkdtemp(prefix="ccu_snewt_"), nsteps=0)[0][0]
     assert np.abs(r["s0_EVI"] / newt["s0_EVI"] - 1).max() > 0.05
 
 
