@@ -1472,6 +1472,70 @@ __global__ void __launch_bounds__(256) ek_layer_sums(const CcuGeom g, const floa
         layer[kz] = a; layer[g.noz + kz] = b;
     }
 }
+// return_horiz_ave (Global_operations.c:133-215) as the reference integrates it, for regional-spherical meshes: layer kz sums, over the
+// element columns, the 2 x 2 Gauss quadrature of the bilinear field on the BOTTOM face of element (min(kz, elz-1), ex, ey) -- the top
+// layer borrows the last element's bottom-face areas, :185-199 -- with the surface Jacobian of get_global_1d_shape_fn's Rsphere branch
+// (Size_does_matter.c:492-527: face nodes rotated into the frame of the element centre)
+__global__ void __launch_bounds__(256) ek_layer_sums_sph(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ X, double *layer)
+{
+    const int kz = blockIdx.x;
+    const int ez = kz < g.elz ? kz : g.elz - 1;
+    const double B = (double)(float)0.57735026918962576451;
+    const double gp[4][2] = { { -B, -B }, { B, -B }, { B, B }, { -B, B } };
+    const int sx[4] = { -1, 1, 1, -1 }, sy[4] = { -1, -1, 1, 1 };          // master-element corners of face nodes 1..4
+    double s = 0.0, w = 0.0;
+    for(int t = threadIdx.x; t < g.elx * g.ely; t += blockDim.x)
+    {
+        const int ex = t % g.elx, ey = t / g.elx;
+        float Xe[3][8];
+        load_elt_coords(g, XX, ey, ex, ez, Xe);
+        double centre[3];
+        for(int i = 0; i < 3; i++)
+        {
+            double v = 0.0;
+            for(int a = 0; a < 8; a++) v += Xe[i][a];
+            centre[i] = v / 8;
+        }
+        const float c3 = (float)sqrt(centre[0] * centre[0] + centre[1] * centre[1] + centre[2] * centre[2]);
+        const float to = (float)acos(centre[2] / c3), fo = (float)sph_myatan(centre[1], centre[0]);     // ECO.centre[1], [2] (float)
+        const double ct = cos((double)to), st = sin((double)to), cf = cos((double)fo), sf = sin((double)fo);
+        double xx[2][4];                                                  // the two in-surface coordinates of the four face nodes
+        for(int i = 0; i < 4; i++)
+        {
+            xx[0][i] = Xe[0][i] * (ct * cf) + Xe[1][i] * (ct * sf) + Xe[2][i] * (-st);
+            xx[1][i] = Xe[0][i] * (-sf) + Xe[1][i] * cf + Xe[2][i] * 0.0;
+        }
+        double val[4];
+        {
+            const int base = kz + g.noz * (ex + g.nox * ey);
+            val[0] = (double)X[base]; val[1] = (double)X[base + g.noz]; val[2] = (double)X[base + g.noz + g.noz * g.nox]; val[3] = (double)X[base + g.noz * g.nox];
+        }
+        for(int k = 0; k < 4; k++)
+        {
+            double dxda[2][2] = { { 0.0, 0.0 }, { 0.0, 0.0 } }, M[4];
+            for(int i = 0; i < 4; i++)
+            {
+                const double lx = 0.5 * (1.0 + sx[i] * gp[k][0]), ly = 0.5 * (1.0 + sy[i] * gp[k][1]);
+                M[i] = lx * ly;
+                const double mx0 = 0.5 * sx[i] * ly, mx1 = 0.5 * sy[i] * lx;      // Mx.vpt(0, i, k), Mx.vpt(1, i, k)
+                dxda[0][0] += xx[0][i] * mx0; dxda[0][1] += xx[1][i] * mx0;
+                dxda[1][0] += xx[0][i] * mx1; dxda[1][1] += xx[1][i] * mx1;
+            }
+            const double jac = dxda[0][0] * dxda[1][1] - dxda[0][1] * dxda[1][0];
+            for(int d = 0; d < 4; d++) { s += val[d] * M[d] * jac; w += M[d] * jac; }
+        }
+    }
+    __shared__ double sh[2][8];
+    for(int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); w += __shfl_down_sync(0xffffffffu, w, o); }
+    if((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = w; }
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        double a = 0.0, b = 0.0;
+        for(int q = 0; q < 8; q++) { a += sh[0][q]; b += sh[1][q]; }
+        layer[kz] = a; layer[g.noz + kz] = b;
+    }
+}
 __global__ void __launch_bounds__(256) ek_remove_layer_ave(const CcuGeom g, const double *__restrict__ layer, float *X)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2348,6 +2412,13 @@ int ccu_set_heating_arrays(ccu_ctx *c, const float *heating_adi, const float *he
 // return_horiz_ave across subdomains (Global_operations.c:205-238): the layer sums of the ranks that share a z position
 // (the reference's horizontal sub-communicator) are added.  One allreduce over ALL ranks of a table with one slot per z
 // position does the same: every rank adds its sums into slot me_z, and reads that slot back.
+// layer sums of a nodal field into E.layer (sums | weights), in the geometry of the context
+static void launch_layer_sums(ccu_ctx *c, const float *field)
+{
+    Level &L = c->L[c->cfg.levmax];
+    if(c->rsphere) LAUNCH(c, ek_layer_sums_sph, L.g.noz, 256, L.g, (const float *)L.XX, field, c->en.layer);
+    else LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, field, c->en.layer);
+}
 static int layer_allreduce(ccu_ctx *c)
 {
     if(!c->multi()) return 0;
@@ -2620,7 +2691,7 @@ int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_i
 int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "thermal_buoyancy");
+    if(c->rsphere && c->en.phase_on) FAIL("thermal_buoyancy: phase changes are Cartesian only on the device");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2632,7 +2703,7 @@ int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
         if(ccu_phase_change(c, (E.step % 10 == 0) ? 1 : 0, nullptr, nullptr, nullptr)) return 1;
         LAUNCH(c, ek_phase_buoyancy, cdiv(L.g.nno, 256), 256, L.g.nno, E.ph.Ra670, E.ph.Ra410, (const float *)E.Fas670, (const float *)E.Fas410, c->buoy);
     }
-    LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->buoy, E.layer);
+    launch_layer_sums(c, (const float *)c->buoy);
     if(layer_allreduce(c)) return 1;                                   // the ranks of one horizontal plane share their sums
     LAUNCH(c, ek_remove_layer_ave, cdiv(L.g.nno, 256), 256, L.g, (const double *)E.layer, c->buoy);
     if(buoyancy_out) CK(cudaMemcpyAsync(buoyancy_out, c->buoy, sizeof(float) * (size_t)L.g.nno, cudaMemcpyDeviceToHost, c->st));
@@ -2792,7 +2863,6 @@ __global__ void __launch_bounds__(128) ek_layer_finish(const int noz, const doub
 int ccu_averages(ccu_ctx *c, float *vrms_out, float *visc_out, float *C_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "averages");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2802,7 +2872,7 @@ int ccu_averages(ccu_ctx *c, float *vrms_out, float *visc_out, float *C_out)
     CK(cudaMalloc(&lay, sizeof(float) * 3 * (size_t)noz));
     auto one = [&](const float *field, int root, float *dev_out, float *host_out) -> int
     {
-        LAUNCH(c, ek_layer_sums, noz, 256, L.g, (const float *)L.XX, field, E.layer);
+        launch_layer_sums(c, field);
         if(layer_allreduce(c)) return 1;
         LAUNCH(c, ek_layer_finish, cdiv(noz, 128), 128, noz, (const double *)E.layer, root, dev_out);
         CK(cudaMemcpyAsync(host_out, dev_out, sizeof(float) * noz, cudaMemcpyDeviceToHost, c->st));

@@ -338,7 +338,7 @@ def test_regional_sphere_heating_and_energy_step():
         pytest.skip("needs the prebuilt reference (oracle/_ref)")
     from test_gpu_build import build_ctx
     text = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-6, TDEPV="on", perturbmag=0.05, adi_heating=1, visc_heating=1,
-                                    surf_temp=0.078947)
+                                    surf_temp=0.078947, storage_spacing=1)
     d = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_rsheat_")), nsteps=2, kat=True)[0][0]
     ctx = build_ctx(d, 0, 0.0)
     adv = d["kat_adv_params"]
@@ -354,6 +354,17 @@ def test_regional_sphere_heating_and_energy_step():
     T, Tdot, dt, Tint = ctx.PG_timestep(d["s0_T"], d["s0_Tdot"])
     assert abs(dt - d["s1_scalars"][1]) <= 1e-6 * d["s1_scalars"][1]
     assert ulps(T, d["s1_T"]) <= 8.0, ulps(T, d["s1_T"])
+    # thermal_buoyancy: the layer averages over spherical shells (return_horiz_ave with the Rsphere surface Jacobian of
+    # get_global_1d_shape_fn) removed from Ra T alpha
+    ctx.set_temperature(d["s0_T"])
+    b = ctx.thermal_buoyancy(float(adv[5]))
+    assert np.abs(b - d["s0_buoyancy"]).max() <= 1e-5 * np.abs(d["s0_buoyancy"]).max()
+    # averages: layer vrms and viscosity of the reference's step-1 state
+    ctx.set_velocity(d["s1_V1"], d["s1_V2"], d["s1_V3"])
+    ctx.set_element_viscosity(d.levmax, d["s1_EVI"])
+    vr, vi = ctx.averages()
+    assert np.abs(vr - d["s1_Have_vrms"]).max() <= 1e-4 * np.abs(d["s1_Have_vrms"]).max()
+    assert np.abs(vi - d["s1_Have_Vi"]).max() <= 1e-4 * np.abs(d["s1_Have_Vi"]).max()
     # the entry points without an Rsphere branch refuse the context
     with pytest.raises(Exception, match="Cartesian geometry only"):
         ctx.heat_flux()
