@@ -1547,7 +1547,7 @@ __global__ void __launch_bounds__(256) ek_remove_layer_ave(const CcuGeom g, cons
 // ================================================================= diagnostics: heat_flux (Process_buoyancy.c:63-203), Nusselt numbers
 // per element: uT = sum_gp (u_z T - kappa dT/dz) gDA / area  (:105-131), area = ECO.area (Size_does_matter.c:712)
 __global__ void __launch_bounds__(64) hf_element(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ T, const float *__restrict__ V,
-                                                 const float *__restrict__ diffusivity, double *uT_out, float *area_out)
+                                                 const float *__restrict__ diffusivity, double *uT_out, float *area_out, const int sph)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -1566,6 +1566,12 @@ __global__ void __launch_bounds__(64) hf_element(const CcuGeom g, const float *_
     for(int i = 0; i < 8; i++)
     {
         const float gda = (float)gp_geom(X, c_sh.Nxv + i, 64, 8, gnx);
+        if(sph)
+        {   // regional sphere: gNX holds d/dtheta, d/dphi, d/dr (get_global_shape_fn's sphere branch), V[3] is the radial velocity
+            double x[3];
+            sph_point(X, c_sh.Nv + i, 8, x);
+            sph_rotate_gnx(x, gnx);
+        }
         double u = 0.0, Tg = 0.0, dTdz = 0.0;
         for(int j = 0; j < 8; j++)
         {
@@ -2912,13 +2918,12 @@ int ccu_averages(ccu_ctx *c, float *vrms_out, float *visc_out, float *C_out)
 int ccu_heat_flux(ccu_ctx *c, float *Nut_out, float *Nub_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "heat_flux");
     if(ensure_energy(c) || energy_ready(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
     const size_t nel = (size_t)L.g.nel, nno = (size_t)L.g.nno;
     if(!E.hf) { CK(cudaMalloc(&E.hf, sizeof(float) * nno)); CK(cudaMalloc(&E.hf_area, sizeof(float) * nel)); CK(cudaMalloc(&E.hf_sums, sizeof(double) * 4)); }
-    LAUNCH(c, hf_element, cdiv(nel, 64), 64, L.g, (const float *)L.XX, (const float *)c->T, (const float *)E.V, (const float *)E.diffusivity, E.Eres, E.hf_area);
+    LAUNCH(c, hf_element, cdiv(nel, 64), 64, L.g, (const float *)L.XX, (const float *)c->T, (const float *)E.V, (const float *)E.diffusivity, E.Eres, E.hf_area, c->rsphere ? 1 : 0);
     int at_bottom = 1, at_top = 1;
     if(!c->multi()) LAUNCH(c, hf_nodal, cdiv(nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const double *)E.Eres, E.hf);
     else

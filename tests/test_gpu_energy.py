@@ -365,7 +365,14 @@ def test_regional_sphere_heating_and_energy_step():
     vr, vi = ctx.averages()
     assert np.abs(vr - d["s1_Have_vrms"]).max() <= 1e-4 * np.abs(d["s1_Have_vrms"]).max()
     assert np.abs(vi - d["s1_Have_Vi"]).max() <= 1e-4 * np.abs(d["s1_Have_Vi"]).max()
+    # heat_flux: Nusselt numbers from the radial derivative (main()'s order: the new temperature with the velocity of the solve before)
+    for k in (1, 2):
+        ctx.set_temperature(d[f"s{k}_T"])
+        ctx.set_velocity(d[f"s{k - 1}_V1"], d[f"s{k - 1}_V2"], d[f"s{k - 1}_V3"])
+        nut, nub = ctx.heat_flux()
+        sc = d[f"s{k}_scalars"]
+        assert abs(nut - sc[2]) <= 1e-4 * abs(sc[2]) and abs(nub - sc[3]) <= 1e-4 * abs(sc[3]), (k, nut, nub, sc[2], sc[3])
     # the entry points without an Rsphere branch refuse the context
     with pytest.raises(Exception, match="Cartesian geometry only"):
-        ctx.heat_flux()
+        ctx.get_stress_topo()
     ctx.close()
