@@ -2466,16 +2466,18 @@ int ccu_set_phase_params(ccu_ctx *c, float zlm, float z410, float Ra_670, float 
 int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fas410_out, float *transT_out /*[2]: 670, 410*/)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "phase_change");
     if(ensure_energy(c)) return 1;
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
     if(!E.phase_on) FAIL("phase_change: ccu_set_phase_params first");
+    // the depth coordinate: z of the box, r of the regional sphere (Xtmp = E->SX there, Phase_change.c:78-87); both [3][nno]
+    if(c->rsphere && !L.have_sxx) FAIL("phase_change: spherical coordinates missing");
+    const float *zco = c->rsphere ? (const float *)L.SXX : (const float *)L.XX;
     if(update_transT)
     {
-        LAUNCH(c, ek_layer_sums, L.g.noz, 256, L.g, (const float *)L.XX, (const float *)c->T, E.layer);
+        launch_layer_sums(c, (const float *)c->T);
         if(layer_allreduce(c)) return 1;
-        LAUNCH(c, ek_phase_transT, 1, 32, L.g, (const float *)L.XX, (const double *)E.layer, E.ph.zlm, E.ph.z410, E.transT);
+        LAUNCH(c, ek_phase_transT, 1, 32, L.g, zco, (const double *)E.layer, E.ph.zlm, E.ph.z410, E.transT);
         if(c->multi() && c->comm->nproc[2] > 1)
         {   // sum_across_depth (Global_operations.c:763, Phase_change.c:103,116): the phase depth lies in ONE z subdomain of a
             // vertical column of ranks (the others found 0): sum over the ranks with this rank's (x, y) through one allreduce table
@@ -2490,7 +2492,7 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
     }
     CcuPhase ph; ph.zlm = E.ph.zlm; ph.z410 = E.ph.z410; ph.Ra670 = E.ph.Ra670; ph.clap670 = E.ph.clap670; ph.width670 = E.ph.width670;
     ph.Ra410 = E.ph.Ra410; ph.clap410 = E.ph.clap410; ph.width410 = E.ph.width410; ph.transT670 = 0; ph.transT410 = 0;
-    LAUNCH(c, ek_phase_functions, cdiv(L.g.nno, 256), 256, L.g, (const float *)L.XX, (const float *)c->T, ph, (const float *)E.transT, E.Fas670, E.Fas410);
+    LAUNCH(c, ek_phase_functions, cdiv(L.g.nno, 256), 256, L.g, zco, (const float *)c->T, ph, (const float *)E.transT, E.Fas670, E.Fas410);
     const size_t nno = (size_t)L.g.nno;
     if(Fas670_out) CK(cudaMemcpyAsync(Fas670_out, E.Fas670, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
     if(Fas410_out) CK(cudaMemcpyAsync(Fas410_out, E.Fas410, sizeof(float) * nno, cudaMemcpyDeviceToHost, c->st));
@@ -2503,7 +2505,6 @@ int ccu_phase_change(ccu_ctx *c, int update_transT, float *Fas670_out, float *Fa
 int ccu_process_heating(ccu_ctx *c, float *heating_adi_out, float *heating_visc_out)
 {   // (heating_latent: ccu_get_heating_latent)
     if(!c) FAIL("null context");
-    if(c->rsphere && c->en.phase_on) FAIL("process_heating: phase changes are Cartesian only on the device");
     if(ensure_energy(c)) return 1;
     auto &E = c->en;
     Level &L = c->L[c->cfg.levmax];
@@ -2697,7 +2698,6 @@ int ccu_PG_timestep(ccu_ctx *c, float *T, float *Tdot, float *dt_out, float *T_i
 int ccu_thermal_buoyancy(ccu_ctx *c, float Atemp, float *buoyancy_out)
 {
     if(!c) FAIL("null context");
-    if(c->rsphere && c->en.phase_on) FAIL("thermal_buoyancy: phase changes are Cartesian only on the device");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;

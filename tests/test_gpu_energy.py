@@ -376,3 +376,35 @@ def test_regional_sphere_heating_and_energy_step():
     with pytest.raises(Exception, match="Cartesian geometry only"):
         ctx.get_stress_topo()
     ctx.close()
+
+
+def test_regional_sphere_phase_changes():
+    """phase_change on the regional sphere (the depth coordinate is r = E->SX[3], the layer averages are shell averages): phase functions,
+    transition temperatures, latent heating and the buoyancy with the phase terms against the reference."""
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    from test_gpu_build import build_ctx
+    text = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-6, TDEPV="on", perturbmag=0.05, adi_heating=1, visc_heating=1,
+                                    surf_temp=0.078947, Ra_410=100.0, Ra_670=-100.0, storage_spacing=1)
+    d = po.run_harness(text, Path(tempfile.mkdtemp(prefix="ccu_rsphase_")), nsteps=2, kat=True)[0][0]
+    ctx = build_ctx(d, 0, 0.0)
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    eb, ph = d["s1_eba"], d["s1_phase"]
+    ctx.set_heating_params(1, 1, eb[0], eb[1], eb[2])
+    ctx.set_phase_params(ph[0], ph[1], ph[2], ph[3], ph[4], ph[6], ph[7], ph[8])
+    load_s0(d, ctx)
+    ctx.set_element_viscosity(d.levmax, d["s0_EVI"])
+    p0 = d["s0_phase"]
+    F6, F4, tT = ctx.phase_change(update_transT=True)
+    assert abs(tT[0] - p0[5]) <= 1e-5 * abs(p0[5]) and abs(tT[1] - p0[9]) <= 1e-5 * abs(p0[9])
+    assert np.abs(F6 - d["s0_Fas670"]).max() <= 1e-5 and np.abs(F4 - d["s0_Fas410"]).max() <= 1e-5
+    assert d["s0_Fas670"].min() < 0.1 and d["s0_Fas670"].max() > 0.9            # the transition is inside the shell
+    adi, visc = ctx.process_heating()
+    lat = ctx.get_heating_latent()
+    assert np.abs(d["s1_heating_latent"] - 1).max() > 1e-3
+    assert np.abs(lat - d["s1_heating_latent"]).max() <= 1e-5
+    ctx.set_step(0)
+    b = ctx.thermal_buoyancy(float(adv[5]))
+    assert np.abs(b - d["s0_buoyancy"]).max() <= 1e-5 * np.abs(d["s0_buoyancy"]).max()
+    ctx.close()
