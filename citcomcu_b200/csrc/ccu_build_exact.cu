@@ -336,49 +336,63 @@ __global__ void __launch_bounds__(128) bk_elt_geometry_sph(const CcuGeom g, cons
     }
 }
 // get_elt_k, Rsphere branch (Element_calculations.c:249-260): bdbmu[i][j] = sum_k W[k] (2 (ba1 ba1 + ba2 ba2 + ba3 ba3) + ba4 ba4 + ba5 ba5 + ba6 ba6)
+struct SphElt
+{
+    float gn[8][3][8];        // [gauss point][d][node], derivatives with respect to (theta, phi, r)
+    double W[8], ra[8], si[8], ct[8];
+    SphTrig A[8], P[8];       // node bases, integration-point bases
+};
+// column_cache: the point bases of the first element of the radial column (get_elt_k called with iconv = 0 from construct_node_ks) or
+// of the element itself (iconv = 1, the imposed-velocity term of get_elt_f)
+__device__ __forceinline__ void sph_elt_setup(const CcuGeom &g, const float *__restrict__ XX, const float *__restrict__ SXX, const float *__restrict__ EVI,
+                                              const int e, const bool column_cache, SphElt &S)
+{
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float X[3][8];
+    load_elt_coords(g, XX, ey, ex, ez, X);
+    load_elt_sph(g, SXX, ey, ex, ez, S.A);
+    for(int k = 0; k < 8; k++)
+    {
+        const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, S.gn[k]);
+        double x[3], th, ph;
+        sph_point(X, c_sh.Nv + k, 8, x);
+        sph_rotate_gnx(x, S.gn[k]);
+        sph_rtf(x, th, ph, S.ra[k]);
+        S.si[k] = 1.0 / sin(th);
+        S.ct[k] = cos(th) * S.si[k];
+        S.P[k] = column_cache ? sph_column_point_trig(g, XX, ey, ex, ez, X, c_sh.Nv + k, 8) : sph_point_trig(x);
+        S.W[k] = (double)(1.0f * gda * EVI[(size_t)e * 8 + k]);
+    }
+}
+__device__ __forceinline__ void sph_elt_pair(const SphElt &S, const int a, const int b, double bd[3][3])
+{
+    for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) bd[i][j] = 0.0;
+    for(int k = 0; k < 8; k++)
+    {
+        double bb[3][6];
+        for(int j = 0; j < 3; j++) sph_ba(S.P[k], S.A[b], j, S.gn[k][0][b], S.gn[k][1][b], S.gn[k][2][b], c_sh.Nv[8 * b + k], S.ra[k], S.si[k], S.ct[k], bb[j]);
+        for(int i = 0; i < 3; i++)
+        {
+            double aa[6];
+            sph_ba(S.P[k], S.A[a], i, S.gn[k][0][a], S.gn[k][1][a], S.gn[k][2][a], c_sh.Nv[8 * a + k], S.ra[k], S.si[k], S.ct[k], aa);
+            for(int j = 0; j < 3; j++)
+                bd[i][j] += S.W[k] * (2.0 * (aa[0] * bb[j][0] + aa[1] * bb[j][1] + aa[2] * bb[j][2]) + aa[3] * bb[j][3] + aa[4] * bb[j][4] + aa[5] * bb[j][5]);
+        }
+    }
+}
 __global__ void __launch_bounds__(64) bk_elt_k_sph(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ SXX, const float *__restrict__ EVI,
                                                   const int e_begin, const int e_count, double *blocks)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if(t >= e_count) return;
-    const int e = e_begin + t;
-    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
-    float X[3][8];
-    load_elt_coords(g, XX, ey, ex, ez, X);
-    SphTrig A[8], P[8];
-    load_elt_sph(g, SXX, ey, ex, ez, A);
-    float gn[8][3][8];        // [gauss point][d][node], derivatives with respect to (theta, phi, r)
-    double W[8], ra[8], si[8], ct[8];
-    for(int k = 0; k < 8; k++)
-    {
-        const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gn[k]);
-        double x[3], th, ph;
-        sph_point(X, c_sh.Nv + k, 8, x);
-        sph_rotate_gnx(x, gn[k]);
-        sph_rtf(x, th, ph, ra[k]);
-        si[k] = 1.0 / sin(th);
-        ct[k] = cos(th) * si[k];
-        P[k] = sph_column_point_trig(g, XX, ey, ex, ez, X, c_sh.Nv + k, 8);
-        W[k] = (double)(1.0f * gda * EVI[(size_t)e * 8 + k]);
-    }
+    SphElt S;
+    sph_elt_setup(g, XX, SXX, EVI, e_begin + t, true, S);
     int pair = 0;
     for(int a = 0; a < 8; a++)
         for(int b = a; b < 8; b++, pair++)
         {
             double bd[3][3];
-            for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) bd[i][j] = 0.0;
-            for(int k = 0; k < 8; k++)
-            {
-                double bb[3][6];
-                for(int j = 0; j < 3; j++) sph_ba(P[k], A[b], j, gn[k][0][b], gn[k][1][b], gn[k][2][b], c_sh.Nv[8 * b + k], ra[k], si[k], ct[k], bb[j]);
-                for(int i = 0; i < 3; i++)
-                {
-                    double aa[6];
-                    sph_ba(P[k], A[a], i, gn[k][0][a], gn[k][1][a], gn[k][2][a], c_sh.Nv[8 * a + k], ra[k], si[k], ct[k], aa);
-                    for(int j = 0; j < 3; j++)
-                        bd[i][j] += W[k] * (2.0 * (aa[0] * bb[j][0] + aa[1] * bb[j][1] + aa[2] * bb[j][2]) + aa[3] * bb[j][3] + aa[4] * bb[j][4] + aa[5] * bb[j][5]);
-                }
-            }
+            sph_elt_pair(S, a, b, bd);
             for(int i = 0; i < 3; i++)
                 for(int j = 0; j < 3; j++) blocks[(size_t)(pair * 9 + 3 * i + j) * e_count + t] = bd[i][j];
         }
@@ -966,12 +980,41 @@ __global__ void __launch_bounds__(128) bk_vb_slots(const int n_vb, const int *__
 __global__ void __launch_bounds__(64) bk_forces_vb_elt(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ EVI,
                                                       const unsigned *__restrict__ node, const float *__restrict__ VB1,
                                                       const float *__restrict__ VB2, const float *__restrict__ VB3,
-                                                      const int n_vb, const int *__restrict__ elems, double *EF)
+                                                      const int n_vb, const int *__restrict__ elems, double *EF, const float *__restrict__ SXX)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if(t >= n_vb) return;
     const int e = elems[t];
     const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    double vb[24], ef[24];
+    if(SXX)
+    {   // regional sphere: the element matrix of get_elt_k's Rsphere branch, point bases of the element itself (iconv = 1, :1102)
+        SphElt S;
+        sph_elt_setup(g, XX, SXX, EVI, e, false, S);
+        for(int a = 0; a < 8; a++)
+        {
+            const int n = elt_node(g, ey, ex, ez, a + 1);
+            const unsigned f = node[n];
+            vb[3 * a + 0] = (f & 0x2u) ? (double)VB1[n] : 0.0;
+            vb[3 * a + 1] = (f & 0x8u) ? (double)VB2[n] : 0.0;
+            vb[3 * a + 2] = (f & 0x4u) ? (double)VB3[n] : 0.0;
+        }
+        for(int p = 0; p < 24; p++) ef[p] = 0.0;
+        for(int a = 0; a < 8; a++)
+            for(int b = a; b < 8; b++)
+            {
+                double bd[3][3];
+                sph_elt_pair(S, a, b, bd);
+                for(int i = 0; i < 3; i++)
+                    for(int j = 0; j < 3; j++)
+                    {
+                        if(!(a == b && i == j)) ef[3 * a + i] -= bd[i][j] * vb[3 * b + j];
+                        if(a != b) ef[3 * b + i] -= bd[j][i] * vb[3 * a + j];
+                    }
+            }
+        for(int p = 0; p < 24; p++) EF[(size_t)p * n_vb + t] = ef[p];
+        return;
+    }
     float X[3][8];
     load_elt_coords(g, XX, ey, ex, ez, X);
     float gn[8][3][8];
@@ -981,7 +1024,6 @@ __global__ void __launch_bounds__(64) bk_forces_vb_elt(const CcuGeom g, const fl
         const float gda = (float)gp_geom(X, c_sh.Nxv + k, 64, 8, gn[k]);
         W[k] = (double)(1.0f * gda * EVI[(size_t)e * 8 + k]);
     }
-    double vb[24], ef[24];
     for(int a = 0; a < 8; a++)
     {
         const int n = elt_node(g, ey, ex, ez, a + 1);
@@ -2219,7 +2261,6 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
     if(c->rsphere)
     {
         if(!L.have_sxx) FAIL("assemble_forces: spherical coordinates missing");
-        if(c->have_vb) FAIL("assemble_forces: imposed non-zero velocities are Cartesian only on the device");
         LAUNCH(c, bk_forces_elt_sph, cdiv(L.g.nel, 128), 128, L.g, L.XX, L.SXX, c->buoy, c->forceEF);
         LAUNCH(c, bk_forces_gather_sph, cdiv(L.g.nno, 128), 128, L.g, c->forceEF, L.flags, L.vec[CCU_VEC_F]);
     }
@@ -2254,7 +2295,8 @@ int ccu_assemble_forces(ccu_ctx *c, const float *buoyancy, double *F_out)
         }
         if(c->n_vb > 0)
         {
-            LAUNCH(c, bk_forces_vb_elt, cdiv(c->n_vb, 64), 64, L.g, L.XX, L.EVI, L.node, c->VB[0], c->VB[1], c->VB[2], c->n_vb, c->vb_elems, c->vbEF);
+            LAUNCH(c, bk_forces_vb_elt, cdiv(c->n_vb, 64), 64, L.g, L.XX, L.EVI, L.node, c->VB[0], c->VB[1], c->VB[2], c->n_vb, c->vb_elems, c->vbEF,
+                   c->rsphere ? (const float *)L.SXX : (const float *)nullptr);
             LAUNCH(c, bk_forces_vb_gather, cdiv(L.g.nno, 128), 128, L.g, c->vb_slot, c->vbEF, c->n_vb, L.flags, L.vec[CCU_VEC_F]);
         }
     }

@@ -117,7 +117,8 @@ def test_rheologies_and_viscosity_coarsening_modes(rheol, smooth):
     ctx.close()
 
 
-def test_imposed_velocity_force_term():
+@pytest.mark.parametrize("geometry", ["cart3d", "Rsphere"])
+def test_imposed_velocity_force_term(geometry):
     """assemble_forces with non-zero E->VB: the -K.VB term of get_elt_f (Element_calculations.c:1038-1063) against the reference's
     F at steps 0 and 1 (step k is assembled with the viscosity of the update before it)."""
     import tempfile
@@ -125,7 +126,11 @@ def test_imposed_velocity_force_term():
     from citcomcu_b200 import inputfile
     if not po.have_ref():
         pytest.skip("needs the prebuilt reference (oracle/_ref)")
-    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, accuracy=1e-5, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
+    if geometry == "Rsphere":      # the element matrix of the Rsphere branch, point bases of the element itself (get_elt_k with iconv = 1)
+        txt = inputfile.input1_rsphere(levels=3, maxstep=3, accuracy=1e-5, TDEPV="on", VISC_UPDATE="on", update_every_steps=1, perturbmag=0.05,
+                                       topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
+    else:
+        txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=3, accuracy=1e-5, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
     d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_vbF_"), nsteps=1)[0][0]
     assert np.abs(d["VB1"]).max() == 40.0 and np.abs(d["VB2"]).max() == 15.0
     ctx = build_ctx(d, 0, 0.0)

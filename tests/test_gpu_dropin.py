@@ -212,8 +212,8 @@ def test_stress_dependent_viscosity_loop(rheology, damp, geometry, monkeypatch):
     assert np.abs(r["s0_EVI"] / newt["s0_EVI"] - 1).max() > 0.05
 
 
-@pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
-def test_imposed_plate_velocity(energy, monkeypatch):
+@pytest.mark.parametrize("energy,geometry", [(0, "cart3d"), (1, "cart3d"), (1, "Rsphere")], ids=["stokes", "stokes+energy", "rsphere"])
+def test_imposed_plate_velocity(energy, geometry, monkeypatch):
     """topvbc=1 with a non-zero plate velocity: E->VB enters U (velocities_conform_bcs) and F (the K.VB term of get_elt_f,
     Element_calculations.c:1038-1063, evaluated with the viscosity of the previous update) on the device."""
     if not po.have_ref() or not DROPIN.exists():
@@ -221,7 +221,10 @@ def test_imposed_plate_velocity(energy, monkeypatch):
     # accuracy: the hot, weak bottom layer under a driven lid is poorly conditioned -- the two arms (and the reference against itself
     # at a tighter tolerance) differ there by about 1000 x accuracy (measured: 5.5e-3, 4e-4, 3e-5 of |U| at 1e-5, 1e-6, 1e-7), so the
     # comparison runs at 1e-7 and allows 3e-4
-    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=4, accuracy=1e-7, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
+    vb = dict(maxstep=4, accuracy=1e-7, topvbc=1, plate_velocity=40.0, topvbyval=-15.0, storage_spacing=1)
+    mk = (lambda **kw: inputfile.input1_rsphere(levels=3, TDEPV="on", VISC_UPDATE="on", update_every_steps=1, perturbmag=0.05, **kw)) \
+        if geometry == "Rsphere" else (lambda **kw: inputfile.tdepv_box(16, 16, 8, 3, **kw))
+    txt = mk(**vb)
     nsteps = 2
     monkeypatch.setenv("CCU_DROPIN_ENERGY", str(energy))
     ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_vbref_"), nsteps=nsteps)
@@ -229,7 +232,7 @@ def test_imposed_plate_velocity(energy, monkeypatch):
     assert "citcomcu_b200 drop-in: Stokes solve on CUDA device" in err
     r, g = ref[0], gpu[0]
     acc = r.control()["accuracy"]
-    free = po.run_harness(inputfile.tdepv_box(16, 16, 8, 3, maxstep=1, accuracy=1e-5), tempfile.mkdtemp(prefix="ccu_vbfree_"), nsteps=0)[0][0]
+    free = po.run_harness(mk(maxstep=1, accuracy=1e-5), tempfile.mkdtemp(prefix="ccu_vbfree_"), nsteps=0)[0][0]
     assert np.abs(r["VB1"]).max() == 40.0 and np.abs(r["VB2"]).max() == 15.0
     # the plate drives the flow: nothing like the free-slip solution of the same state
     assert np.linalg.norm(r["s0_U"] - free["s0_U"]) > 0.5 * np.linalg.norm(r["s0_U"])
