@@ -2113,7 +2113,10 @@ int ccu_get_system_viscosity(ccu_ctx *c)
     const bool sd = c->visc.sdepv != 0, cd = c->visc.cdepv != 0;
     const float *Ccomp = c->mk.ready ? (const float *)c->mk.C : (const float *)c->Cnode;
     if(cd && !Ccomp) FAIL("get_system_viscosity: composition-dependent viscosity needs the nodal composition (device markers or ccu_set_composition)");
-    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr, L.EVI, (sd || cd) ? 0 : 1);
+    // the depth coordinate of laws 2 and 4: z of the box, r of the regional sphere (Xtmp = E->SX, Viscosity_structures.c:525-530)
+    const float *zco = c->rsphere ? (L.SXX ? L.SXX + 2 * (size_t)L.g.nno : (const float *)nullptr) : (L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr);
+    if(c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4) && !zco) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
+    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, zco, L.EVI, (sd || cd) ? 0 : 1);
     if(cd && !sd)
     {   // temperature law, composition factor, then the min / max clip (Viscosity_structures.c:386-425)
         LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);

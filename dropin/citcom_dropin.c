@@ -78,8 +78,6 @@ void ccu_dropin_init(struct All_variables *E)
     if(E->viscosity.SDEPV && E->viscosity.sdepv_rheology != 1 && E->viscosity.sdepv_rheology != 2)
         die("stress-dependent viscosity: sdepv_rheology 1 and 2 are on the device path, 3 (dimensional Arrhenius law) is not");
     if(E->viscosity.SDEPV && E->control.restart) die("stress-dependent viscosity with restart (strain rate of the restart velocity) is not on the device path");
-    if(!E->control.CART3D && E->viscosity.TDEPV && (E->viscosity.RHEOL == 2 || E->viscosity.RHEOL == 4))
-        die("regional-spherical geometry with a depth-dependent viscosity law (rheol 2, 4) is not on the device path");
     if(E->control.force_initial_stokes_iteration) die("force_initial_stokes_iteration is not on the device path");
     /* options that change the operator and that the device build does not implement: stop, never differ silently */
     if(E->viscosity.SMOOTH) die("viscosity smoothing (VISC_SMOOTH / apply_viscosity_smoother) is not on the device path");

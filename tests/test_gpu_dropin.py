@@ -270,7 +270,7 @@ def test_regional_sphere_solver_on_device(funcs, monkeypatch):
 
 
 @pytest.mark.parametrize("energy", [0, 1], ids=["stokes", "stokes+energy"])
-@pytest.mark.parametrize("tdepv", ["off", "on", "on-eba"])
+@pytest.mark.parametrize("tdepv", ["off", "on", "on-eba", "on-rheol2"])
 def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, energy, monkeypatch):
     """BASELINE config 4 geometry through the whole-step bindings: operator assembly (Rsphere get_elt_k / get_elt_g / get_elt_f) and the
     Stokes solve on the device; in the second variant also the SUPG energy step with the Rsphere branches of pg_shape_fn /
@@ -280,6 +280,8 @@ def test_regional_sphere_stokes_assembled_and_solved_on_device(tdepv, energy, mo
     # "on-eba": BASELINE config 4 proper, the extended-Boussinesq terms of the shipped input1 (adiabatic + viscous heating, computed by
     # the reference's host process_heating and uploaded before each device energy step)
     eba = dict(adi_heating=1, visc_heating=1, surf_temp=0.078947) if tdepv == "on-eba" else {}
+    if tdepv == "on-rheol2":        # a depth-dependent law: the depth coordinate is r (E->SX[3]) on the sphere
+        eba = dict(rheol=2, viscE="3.0,3.0,3.0,3.0", viscT="0.5,0.5,0.5,0.5", viscZ="1.0,1.0,1.0,1.0")
     txt = inputfile.input1_rsphere(levels=3, maxstep=5, accuracy=1e-5, TDEPV=tdepv.split("-")[0], VISC_UPDATE="on", update_every_steps=1,
                                    storage_spacing=1, perturbmag=0.05, **eba)
     nsteps = 4
