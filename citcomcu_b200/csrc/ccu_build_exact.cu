@@ -1972,9 +1972,6 @@ int ccu_set_spherical_coordinates(ccu_ctx *c, int lev, const float *S1, const fl
     c->rsphere = true;
     return 0;
 }
-// the entry points that only know the Cartesian element routines
-#define CART_ONLY(c, what) do { if((c)->rsphere) FAIL(what ": Cartesian geometry only on the device (regional-spherical runs keep the reference's host routine)"); } while(0)
-
 int ccu_build_geometry(ccu_ctx *c)
 {
     if(!c) FAIL("null context");
@@ -2779,7 +2776,7 @@ int ccu_get_heating_latent(ccu_ctx *c, float *heating_latent_out)
 // ================================================================= get_stress / get_STD_topo (Topo_gravity.c:352-562, 307-335)
 // per element: S = sum_gp pre * strain rate / area - P (diagonal), pre = EVI * gDA, float arithmetic as the reference
 __global__ void __launch_bounds__(64) st_element(const CcuGeom g, const float *__restrict__ XX, const float *__restrict__ EVI, const float *__restrict__ V,
-                                                 const double *__restrict__ P, float *S6)
+                                                 const double *__restrict__ P, float *S6, const int sph)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= g.nel) return;
@@ -2798,6 +2795,25 @@ __global__ void __launch_bounds__(64) st_element(const CcuGeom g, const float *_
         const float gda = (float)gp_geom(X, c_sh.Nxv + i, 64, 8, gnx);
         const float pre = EVI[(size_t)e * 8 + i] * gda;
         float Vzz = 0.f, Vxx = 0.f, Vyy = 0.f, Vxy = 0.f, Vxz = 0.f, Vzy = 0.f;
+        if(sph)
+        {   // Rsphere branch (Topo_gravity.c:429-439): x, y, z stand for theta, phi, r; gNX holds d/dtheta, d/dphi, d/dr
+            double x[3], th, ph, ri;
+            sph_point(X, c_sh.Nv + i, 8, x);
+            sph_rotate_gnx(x, gnx);
+            sph_rtf(x, th, ph, ri);
+            const double ct = cos(th), sn = sin(th);
+            for(int j = 0; j < 8; j++)
+            {
+                const double N = c_sh.Nv[8 * j + i];
+                Vzz += VZ[j] * gnx[2][j];
+                Vxx = (float)((double)Vxx + ((double)(VX[j] * gnx[0][j]) + VZ[j] * N) * ri);
+                Vxz = (float)((double)Vxz + ((double)(VX[j] * gnx[2][j]) + ri * ((double)(VZ[j] * gnx[0][j]) - VX[j] * N)));
+                Vyy = (float)((double)Vyy + (((double)(VY[j] * gnx[1][j]) + VX[j] * N * ct) / sn + VZ[j] * N) * ri);
+                Vxy = (float)((double)Vxy + (((double)(VX[j] * gnx[1][j]) - VY[j] * N * ct) / sn + (double)(VY[j] * gnx[0][j])) * ri);
+                Vzy = (float)((double)Vzy + ((double)(VY[j] * gnx[2][j]) + ri * ((double)(VZ[j] * gnx[1][j]) / sn - VY[j] * N)));
+            }
+        }
+        else
         for(int j = 0; j < 8; j++)
         {
             Vzz += VZ[j] * gnx[2][j];
@@ -2860,7 +2876,6 @@ __global__ void __launch_bounds__(128) st_topo(const CcuGeom g, const float *__r
 int ccu_get_stress_topo(ccu_ctx *c, float *S_out, float *tpg_out, float *tpgb_out)
 {
     if(!c) FAIL("null context");
-    CART_ONLY(c, "get_stress / get_STD_topo");
     if(ensure_energy(c)) return 1;
     Level &L = c->L[c->cfg.levmax];
     auto &E = c->en;
@@ -2870,7 +2885,7 @@ int ccu_get_stress_topo(ccu_ctx *c, float *S_out, float *tpg_out, float *tpgb_ou
     const size_t nel = (size_t)L.g.nel, nno = (size_t)L.g.nno, nsf = (size_t)L.g.nox * L.g.noy;
     float *Se = nullptr, *Sn = nullptr, *tp = nullptr;
     CK(cudaMalloc(&Se, sizeof(float) * 6 * nel)); CK(cudaMalloc(&Sn, sizeof(float) * 6 * nno)); CK(cudaMalloc(&tp, sizeof(float) * 2 * nsf));
-    LAUNCH(c, st_element, cdiv(nel, 64), 64, L.g, (const float *)L.XX, (const float *)L.EVI, (const float *)E.V, (const double *)c->P, Se);
+    LAUNCH(c, st_element, cdiv(nel, 64), 64, L.g, (const float *)L.XX, (const float *)L.EVI, (const float *)E.V, (const double *)c->P, Se, c->rsphere ? 1 : 0);
     int rc = 0;
     if(!c->multi()) LAUNCH(c, st_nodal, cdiv(nno, 128), 128, L.g, (const float *)L.TWW, (const float *)L.MASS, (const float *)Se, Sn);
     else

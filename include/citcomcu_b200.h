@@ -127,7 +127,7 @@ int ccu_set_coordinates(ccu_ctx *ctx, int lev, const float *X1, const float *X2,
  * of get_elt_k (Element_calculations.c:249-260), get_elt_g (:896-920), get_elt_f (:1072-1086) and mass_matrix's ECO.size
  * (Size_does_matter.c:661-680), of the SUPG residual, of strain_rate_2_inv in ccu_process_heating and of the marker position update.
  * ccu_thermal_buoyancy and ccu_averages integrate their layer averages over the spherical shells, ccu_heat_flux takes the radial
- * derivative, ccu_phase_change reads r as the depth.  ccu_get_stress_topo stays Cartesian-only. */
+ * derivative, ccu_phase_change reads r as the depth, ccu_get_stress_topo uses the Rsphere strain rates of get_stress. */
 int ccu_set_spherical_coordinates(ccu_ctx *ctx, int lev, const float *theta, const float *phi, const float *r);
 /* mass_matrix (Size_does_matter.c:618): TWW, MASS, ECO.size; construct_elt_gs / get_elt_g (Element_calculations.c:831): elt_del; all levels */
 int ccu_build_geometry(ccu_ctx *ctx);

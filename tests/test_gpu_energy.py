@@ -272,7 +272,8 @@ def test_observables_on_a_developed_state():
     assert abs(seen[-1][0] - seen[0][0]) > 1.0 and abs(seen[-1][1] - seen[0][1]) > 0.1 * seen[0][1]
 
 
-def test_stress_and_dynamic_topography():
+@pytest.mark.parametrize("geometry", ["cart3d", "Rsphere"])
+def test_stress_and_dynamic_topography(geometry):
     """get_stress / get_STD_topo (Topo_gravity.c:352,307) on the reference's state after a Stokes solve: the six nodal stress
     fields and the top / bottom dynamic topography within 1e-4 of the reference's own functions (float sums)."""
     import tempfile
@@ -281,11 +282,18 @@ def test_stress_and_dynamic_topography():
     from citcomcu_b200.stokes import context_from_problem
     if not po.have_ref():
         pytest.skip("needs the prebuilt reference (oracle/_ref)")
-    txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=2, accuracy=1e-5, viscE="4.6,4.6,4.6,4.6")
-    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_stress_"), nsteps=0, kat=True)[0][0]      # the known answers are taken on the step-0 state
-    prob = CartesianProblem(txt)
-    ctx = context_from_problem(prob)
-    lm = prob.levmax
+    if geometry == "Rsphere":          # the Rsphere branch of get_stress (Topo_gravity.c:429-439)
+        from test_gpu_build import build_ctx
+        txt = inputfile.input1_rsphere(levels=3, maxstep=2, accuracy=1e-5, TDEPV="on", perturbmag=0.05)
+        d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_stress_"), nsteps=0, kat=True)[0][0]
+        ctx = build_ctx(d, 0, 0.0)
+        lm = d.levmax
+    else:
+        txt = inputfile.tdepv_box(16, 16, 8, 3, maxstep=2, accuracy=1e-5, viscE="4.6,4.6,4.6,4.6")
+        d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_stress_"), nsteps=0, kat=True)[0][0]      # the known answers are taken on the step-0 state
+        prob = CartesianProblem(txt)
+        ctx = context_from_problem(prob)
+        lm = prob.levmax
     ctx.set_temperature(d["s0_T"])
     ctx.set_velocity(d["s0_V1"], d["s0_V2"], d["s0_V3"])
     ctx.set_element_viscosity(lm, d["s0_EVI"])
@@ -372,9 +380,6 @@ def test_regional_sphere_heating_and_energy_step():
         nut, nub = ctx.heat_flux()
         sc = d[f"s{k}_scalars"]
         assert abs(nut - sc[2]) <= 1e-4 * abs(sc[2]) and abs(nub - sc[3]) <= 1e-4 * abs(sc[3]), (k, nut, nub, sc[2], sc[3])
-    # the entry points without an Rsphere branch refuse the context
-    with pytest.raises(Exception, match="Cartesian geometry only"):
-        ctx.get_stress_topo()
     ctx.close()
 
 
