@@ -28,7 +28,7 @@
  * Regional-spherical runs (Geometry=Rsphere): the node positions E->XX and E->SXX go up and the device uses the Rsphere branches of
  * the element routines; process_heating / thermal_buoyancy / heat_flux stay the reference's host code.
  *
- * Unsupported configurations stop the run loudly (there is no CPU fallback): Byerlee-type plastic viscosity, viscosity smoothing,
+ * Unsupported configurations stop the run loudly (there is no CPU fallback): Byerlee-type plastic viscosity,
  * anisotropic viscosity, periodic side walls, heat-flux boundary conditions.
  *
  * citcom_dropin_funcs.c (same library) binds the INNER functions of the path one by one (CCU_DROPIN_FUNCS).
@@ -80,7 +80,8 @@ void ccu_dropin_init(struct All_variables *E)
     if(E->viscosity.SDEPV && E->control.restart) die("stress-dependent viscosity with restart (strain rate of the restart velocity) is not on the device path");
     if(E->control.force_initial_stokes_iteration) die("force_initial_stokes_iteration is not on the device path");
     /* options that change the operator and that the device build does not implement: stop, never differ silently */
-    if(E->viscosity.SMOOTH) die("viscosity smoothing (VISC_SMOOTH / apply_viscosity_smoother) is not on the device path");
+    /* VISC_SMOOTH: apply_viscosity_smoother (Viscosity_structures.c:446) smooths the NODAL array E->VI only; the Gauss-point viscosity the
+       operator is built from is untouched (the reference's U, T, EVI are bitwise the same with it on and off), so nothing to do here */
     if(E->viscosity.allow_anisotropic_viscosity) die("anisotropic viscosity is not on the device path");
 #ifdef USE_GGRD
     if(E->control.ggrd.mat_control) die("ggrd material control (viscosity prefactors from grids) is not on the device path");
