@@ -644,6 +644,72 @@ __global__ void __launch_bounds__(128) bk_visc_cdepv(const CcuGeom g, const CcuV
     }
 }
 
+// visc_from_B (Viscosity_structures.c:1470-1755), regular plasticity: yield stress tau = a depth + b (capped at lambda; or (a z[m] + b) lambda /
+// tau_scale in the dimensional form), "Byerlee viscosity" tau / (2 (eII + 1e-7)) + offset, combined with the viscosity so far as a
+// harmonic sum (plasticity_trans) or a minimum.  eII: second invariant at the pressure point, 1 on the very first call of a run.
+__global__ void __launch_bounds__(64) bk_visc_bdepv(const CcuGeom g, const CcuViscParams vp, const int first, const int *__restrict__ mat,
+                                                    const float *__restrict__ XX, const float *__restrict__ depthco, const float *__restrict__ V,
+                                                    float *EVI, const int sph)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= g.nel) return;
+    const int ez = e % g.elz, ex = (e / g.elz) % g.elx, ey = e / (g.elz * g.elx);
+    float eedot = 1.0f;
+    if(!first)
+    {
+        float X[3][8], gnx[3][8], VV[3][8];
+        load_elt_coords(g, XX, ey, ex, ez, X);
+        gp_geom(X, c_sh.Nxp, 8, 1, gnx);
+        for(int a = 1; a <= 8; a++)
+        {
+            const int n = elt_node(g, ey, ex, ez, a);
+            for(int d = 0; d < 3; d++) VV[d][a - 1] = V[(size_t)d * g.nno + n];
+        }
+        float ee;
+        if(sph) ee = sph_strain2(X, VV, gnx);
+        else
+        {
+            double dudx[3][3];
+            for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) dudx[p][q] = 0.0;
+            for(int i = 0; i < 8; i++)
+                for(int p = 0; p < 3; p++)
+                    for(int q = 0; q < 3; q++) dudx[p][q] += VV[p][i] * gnx[q][i];
+            double ed[3][3];
+            for(int p = 0; p < 3; p++) for(int q = 0; q < 3; q++) ed[p][q] = 0.5 * (dudx[p][q] + dudx[q][p]);
+            ee = (float)(ed[0][0] * ed[0][0] + ed[0][1] * ed[0][1] * 2.0 + ed[1][1] * ed[1][1] + ed[1][2] * ed[1][2] * 2.0 +
+                         ed[2][2] * ed[2][2] + ed[0][2] * ed[0][2] * 2.0);
+        }
+        eedot = (float)sqrt(0.5 * (double)ee);
+    }
+    const int l = mat[e] - 1;
+    float zz[8];
+    for(int a = 1; a <= 8; a++)
+    {
+        zz[a - 1] = (float)(1.0 - (double)depthco[elt_node(g, ey, ex, ez, a)]);
+        if(vp.bdepv_dimensional) zz[a - 1] *= vp.bdepv_ndz_to_m;
+    }
+    for(int jj = 0; jj < 8; jj++)
+    {
+        float zzz = 0.0f;
+        for(int kk = 0; kk < 8; kk++) zzz += zz[kk] * (float)c_sh.Nv[8 * kk + jj];
+        float tau;
+        if(vp.bdepv_dimensional)
+        {
+            tau = (vp.abyerlee[l] * zzz + vp.bbyerlee[l]) * vp.lbyerlee[l];
+            tau /= vp.bdepv_tau_scale;
+        }
+        else
+        {
+            tau = vp.abyerlee[l] * zzz + vp.bbyerlee[l];
+            tau = tau < vp.lbyerlee[l] ? tau : vp.lbyerlee[l];
+        }
+        const float ettby = (float)((double)tau / (2.0 * ((double)eedot + 1e-7)) + (double)vp.bdepv_offset);
+        const size_t q = (size_t)e * 8 + jj;
+        const float eta = EVI[q];
+        EVI[q] = vp.bdepv_trans ? (float)(1.0 / (1.0 / (double)eta + 1.0 / (double)ettby)) : (eta < ettby ? eta : ettby);
+    }
+}
+
 // visc_from_gint_to_ele (Nodal_mesh.c:559-581): element mean of the eight Gauss-point values (double sum)
 __global__ void __launch_bounds__(128) bk_gint_to_ele(const int nel, const float *__restrict__ EVI, float *VN)
 {
@@ -2014,6 +2080,22 @@ int ccu_set_viscosity_law(ccu_ctx *c, int tdepv, int rheol, int num_mat, const f
     return 0;
 }
 
+// E->viscosity.{BDEPV, abyerlee, bbyerlee, lbyerlee, plasticity_dimensional, plasticity_trans, plasticity_viscosity_offset},
+// E->monitor.{length_scale, tau_scale} (Viscosity_structures.c:69-99, 186-200): the regular branch of visc_from_B.  Iterated with the
+// velocity like SDEPV (need_to_iterate), with the same misfit / damping / iteration cap (ccu_set_sdepv carries those; on = 0 there is fine).
+int ccu_set_bdepv(ccu_ctx *c, int on, const float *abyerlee, const float *bbyerlee, const float *lbyerlee, int dimensional, float length_scale,
+                  float tau_scale, int plasticity_trans, float viscosity_offset)
+{
+    if(!c) FAIL("null context");
+    CcuViscParams &v = c->visc;
+    v.bdepv = on != 0; v.bdepv_visits = 0;
+    if(!on) return 0;
+    if(!abyerlee || !bbyerlee || !lbyerlee) FAIL("set_bdepv: yield-stress parameters missing");
+    for(int i = 0; i < v.num_mat && i < 40; i++) { v.abyerlee[i] = abyerlee[i]; v.bbyerlee[i] = bbyerlee[i]; v.lbyerlee[i] = lbyerlee[i]; }
+    v.bdepv_dimensional = dimensional != 0; v.bdepv_ndz_to_m = length_scale; v.bdepv_tau_scale = tau_scale;
+    v.bdepv_trans = plasticity_trans != 0; v.bdepv_offset = viscosity_offset;
+    return 0;
+}
 // E->viscosity.{CDEPV, layer_pre_comp, pre_comp, cdepv_absolute}, E->control.check_c_irange (Viscosity_structures.c:178-281): pre_comp holds
 // 2 * num_mat values with layer_pre_comp, else 2.  The flavour / lithosphere / crust variants of visc_from_C are not implemented.
 int ccu_set_cdepv(ccu_ctx *c, int on, int layer_pre_comp, const float *pre_comp, int absolute, int check_c_irange)
@@ -2107,20 +2189,17 @@ int ccu_get_system_viscosity(ccu_ctx *c)
     if(!c->mat) FAIL("get_system_viscosity: material groups missing");
     Level &L = c->L[c->cfg.levmax];
     if(c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4) && !L.have_xx) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
-    const bool sd = c->visc.sdepv != 0, cd = c->visc.cdepv != 0;
+    const bool sd = c->visc.sdepv != 0, cd = c->visc.cdepv != 0, bd = c->visc.bdepv != 0;
+    const bool post = sd || cd || bd;                  // anything between the temperature law and the min / max clip
     const float *Ccomp = c->mk.ready ? (const float *)c->mk.C : (const float *)c->Cnode;
     if(cd && !Ccomp) FAIL("get_system_viscosity: composition-dependent viscosity needs the nodal composition (device markers or ccu_set_composition)");
-    // the depth coordinate of laws 2 and 4: z of the box, r of the regional sphere (Xtmp = E->SX, Viscosity_structures.c:525-530)
+    // the depth coordinate of laws 2 and 4 and of the yield stress: z of the box, r of the regional sphere (Xtmp = E->SX, Viscosity_structures.c:525-530)
     const float *zco = c->rsphere ? (L.SXX ? L.SXX + 2 * (size_t)L.g.nno : (const float *)nullptr) : (L.XX ? L.XX + 2 * (size_t)L.g.nno : (const float *)nullptr);
-    if(c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4) && !zco) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
-    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, zco, L.EVI, (sd || cd) ? 0 : 1);
-    if(cd && !sd)
-    {   // temperature law, composition factor, then the min / max clip (Viscosity_structures.c:386-425)
-        LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);
-        LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);
-    }
+    if(((c->visc.tdepv && (c->visc.rheol == 2 || c->visc.rheol == 4)) || bd) && !zco) FAIL("get_system_viscosity: depth-dependent law needs the node coordinates");
+    // get_system_viscosity's order (Viscosity_structures.c:386-425): temperature law, stress, composition, plastic yielding, then the clip
+    LAUNCH(c, bk_visc, cdiv(L.g.nel, 128), 128, L.g, c->visc, c->mat, c->T, zco, L.EVI, post ? 0 : 1);
     if(sd)
-    {   // get_system_viscosity's order (Viscosity_structures.c:386-425): temperature law, stress dependence, then the min / max clip
+    {
         CcuViscParams &v = c->visc;
         const int first = v.sdepv_visits == 0;                     // a run that did not restart: unit strain rate on the first call
         if(!first && !c->en.have_v) FAIL("get_system_viscosity: stress-dependent viscosity needs the velocity of the last solve (ccu_v_from_vector)");
@@ -2129,9 +2208,19 @@ int ccu_get_system_viscosity(ccu_ctx *c)
             LAUNCH(c, bk_visc_sdepv, cdiv(L.g.nel, 64), 64, L.g, c->visc, first, (const int *)c->mat, (const float *)L.XX, (const float *)c->en.V, (const float *)c->T,
                    Ccomp, L.EVI, c->rsphere ? 1 : 0);
         v.sdepv_visits++;
-        if(cd) LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);
-        LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);
     }
+    if(cd) LAUNCH(c, bk_visc_cdepv, cdiv(L.g.nel, 128), 128, L.g, c->visc, (const int *)c->mat, Ccomp, L.EVI);
+    if(bd)
+    {
+        CcuViscParams &v = c->visc;
+        const int first = v.bdepv_visits == 0;
+        if(!first && !c->en.have_v) FAIL("get_system_viscosity: plastic yielding needs the velocity of the last solve (ccu_v_from_vector)");
+        if(!L.have_xx) FAIL("get_system_viscosity: coordinates missing");
+        LAUNCH(c, bk_visc_bdepv, cdiv(L.g.nel, 64), 64, L.g, c->visc, first, (const int *)c->mat, (const float *)L.XX, zco, (const float *)c->en.V, L.EVI,
+               c->rsphere ? 1 : 0);
+        v.bdepv_visits++;
+    }
+    if(post) LAUNCH(c, bk_visc_clip, cdiv(8 * (size_t)L.g.nel, 256), 256, 8 * (size_t)L.g.nel, c->visc, L.EVI);
     CK(cudaGetLastError());
     L.have_evi = true;
     return 0;

@@ -26,6 +26,9 @@ struct CcuViscParams
     // composition-dependent viscosity (visc_from_C, Viscosity_structures.c:1784-1935; the plain prefactor mode and cdepv_absolute)
     int cdepv = 0, cdepv_layer = 0, cdepv_absolute = 0, cdepv_check_range = 0;
     double cdepv_logv[80] = { 0 };     // log(pre_comp[2 l]), log(pre_comp[2 l + 1]) per material layer (or one pair)
+    // Byerlee-type plastic yielding (visc_from_B, Viscosity_structures.c:1470-1755, the regular branch without flavours / strain weakening)
+    int bdepv = 0, bdepv_dimensional = 0, bdepv_trans = 0, bdepv_visits = 0;
+    float abyerlee[40] = { 0 }, bbyerlee[40] = { 0 }, lbyerlee[40] = { 0 }, bdepv_offset = 0, bdepv_ndz_to_m = 1, bdepv_tau_scale = 1;
 };
 
 struct Level

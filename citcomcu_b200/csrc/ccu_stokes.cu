@@ -1220,7 +1220,7 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     if(rebuild)
     {
         CcuProfScope ps(c, CCU_PROF_BUILD, true);
-        if(c->visc.tdepv || c->visc.sdepv || !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
+        if(c->visc.tdepv || c->visc.sdepv || c->visc.cdepv || c->visc.bdepv || !L.have_evi) { if(ccu_get_system_viscosity(c)) return 1; }
         if(ccu_construct_stiffness_B_matrix(c, augmented_Lagr, augmented, precondition)) return 1;
     }
     if(!L.have_K || !L.have_flags || !L.have_p) FAIL("general_stokes_solver: operator not built");
@@ -1239,9 +1239,9 @@ int ccu_general_stokes_solver(ccu_ctx *c, const float *T, const float *buoyancy,
     else d_strip(c, L, L.vec[CCU_VEC_U]);       // the same with zero imposed velocities
     int steps = c->cfg.p_iterations;
     if(d_solve_Ahat_p_fhat(c, c->cfg.accuracy, &steps, residual_out, nullptr)) return 1;
-    if(c->visc.sdepv)
+    if(c->visc.sdepv || c->visc.bdepv)      // need_to_iterate (Drive_solvers.c)
     {   // E->V of the solve just done (solve_constrained_flow_iterative ends with v_from_vector, before any damping): what the next
-        // visc_from_S call reads
+        // visc_from_S / visc_from_B call reads
         if(ccu_v_from_vector(c, nullptr)) return 1;
         // stress-dependent viscosity: viscosity <-> velocity iteration (Drive_solvers.c:120-159) with the damping of :137-141
         if(!c->sdepv_oldU)

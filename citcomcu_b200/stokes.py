@@ -190,6 +190,12 @@ class StokesContext:
         assert Cn.size == self.nno(self.levmax)
         check(self.lib.ccu_set_composition(self._ctx, Cn.ctypes.data_as(C.c_void_p)))
 
+    def set_bdepv(self, on, abyerlee, bbyerlee, lbyerlee, dimensional=0, length_scale=1.0, tau_scale=1.0, plasticity_trans=1, viscosity_offset=0.0):
+        """visc_from_B, regular branch: yield stress a depth + b (capped at l), or (a z[m] + b) l / tau_scale when dimensional."""
+        a, b, l = [np.ascontiguousarray(v, dtype=np.float32) for v in (abyerlee, bbyerlee, lbyerlee)]
+        check(self.lib.ccu_set_bdepv(self._ctx, int(on), a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), l.ctypes.data_as(C.c_void_p),
+                                     int(dimensional), C.c_float(length_scale), C.c_float(tau_scale), int(plasticity_trans), C.c_float(viscosity_offset)))
+
     def sdepv_iterations(self):
         n, m = C.c_int(0), C.c_double(0.0)
         check(self.lib.ccu_get_sdepv_iterations(self._ctx, C.byref(n), C.byref(m)))

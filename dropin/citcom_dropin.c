@@ -28,7 +28,7 @@
  * Regional-spherical runs (Geometry=Rsphere): the node positions E->XX and E->SXX go up and the device uses the Rsphere branches of
  * the element routines; process_heating / thermal_buoyancy / heat_flux stay the reference's host code.
  *
- * Unsupported configurations stop the run loudly (there is no CPU fallback): Byerlee-type plastic viscosity,
+ * Unsupported configurations stop the run loudly (there is no CPU fallback): the selective / strain-weakening variants of plastic yielding,
  * anisotropic viscosity, periodic side walls, heat-flux boundary conditions.
  *
  * citcom_dropin_funcs.c (same library) binds the INNER functions of the path one by one (CCU_DROPIN_FUNCS).
@@ -72,7 +72,10 @@ void ccu_dropin_init(struct All_variables *E)
         const char *sw = getenv("CCU_DROPIN_STOKES");
         g_ccu_device_geometry = (g_ccu_cartesian || !(sw && atoi(sw) == 0)) ? 1 : 0;
     }
-    if(E->viscosity.BDEPV) die("Byerlee-type plastic viscosity (BDEPV) is not on the device path");
+    if(E->viscosity.BDEPV && (E->viscosity.psrw || E->viscosity.pdepv_for_flavor || E->viscosity.pdepv_for_zero_comp ||
+                              E->viscosity.pdepv_for_unity_comp || E->viscosity.strain_dep_plasticity))
+        die("plastic yielding (BDEPV): the strain-rate-weakening, flavour / composition-selective and strain-dependent variants of visc_from_B are not on the device path");
+    if(E->viscosity.BDEPV && E->control.restart) die("plastic yielding with restart (strain rate of the restart velocity) is not on the device path");
     if(E->viscosity.CDEPV && (E->viscosity.cdepv_for_flavor || E->viscosity.const_lith_visc || E->viscosity.crust_option == 2))
         die("composition-dependent viscosity: the flavour / crust / constant-lithosphere variants of visc_from_C are not on the device path");
     if(E->viscosity.SDEPV && E->viscosity.sdepv_rheology != 1 && E->viscosity.sdepv_rheology != 2)
@@ -139,6 +142,13 @@ void ccu_dropin_init(struct All_variables *E)
     }
     if(E->viscosity.CDEPV)
         CCU(ccu_set_cdepv(g_ctx, 1, E->viscosity.layer_pre_comp, E->viscosity.pre_comp, E->viscosity.cdepv_absolute, E->control.check_c_irange));
+    if(E->viscosity.BDEPV)
+    {
+        CCU(ccu_set_bdepv(g_ctx, 1, E->viscosity.abyerlee, E->viscosity.bbyerlee, E->viscosity.lbyerlee, E->viscosity.plasticity_dimensional,
+                          E->monitor.length_scale, E->monitor.tau_scale, E->viscosity.plasticity_trans, E->viscosity.plasticity_viscosity_offset));
+        if(!E->viscosity.SDEPV)     /* the iteration controls are shared with SDEPV (Drive_solvers.c:157-159) */
+            CCU(ccu_set_sdepv(g_ctx, 0, 1, NULL, NULL, E->viscosity.sdepv_misfit, E->viscosity.sdepv_iter_damp, E->monitor.max_sdep_visc_iter, 0, 0.0f, 0.0f));
+    }
     if(E->viscosity.SDEPV)
         CCU(ccu_set_sdepv(g_ctx, 1, E->viscosity.sdepv_rheology, E->viscosity.sdepv_expt, E->viscosity.sdepv_trns, E->viscosity.sdepv_misfit,
                           E->viscosity.sdepv_iter_damp, E->monitor.max_sdep_visc_iter, E->viscosity.sdepv_start_from_newtonian,
@@ -181,7 +191,7 @@ void general_stokes_solver(struct All_variables *E)
     if(rebuild) CCU(ccu_get_level_array(g_ctx, lm, CCU_ARR_EVI, E->EVI[lm] + 1));
     v_from_vector(E, E->V, E->U);
     E->monitor.visc_iter_count = 1;
-    if(E->viscosity.SDEPV) { double mis; CCU(ccu_get_sdepv_iterations(g_ctx, &E->monitor.visc_iter_count, &mis)); }
+    if(E->viscosity.SDEPV || E->viscosity.BDEPV) { double mis; CCU(ccu_get_sdepv_iterations(g_ctx, &E->monitor.visc_iter_count, &mis)); }
     g_calls++;
     if(E->control.print_convergence && E->parallel.me == 0)
     {

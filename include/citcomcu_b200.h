@@ -144,6 +144,12 @@ int ccu_set_sdepv(ccu_ctx *ctx, int on, int rheology, const float *expt, const f
  * E->viscosity.{CDEPV, layer_pre_comp, pre_comp[2 or 2*num_mat], cdepv_absolute}, E->control.check_c_irange.  The composition is the
  * device marker set's nodal C when one lives on the device, else what ccu_set_composition handed in (E->C+1). */
 int ccu_set_cdepv(ccu_ctx *ctx, int on, int layer_pre_comp, const float *pre_comp, int absolute, int check_c_irange);
+/* Byerlee-type plastic yielding, visc_from_B (Viscosity_structures.c:1470-1755), regular branch: E->viscosity.{abyerlee, bbyerlee, lbyerlee}
+ * [num_mat], plasticity_dimensional with E->monitor.{length_scale, tau_scale}, plasticity_trans, plasticity_viscosity_offset.  The
+ * viscosity <-> velocity iteration of general_stokes_solver runs for it as for SDEPV; misfit, damping and iteration cap come from ccu_set_sdepv
+ * (call it with on = 0 when only BDEPV is active). */
+int ccu_set_bdepv(ccu_ctx *ctx, int on, const float *abyerlee, const float *bbyerlee, const float *lbyerlee, int dimensional, float length_scale,
+                  float tau_scale, int plasticity_trans, float viscosity_offset);
 int ccu_set_composition(ccu_ctx *ctx, const float *C /*[nno]*/);
 /* iterations and relative velocity change of the last stress-dependent-viscosity loop (E->monitor.visc_iter_count) */
 int ccu_get_sdepv_iterations(ccu_ctx *ctx, int *count_out, double *misfit_out);

@@ -385,3 +385,29 @@ def test_composition_dependent_viscosity(opts, monkeypatch):
         U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
         assert np.linalg.norm(Ug - U) <= 50 * acc * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
         assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+
+
+@pytest.mark.parametrize("trans", ["on", "off"])
+def test_plastic_yielding_loop(trans, monkeypatch):
+    """BDEPV: visc_from_B (Viscosity_structures.c:1470-1755, regular branch: yield stress a depth + b, harmonic or minimum combination with the
+    viscosity so far) and the viscosity <-> velocity iteration it shares with SDEPV, on the device inside the reference's own time loop."""
+    if not po.have_ref() or not DROPIN.exists():
+        pytest.skip("needs the prebuilt reference (oracle/_ref) and dropin/libcitcomcu_dropin.so")
+    four = lambda v: ",".join([v] * 4)      # noqa: E731
+    base = dict(maxstep=3, accuracy=1e-6, viscE=four("4.6"), storage_spacing=1, sdepv_misfit=1e-3)
+    txt = inputfile.tdepv_box(16, 16, 8, 3, BDEPV="on", plasticity_dimensional="off", abyerlee=four("1e5"), bbyerlee=four("2e4"), lbyerlee=four("1e20"),
+                              plasticity_trans=trans, plasticity_viscosity_offset=1e-2, **base)
+    nsteps = 2
+    ref, _ = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_bdref_"), nsteps=nsteps)
+    monkeypatch.setenv("CCU_DROPIN_ENERGY", "1")
+    gpu, err = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_bdgpu_"), nsteps=nsteps, preload=str(DROPIN))
+    assert "Stokes solve on CUDA device" in err
+    r, g = ref[0], gpu[0]
+    for k in range(nsteps + 1):
+        U, Ug = r[f"s{k}_U"], g[f"s{k}_U"]
+        # both arms stop the outer iteration at a relative velocity change of sdepv_misfit = 1e-3
+        assert np.linalg.norm(Ug - U) < 5e-3 * np.linalg.norm(U), (k, np.linalg.norm(Ug - U) / np.linalg.norm(U))
+        assert np.allclose(g[f"s{k}_EVI"], r[f"s{k}_EVI"], rtol=2e-2), k
+        assert np.abs(g[f"s{k}_T"] - r[f"s{k}_T"]).max() < 1e-3, k
+    plain = po.run_harness(inputfile.tdepv_box(16, 16, 8, 3, **base), tempfile.mkdtemp(prefix="ccu_bd0_"), nsteps=0)[0][0]
+    assert (r["s1_EVI"] / plain["s0_EVI"]).min() < 0.2                  # the material did yield (from the second solve on: the first call sees unit strain rate)
