@@ -64,13 +64,14 @@ def _ivec(s):
 class CartesianProblem:
     """One rank's view of a cart3d input file.  `me_loc` = (x, y, z) position in the processor grid;
     rank = z + nprocz*x + nprocz*nprocx*y (Parallel_related.c:108-121)."""
+    GEOMETRY = "cart3d"
 
     def __init__(self, text: str, me_loc=(0, 0, 0)):
         self.text = text
         p = self.params = parse_input(text)
         g = lambda k, d=None: p.get(k, d)  # noqa: E731
-        if g("Geometry", "cart3d") != "cart3d":
-            raise ValueError("CartesianProblem: only Geometry=cart3d")
+        if g("Geometry", "cart3d") != self.GEOMETRY:
+            raise ValueError(f"{type(self).__name__}: Geometry={self.GEOMETRY} expected")
         self.nproc = (int(g("nprocx", 1)), int(g("nprocy", 1)), int(g("nprocz", 1)))
         self.me_loc = tuple(me_loc)
         self.levels = int(g("levels"))
@@ -326,7 +327,7 @@ class CartesianProblem:
         """The same input file seen by a single rank owning the whole mesh."""
         if self.nproc == (1, 1, 1):
             return self
-        return CartesianProblem(self.text + "nprocx=1\nnprocy=1\nnprocz=1\n")
+        return type(self)(self.text + "nprocx=1\nnprocy=1\nnprocz=1\n")
 
     def local_slice(self, field, lev=None, per_node=1):
         """This subdomain's part (duplicated faces included) of a nodal field given on the global mesh."""
@@ -342,3 +343,63 @@ class CartesianProblem:
         a = np.asarray(field).reshape(self.NOY[lev] - 1, self.NOX[lev] - 1, self.NOZ[lev] - 1, per_elt)
         i0, j0, k0 = self.NYS[lev] - 1, self.NXS[lev] - 1, self.NZS[lev] - 1
         return np.ascontiguousarray(a[i0:i0 + noy - 1, j0:j0 + nox - 1, k0:k0 + noz - 1]).reshape(-1)
+
+
+class SphericalProblem(CartesianProblem):
+    """One rank's view of a Geometry=Rsphere input file (regional spherical block, BASELINE config 4): mesh and boundary flags.
+    Directions 1, 2, 3 are colatitude, longitude (degrees in the file) and radius; `spherical_coordinates` returns E->SXX
+    (theta, phi in radians, r), `coordinates` the Cartesian node positions E->XX the element routines integrate on
+    (Nodal_mesh.c:87-96, 188-203).  Initial temperature, material groups and buoyancy are not mirrored: take them from the host
+    code that owns the run."""
+    GEOMETRY = "Rsphere"
+
+    def __init__(self, text: str, me_loc=(0, 0, 0)):
+        super().__init__(text, me_loc)
+        g = self.params.get
+        self.corner = ((f32(float(g("theta_north"))), f32(float(g("theta_south")))), (f32(float(g("fi_west"))), f32(float(g("fi_east")))),
+                       (f32(float(g("radius_inner"))), f32(float(g("radius_outer")))))
+
+    def _axis(self, d):
+        """Global 1-D node positions in direction d (0 theta [deg], 1 phi [deg], 2 r), float accumulation as Nodal_mesh.c:87-166."""
+        p = self.params
+        lm = self.levmax
+        nnx = (self.NOX[lm], self.NOY[lm], self.NOZ[lm])[d]
+        lo, hi = self.corner[d]
+        X = np.zeros(nnx + 2, dtype=f32)
+        dx = f32(f32(hi - lo) / f32(nnx - 1))
+        X[1] = lo
+        X[nnx] = hi
+        for i in range(2, nnx):
+            X[i] = f32(X[i - 1] + dx)
+        name = "tfr"[d]
+        nl = int(p.get(f"{name}_grid_layers", 1))
+        zz = _fvec(p.get(name * 2, f"{lo},{hi}"), nl)
+        nz = _ivec(p.get("n" + name, f"1,{nnx}"))[:nl]
+        dxx = [f32(0)] + [f32(f32(zz[j] - zz[j - 1]) / f32(nz[j] - nz[j - 1])) for j in range(1, nl)]
+        j = 1
+        for i in range(2, nnx):
+            if j < nl and i <= nz[j]:
+                X[i] = f32(X[i - 1] + dxx[j])
+            if j < nl and i == nz[j]:
+                j += 1
+        return X[1:nnx + 1].copy()
+
+    def spherical_coordinates(self, lev):
+        """(theta, phi, r) float32[nno] = E->SXX[lev][1..3]."""
+        T, F, R = super().coordinates(lev)                       # the 1-D arrays broadcast over the block; angles still in degrees
+        rad = np.pi / 180
+        return (T.astype(np.float64) * rad).astype(f32), (F.astype(np.float64) * rad).astype(f32), R
+
+    def coordinates(self, lev):
+        """Cartesian node positions E->XX[lev] (float products of double sines / cosines of the float angles, :197-199)."""
+        t, f, r = [a.astype(np.float64) for a in self.spherical_coordinates(lev)]
+        return (r * np.sin(t) * np.cos(f)).astype(f32), (r * np.sin(t) * np.sin(f)).astype(f32), (r * np.cos(t)).astype(f32)
+
+    def initial_temperature(self):
+        raise NotImplementedError("SphericalProblem mirrors mesh and flags only")
+
+    def material(self):
+        raise NotImplementedError("SphericalProblem mirrors mesh and flags only")
+
+    def buoyancy(self, T):
+        raise NotImplementedError("SphericalProblem mirrors mesh and flags only")

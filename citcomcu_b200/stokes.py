@@ -696,6 +696,8 @@ def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, commu
     for lev in range(prob.levmin, prob.levmax + 1):
         ctx.set_node_flags(lev, prob.node_flags(lev))
         ctx.set_coordinates(lev, *prob.coordinates(lev))
+        if hasattr(prob, "spherical_coordinates"):                 # regional-spherical block: E->SXX next to the Cartesian E->XX
+            ctx.set_spherical_coordinates(lev, *prob.spherical_coordinates(lev))
     ctx.build_geometry()
     vb = prob.velocity_bcs()
     if any(np.any(v != 0) for v in vb) or getattr(prob, "force_velocity_bcs", False):
@@ -708,11 +710,16 @@ def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, commu
             for lev in range(g.levmin, g.levmax + 1):
                 g.set_node_flags(lev, gp.node_flags(lev))
                 g.set_coordinates(lev, *gp.coordinates(lev))
+                if hasattr(gp, "spherical_coordinates"):
+                    g.set_spherical_coordinates(lev, *gp.spherical_coordinates(lev))
             g.build_geometry()
     v = prob.visc
     ctx.set_viscosity_law(v["tdepv"], v["rheol"], v["N0"], v["E"], v["T"], v["Z"], v["vmin"], v["min_value"], v["vmax"],
                           v["max_value"], v["smooth_cycles"])
-    ctx.set_material(prob.material())
+    try:
+        ctx.set_material(prob.material())
+    except NotImplementedError:          # SphericalProblem: the material groups come from the host code (ctx.set_material)
+        pass
     if v.get("sdepv"):
         ctx.set_sdepv(1, v["sdepv_rheology"], v["sdepv_expt"], v["sdepv_trns"], v["sdepv_misfit"], v["sdepv_iter_damp"], v["sdepv_max_iter"],
                       v["sdepv_start_from_newtonian"], v["sdepv_trns_T"], v["sdepv_trns_c"])

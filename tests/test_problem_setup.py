@@ -51,3 +51,31 @@ def test_imposed_velocities_match_reference(oracle_built):
         m = (node & np.uint32(bit)) != 0
         assert np.array_equal(vb[m], d[nm][m]), nm
         assert np.abs(d[nm][m]).max() > 0 or nm == "VB3"
+
+
+@pytest.mark.parametrize("nproc", [(1, 1, 1), (2, 1, 2)])
+def test_regional_sphere_mesh_and_flags_match_reference(nproc, oracle_built):
+    """SphericalProblem: E->SXX (theta, phi, r), the Cartesian node positions E->XX and the boundary flags of every level and rank of a
+    regional-spherical block with refined radial boundary layers, bit for bit against the reference's own setup."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import SphericalProblem
+    if not po.have_ref():
+        pytest.skip("needs the reference build (oracle/_ref)")
+    txt = inputfile.input1_rsphere(levels=3, maxstep=1, nproc=nproc)
+    world = nproc[0] * nproc[1] * nproc[2]
+    dumps = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rssetup_"), nsteps=0, nproc=world)[0]
+    for d in dumps:
+        P = SphericalProblem(txt, me_loc=d.control()["me_loc"])
+        for lev in range(d.levmin, d.levmax + 1):
+            dm = d.dims(lev)
+            assert P.dims(lev) == (dm["nox"], dm["noy"], dm["noz"])
+            if f"L{lev}_SXX1" not in d:
+                continue
+            for A, nm in zip(P.spherical_coordinates(lev), ("SXX1", "SXX2", "SXX3")):
+                assert np.array_equal(A, d[f"L{lev}_{nm}"]), (lev, nm)
+            for A, nm in zip(P.coordinates(lev), ("XX1", "XX2", "XX3")):
+                assert np.array_equal(A, d[f"L{lev}_{nm}"]), (lev, nm)
+            mask = np.uint32(BC_MASK | (INTX | INTY | INTZ if lev == d.levmax else 0))
+            assert np.array_equal(P.node_flags(lev) & mask, d[f"L{lev}_NODE"] & mask), lev
