@@ -279,11 +279,15 @@ class CartesianProblem:
             T3[:, :, noz - 1] = self.toptbcval
         return T
 
+    def _depth_coordinate(self, lev):
+        """Xtmp[3] of construct_mat_group / visc_from_T: z of the box (r of the regional sphere in SphericalProblem)."""
+        return self.coordinates(lev)[2]
+
     def material(self):
         """construct_mat_group: layer index from the float mean of the 8 node depths."""
         lm = self.levmax
         nox, noy, noz = self.dims(lm)
-        zs = self.coordinates(lm)[2].reshape(noy, nox, noz)[0, 0, :]
+        zs = self._depth_coordinate(lm).reshape(noy, nox, noz)[0, 0, :]
         zlo, zhi = zs[:-1], zs[1:]
         # x3 = sum over local nodes 1..8 (four at the lower z, then four at the upper z), in float
         x3 = np.zeros(noz - 1, dtype=f32)
@@ -349,8 +353,7 @@ class SphericalProblem(CartesianProblem):
     """One rank's view of a Geometry=Rsphere input file (regional spherical block, BASELINE config 4): mesh and boundary flags.
     Directions 1, 2, 3 are colatitude, longitude (degrees in the file) and radius; `spherical_coordinates` returns E->SXX
     (theta, phi in radians, r), `coordinates` the Cartesian node positions E->XX the element routines integrate on
-    (Nodal_mesh.c:87-96, 188-203).  Initial temperature, material groups and buoyancy are not mirrored: take them from the host
-    code that owns the run."""
+    (Nodal_mesh.c:87-96, 188-203); initial temperature and material groups as the reference sets them up."""
     GEOMETRY = "Rsphere"
 
     def __init__(self, text: str, me_loc=(0, 0, 0)):
@@ -358,6 +361,8 @@ class SphericalProblem(CartesianProblem):
         g = self.params.get
         self.corner = ((f32(float(g("theta_north"))), f32(float(g("theta_south")))), (f32(float(g("fi_west"))), f32(float(g("fi_east")))),
                        (f32(float(g("radius_inner"))), f32(float(g("radius_outer")))))
+        # material layers by radius (Viscosity_structures.c:122-141)
+        self.zbase_layer = [f32(float(g("r_lith", 0.0))), f32(float(g("r_410", 1.0))), f32(float(g("r_lmantle", 1.0))), f32(0.55)]
 
     def _axis(self, d):
         """Global 1-D node positions in direction d (0 theta [deg], 1 phi [deg], 2 r), float accumulation as Nodal_mesh.c:87-166."""
@@ -395,11 +400,30 @@ class SphericalProblem(CartesianProblem):
         t, f, r = [a.astype(np.float64) for a in self.spherical_coordinates(lev)]
         return (r * np.sin(t) * np.cos(f)).astype(f32), (r * np.sin(t) * np.sin(f)).astype(f32), (r * np.cos(t)).astype(f32)
 
-    def initial_temperature(self):
-        raise NotImplementedError("SphericalProblem mirrors mesh and flags only")
+    def _depth_coordinate(self, lev):
+        return self.spherical_coordinates(lev)[2]
 
-    def material(self):
-        raise NotImplementedError("SphericalProblem mirrors mesh and flags only")
+    def initial_temperature(self):
+        """convection_initial_temperature, Rsphere branch (Convection.c:364-408), restart=0, then temperatures_conform_bcs."""
+        lm = self.levmax
+        t, f, r = [a.astype(np.float64) for a in self.spherical_coordinates(lm)]
+        (ti, to), (fi, fo), (ri, ro) = self.corner
+        rad, eps = np.pi / 180, 1.0e-6                               # CITCOM_TRACER_EPS_MARGIN (global_defs.h:93)
+        xg1 = (float(ti) * rad + eps, float(fi) * rad + eps)
+        xg2 = (float(to) * rad - eps, float(fo) * rad - eps)
+        beta = float(f32(ri / f32(ri - ro)))
+        T = (beta * (1.0 - 1.0 / r)).astype(f32)
+        k = float(self.perturb_k)
+        pert = float(self.perturb_mag) * np.sin(np.pi * (float(ro) - r) / float(f32(ro - ri))) * \
+            np.cos(k * np.pi * (t - xg1[0]) / (xg2[0] - xg1[0])) * np.cos(k * np.pi * (f - xg1[1]) / (xg2[1] - xg1[1]))
+        T = (T.astype(np.float64) + pert).astype(f32)
+        nox, noy, noz = self.dims(lm)
+        T3 = T.reshape(noy, nox, noz)
+        if self.me_loc[2] == 0 and self.bottbc in (1, 2):
+            T3[:, :, 0] = self.bottbcval
+        if self.me_loc[2] == self.nproc[2] - 1 and self.toptbc >= 1:
+            T3[:, :, noz - 1] = self.toptbcval
+        return T
 
     def buoyancy(self, T):
-        raise NotImplementedError("SphericalProblem mirrors mesh and flags only")
+        raise NotImplementedError("SphericalProblem: the shell averages of thermal_buoyancy live on the device (StokesContext.thermal_buoyancy)")

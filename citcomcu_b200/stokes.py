@@ -716,10 +716,7 @@ def context_from_problem(prob, device=0, unique_id=None, agglomerate=True, commu
     v = prob.visc
     ctx.set_viscosity_law(v["tdepv"], v["rheol"], v["N0"], v["E"], v["T"], v["Z"], v["vmin"], v["min_value"], v["vmax"],
                           v["max_value"], v["smooth_cycles"])
-    try:
-        ctx.set_material(prob.material())
-    except NotImplementedError:          # SphericalProblem: the material groups come from the host code (ctx.set_material)
-        pass
+    ctx.set_material(prob.material())
     if v.get("sdepv"):
         ctx.set_sdepv(1, v["sdepv_rheology"], v["sdepv_expt"], v["sdepv_trns"], v["sdepv_misfit"], v["sdepv_iter_damp"], v["sdepv_max_iter"],
                       v["sdepv_start_from_newtonian"], v["sdepv_trns_T"], v["sdepv_trns_c"])

@@ -56,7 +56,8 @@ def test_imposed_velocities_match_reference(oracle_built):
 @pytest.mark.parametrize("nproc", [(1, 1, 1), (2, 1, 2)])
 def test_regional_sphere_mesh_and_flags_match_reference(nproc, oracle_built):
     """SphericalProblem: E->SXX (theta, phi, r), the Cartesian node positions E->XX and the boundary flags of every level and rank of a
-    regional-spherical block with refined radial boundary layers, bit for bit against the reference's own setup."""
+    regional-spherical block with refined radial boundary layers, the initial temperature and the material groups, bit for bit
+    against the reference's own setup."""
     import tempfile
     from conftest import po
     from citcomcu_b200 import inputfile
@@ -79,3 +80,5 @@ def test_regional_sphere_mesh_and_flags_match_reference(nproc, oracle_built):
                 assert np.array_equal(A, d[f"L{lev}_{nm}"]), (lev, nm)
             mask = np.uint32(BC_MASK | (INTX | INTY | INTZ if lev == d.levmax else 0))
             assert np.array_equal(P.node_flags(lev) & mask, d[f"L{lev}_NODE"] & mask), lev
+        assert np.array_equal(P.initial_temperature(), d["s0_T"])
+        assert np.array_equal(P.material(), d["s0_mat"])
