@@ -189,3 +189,31 @@ def test_regional_sphere_operator_construction(tdepv):
     V, P, steps, res, hist = ctx.solve_Ahat_p_fhat(np.zeros(n), np.zeros(npno), F, ctl["accuracy"], 375)
     assert np.linalg.norm(V - d["s0_U"]) < 20 * ctl["accuracy"] * np.linalg.norm(d["s0_U"])
     ctx.close()
+
+
+def test_regional_sphere_from_the_python_mirror():
+    """A regional-spherical block driven from Python alone: SphericalProblem (mesh, flags, initial temperature, material groups) ->
+    context_from_problem -> shell-averaged thermal_buoyancy and general_stokes_solver on the device, against the reference's step 0."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import SphericalProblem
+    from citcomcu_b200.stokes import context_from_problem
+    if not po.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    txt = inputfile.input1_rsphere(levels=3, maxstep=1, accuracy=1e-6, TDEPV="on", perturbmag=0.05)
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rspy_"), nsteps=0, kat=True)[0][0]
+    prob = SphericalProblem(txt)
+    ctx = context_from_problem(prob)
+    T = prob.initial_temperature()
+    assert np.array_equal(T, d["s0_T"])
+    ctx.set_temperature(T)
+    adv = d["kat_adv_params"]
+    ctx.set_energy_params(adv[0], adv[1], adv[2], int(adv[3]), d["kat_diffusivity"], d["kat_expansivity"], adv[4])
+    b = ctx.thermal_buoyancy(float(adv[5]))
+    assert np.abs(b - d["s0_buoyancy"]).max() <= 1e-5 * np.abs(d["s0_buoyancy"]).max()
+    ctl = prob.control
+    U, P, its, res = ctx.general_stokes_solver(T, b, rebuild=1, augmented_Lagr=ctl["augmented_Lagr"], augmented=ctl["augmented"],
+                                               precondition=ctl["precondition"], guess=0)
+    assert np.linalg.norm(U - d["s0_U"]) <= 20 * ctl["accuracy"] * np.linalg.norm(d["s0_U"])
+    ctx.close()
