@@ -82,3 +82,23 @@ def test_regional_sphere_mesh_and_flags_match_reference(nproc, oracle_built):
             assert np.array_equal(P.node_flags(lev) & mask, d[f"L{lev}_NODE"] & mask), lev
         assert np.array_equal(P.initial_temperature(), d["s0_T"])
         assert np.array_equal(P.material(), d["s0_mat"])
+
+
+def test_regional_sphere_imposed_velocities_match_reference(oracle_built):
+    """E->VB of a regional-spherical block with a moving lid, where a velocity flag reads it, and the flags of that configuration."""
+    import tempfile
+    from conftest import po
+    from citcomcu_b200 import inputfile
+    from citcomcu_b200.problem import SphericalProblem, VBX, VBY, VBZ
+    if not po.have_ref():
+        pytest.skip("needs the reference build (oracle/_ref)")
+    txt = inputfile.input1_rsphere(levels=2, maxstep=1, topvbc=1, plate_velocity=40.0, topvbyval=-15.0)
+    d = po.run_harness(txt, tempfile.mkdtemp(prefix="ccu_rsvbsetup_"), nsteps=0)[0][0]
+    P = SphericalProblem(txt)
+    lm = d.levmax
+    node = d[f"L{lm}_NODE"]
+    assert np.array_equal(P.node_flags(lm) & np.uint32(BC_MASK), node & np.uint32(BC_MASK))
+    for vb, nm, bit in zip(P.velocity_bcs(), ("VB1", "VB2", "VB3"), (VBX, VBY, VBZ)):
+        m = (node & np.uint32(bit)) != 0
+        assert np.array_equal(vb[m], d[nm][m]), nm
+    assert np.abs(d["VB1"]).max() == 40.0
